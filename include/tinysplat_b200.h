@@ -1,0 +1,151 @@
+/* tinysplat_b200 — C ABI of the B200 (sm_100a) Gaussian-splatting hot path.
+ *
+ * This is the drop-in boundary underneath the five `gsplat` symbols tinysplat imports
+ * [REF tinysplat/splatting/rasterize.py:3-4; tinysplat/splatting/model_gaussian.py:14].
+ * Every entry point is `extern "C"`, takes plain device pointers + sizes + a CUDA stream,
+ * returns 0 on success or a negative ts_status, allocates nothing persistent and never
+ * throws.  The caller owns every buffer.  All pointers are DEVICE pointers unless the
+ * parameter name ends in `_host`.  All float arrays are fp32, row-major, contiguous.
+ * Pointers marked [16B] must be 16-byte aligned (any fresh torch allocation is).
+ *
+ * The reference-side binding is a ctypes stub: see INTEGRATION.md and
+ * tinysplat_b200/_lib.py.
+ */
+#ifndef TINYSPLAT_B200_H
+#define TINYSPLAT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define TS_API __declspec(dllexport)
+#else
+#define TS_API __attribute__((visibility("default")))
+#endif
+
+typedef void* ts_stream_t; /* cudaStream_t */
+
+enum ts_status {
+    TS_OK = 0,
+    TS_ERR_INVALID = -1,   /* bad argument (size, channel count, degree, null pointer) */
+    TS_ERR_ALIGN = -2,     /* a [16B] pointer is misaligned */
+    TS_ERR_CUDA = -3,      /* a CUDA runtime call or launch failed; see ts_last_error() */
+    TS_ERR_CAPACITY = -4   /* a caller-provided workspace is too small */
+};
+
+/* Library version (major*10000 + minor*100 + patch) and last CUDA error text. */
+TS_API int ts_version(void);
+TS_API const char* ts_last_error(void);
+/* Number of floats in one packed per-Gaussian raster record / gradient record. */
+TS_API int ts_rec_floats(void);
+TS_API int ts_grad_floats(void);
+/* Number of kernels this library has launched since load (for bench.py's gpu_launches). */
+TS_API int64_t ts_launch_count(void);
+
+/* ---- K1: EWA projection forward ----------------------------------------------------
+ * Replaces gsplat.project_gaussians  [REF rasterize.py:32, args marshalled at :64-73].
+ * viewmat: 3x4 (first three rows of the 4x4 world->camera matrix), projmat: 4x4 full
+ * projection (proj @ view).  Outputs: xys[N,2], depths[N], radii[N] (int32),
+ * conics[N,3], num_tiles_hit[N] (int32), cov3d[N,6].  Culled Gaussians get zeros. */
+TS_API int ts_project_fwd(int N,
+                          const float* means3d /*[16B]*/, const float* scales /*[16B]*/,
+                          float glob_scale, const float* quats /*[16B]*/,
+                          const float* viewmat, const float* projmat,
+                          float fx, float fy, float cx, float cy,
+                          int img_height, int img_width, int tiles_x, int tiles_y,
+                          float clip_thresh,
+                          float* xys /*[16B]*/, float* depths, int32_t* radii,
+                          float* conics /*[16B]*/, int32_t* num_tiles_hit,
+                          float* cov3d /*[16B]*/, ts_stream_t stream);
+
+/* ---- K6: EWA projection backward ---------------------------------------------------
+ * Backward of ts_project_fwd: consumes v_xys[N,2], v_depths[N], v_conics[N,3] (the depth
+ * cotangent is live because the reference rasterises depth as a colour
+ * [REF rasterize.py:48-51]) and produces v_means3d[N,3], v_scales[N,3], v_quats[N,4]. */
+TS_API int ts_project_bwd(int N,
+                          const float* means3d /*[16B]*/, const float* scales /*[16B]*/,
+                          float glob_scale, const float* quats /*[16B]*/,
+                          const float* viewmat, const float* projmat,
+                          float fx, float fy, float cx, float cy,
+                          int img_height, int img_width,
+                          const int32_t* radii,
+                          const float* v_xys /*[16B]*/, const float* v_depths,
+                          const float* v_conics /*[16B]*/,
+                          float* v_means3d /*[16B]*/, float* v_scales /*[16B]*/,
+                          float* v_quats /*[16B]*/, ts_stream_t stream);
+
+/* ---- K2/K7: spherical harmonics ----------------------------------------------------
+ * Replaces gsplat.sh.spherical_harmonics  [REF rasterize.py:38, args at :75-81].
+ * coeffs is [N,K,3]; the first (degree+1)^2 bases are used.  colors is [N,3].
+ * If coeffs_rest is non-null, coeffs holds only the DC band [N,1,3] and coeffs_rest the
+ * remaining [N,K-1,3] (the reference stores them as two Parameters
+ * [REF model_gaussian.py:86-87] and concatenates every step [REF rasterize.py:80]). */
+TS_API int ts_sh_fwd(int N, int degree, int K, const float* dirs /*[16B]*/,
+                     const float* coeffs /*[16B]*/, const float* coeffs_rest /*[16B] or NULL*/,
+                     float* colors /*[16B]*/, ts_stream_t stream);
+TS_API int ts_sh_bwd(int N, int degree, int K, const float* dirs /*[16B]*/,
+                     const float* v_colors /*[16B]*/,
+                     float* v_coeffs /*[16B]*/, float* v_coeffs_rest /*[16B] or NULL*/,
+                     ts_stream_t stream);
+
+/* ---- K3: tile binning + per-tile depth sort ------------------------------------------
+ * Inside gsplat.rasterize_gaussians  [REF rasterize.py:44,50: no bins are passed in, so
+ * binning happens behind the call].  Four steps; the caller reads stats_host between
+ * ts_bin_scan and ts_bin_emit to size `keys` / `ids_sorted`.
+ *
+ * ts_bin_count : packs one raster record per Gaussian (recs[N, ts_rec_floats()]) and
+ *                counts, per tile, the Gaussians whose footprint can reach a pixel of it
+ *                (tile_counts[T], zeroed by the callee).  CH = colour channels (1..4).
+ * ts_bin_scan  : exclusive scan -> tile_offsets[T+1]; stats[4] = {total M, max per-tile
+ *                count, number of tiles whose count exceeds smem_sort_cap, 0}.
+ * ts_bin_emit  : writes keys[M] = depth_bits<<32 | gaussian_id grouped by tile
+ *                (cursors[T] is scratch).
+ * ts_bin_sort  : sorts every tile's keys in place and writes ids_sorted[M] (gaussian ids,
+ *                front to back, ties by gaussian id).  big_scratch must hold
+ *                n_big_tiles * next_pow2(max_count) uint64 when n_big_tiles > 0. */
+TS_API int ts_bin_count(int N, int CH, const float* xys, const float* depths,
+                        const int32_t* radii, const float* conics, const float* opacity,
+                        const float* colors, int img_height, int img_width,
+                        int tiles_x, int tiles_y, int cull_mode,
+                        float* recs /*[16B]*/, int32_t* tile_counts, ts_stream_t stream);
+TS_API int ts_bin_scan(int num_tiles, const int32_t* tile_counts, int32_t* tile_offsets,
+                       int32_t* stats, int smem_sort_cap, ts_stream_t stream);
+TS_API int ts_bin_emit(int N, const float* depths, const int32_t* radii,
+                       const float* recs /*[16B]*/, int tiles_x, int tiles_y, int cull_mode,
+                       const int32_t* tile_offsets, int32_t* cursors, uint64_t* keys,
+                       ts_stream_t stream);
+TS_API int ts_bin_sort(int num_tiles, const int32_t* tile_offsets, uint64_t* keys,
+                       int32_t* ids_sorted, int max_count, int n_big_tiles,
+                       uint64_t* big_scratch, int32_t* big_counter, ts_stream_t stream);
+/* Largest per-tile list ts_bin_sort sorts in shared memory. */
+TS_API int ts_bin_smem_sort_cap(void);
+
+/* ---- K4/K5: alpha-blend forward / backward -----------------------------------------
+ * ts_blend_fwd: per-pixel front-to-back compositing of each tile's sorted list.
+ *   out_img[H,W,CH], final_T[H,W], n_contrib[H,W] (int32: position after the last
+ *   contributing list entry; what backward replays from).
+ * ts_blend_bwd: replays back to front; accumulates per-Gaussian packed gradients
+ *   grads[N, ts_grad_floats()] (zeroed by the callee).  v_out_alpha may be NULL.
+ * ts_blend_unpack_grads: packed -> v_xys[N,2], v_conics[N,3], v_colors[N,CH], v_opacity[N]. */
+TS_API int ts_blend_fwd(int CH, int img_height, int img_width, int tiles_x, int tiles_y,
+                        const int32_t* tile_offsets, const int32_t* ids_sorted,
+                        const float* recs /*[16B]*/, const float* background,
+                        float* out_img, float* final_T, int32_t* n_contrib,
+                        ts_stream_t stream);
+TS_API int ts_blend_bwd(int N, int CH, int img_height, int img_width, int tiles_x, int tiles_y,
+                        const int32_t* tile_offsets, const int32_t* ids_sorted,
+                        const float* recs /*[16B]*/, const float* background,
+                        const float* final_T, const int32_t* n_contrib,
+                        const float* v_out_img, const float* v_out_alpha /*or NULL*/,
+                        float* grads /*[16B]*/, ts_stream_t stream);
+TS_API int ts_blend_unpack_grads(int N, int CH, const int32_t* radii, const float* conics,
+                                 const float* grads /*[16B]*/, float* v_xys, float* v_conics,
+                                 float* v_colors, float* v_opacity, ts_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TINYSPLAT_B200_H */

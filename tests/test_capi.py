@@ -1,0 +1,102 @@
+"""CPU checks of the C-ABI boundary: the library builds, loads, exports exactly the symbols
+include/tinysplat_b200.h declares, and rejects bad arguments without touching a GPU."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "tinysplat_b200.h")
+
+
+def header_symbols():
+    text = open(HEADER).read()
+    return sorted(set(re.findall(r"TS_API\s+[\w\s\*]+?\b(ts_\w+)\s*\(", text)))
+
+
+def test_header_declares_the_expected_entry_points():
+    syms = header_symbols()
+    for must in ("ts_project_fwd", "ts_project_bwd", "ts_sh_fwd", "ts_sh_bwd", "ts_bin_count",
+                 "ts_bin_scan", "ts_bin_emit", "ts_bin_sort", "ts_blend_fwd", "ts_blend_bwd",
+                 "ts_blend_unpack_grads"):
+        assert must in syms
+
+
+def test_library_exports_every_declared_symbol(lib):
+    from tinysplat_b200 import _lib
+    declared = header_symbols()
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    # and the ctypes table binds exactly the header's set
+    assert sorted(_lib.exported_symbols()) == declared
+
+
+def test_no_torch_or_python_in_the_abi(lib):
+    from tinysplat_b200 import _lib
+    import subprocess
+    out = subprocess.run(["ldd", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "libtorch" not in out and "libpython" not in out and "libc10" not in out
+
+
+def test_version_and_record_sizes(lib):
+    assert lib.ts_version() >= 100
+    assert lib.ts_rec_floats() == 12 and lib.ts_grad_floats() == 12
+    assert lib.ts_bin_smem_sort_cap() >= 4096
+
+
+def test_invalid_arguments_are_rejected_before_any_cuda_call(lib):
+    assert lib.ts_project_fwd(-1, *([None] * 2), 1.0, *([None] * 3), 1.0, 1.0, 0.0, 0.0, 16, 16, 1, 1, 0.01,
+                              *([None] * 7)) == -1
+    assert lib.ts_sh_fwd(4, 5, 16, None, None, None, None, None) == -1       # degree > 4
+    assert lib.ts_sh_fwd(4, 3, 9, None, None, None, None, None) == -1        # K too small
+    assert lib.ts_blend_fwd(7, 16, 16, 1, 1, *([None] * 8)) == -1            # 7 channels
+    assert lib.ts_bin_scan(0, None, None, None, 1, None) == -1
+    # N == 0 is a valid no-op everywhere
+    assert lib.ts_project_bwd(0, None, None, 1.0, None, None, None, 1.0, 1.0, 0.0, 0.0, 16, 16,
+                              *([None] * 8)) == 0
+    assert lib.ts_sh_bwd(0, 3, 16, None, None, None, None, None) == 0
+
+
+def test_misaligned_pointer_is_reported(lib):
+    buf = (ctypes.c_float * 64)()
+    base = ctypes.addressof(buf)
+    base += (16 - base % 16) % 16
+    bad = ctypes.c_void_p(base + 4)
+    ok = ctypes.c_void_p(base)
+    assert lib.ts_sh_fwd(1, 0, 1, bad, ok, None, ok, None) == -2
+
+
+def test_product_fails_loudly_without_cuda():
+    import gsplat
+    from tinysplat_b200._lib import TinysplatError
+    x = torch.zeros(4, 3)
+    with pytest.raises(TinysplatError):
+        gsplat.project_gaussians(x, x, 1.0, torch.zeros(4, 4), torch.eye(4)[:3], torch.eye(4), 1., 1., 8., 8.,
+                                 16, 16, (1, 1, 1))
+    with pytest.raises(TinysplatError):
+        gsplat.sh.spherical_harmonics(0, x, torch.zeros(4, 1, 3))
+    with pytest.raises(TinysplatError):
+        gsplat.rasterize_gaussians(torch.zeros(4, 2), torch.zeros(4), torch.zeros(4, dtype=torch.int32), x,
+                                   torch.zeros(4, dtype=torch.int32), x, torch.zeros(4, 1), 16, 16, torch.zeros(3))
+
+
+def test_product_never_imports_the_oracle():
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r); import gsplat, tinysplat_b200, tinysplat_b200.rasterizer, "
+            "tinysplat_b200.parallel; assert not any(m.split('.')[0] == 'oracle' for m in sys.modules), 'oracle imported'"
+            % ROOT)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
+def test_gsplat_surface():
+    import gsplat
+    from gsplat.sh import spherical_harmonics, num_sh_bases, deg_from_sh
+    from gsplat import project_gaussians, rasterize_gaussians
+    assert [num_sh_bases(d) for d in range(5)] == [1, 4, 9, 16, 25]
+    assert [deg_from_sh(n) for n in (1, 4, 9, 16, 25)] == [0, 1, 2, 3, 4]
+    with pytest.raises(ValueError):
+        deg_from_sh(7)

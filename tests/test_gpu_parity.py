@@ -1,0 +1,333 @@
+"""GPU parity tests: the sm_100a kernels (called through the C ABI) against the CPU oracle on
+identical seeded inputs, against the committed golden vectors, and through size-independent
+properties at full size.
+
+Tolerances (fp32 path; the calibration is the fp32-oracle vs fp64-oracle gap printed by
+tests/golden/make_golden.py, <= ~6e-6 relative):
+  * per-Gaussian streaming kernels (project, SH): 1e-5 relative to the tensor's max |value|
+  * image: 2e-4 absolute on [0,1] colours (ex2.approx + reordered fp32 sums)
+  * gradients: 1e-3 relative to the tensor's max |value| (float atomics reorder the sums)
+Integer outputs (radii, tile counts) must match exactly except where a ceil/floor sits within
+one fp32 ulp of an integer; at most 0.1% of entries may differ, by at most 1."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from tinysplat_b200 import synthetic
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "config1.npz")
+DEV = "cuda:0"
+PARAMS = ["means", "scales", "quats", "opacities", "colors_dc", "colors_rest"]
+
+TOL_STREAM = 1e-5
+TOL_IMG = 2e-4
+TOL_GRAD = 1e-3
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_cuda(lib):
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+
+
+def rel_err(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return (a - b).abs().max().item() / max(b.abs().max().item(), 1e-30)
+
+
+def proj_inputs(sc, cam, W, H, dtype=torch.float32, device="cpu"):
+    V = cam.view_matrix.to(dtype).to(device)
+    P = cam.proj_matrix.to(dtype).to(device)
+    q = sc["quats"].to(dtype).to(device)
+    tb = ((W + 15) // 16, (H + 15) // 16, 1)
+    return [sc["means"].to(dtype).to(device), torch.exp(sc["scales"].to(dtype)).to(device), 1.0,
+            q / q.norm(dim=-1, keepdim=True), V[:3], P @ V, cam.f_x, cam.f_y, W / 2, H / 2, H, W, tb]
+
+
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N,W,H", [(256, 128, 128), (5000, 640, 360), (1, 16, 16), (777, 37, 21)])
+def test_project_forward_and_backward(N, W, H):
+    import gsplat
+    cam = synthetic.make_camera(W, H, yaw_deg=7.0, shift=(0.3, -0.2, 0.1))
+    sc = synthetic.make_scene(N, W, H, seed=N)
+    sc["means"][::17, 2] = -1.0          # some behind the camera
+    sc["means"][::23, 0] *= 4.0          # some far outside the frustum (exercises the fov clamp)
+    ref_in = proj_inputs(sc, cam, W, H, torch.float64)
+    for i in (0, 1, 3):
+        ref_in[i] = ref_in[i].clone().requires_grad_(True)
+    r_xys, r_dep, r_rad, r_con, r_nt, r_cov = oracle.project_gaussians(*ref_in)
+    gpu_in = proj_inputs(sc, cam, W, H, torch.float32, DEV)
+    for i in (0, 1, 3):
+        gpu_in[i] = gpu_in[i].clone().requires_grad_(True)
+    xys, dep, rad, con, nt, cov = gsplat.project_gaussians(*gpu_in)
+    assert rad.dtype == torch.int32 and nt.dtype == torch.int32
+    assert xys.shape == (N, 2) and con.shape == (N, 3) and cov.shape == (N, 6)
+    bad = (rad.cpu() != r_rad)
+    assert bad.float().mean().item() <= 1e-3 and (rad.cpu() - r_rad).abs().max().item() <= 1
+    same = ~bad & ((rad.cpu() > 0) == (r_rad > 0))
+    assert (nt.cpu()[same] != r_nt[same]).float().mean().item() <= 1e-3
+    for got, want in ((xys, r_xys), (dep, r_dep), (con, r_con), (cov, r_cov)):
+        g, w = got.cpu()[same], want[same]
+        assert rel_err(g, w) < TOL_STREAM
+    # zeros for culled Gaussians
+    culled = rad == 0
+    assert xys[culled].abs().sum() == 0 and con[culled].abs().sum() == 0 and dep[culled].abs().sum() == 0
+    # backward with random cotangents on xys, depths AND conics
+    g = torch.Generator().manual_seed(0)
+    c_xy = torch.randn(N, 2, generator=g, dtype=torch.float64)
+    c_dep = torch.randn(N, generator=g, dtype=torch.float64)
+    c_con = torch.randn(N, 3, generator=g, dtype=torch.float64)
+    keep = same.double()
+    ((r_xys * c_xy * keep[:, None]).sum() + (r_dep * c_dep * keep).sum() + (r_con * c_con * keep[:, None]).sum()).backward()
+    kd = keep.float().to(DEV)
+    ((xys * c_xy.float().to(DEV) * kd[:, None]).sum() + (dep * c_dep.float().to(DEV) * kd).sum()
+     + (con * c_con.float().to(DEV) * kd[:, None]).sum()).backward()
+    for i in (0, 1, 3):
+        assert torch.isfinite(gpu_in[i].grad).all()
+        assert rel_err(gpu_in[i].grad, ref_in[i].grad) < 1e-4, f"input {i}"
+
+
+@pytest.mark.parametrize("deg,K", [(0, 1), (1, 4), (2, 9), (3, 16), (4, 25), (1, 16), (0, 16), (2, 16)])
+def test_spherical_harmonics(deg, K):
+    import gsplat
+    from tinysplat_b200 import spherical_harmonics_split
+    N = 1000 + deg
+    g = torch.Generator().manual_seed(deg * 100 + K)
+    dirs = torch.randn(N, 3, generator=g)
+    dirs = dirs / dirs.norm(dim=-1, keepdim=True)
+    co = torch.randn(N, K, 3, generator=g)
+    cot = torch.randn(N, 3, generator=g)
+    r_co = co.double().requires_grad_(True)
+    want = oracle.spherical_harmonics(deg, dirs.double(), r_co)
+    (want * cot.double()).sum().backward()
+    g_co = co.to(DEV).requires_grad_(True)
+    got = gsplat.sh.spherical_harmonics(deg, dirs.to(DEV), g_co)
+    (got * cot.to(DEV)).sum().backward()
+    assert rel_err(got, want) < TOL_STREAM
+    assert rel_err(g_co.grad, r_co.grad) < TOL_STREAM
+    if deg < gsplat.sh.deg_from_sh(K):
+        assert g_co.grad[:, (deg + 1) ** 2:, :].abs().max() == 0
+    if K > 1:   # (dc, rest) split entry point gives the same numbers
+        dc = co[:, 0, :].contiguous().to(DEV).requires_grad_(True)
+        rest = co[:, 1:, :].contiguous().to(DEV).requires_grad_(True)
+        got2 = spherical_harmonics_split(deg, dirs.to(DEV), dc, rest)
+        (got2 * cot.to(DEV)).sum().backward()
+        assert torch.equal(got2, got)
+        assert torch.equal(dc.grad, g_co.grad[:, 0, :]) and torch.equal(rest.grad, g_co.grad[:, 1:, :])
+
+
+def _raster_case(N, W, H, seed, CH=3):
+    """Projected inputs (from the fp32 oracle, so both sides see identical fp32 values)."""
+    cam = synthetic.make_camera(W, H)
+    sc = synthetic.make_scene(N, W, H, seed=seed)
+    xys, dep, rad, con, nt, _ = oracle.project_gaussians(*proj_inputs(sc, cam, W, H, torch.float32))
+    g = torch.Generator().manual_seed(seed + 1)
+    colors = torch.rand(N, CH, generator=g)
+    opac = torch.sigmoid(sc["opacities"])
+    bg = torch.rand(CH, generator=g)
+    return xys, dep, rad, con, nt, colors, opac, bg
+
+
+@pytest.mark.parametrize("N,W,H,CH", [(256, 128, 128, 3), (3000, 320, 200, 3), (400, 50, 35, 4),
+                                      (300, 64, 64, 1), (1500, 96, 96, 2)])
+def test_rasterize_forward_and_backward(N, W, H, CH):
+    import gsplat
+    xys, dep, rad, con, nt, colors, opac, bg = _raster_case(N, W, H, seed=N + CH, CH=CH)
+    leaf = lambda t, dt, dev: t.to(dt).to(dev).clone().requires_grad_(True)
+    r = [leaf(xys, torch.float64, "cpu"), leaf(con, torch.float64, "cpu"),
+         leaf(colors, torch.float64, "cpu"), leaf(opac, torch.float64, "cpu")]
+    want, want_a, aux = oracle.rasterize_gaussians(r[0], dep.double(), rad, r[1], nt, r[2], r[3], H, W,
+                                                   bg.double(), return_aux=True)
+    c = [leaf(xys, torch.float32, DEV), leaf(con, torch.float32, DEV),
+         leaf(colors, torch.float32, DEV), leaf(opac, torch.float32, DEV)]
+    got, got_a = gsplat.rasterize_gaussians(c[0], dep.to(DEV), rad.to(DEV), c[1], nt.to(DEV), c[2], c[3],
+                                            H, W, bg.to(DEV))
+    assert got.shape == (H, W, CH) and got_a.shape == (H, W)
+    assert (got.cpu().double() - want).abs().max().item() < TOL_IMG
+    assert (got_a.cpu().double() - want_a).abs().max().item() < TOL_IMG
+    g = torch.Generator().manual_seed(7)
+    w_img = torch.rand(H, W, CH, generator=g)
+    w_a = torch.rand(H, W, generator=g)
+    ((want * w_img.double()).sum() + (want_a * w_a.double()).sum()).backward()
+    ((got * w_img.to(DEV)).sum() + (got_a * w_a.to(DEV)).sum()).backward()
+    for name, a, b in zip(("xys", "conics", "colors", "opacity"), c, r):
+        assert a.grad.shape == a.shape
+        assert torch.isfinite(a.grad).all()
+        assert rel_err(a.grad, b.grad) < TOL_GRAD, name
+
+
+def test_footprint_culling_is_result_invariant():
+    """cull_mode=1 (opacity-aware footprint culling at tile and sub-tile level) must not change
+    the image or the gradients relative to the plain 3-sigma-bbox algorithm (cull_mode=0)."""
+    import gsplat
+    from tinysplat_b200 import rasterize as rz
+    N, W, H = 4000, 256, 192
+    xys, dep, rad, con, nt, colors, opac, bg = _raster_case(N, W, H, seed=5)
+    outs = []
+    for mode in (0, 1):
+        leafs = [t.to(DEV).clone().requires_grad_(True) for t in (xys, con, colors, opac)]
+        rz.clear_bin_cache()
+        img, a = gsplat.rasterize_gaussians(leafs[0], dep.to(DEV), rad.to(DEV), leafs[1], nt.to(DEV), leafs[2],
+                                            leafs[3], H, W, bg.to(DEV), cull_mode=mode)
+        M = rz.last_stats["num_intersects"]
+        (img.sum() + a.sum()).backward()
+        outs.append((img, a, [l.grad for l in leafs], M))
+    assert outs[1][3] < outs[0][3], "culling should drop intersections"
+    assert outs[0][3] == int(nt.sum()), "cull_mode=0 must emit exactly sum(num_tiles_hit) intersections"
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    for g0, g1 in zip(outs[0][2], outs[1][2]):
+        assert rel_err(g1, g0) < 1e-5   # identical terms; only the float-atomic order differs
+
+
+def test_sorted_lists_match_oracle_order():
+    """K3 alone: with cull_mode=0 every tile's id list must equal the oracle's (tile, depth, id)
+    order exactly — integer/index work is bit-exact."""
+    from tinysplat_b200 import rasterize as rz
+    N, W, H = 3000, 200, 120
+    xys, dep, rad, con, nt, colors, opac, bg = _raster_case(N, W, H, seed=21)
+    dep[::7] = dep[0]      # depth ties: order must fall back to the gaussian id
+    tb = ((W + 15) // 16, (H + 15) // 16, 1)
+    tile, gid = oracle.gsplat_oracle.bin_and_sort(xys, dep, rad, tb)
+    edges = torch.searchsorted(tile, torch.arange(tb[0] * tb[1] + 1))
+    rz.clear_bin_cache()
+    recs, bins = rz.pack_and_bin(xys.to(DEV), dep.to(DEV), rad.to(DEV), con.to(DEV),
+                                 opac.reshape(-1).to(DEV), colors.to(DEV), H, W, cull_mode=0, reuse=False)
+    assert bins.num_intersects == gid.numel()
+    assert torch.equal(bins.tile_offsets.cpu().long(), edges)
+    assert torch.equal(bins.ids_sorted.cpu().long()[:gid.numel()], gid)
+
+
+def test_big_tile_fallback_sort():
+    """A tile list longer than the shared-memory sort capacity goes through the global-memory
+    fallback and must still be exactly sorted."""
+    from tinysplat_b200 import rasterize as rz, _lib
+    cap = _lib.load().ts_bin_smem_sort_cap()
+    N = cap + 1500
+    g = torch.Generator().manual_seed(3)
+    xys = torch.rand(N, 2, generator=g) * 14 + 1          # all inside tile (0,0)
+    dep = torch.rand(N, generator=g) + 0.5
+    rad = torch.ones(N, dtype=torch.int32)
+    con = torch.tensor([[0.5, 0.0, 0.5]]).repeat(N, 1)
+    opac = torch.full((N,), 0.5)
+    colors = torch.rand(N, 3, generator=g)
+    xys[:, :] = xys.clamp(2, 13)
+    rz.clear_bin_cache()
+    recs, bins = rz.pack_and_bin(xys.to(DEV), dep.to(DEV), rad.to(DEV), con.to(DEV), opac.to(DEV),
+                                 colors.to(DEV), 16, 16, cull_mode=0, reuse=False)
+    assert bins.num_intersects == N and bins.max_per_tile == N
+    want = torch.argsort(dep, stable=True)
+    assert torch.equal(bins.ids_sorted.cpu().long(), want)
+
+
+def test_full_adapter_matches_golden_config1():
+    """BASELINE config 1 (256 Gaussians, 128x128) through both pipelines of the adapter mirror,
+    against the committed fp64-oracle vectors."""
+    from tinysplat_b200.rasterizer import GaussianRasterizer, ParamModel
+    gold = np.load(GOLD)
+    sc = {k[3:]: torch.from_numpy(gold[k]) for k in gold.files if k.startswith("in_")}
+    cam = synthetic.make_camera(128, 128)
+    g = torch.Generator().manual_seed(1234)
+    wi = torch.rand(128, 128, 3, generator=g, dtype=torch.float64).float().to(DEV)
+    wd = torch.rand(128, 128, generator=g, dtype=torch.float64).float().to(DEV)
+    for pipeline in ("reference", "fused"):
+        model = ParamModel(sc, DEV, 3)
+        img, ex = GaussianRasterizer(model, None, DEV, pipeline)(cam, None, 3)
+        assert torch.equal(ex["radii"].cpu(), torch.from_numpy(gold["radii"]))
+        assert (img.cpu() - torch.from_numpy(gold["img"])).abs().max().item() < TOL_IMG
+        assert (ex["depth"].cpu() - torch.from_numpy(gold["depth"])).abs().max().item() < 20 * TOL_IMG
+        ((img * wi).sum() + 0.1 * (ex["depth"] * wd).sum()).backward()
+        assert rel_err(ex["xys"].grad, torch.from_numpy(gold["v_xys"])) < TOL_GRAD
+        for k in PARAMS:
+            assert rel_err(getattr(model, k).grad, torch.from_numpy(gold["v_" + k])) < TOL_GRAD, (pipeline, k)
+
+
+def test_no_grad_forward_and_retain_graph():
+    """The viewer renders under no_grad [REF tinysplat/viewer.py:90-93]; training calls
+    backward(retain_graph=True) [REF scripts/train.py:94]: a second backward must reproduce the
+    first (saved buffers are neither freed nor mutated)."""
+    from tinysplat_b200.rasterizer import GaussianRasterizer, ParamModel
+    W, H = 96, 64
+    cam = synthetic.make_camera(W, H)
+    sc = synthetic.make_scene(500, W, H, seed=4)
+    model = ParamModel(sc, DEV, 2)
+    rast = GaussianRasterizer(model, None, DEV, "reference")
+    with torch.no_grad():
+        img0, ex0 = rast(cam, (W, H), 2)
+    assert not img0.requires_grad and ex0["xys"].grad_fn is None
+    img, ex = rast(cam, (W, H), 2)
+    assert torch.equal(img, img0)
+    loss = img.sum() + ex["depth"].sum()
+    loss.backward(retain_graph=True)
+    g1 = [p.grad.clone() for p in model.parameters()]
+    xg1 = ex["xys"].grad.clone()
+    model.zero_grad()
+    ex["xys"].grad = None
+    loss.backward()
+    for a, p in zip(g1, model.parameters()):
+        assert rel_err(p.grad, a) < 1e-5
+    assert rel_err(ex["xys"].grad, xg1) < 1e-5
+    assert ex["xys"].grad.norm(dim=-1).shape == (500,)    # what update_grad_accum reads
+
+
+def test_empty_and_all_culled_scenes():
+    import gsplat
+    W, H = 40, 24
+    bg = torch.tensor([0.1, 0.6, 0.9], device=DEV)
+    z = lambda *s, dt=torch.float32: torch.zeros(*s, dtype=dt, device=DEV)
+    # N = 0
+    img, a = gsplat.rasterize_gaussians(z(0, 2), z(0), z(0, dt=torch.int32), z(0, 3), z(0, dt=torch.int32),
+                                        z(0, 3), z(0, 1), H, W, bg)
+    assert torch.equal(img, bg.expand(H, W, 3)) and a.abs().max() == 0
+    # everything behind the camera
+    cam = synthetic.make_camera(W, H)
+    sc = synthetic.make_scene(64, W, H, seed=1)
+    sc["means"][:, 2] = -2.0
+    ins = proj_inputs(sc, cam, W, H, torch.float32, DEV)
+    ins[0].requires_grad_(True)
+    xys, dep, rad, con, nt, _ = gsplat.project_gaussians(*ins)
+    assert rad.abs().sum() == 0 and nt.abs().sum() == 0
+    img, a = gsplat.rasterize_gaussians(xys, dep, rad, con, nt, z(64, 3) + 0.5, z(64, 1) + 0.5, H, W, bg)
+    assert torch.equal(img, bg.expand(H, W, 3))
+    img.sum().backward()
+    assert ins[0].grad.abs().max() == 0
+
+
+def test_full_size_properties_1080p():
+    """BASELINE-sized run (1M Gaussians, 1080p; too big for the oracle): size-independent
+    properties instead — (a) opaque background conservation: out = sum w_i c_i + T*bg, so with all
+    colours == 1 and bg == 1 every pixel is exactly 1 up to fp32 rounding; (b) alpha + T == 1;
+    (c) linearity of the image in colour; (d) determinism of forward; (e) finite gradients whose
+    colour-gradient sum equals sum of (1 - T) for a unit cotangent."""
+    import gsplat
+    from tinysplat_b200 import rasterize as rz
+    W, H, N = 1920, 1080, 1_000_000
+    cam = synthetic.make_camera(W, H)
+    sc = synthetic.make_scene(N, W, H, seed=0)
+    ins = proj_inputs(sc, cam, W, H, torch.float32, DEV)
+    xys, dep, rad, con, nt, _ = gsplat.project_gaussians(*ins)
+    opac = torch.sigmoid(sc["opacities"]).to(DEV)
+    ones = torch.ones(N, 3, device=DEV)
+    bg1 = torch.ones(3, device=DEV)
+    img, alpha = gsplat.rasterize_gaussians(xys, dep, rad, con, nt, ones, opac, H, W, bg1)
+    assert (img - 1).abs().max().item() < 1e-4
+    g = torch.Generator().manual_seed(0)
+    c1 = torch.rand(N, 3, generator=g).to(DEV).requires_grad_(True)
+    c2 = torch.rand(N, 3, generator=g).to(DEV)
+    bg0 = torch.zeros(3, device=DEV)
+    i1, a1 = gsplat.rasterize_gaussians(xys, dep, rad, con, nt, c1, opac, H, W, bg0)
+    i2, _ = gsplat.rasterize_gaussians(xys, dep, rad, con, nt, c2, opac, H, W, bg0)
+    i12, _ = gsplat.rasterize_gaussians(xys, dep, rad, con, nt, 0.5 * c1 + 2.0 * c2, opac, H, W, bg0)
+    assert (i12 - (0.5 * i1 + 2.0 * i2)).abs().max().item() < 1e-4
+    assert torch.equal(a1, alpha)
+    i1b, _ = gsplat.rasterize_gaussians(xys, dep, rad, con, nt, c1, opac, H, W, bg0)
+    assert torch.equal(i1, i1b)
+    i1.sum().backward()
+    assert torch.isfinite(c1.grad).all()
+    # d(sum img)/d c_i = sum_pixels w_i ; summed over i and channels = 3 * sum_pixels (1 - T)
+    assert abs(c1.grad.sum().item() / (3 * a1.double().sum().item()) - 1) < 1e-3
+    assert rz.last_stats["num_intersects"] > N

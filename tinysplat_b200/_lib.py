@@ -1,0 +1,108 @@
+"""ctypes binding of libtinysplat_b200.so (the C ABI declared in include/tinysplat_b200.h).
+
+There is deliberately NO fallback: if the shared library is missing or a call fails, the
+product raises.  (The CPU oracle under oracle/ is test infrastructure and is never imported
+from here.)"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtinysplat_b200.so")
+
+_p = C.c_void_p
+_i = C.c_int
+_f = C.c_float
+
+_SIGNATURES = {
+    "ts_version": ([], C.c_int),
+    "ts_last_error": ([], C.c_char_p),
+    "ts_rec_floats": ([], C.c_int),
+    "ts_grad_floats": ([], C.c_int),
+    "ts_launch_count": ([], C.c_int64),
+    "ts_project_fwd": ([_i, _p, _p, _f, _p, _p, _p, _f, _f, _f, _f, _i, _i, _i, _i, _f,
+                        _p, _p, _p, _p, _p, _p, _p], C.c_int),
+    "ts_project_bwd": ([_i, _p, _p, _f, _p, _p, _p, _f, _f, _f, _f, _i, _i,
+                        _p, _p, _p, _p, _p, _p, _p, _p], C.c_int),
+    "ts_sh_fwd": ([_i, _i, _i, _p, _p, _p, _p, _p], C.c_int),
+    "ts_sh_bwd": ([_i, _i, _i, _p, _p, _p, _p, _p], C.c_int),
+    "ts_bin_count": ([_i, _i, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p], C.c_int),
+    "ts_bin_scan": ([_i, _p, _p, _p, _i, _p], C.c_int),
+    "ts_bin_emit": ([_i, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p], C.c_int),
+    "ts_bin_sort": ([_i, _p, _p, _p, _i, _i, _p, _p, _p], C.c_int),
+    "ts_bin_smem_sort_cap": ([], C.c_int),
+    "ts_blend_fwd": ([_i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p], C.c_int),
+    "ts_blend_bwd": ([_i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p], C.c_int),
+    "ts_blend_unpack_grads": ([_i, _i, _p, _p, _p, _p, _p, _p, _p, _p], C.c_int),
+}
+
+_STATUS = {0: "TS_OK", -1: "TS_ERR_INVALID", -2: "TS_ERR_ALIGN", -3: "TS_ERR_CUDA",
+           -4: "TS_ERR_CAPACITY"}
+
+_lib: Optional[C.CDLL] = None
+
+
+class TinysplatError(RuntimeError):
+    pass
+
+
+def exported_symbols():
+    return list(_SIGNATURES)
+
+
+def load() -> C.CDLL:
+    """dlopen the in-tree library; raises loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise TinysplatError(
+            f"{LIB_PATH} is missing: build it with `python -m tinysplat_b200.build` "
+            "(or __graft_entry__.build()).  There is no CPU/PyTorch fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (argtypes, restype) in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = restype
+    _lib = lib
+    return lib
+
+
+def check(status: int, what: str) -> None:
+    if status != 0:
+        detail = load().ts_last_error().decode() if status == -3 else ""
+        raise TinysplatError(f"{what} failed: {_STATUS.get(status, status)} {detail}")
+
+
+def ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def require_cuda(*tensors: torch.Tensor) -> None:
+    for t in tensors:
+        if not t.is_cuda:
+            raise TinysplatError(
+                "tinysplat_b200 ops run only on CUDA tensors (sm_100a); got a "
+                f"{t.device} tensor.  There is no CPU fallback.")
+
+
+def f32c(t: torch.Tensor) -> torch.Tensor:
+    """fp32, contiguous, 16-byte aligned view/copy of t."""
+    if t.dtype != torch.float32:
+        t = t.float()
+    t = t.contiguous()
+    if t.data_ptr() % 16 != 0:
+        t = t.clone()
+    return t
+
+
+def launch_count() -> int:
+    return int(load().ts_launch_count())

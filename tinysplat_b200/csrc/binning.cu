@@ -1,0 +1,337 @@
+// K3 — tile binning and per-tile depth sort.
+// Happens behind gsplat.rasterize_gaussians  [REF tinysplat/splatting/rasterize.py:44,50].
+//
+// B200-first design (instead of one global 64-bit radix sort over all intersections):
+//   count  : per Gaussian, atomically count the tiles its alpha>=1/255 footprint can reach
+//            (3-sigma bbox of the stated algorithm, intersected with the opacity-aware extent:
+//            a pair that cannot light any pixel is never emitted -> smaller M, same image);
+//            the same pass packs the 48-byte raster record the blend kernels gather.
+//   scan   : exclusive scan of per-tile counts (single CTA; T <= ~130k tiles).
+//   emit   : scatter key = depth_bits<<32 | gaussian_id into the tile's bucket.
+//   sort   : one CTA per tile sorts its bucket in SHARED memory (bitonic on 64-bit keys: unique
+//            keys -> deterministic, ties in depth resolved by gaussian id exactly like a stable
+//            sort of the emission order), writes the 32-bit id list.
+// Traffic per intersection: 8 B write + 8 B read + 4 B write, vs ~150 B for 6 radix passes.
+#include "ts_common.cuh"
+
+namespace ts {
+
+constexpr int kBinThreads = 256;
+constexpr int kSortThreads = 256;
+constexpr int kSmemSortCap = 16384;  // 128 KB of 64-bit keys
+constexpr int kCoopThreshold = 8;    // rects larger than this are expanded by the whole warp
+
+// Tile rectangle [lo,hi) of a packed record: 3-sigma bbox ∩ opacity-aware footprint.
+__device__ __forceinline__ void tile_rect(float4 q0, float radius, int tbx, int tby, int cull,
+                                          int& lox, int& loy, int& hix, int& hiy) {
+    tile_bbox(q0.x, q0.y, radius, tbx, tby, lox, loy, hix, hiy);
+    if (cull) {
+        // pixel centres of tile t along x: 16t + 0.5 .. 16t + 15.5
+        float fl = ceilf((q0.x - q0.z - 15.5f) * (1.f / kBlock));
+        float fh = floorf((q0.x + q0.z - 0.5f) * (1.f / kBlock));
+        float gl = ceilf((q0.y - q0.w - 15.5f) * (1.f / kBlock));
+        float gh = floorf((q0.y + q0.w - 0.5f) * (1.f / kBlock));
+        fl = fminf(fmaxf(fl, -1.f), 1e9f); gl = fminf(fmaxf(gl, -1.f), 1e9f);
+        fh = fminf(fmaxf(fh, -2.f), 1e9f); gh = fminf(fmaxf(gh, -2.f), 1e9f);
+        lox = max(lox, (int)fl); loy = max(loy, (int)gl);
+        hix = min(hix, (int)fh + 1); hiy = min(hiy, (int)gh + 1);
+        if (hix < lox) hix = lox;
+        if (hiy < loy) hiy = loy;
+    }
+}
+
+// Run f(tile_id, payload) for every tile of every lane's rectangle.  Small rectangles are
+// walked by their own lane; large ones are expanded cooperatively by the whole warp (payload
+// broadcast from the owning lane) so that one screen-filling Gaussian does not serialise
+// thousands of atomics on a single lane.  Must be reached by all 32 lanes.
+template <typename F>
+__device__ __forceinline__ void for_each_tile(int lox, int loy, int hix, int hiy, int tbx,
+                                              uint32_t pay_lo, uint32_t pay_hi, F f) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    int w = hix - lox, h = hiy - loy;
+    int n = (w > 0 && h > 0) ? w * h : 0;
+    if (n > 0 && n <= kCoopThreshold) {
+        for (int y = loy; y < hiy; ++y)
+            for (int x = lox; x < hix; ++x) f(y * tbx + x, pay_lo, pay_hi);
+    }
+    __syncwarp(full);
+    unsigned big = __ballot_sync(full, n > kCoopThreshold);
+    while (big) {
+        int src = __ffs(big) - 1;
+        big &= big - 1;
+        int slox = __shfl_sync(full, lox, src), sloy = __shfl_sync(full, loy, src);
+        int sw = __shfl_sync(full, w, src), sn = __shfl_sync(full, n, src);
+        uint32_t plo = __shfl_sync(full, pay_lo, src), phi = __shfl_sync(full, pay_hi, src);
+        for (int k = lane; k < sn; k += 32) {
+            int y = k / sw, x = k - y * sw;
+            f((sloy + y) * tbx + slox + x, plo, phi);
+        }
+    }
+}
+
+template <int CH>
+__global__ void __launch_bounds__(kBinThreads)
+bin_count_kernel(int N, const float2* __restrict__ xys, const int32_t* __restrict__ radii,
+                 const float* __restrict__ conics, const float* __restrict__ opacity,
+                 const float* __restrict__ colors, int tbx, int tby, int cull,
+                 float4* __restrict__ recs, int32_t* __restrict__ tile_counts) {
+    const int i = blockIdx.x * kBinThreads + threadIdx.x;
+    int lox = 0, loy = 0, hix = 0, hiy = 0;
+    if (i < N) {
+        int r = __ldg(radii + i);
+        float2 xy = __ldg(xys + i);
+        float a = __ldg(conics + 3 * i), b = __ldg(conics + 3 * i + 1), c = __ldg(conics + 3 * i + 2);
+        float op = __ldg(opacity + i);
+        float hx = 1e30f, hy = 1e30f;
+        if (cull) {
+            // footprint of alpha >= 1/255:  sigma <= tau = ln(255*opac);  half extents of the
+            // ellipse's axis-aligned box are sqrt(2*tau*cov_xx), sqrt(2*tau*cov_yy), cov = conic^-1
+            float tau = __logf(255.f * op);
+            float det = a * c - b * b;
+            if (!(op * 255.f >= 1.f)) { hx = -1e30f; hy = -1e30f; }       // can never reach 1/255
+            else if (det > 0.f && a > 0.f && c > 0.f) {
+                float two_tau = 2.f * (tau + 0.01f);
+                hx = sqrtf(two_tau * c / det) * 1.001f + 0.01f;
+                hy = sqrtf(two_tau * a / det) * 1.001f + 0.01f;
+            }
+        }
+        float4 q0 = make_float4(xy.x, xy.y, hx, hy);
+        float4 q1 = make_float4(0.5f * kLog2e * a, kLog2e * b, 0.5f * kLog2e * c, op);
+        float4 q2 = make_float4(0.f, 0.f, 0.f, 0.f);
+        q2.x = __ldg(colors + (size_t)CH * i);
+        if (CH > 1) q2.y = __ldg(colors + (size_t)CH * i + 1);
+        if (CH > 2) q2.z = __ldg(colors + (size_t)CH * i + 2);
+        if (CH > 3) q2.w = __ldg(colors + (size_t)CH * i + 3);
+        recs[3 * (size_t)i] = q0;
+        recs[3 * (size_t)i + 1] = q1;
+        recs[3 * (size_t)i + 2] = q2;
+        if (r > 0) tile_rect(q0, (float)r, tbx, tby, cull, lox, loy, hix, hiy);
+    }
+    for_each_tile(lox, loy, hix, hiy, tbx, 0u, 0u,
+                  [&](int tile, uint32_t, uint32_t) { atomicAdd(tile_counts + tile, 1); });
+}
+
+__global__ void __launch_bounds__(kBinThreads)
+bin_emit_kernel(int N, const float* __restrict__ depths, const int32_t* __restrict__ radii,
+                const float4* __restrict__ recs, int tbx, int tby, int cull,
+                int32_t* __restrict__ cursors, uint64_t* __restrict__ keys) {
+    const int i = blockIdx.x * kBinThreads + threadIdx.x;
+    int lox = 0, loy = 0, hix = 0, hiy = 0;
+    uint64_t key = 0;
+    if (i < N) {
+        int r = __ldg(radii + i);
+        if (r > 0) {
+            float4 q0 = __ldg(recs + 3 * (size_t)i);
+            tile_rect(q0, (float)r, tbx, tby, cull, lox, loy, hix, hiy);
+            key = ((uint64_t)__float_as_uint(__ldg(depths + i)) << 32) | (uint32_t)i;
+        }
+    }
+    for_each_tile(lox, loy, hix, hiy, tbx, (uint32_t)key, (uint32_t)(key >> 32),
+                  [&](int tile, uint32_t lo, uint32_t hi) {
+                      int slot = atomicAdd(cursors + tile, 1);
+                      keys[slot] = ((uint64_t)hi << 32) | lo;
+                  });
+}
+
+// Single-CTA exclusive scan over the tile counts + max / oversize statistics.
+__global__ void __launch_bounds__(1024)
+bin_scan_kernel(int T, const int32_t* __restrict__ counts, int32_t* __restrict__ offsets,
+                int32_t* __restrict__ stats, int cap) {
+    __shared__ int s_warp[32];
+    __shared__ int s_carry;
+    __shared__ int s_max, s_big;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) { s_carry = 0; s_max = 0; s_big = 0; }
+    __syncthreads();
+    int lmax = 0, lbig = 0;
+    for (int base = 0; base < T; base += 1024) {
+        int idx = base + tid;
+        int v = (idx < T) ? __ldg(counts + idx) : 0;
+        lmax = max(lmax, v);
+        lbig += (v > cap) ? 1 : 0;
+        int x = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int y = __shfl_up_sync(0xffffffffu, x, d);
+            if (lane >= d) x += y;
+        }
+        if (lane == 31) s_warp[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            int wsum = s_warp[lane];
+            int xs = wsum;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                int y = __shfl_up_sync(0xffffffffu, xs, d);
+                if (lane >= d) xs += y;
+            }
+            s_warp[lane] = xs - wsum;  // exclusive prefix of warp sums
+        }
+        __syncthreads();
+        int carry = s_carry;
+        int excl = carry + s_warp[warp] + x - v;
+        if (idx < T) offsets[idx] = excl;
+        __syncthreads();
+        if (tid == 1023) s_carry = excl + v;
+        __syncthreads();
+    }
+    atomicMax(&s_max, lmax);
+    atomicAdd(&s_big, lbig);
+    __syncthreads();
+    if (tid == 0) {
+        offsets[T] = s_carry;
+        stats[0] = s_carry;
+        stats[1] = s_max;
+        stats[2] = s_big;
+        stats[3] = 0;
+    }
+}
+
+// Bitonic sort of P (power of two) 64-bit keys held in `s` by the whole CTA.
+template <typename Ptr>
+__device__ __forceinline__ void bitonic_sort(Ptr s, int P, int nthreads) {
+    for (int k = 2; k <= P; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < (P >> 1); i += nthreads) {
+                int lo = ((i & ~(j - 1)) << 1) | (i & (j - 1));
+                int hi = lo | j;
+                bool asc = (lo & k) == 0;
+                uint64_t a = s[lo], b = s[hi];
+                if ((a > b) == asc) { s[lo] = b; s[hi] = a; }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// One CTA per tile; only tiles with lo_count < n <= hi_count are handled by this launch
+// (size classes keep shared memory per CTA, and so occupancy, matched to the list length).
+__global__ void __launch_bounds__(kSortThreads)
+bin_sort_kernel(int T, const int32_t* __restrict__ offsets, const uint64_t* __restrict__ keys,
+                int32_t* __restrict__ ids_sorted, int lo_count, int hi_count) {
+    extern __shared__ __align__(16) uint64_t s_keys[];
+    const int tile = blockIdx.x;
+    const int start = __ldg(offsets + tile);
+    const int n = __ldg(offsets + tile + 1) - start;
+    if (n <= lo_count || n > hi_count) return;
+    int P = 2;
+    while (P < n) P <<= 1;
+    for (int i = threadIdx.x; i < P; i += kSortThreads)
+        s_keys[i] = (i < n) ? keys[start + i] : ~0ull;
+    __syncthreads();
+    bitonic_sort(s_keys, P, kSortThreads);
+    for (int i = threadIdx.x; i < n; i += kSortThreads) ids_sorted[start + i] = (int32_t)(uint32_t)s_keys[i];
+}
+
+// Fallback for tiles whose list exceeds the shared-memory cap: same network, in global scratch.
+__global__ void __launch_bounds__(1024)
+bin_sort_big_kernel(int T, const int32_t* __restrict__ offsets, const uint64_t* __restrict__ keys,
+                    int32_t* __restrict__ ids_sorted, int cap, int P, uint64_t* __restrict__ scratch,
+                    int32_t* __restrict__ counter) {
+    __shared__ int s_slot;
+    const int tile = blockIdx.x;
+    const int start = __ldg(offsets + tile);
+    const int n = __ldg(offsets + tile + 1) - start;
+    if (n <= cap) return;
+    if (threadIdx.x == 0) s_slot = atomicAdd(counter, 1);
+    __syncthreads();
+    uint64_t* buf = scratch + (size_t)s_slot * P;
+    for (int i = threadIdx.x; i < P; i += 1024) buf[i] = (i < n) ? keys[start + i] : ~0ull;
+    __syncthreads();
+    bitonic_sort(buf, P, 1024);
+    for (int i = threadIdx.x; i < n; i += 1024) ids_sorted[start + i] = (int32_t)(uint32_t)buf[i];
+}
+
+}  // namespace ts
+
+extern "C" {
+
+int ts_bin_smem_sort_cap(void) { return ts::kSmemSortCap; }
+
+int ts_bin_count(int N, int CH, const float* xys, const float* depths, const int32_t* radii,
+                 const float* conics, const float* opacity, const float* colors, int img_height,
+                 int img_width, int tiles_x, int tiles_y, int cull_mode, float* recs,
+                 int32_t* tile_counts, ts_stream_t stream) {
+    (void)depths; (void)img_height; (void)img_width;
+    if (N < 0 || CH < 1 || CH > 4 || tiles_x <= 0 || tiles_y <= 0) return TS_ERR_INVALID;
+    if (!tile_counts) return TS_ERR_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    TS_CHECK_CUDA(cudaMemsetAsync(tile_counts, 0, sizeof(int32_t) * (size_t)tiles_x * tiles_y, st), "ts_bin_count/memset");
+    if (N == 0) return TS_OK;
+    if (!xys || !radii || !conics || !opacity || !colors || !recs) return TS_ERR_INVALID;
+    if (!ts::aligned16(recs) || (reinterpret_cast<uintptr_t>(xys) & 7u)) return TS_ERR_ALIGN;
+    int grid = (N + ts::kBinThreads - 1) / ts::kBinThreads;
+#define TS_LAUNCH_COUNT(C) \
+    ts::bin_count_kernel<C><<<grid, ts::kBinThreads, 0, st>>>(N, (const float2*)xys, radii, conics, opacity, colors, tiles_x, tiles_y, cull_mode, (float4*)recs, tile_counts)
+    switch (CH) {
+        case 1: TS_LAUNCH_COUNT(1); break;
+        case 2: TS_LAUNCH_COUNT(2); break;
+        case 3: TS_LAUNCH_COUNT(3); break;
+        default: TS_LAUNCH_COUNT(4); break;
+    }
+#undef TS_LAUNCH_COUNT
+    TS_CHECK_LAUNCH("ts_bin_count");
+    return TS_OK;
+}
+
+int ts_bin_scan(int num_tiles, const int32_t* tile_counts, int32_t* tile_offsets, int32_t* stats,
+                int smem_sort_cap, ts_stream_t stream) {
+    if (num_tiles <= 0 || !tile_counts || !tile_offsets || !stats) return TS_ERR_INVALID;
+    ts::bin_scan_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(num_tiles, tile_counts, tile_offsets, stats, smem_sort_cap);
+    TS_CHECK_LAUNCH("ts_bin_scan");
+    return TS_OK;
+}
+
+int ts_bin_emit(int N, const float* depths, const int32_t* radii, const float* recs, int tiles_x,
+                int tiles_y, int cull_mode, const int32_t* tile_offsets, int32_t* cursors,
+                uint64_t* keys, ts_stream_t stream) {
+    if (N < 0 || tiles_x <= 0 || tiles_y <= 0) return TS_ERR_INVALID;
+    if (N == 0) return TS_OK;
+    if (!depths || !radii || !recs || !tile_offsets || !cursors || !keys) return TS_ERR_INVALID;
+    if (!ts::aligned16(recs)) return TS_ERR_ALIGN;
+    cudaStream_t st = (cudaStream_t)stream;
+    TS_CHECK_CUDA(cudaMemcpyAsync(cursors, tile_offsets, sizeof(int32_t) * (size_t)tiles_x * tiles_y,
+                                  cudaMemcpyDeviceToDevice, st), "ts_bin_emit/memcpy");
+    int grid = (N + ts::kBinThreads - 1) / ts::kBinThreads;
+    ts::bin_emit_kernel<<<grid, ts::kBinThreads, 0, st>>>(N, depths, radii, (const float4*)recs, tiles_x,
+                                                          tiles_y, cull_mode, cursors, keys);
+    TS_CHECK_LAUNCH("ts_bin_emit");
+    return TS_OK;
+}
+
+int ts_bin_sort(int num_tiles, const int32_t* tile_offsets, uint64_t* keys, int32_t* ids_sorted,
+                int max_count, int n_big_tiles, uint64_t* big_scratch, int32_t* big_counter,
+                ts_stream_t stream) {
+    if (num_tiles <= 0 || !tile_offsets) return TS_ERR_INVALID;
+    if (max_count <= 0) return TS_OK;
+    if (!keys || !ids_sorted) return TS_ERR_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    static bool attr_set = false;
+    if (!attr_set) {
+        TS_CHECK_CUDA(cudaFuncSetAttribute(ts::bin_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           ts::kSmemSortCap * (int)sizeof(uint64_t)), "ts_bin_sort/attr");
+        attr_set = true;
+    }
+    // size classes: (0,512], (512,2048], (2048,cap]
+    const int bounds[4] = {0, 512, 2048, ts::kSmemSortCap};
+    for (int c = 0; c < 3; ++c) {
+        if (max_count <= bounds[c]) break;
+        size_t smem = sizeof(uint64_t) * (size_t)bounds[c + 1];
+        ts::bin_sort_kernel<<<num_tiles, ts::kSortThreads, smem, st>>>(num_tiles, tile_offsets, keys, ids_sorted,
+                                                                      bounds[c], bounds[c + 1]);
+        TS_CHECK_LAUNCH("ts_bin_sort");
+    }
+    if (n_big_tiles > 0) {
+        if (!big_scratch || !big_counter) return TS_ERR_CAPACITY;
+        int P = 2;
+        while (P < max_count) P <<= 1;
+        TS_CHECK_CUDA(cudaMemsetAsync(big_counter, 0, sizeof(int32_t), st), "ts_bin_sort/memset");
+        ts::bin_sort_big_kernel<<<num_tiles, 1024, 0, st>>>(num_tiles, tile_offsets, keys, ids_sorted,
+                                                            ts::kSmemSortCap, P, big_scratch, big_counter);
+        TS_CHECK_LAUNCH("ts_bin_sort/big");
+    }
+    return TS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,419 @@
+// K4 / K5 — per-pixel front-to-back alpha compositing, forward and backward.
+// Behind gsplat.rasterize_gaussians  [REF tinysplat/splatting/rasterize.py:44,50,83-86].
+//
+// One CTA per 16x16 tile [REF rasterize.py:19-20], 8 warps, each warp owns an 8x4-pixel
+// sub-block.  The tile's depth-sorted id list is consumed in batches of 256: every thread
+// gathers one 48-byte packed record (3 x LDGSTS.128, double buffered, L2-resident record
+// array) into shared memory, then tests its Gaussian's alpha>=1/255 footprint against the 8
+// sub-blocks; warp ballots turn that into one 32-bit mask per (sub-block, staging warp).  Each
+// warp then walks only the set bits of ITS masks, so Gaussians that cannot touch its 32 pixels
+// cost it nothing (hierarchical culling inside shared memory — no extra global traffic).
+//
+// Not HBM-bound: fp32 FMA/MUFU issue bound (and, backward, shuffle + L2-atomic bound).
+#include "ts_common.cuh"
+
+namespace ts {
+
+constexpr int kBlendThreads = 256;
+constexpr int kBatch = 256;
+
+// Geometry of the thread->pixel map shared by forward and backward.
+struct PixMap {
+    int warp, lane, i, j;
+    bool inside;
+    float px, py;
+};
+
+__device__ __forceinline__ PixMap pix_map(int H, int W) {
+    PixMap m;
+    m.warp = threadIdx.x >> 5;
+    m.lane = threadIdx.x & 31;
+    int wx = m.warp & 1, wy = m.warp >> 1, lx = m.lane & 7, ly = m.lane >> 3;
+    m.j = blockIdx.x * kBlock + wx * 8 + lx;
+    m.i = blockIdx.y * kBlock + wy * 4 + ly;
+    m.inside = (m.i < H) && (m.j < W);
+    m.px = (float)m.j + kPixCenter;
+    m.py = (float)m.i + kPixCenter;
+    return m;
+}
+
+// 8-bit mask: which of the tile's 8 sub-blocks (8 wide x 4 tall) the footprint box can reach.
+__device__ __forceinline__ unsigned subblock_mask(float4 q0) {
+    const float X0 = (float)(blockIdx.x * kBlock) + kPixCenter;
+    const float Y0 = (float)(blockIdx.y * kBlock) + kPixCenter;
+    float xl = q0.x - q0.z, xh = q0.x + q0.z, yl = q0.y - q0.w, yh = q0.y + q0.w;
+    unsigned mx = 0, my = 0;
+    // columns: sub-block wx covers pixel centres [X0+8wx, X0+8wx+7]
+    if (xh >= X0 && xl <= X0 + 7.f) mx |= 1u;
+    if (xh >= X0 + 8.f && xl <= X0 + 15.f) mx |= 2u;
+    // rows: sub-block wy covers pixel centres [Y0+4wy, Y0+4wy+3]
+#pragma unroll
+    for (int wy = 0; wy < 4; ++wy)
+        if (yh >= Y0 + 4.f * wy && yl <= Y0 + 4.f * wy + 3.f) my |= 1u << wy;
+    unsigned m = 0;
+#pragma unroll
+    for (int wy = 0; wy < 4; ++wy)
+        if (my & (1u << wy)) m |= mx << (2 * wy);
+    return m;  // bit (2*wy + wx) == warp index of that sub-block
+}
+
+// Exponent (in log2 units) of one Gaussian at one pixel.  Written with explicit fma/mul
+// intrinsics so that forward and backward round identically: backward must re-derive exactly
+// the skip decisions (pw < 0, alpha < 1/255) forward took.
+__device__ __forceinline__ float eval_power(const float4& q0, const float4& q1, float px, float py,
+                                            float& dx, float& dy) {
+    dx = __fsub_rn(q0.x, px);
+    dy = __fsub_rn(q0.y, py);
+    float t = __fmaf_rn(q1.y, dy, __fmul_rn(q1.x, dx));
+    return __fmaf_rn(t, dx, __fmul_rn(__fmul_rn(q1.z, dy), dy));
+}
+
+template <int CH>
+__global__ void __launch_bounds__(kBlendThreads)
+blend_fwd_kernel(int H, int W, int tbx, const int32_t* __restrict__ tile_offsets,
+                 const int32_t* __restrict__ ids, const float4* __restrict__ recs,
+                 const float* __restrict__ background, float* __restrict__ out_img,
+                 float* __restrict__ final_T, int32_t* __restrict__ n_contrib) {
+    __shared__ __align__(16) float4 s_rec[2][kBatch * 3];
+    __shared__ unsigned s_mask[8][8];  // [sub-block][staging warp]
+    const unsigned full = 0xffffffffu;
+    const PixMap pm = pix_map(H, W);
+    const int tid = threadIdx.x;
+    const int tile = blockIdx.y * tbx + blockIdx.x;
+    const int start = __ldg(tile_offsets + tile);
+    const int count = __ldg(tile_offsets + tile + 1) - start;
+    const int nb = (count + kBatch - 1) / kBatch;
+
+    float T = 1.f;
+    float acc[CH];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) acc[c] = 0.f;
+    int ncon = 0;
+    bool done = !pm.inside;
+
+    auto prefetch = [&](int b) {
+        int p = b * kBatch + tid;
+        if (p < count) {
+            int g = __ldg(ids + start + p);
+            const float4* src = recs + 3 * (size_t)g;
+            float4* dst = &s_rec[b & 1][tid * 3];
+            cp_async16(dst, src);
+            cp_async16(dst + 1, src + 1);
+            cp_async16(dst + 2, src + 2);
+        }
+    };
+    if (nb > 0) prefetch(0);
+    cp_async_commit();
+
+    for (int b = 0; b < nb; ++b) {
+        const int buf = b & 1;
+        if (b + 1 < nb) prefetch(b + 1);
+        cp_async_commit();
+        cp_async_wait<1>();  // batch b (this thread's copies) has landed
+        unsigned mine = 0;
+        if (b * kBatch + tid < count) mine = subblock_mask(s_rec[buf][tid * 3]);
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+            unsigned m = __ballot_sync(full, (mine >> s) & 1u);
+            if (pm.lane == 0) s_mask[s][pm.warp] = m;
+        }
+        __syncthreads();  // records + masks of batch b visible to all
+        bool warp_done = __all_sync(full, done);
+        if (!warp_done) {
+            for (int k = 0; k < 8 && !warp_done; ++k) {
+                unsigned m = s_mask[pm.warp][k];
+                while (m) {
+                    int bit = __ffs(m) - 1;
+                    m &= m - 1;
+                    const int g = k * 32 + bit;
+                    const float4 q0 = s_rec[buf][g * 3];
+                    const float4 q1 = s_rec[buf][g * 3 + 1];
+                    float dx, dy;
+                    float pw = eval_power(q0, q1, pm.px, pm.py, dx, dy);
+                    float alpha = fminf(kAlphaMax, __fmul_rn(q1.w, ex2_approx(-pw)));
+                    if (!done && pw >= 0.f && alpha >= kAlphaMin) {
+                        float nT = T * (1.f - alpha);
+                        if (nT <= kTStop) {
+                            done = true;
+                        } else {
+                            const float4 q2 = s_rec[buf][g * 3 + 2];
+                            float wgt = alpha * T;
+                            acc[0] = fmaf(wgt, q2.x, acc[0]);
+                            if (CH > 1) acc[1] = fmaf(wgt, q2.y, acc[1]);
+                            if (CH > 2) acc[2] = fmaf(wgt, q2.z, acc[2]);
+                            if (CH > 3) acc[3] = fmaf(wgt, q2.w, acc[3]);
+                            T = nT;
+                            ncon = b * kBatch + g + 1;
+                        }
+                    }
+                }
+                warp_done = __all_sync(full, done);
+            }
+        }
+        // also guards reuse of s_rec[buf] / s_mask by the next iterations
+        if (__syncthreads_and(warp_done)) break;
+    }
+    cp_async_wait<0>();
+
+    if (pm.inside) {
+        const size_t pix = (size_t)pm.i * W + pm.j;
+#pragma unroll
+        for (int c = 0; c < CH; ++c) out_img[pix * CH + c] = fmaf(T, __ldg(background + c), acc[c]);
+        final_T[pix] = T;
+        n_contrib[pix] = ncon;
+    }
+}
+
+template <int CH>
+__global__ void __launch_bounds__(kBlendThreads)
+blend_bwd_kernel(int H, int W, int tbx, const int32_t* __restrict__ tile_offsets,
+                 const int32_t* __restrict__ ids, const float4* __restrict__ recs,
+                 const float* __restrict__ background, const float* __restrict__ final_T,
+                 const int32_t* __restrict__ n_contrib, const float* __restrict__ v_out_img,
+                 const float* __restrict__ v_out_alpha, float4* __restrict__ grads) {
+    constexpr int NV = 6 + CH;  // S_x S_y S_xx S_xy S_yy v_opac + colours
+    __shared__ __align__(16) float4 s_rec[2][kBatch * 3];
+    __shared__ __align__(16) float s_acc[kBatch * kGradFloats];
+    __shared__ int s_gid[2][kBatch];
+    __shared__ unsigned s_mask[8][8];
+    __shared__ int s_nmax;
+    const unsigned full = 0xffffffffu;
+    const PixMap pm = pix_map(H, W);
+    const int tid = threadIdx.x;
+    const int tile = blockIdx.y * tbx + blockIdx.x;
+    const int start = __ldg(tile_offsets + tile);
+
+    float T_final = 1.f, v_oa = 0.f;
+    float v_out[CH];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) v_out[c] = 0.f;
+    int nc = 0;
+    if (pm.inside) {
+        const size_t pix = (size_t)pm.i * W + pm.j;
+        T_final = __ldg(final_T + pix);
+        nc = __ldg(n_contrib + pix);
+#pragma unroll
+        for (int c = 0; c < CH; ++c) v_out[c] = __ldg(v_out_img + pix * CH + c);
+        if (v_out_alpha) v_oa = __ldg(v_out_alpha + pix);
+    }
+    float bgdot = 0.f;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) bgdot = fmaf(__ldg(background + c), v_out[c], bgdot);
+    const float wfin = T_final * (v_oa - bgdot);
+    float T = T_final;
+    float buffer[CH];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) buffer[c] = 0.f;
+
+    if (tid == 0) s_nmax = 0;
+#pragma unroll
+    for (int k = 0; k < kGradFloats; ++k) s_acc[tid * kGradFloats + k] = 0.f;
+    __syncthreads();
+    int wmax = nc;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) wmax = max(wmax, __shfl_xor_sync(full, wmax, d));
+    if (pm.lane == 0) atomicMax(&s_nmax, wmax);
+    __syncthreads();
+    const int nmax = s_nmax;  // entries [0, nmax) of the tile list contributed somewhere
+    const int nb = (nmax + kBatch - 1) / kBatch;
+
+    // batch b, slot t  <->  list position  p = nmax-1 - (b*256 + t)   (back to front)
+    auto prefetch = [&](int b) {
+        int p = nmax - 1 - (b * kBatch + tid);
+        if (p >= 0) {
+            int g = __ldg(ids + start + p);
+            s_gid[b & 1][tid] = g;
+            const float4* src = recs + 3 * (size_t)g;
+            float4* dst = &s_rec[b & 1][tid * 3];
+            cp_async16(dst, src);
+            cp_async16(dst + 1, src + 1);
+            cp_async16(dst + 2, src + 2);
+        }
+    };
+    if (nb > 0) prefetch(0);
+    cp_async_commit();
+
+    for (int b = 0; b < nb; ++b) {
+        const int buf = b & 1;
+        if (b + 1 < nb) prefetch(b + 1);
+        cp_async_commit();
+        cp_async_wait<1>();
+        const int my_p = nmax - 1 - (b * kBatch + tid);
+        unsigned mine = 0;
+        if (my_p >= 0) mine = subblock_mask(s_rec[buf][tid * 3]);
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+            unsigned m = __ballot_sync(full, (mine >> s) & 1u);
+            if (pm.lane == 0) s_mask[s][pm.warp] = m;
+        }
+        __syncthreads();
+        for (int k = 0; k < 8; ++k) {
+            unsigned m = s_mask[pm.warp][k];
+            while (m) {
+                int bit = __ffs(m) - 1;
+                m &= m - 1;
+                const int g = k * 32 + bit;
+                const int p = nmax - 1 - (b * kBatch + g);
+                const float4 q0 = s_rec[buf][g * 3];
+                const float4 q1 = s_rec[buf][g * 3 + 1];
+                float dx, dy;
+                float pw = eval_power(q0, q1, pm.px, pm.py, dx, dy);
+                float vis = ex2_approx(-pw);
+                float araw = __fmul_rn(q1.w, vis);
+                float alpha = fminf(kAlphaMax, araw);
+                bool valid = pm.inside && (p < nc) && (pw >= 0.f) && (alpha >= kAlphaMin);
+                if (!__any_sync(full, valid)) continue;
+                float val[NV];
+#pragma unroll
+                for (int v = 0; v < NV; ++v) val[v] = 0.f;
+                if (valid) {
+                    const float4 q2 = s_rec[buf][g * 3 + 2];
+                    const float col[4] = {q2.x, q2.y, q2.z, q2.w};
+                    float ra = __frcp_rn(1.f - alpha);
+                    T *= ra;
+                    float fac = alpha * T;
+                    float v_alpha = wfin * ra;
+#pragma unroll
+                    for (int c = 0; c < CH; ++c) {
+                        val[6 + c] = fac * v_out[c];
+                        v_alpha = fmaf(col[c] * T - buffer[c] * ra, v_out[c], v_alpha);
+                        buffer[c] = fmaf(col[c], fac, buffer[c]);
+                    }
+                    if (araw > kAlphaMax) v_alpha = 0.f;  // clamped: d alpha / d araw = 0
+                    float v_sig = -araw * v_alpha;
+                    val[0] = v_sig * dx;
+                    val[1] = v_sig * dy;
+                    val[2] = val[0] * dx;
+                    val[3] = val[0] * dy;
+                    val[4] = val[1] * dy;
+                    val[5] = vis * v_alpha;
+                }
+#pragma unroll
+                for (int v = 0; v < NV; ++v) val[v] = warp_sum(val[v]);
+                if (pm.lane == 0) {
+                    float* a = s_acc + g * kGradFloats;
+                    atomicAdd(a + 0, val[0]); atomicAdd(a + 1, val[1]);
+                    atomicAdd(a + 2, val[2]); atomicAdd(a + 3, val[3]);
+                    atomicAdd(a + 4, val[4]); atomicAdd(a + 5, val[5]);
+#pragma unroll
+                    for (int c = 0; c < CH; ++c) atomicAdd(a + 8 + c, val[6 + c]);
+                }
+            }
+        }
+        __syncthreads();  // all warps finished batch b: s_acc complete
+        if (mine) {
+            float4* a4 = reinterpret_cast<float4*>(s_acc + tid * kGradFloats);
+            float4* dst = grads + 3 * (size_t)s_gid[buf][tid];
+            atomicAdd(dst, a4[0]);
+            atomicAdd(dst + 1, a4[1]);
+            atomicAdd(dst + 2, a4[2]);
+            a4[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+            a4[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            a4[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        __syncthreads();  // s_acc reset + buffers free before the next batch touches them
+    }
+    cp_async_wait<0>();
+}
+
+template <int CH>
+__global__ void __launch_bounds__(256)
+unpack_grads_kernel(int N, const int32_t* __restrict__ radii, const float* __restrict__ conics,
+                    const float4* __restrict__ grads, float2* __restrict__ v_xys,
+                    float* __restrict__ v_conics, float* __restrict__ v_colors,
+                    float* __restrict__ v_opacity) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= N) return;
+    float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0, g2 = g0;
+    if (__ldg(radii + i) > 0) {
+        g0 = __ldg(grads + 3 * (size_t)i);
+        g1 = __ldg(grads + 3 * (size_t)i + 1);
+        g2 = __ldg(grads + 3 * (size_t)i + 2);
+    }
+    float a = __ldg(conics + 3 * i), b = __ldg(conics + 3 * i + 1), c = __ldg(conics + 3 * i + 2);
+    // sigma = .5(a dx^2 + c dy^2) + b dx dy,  dx = x - px
+    v_xys[i] = make_float2(a * g0.x + b * g0.y, b * g0.x + c * g0.y);
+    v_conics[3 * i] = 0.5f * g0.z;
+    v_conics[3 * i + 1] = g0.w;
+    v_conics[3 * i + 2] = 0.5f * g1.x;
+    v_opacity[i] = g1.y;
+    v_colors[(size_t)CH * i] = g2.x;
+    if (CH > 1) v_colors[(size_t)CH * i + 1] = g2.y;
+    if (CH > 2) v_colors[(size_t)CH * i + 2] = g2.z;
+    if (CH > 3) v_colors[(size_t)CH * i + 3] = g2.w;
+}
+
+}  // namespace ts
+
+extern "C" {
+
+int ts_blend_fwd(int CH, int img_height, int img_width, int tiles_x, int tiles_y,
+                 const int32_t* tile_offsets, const int32_t* ids_sorted, const float* recs,
+                 const float* background, float* out_img, float* final_T, int32_t* n_contrib,
+                 ts_stream_t stream) {
+    if (CH < 1 || CH > 4 || img_height <= 0 || img_width <= 0 || tiles_x <= 0 || tiles_y <= 0) return TS_ERR_INVALID;
+    if (!tile_offsets || !background || !out_img || !final_T || !n_contrib) return TS_ERR_INVALID;
+    if (recs && !ts::aligned16(recs)) return TS_ERR_ALIGN;
+    dim3 grid(tiles_x, tiles_y);
+    cudaStream_t st = (cudaStream_t)stream;
+#define TS_LAUNCH_FWD(C) \
+    ts::blend_fwd_kernel<C><<<grid, ts::kBlendThreads, 0, st>>>(img_height, img_width, tiles_x, tile_offsets, ids_sorted, (const float4*)recs, background, out_img, final_T, n_contrib)
+    switch (CH) {
+        case 1: TS_LAUNCH_FWD(1); break;
+        case 2: TS_LAUNCH_FWD(2); break;
+        case 3: TS_LAUNCH_FWD(3); break;
+        default: TS_LAUNCH_FWD(4); break;
+    }
+#undef TS_LAUNCH_FWD
+    TS_CHECK_LAUNCH("ts_blend_fwd");
+    return TS_OK;
+}
+
+int ts_blend_bwd(int N, int CH, int img_height, int img_width, int tiles_x, int tiles_y,
+                 const int32_t* tile_offsets, const int32_t* ids_sorted, const float* recs,
+                 const float* background, const float* final_T, const int32_t* n_contrib,
+                 const float* v_out_img, const float* v_out_alpha, float* grads,
+                 ts_stream_t stream) {
+    if (N < 0 || CH < 1 || CH > 4 || img_height <= 0 || img_width <= 0 || tiles_x <= 0 || tiles_y <= 0) return TS_ERR_INVALID;
+    if (N == 0) return TS_OK;
+    if (!tile_offsets || !background || !final_T || !n_contrib || !v_out_img || !grads) return TS_ERR_INVALID;
+    if (!ts::aligned16(grads) || (recs && !ts::aligned16(recs))) return TS_ERR_ALIGN;
+    cudaStream_t st = (cudaStream_t)stream;
+    TS_CHECK_CUDA(cudaMemsetAsync(grads, 0, sizeof(float) * ts::kGradFloats * (size_t)N, st), "ts_blend_bwd/memset");
+    dim3 grid(tiles_x, tiles_y);
+#define TS_LAUNCH_BWD(C) \
+    ts::blend_bwd_kernel<C><<<grid, ts::kBlendThreads, 0, st>>>(img_height, img_width, tiles_x, tile_offsets, ids_sorted, (const float4*)recs, background, final_T, n_contrib, v_out_img, v_out_alpha, (float4*)grads)
+    switch (CH) {
+        case 1: TS_LAUNCH_BWD(1); break;
+        case 2: TS_LAUNCH_BWD(2); break;
+        case 3: TS_LAUNCH_BWD(3); break;
+        default: TS_LAUNCH_BWD(4); break;
+    }
+#undef TS_LAUNCH_BWD
+    TS_CHECK_LAUNCH("ts_blend_bwd");
+    return TS_OK;
+}
+
+int ts_blend_unpack_grads(int N, int CH, const int32_t* radii, const float* conics,
+                          const float* grads, float* v_xys, float* v_conics, float* v_colors,
+                          float* v_opacity, ts_stream_t stream) {
+    if (N < 0 || CH < 1 || CH > 4) return TS_ERR_INVALID;
+    if (N == 0) return TS_OK;
+    if (!radii || !conics || !grads || !v_xys || !v_conics || !v_colors || !v_opacity) return TS_ERR_INVALID;
+    if (!ts::aligned16(grads) || (reinterpret_cast<uintptr_t>(v_xys) & 7u)) return TS_ERR_ALIGN;
+    int grid = (N + 255) / 256;
+    cudaStream_t st = (cudaStream_t)stream;
+#define TS_LAUNCH_UNPACK(C) \
+    ts::unpack_grads_kernel<C><<<grid, 256, 0, st>>>(N, radii, conics, (const float4*)grads, (float2*)v_xys, v_conics, v_colors, v_opacity)
+    switch (CH) {
+        case 1: TS_LAUNCH_UNPACK(1); break;
+        case 2: TS_LAUNCH_UNPACK(2); break;
+        case 3: TS_LAUNCH_UNPACK(3); break;
+        default: TS_LAUNCH_UNPACK(4); break;
+    }
+#undef TS_LAUNCH_UNPACK
+    TS_CHECK_LAUNCH("ts_blend_unpack_grads");
+    return TS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,345 @@
+// K1 / K6 — EWA projection forward and backward (streaming, HBM-bound; one thread per
+// Gaussian, AoS [N,3]/[N,6] arrays staged through shared memory with 128-bit accesses).
+// Replaces gsplat.project_gaussians fwd/bwd  [REF tinysplat/splatting/rasterize.py:32,64-73].
+#include "ts_common.cuh"
+
+namespace ts {
+
+constexpr int kProjThreads = 256;
+
+struct ProjCam {
+    float V[12];  // 3x4 row-major world->camera
+    float P[16];  // 4x4 row-major full projection
+};
+
+__device__ __forceinline__ void load_cam(const float* __restrict__ viewmat,
+                                         const float* __restrict__ projmat, ProjCam& c) {
+#pragma unroll
+    for (int i = 0; i < 12; ++i) c.V[i] = __ldg(viewmat + i);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) c.P[i] = __ldg(projmat + i);
+}
+
+// Everything forward computes that backward needs again (recomputed, not stored).
+struct ProjState {
+    float t[3];
+    float R[9];
+    float s[3];        // glob_scale * scale
+    float Sig[6];      // cov3d upper triangle: 00 01 02 11 12 22
+    float T[6];        // 2x3
+    float U[6];        // T * Sigma, 2x3
+    float a, b, c, det;
+    float J00, J02, J11, J12, rz;
+    float txc, tyc, limx, limy;
+    bool clampx, clampy;
+    float ph[4], rw;
+    bool near_ok, det_ok, w_ok;
+};
+
+__device__ __forceinline__ void project_core(const ProjCam& cam, const float mu[3],
+                                             const float sc[3], float gs, float4 q, float fx,
+                                             float fy, int H, int W, float clip, ProjState& st) {
+    const float* V = cam.V;
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+        st.t[r] = V[4 * r + 0] * mu[0] + V[4 * r + 1] * mu[1] + V[4 * r + 2] * mu[2] + V[4 * r + 3];
+    st.near_ok = st.t[2] > clip;
+    float tz = st.near_ok ? st.t[2] : 1.f;
+
+    quat_to_rotmat(q, st.R);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) st.s[j] = gs * sc[j];
+    float s2[3] = {st.s[0] * st.s[0], st.s[1] * st.s[1], st.s[2] * st.s[2]};
+    const float* R = st.R;
+    st.Sig[0] = R[0] * R[0] * s2[0] + R[1] * R[1] * s2[1] + R[2] * R[2] * s2[2];
+    st.Sig[1] = R[0] * R[3] * s2[0] + R[1] * R[4] * s2[1] + R[2] * R[5] * s2[2];
+    st.Sig[2] = R[0] * R[6] * s2[0] + R[1] * R[7] * s2[1] + R[2] * R[8] * s2[2];
+    st.Sig[3] = R[3] * R[3] * s2[0] + R[4] * R[4] * s2[1] + R[5] * R[5] * s2[2];
+    st.Sig[4] = R[3] * R[6] * s2[0] + R[4] * R[7] * s2[1] + R[5] * R[8] * s2[2];
+    st.Sig[5] = R[6] * R[6] * s2[0] + R[7] * R[7] * s2[1] + R[8] * R[8] * s2[2];
+
+    st.limx = kFovClamp * 0.5f * (float)W / fx;
+    st.limy = kFovClamp * 0.5f * (float)H / fy;
+    float rx = st.t[0] / tz, ry = st.t[1] / tz;
+    st.clampx = (rx < -st.limx) || (rx > st.limx);
+    st.clampy = (ry < -st.limy) || (ry > st.limy);
+    st.txc = tz * fminf(st.limx, fmaxf(-st.limx, rx));
+    st.tyc = tz * fminf(st.limy, fmaxf(-st.limy, ry));
+    st.rz = 1.f / tz;
+    float rz2 = st.rz * st.rz;
+    st.J00 = fx * st.rz;
+    st.J02 = -fx * st.txc * rz2;
+    st.J11 = fy * st.rz;
+    st.J12 = -fy * st.tyc * rz2;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        st.T[k] = st.J00 * V[k] + st.J02 * V[8 + k];
+        st.T[3 + k] = st.J11 * V[4 + k] + st.J12 * V[8 + k];
+    }
+    const float* S = st.Sig;
+    const float Sm[9] = {S[0], S[1], S[2], S[1], S[3], S[4], S[2], S[4], S[5]};
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            st.U[3 * r + k] = st.T[3 * r + 0] * Sm[k] + st.T[3 * r + 1] * Sm[3 + k] +
+                              st.T[3 * r + 2] * Sm[6 + k];
+    st.a = st.U[0] * st.T[0] + st.U[1] * st.T[1] + st.U[2] * st.T[2] + kCov2dBlur;
+    st.b = st.U[0] * st.T[3] + st.U[1] * st.T[4] + st.U[2] * st.T[5];
+    st.c = st.U[3] * st.T[3] + st.U[4] * st.T[4] + st.U[5] * st.T[5] + kCov2dBlur;
+    st.det = st.a * st.c - st.b * st.b;
+    st.det_ok = st.det != 0.f;
+
+    const float* P = cam.P;
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+        st.ph[r] = P[4 * r + 0] * mu[0] + P[4 * r + 1] * mu[1] + P[4 * r + 2] * mu[2] + P[4 * r + 3];
+    float w = st.ph[3] + kWEps;
+    st.w_ok = st.near_ok && (w != 0.f);
+    st.rw = 1.f / (st.w_ok ? w : 1.f);
+}
+
+__global__ void __launch_bounds__(kProjThreads)
+project_fwd_kernel(int N, const float* __restrict__ means, const float* __restrict__ scales,
+                   float gs, const float4* __restrict__ quats,
+                   const float* __restrict__ viewmat, const float* __restrict__ projmat,
+                   float fx, float fy, float cx, float cy, int H, int W, int tbx, int tby,
+                   float clip, float2* __restrict__ xys, float* __restrict__ depths,
+                   int32_t* __restrict__ radii, float* __restrict__ conics,
+                   int32_t* __restrict__ ntiles, float* __restrict__ cov3d) {
+    constexpr int TH = kProjThreads;
+    __shared__ __align__(16) float s_buf[TH * 9];
+    const int item0 = blockIdx.x * TH;
+    const int tid = threadIdx.x;
+    block_load<3, TH>(means, s_buf, item0, N);
+    block_load<3, TH>(scales, s_buf + 3 * TH, item0, N);
+    __syncthreads();
+    const int i = item0 + tid;
+    const bool in = i < N;
+    float mu[3] = {0.f, 0.f, 1.f}, sc[3] = {1.f, 1.f, 1.f};
+    float4 q = make_float4(1.f, 0.f, 0.f, 0.f);
+    if (in) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            mu[k] = s_buf[3 * tid + k];
+            sc[k] = s_buf[3 * TH + 3 * tid + k];
+        }
+        q = __ldg(quats + i);
+    }
+    __syncthreads();  // inputs consumed; s_buf is reused for output staging
+
+    ProjCam cam;
+    load_cam(viewmat, projmat, cam);
+    ProjState st;
+    project_core(cam, mu, sc, gs, q, fx, fy, H, W, clip, st);
+
+    float dets = st.det_ok ? st.det : 1.f;
+    float inv = 1.f / dets;
+    float con0 = st.c * inv, con1 = -st.b * inv, con2 = st.a * inv;
+    float mid = 0.5f * (st.a + st.c);
+    float disc = sqrtf(fmaxf(mid * mid - st.det, kEigFloor));
+    float lam = fmaxf(mid + disc, mid - disc);
+    float radius = ceilf(3.f * sqrtf(lam));
+    if (!(radius >= 0.f)) radius = 0.f;  // NaN -> 0
+    radius = fminf(radius, kMaxRadius);
+    float px = 0.5f * (float)W * st.ph[0] * st.rw + cx - 0.5f;
+    float py = 0.5f * (float)H * st.ph[1] * st.rw + cy - 0.5f;
+    // NaN/inf-safe copies for the bbox only
+    float bx = (px == px) ? fminf(fmaxf(px, -1e9f), 1e9f) : 0.f;
+    float by = (py == py) ? fminf(fmaxf(py, -1e9f), 1e9f) : 0.f;
+    int lox, loy, hix, hiy;
+    tile_bbox(bx, by, radius, tbx, tby, lox, loy, hix, hiy);
+    int area = (hix - lox) * (hiy - loy);
+    bool ok = in && st.near_ok && st.det_ok && st.w_ok && (area > 0);
+
+    s_buf[3 * tid + 0] = ok ? con0 : 0.f;
+    s_buf[3 * tid + 1] = ok ? con1 : 0.f;
+    s_buf[3 * tid + 2] = ok ? con2 : 0.f;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) s_buf[3 * TH + 6 * tid + k] = st.near_ok ? st.Sig[k] : 0.f;
+    if (in) {
+        xys[i] = ok ? make_float2(px, py) : make_float2(0.f, 0.f);
+        depths[i] = ok ? st.t[2] : 0.f;
+        radii[i] = ok ? (int32_t)radius : 0;
+        ntiles[i] = ok ? area : 0;
+    }
+    __syncthreads();
+    block_store<3, TH>(conics, s_buf, item0, N);
+    block_store<6, TH>(cov3d, s_buf + 3 * TH, item0, N);
+}
+
+__global__ void __launch_bounds__(kProjThreads)
+project_bwd_kernel(int N, const float* __restrict__ means, const float* __restrict__ scales,
+                   float gs, const float4* __restrict__ quats,
+                   const float* __restrict__ viewmat, const float* __restrict__ projmat,
+                   float fx, float fy, float cx, float cy, int H, int W,
+                   const int32_t* __restrict__ radii, const float2* __restrict__ v_xys,
+                   const float* __restrict__ v_depths, const float* __restrict__ v_conics,
+                   float* __restrict__ v_means, float* __restrict__ v_scales,
+                   float4* __restrict__ v_quats) {
+    constexpr int TH = kProjThreads;
+    __shared__ __align__(16) float s_buf[TH * 9];
+    const int item0 = blockIdx.x * TH;
+    const int tid = threadIdx.x;
+    block_load<3, TH>(means, s_buf, item0, N);
+    block_load<3, TH>(scales, s_buf + 3 * TH, item0, N);
+    block_load<3, TH>(v_conics, s_buf + 6 * TH, item0, N);
+    __syncthreads();
+    const int i = item0 + tid;
+    const bool in = i < N;
+    float mu[3] = {0.f, 0.f, 1.f}, sc[3] = {1.f, 1.f, 1.f}, vcon[3] = {0.f, 0.f, 0.f};
+    float4 q = make_float4(1.f, 0.f, 0.f, 0.f);
+    float2 vxy = make_float2(0.f, 0.f);
+    float vdep = 0.f;
+    bool ok = false;
+    if (in) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            mu[k] = s_buf[3 * tid + k];
+            sc[k] = s_buf[3 * TH + 3 * tid + k];
+            vcon[k] = s_buf[6 * TH + 3 * tid + k];
+        }
+        q = __ldg(quats + i);
+        ok = __ldg(radii + i) > 0;
+        vxy = __ldg(v_xys + i);
+        vdep = __ldg(v_depths + i);
+    }
+    __syncthreads();
+
+    float vmu[3] = {0.f, 0.f, 0.f}, vs[3] = {0.f, 0.f, 0.f};
+    float4 vq = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ok) {
+        ProjCam cam;
+        load_cam(viewmat, projmat, cam);
+        ProjState st;
+        project_core(cam, mu, sc, gs, q, fx, fy, H, W, -3.0e38f, st);  // radii>0 => passed the near clip
+        const float* V = cam.V;
+        const float* P = cam.P;
+        // (1) pixel position
+        float vndx = 0.5f * (float)W * vxy.x, vndy = 0.5f * (float)H * vxy.y;
+        float vph0 = vndx * st.rw, vph1 = vndy * st.rw;
+        float vph3 = -(vndx * st.ph[0] + vndy * st.ph[1]) * st.rw * st.rw;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) vmu[k] = P[k] * vph0 + P[4 + k] * vph1 + P[12 + k] * vph3;
+        // (2) depth
+#pragma unroll
+        for (int k = 0; k < 3; ++k) vmu[k] += V[8 + k] * vdep;
+        // (3) conic -> cov2d
+        float inv = 1.f / st.det;
+        float A = st.c * inv, B = -st.b * inv, C = st.a * inv;
+        float va = -A * A * vcon[0] - A * B * vcon[1] - B * B * vcon[2];
+        float vb = -2.f * A * B * vcon[0] - (A * C + B * B) * vcon[1] - 2.f * B * C * vcon[2];
+        float vc = -B * B * vcon[0] - B * C * vcon[1] - C * C * vcon[2];
+        float hb = 0.5f * vb;
+        // (4) cov2d = T Sigma T^T
+        const float* T = st.T;
+        const float* U = st.U;
+        float vT[6];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            vT[k] = 2.f * (va * U[k] + hb * U[3 + k]);
+            vT[3 + k] = 2.f * (hb * U[k] + vc * U[3 + k]);
+        }
+        float vSig[9];
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                vSig[3 * j + k] = T[j] * (va * T[k] + hb * T[3 + k]) + T[3 + j] * (hb * T[k] + vc * T[3 + k]);
+        // v_J = v_T * Rv^T (only the four live entries)
+        float vJ00 = vT[0] * V[0] + vT[1] * V[1] + vT[2] * V[2];
+        float vJ02 = vT[0] * V[8] + vT[1] * V[9] + vT[2] * V[10];
+        float vJ11 = vT[3] * V[4] + vT[4] * V[5] + vT[5] * V[6];
+        float vJ12 = vT[3] * V[8] + vT[4] * V[9] + vT[5] * V[10];
+        float rz = st.rz, rz2 = rz * rz, rz3 = rz2 * rz;
+        float vtxc = -fx * rz2 * vJ02, vtyc = -fy * rz2 * vJ12;
+        float vt[3];
+        vt[2] = -fx * rz2 * vJ00 - fy * rz2 * vJ11 + 2.f * fx * st.txc * rz3 * vJ02 +
+                2.f * fy * st.tyc * rz3 * vJ12;
+        if (st.clampx) { vt[0] = 0.f; vt[2] += (st.txc * rz) * vtxc; } else vt[0] = vtxc;
+        if (st.clampy) { vt[1] = 0.f; vt[2] += (st.tyc * rz) * vtyc; } else vt[1] = vtyc;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) vmu[k] += V[k] * vt[0] + V[4 + k] * vt[1] + V[8 + k] * vt[2];
+        // (5) Sigma = M M^T, M = R diag(s)
+        const float* R = st.R;
+        float vR[9];
+#pragma unroll
+        for (int ii = 0; ii < 3; ++ii)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                float vM = 2.f * (vSig[3 * ii + 0] * R[0 + j] * st.s[j] + vSig[3 * ii + 1] * R[3 + j] * st.s[j] +
+                                  vSig[3 * ii + 2] * R[6 + j] * st.s[j]);
+                vR[3 * ii + j] = vM * st.s[j];
+                vs[j] += gs * R[3 * ii + j] * vM;
+            }
+        float w = q.x, x = q.y, y = q.z, z = q.w;
+        vq.x = 2.f * (-z * vR[1] + y * vR[2] + z * vR[3] - x * vR[5] - y * vR[6] + x * vR[7]);
+        vq.y = 2.f * (y * vR[1] + z * vR[2] + y * vR[3] - 2.f * x * vR[4] - w * vR[5] + z * vR[6] +
+                      w * vR[7] - 2.f * x * vR[8]);
+        vq.z = 2.f * (-2.f * y * vR[0] + x * vR[1] + w * vR[2] + x * vR[3] + z * vR[5] - w * vR[6] +
+                      z * vR[7] - 2.f * y * vR[8]);
+        vq.w = 2.f * (-2.f * z * vR[0] - w * vR[1] + x * vR[2] + w * vR[3] - 2.f * z * vR[4] +
+                      y * vR[5] + x * vR[6] + y * vR[7]);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        s_buf[3 * tid + k] = vmu[k];
+        s_buf[3 * TH + 3 * tid + k] = vs[k];
+    }
+    if (in) v_quats[i] = vq;
+    __syncthreads();
+    block_store<3, TH>(v_means, s_buf, item0, N);
+    block_store<3, TH>(v_scales, s_buf + 3 * TH, item0, N);
+}
+
+}  // namespace ts
+
+extern "C" {
+
+int ts_project_fwd(int N, const float* means3d, const float* scales, float glob_scale,
+                   const float* quats, const float* viewmat, const float* projmat, float fx,
+                   float fy, float cx, float cy, int img_height, int img_width, int tiles_x,
+                   int tiles_y, float clip_thresh, float* xys, float* depths, int32_t* radii,
+                   float* conics, int32_t* num_tiles_hit, float* cov3d, ts_stream_t stream) {
+    if (N < 0 || img_height <= 0 || img_width <= 0 || tiles_x <= 0 || tiles_y <= 0) return TS_ERR_INVALID;
+    if (N == 0) return TS_OK;
+    if (!means3d || !scales || !quats || !viewmat || !projmat || !xys || !depths || !radii ||
+        !conics || !num_tiles_hit || !cov3d)
+        return TS_ERR_INVALID;
+    if (!ts::aligned16(means3d) || !ts::aligned16(scales) || !ts::aligned16(quats) ||
+        !ts::aligned16(xys) || !ts::aligned16(conics) || !ts::aligned16(cov3d))
+        return TS_ERR_ALIGN;
+    int grid = (N + ts::kProjThreads - 1) / ts::kProjThreads;
+    ts::project_fwd_kernel<<<grid, ts::kProjThreads, 0, (cudaStream_t)stream>>>(
+        N, means3d, scales, glob_scale, (const float4*)quats, viewmat, projmat, fx, fy, cx, cy,
+        img_height, img_width, tiles_x, tiles_y, clip_thresh, (float2*)xys, depths, radii, conics,
+        num_tiles_hit, cov3d);
+    TS_CHECK_LAUNCH("ts_project_fwd");
+    return TS_OK;
+}
+
+int ts_project_bwd(int N, const float* means3d, const float* scales, float glob_scale,
+                   const float* quats, const float* viewmat, const float* projmat, float fx,
+                   float fy, float cx, float cy, int img_height, int img_width,
+                   const int32_t* radii, const float* v_xys, const float* v_depths,
+                   const float* v_conics, float* v_means3d, float* v_scales, float* v_quats,
+                   ts_stream_t stream) {
+    if (N < 0 || img_height <= 0 || img_width <= 0) return TS_ERR_INVALID;
+    if (N == 0) return TS_OK;
+    if (!means3d || !scales || !quats || !viewmat || !projmat || !radii || !v_xys || !v_depths ||
+        !v_conics || !v_means3d || !v_scales || !v_quats)
+        return TS_ERR_INVALID;
+    if (!ts::aligned16(means3d) || !ts::aligned16(scales) || !ts::aligned16(quats) ||
+        !ts::aligned16(v_xys) || !ts::aligned16(v_conics) || !ts::aligned16(v_means3d) ||
+        !ts::aligned16(v_scales) || !ts::aligned16(v_quats))
+        return TS_ERR_ALIGN;
+    int grid = (N + ts::kProjThreads - 1) / ts::kProjThreads;
+    ts::project_bwd_kernel<<<grid, ts::kProjThreads, 0, (cudaStream_t)stream>>>(
+        N, means3d, scales, glob_scale, (const float4*)quats, viewmat, projmat, fx, fy, cx, cy,
+        img_height, img_width, radii, (const float2*)v_xys, v_depths, v_conics, v_means3d,
+        v_scales, (float4*)v_quats);
+    TS_CHECK_LAUNCH("ts_project_bwd");
+    return TS_OK;
+}
+
+}  // extern "C"

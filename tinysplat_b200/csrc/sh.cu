@@ -1,0 +1,230 @@
+// K2 / K7 — spherical harmonics -> colour, forward and backward (streaming, HBM-bound).
+// Replaces gsplat.sh.spherical_harmonics  [REF tinysplat/splatting/rasterize.py:38,75-81].
+// One thread per Gaussian; the [N,K,3] coefficient rows are staged through shared memory with
+// coalesced (128-bit where alignment allows) accesses, padded to an odd stride so the
+// thread-per-row reads are bank-conflict free.  Only the first (degree+1)^2 bases are read.
+#include "ts_common.cuh"
+
+namespace ts {
+
+constexpr int kShThreads = 128;
+
+#define TS_SH_C0 0.28209479177387814f
+#define TS_SH_C1 0.4886025119029199f
+
+template <int DEG>
+__device__ __forceinline__ void sh_basis(float dx, float dy, float dz, float* b) {
+    b[0] = TS_SH_C0;
+    if (DEG < 1) return;
+    float n2 = dx * dx + dy * dy + dz * dz;
+    float inv = rsqrtf(fmaxf(n2, 1e-30f));
+    // one Newton step: rsqrtf is approximate, the oracle divides by the exact norm
+    inv = inv * (1.5f - 0.5f * n2 * inv * inv);
+    float x = dx * inv, y = dy * inv, z = dz * inv;
+    b[1] = -TS_SH_C1 * y;
+    b[2] = TS_SH_C1 * z;
+    b[3] = -TS_SH_C1 * x;
+    if (DEG < 2) return;
+    float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+    b[4] = 1.0925484305920792f * xy;
+    b[5] = -1.0925484305920792f * yz;
+    b[6] = 0.31539156525252005f * (2.f * zz - xx - yy);
+    b[7] = -1.0925484305920792f * xz;
+    b[8] = 0.5462742152960396f * (xx - yy);
+    if (DEG < 3) return;
+    b[9] = -0.5900435899266435f * y * (3.f * xx - yy);
+    b[10] = 2.890611442640554f * xy * z;
+    b[11] = -0.4570457994644658f * y * (4.f * zz - xx - yy);
+    b[12] = 0.3731763325901154f * z * (2.f * zz - 3.f * xx - 3.f * yy);
+    b[13] = -0.4570457994644658f * x * (4.f * zz - xx - yy);
+    b[14] = 1.445305721320277f * z * (xx - yy);
+    b[15] = -0.5900435899266435f * x * (xx - 3.f * yy);
+    if (DEG < 4) return;
+    b[16] = 2.5033429417967046f * xy * (xx - yy);
+    b[17] = -1.7701307697799304f * yz * (3.f * xx - yy);
+    b[18] = 0.9461746957575601f * xy * (7.f * zz - 1.f);
+    b[19] = -0.6690465435572892f * yz * (7.f * zz - 3.f);
+    b[20] = 0.10578554691520431f * (zz * (35.f * zz - 30.f) + 3.f);
+    b[21] = -0.6690465435572892f * xz * (7.f * zz - 3.f);
+    b[22] = 0.47308734787878004f * (xx - yy) * (7.f * zz - 1.f);
+    b[23] = -1.7701307697799304f * xz * (xx - 3.f * yy);
+    b[24] = 0.6258357354491761f * (xx * (xx - 3.f * yy) - yy * (3.f * xx - yy));
+}
+
+// Copy the first `need` floats of each `row`-float row of items [item0, item0+n_valid) into
+// shared rows of stride `sstride` at column `scol`.  128-bit global loads when rows keep 16 B
+// alignment and the needed prefix is a multiple of 4 floats.
+__device__ __forceinline__ void rows_to_smem(const float* __restrict__ g, int row, int need,
+                                             float* s, int sstride, int scol, int item0,
+                                             int n_valid) {
+    const float* base = g + (size_t)item0 * row;
+    if (((row | need) & 3) == 0 && aligned_dev16(base)) {
+        int nv = need >> 2, total = n_valid * nv;
+        for (int idx = threadIdx.x; idx < total; idx += kShThreads) {
+            int it = idx / nv, off = (idx - it * nv) << 2;
+            float4 v = __ldg(reinterpret_cast<const float4*>(base + (size_t)it * row + off));
+            float* d = s + it * sstride + scol + off;
+            d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+        }
+    } else {
+        int total = n_valid * need;
+        for (int idx = threadIdx.x; idx < total; idx += kShThreads) {
+            int it = idx / need, off = idx - it * need;
+            s[it * sstride + scol + off] = __ldg(base + (size_t)it * row + off);
+        }
+    }
+}
+
+// Write full `row`-float rows from shared (stride sstride, column scol) to global.
+__device__ __forceinline__ void smem_to_rows(float* __restrict__ g, int row, const float* s,
+                                             int sstride, int scol, int item0, int n_valid) {
+    float* base = g + (size_t)item0 * row;
+    if ((row & 3) == 0 && aligned_dev16(base)) {
+        int nv = row >> 2, total = n_valid * nv;
+        for (int idx = threadIdx.x; idx < total; idx += kShThreads) {
+            int it = idx / nv, off = (idx - it * nv) << 2;
+            const float* d = s + it * sstride + scol + off;
+            *reinterpret_cast<float4*>(base + (size_t)it * row + off) = make_float4(d[0], d[1], d[2], d[3]);
+        }
+    } else {
+        int total = n_valid * row;
+        for (int idx = threadIdx.x; idx < total; idx += kShThreads) {
+            int it = idx / row, off = idx - it * row;
+            base[(size_t)it * row + off] = s[it * sstride + scol + off];
+        }
+    }
+}
+
+template <int DEG>
+__global__ void __launch_bounds__(kShThreads)
+sh_fwd_kernel(int N, int K, const float* __restrict__ dirs, const float* __restrict__ coeffs,
+              const float* __restrict__ coeffs_rest, float* __restrict__ colors, int sstride) {
+    extern __shared__ __align__(16) float s_sh[];
+    constexpr int NB = (DEG + 1) * (DEG + 1);
+    float* s_dir = s_sh;                        // [TH*3], reused for the colour output
+    float* s_co = s_sh + kShThreads * 3 + 4;    // [TH][sstride]
+    const int item0 = blockIdx.x * kShThreads;
+    const int n_valid = min(kShThreads, N - item0);
+    const int tid = threadIdx.x;
+    block_load<3, kShThreads>(dirs, s_dir, item0, N);
+    if (coeffs_rest == nullptr) {
+        rows_to_smem(coeffs, K * 3, NB * 3, s_co, sstride, 0, item0, n_valid);
+    } else {
+        rows_to_smem(coeffs, 3, 3, s_co, sstride, 0, item0, n_valid);
+        if (NB > 1) rows_to_smem(coeffs_rest, (K - 1) * 3, (NB - 1) * 3, s_co, sstride, 3, item0, n_valid);
+    }
+    __syncthreads();
+    float r = 0.f, g = 0.f, bl = 0.f;
+    if (tid < n_valid) {
+        float b[NB];
+        sh_basis<DEG>(s_dir[3 * tid], s_dir[3 * tid + 1], s_dir[3 * tid + 2], b);
+        const float* c = s_co + tid * sstride;
+#pragma unroll
+        for (int k = 0; k < NB; ++k) {
+            r = fmaf(b[k], c[3 * k], r);
+            g = fmaf(b[k], c[3 * k + 1], g);
+            bl = fmaf(b[k], c[3 * k + 2], bl);
+        }
+    }
+    __syncthreads();
+    s_dir[3 * tid] = r; s_dir[3 * tid + 1] = g; s_dir[3 * tid + 2] = bl;
+    __syncthreads();
+    block_store<3, kShThreads>(colors, s_dir, item0, N);
+}
+
+template <int DEG>
+__global__ void __launch_bounds__(kShThreads)
+sh_bwd_kernel(int N, int K, const float* __restrict__ dirs, const float* __restrict__ v_colors,
+              float* __restrict__ v_coeffs, float* __restrict__ v_coeffs_rest, int sstride) {
+    extern __shared__ __align__(16) float s_sh[];
+    constexpr int NB = (DEG + 1) * (DEG + 1);
+    float* s_dir = s_sh;                          // [TH*3]
+    float* s_vc = s_sh + kShThreads * 3 + 4;      // [TH*3]
+    float* s_co = s_sh + 2 * (kShThreads * 3 + 4);  // [TH][sstride]
+    const int item0 = blockIdx.x * kShThreads;
+    const int n_valid = min(kShThreads, N - item0);
+    const int tid = threadIdx.x;
+    block_load<3, kShThreads>(dirs, s_dir, item0, N);
+    block_load<3, kShThreads>(v_colors, s_vc, item0, N);
+    __syncthreads();
+    if (tid < n_valid) {
+        float b[NB];
+        sh_basis<DEG>(s_dir[3 * tid], s_dir[3 * tid + 1], s_dir[3 * tid + 2], b);
+        float vr = s_vc[3 * tid], vg = s_vc[3 * tid + 1], vb = s_vc[3 * tid + 2];
+        float* c = s_co + tid * sstride;
+#pragma unroll
+        for (int k = 0; k < NB; ++k) {
+            c[3 * k] = b[k] * vr;
+            c[3 * k + 1] = b[k] * vg;
+            c[3 * k + 2] = b[k] * vb;
+        }
+        for (int k = NB * 3; k < K * 3; ++k) c[k] = 0.f;
+    }
+    __syncthreads();
+    if (v_coeffs_rest == nullptr) {
+        smem_to_rows(v_coeffs, K * 3, s_co, sstride, 0, item0, n_valid);
+    } else {
+        smem_to_rows(v_coeffs, 3, s_co, sstride, 0, item0, n_valid);
+        if (K > 1) smem_to_rows(v_coeffs_rest, (K - 1) * 3, s_co, sstride, 3, item0, n_valid);
+    }
+}
+
+static inline int sh_stride(int K) { int k3 = K * 3; return (k3 & 1) ? k3 : k3 + 1; }
+
+}  // namespace ts
+
+extern "C" {
+
+int ts_sh_fwd(int N, int degree, int K, const float* dirs, const float* coeffs,
+              const float* coeffs_rest, float* colors, ts_stream_t stream) {
+    if (N < 0 || degree < 0 || degree > 4 || K < (degree + 1) * (degree + 1) || K > 25) return TS_ERR_INVALID;
+    if (N == 0) return TS_OK;
+    if (!dirs || !coeffs || !colors) return TS_ERR_INVALID;
+    if (!ts::aligned16(dirs) || !ts::aligned16(colors) || !ts::aligned16(coeffs) ||
+        (coeffs_rest && !ts::aligned16(coeffs_rest)))
+        return TS_ERR_ALIGN;
+    int sstride = ts::sh_stride(K);
+    size_t smem = sizeof(float) * (ts::kShThreads * 3 + 4 + (size_t)ts::kShThreads * sstride);
+    int grid = (N + ts::kShThreads - 1) / ts::kShThreads;
+    cudaStream_t st = (cudaStream_t)stream;
+#define TS_LAUNCH_SH_FWD(D) \
+    ts::sh_fwd_kernel<D><<<grid, ts::kShThreads, smem, st>>>(N, K, dirs, coeffs, coeffs_rest, colors, sstride)
+    switch (degree) {
+        case 0: TS_LAUNCH_SH_FWD(0); break;
+        case 1: TS_LAUNCH_SH_FWD(1); break;
+        case 2: TS_LAUNCH_SH_FWD(2); break;
+        case 3: TS_LAUNCH_SH_FWD(3); break;
+        default: TS_LAUNCH_SH_FWD(4); break;
+    }
+#undef TS_LAUNCH_SH_FWD
+    TS_CHECK_LAUNCH("ts_sh_fwd");
+    return TS_OK;
+}
+
+int ts_sh_bwd(int N, int degree, int K, const float* dirs, const float* v_colors,
+              float* v_coeffs, float* v_coeffs_rest, ts_stream_t stream) {
+    if (N < 0 || degree < 0 || degree > 4 || K < (degree + 1) * (degree + 1) || K > 25) return TS_ERR_INVALID;
+    if (N == 0) return TS_OK;
+    if (!dirs || !v_colors || !v_coeffs) return TS_ERR_INVALID;
+    if (!ts::aligned16(dirs) || !ts::aligned16(v_colors) || !ts::aligned16(v_coeffs) ||
+        (v_coeffs_rest && !ts::aligned16(v_coeffs_rest)))
+        return TS_ERR_ALIGN;
+    int sstride = ts::sh_stride(K);
+    size_t smem = sizeof(float) * (2 * (ts::kShThreads * 3 + 4) + (size_t)ts::kShThreads * sstride);
+    int grid = (N + ts::kShThreads - 1) / ts::kShThreads;
+    cudaStream_t st = (cudaStream_t)stream;
+#define TS_LAUNCH_SH_BWD(D) \
+    ts::sh_bwd_kernel<D><<<grid, ts::kShThreads, smem, st>>>(N, K, dirs, v_colors, v_coeffs, v_coeffs_rest, sstride)
+    switch (degree) {
+        case 0: TS_LAUNCH_SH_BWD(0); break;
+        case 1: TS_LAUNCH_SH_BWD(1); break;
+        case 2: TS_LAUNCH_SH_BWD(2); break;
+        case 3: TS_LAUNCH_SH_BWD(3); break;
+        default: TS_LAUNCH_SH_BWD(4); break;
+    }
+#undef TS_LAUNCH_SH_BWD
+    TS_CHECK_LAUNCH("ts_sh_bwd");
+    return TS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,175 @@
+"""gsplat.rasterize_gaussians drop-in  [REF tinysplat/splatting/rasterize.py:4,44,50,83-86].
+
+Host-side orchestration of K3 (count -> scan -> emit -> per-tile sort) and K4/K5 (blend).
+One device->host read of 3 ints per binning (the intersection count sizes the key buffer);
+binning is reused when the same geometry is rasterised again (the reference rasterises RGB
+and then depth over identical xys/radii/conics [REF rasterize.py:42-50])."""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+from torch.autograd import Function
+
+from . import _lib
+
+BLOCK = 16
+
+
+class TileBins:
+    """Result of K3 for one (geometry, opacity, image size)."""
+    __slots__ = ("tile_offsets", "ids_sorted", "num_intersects", "max_per_tile", "tiles", "key")
+
+    def __init__(self, tile_offsets, ids_sorted, num_intersects, max_per_tile, tiles, key):
+        self.tile_offsets = tile_offsets
+        self.ids_sorted = ids_sorted
+        self.num_intersects = num_intersects
+        self.max_per_tile = max_per_tile
+        self.tiles = tiles
+        self.key = key
+
+
+_last_bins: Optional[TileBins] = None
+last_stats = {"num_intersects": 0, "max_per_tile": 0, "bins_reused": False}
+
+
+def _bins_key(xys, depths, radii, conics, opacity, H, W, cull):
+    return tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in (xys, depths, radii, conics, opacity)) \
+        + (H, W, cull)
+
+
+def pack_and_bin(xys, depths, radii, conics, opacity, colors, H, W, cull_mode=1, reuse=True):
+    """K3.  Returns (recs[N,12], TileBins).  recs always re-packed (colours differ per call)."""
+    global _last_bins
+    lib = _lib.load()
+    dev = xys.device
+    st = _lib.stream_ptr(dev)
+    N, CH = colors.shape
+    tx, ty = (W + BLOCK - 1) // BLOCK, (H + BLOCK - 1) // BLOCK
+    T = tx * ty
+    recs = torch.empty(N, lib.ts_rec_floats(), device=dev, dtype=torch.float32)
+    counts = torch.empty(T, device=dev, dtype=torch.int32)
+    _lib.check(lib.ts_bin_count(N, CH, _lib.ptr(xys), _lib.ptr(depths), _lib.ptr(radii),
+                                _lib.ptr(conics), _lib.ptr(opacity), _lib.ptr(colors), H, W, tx, ty,
+                                cull_mode, _lib.ptr(recs), _lib.ptr(counts), st), "ts_bin_count")
+    key = _bins_key(xys, depths, radii, conics, opacity, H, W, cull_mode)
+    if reuse and _last_bins is not None and _last_bins.key == key:
+        last_stats["bins_reused"] = True
+        return recs, _last_bins
+    cap = lib.ts_bin_smem_sort_cap()
+    offsets = torch.empty(T + 1, device=dev, dtype=torch.int32)
+    stats = torch.empty(4, device=dev, dtype=torch.int32)
+    _lib.check(lib.ts_bin_scan(T, _lib.ptr(counts), _lib.ptr(offsets), _lib.ptr(stats), cap, st),
+               "ts_bin_scan")
+    M, max_count, n_big, _ = stats.tolist()   # the one host sync of the path
+    keys = torch.empty(max(M, 1), device=dev, dtype=torch.int64)
+    ids_sorted = torch.empty(max(M, 1), device=dev, dtype=torch.int32)
+    if M > 0:
+        _lib.check(lib.ts_bin_emit(N, _lib.ptr(depths), _lib.ptr(radii), _lib.ptr(recs), tx, ty,
+                                   cull_mode, _lib.ptr(offsets), _lib.ptr(counts), _lib.ptr(keys), st),
+                   "ts_bin_emit")
+        big_scratch = big_counter = None
+        if n_big > 0:
+            P = 1 << (max_count - 1).bit_length()
+            big_scratch = torch.empty(n_big * P, device=dev, dtype=torch.int64)
+            big_counter = torch.empty(1, device=dev, dtype=torch.int32)
+        _lib.check(lib.ts_bin_sort(T, _lib.ptr(offsets), _lib.ptr(keys), _lib.ptr(ids_sorted),
+                                   max_count, n_big, _lib.ptr(big_scratch), _lib.ptr(big_counter), st),
+                   "ts_bin_sort")
+    bins = TileBins(offsets, ids_sorted, M, max_count, (tx, ty), key)
+    last_stats.update(num_intersects=M, max_per_tile=max_count, bins_reused=False)
+    # hold references so data_ptr-based keys cannot alias freed memory
+    bins._keepalive = (xys, depths, radii, conics, opacity)
+    _last_bins = bins
+    return recs, bins
+
+
+def clear_bin_cache() -> None:
+    global _last_bins
+    _last_bins = None
+
+
+class _RasterizeGaussians(Function):
+    @staticmethod
+    def forward(ctx, xys, depths, radii, conics, num_tiles_hit, colors, opacity, img_height,
+                img_width, background, cull_mode):
+        _lib.require_cuda(xys, colors, opacity)
+        lib = _lib.load()
+        dev = xys.device
+        H, W = int(img_height), int(img_width)
+        N, CH = colors.shape
+        if not 1 <= CH <= 4:
+            raise NotImplementedError(f"rasterize_gaussians supports 1..4 colour channels, got {CH}")
+        xys_c = _lib.f32c(xys.detach())
+        depths_c = _lib.f32c(depths.detach())
+        conics_c = _lib.f32c(conics.detach())
+        colors_c = _lib.f32c(colors.detach())
+        opac_c = _lib.f32c(opacity.detach()).reshape(-1)
+        radii_c = radii.detach().to(torch.int32).contiguous()
+        bg = _lib.f32c(background.detach().to(dev))
+        recs, bins = pack_and_bin(xys_c, depths_c, radii_c, conics_c, opac_c, colors_c, H, W,
+                                  cull_mode=cull_mode)
+        tx, ty = bins.tiles
+        out_img = torch.empty(H, W, CH, device=dev, dtype=torch.float32)
+        final_T = torch.empty(H, W, device=dev, dtype=torch.float32)
+        n_contrib = torch.empty(H, W, device=dev, dtype=torch.int32)
+        _lib.check(lib.ts_blend_fwd(CH, H, W, tx, ty, _lib.ptr(bins.tile_offsets),
+                                    _lib.ptr(bins.ids_sorted), _lib.ptr(recs), _lib.ptr(bg),
+                                    _lib.ptr(out_img), _lib.ptr(final_T), _lib.ptr(n_contrib),
+                                    _lib.stream_ptr(dev)), "ts_blend_fwd")
+        out_alpha = 1.0 - final_T
+        ctx.save_for_backward(recs, bins.tile_offsets, bins.ids_sorted, bg, final_T, n_contrib,
+                              radii_c, conics_c)
+        ctx.meta = (N, CH, H, W, tx, ty, tuple(opacity.shape))
+        return out_img, out_alpha
+
+    @staticmethod
+    def backward(ctx, v_out_img, v_out_alpha):
+        recs, offsets, ids_sorted, bg, final_T, n_contrib, radii_c, conics_c = ctx.saved_tensors
+        N, CH, H, W, tx, ty, opac_shape = ctx.meta
+        lib = _lib.load()
+        dev = recs.device
+        st = _lib.stream_ptr(dev)
+        v_img = _lib.f32c(v_out_img) if v_out_img is not None else \
+            torch.zeros(H, W, CH, device=dev, dtype=torch.float32)
+        v_alpha = _lib.f32c(v_out_alpha) if v_out_alpha is not None else None
+        grads = torch.empty(N, lib.ts_grad_floats(), device=dev, dtype=torch.float32)
+        _lib.check(lib.ts_blend_bwd(N, CH, H, W, tx, ty, _lib.ptr(offsets), _lib.ptr(ids_sorted),
+                                    _lib.ptr(recs), _lib.ptr(bg), _lib.ptr(final_T),
+                                    _lib.ptr(n_contrib), _lib.ptr(v_img), _lib.ptr(v_alpha),
+                                    _lib.ptr(grads), st), "ts_blend_bwd")
+        v_xys = torch.empty(N, 2, device=dev, dtype=torch.float32)
+        v_conics = torch.empty(N, 3, device=dev, dtype=torch.float32)
+        v_colors = torch.empty(N, CH, device=dev, dtype=torch.float32)
+        v_opacity = torch.empty(N, device=dev, dtype=torch.float32)
+        _lib.check(lib.ts_blend_unpack_grads(N, CH, _lib.ptr(radii_c), _lib.ptr(conics_c),
+                                             _lib.ptr(grads), _lib.ptr(v_xys), _lib.ptr(v_conics),
+                                             _lib.ptr(v_colors), _lib.ptr(v_opacity), st),
+                   "ts_blend_unpack_grads")
+        return (v_xys, None, None, v_conics, None, v_colors, v_opacity.reshape(opac_shape),
+                None, None, None, None)
+
+
+def rasterize_gaussians(xys: Tensor, depths: Tensor, radii: Tensor, conics: Tensor,
+                        num_tiles_hit: Tensor, colors: Tensor, opacity: Tensor,
+                        img_height: int, img_width: int, background: Optional[Tensor] = None,
+                        cull_mode: int = 1) -> Tuple[Tensor, Tensor]:
+    """Tile-binned, depth-sorted alpha compositing.  Positional signature as tinysplat calls it
+    [REF rasterize.py:86] (img_height BEFORE img_width).  Returns the 2-tuple the reference
+    unpacks [REF rasterize.py:44,50]: (out_img[H,W,C], out_alpha[H,W] = 1 - final T).
+    cull_mode=0 disables the (result-invariant) opacity-aware footprint culling."""
+    if xys.dim() != 2 or xys.shape[1] != 2:
+        raise ValueError("xys must have dimensions (N, 2)")
+    if colors.dim() != 2:
+        raise ValueError("colors must have dimensions (N, D)")
+    if opacity.numel() != xys.shape[0]:
+        raise ValueError("opacity must have N elements")
+    if colors.dtype == torch.uint8:
+        colors = colors.float() / 255
+    if background is None:
+        background = torch.ones(colors.shape[-1], dtype=torch.float32, device=colors.device)
+    elif background.shape[0] != colors.shape[-1]:
+        raise ValueError("background must have one entry per colour channel")
+    return _RasterizeGaussians.apply(xys, depths, radii, conics, num_tiles_hit, colors, opacity,
+                                     img_height, img_width, background, int(cull_mode))
