@@ -1,0 +1,391 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the hot path: Mpix/s forward+backward of the Gaussian
+rasterizer (project -> SH -> tile bin/sort -> alpha-blend, and back), one view per GPU per step.
+
+  python bench.py --gpus N --steps K --warmup W            (our arm; torchrun for N > 1)
+  python bench.py --impl reference --gpus N --steps K ...  (CPU restatement on the host cores)
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for what each key means.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "Mpix/s fwd+bwd @1M Gaussians/1080p"
+UNIT = "Mpix/s"
+
+# name -> (N gaussians, W, H, sh degree, depth loss weight, forward only)
+WORKLOADS = {
+    # the configuration the metric is quoted on (synthetic stand-in: no dataset on disk)
+    "synthetic_1M_1080p": (1_000_000, 1920, 1080, 3, 0.0, False),
+    # BASELINE configs[1] (T&T truck stand-in), configs[2], configs[4]
+    "synthetic_500k_1080p": (500_000, 1920, 1080, 3, 0.0, False),
+    "synthetic_2M_1080p_depthreg": (2_000_000, 1920, 1080, 3, 0.2, False),
+    "synthetic_4M_4k_fwd": (4_000_000, 3840, 2160, 3, 0.0, True),
+    # small case for quick checks
+    "synthetic_100k_720p": (100_000, 1280, 720, 3, 0.0, False),
+}
+DEFAULT_WORKLOAD = "synthetic_1M_1080p"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--pipeline", default="fused", choices=["fused", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-window", type=int, default=8, help="CPU sample: window edge in tiles")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------
+def view_for(step: int, rank: int, W: int, H: int):
+    """A different (deterministic) camera per rank and step: small yaw + lateral shift."""
+    from tinysplat_b200 import synthetic
+    k = step * 131 + rank * 17
+    yaw = ((k * 37) % 160) / 10.0 - 8.0
+    sx = ((k * 53) % 100) / 250.0 - 0.2
+    sy = ((k * 29) % 100) / 500.0 - 0.1
+    return synthetic.make_camera(W, H, yaw_deg=yaw, shift=(sx, sy, 0.0))
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons of one GPU during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.lines = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._pump, daemon=True)
+        self.thread.start()
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0: float, t1: float):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, power, reasons = [], None, [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.lines:
+            if not (t0 <= ts <= t1 + 0.2):
+                continue
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[0]))
+                smax = float(f[1])
+                power.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax,
+                "power_w_max": max(power) if power else None, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def algorithmic_bytes(name: str, N: int, M: int, P: int, CH: int, K: int, nb: int) -> float:
+    """Algorithmic HBM bytes of one launch of C-ABI entry `name` (per-kernel table).
+    N Gaussians, M tile intersections, P pixels, CH blended channels, K stored / nb active SH
+    bases."""
+    table = {
+        "ts_project_fwd": 96 * N,                      # 40 in, 56 out
+        "ts_project_bwd": 108 * N,                     # 68 in, 40 out
+        "ts_sh_fwd": (24 + 12 * nb) * N,
+        "ts_sh_bwd": (24 + 12 * K) * N,
+        "ts_bin_count": (76 + 4 * CH) * N + 4 * M,     # pack 48 B record + count atomics
+        "ts_bin_scan": 8 * (P // 256),
+        "ts_bin_emit": 24 * N + 12 * M,
+        "ts_bin_sort": 12 * M,
+        "ts_blend_fwd": 52 * M + (8 + 4 * CH) * P,     # id + 48 B record per pair; image, T, n
+        "ts_blend_bwd": 52 * M + (12 + 4 * CH) * P + 96 * N,   # + zero & RMW of packed grads
+        "ts_blend_unpack_grads": (64 + 24 + 4 * CH) * N,
+    }
+    return float(table.get(name, 0))
+
+
+# ---------------------------------------------------------------------------------------------
+def cpu_sample(workload: str, window_tiles: int, steps: int, warmup: int, threads: int | None = None):
+    """Times the CPU oracle (our PyTorch restatement — the reference has no CPU rasterizer) on a
+    bounded sample of the workload: the central window of `window_tiles`^2 tiles, with the
+    Gaussians that can reach it.  Returns (Mpix/s, description, cores, per-step seconds)."""
+    import oracle  # the checker, used here only as the reported CPU baseline
+    from tinysplat_b200 import synthetic
+    N, W, H, deg, depth_w, fwd_only = WORKLOADS[workload]
+    if threads:
+        torch.set_num_threads(threads)
+    cores = torch.get_num_threads()
+    cam = synthetic.make_camera(W, H)
+    sc = synthetic.make_scene(N, W, H, seed=0)
+    tbx, tby = (W + 15) // 16, (H + 15) // 16
+    tx0, ty0 = (tbx - window_tiles) // 2, (tby - window_tiles) // 2
+    win = (tx0, ty0, tx0 + window_tiles, ty0 + window_tiles)
+    # sample preparation (untimed): keep Gaussians whose 3-sigma box can reach the window
+    with torch.no_grad():
+        q = sc["quats"]
+        V, Pm = cam.view_matrix, cam.proj_matrix
+        xys, _, radii, _, _, _ = oracle.project_gaussians(
+            sc["means"], torch.exp(sc["scales"]), 1.0, q / q.norm(dim=-1, keepdim=True), V[:3], Pm @ V,
+            cam.f_x, cam.f_y, W / 2, H / 2, H, W, (tbx, tby, 1))
+        r = radii.float() + 16
+        keep = (radii > 0) & (xys[:, 0] + r >= win[0] * 16) & (xys[:, 0] - r <= win[2] * 16) & \
+               (xys[:, 1] + r >= win[1] * 16) & (xys[:, 1] - r <= win[3] * 16)
+    sub = {k: (v[keep].clone() if k != "background" else v) for k, v in sc.items()}
+    n_sub = int(keep.sum())
+    names = ["means", "scales", "quats", "opacities", "colors_dc", "colors_rest"]
+    pix = (window_tiles * 16) ** 2
+    g = torch.Generator().manual_seed(1)
+    gt = torch.rand(window_tiles * 16, window_tiles * 16, 3, generator=g)
+    times = []
+    for it in range(warmup + steps):
+        p = {k: (v.clone().requires_grad_(not fwd_only) if k in names else v) for k, v in sub.items()}
+        t0 = time.perf_counter()
+        img, ex = oracle.render_reference_adapter(p, cam.view_matrix, cam.proj_matrix, cam.f_x, cam.f_y,
+                                                  (W, H), deg, tile_window=win)
+        if not fwd_only:
+            loss = (img - gt).abs().mean()
+            if depth_w:
+                loss = loss + depth_w * ex["depth"].abs().mean()
+            loss.backward()
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    sec = statistics.mean(times)
+    desc = (f"central {window_tiles}x{window_tiles}-tile window ({window_tiles * 16}^2 px) of {workload}, "
+            f"{n_sub} Gaussians reaching it, full adapter op sequence "
+            f"({'fwd' if fwd_only else 'fwd+bwd'}), fp32 torch CPU, {steps} steps")
+    return pix / sec / 1e6, desc, cores, sec
+
+
+def run_reference(args):
+    """--impl reference: the reference has no CPU (or any in-tree) implementation of this path —
+    its arithmetic is the absent gsplat package — so this arm times our CPU restatement (the
+    oracle, kind "port") on the host cores, on a bounded sample of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    N, W, H, deg, depth_w, fwd_only = WORKLOADS[args.workload]
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    # bound the work: each sample step is O(1 s); keep the whole run within a few minutes
+    steps_eff, warm_eff = min(steps, 20), min(warmup, 3)
+    val, desc, cores, sec = cpu_sample(args.workload, args.cpu_window, steps_eff, warm_eff)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps_eff, "warmup": warm_eff, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "gaussians": N, "width": W, "height": H, "sh_degree": deg,
+                   "views_per_step": 1, "note": "CPU restatement on a bounded sample; host cores only"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    from tinysplat_b200 import _lib, synthetic, rasterize as rz
+    from tinysplat_b200.parallel import GradientAllReducer
+    from tinysplat_b200.rasterizer import GaussianRasterizer, ParamModel
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (our arm) needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+
+    N, W, H, deg, depth_w, fwd_only = WORKLOADS[args.workload]
+    P = W * H
+    sc = synthetic.make_scene(N, W, H, seed=0)          # every rank holds the same replica
+    model = ParamModel(sc, dev, deg, requires_grad=not fwd_only)
+    rast = GaussianRasterizer(model, None, dev, args.pipeline)
+    reducer = GradientAllReducer(model.parameters(), average=True, overlap=True) if not fwd_only else None
+    g = torch.Generator().manual_seed(100 + rank)
+    gt_host = torch.rand(H, W, 3, generator=g).pin_memory()
+    gt_dev = gt_host.to(dev)
+    K, Wm = max(1, args.steps), max(3, args.warmup)
+
+    def one_step(i: int, gt: torch.Tensor):
+        cam = view_for(i, rank, W, H)
+        if fwd_only:
+            with torch.no_grad():
+                img, ex = rast(cam, (W, H), deg)
+            return img.mean()
+        img, ex = rast(cam, (W, H), deg)
+        loss = (img - gt).abs().mean()
+        if depth_w:
+            loss = loss + depth_w * ex["depth"].abs().mean()
+        loss.backward()
+        reducer.finish()
+        model.zero_grad()
+        return loss.detach()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, first_index):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.time()
+        e0.record()
+        for i in range(steps):
+            fn(first_index + i)
+        e1.record()
+        barrier()
+        t1 = time.time()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item(), t0, t1
+
+    # ---- device-resident arm: `value` -------------------------------------------------------
+    for i in range(Wm):
+        one_step(i, gt_dev)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    n0 = _lib.launch_count()
+    _lib.profile_start()
+    ms_total, t0, t1 = timed(lambda i: one_step(i, gt_dev), K, Wm)
+    prof = _lib.profile_stop()
+    launches = _lib.launch_count() - n0
+    clocks = sampler.stop(t0, t1) if rank == 0 else None
+    M = rz.last_stats["num_intersects"]
+    ms_step = ms_total / K
+    value = world * P / (ms_step * 1e-3) / 1e6
+
+    # ---- end-to-end arm: host buffers in, loss out -------------------------------------------
+    def e2e_step(i):
+        gt = gt_host.to(dev, non_blocking=True)           # H2D of this step's target image
+        loss = one_step(i, gt)
+        return float(loss.item())                          # D2H of the step's result
+
+    for i in range(3):
+        e2e_step(i)
+    ms_e2e, _, _ = timed(e2e_step, K, Wm + K)
+    e2e_val = world * P / (ms_e2e / K * 1e-3) / 1e6
+    h2d = gt_host.numel() * 4 + 2 * 16 * 4                  # target image + view/proj matrices
+    d2h = 4 + 16                                            # loss scalar + binning stats (4 x int32)
+
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- per-kernel breakdown and roofline of the dominant kernel ----------------------------
+    CH = 4 if args.pipeline == "fused" else 3
+    Kb = 16 if deg <= 3 else 25
+    nb = (deg + 1) ** 2
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    kern = {}
+    for name, ms_list in prof.items():
+        tot = sum(ms_list)
+        per = tot / len(ms_list)
+        by = algorithmic_bytes(name, N, M, P, CH, Kb, nb)
+        kern[name] = {"launches_per_step": len(ms_list) / K, "ms_per_launch": per, "ms_per_step": tot / K,
+                      "share": tot / ms_total, "algorithmic_bytes": by,
+                      "gbs": by / (per * 1e-3) / 1e9 if per > 0 else None}
+    top = max(kern, key=lambda k: kern[k]["ms_per_step"]) if kern else None
+    roof = None
+    if top:
+        a = kern[top]["gbs"]
+        roof = {"kernel": top, "bound": "hbm", "achieved": a, "peak": peak, "unit": "GB/s",
+                "frac": a / peak, "traffic": None, "peak_source": peak_src,
+                "note": "blend kernels are fp32-issue/atomic bound, not HBM bound (DESIGN.md); "
+                        "streaming kernels listed in `kernels`"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "gaussians": N, "width": W, "height": H, "sh_degree": deg,
+                   "views_per_step": world, "pipeline": args.pipeline, "intersections_M": M,
+                   "max_per_tile": rz.last_stats["max_per_tile"],
+                   "raster_passes_per_render": 1 if args.pipeline == "fused" else 2,
+                   "mode": "fwd" if fwd_only else "fwd+bwd", "depth_loss_weight": depth_w,
+                   "parallelism": f"dp{world} over cameras, replica per GPU, NCCL grad all-reduce"
+                   if world > 1 and not fwd_only else ("replicas only" if world > 1 else "single GPU"),
+                   "l2": "inputs larger than L2: 236 B/Gaussian parameters + 48 B records + image buffers "
+                         "> 126 MB; a different camera every step"},
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_e2e / K},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roof,
+        "kernels": kern,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            v, desc, cores, sec = cpu_sample(args.workload, args.cpu_window, 8, 2)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc,
+                                    "host_cpu_count": os.cpu_count(), "ms_per_sample_step": sec * 1e3}
+        except Exception as exc:  # the baseline is reporting, never a reason to lose the GPU number
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": None, "kind": "port",
+                                    "sample": f"failed: {exc!r}"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -78,6 +78,42 @@ def check(status: int, what: str) -> None:
         raise TinysplatError(f"{what} failed: {_STATUS.get(status, status)} {detail}")
 
 
+# ---- optional per-call CUDA-event timing (bench.py's live per-kernel breakdown) ---------------
+_profile = None
+
+
+def profile_start() -> None:
+    global _profile
+    _profile = []
+
+
+def profile_stop():
+    """Returns {entry point: [ms, ...]} for every C-ABI call since profile_start()."""
+    global _profile
+    rec, _profile = _profile or [], None
+    torch.cuda.synchronize()
+    out = {}
+    for name, s, e in rec:
+        out.setdefault(name, []).append(s.elapsed_time(e))
+    return out
+
+
+def call(name: str, *args) -> None:
+    """Invoke C-ABI entry `name`; raise on a non-zero status.  Events go on the current stream,
+    which is the stream every kernel is launched on."""
+    fn = getattr(load(), name)
+    if _profile is None:
+        check(fn(*args), name)
+        return
+    s = torch.cuda.Event(enable_timing=True)
+    e = torch.cuda.Event(enable_timing=True)
+    s.record()
+    status = fn(*args)
+    e.record()
+    _profile.append((name, s, e))
+    check(status, name)
+
+
 def ptr(t: Optional[torch.Tensor]):
     return None if t is None else t.data_ptr()
 

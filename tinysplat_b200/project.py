@@ -35,12 +35,11 @@ class _ProjectGaussians(Function):
         cov3d = torch.empty(N, 6, **f32)
         args = (float(glob_scale), float(fx), float(fy), float(cx), float(cy), int(img_height),
                 int(img_width))
-        _lib.check(lib.ts_project_fwd(
-            N, _lib.ptr(means_c), _lib.ptr(scales_c), args[0], _lib.ptr(quats_c),
+        _lib.call("ts_project_fwd", N, _lib.ptr(means_c), _lib.ptr(scales_c), args[0], _lib.ptr(quats_c),
             _lib.ptr(view_c), _lib.ptr(proj_c), args[1], args[2], args[3], args[4], args[5], args[6],
             int(tile_bounds[0]), int(tile_bounds[1]), float(clip_thresh),
             _lib.ptr(xys), _lib.ptr(depths), _lib.ptr(radii), _lib.ptr(conics),
-            _lib.ptr(num_tiles_hit), _lib.ptr(cov3d), _lib.stream_ptr(dev)), "ts_project_fwd")
+            _lib.ptr(num_tiles_hit), _lib.ptr(cov3d), _lib.stream_ptr(dev))
         ctx.save_for_backward(means_c, scales_c, quats_c, view_c, proj_c, radii)
         ctx.args = args
         ctx.mark_non_differentiable(radii, num_tiles_hit, cov3d)
@@ -60,11 +59,10 @@ class _ProjectGaussians(Function):
         v_means = torch.empty(N, 3, device=dev, dtype=torch.float32)
         v_scales = torch.empty(N, 3, device=dev, dtype=torch.float32)
         v_quats = torch.empty(N, 4, device=dev, dtype=torch.float32)
-        _lib.check(lib.ts_project_bwd(
-            N, _lib.ptr(means_c), _lib.ptr(scales_c), gs, _lib.ptr(quats_c), _lib.ptr(view_c),
+        _lib.call("ts_project_bwd", N, _lib.ptr(means_c), _lib.ptr(scales_c), gs, _lib.ptr(quats_c), _lib.ptr(view_c),
             _lib.ptr(proj_c), fx, fy, cx, cy, H, W, _lib.ptr(radii), _lib.ptr(v_xys),
             _lib.ptr(v_depths), _lib.ptr(v_conics), _lib.ptr(v_means), _lib.ptr(v_scales),
-            _lib.ptr(v_quats), _lib.stream_ptr(dev)), "ts_project_bwd")
+            _lib.ptr(v_quats), _lib.stream_ptr(dev))
         return (v_means, v_scales, None, v_quats) + (None,) * 10
 
 

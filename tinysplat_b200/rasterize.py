@@ -19,7 +19,8 @@ BLOCK = 16
 
 class TileBins:
     """Result of K3 for one (geometry, opacity, image size)."""
-    __slots__ = ("tile_offsets", "ids_sorted", "num_intersects", "max_per_tile", "tiles", "key")
+    __slots__ = ("tile_offsets", "ids_sorted", "num_intersects", "max_per_tile", "tiles", "key",
+                 "_keepalive")
 
     def __init__(self, tile_offsets, ids_sorted, num_intersects, max_per_tile, tiles, key):
         self.tile_offsets = tile_offsets
@@ -50,9 +51,9 @@ def pack_and_bin(xys, depths, radii, conics, opacity, colors, H, W, cull_mode=1,
     T = tx * ty
     recs = torch.empty(N, lib.ts_rec_floats(), device=dev, dtype=torch.float32)
     counts = torch.empty(T, device=dev, dtype=torch.int32)
-    _lib.check(lib.ts_bin_count(N, CH, _lib.ptr(xys), _lib.ptr(depths), _lib.ptr(radii),
+    _lib.call("ts_bin_count", N, CH, _lib.ptr(xys), _lib.ptr(depths), _lib.ptr(radii),
                                 _lib.ptr(conics), _lib.ptr(opacity), _lib.ptr(colors), H, W, tx, ty,
-                                cull_mode, _lib.ptr(recs), _lib.ptr(counts), st), "ts_bin_count")
+                                cull_mode, _lib.ptr(recs), _lib.ptr(counts), st)
     key = _bins_key(xys, depths, radii, conics, opacity, H, W, cull_mode)
     if reuse and _last_bins is not None and _last_bins.key == key:
         last_stats["bins_reused"] = True
@@ -60,23 +61,20 @@ def pack_and_bin(xys, depths, radii, conics, opacity, colors, H, W, cull_mode=1,
     cap = lib.ts_bin_smem_sort_cap()
     offsets = torch.empty(T + 1, device=dev, dtype=torch.int32)
     stats = torch.empty(4, device=dev, dtype=torch.int32)
-    _lib.check(lib.ts_bin_scan(T, _lib.ptr(counts), _lib.ptr(offsets), _lib.ptr(stats), cap, st),
-               "ts_bin_scan")
+    _lib.call("ts_bin_scan", T, _lib.ptr(counts), _lib.ptr(offsets), _lib.ptr(stats), cap, st)
     M, max_count, n_big, _ = stats.tolist()   # the one host sync of the path
     keys = torch.empty(max(M, 1), device=dev, dtype=torch.int64)
     ids_sorted = torch.empty(max(M, 1), device=dev, dtype=torch.int32)
     if M > 0:
-        _lib.check(lib.ts_bin_emit(N, _lib.ptr(depths), _lib.ptr(radii), _lib.ptr(recs), tx, ty,
-                                   cull_mode, _lib.ptr(offsets), _lib.ptr(counts), _lib.ptr(keys), st),
-                   "ts_bin_emit")
+        _lib.call("ts_bin_emit", N, _lib.ptr(depths), _lib.ptr(radii), _lib.ptr(recs), tx, ty,
+                                   cull_mode, _lib.ptr(offsets), _lib.ptr(counts), _lib.ptr(keys), st)
         big_scratch = big_counter = None
         if n_big > 0:
             P = 1 << (max_count - 1).bit_length()
             big_scratch = torch.empty(n_big * P, device=dev, dtype=torch.int64)
             big_counter = torch.empty(1, device=dev, dtype=torch.int32)
-        _lib.check(lib.ts_bin_sort(T, _lib.ptr(offsets), _lib.ptr(keys), _lib.ptr(ids_sorted),
-                                   max_count, n_big, _lib.ptr(big_scratch), _lib.ptr(big_counter), st),
-                   "ts_bin_sort")
+        _lib.call("ts_bin_sort", T, _lib.ptr(offsets), _lib.ptr(keys), _lib.ptr(ids_sorted),
+                                   max_count, n_big, _lib.ptr(big_scratch), _lib.ptr(big_counter), st)
     bins = TileBins(offsets, ids_sorted, M, max_count, (tx, ty), key)
     last_stats.update(num_intersects=M, max_per_tile=max_count, bins_reused=False)
     # hold references so data_ptr-based keys cannot alias freed memory
@@ -114,10 +112,10 @@ class _RasterizeGaussians(Function):
         out_img = torch.empty(H, W, CH, device=dev, dtype=torch.float32)
         final_T = torch.empty(H, W, device=dev, dtype=torch.float32)
         n_contrib = torch.empty(H, W, device=dev, dtype=torch.int32)
-        _lib.check(lib.ts_blend_fwd(CH, H, W, tx, ty, _lib.ptr(bins.tile_offsets),
+        _lib.call("ts_blend_fwd", CH, H, W, tx, ty, _lib.ptr(bins.tile_offsets),
                                     _lib.ptr(bins.ids_sorted), _lib.ptr(recs), _lib.ptr(bg),
                                     _lib.ptr(out_img), _lib.ptr(final_T), _lib.ptr(n_contrib),
-                                    _lib.stream_ptr(dev)), "ts_blend_fwd")
+                                    _lib.stream_ptr(dev))
         out_alpha = 1.0 - final_T
         ctx.save_for_backward(recs, bins.tile_offsets, bins.ids_sorted, bg, final_T, n_contrib,
                               radii_c, conics_c)
@@ -135,18 +133,17 @@ class _RasterizeGaussians(Function):
             torch.zeros(H, W, CH, device=dev, dtype=torch.float32)
         v_alpha = _lib.f32c(v_out_alpha) if v_out_alpha is not None else None
         grads = torch.empty(N, lib.ts_grad_floats(), device=dev, dtype=torch.float32)
-        _lib.check(lib.ts_blend_bwd(N, CH, H, W, tx, ty, _lib.ptr(offsets), _lib.ptr(ids_sorted),
+        _lib.call("ts_blend_bwd", N, CH, H, W, tx, ty, _lib.ptr(offsets), _lib.ptr(ids_sorted),
                                     _lib.ptr(recs), _lib.ptr(bg), _lib.ptr(final_T),
                                     _lib.ptr(n_contrib), _lib.ptr(v_img), _lib.ptr(v_alpha),
-                                    _lib.ptr(grads), st), "ts_blend_bwd")
+                                    _lib.ptr(grads), st)
         v_xys = torch.empty(N, 2, device=dev, dtype=torch.float32)
         v_conics = torch.empty(N, 3, device=dev, dtype=torch.float32)
         v_colors = torch.empty(N, CH, device=dev, dtype=torch.float32)
         v_opacity = torch.empty(N, device=dev, dtype=torch.float32)
-        _lib.check(lib.ts_blend_unpack_grads(N, CH, _lib.ptr(radii_c), _lib.ptr(conics_c),
+        _lib.call("ts_blend_unpack_grads", N, CH, _lib.ptr(radii_c), _lib.ptr(conics_c),
                                              _lib.ptr(grads), _lib.ptr(v_xys), _lib.ptr(v_conics),
-                                             _lib.ptr(v_colors), _lib.ptr(v_opacity), st),
-                   "ts_blend_unpack_grads")
+                                             _lib.ptr(v_colors), _lib.ptr(v_opacity), st)
         return (v_xys, None, None, v_conics, None, v_colors, v_opacity.reshape(opac_shape),
                 None, None, None, None)
 
