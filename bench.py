@@ -66,59 +66,70 @@ def view_for(step: int, rank: int, W: int, H: int):
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons of one GPU during the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """Samples SM clock, power and clock-event (throttle) reasons of one GPU through NVML every
+    few milliseconds on a background thread, DURING the timed region."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+               0x4: "sw_power_cap", 0x80: "hw_power_brake_slowdown"}
 
-    def __init__(self, index: int):
-        self.index = index
-        self.lines = []
-        self.proc = None
+    def __init__(self, device_index: int, period_s: float = 0.004):
+        self.period = period_s
+        self.samples = []
         self.thread = None
+        self.stop_flag = threading.Event()
+        self.handle = None
+        self.err = None
+        try:
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            try:
+                uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+                uuid = uuid if uuid.startswith("GPU-") else "GPU-" + uuid
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+            except Exception:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception as exc:  # NVML missing: report it, never fail the bench
+            self.err = repr(exc)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
-                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-        except OSError:
-            self.proc = None
+        if self.handle is None:
             return
         self.thread = threading.Thread(target=self._pump, daemon=True)
         self.thread.start()
 
     def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append((time.time(), line.strip()))
+        nv, h = self.nv, self.handle
+        while not self.stop_flag.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                self.samples.append((time.time(), float(sm), int(rs), pw))
+            except Exception as exc:
+                self.err = repr(exc)
+                return
+            time.sleep(self.period)
 
     def stop(self, t0: float, t1: float):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        sm, smax, power, reasons = [], None, [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ts, line in self.lines:
-            if not (t0 <= ts <= t1 + 0.2):
-                continue
-            f = [x.strip() for x in line.split(",")]
-            if len(f) < 8:
-                continue
-            try:
-                sm.append(float(f[0]))
-                smax = float(f[1])
-                power.append(float(f[2]))
-            except ValueError:
-                continue
-            for nm, val in zip(names, f[4:8]):
-                if val.lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax,
-                "power_w_max": max(power) if power else None, "samples": len(sm),
+        if self.handle is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [f"nvml unavailable: {self.err}"]}
+        self.stop_flag.set()
+        self.thread.join(timeout=2)
+        win = [x for x in self.samples if t0 <= x[0] <= t1]
+        if not win:   # region shorter than one period: take the samples closest to it
+            win = sorted(self.samples, key=lambda x: abs(x[0] - 0.5 * (t0 + t1)))[:3]
+        reasons = set()
+        for _, _, rs, _ in win:
+            for bit, name in self.REASONS.items():
+                if rs & bit:
+                    reasons.add(name)
+        sm = [x[1] for x in win]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.sm_max,
+                "power_w_max": max((x[3] for x in win), default=None), "samples": len(win),
                 "reasons": sorted(reasons)}
 
 
@@ -291,7 +302,6 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-        time.sleep(0.3)
     n0 = _lib.launch_count()
     _lib.profile_start()
     ms_total, t0, t1 = timed(lambda i: one_step(i, gt_dev), K, Wm)

@@ -171,7 +171,9 @@ blend_bwd_kernel(int H, int W, int tbx, const int32_t* __restrict__ tile_offsets
                  const float* __restrict__ background, const float* __restrict__ final_T,
                  const int32_t* __restrict__ n_contrib, const float* __restrict__ v_out_img,
                  const float* __restrict__ v_out_alpha, float4* __restrict__ grads) {
-    constexpr int NV = 6 + CH;  // S_x S_y S_xx S_xy S_yy v_opac + colours
+    constexpr int kSlotsUsed = 6 + CH;  // S_x S_y S_xx S_xy S_yy v_opac + colours
+    // reduction slot s -> float offset inside the 12-float packed gradient record:
+    // s < 6 ? s : s + 2   (colours live in the third float4)
     __shared__ __align__(16) float4 s_rec[2][kBatch * 3];
     __shared__ __align__(16) float s_acc[kBatch * kGradFloats];
     __shared__ int s_gid[2][kBatch];
@@ -263,9 +265,9 @@ blend_bwd_kernel(int H, int W, int tbx, const int32_t* __restrict__ tile_offsets
                 float alpha = fminf(kAlphaMax, araw);
                 bool valid = pm.inside && (p < nc) && (pw >= 0.f) && (alpha >= kAlphaMin);
                 if (!__any_sync(full, valid)) continue;
-                float val[NV];
+                float val[16];   // slots 0..5 geometry/opacity, 6..9 colours, rest zero
 #pragma unroll
-                for (int v = 0; v < NV; ++v) val[v] = 0.f;
+                for (int v = 0; v < 16; ++v) val[v] = 0.f;
                 if (valid) {
                     const float4 q2 = s_rec[buf][g * 3 + 2];
                     const float col[4] = {q2.x, q2.y, q2.z, q2.w};
@@ -288,15 +290,40 @@ blend_bwd_kernel(int H, int W, int tbx, const int32_t* __restrict__ tile_offsets
                     val[4] = val[1] * dy;
                     val[5] = vis * v_alpha;
                 }
+                // butterfly reduction of all 16 slots at once: 8+4+2+1+1 = 16 shuffles (instead
+                // of 5 per value); afterwards lane l (l even) holds the warp total of slot
+                // rev4(l>>1) and adds it to the CTA accumulator — up to 16 lanes, one shared
+                // atomic each, distinct banks.
+                {
+                    const bool b4 = pm.lane & 16, b3 = pm.lane & 8, b2 = pm.lane & 4, b1 = pm.lane & 2;
 #pragma unroll
-                for (int v = 0; v < NV; ++v) val[v] = warp_sum(val[v]);
-                if (pm.lane == 0) {
-                    float* a = s_acc + g * kGradFloats;
-                    atomicAdd(a + 0, val[0]); atomicAdd(a + 1, val[1]);
-                    atomicAdd(a + 2, val[2]); atomicAdd(a + 3, val[3]);
-                    atomicAdd(a + 4, val[4]); atomicAdd(a + 5, val[5]);
+                    for (int i = 0; i < 8; ++i) {
+                        float send = b4 ? val[i] : val[i + 8];
+                        float keep = b4 ? val[i + 8] : val[i];
+                        val[i] = keep + __shfl_xor_sync(full, send, 16);
+                    }
 #pragma unroll
-                    for (int c = 0; c < CH; ++c) atomicAdd(a + 8 + c, val[6 + c]);
+                    for (int i = 0; i < 4; ++i) {
+                        float send = b3 ? val[i] : val[i + 4];
+                        float keep = b3 ? val[i + 4] : val[i];
+                        val[i] = keep + __shfl_xor_sync(full, send, 8);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        float send = b2 ? val[i] : val[i + 2];
+                        float keep = b2 ? val[i + 2] : val[i];
+                        val[i] = keep + __shfl_xor_sync(full, send, 4);
+                    }
+                    {
+                        float send = b1 ? val[0] : val[1];
+                        float keep = b1 ? val[1] : val[0];
+                        val[0] = keep + __shfl_xor_sync(full, send, 2);
+                    }
+                    val[0] += __shfl_xor_sync(full, val[0], 1);
+                    // slot held by this lane: bit4 -> +8, bit3 -> +4, bit2 -> +2, bit1 -> +1
+                    const int slot = (b4 ? 8 : 0) + (b3 ? 4 : 0) + (b2 ? 2 : 0) + (b1 ? 1 : 0);
+                    if (!(pm.lane & 1) && slot < kSlotsUsed)
+                        atomicAdd(s_acc + g * kGradFloats + (slot < 6 ? slot : slot + 2), val[0]);
                 }
             }
         }
