@@ -48,7 +48,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
-    ap.add_argument("--pipeline", default="fused", choices=["fused", "reference"])
+    ap.add_argument("--pipeline", default="fused", choices=["fused", "reference", "unfused4"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-window", type=int, default=8, help="CPU sample: window edge in tiles")
     return ap.parse_args()
@@ -333,7 +333,7 @@ def run_ours(args):
         return
 
     # ---- per-kernel breakdown and roofline of the dominant kernel ----------------------------
-    CH = 4 if args.pipeline == "fused" else 3
+    CH = 3 if args.pipeline == "reference" else 4
     Kb = 16 if deg <= 3 else 25
     nb = (deg + 1) ** 2
     peaks = {}
@@ -367,7 +367,7 @@ def run_ours(args):
         "config": {"workload": args.workload, "gaussians": N, "width": W, "height": H, "sh_degree": deg,
                    "views_per_step": world, "pipeline": args.pipeline, "intersections_M": M,
                    "max_per_tile": rz.last_stats["max_per_tile"],
-                   "raster_passes_per_render": 1 if args.pipeline == "fused" else 2,
+                   "raster_passes_per_render": 2 if args.pipeline == "reference" else 1,
                    "mode": "fwd" if fwd_only else "fwd+bwd", "depth_loss_weight": depth_w,
                    "parallelism": f"dp{world} over cameras, replica per GPU, NCCL grad all-reduce"
                    if world > 1 and not fwd_only else ("replicas only" if world > 1 else "single GPU"),

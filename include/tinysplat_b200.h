@@ -36,6 +36,17 @@ enum ts_status {
     TS_ERR_CAPACITY = -4   /* a caller-provided workspace is too small */
 };
 
+/* Flags of the fused pipeline: the activations the reference adapter applies in torch around
+ * the gsplat calls [REF rasterize.py:39,72-73,77-79,86] folded into the kernels. */
+enum ts_flags {
+    TS_PROJ_LOG_SCALES = 1,   /* scales are log-scales: exp() inside, Jacobian in backward */
+    TS_PROJ_RAW_QUATS = 2,    /* quats are unnormalised: q/|q| inside, Jacobian in backward */
+    TS_PROJ_DEPTH_CH3 = 4,    /* backward: depth cotangent = colour channel 3 of packed grads */
+    TS_SH_DIRS_FROM_MEANS = 1,/* `dirs` holds means3d; dir = mean - viewmat[:3,3] */
+    TS_SH_OFFSET_CLAMP = 2,   /* colour = max(sh + 0.5, 0); mask of passing channels saved */
+    TS_BIN_OPACITY_LOGIT = 1  /* `opacity` holds logits: sigmoid() inside */
+};
+
 /* Library version (major*10000 + minor*100 + patch) and last CUDA error text. */
 TS_API int ts_version(void);
 TS_API const char* ts_last_error(void);
@@ -49,54 +60,70 @@ TS_API int64_t ts_launch_count(void);
  * Replaces gsplat.project_gaussians  [REF rasterize.py:32, args marshalled at :64-73].
  * viewmat: 3x4 (first three rows of the 4x4 world->camera matrix), projmat: 4x4 full
  * projection (proj @ view).  Outputs: xys[N,2], depths[N], radii[N] (int32),
- * conics[N,3], num_tiles_hit[N] (int32), cov3d[N,6].  Culled Gaussians get zeros. */
+ * conics[N,3], num_tiles_hit[N] (int32), cov3d[N,6].  Culled Gaussians get zeros.
+ * flags: TS_PROJ_LOG_SCALES | TS_PROJ_RAW_QUATS (0 = the gsplat contract). */
 TS_API int ts_project_fwd(int N,
                           const float* means3d /*[16B]*/, const float* scales /*[16B]*/,
                           float glob_scale, const float* quats /*[16B]*/,
                           const float* viewmat, const float* projmat,
                           float fx, float fy, float cx, float cy,
                           int img_height, int img_width, int tiles_x, int tiles_y,
-                          float clip_thresh,
+                          float clip_thresh, int flags,
                           float* xys /*[16B]*/, float* depths, int32_t* radii,
                           float* conics /*[16B]*/, int32_t* num_tiles_hit,
                           float* cov3d /*[16B]*/, ts_stream_t stream);
 
 /* ---- K6: EWA projection backward ---------------------------------------------------
- * Backward of ts_project_fwd: consumes v_xys[N,2], v_depths[N], v_conics[N,3] (the depth
- * cotangent is live because the reference rasterises depth as a colour
- * [REF rasterize.py:48-51]) and produces v_means3d[N,3], v_scales[N,3], v_quats[N,4]. */
+ * Backward of ts_project_fwd: consumes v_xys[N,2], v_depths[N], v_conics[N,3] (each may be
+ * NULL = zero; the depth cotangent is live because the reference rasterises depth as a
+ * colour [REF rasterize.py:48-51]) and produces v_means3d[N,3], v_scales[N,3], v_quats[N,4].
+ * Fused pipeline: packed_grads[N, ts_grad_floats()] (blend-backward's output) is consumed
+ * directly and ADDED to the explicit cotangents; with opacity_logits/v_opacity_logits the
+ * sigmoid Jacobian is applied here too; v_xys_out[N,2] (optional) receives d loss / d xy, the
+ * densification statistic's input [REF model_gaussian.py:130-132]. */
 TS_API int ts_project_bwd(int N,
                           const float* means3d /*[16B]*/, const float* scales /*[16B]*/,
                           float glob_scale, const float* quats /*[16B]*/,
                           const float* viewmat, const float* projmat,
                           float fx, float fy, float cx, float cy,
-                          int img_height, int img_width,
+                          int img_height, int img_width, int flags,
                           const int32_t* radii,
-                          const float* v_xys /*[16B]*/, const float* v_depths,
-                          const float* v_conics /*[16B]*/,
+                          const float* v_xys /*or NULL*/, const float* v_depths /*or NULL*/,
+                          const float* v_conics /*[16B] or NULL*/,
+                          const float* packed_grads /*[16B] or NULL*/,
+                          const float* opacity_logits /*or NULL*/,
                           float* v_means3d /*[16B]*/, float* v_scales /*[16B]*/,
-                          float* v_quats /*[16B]*/, ts_stream_t stream);
+                          float* v_quats /*[16B]*/, float* v_opacity_logits /*or NULL*/,
+                          float* v_xys_out /*or NULL*/, ts_stream_t stream);
 
 /* ---- K2/K7: spherical harmonics ----------------------------------------------------
  * Replaces gsplat.sh.spherical_harmonics  [REF rasterize.py:38, args at :75-81].
- * coeffs is [N,K,3]; the first (degree+1)^2 bases are used.  colors is [N,3].
+ * coeffs is [N,K,3]; the first (degree+1)^2 bases are used.
  * If coeffs_rest is non-null, coeffs holds only the DC band [N,1,3] and coeffs_rest the
  * remaining [N,K-1,3] (the reference stores them as two Parameters
- * [REF model_gaussian.py:86-87] and concatenates every step [REF rasterize.py:80]). */
+ * [REF model_gaussian.py:86-87] and concatenates every step [REF rasterize.py:80]).
+ * colors: out_stride floats per Gaussian (3 = plain [N,3]; 12 with colors = recs+8 writes
+ * straight into the packed raster record, channel 3 <- ch3[N] if given).
+ * flags: TS_SH_DIRS_FROM_MEANS (needs viewmat) | TS_SH_OFFSET_CLAMP (clamp_mask[N] out). */
 TS_API int ts_sh_fwd(int N, int degree, int K, const float* dirs /*[16B]*/,
+                     const float* viewmat /*or NULL*/,
                      const float* coeffs /*[16B]*/, const float* coeffs_rest /*[16B] or NULL*/,
-                     float* colors /*[16B]*/, ts_stream_t stream);
+                     float* colors /*[16B]*/, int out_stride, const float* ch3 /*or NULL*/,
+                     uint8_t* clamp_mask /*or NULL*/, int flags, ts_stream_t stream);
 TS_API int ts_sh_bwd(int N, int degree, int K, const float* dirs /*[16B]*/,
-                     const float* v_colors /*[16B]*/,
+                     const float* viewmat /*or NULL*/,
+                     const float* v_colors /*[16B]*/, int v_stride,
+                     const uint8_t* clamp_mask /*or NULL*/,
                      float* v_coeffs /*[16B]*/, float* v_coeffs_rest /*[16B] or NULL*/,
-                     ts_stream_t stream);
+                     int flags, ts_stream_t stream);
 
 /* ---- K3: tile binning + per-tile depth sort ------------------------------------------
  * Inside gsplat.rasterize_gaussians  [REF rasterize.py:44,50: no bins are passed in, so
  * binning happens behind the call].  Four steps; the caller reads stats_host between
  * ts_bin_scan and ts_bin_emit to size `keys` / `ids_sorted`.
  *
- * ts_bin_count : packs one raster record per Gaussian (recs[N, ts_rec_floats()]) and
+ * ts_bin_count : packs one raster record per Gaussian (recs[N, ts_rec_floats()]; the colour
+ *                float4 is skipped when colors == NULL, ts_sh_fwd then writes it) and
  *                counts, per tile, the Gaussians whose footprint can reach a pixel of it
  *                (tile_counts[T], zeroed by the callee).  CH = colour channels (1..4).
  * ts_bin_scan  : exclusive scan -> tile_offsets[T+1]; stats[4] = {total M, max per-tile
@@ -109,7 +136,7 @@ TS_API int ts_sh_bwd(int N, int degree, int K, const float* dirs /*[16B]*/,
 TS_API int ts_bin_count(int N, int CH, const float* xys, const float* depths,
                         const int32_t* radii, const float* conics, const float* opacity,
                         const float* colors, int img_height, int img_width,
-                        int tiles_x, int tiles_y, int cull_mode,
+                        int tiles_x, int tiles_y, int cull_mode, int flags,
                         float* recs /*[16B]*/, int32_t* tile_counts, ts_stream_t stream);
 TS_API int ts_bin_scan(int num_tiles, const int32_t* tile_counts, int32_t* tile_offsets,
                        int32_t* stats, int smem_sort_cap, ts_stream_t stream);
@@ -126,20 +153,23 @@ TS_API int ts_bin_smem_sort_cap(void);
 /* ---- K4/K5: alpha-blend forward / backward -----------------------------------------
  * ts_blend_fwd: per-pixel front-to-back compositing of each tile's sorted list.
  *   out_img[H,W,CH], final_T[H,W], n_contrib[H,W] (int32: position after the last
- *   contributing list entry; what backward replays from).
+ *   contributing list entry; what backward replays from).  With CH == 4 and out_ch3 != NULL
+ *   the output is split: out_img[H,W,3] + out_ch3[H,W] (RGB + depth of the fused pass);
+ *   backward mirrors it with split_ch3 = 1 (v_out_img[H,W,3] / v_out_ch3[H,W], NULL = 0).
  * ts_blend_bwd: replays back to front; accumulates per-Gaussian packed gradients
  *   grads[N, ts_grad_floats()] (zeroed by the callee).  v_out_alpha may be NULL.
  * ts_blend_unpack_grads: packed -> v_xys[N,2], v_conics[N,3], v_colors[N,CH], v_opacity[N]. */
 TS_API int ts_blend_fwd(int CH, int img_height, int img_width, int tiles_x, int tiles_y,
                         const int32_t* tile_offsets, const int32_t* ids_sorted,
                         const float* recs /*[16B]*/, const float* background,
-                        float* out_img, float* final_T, int32_t* n_contrib,
-                        ts_stream_t stream);
+                        float* out_img, float* out_ch3 /*or NULL*/, float* final_T,
+                        int32_t* n_contrib, ts_stream_t stream);
 TS_API int ts_blend_bwd(int N, int CH, int img_height, int img_width, int tiles_x, int tiles_y,
                         const int32_t* tile_offsets, const int32_t* ids_sorted,
                         const float* recs /*[16B]*/, const float* background,
                         const float* final_T, const int32_t* n_contrib,
-                        const float* v_out_img, const float* v_out_alpha /*or NULL*/,
+                        const float* v_out_img, const float* v_out_ch3 /*or NULL*/,
+                        int split_ch3, const float* v_out_alpha /*or NULL*/,
                         float* grads /*[16B]*/, ts_stream_t stream);
 TS_API int ts_blend_unpack_grads(int N, int CH, const int32_t* radii, const float* conics,
                                  const float* grads /*[16B]*/, float* v_xys, float* v_conics,

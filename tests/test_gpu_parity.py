@@ -234,7 +234,7 @@ def test_full_adapter_matches_golden_config1():
     g = torch.Generator().manual_seed(1234)
     wi = torch.rand(128, 128, 3, generator=g, dtype=torch.float64).float().to(DEV)
     wd = torch.rand(128, 128, generator=g, dtype=torch.float64).float().to(DEV)
-    for pipeline in ("reference", "fused"):
+    for pipeline in ("reference", "unfused4", "fused"):
         model = ParamModel(sc, DEV, 3)
         img, ex = GaussianRasterizer(model, None, DEV, pipeline)(cam, None, 3)
         assert torch.equal(ex["radii"].cpu(), torch.from_numpy(gold["radii"]))
@@ -246,7 +246,8 @@ def test_full_adapter_matches_golden_config1():
             assert rel_err(getattr(model, k).grad, torch.from_numpy(gold["v_" + k])) < TOL_GRAD, (pipeline, k)
 
 
-def test_no_grad_forward_and_retain_graph():
+@pytest.mark.parametrize("pipeline", ["reference", "fused"])
+def test_no_grad_forward_and_retain_graph(pipeline):
     """The viewer renders under no_grad [REF tinysplat/viewer.py:90-93]; training calls
     backward(retain_graph=True) [REF scripts/train.py:94]: a second backward must reproduce the
     first (saved buffers are neither freed nor mutated)."""
@@ -255,7 +256,7 @@ def test_no_grad_forward_and_retain_graph():
     cam = synthetic.make_camera(W, H)
     sc = synthetic.make_scene(500, W, H, seed=4)
     model = ParamModel(sc, DEV, 2)
-    rast = GaussianRasterizer(model, None, DEV, "reference")
+    rast = GaussianRasterizer(model, None, DEV, pipeline)
     with torch.no_grad():
         img0, ex0 = rast(cam, (W, H), 2)
     assert not img0.requires_grad and ex0["xys"].grad_fn is None
@@ -272,6 +273,33 @@ def test_no_grad_forward_and_retain_graph():
         assert rel_err(p.grad, a) < 1e-5
     assert rel_err(ex["xys"].grad, xg1) < 1e-5
     assert ex["xys"].grad.norm(dim=-1).shape == (500,)    # what update_grad_accum reads
+
+
+def test_fused_node_matches_unfused_ops_on_a_larger_scene():
+    """The single fused autograd node (activations folded into the kernels, packed gradients
+    consumed in place) against the composition of the five public ops, 20k Gaussians, with a
+    depth loss so the depth cotangent path (colour channel 3 -> v_depths) is live."""
+    from tinysplat_b200.rasterizer import GaussianRasterizer, ParamModel
+    W, H, N = 400, 300, 20000
+    cam = synthetic.make_camera(W, H, yaw_deg=5.0, shift=(0.1, 0.05, 0.0))
+    sc = synthetic.make_scene(N, W, H, seed=12, sh_degree=3)
+    sc["background"] = torch.tensor([0.3, 0.1, 0.7])
+    sc["quats"] = sc["quats"] * (0.5 + torch.rand(N, 1))        # un-normalised on purpose
+    g = torch.Generator().manual_seed(3)
+    wi = torch.rand(H, W, 3, generator=g).to(DEV)
+    wd = torch.rand(H, W, generator=g).to(DEV)
+    res = {}
+    for pipeline in ("reference", "fused"):
+        model = ParamModel(sc, DEV, 3)
+        img, ex = GaussianRasterizer(model, None, DEV, pipeline)(cam, (W, H), 2)
+        ((img * wi).sum() + 0.05 * (ex["depth"] * wd).sum()).backward()
+        res[pipeline] = (img, ex["depth"], ex["xys"].grad, [p.grad for p in model.parameters()], ex["radii"])
+    a, b = res["reference"], res["fused"]
+    assert torch.equal(a[4], b[4])
+    assert (a[0] - b[0]).abs().max().item() < 1e-5 and (a[1] - b[1]).abs().max().item() < 1e-4
+    assert rel_err(b[2], a[2]) < 1e-4
+    for name, ga, gb in zip(PARAMS, a[3], b[3]):
+        assert rel_err(gb, ga) < 1e-4, name
 
 
 def test_empty_and_all_culled_scenes():

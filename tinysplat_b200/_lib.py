@@ -24,21 +24,26 @@ _SIGNATURES = {
     "ts_rec_floats": ([], C.c_int),
     "ts_grad_floats": ([], C.c_int),
     "ts_launch_count": ([], C.c_int64),
-    "ts_project_fwd": ([_i, _p, _p, _f, _p, _p, _p, _f, _f, _f, _f, _i, _i, _i, _i, _f,
+    "ts_project_fwd": ([_i, _p, _p, _f, _p, _p, _p, _f, _f, _f, _f, _i, _i, _i, _i, _f, _i,
                         _p, _p, _p, _p, _p, _p, _p], C.c_int),
-    "ts_project_bwd": ([_i, _p, _p, _f, _p, _p, _p, _f, _f, _f, _f, _i, _i,
-                        _p, _p, _p, _p, _p, _p, _p, _p], C.c_int),
-    "ts_sh_fwd": ([_i, _i, _i, _p, _p, _p, _p, _p], C.c_int),
-    "ts_sh_bwd": ([_i, _i, _i, _p, _p, _p, _p, _p], C.c_int),
-    "ts_bin_count": ([_i, _i, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p], C.c_int),
+    "ts_project_bwd": ([_i, _p, _p, _f, _p, _p, _p, _f, _f, _f, _f, _i, _i, _i,
+                        _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p], C.c_int),
+    "ts_sh_fwd": ([_i, _i, _i, _p, _p, _p, _p, _p, _i, _p, _p, _i, _p], C.c_int),
+    "ts_sh_bwd": ([_i, _i, _i, _p, _p, _p, _i, _p, _p, _p, _i, _p], C.c_int),
+    "ts_bin_count": ([_i, _i, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p], C.c_int),
     "ts_bin_scan": ([_i, _p, _p, _p, _i, _p], C.c_int),
     "ts_bin_emit": ([_i, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p], C.c_int),
     "ts_bin_sort": ([_i, _p, _p, _p, _i, _i, _p, _p, _p], C.c_int),
     "ts_bin_smem_sort_cap": ([], C.c_int),
-    "ts_blend_fwd": ([_i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p], C.c_int),
-    "ts_blend_bwd": ([_i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p], C.c_int),
+    "ts_blend_fwd": ([_i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p], C.c_int),
+    "ts_blend_bwd": ([_i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p], C.c_int),
     "ts_blend_unpack_grads": ([_i, _i, _p, _p, _p, _p, _p, _p, _p, _p], C.c_int),
 }
+
+# flags (include/tinysplat_b200.h enum ts_flags)
+PROJ_LOG_SCALES, PROJ_RAW_QUATS, PROJ_DEPTH_CH3 = 1, 2, 4
+SH_DIRS_FROM_MEANS, SH_OFFSET_CLAMP = 1, 2
+BIN_OPACITY_LOGIT = 1
 
 _STATUS = {0: "TS_OK", -1: "TS_ERR_INVALID", -2: "TS_ERR_ALIGN", -3: "TS_ERR_CUDA",
            -4: "TS_ERR_CAPACITY"}

@@ -74,7 +74,7 @@ template <int CH>
 __global__ void __launch_bounds__(kBinThreads)
 bin_count_kernel(int N, const float2* __restrict__ xys, const int32_t* __restrict__ radii,
                  const float* __restrict__ conics, const float* __restrict__ opacity,
-                 const float* __restrict__ colors, int tbx, int tby, int cull,
+                 const float* __restrict__ colors, int tbx, int tby, int cull, int flags,
                  float4* __restrict__ recs, int32_t* __restrict__ tile_counts) {
     const int i = blockIdx.x * kBinThreads + threadIdx.x;
     int lox = 0, loy = 0, hix = 0, hiy = 0;
@@ -83,6 +83,7 @@ bin_count_kernel(int N, const float2* __restrict__ xys, const int32_t* __restric
         float2 xy = __ldg(xys + i);
         float a = __ldg(conics + 3 * i), b = __ldg(conics + 3 * i + 1), c = __ldg(conics + 3 * i + 2);
         float op = __ldg(opacity + i);
+        if (flags & TS_BIN_OPACITY_LOGIT) op = 1.f / (1.f + expf(-op));   // sigmoid [REF rasterize.py:86]
         float hx = 1e30f, hy = 1e30f;
         if (cull) {
             // footprint of alpha >= 1/255:  sigma <= tau = ln(255*opac);  half extents of the
@@ -98,14 +99,16 @@ bin_count_kernel(int N, const float2* __restrict__ xys, const int32_t* __restric
         }
         float4 q0 = make_float4(xy.x, xy.y, hx, hy);
         float4 q1 = make_float4(0.5f * kLog2e * a, kLog2e * b, 0.5f * kLog2e * c, op);
-        float4 q2 = make_float4(0.f, 0.f, 0.f, 0.f);
-        q2.x = __ldg(colors + (size_t)CH * i);
-        if (CH > 1) q2.y = __ldg(colors + (size_t)CH * i + 1);
-        if (CH > 2) q2.z = __ldg(colors + (size_t)CH * i + 2);
-        if (CH > 3) q2.w = __ldg(colors + (size_t)CH * i + 3);
         recs[3 * (size_t)i] = q0;
         recs[3 * (size_t)i + 1] = q1;
-        recs[3 * (size_t)i + 2] = q2;
+        if (colors) {   // otherwise the colour float4 is written by ts_sh_fwd (fused pipeline)
+            float4 q2 = make_float4(0.f, 0.f, 0.f, 0.f);
+            q2.x = __ldg(colors + (size_t)CH * i);
+            if (CH > 1) q2.y = __ldg(colors + (size_t)CH * i + 1);
+            if (CH > 2) q2.z = __ldg(colors + (size_t)CH * i + 2);
+            if (CH > 3) q2.w = __ldg(colors + (size_t)CH * i + 3);
+            recs[3 * (size_t)i + 2] = q2;
+        }
         if (r > 0) tile_rect(q0, (float)r, tbx, tby, cull, lox, loy, hix, hiy);
     }
     for_each_tile(lox, loy, hix, hiy, tbx, 0u, 0u,
@@ -251,7 +254,7 @@ int ts_bin_smem_sort_cap(void) { return ts::kSmemSortCap; }
 
 int ts_bin_count(int N, int CH, const float* xys, const float* depths, const int32_t* radii,
                  const float* conics, const float* opacity, const float* colors, int img_height,
-                 int img_width, int tiles_x, int tiles_y, int cull_mode, float* recs,
+                 int img_width, int tiles_x, int tiles_y, int cull_mode, int flags, float* recs,
                  int32_t* tile_counts, ts_stream_t stream) {
     (void)depths; (void)img_height; (void)img_width;
     if (N < 0 || CH < 1 || CH > 4 || tiles_x <= 0 || tiles_y <= 0) return TS_ERR_INVALID;
@@ -259,11 +262,11 @@ int ts_bin_count(int N, int CH, const float* xys, const float* depths, const int
     cudaStream_t st = (cudaStream_t)stream;
     TS_CHECK_CUDA(cudaMemsetAsync(tile_counts, 0, sizeof(int32_t) * (size_t)tiles_x * tiles_y, st), "ts_bin_count/memset");
     if (N == 0) return TS_OK;
-    if (!xys || !radii || !conics || !opacity || !colors || !recs) return TS_ERR_INVALID;
+    if (!xys || !radii || !conics || !opacity || !recs) return TS_ERR_INVALID;
     if (!ts::aligned16(recs) || (reinterpret_cast<uintptr_t>(xys) & 7u)) return TS_ERR_ALIGN;
     int grid = (N + ts::kBinThreads - 1) / ts::kBinThreads;
 #define TS_LAUNCH_COUNT(C) \
-    ts::bin_count_kernel<C><<<grid, ts::kBinThreads, 0, st>>>(N, (const float2*)xys, radii, conics, opacity, colors, tiles_x, tiles_y, cull_mode, (float4*)recs, tile_counts)
+    ts::bin_count_kernel<C><<<grid, ts::kBinThreads, 0, st>>>(N, (const float2*)xys, radii, conics, opacity, colors, tiles_x, tiles_y, cull_mode, flags, (float4*)recs, tile_counts)
     switch (CH) {
         case 1: TS_LAUNCH_COUNT(1); break;
         case 2: TS_LAUNCH_COUNT(2); break;

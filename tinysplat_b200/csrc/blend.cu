@@ -73,7 +73,8 @@ __global__ void __launch_bounds__(kBlendThreads)
 blend_fwd_kernel(int H, int W, int tbx, const int32_t* __restrict__ tile_offsets,
                  const int32_t* __restrict__ ids, const float4* __restrict__ recs,
                  const float* __restrict__ background, float* __restrict__ out_img,
-                 float* __restrict__ final_T, int32_t* __restrict__ n_contrib) {
+                 float* __restrict__ out_ch3, float* __restrict__ final_T,
+                 int32_t* __restrict__ n_contrib) {
     __shared__ __align__(16) float4 s_rec[2][kBatch * 3];
     __shared__ unsigned s_mask[8][8];  // [sub-block][staging warp]
     const unsigned full = 0xffffffffu;
@@ -157,8 +158,14 @@ blend_fwd_kernel(int H, int W, int tbx, const int32_t* __restrict__ tile_offsets
 
     if (pm.inside) {
         const size_t pix = (size_t)pm.i * W + pm.j;
+        if (CH == 4 && out_ch3) {   // split output: RGB image + separate 4th-channel (depth) map
 #pragma unroll
-        for (int c = 0; c < CH; ++c) out_img[pix * CH + c] = fmaf(T, __ldg(background + c), acc[c]);
+            for (int c = 0; c < 3; ++c) out_img[pix * 3 + c] = fmaf(T, __ldg(background + c), acc[c]);
+            out_ch3[pix] = fmaf(T, __ldg(background + 3), acc[CH - 1]);
+        } else {
+#pragma unroll
+            for (int c = 0; c < CH; ++c) out_img[pix * CH + c] = fmaf(T, __ldg(background + c), acc[c]);
+        }
         final_T[pix] = T;
         n_contrib[pix] = ncon;
     }
@@ -170,6 +177,7 @@ blend_bwd_kernel(int H, int W, int tbx, const int32_t* __restrict__ tile_offsets
                  const int32_t* __restrict__ ids, const float4* __restrict__ recs,
                  const float* __restrict__ background, const float* __restrict__ final_T,
                  const int32_t* __restrict__ n_contrib, const float* __restrict__ v_out_img,
+                 const float* __restrict__ v_out_ch3, int split_ch3,
                  const float* __restrict__ v_out_alpha, float4* __restrict__ grads) {
     constexpr int kSlotsUsed = 6 + CH;  // S_x S_y S_xx S_xy S_yy v_opac + colours
     // reduction slot s -> float offset inside the 12-float packed gradient record:
@@ -194,8 +202,14 @@ blend_bwd_kernel(int H, int W, int tbx, const int32_t* __restrict__ tile_offsets
         const size_t pix = (size_t)pm.i * W + pm.j;
         T_final = __ldg(final_T + pix);
         nc = __ldg(n_contrib + pix);
+        if (CH == 4 && split_ch3) {
 #pragma unroll
-        for (int c = 0; c < CH; ++c) v_out[c] = __ldg(v_out_img + pix * CH + c);
+            for (int c = 0; c < 3; ++c) v_out[c] = v_out_img ? __ldg(v_out_img + pix * 3 + c) : 0.f;
+            v_out[CH - 1] = v_out_ch3 ? __ldg(v_out_ch3 + pix) : 0.f;
+        } else {
+#pragma unroll
+            for (int c = 0; c < CH; ++c) v_out[c] = __ldg(v_out_img + pix * CH + c);
+        }
         if (v_out_alpha) v_oa = __ldg(v_out_alpha + pix);
     }
     float bgdot = 0.f;
@@ -376,15 +390,15 @@ extern "C" {
 
 int ts_blend_fwd(int CH, int img_height, int img_width, int tiles_x, int tiles_y,
                  const int32_t* tile_offsets, const int32_t* ids_sorted, const float* recs,
-                 const float* background, float* out_img, float* final_T, int32_t* n_contrib,
-                 ts_stream_t stream) {
+                 const float* background, float* out_img, float* out_ch3, float* final_T,
+                 int32_t* n_contrib, ts_stream_t stream) {
     if (CH < 1 || CH > 4 || img_height <= 0 || img_width <= 0 || tiles_x <= 0 || tiles_y <= 0) return TS_ERR_INVALID;
     if (!tile_offsets || !background || !out_img || !final_T || !n_contrib) return TS_ERR_INVALID;
     if (recs && !ts::aligned16(recs)) return TS_ERR_ALIGN;
     dim3 grid(tiles_x, tiles_y);
     cudaStream_t st = (cudaStream_t)stream;
 #define TS_LAUNCH_FWD(C) \
-    ts::blend_fwd_kernel<C><<<grid, ts::kBlendThreads, 0, st>>>(img_height, img_width, tiles_x, tile_offsets, ids_sorted, (const float4*)recs, background, out_img, final_T, n_contrib)
+    ts::blend_fwd_kernel<C><<<grid, ts::kBlendThreads, 0, st>>>(img_height, img_width, tiles_x, tile_offsets, ids_sorted, (const float4*)recs, background, out_img, out_ch3, final_T, n_contrib)
     switch (CH) {
         case 1: TS_LAUNCH_FWD(1); break;
         case 2: TS_LAUNCH_FWD(2); break;
@@ -399,17 +413,18 @@ int ts_blend_fwd(int CH, int img_height, int img_width, int tiles_x, int tiles_y
 int ts_blend_bwd(int N, int CH, int img_height, int img_width, int tiles_x, int tiles_y,
                  const int32_t* tile_offsets, const int32_t* ids_sorted, const float* recs,
                  const float* background, const float* final_T, const int32_t* n_contrib,
-                 const float* v_out_img, const float* v_out_alpha, float* grads,
-                 ts_stream_t stream) {
+                 const float* v_out_img, const float* v_out_ch3, int split_ch3,
+                 const float* v_out_alpha, float* grads, ts_stream_t stream) {
     if (N < 0 || CH < 1 || CH > 4 || img_height <= 0 || img_width <= 0 || tiles_x <= 0 || tiles_y <= 0) return TS_ERR_INVALID;
     if (N == 0) return TS_OK;
-    if (!tile_offsets || !background || !final_T || !n_contrib || !v_out_img || !grads) return TS_ERR_INVALID;
+    if (!tile_offsets || !background || !final_T || !n_contrib || !grads) return TS_ERR_INVALID;
+    if (!v_out_img && !(CH == 4 && split_ch3)) return TS_ERR_INVALID;
     if (!ts::aligned16(grads) || (recs && !ts::aligned16(recs))) return TS_ERR_ALIGN;
     cudaStream_t st = (cudaStream_t)stream;
     TS_CHECK_CUDA(cudaMemsetAsync(grads, 0, sizeof(float) * ts::kGradFloats * (size_t)N, st), "ts_blend_bwd/memset");
     dim3 grid(tiles_x, tiles_y);
 #define TS_LAUNCH_BWD(C) \
-    ts::blend_bwd_kernel<C><<<grid, ts::kBlendThreads, 0, st>>>(img_height, img_width, tiles_x, tile_offsets, ids_sorted, (const float4*)recs, background, final_T, n_contrib, v_out_img, v_out_alpha, (float4*)grads)
+    ts::blend_bwd_kernel<C><<<grid, ts::kBlendThreads, 0, st>>>(img_height, img_width, tiles_x, tile_offsets, ids_sorted, (const float4*)recs, background, final_T, n_contrib, v_out_img, v_out_ch3, split_ch3, v_out_alpha, (float4*)grads)
     switch (CH) {
         case 1: TS_LAUNCH_BWD(1); break;
         case 2: TS_LAUNCH_BWD(2); break;

@@ -20,6 +20,22 @@ __device__ __forceinline__ void load_cam(const float* __restrict__ viewmat,
     for (int i = 0; i < 16; ++i) c.P[i] = __ldg(projmat + i);
 }
 
+// The reference adapter feeds exp(log-scales) and quats/|quats| [REF rasterize.py:72-73]; the
+// fused pipeline folds those activations (and their Jacobians) into the kernels.
+__device__ __forceinline__ float apply_activations(int flags, float sc[3], float4& q) {
+    if (flags & TS_PROJ_LOG_SCALES) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) sc[k] = expf(sc[k]);
+    }
+    float qn = 1.f;
+    if (flags & TS_PROJ_RAW_QUATS) {
+        qn = sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
+        float inv = 1.f / qn;
+        q.x *= inv; q.y *= inv; q.z *= inv; q.w *= inv;
+    }
+    return qn;
+}
+
 // Everything forward computes that backward needs again (recomputed, not stored).
 struct ProjState {
     float t[3];
@@ -104,7 +120,7 @@ project_fwd_kernel(int N, const float* __restrict__ means, const float* __restri
                    float gs, const float4* __restrict__ quats,
                    const float* __restrict__ viewmat, const float* __restrict__ projmat,
                    float fx, float fy, float cx, float cy, int H, int W, int tbx, int tby,
-                   float clip, float2* __restrict__ xys, float* __restrict__ depths,
+                   float clip, int flags, float2* __restrict__ xys, float* __restrict__ depths,
                    int32_t* __restrict__ radii, float* __restrict__ conics,
                    int32_t* __restrict__ ntiles, float* __restrict__ cov3d) {
     constexpr int TH = kProjThreads;
@@ -126,6 +142,7 @@ project_fwd_kernel(int N, const float* __restrict__ means, const float* __restri
         }
         q = __ldg(quats + i);
     }
+    apply_activations(flags, sc, q);
     __syncthreads();  // inputs consumed; s_buf is reused for output staging
 
     ProjCam cam;
@@ -172,18 +189,20 @@ __global__ void __launch_bounds__(kProjThreads)
 project_bwd_kernel(int N, const float* __restrict__ means, const float* __restrict__ scales,
                    float gs, const float4* __restrict__ quats,
                    const float* __restrict__ viewmat, const float* __restrict__ projmat,
-                   float fx, float fy, float cx, float cy, int H, int W,
+                   float fx, float fy, float cx, float cy, int H, int W, int flags,
                    const int32_t* __restrict__ radii, const float2* __restrict__ v_xys,
                    const float* __restrict__ v_depths, const float* __restrict__ v_conics,
+                   const float4* __restrict__ packed, const float* __restrict__ opac_logits,
                    float* __restrict__ v_means, float* __restrict__ v_scales,
-                   float4* __restrict__ v_quats) {
+                   float4* __restrict__ v_quats, float* __restrict__ v_opac_logits,
+                   float2* __restrict__ v_xys_out) {
     constexpr int TH = kProjThreads;
     __shared__ __align__(16) float s_buf[TH * 9];
     const int item0 = blockIdx.x * TH;
     const int tid = threadIdx.x;
     block_load<3, TH>(means, s_buf, item0, N);
     block_load<3, TH>(scales, s_buf + 3 * TH, item0, N);
-    block_load<3, TH>(v_conics, s_buf + 6 * TH, item0, N);
+    if (v_conics) block_load<3, TH>(v_conics, s_buf + 6 * TH, item0, N);
     __syncthreads();
     const int i = item0 + tid;
     const bool in = i < N;
@@ -197,17 +216,19 @@ project_bwd_kernel(int N, const float* __restrict__ means, const float* __restri
         for (int k = 0; k < 3; ++k) {
             mu[k] = s_buf[3 * tid + k];
             sc[k] = s_buf[3 * TH + 3 * tid + k];
-            vcon[k] = s_buf[6 * TH + 3 * tid + k];
+            if (v_conics) vcon[k] = s_buf[6 * TH + 3 * tid + k];
         }
         q = __ldg(quats + i);
         ok = __ldg(radii + i) > 0;
-        vxy = __ldg(v_xys + i);
-        vdep = __ldg(v_depths + i);
+        if (v_xys) vxy = __ldg(v_xys + i);
+        if (v_depths) vdep = __ldg(v_depths + i);
     }
+    const float qn = apply_activations(flags, sc, q);
     __syncthreads();
 
     float vmu[3] = {0.f, 0.f, 0.f}, vs[3] = {0.f, 0.f, 0.f};
     float4 vq = make_float4(0.f, 0.f, 0.f, 0.f);
+    float vlogit = 0.f;
     if (ok) {
         ProjCam cam;
         load_cam(viewmat, projmat, cam);
@@ -215,6 +236,23 @@ project_bwd_kernel(int N, const float* __restrict__ means, const float* __restri
         project_core(cam, mu, sc, gs, q, fx, fy, H, W, -3.0e38f, st);  // radii>0 => passed the near clip
         const float* V = cam.V;
         const float* P = cam.P;
+        float inv = 1.f / st.det;
+        float A = st.c * inv, B = -st.b * inv, C = st.a * inv;   // the conic
+        if (packed) {
+            // blend-backward's packed record: S-sums -> cotangents of xy and conic; the fused
+            // pipeline's depth cotangent rides in colour channel 3; v_opacity in g1.y
+            float4 g0 = __ldg(packed + 3 * (size_t)i), g1 = __ldg(packed + 3 * (size_t)i + 1);
+            vxy.x += A * g0.x + B * g0.y;
+            vxy.y += B * g0.x + C * g0.y;
+            vcon[0] += 0.5f * g0.z;
+            vcon[1] += g0.w;
+            vcon[2] += 0.5f * g1.x;
+            if (flags & TS_PROJ_DEPTH_CH3) vdep += __ldg(reinterpret_cast<const float*>(packed) + 12 * (size_t)i + 11);
+            if (opac_logits) {
+                float o = 1.f / (1.f + expf(-__ldg(opac_logits + i)));
+                vlogit = g1.y * o * (1.f - o);
+            }
+        }
         // (1) pixel position
         float vndx = 0.5f * (float)W * vxy.x, vndy = 0.5f * (float)H * vxy.y;
         float vph0 = vndx * st.rw, vph1 = vndy * st.rw;
@@ -225,8 +263,6 @@ project_bwd_kernel(int N, const float* __restrict__ means, const float* __restri
 #pragma unroll
         for (int k = 0; k < 3; ++k) vmu[k] += V[8 + k] * vdep;
         // (3) conic -> cov2d
-        float inv = 1.f / st.det;
-        float A = st.c * inv, B = -st.b * inv, C = st.a * inv;
         float va = -A * A * vcon[0] - A * B * vcon[1] - B * B * vcon[2];
         float vb = -2.f * A * B * vcon[0] - (A * C + B * B) * vcon[1] - 2.f * B * C * vcon[2];
         float vc = -B * B * vcon[0] - B * C * vcon[1] - C * C * vcon[2];
@@ -280,13 +316,28 @@ project_bwd_kernel(int N, const float* __restrict__ means, const float* __restri
                       z * vR[7] - 2.f * y * vR[8]);
         vq.w = 2.f * (-2.f * z * vR[0] - w * vR[1] + x * vR[2] + w * vR[3] - 2.f * z * vR[4] +
                       y * vR[5] + x * vR[6] + y * vR[7]);
+        // activation Jacobians of the fused pipeline
+        if (flags & TS_PROJ_LOG_SCALES) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) vs[k] *= sc[k];           // d exp(l)/dl = exp(l)
+        }
+        if (flags & TS_PROJ_RAW_QUATS) {                           // q = r/|r|
+            float d = vq.x * q.x + vq.y * q.y + vq.z * q.z + vq.w * q.w;
+            float iq = 1.f / qn;
+            vq.x = (vq.x - d * q.x) * iq; vq.y = (vq.y - d * q.y) * iq;
+            vq.z = (vq.z - d * q.z) * iq; vq.w = (vq.w - d * q.w) * iq;
+        }
     }
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         s_buf[3 * tid + k] = vmu[k];
         s_buf[3 * TH + 3 * tid + k] = vs[k];
     }
-    if (in) v_quats[i] = vq;
+    if (in) {
+        v_quats[i] = vq;
+        if (v_opac_logits) v_opac_logits[i] = vlogit;
+        if (v_xys_out) v_xys_out[i] = ok ? vxy : make_float2(0.f, 0.f);
+    }
     __syncthreads();
     block_store<3, TH>(v_means, s_buf, item0, N);
     block_store<3, TH>(v_scales, s_buf + 3 * TH, item0, N);
@@ -299,8 +350,9 @@ extern "C" {
 int ts_project_fwd(int N, const float* means3d, const float* scales, float glob_scale,
                    const float* quats, const float* viewmat, const float* projmat, float fx,
                    float fy, float cx, float cy, int img_height, int img_width, int tiles_x,
-                   int tiles_y, float clip_thresh, float* xys, float* depths, int32_t* radii,
-                   float* conics, int32_t* num_tiles_hit, float* cov3d, ts_stream_t stream) {
+                   int tiles_y, float clip_thresh, int flags, float* xys, float* depths,
+                   int32_t* radii, float* conics, int32_t* num_tiles_hit, float* cov3d,
+                   ts_stream_t stream) {
     if (N < 0 || img_height <= 0 || img_width <= 0 || tiles_x <= 0 || tiles_y <= 0) return TS_ERR_INVALID;
     if (N == 0) return TS_OK;
     if (!means3d || !scales || !quats || !viewmat || !projmat || !xys || !depths || !radii ||
@@ -312,32 +364,36 @@ int ts_project_fwd(int N, const float* means3d, const float* scales, float glob_
     int grid = (N + ts::kProjThreads - 1) / ts::kProjThreads;
     ts::project_fwd_kernel<<<grid, ts::kProjThreads, 0, (cudaStream_t)stream>>>(
         N, means3d, scales, glob_scale, (const float4*)quats, viewmat, projmat, fx, fy, cx, cy,
-        img_height, img_width, tiles_x, tiles_y, clip_thresh, (float2*)xys, depths, radii, conics,
-        num_tiles_hit, cov3d);
+        img_height, img_width, tiles_x, tiles_y, clip_thresh, flags, (float2*)xys, depths, radii,
+        conics, num_tiles_hit, cov3d);
     TS_CHECK_LAUNCH("ts_project_fwd");
     return TS_OK;
 }
 
 int ts_project_bwd(int N, const float* means3d, const float* scales, float glob_scale,
                    const float* quats, const float* viewmat, const float* projmat, float fx,
-                   float fy, float cx, float cy, int img_height, int img_width,
+                   float fy, float cx, float cy, int img_height, int img_width, int flags,
                    const int32_t* radii, const float* v_xys, const float* v_depths,
-                   const float* v_conics, float* v_means3d, float* v_scales, float* v_quats,
-                   ts_stream_t stream) {
+                   const float* v_conics, const float* packed_grads, const float* opacity_logits,
+                   float* v_means3d, float* v_scales, float* v_quats, float* v_opacity_logits,
+                   float* v_xys_out, ts_stream_t stream) {
     if (N < 0 || img_height <= 0 || img_width <= 0) return TS_ERR_INVALID;
     if (N == 0) return TS_OK;
-    if (!means3d || !scales || !quats || !viewmat || !projmat || !radii || !v_xys || !v_depths ||
-        !v_conics || !v_means3d || !v_scales || !v_quats)
+    if (!means3d || !scales || !quats || !viewmat || !projmat || !radii || !v_means3d || !v_scales ||
+        !v_quats)
         return TS_ERR_INVALID;
     if (!ts::aligned16(means3d) || !ts::aligned16(scales) || !ts::aligned16(quats) ||
-        !ts::aligned16(v_xys) || !ts::aligned16(v_conics) || !ts::aligned16(v_means3d) ||
-        !ts::aligned16(v_scales) || !ts::aligned16(v_quats))
+        (v_conics && !ts::aligned16(v_conics)) || (packed_grads && !ts::aligned16(packed_grads)) ||
+        !ts::aligned16(v_means3d) || !ts::aligned16(v_scales) || !ts::aligned16(v_quats) ||
+        (v_xys && (reinterpret_cast<uintptr_t>(v_xys) & 7u)) ||
+        (v_xys_out && (reinterpret_cast<uintptr_t>(v_xys_out) & 7u)))
         return TS_ERR_ALIGN;
     int grid = (N + ts::kProjThreads - 1) / ts::kProjThreads;
     ts::project_bwd_kernel<<<grid, ts::kProjThreads, 0, (cudaStream_t)stream>>>(
         N, means3d, scales, glob_scale, (const float4*)quats, viewmat, projmat, fx, fy, cx, cy,
-        img_height, img_width, radii, (const float2*)v_xys, v_depths, v_conics, v_means3d,
-        v_scales, (float4*)v_quats);
+        img_height, img_width, flags, radii, (const float2*)v_xys, v_depths, v_conics,
+        (const float4*)packed_grads, opacity_logits, v_means3d, v_scales, (float4*)v_quats,
+        v_opacity_logits, (float2*)v_xys_out);
     TS_CHECK_LAUNCH("ts_project_bwd");
     return TS_OK;
 }

@@ -95,10 +95,23 @@ __device__ __forceinline__ void smem_to_rows(float* __restrict__ g, int row, con
     }
 }
 
+// Unit view direction of item `tid`: either given, or derived from the mean and the view
+// matrix' translation column exactly as the reference adapter does [REF rasterize.py:77-79].
+__device__ __forceinline__ void load_dir(const float* s_dir, int tid, int flags,
+                                         const float* __restrict__ viewmat, float& dx, float& dy,
+                                         float& dz) {
+    dx = s_dir[3 * tid]; dy = s_dir[3 * tid + 1]; dz = s_dir[3 * tid + 2];
+    if (flags & TS_SH_DIRS_FROM_MEANS) {
+        dx -= __ldg(viewmat + 3); dy -= __ldg(viewmat + 7); dz -= __ldg(viewmat + 11);
+    }
+}
+
 template <int DEG>
 __global__ void __launch_bounds__(kShThreads)
-sh_fwd_kernel(int N, int K, const float* __restrict__ dirs, const float* __restrict__ coeffs,
-              const float* __restrict__ coeffs_rest, float* __restrict__ colors, int sstride) {
+sh_fwd_kernel(int N, int K, const float* __restrict__ dirs, const float* __restrict__ viewmat,
+              const float* __restrict__ coeffs, const float* __restrict__ coeffs_rest,
+              float* __restrict__ colors, int out_stride, const float* __restrict__ ch3,
+              uint8_t* __restrict__ clamp_mask, int flags, int sstride) {
     extern __shared__ __align__(16) float s_sh[];
     constexpr int NB = (DEG + 1) * (DEG + 1);
     float* s_dir = s_sh;                        // [TH*3], reused for the colour output
@@ -117,7 +130,9 @@ sh_fwd_kernel(int N, int K, const float* __restrict__ dirs, const float* __restr
     float r = 0.f, g = 0.f, bl = 0.f;
     if (tid < n_valid) {
         float b[NB];
-        sh_basis<DEG>(s_dir[3 * tid], s_dir[3 * tid + 1], s_dir[3 * tid + 2], b);
+        float dx, dy, dz;
+        load_dir(s_dir, tid, flags, viewmat, dx, dy, dz);
+        sh_basis<DEG>(dx, dy, dz, b);
         const float* c = s_co + tid * sstride;
 #pragma unroll
         for (int k = 0; k < NB; ++k) {
@@ -125,17 +140,38 @@ sh_fwd_kernel(int N, int K, const float* __restrict__ dirs, const float* __restr
             g = fmaf(b[k], c[3 * k + 1], g);
             bl = fmaf(b[k], c[3 * k + 2], bl);
         }
+        if (flags & TS_SH_OFFSET_CLAMP) {   // clamp(rgb + 0.5, min=0) [REF rasterize.py:39]
+            r += 0.5f; g += 0.5f; bl += 0.5f;
+            unsigned m = (r >= 0.f ? 1u : 0u) | (g >= 0.f ? 2u : 0u) | (bl >= 0.f ? 4u : 0u);
+            r = fmaxf(r, 0.f); g = fmaxf(g, 0.f); bl = fmaxf(bl, 0.f);
+            if (clamp_mask) clamp_mask[item0 + tid] = (uint8_t)m;
+        }
     }
-    __syncthreads();
-    s_dir[3 * tid] = r; s_dir[3 * tid + 1] = g; s_dir[3 * tid + 2] = bl;
-    __syncthreads();
-    block_store<3, kShThreads>(colors, s_dir, item0, N);
+    if (out_stride == 3) {
+        __syncthreads();
+        s_dir[3 * tid] = r; s_dir[3 * tid + 1] = g; s_dir[3 * tid + 2] = bl;
+        __syncthreads();
+        block_store<3, kShThreads>(colors, s_dir, item0, N);
+    } else if (tid < n_valid) {
+        // strided output (e.g. straight into the third float4 of the packed raster record);
+        // channel 3 carries `ch3` (the depth, in the fused RGB+depth pass)
+        float* o = colors + (size_t)out_stride * (item0 + tid);
+        float d = ch3 ? __ldg(ch3 + item0 + tid) : 0.f;
+        if ((out_stride & 3) == 0 && aligned_dev16(colors)) {
+            *reinterpret_cast<float4*>(o) = make_float4(r, g, bl, d);
+        } else {
+            o[0] = r; o[1] = g; o[2] = bl;
+            if (ch3) o[3] = d;
+        }
+    }
 }
 
 template <int DEG>
 __global__ void __launch_bounds__(kShThreads)
-sh_bwd_kernel(int N, int K, const float* __restrict__ dirs, const float* __restrict__ v_colors,
-              float* __restrict__ v_coeffs, float* __restrict__ v_coeffs_rest, int sstride) {
+sh_bwd_kernel(int N, int K, const float* __restrict__ dirs, const float* __restrict__ viewmat,
+              const float* __restrict__ v_colors, int v_stride,
+              const uint8_t* __restrict__ clamp_mask, float* __restrict__ v_coeffs,
+              float* __restrict__ v_coeffs_rest, int flags, int sstride) {
     extern __shared__ __align__(16) float s_sh[];
     constexpr int NB = (DEG + 1) * (DEG + 1);
     float* s_dir = s_sh;                          // [TH*3]
@@ -145,12 +181,31 @@ sh_bwd_kernel(int N, int K, const float* __restrict__ dirs, const float* __restr
     const int n_valid = min(kShThreads, N - item0);
     const int tid = threadIdx.x;
     block_load<3, kShThreads>(dirs, s_dir, item0, N);
-    block_load<3, kShThreads>(v_colors, s_vc, item0, N);
+    if (v_stride == 3) block_load<3, kShThreads>(v_colors, s_vc, item0, N);
     __syncthreads();
     if (tid < n_valid) {
         float b[NB];
-        sh_basis<DEG>(s_dir[3 * tid], s_dir[3 * tid + 1], s_dir[3 * tid + 2], b);
-        float vr = s_vc[3 * tid], vg = s_vc[3 * tid + 1], vb = s_vc[3 * tid + 2];
+        float dx, dy, dz;
+        load_dir(s_dir, tid, flags, viewmat, dx, dy, dz);
+        sh_basis<DEG>(dx, dy, dz, b);
+        float vr, vg, vb;
+        if (v_stride == 3) {
+            vr = s_vc[3 * tid]; vg = s_vc[3 * tid + 1]; vb = s_vc[3 * tid + 2];
+        } else {
+            const float* v = v_colors + (size_t)v_stride * (item0 + tid);
+            if ((v_stride & 3) == 0 && aligned_dev16(v_colors)) {
+                float4 t = __ldg(reinterpret_cast<const float4*>(v));
+                vr = t.x; vg = t.y; vb = t.z;
+            } else {
+                vr = __ldg(v); vg = __ldg(v + 1); vb = __ldg(v + 2);
+            }
+        }
+        if (clamp_mask) {
+            unsigned m = clamp_mask[item0 + tid];
+            if (!(m & 1u)) vr = 0.f;
+            if (!(m & 2u)) vg = 0.f;
+            if (!(m & 4u)) vb = 0.f;
+        }
         float* c = s_co + tid * sstride;
 #pragma unroll
         for (int k = 0; k < NB; ++k) {
@@ -175,11 +230,14 @@ static inline int sh_stride(int K) { int k3 = K * 3; return (k3 & 1) ? k3 : k3 +
 
 extern "C" {
 
-int ts_sh_fwd(int N, int degree, int K, const float* dirs, const float* coeffs,
-              const float* coeffs_rest, float* colors, ts_stream_t stream) {
-    if (N < 0 || degree < 0 || degree > 4 || K < (degree + 1) * (degree + 1) || K > 25) return TS_ERR_INVALID;
+int ts_sh_fwd(int N, int degree, int K, const float* dirs, const float* viewmat, const float* coeffs,
+              const float* coeffs_rest, float* colors, int out_stride, const float* ch3,
+              uint8_t* clamp_mask, int flags, ts_stream_t stream) {
+    if (N < 0 || degree < 0 || degree > 4 || K < (degree + 1) * (degree + 1) || K > 25 || out_stride < 3)
+        return TS_ERR_INVALID;
     if (N == 0) return TS_OK;
     if (!dirs || !coeffs || !colors) return TS_ERR_INVALID;
+    if ((flags & TS_SH_DIRS_FROM_MEANS) && !viewmat) return TS_ERR_INVALID;
     if (!ts::aligned16(dirs) || !ts::aligned16(colors) || !ts::aligned16(coeffs) ||
         (coeffs_rest && !ts::aligned16(coeffs_rest)))
         return TS_ERR_ALIGN;
@@ -188,7 +246,7 @@ int ts_sh_fwd(int N, int degree, int K, const float* dirs, const float* coeffs,
     int grid = (N + ts::kShThreads - 1) / ts::kShThreads;
     cudaStream_t st = (cudaStream_t)stream;
 #define TS_LAUNCH_SH_FWD(D) \
-    ts::sh_fwd_kernel<D><<<grid, ts::kShThreads, smem, st>>>(N, K, dirs, coeffs, coeffs_rest, colors, sstride)
+    ts::sh_fwd_kernel<D><<<grid, ts::kShThreads, smem, st>>>(N, K, dirs, viewmat, coeffs, coeffs_rest, colors, out_stride, ch3, clamp_mask, flags, sstride)
     switch (degree) {
         case 0: TS_LAUNCH_SH_FWD(0); break;
         case 1: TS_LAUNCH_SH_FWD(1); break;
@@ -201,11 +259,14 @@ int ts_sh_fwd(int N, int degree, int K, const float* dirs, const float* coeffs,
     return TS_OK;
 }
 
-int ts_sh_bwd(int N, int degree, int K, const float* dirs, const float* v_colors,
-              float* v_coeffs, float* v_coeffs_rest, ts_stream_t stream) {
-    if (N < 0 || degree < 0 || degree > 4 || K < (degree + 1) * (degree + 1) || K > 25) return TS_ERR_INVALID;
+int ts_sh_bwd(int N, int degree, int K, const float* dirs, const float* viewmat, const float* v_colors,
+              int v_stride, const uint8_t* clamp_mask, float* v_coeffs, float* v_coeffs_rest, int flags,
+              ts_stream_t stream) {
+    if (N < 0 || degree < 0 || degree > 4 || K < (degree + 1) * (degree + 1) || K > 25 || v_stride < 3)
+        return TS_ERR_INVALID;
     if (N == 0) return TS_OK;
     if (!dirs || !v_colors || !v_coeffs) return TS_ERR_INVALID;
+    if ((flags & TS_SH_DIRS_FROM_MEANS) && !viewmat) return TS_ERR_INVALID;
     if (!ts::aligned16(dirs) || !ts::aligned16(v_colors) || !ts::aligned16(v_coeffs) ||
         (v_coeffs_rest && !ts::aligned16(v_coeffs_rest)))
         return TS_ERR_ALIGN;
@@ -214,7 +275,7 @@ int ts_sh_bwd(int N, int degree, int K, const float* dirs, const float* v_colors
     int grid = (N + ts::kShThreads - 1) / ts::kShThreads;
     cudaStream_t st = (cudaStream_t)stream;
 #define TS_LAUNCH_SH_BWD(D) \
-    ts::sh_bwd_kernel<D><<<grid, ts::kShThreads, smem, st>>>(N, K, dirs, v_colors, v_coeffs, v_coeffs_rest, sstride)
+    ts::sh_bwd_kernel<D><<<grid, ts::kShThreads, smem, st>>>(N, K, dirs, viewmat, v_colors, v_stride, clamp_mask, v_coeffs, v_coeffs_rest, flags, sstride)
     switch (degree) {
         case 0: TS_LAUNCH_SH_BWD(0); break;
         case 1: TS_LAUNCH_SH_BWD(1); break;

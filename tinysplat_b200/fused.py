@@ -1,0 +1,187 @@
+"""One autograd node for the whole raster adapter  [REF tinysplat/splatting/rasterize.py:26-62].
+
+The reference's host code issues ~25 small torch ops around the three gsplat calls (exp,
+normalise, sigmoid, view-direction arithmetic, +0.5/clamp, cat, repeat ...), each with its own
+backward kernels; on a B200 the step is then bound by CPU launch overhead, not by the GPU.
+Here every one of those activations is folded into the sm_100a kernels (flags of the C ABI),
+SH colour is written straight into the packed raster record, RGB and depth share one
+4-channel blend pass, and blend-backward's packed gradients are consumed directly by
+projection-backward and SH-backward.  Forward = 7-8 launches, backward = 3 + one memset.
+
+The single device->host read (3 ints: intersection count, max list length, oversize tiles) is
+issued right after the tile scan and hidden behind the SH kernel: the host waits on an event
+while the GPU still has SH work queued, then launches emit/sort/blend before the GPU drains.
+"""
+from __future__ import annotations
+
+import weakref
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+from torch.autograd import Function
+
+from . import _lib
+from . import rasterize as _rz
+
+BLOCK = 16
+_pinned_stats = {}
+
+
+def _stats_buffer(dev) -> Tensor:
+    key = str(dev)
+    if key not in _pinned_stats:
+        _pinned_stats[key] = torch.empty(4, dtype=torch.int32).pin_memory()
+    return _pinned_stats[key]
+
+
+class XysSink:
+    """Receives d loss / d xy from the fused node's backward and exposes it the way the
+    reference reads it: `extras['xys'].grad.norm(dim=-1)`  [REF model_gaussian.py:130-132]."""
+    __slots__ = ("ref",)
+
+    def __init__(self):
+        self.ref = None
+
+    def attach(self, xys: Tensor) -> None:
+        self.ref = weakref.ref(xys)
+
+    def deliver(self, v_xys: Tensor) -> None:
+        t = self.ref() if self.ref is not None else None
+        if t is not None:
+            t.grad = v_xys if t.grad is None else t.grad + v_xys
+
+
+class _RenderFused(Function):
+    @staticmethod
+    def forward(ctx, means, log_scales, quats, opac_logits, colors_dc, colors_rest, view_dev,
+                fullproj_dev, fx, fy, width, height, sh_degree, bg4, cull_mode, sink):
+        _lib.require_cuda(means, log_scales, quats, opac_logits, colors_dc, colors_rest)
+        lib = _lib.load()
+        dev = means.device
+        st = _lib.stream_ptr(dev)
+        N = means.shape[0]
+        W, H = int(width), int(height)
+        tx, ty = -(-W // BLOCK), -(-H // BLOCK)
+        T = tx * ty
+        K = colors_rest.shape[1] + 1
+        f32 = dict(device=dev, dtype=torch.float32)
+        i32 = dict(device=dev, dtype=torch.int32)
+        means_c, scales_c, quats_c = (_lib.f32c(t.detach()) for t in (means, log_scales, quats))
+        logit_c = _lib.f32c(opac_logits.detach()).reshape(-1)
+        dc_c, rest_c = _lib.f32c(colors_dc.detach()), _lib.f32c(colors_rest.detach())
+        view_c, proj_c, bg_c = _lib.f32c(view_dev), _lib.f32c(fullproj_dev), _lib.f32c(bg4)
+        pflags = _lib.PROJ_LOG_SCALES | _lib.PROJ_RAW_QUATS
+        sflags = _lib.SH_DIRS_FROM_MEANS | _lib.SH_OFFSET_CLAMP
+
+        xys = torch.empty(N, 2, **f32)
+        depths = torch.empty(N, **f32)
+        radii = torch.empty(N, **i32)
+        conics = torch.empty(N, 3, **f32)
+        ntiles = torch.empty(N, **i32)
+        cov3d = torch.empty(N, 6, **f32)
+        _lib.call("ts_project_fwd", N, _lib.ptr(means_c), _lib.ptr(scales_c), 1.0, _lib.ptr(quats_c),
+                  _lib.ptr(view_c), _lib.ptr(proj_c), float(fx), float(fy), W / 2, H / 2, H, W, tx, ty,
+                  0.01, pflags, _lib.ptr(xys), _lib.ptr(depths), _lib.ptr(radii), _lib.ptr(conics),
+                  _lib.ptr(ntiles), _lib.ptr(cov3d), st)
+        recs = torch.empty(N, lib.ts_rec_floats(), **f32)
+        counts = torch.empty(T, **i32)
+        _lib.call("ts_bin_count", N, 4, _lib.ptr(xys), _lib.ptr(depths), _lib.ptr(radii), _lib.ptr(conics),
+                  _lib.ptr(logit_c), None, H, W, tx, ty, int(cull_mode), _lib.BIN_OPACITY_LOGIT,
+                  _lib.ptr(recs), _lib.ptr(counts), st)
+        offsets = torch.empty(T + 1, **i32)
+        stats = torch.empty(4, **i32)
+        _lib.call("ts_bin_scan", T, _lib.ptr(counts), _lib.ptr(offsets), _lib.ptr(stats),
+                  lib.ts_bin_smem_sort_cap(), st)
+        host = _stats_buffer(dev)
+        host.copy_(stats, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        # SH (independent of the bins) keeps the GPU busy while the host waits for the 3 ints
+        mask = torch.empty(N, device=dev, dtype=torch.uint8)
+        _lib.call("ts_sh_fwd", N, int(sh_degree), K, _lib.ptr(means_c), _lib.ptr(view_c), _lib.ptr(dc_c),
+                  _lib.ptr(rest_c), recs.data_ptr() + 32, 12, _lib.ptr(depths), _lib.ptr(mask), sflags, st)
+        ev.synchronize()
+        M, max_count, n_big, _ = host.tolist()
+        keys = torch.empty(max(M, 1), device=dev, dtype=torch.int64)
+        ids_sorted = torch.empty(max(M, 1), **i32)
+        if M > 0:
+            _lib.call("ts_bin_emit", N, _lib.ptr(depths), _lib.ptr(radii), _lib.ptr(recs), tx, ty,
+                      int(cull_mode), _lib.ptr(offsets), _lib.ptr(counts), _lib.ptr(keys), st)
+            big_scratch = big_counter = None
+            if n_big > 0:
+                P = 1 << (max_count - 1).bit_length()
+                big_scratch = torch.empty(n_big * P, device=dev, dtype=torch.int64)
+                big_counter = torch.empty(1, **i32)
+            _lib.call("ts_bin_sort", T, _lib.ptr(offsets), _lib.ptr(keys), _lib.ptr(ids_sorted), max_count,
+                      n_big, _lib.ptr(big_scratch), _lib.ptr(big_counter), st)
+        _rz.last_stats.update(num_intersects=M, max_per_tile=max_count, bins_reused=False)
+        rgb = torch.empty(H, W, 3, **f32)
+        depth_img = torch.empty(H, W, **f32)
+        final_T = torch.empty(H, W, **f32)
+        n_contrib = torch.empty(H, W, **i32)
+        _lib.call("ts_blend_fwd", 4, H, W, tx, ty, _lib.ptr(offsets), _lib.ptr(ids_sorted), _lib.ptr(recs),
+                  _lib.ptr(bg_c), _lib.ptr(rgb), _lib.ptr(depth_img), _lib.ptr(final_T), _lib.ptr(n_contrib), st)
+        ctx.save_for_backward(means_c, scales_c, quats_c, logit_c, view_c, proj_c, bg_c, radii, recs,
+                              offsets, ids_sorted, final_T, n_contrib, mask)
+        ctx.meta = (N, K, W, H, tx, ty, float(fx), float(fy), int(sh_degree), pflags, sflags,
+                    tuple(opac_logits.shape), tuple(colors_dc.shape))
+        ctx.sink = sink
+        ctx.mark_non_differentiable(xys, depths, radii)
+        return rgb, depth_img, 1.0 - final_T, xys, depths, radii
+
+    @staticmethod
+    def backward(ctx, v_rgb, v_depth, v_alpha, _vx, _vd, _vr):
+        (means_c, scales_c, quats_c, logit_c, view_c, proj_c, bg_c, radii, recs, offsets, ids_sorted,
+         final_T, n_contrib, mask) = ctx.saved_tensors
+        N, K, W, H, tx, ty, fx, fy, deg, pflags, sflags, opac_shape, dc_shape = ctx.meta
+        lib = _lib.load()
+        dev = means_c.device
+        st = _lib.stream_ptr(dev)
+        f32 = dict(device=dev, dtype=torch.float32)
+        v_rgb = _lib.f32c(v_rgb) if v_rgb is not None else None
+        v_depth = _lib.f32c(v_depth) if v_depth is not None else None
+        v_alpha = _lib.f32c(v_alpha) if v_alpha is not None else None
+        grads = torch.empty(N, lib.ts_grad_floats(), **f32)
+        _lib.call("ts_blend_bwd", N, 4, H, W, tx, ty, _lib.ptr(offsets), _lib.ptr(ids_sorted), _lib.ptr(recs),
+                  _lib.ptr(bg_c), _lib.ptr(final_T), _lib.ptr(n_contrib), _lib.ptr(v_rgb), _lib.ptr(v_depth), 1,
+                  _lib.ptr(v_alpha), _lib.ptr(grads), st)
+        # colours first: the largest gradient (colors_rest) becomes available for its all-reduce
+        # while projection-backward is still running (parallel.py)
+        v_dc = torch.empty(N, 1, 3, **f32)
+        v_rest = torch.empty(N, K - 1, 3, **f32)
+        _lib.call("ts_sh_bwd", N, deg, K, _lib.ptr(means_c), _lib.ptr(view_c), grads.data_ptr() + 32, 12,
+                  _lib.ptr(mask), _lib.ptr(v_dc), _lib.ptr(v_rest), sflags, st)
+        v_means = torch.empty(N, 3, **f32)
+        v_scales = torch.empty(N, 3, **f32)
+        v_quats = torch.empty(N, 4, **f32)
+        v_logit = torch.empty(N, **f32)
+        v_xys = torch.empty(N, 2, **f32)
+        _lib.call("ts_project_bwd", N, _lib.ptr(means_c), _lib.ptr(scales_c), 1.0, _lib.ptr(quats_c),
+                  _lib.ptr(view_c), _lib.ptr(proj_c), fx, fy, W / 2, H / 2, H, W,
+                  pflags | _lib.PROJ_DEPTH_CH3, _lib.ptr(radii), None, None, None, _lib.ptr(grads),
+                  _lib.ptr(logit_c), _lib.ptr(v_means), _lib.ptr(v_scales), _lib.ptr(v_quats),
+                  _lib.ptr(v_logit), _lib.ptr(v_xys), st)
+        if ctx.sink is not None:
+            ctx.sink.deliver(v_xys)
+        return (v_means, v_scales, v_quats, v_logit.reshape(opac_shape), v_dc.reshape(dc_shape), v_rest,
+                None, None, None, None, None, None, None, None, None, None)
+
+
+def render_fused(means: Tensor, log_scales: Tensor, quats: Tensor, opacity_logits: Tensor,
+                 colors_dc: Tensor, colors_rest: Tensor, view_matrix: Tensor, full_proj: Tensor,
+                 fx: float, fy: float, width: int, height: int, sh_degree: int, background: Tensor,
+                 cull_mode: int = 1) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """Fused equivalent of project -> SH(+0.5, clamp) -> rasterise RGB -> rasterise depth.
+
+    Inputs are the raw GaussianModel parameters [REF model_gaussian.py:84-89] and DEVICE camera
+    matrices (view 4x4, full projection 4x4).  Returns (rgb[H,W,3] unclamped, depth[H,W],
+    alpha[H,W], xys[N,2], depths[N], radii[N]).  `xys.grad` is populated by backward."""
+    sink = XysSink()
+    bg = background.to(means.device).float()
+    bg4 = torch.cat([bg, bg[:1]])       # depth is composited over background[0] [REF rasterize.py:48-51]
+    out = _RenderFused.apply(means, log_scales, quats, opacity_logits, colors_dc, colors_rest,
+                             view_matrix, full_proj, fx, fy, width, height, sh_degree, bg4,
+                             cull_mode, sink)
+    sink.attach(out[3])
+    return out

@@ -37,7 +37,7 @@ class _ProjectGaussians(Function):
                 int(img_width))
         _lib.call("ts_project_fwd", N, _lib.ptr(means_c), _lib.ptr(scales_c), args[0], _lib.ptr(quats_c),
             _lib.ptr(view_c), _lib.ptr(proj_c), args[1], args[2], args[3], args[4], args[5], args[6],
-            int(tile_bounds[0]), int(tile_bounds[1]), float(clip_thresh),
+            int(tile_bounds[0]), int(tile_bounds[1]), float(clip_thresh), 0,
             _lib.ptr(xys), _lib.ptr(depths), _lib.ptr(radii), _lib.ptr(conics),
             _lib.ptr(num_tiles_hit), _lib.ptr(cov3d), _lib.stream_ptr(dev))
         ctx.save_for_backward(means_c, scales_c, quats_c, view_c, proj_c, radii)
@@ -52,17 +52,16 @@ class _ProjectGaussians(Function):
         lib = _lib.load()
         dev = means_c.device
         N = means_c.shape[0]
-        zeros = lambda *s: torch.zeros(*s, device=dev, dtype=torch.float32)
-        v_xys = _lib.f32c(v_xys) if v_xys is not None else zeros(N, 2)
-        v_depths = _lib.f32c(v_depths) if v_depths is not None else zeros(N)
-        v_conics = _lib.f32c(v_conics) if v_conics is not None else zeros(N, 3)
+        v_xys = _lib.f32c(v_xys) if v_xys is not None else None
+        v_depths = _lib.f32c(v_depths) if v_depths is not None else None
+        v_conics = _lib.f32c(v_conics) if v_conics is not None else None
         v_means = torch.empty(N, 3, device=dev, dtype=torch.float32)
         v_scales = torch.empty(N, 3, device=dev, dtype=torch.float32)
         v_quats = torch.empty(N, 4, device=dev, dtype=torch.float32)
         _lib.call("ts_project_bwd", N, _lib.ptr(means_c), _lib.ptr(scales_c), gs, _lib.ptr(quats_c), _lib.ptr(view_c),
-            _lib.ptr(proj_c), fx, fy, cx, cy, H, W, _lib.ptr(radii), _lib.ptr(v_xys),
-            _lib.ptr(v_depths), _lib.ptr(v_conics), _lib.ptr(v_means), _lib.ptr(v_scales),
-            _lib.ptr(v_quats), _lib.stream_ptr(dev))
+            _lib.ptr(proj_c), fx, fy, cx, cy, H, W, 0, _lib.ptr(radii), _lib.ptr(v_xys),
+            _lib.ptr(v_depths), _lib.ptr(v_conics), None, None, _lib.ptr(v_means), _lib.ptr(v_scales),
+            _lib.ptr(v_quats), None, None, _lib.stream_ptr(dev))
         return (v_means, v_scales, None, v_quats) + (None,) * 10
 
 

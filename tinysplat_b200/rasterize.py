@@ -53,7 +53,7 @@ def pack_and_bin(xys, depths, radii, conics, opacity, colors, H, W, cull_mode=1,
     counts = torch.empty(T, device=dev, dtype=torch.int32)
     _lib.call("ts_bin_count", N, CH, _lib.ptr(xys), _lib.ptr(depths), _lib.ptr(radii),
                                 _lib.ptr(conics), _lib.ptr(opacity), _lib.ptr(colors), H, W, tx, ty,
-                                cull_mode, _lib.ptr(recs), _lib.ptr(counts), st)
+              cull_mode, 0, _lib.ptr(recs), _lib.ptr(counts), st)
     key = _bins_key(xys, depths, radii, conics, opacity, H, W, cull_mode)
     if reuse and _last_bins is not None and _last_bins.key == key:
         last_stats["bins_reused"] = True
@@ -114,8 +114,8 @@ class _RasterizeGaussians(Function):
         n_contrib = torch.empty(H, W, device=dev, dtype=torch.int32)
         _lib.call("ts_blend_fwd", CH, H, W, tx, ty, _lib.ptr(bins.tile_offsets),
                                     _lib.ptr(bins.ids_sorted), _lib.ptr(recs), _lib.ptr(bg),
-                                    _lib.ptr(out_img), _lib.ptr(final_T), _lib.ptr(n_contrib),
-                                    _lib.stream_ptr(dev))
+                  _lib.ptr(out_img), None, _lib.ptr(final_T), _lib.ptr(n_contrib),
+                  _lib.stream_ptr(dev))
         out_alpha = 1.0 - final_T
         ctx.save_for_backward(recs, bins.tile_offsets, bins.ids_sorted, bg, final_T, n_contrib,
                               radii_c, conics_c)
@@ -135,8 +135,8 @@ class _RasterizeGaussians(Function):
         grads = torch.empty(N, lib.ts_grad_floats(), device=dev, dtype=torch.float32)
         _lib.call("ts_blend_bwd", N, CH, H, W, tx, ty, _lib.ptr(offsets), _lib.ptr(ids_sorted),
                                     _lib.ptr(recs), _lib.ptr(bg), _lib.ptr(final_T),
-                                    _lib.ptr(n_contrib), _lib.ptr(v_img), _lib.ptr(v_alpha),
-                                    _lib.ptr(grads), st)
+                                    _lib.ptr(n_contrib), _lib.ptr(v_img), None, 0, _lib.ptr(v_alpha),
+                  _lib.ptr(grads), st)
         v_xys = torch.empty(N, 2, device=dev, dtype=torch.float32)
         v_conics = torch.empty(N, 3, device=dev, dtype=torch.float32)
         v_colors = torch.empty(N, CH, device=dev, dtype=torch.float32)

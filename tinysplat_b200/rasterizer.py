@@ -10,9 +10,12 @@ tinysplat.splatting.rasterize.GaussianRasterizer  [REF tinysplat/splatting/raste
 Two pipelines over the same kernels:
   * "reference": the reference's exact op sequence through the five gsplat symbols —
     project, SH on concatenated coefficients, rasterise RGB, rasterise depth-as-colour.
-  * "fused" (default): one 4-channel rasterise (RGB + depth share binning, sort and the blend
-    pass) and SH evaluated on the (dc, rest) pair without the per-step
-    concatenation.  Same numbers, about half the raster work.
+  * "fused" (default): ONE autograd node (tinysplat_b200.fused.render_fused): the adapter's
+    torch-side activations are folded into the kernels, RGB + depth share binning, sort and one
+    4-channel blend pass, SH reads the (dc, rest) pair without the per-step
+    concatenation.  Same numbers; ~11 kernel launches per forward+backward instead of ~70.
+  * "unfused4": the previous composition of the five public ops with a 4-channel rasterise
+    (kept as a parity cross-check of the fused node).
 """
 from __future__ import annotations
 
@@ -21,6 +24,7 @@ from typing import Dict, Optional, Sequence, Tuple
 import torch
 from torch import Tensor
 
+from .fused import render_fused
 from .project import project_gaussians
 from .rasterize import rasterize_gaussians
 from .sh import spherical_harmonics, spherical_harmonics_split
@@ -36,8 +40,8 @@ def tile_grid(width: int, height: int) -> Tuple[int, int, int]:
 class GaussianRasterizer:
     def __init__(self, model, cameras: Optional[Sequence] = None, device="cuda:0",
                  pipeline: str = "fused"):
-        if pipeline not in ("fused", "reference"):
-            raise ValueError("pipeline must be 'fused' or 'reference'")
+        if pipeline not in ("fused", "reference", "unfused4"):
+            raise ValueError("pipeline must be 'fused', 'reference' or 'unfused4'")
         self.model = model
         self.device = torch.device(device)
         self.pipeline = pipeline
@@ -58,9 +62,23 @@ class GaussianRasterizer:
         d = self.model.means - view[:3, 3]
         return d / d.norm(dim=-1, keepdim=True)
 
+    def _render_fused(self, camera, width: int, height: int, sh_degree: int):
+        m = self.model
+        # one small H2D for both matrices (full projection composed on the host)
+        view = camera.view_matrix.float()
+        mats = torch.stack([view, camera.proj_matrix.float() @ view]).to(self.device, non_blocking=True)
+        rgb, depth_img, _, xys, _, radii = render_fused(
+            m.means, m.scales, m.quats, m.opacities, m.colors_dc, m.colors_rest, mats[0], mats[1],
+            camera.f_x, camera.f_y, width, height, sh_degree, m.background)
+        extras: Dict = {"depth": depth_img, "radii": radii, "xys": xys,
+                        "camera": {"height": camera.height, "width": camera.width}}
+        return torch.clamp(rgb, max=1.0), extras
+
     def __call__(self, camera, dims: Optional[Tuple[int, int]], sh_degree: int):
         m = self.model
         width, height = dims if dims is not None else (camera.width, camera.height)
+        if self.pipeline == "fused":
+            return self._render_fused(camera, width, height, sh_degree)
         (xys, depths, radii, conics, num_tiles, _), view = self._project(camera, width, height)
         if xys.requires_grad:
             xys.retain_grad()

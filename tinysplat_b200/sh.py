@@ -43,8 +43,8 @@ class _SphericalHarmonics(Function):
         co = _lib.f32c(coeffs.detach())
         re = _lib.f32c(rest.detach()) if rest is not None else None
         colors = torch.empty(N, 3, device=coeffs.device, dtype=torch.float32)
-        _lib.call("ts_sh_fwd", N, degree, K, _lib.ptr(dirs_c), _lib.ptr(co), _lib.ptr(re),
-                                 _lib.ptr(colors), _lib.stream_ptr(coeffs.device))
+        _lib.call("ts_sh_fwd", N, degree, K, _lib.ptr(dirs_c), None, _lib.ptr(co), _lib.ptr(re),
+                  _lib.ptr(colors), 3, None, None, 0, _lib.stream_ptr(coeffs.device))
         ctx.save_for_backward(dirs_c)
         ctx.meta = (degree, K, N, rest is not None)
         return colors
@@ -62,8 +62,8 @@ class _SphericalHarmonics(Function):
         else:
             v_dc = torch.empty(N, K, 3, device=dev, dtype=torch.float32)
             v_rest = None
-        _lib.call("ts_sh_bwd", N, degree, K, _lib.ptr(dirs_c), _lib.ptr(v_colors),
-                                 _lib.ptr(v_dc), _lib.ptr(v_rest), _lib.stream_ptr(dev))
+        _lib.call("ts_sh_bwd", N, degree, K, _lib.ptr(dirs_c), None, _lib.ptr(v_colors), 3, None,
+                  _lib.ptr(v_dc), _lib.ptr(v_rest), 0, _lib.stream_ptr(dev))
         # view directions get no gradient (recorded in DESIGN.md)
         return None, None, v_dc, v_rest
 
