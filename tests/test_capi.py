@@ -47,16 +47,17 @@ def test_version_and_record_sizes(lib):
 
 
 def test_invalid_arguments_are_rejected_before_any_cuda_call(lib):
-    assert lib.ts_project_fwd(-1, *([None] * 2), 1.0, *([None] * 3), 1.0, 1.0, 0.0, 0.0, 16, 16, 1, 1, 0.01,
-                              *([None] * 7)) == -1
-    assert lib.ts_sh_fwd(4, 5, 16, None, None, None, None, None) == -1       # degree > 4
-    assert lib.ts_sh_fwd(4, 3, 9, None, None, None, None, None) == -1        # K too small
-    assert lib.ts_blend_fwd(7, 16, 16, 1, 1, *([None] * 8)) == -1            # 7 channels
-    assert lib.ts_bin_scan(0, None, None, None, 1, None) == -1
+    N = None
+    assert lib.ts_project_fwd(-1, N, N, 1.0, N, N, N, 1.0, 1.0, 0.0, 0.0, 16, 16, 1, 1, 0.01, 0,
+                              N, N, N, N, N, N, N) == -1
+    assert lib.ts_sh_fwd(4, 5, 16, N, N, N, N, N, 3, N, N, 0, N) == -1        # degree > 4
+    assert lib.ts_sh_fwd(4, 3, 9, N, N, N, N, N, 3, N, N, 0, N) == -1         # K too small
+    assert lib.ts_blend_fwd(7, 16, 16, 1, 1, N, N, N, N, N, N, N, N, N) == -1  # 7 channels
+    assert lib.ts_bin_scan(0, N, N, N, 1, N) == -1
     # N == 0 is a valid no-op everywhere
-    assert lib.ts_project_bwd(0, None, None, 1.0, None, None, None, 1.0, 1.0, 0.0, 0.0, 16, 16,
-                              *([None] * 8)) == 0
-    assert lib.ts_sh_bwd(0, 3, 16, None, None, None, None, None) == 0
+    assert lib.ts_project_bwd(0, N, N, 1.0, N, N, N, 1.0, 1.0, 0.0, 0.0, 16, 16, 0,
+                              N, N, N, N, N, N, N, N, N, N, N, N) == 0
+    assert lib.ts_sh_bwd(0, 3, 16, N, N, N, 3, N, N, N, 0, N) == 0
 
 
 def test_misaligned_pointer_is_reported(lib):
@@ -65,7 +66,7 @@ def test_misaligned_pointer_is_reported(lib):
     base += (16 - base % 16) % 16
     bad = ctypes.c_void_p(base + 4)
     ok = ctypes.c_void_p(base)
-    assert lib.ts_sh_fwd(1, 0, 1, bad, ok, None, ok, None) == -2
+    assert lib.ts_sh_fwd(1, 0, 1, bad, None, ok, None, ok, 3, None, None, 0, None) == -2
 
 
 def test_product_fails_loudly_without_cuda():

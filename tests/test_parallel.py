@@ -1,0 +1,81 @@
+"""Host logic of the data-parallel path on CPU: world_size 2, gloo.  A pure-torch stand-in
+renderer replaces the CUDA rasterizer (the collective plumbing is what is under test)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _fake_render(params):
+    def rast(camera, dims, sh_degree):
+        a, b = params
+        xys = (a[:, :2] * camera).clone()
+        if xys.requires_grad:
+            xys.retain_grad()
+        img = (xys.sum(-1, keepdim=True) * b).tanh()
+        return img, {"xys": xys}
+    return rast
+
+
+def _worker(rank, world, port, overlap, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from tinysplat_b200.parallel import DataParallelRenderer
+    g = torch.Generator().manual_seed(0)
+    a = torch.randn(50, 3, generator=g).requires_grad_(True)       # same replica on every rank
+    b = torch.randn(50, 4, generator=g).requires_grad_(True)
+    dp = DataParallelRenderer(_fake_render((a, b)), [a, b], average=True, overlap=overlap)
+    cam = float(rank + 1)                                            # a different "view" per rank
+    loss, img, extras = dp.step(cam, None, 0, lambda im, ex: im.pow(2).sum())
+    stat = dp.reduce_densify_stat(extras)
+    # reference: average of the per-view gradients computed locally
+    ga, gb, st = torch.zeros_like(a), torch.zeros_like(b), torch.zeros(50)
+    for r in range(world):
+        a2 = a.detach().clone().requires_grad_(True)
+        b2 = b.detach().clone().requires_grad_(True)
+        im, ex = _fake_render((a2, b2))(float(r + 1), None, 0)
+        im.pow(2).sum().backward()
+        ga += a2.grad / world
+        gb += b2.grad / world
+        st += ex["xys"].grad.norm(dim=-1)
+    ok = torch.allclose(a.grad, ga, atol=1e-6) and torch.allclose(b.grad, gb, atol=1e-6) and \
+        torch.allclose(stat, st, atol=1e-6)
+    q.put((rank, bool(ok), dp.reducer.payload_bytes()))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("overlap", [True, False])
+def test_gradient_allreduce_two_ranks_gloo(overlap):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, overlap, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok, _ in res), res
+    assert res[0][2] == (50 * 3 + 50 * 4) * 4
+
+
+def test_single_process_is_a_noop():
+    from tinysplat_b200.parallel import GradientAllReducer
+    a = torch.randn(4, 3, requires_grad=True)
+    red = GradientAllReducer([a])
+    (a * 2).sum().backward()
+    red.finish()
+    assert red.world_size == 1 and torch.allclose(a.grad, torch.full_like(a, 2.0))
