@@ -313,14 +313,32 @@ def run_ours(args):
     value = world * P / (ms_step * 1e-3) / 1e6
 
     # ---- end-to-end arm: host buffers in, loss out -------------------------------------------
+    # Every step copies ITS target image (pinned host -> device) and reads its loss back.  Like a
+    # training data loader, step i+1's image is prefetched on a copy stream while step i renders;
+    # all copies happen inside the timed region.
+    copy_stream = torch.cuda.Stream(device=dev)
+    gt_bufs = [torch.empty_like(gt_dev), torch.empty_like(gt_dev)]
+    copied = [torch.cuda.Event(), torch.cuda.Event()]
+    issued = set()
+
+    def issue_copy(i):
+        if i in issued:
+            return
+        issued.add(i)
+        with torch.cuda.stream(copy_stream):
+            gt_bufs[i % 2].copy_(gt_host, non_blocking=True)
+            copied[i % 2].record(copy_stream)
+
     def e2e_step(i):
-        gt = gt_host.to(dev, non_blocking=True)           # H2D of this step's target image
-        loss = one_step(i, gt)
-        return float(loss.item())                          # D2H of the step's result
+        issue_copy(i)
+        issue_copy(i + 1)                                    # H2D of the next step's target image
+        torch.cuda.current_stream().wait_event(copied[i % 2])
+        loss = one_step(i, gt_bufs[i % 2])
+        return float(loss.item())                            # D2H of the step's result (also fences buffer reuse)
 
     for i in range(3):
-        e2e_step(i)
-    ms_e2e, _, _ = timed(e2e_step, K, Wm + K)
+        e2e_step(1000 + i)
+    ms_e2e, _, _ = timed(e2e_step, K, 2000)
     e2e_val = world * P / (ms_e2e / K * 1e-3) / 1e6
     h2d = gt_host.numel() * 4 + 2 * 16 * 4                  # target image + view/proj matrices
     d2h = 4 + 16                                            # loss scalar + binning stats (4 x int32)

@@ -171,7 +171,20 @@ blend_fwd_kernel(int H, int W, int tbx, const int32_t* __restrict__ tile_offsets
     }
 }
 
-template <int CH>
+// Shared-memory plan of blend_bwd (dynamic, ~70 KB -> 3 CTAs/SM):
+//   s_rec  [2][256*3] float4   double-buffered gathered records
+//   s_acc  [256*12]   float    per-batch CTA accumulators (packed gradient layout)
+//   s_part [8 warps][3 candidates][10 values][32 lanes] float   per-warp reduction staging
+//   s_gid  [2][256] int, s_mask [8][8] unsigned, s_nmax
+constexpr int kGroup = 3;                 // candidates reduced together (3*10 = 30 busy lanes)
+constexpr int kPartFloats = 10 * 32;      // one candidate's staged partials
+constexpr size_t kBwdSmemBytes = sizeof(float4) * 2 * kBatch * 3 + sizeof(float) * kBatch * kGradFloats +
+                                 sizeof(float) * 8 * kGroup * kPartFloats + sizeof(int) * 2 * kBatch +
+                                 sizeof(unsigned) * 64 + sizeof(int) * 8 * 4 + 16;
+
+// GCH = number of colour channels that carry a cotangent (GCH <= CH; the fused RGB+depth pass
+// with no depth loss has CH = 4, GCH = 3 and skips all channel-3 gradient arithmetic).
+template <int CH, int GCH>
 __global__ void __launch_bounds__(kBlendThreads)
 blend_bwd_kernel(int H, int W, int tbx, const int32_t* __restrict__ tile_offsets,
                  const int32_t* __restrict__ ids, const float4* __restrict__ recs,
@@ -179,14 +192,14 @@ blend_bwd_kernel(int H, int W, int tbx, const int32_t* __restrict__ tile_offsets
                  const int32_t* __restrict__ n_contrib, const float* __restrict__ v_out_img,
                  const float* __restrict__ v_out_ch3, int split_ch3,
                  const float* __restrict__ v_out_alpha, float4* __restrict__ grads) {
-    constexpr int kSlotsUsed = 6 + CH;  // S_x S_y S_xx S_xy S_yy v_opac + colours
-    // reduction slot s -> float offset inside the 12-float packed gradient record:
-    // s < 6 ? s : s + 2   (colours live in the third float4)
-    __shared__ __align__(16) float4 s_rec[2][kBatch * 3];
-    __shared__ __align__(16) float s_acc[kBatch * kGradFloats];
-    __shared__ int s_gid[2][kBatch];
-    __shared__ unsigned s_mask[8][8];
-    __shared__ int s_nmax;
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    float4* s_rec = reinterpret_cast<float4*>(s_raw);                         // [2][kBatch*3]
+    float* s_acc = reinterpret_cast<float*>(s_rec + 2 * kBatch * 3);          // [kBatch*12]
+    float* s_part = s_acc + kBatch * kGradFloats;                             // [8][kGroup][320]
+    int* s_gid = reinterpret_cast<int*>(s_part + 8 * kGroup * kPartFloats);   // [2][kBatch]
+    unsigned* s_mask = reinterpret_cast<unsigned*>(s_gid + 2 * kBatch);       // [8][8]
+    int* s_slot = reinterpret_cast<int*>(s_mask + 64);                        // [8 warps][4]
+    int* s_nmax = s_slot + 32;
     const unsigned full = 0xffffffffu;
     const PixMap pm = pix_map(H, W);
     const int tid = threadIdx.x;
@@ -205,7 +218,7 @@ blend_bwd_kernel(int H, int W, int tbx, const int32_t* __restrict__ tile_offsets
         if (CH == 4 && split_ch3) {
 #pragma unroll
             for (int c = 0; c < 3; ++c) v_out[c] = v_out_img ? __ldg(v_out_img + pix * 3 + c) : 0.f;
-            v_out[CH - 1] = v_out_ch3 ? __ldg(v_out_ch3 + pix) : 0.f;
+            if (GCH == 4) v_out[CH - 1] = v_out_ch3 ? __ldg(v_out_ch3 + pix) : 0.f;
         } else {
 #pragma unroll
             for (int c = 0; c < CH; ++c) v_out[c] = __ldg(v_out_img + pix * CH + c);
@@ -214,33 +227,38 @@ blend_bwd_kernel(int H, int W, int tbx, const int32_t* __restrict__ tile_offsets
     }
     float bgdot = 0.f;
 #pragma unroll
-    for (int c = 0; c < CH; ++c) bgdot = fmaf(__ldg(background + c), v_out[c], bgdot);
+    for (int c = 0; c < GCH; ++c) bgdot = fmaf(__ldg(background + c), v_out[c], bgdot);
     const float wfin = T_final * (v_oa - bgdot);
     float T = T_final;
-    float buffer[CH];
+    float buffer[GCH];
 #pragma unroll
-    for (int c = 0; c < CH; ++c) buffer[c] = 0.f;
+    for (int c = 0; c < GCH; ++c) buffer[c] = 0.f;
 
-    if (tid == 0) s_nmax = 0;
+    if (tid == 0) *s_nmax = 0;
 #pragma unroll
     for (int k = 0; k < kGradFloats; ++k) s_acc[tid * kGradFloats + k] = 0.f;
     __syncthreads();
     int wmax = nc;
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) wmax = max(wmax, __shfl_xor_sync(full, wmax, d));
-    if (pm.lane == 0) atomicMax(&s_nmax, wmax);
+    if (pm.lane == 0) atomicMax(s_nmax, wmax);
     __syncthreads();
-    const int nmax = s_nmax;  // entries [0, nmax) of the tile list contributed somewhere
+    const int nmax = *s_nmax;  // entries [0, nmax) of the tile list contributed somewhere
     const int nb = (nmax + kBatch - 1) / kBatch;
+
+    // this lane's role in the group reduction: row (candidate rc, value rv) of s_part
+    float* my_part = s_part + pm.warp * kGroup * kPartFloats;
+    const int rc = pm.lane / 10, rv = pm.lane - 10 * rc;
+    const int racc = rv < 6 ? rv : rv + 2;    // slot -> float offset in the packed gradient record
 
     // batch b, slot t  <->  list position  p = nmax-1 - (b*256 + t)   (back to front)
     auto prefetch = [&](int b) {
         int p = nmax - 1 - (b * kBatch + tid);
         if (p >= 0) {
             int g = __ldg(ids + start + p);
-            s_gid[b & 1][tid] = g;
+            s_gid[(b & 1) * kBatch + tid] = g;
             const float4* src = recs + 3 * (size_t)g;
-            float4* dst = &s_rec[b & 1][tid * 3];
+            float4* dst = s_rec + (b & 1) * kBatch * 3 + tid * 3;
             cp_async16(dst, src);
             cp_async16(dst + 1, src + 1);
             cp_async16(dst + 2, src + 2);
@@ -251,27 +269,49 @@ blend_bwd_kernel(int H, int W, int tbx, const int32_t* __restrict__ tile_offsets
 
     for (int b = 0; b < nb; ++b) {
         const int buf = b & 1;
+        const float4* rec = s_rec + buf * kBatch * 3;
         if (b + 1 < nb) prefetch(b + 1);
         cp_async_commit();
         cp_async_wait<1>();
-        const int my_p = nmax - 1 - (b * kBatch + tid);
+        const int pbase = nmax - 1 - b * kBatch;
+        const int my_p = pbase - tid;
         unsigned mine = 0;
-        if (my_p >= 0) mine = subblock_mask(s_rec[buf][tid * 3]);
+        if (my_p >= 0) mine = subblock_mask(rec[tid * 3]);
 #pragma unroll
         for (int s = 0; s < 8; ++s) {
             unsigned m = __ballot_sync(full, (mine >> s) & 1u);
-            if (pm.lane == 0) s_mask[s][pm.warp] = m;
+            if (pm.lane == 0) s_mask[s * 8 + pm.warp] = m;
         }
         __syncthreads();
+
+        int gcount = 0;                           // candidates staged in the current group
+        int* my_slot = s_slot + pm.warp * 4;      // their batch slots
+        // sums the staged rows: 30 lanes x (8 LDS.128 + 32 FADD), then one shared atomic per lane
+        auto flush_group = [&]() {
+            __syncwarp(full);
+            if (pm.lane < gcount * 10) {
+                const float4* row = reinterpret_cast<const float4*>(my_part + (rc * 10 + rv) * 32);
+                float4 acc4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float4 t = row[(j + pm.lane) & 7];   // rotated start: conflict-free LDS.128
+                    acc4.x += t.x; acc4.y += t.y; acc4.z += t.z; acc4.w += t.w;
+                }
+                atomicAdd(s_acc + my_slot[rc] * kGradFloats + racc, (acc4.x + acc4.y) + (acc4.z + acc4.w));
+            }
+            __syncwarp(full);
+            gcount = 0;
+        };
+
         for (int k = 0; k < 8; ++k) {
-            unsigned m = s_mask[pm.warp][k];
+            unsigned m = s_mask[pm.warp * 8 + k];
             while (m) {
                 int bit = __ffs(m) - 1;
                 m &= m - 1;
                 const int g = k * 32 + bit;
-                const int p = nmax - 1 - (b * kBatch + g);
-                const float4 q0 = s_rec[buf][g * 3];
-                const float4 q1 = s_rec[buf][g * 3 + 1];
+                const int p = pbase - g;
+                const float4 q0 = rec[g * 3];
+                const float4 q1 = rec[g * 3 + 1];
                 float dx, dy;
                 float pw = eval_power(q0, q1, pm.px, pm.py, dx, dy);
                 float vis = ex2_approx(-pw);
@@ -279,18 +319,18 @@ blend_bwd_kernel(int H, int W, int tbx, const int32_t* __restrict__ tile_offsets
                 float alpha = fminf(kAlphaMax, araw);
                 bool valid = pm.inside && (p < nc) && (pw >= 0.f) && (alpha >= kAlphaMin);
                 if (!__any_sync(full, valid)) continue;
-                float val[16];   // slots 0..5 geometry/opacity, 6..9 colours, rest zero
+                float val[10];
 #pragma unroll
-                for (int v = 0; v < 16; ++v) val[v] = 0.f;
+                for (int v = 0; v < 10; ++v) val[v] = 0.f;
                 if (valid) {
-                    const float4 q2 = s_rec[buf][g * 3 + 2];
+                    const float4 q2 = rec[g * 3 + 2];
                     const float col[4] = {q2.x, q2.y, q2.z, q2.w};
-                    float ra = __frcp_rn(1.f - alpha);
+                    float ra = rcp_approx(1.f - alpha);
                     T *= ra;
                     float fac = alpha * T;
                     float v_alpha = wfin * ra;
 #pragma unroll
-                    for (int c = 0; c < CH; ++c) {
+                    for (int c = 0; c < GCH; ++c) {
                         val[6 + c] = fac * v_out[c];
                         v_alpha = fmaf(col[c] * T - buffer[c] * ra, v_out[c], v_alpha);
                         buffer[c] = fmaf(col[c], fac, buffer[c]);
@@ -304,47 +344,18 @@ blend_bwd_kernel(int H, int W, int tbx, const int32_t* __restrict__ tile_offsets
                     val[4] = val[1] * dy;
                     val[5] = vis * v_alpha;
                 }
-                // butterfly reduction of all 16 slots at once: 8+4+2+1+1 = 16 shuffles (instead
-                // of 5 per value); afterwards lane l (l even) holds the warp total of slot
-                // rev4(l>>1) and adds it to the CTA accumulator — up to 16 lanes, one shared
-                // atomic each, distinct banks.
-                {
-                    const bool b4 = pm.lane & 16, b3 = pm.lane & 8, b2 = pm.lane & 4, b1 = pm.lane & 2;
+                float* pp = my_part + gcount * kPartFloats + pm.lane;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        float send = b4 ? val[i] : val[i + 8];
-                        float keep = b4 ? val[i + 8] : val[i];
-                        val[i] = keep + __shfl_xor_sync(full, send, 16);
-                    }
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        float send = b3 ? val[i] : val[i + 4];
-                        float keep = b3 ? val[i + 4] : val[i];
-                        val[i] = keep + __shfl_xor_sync(full, send, 8);
-                    }
-#pragma unroll
-                    for (int i = 0; i < 2; ++i) {
-                        float send = b2 ? val[i] : val[i + 2];
-                        float keep = b2 ? val[i + 2] : val[i];
-                        val[i] = keep + __shfl_xor_sync(full, send, 4);
-                    }
-                    {
-                        float send = b1 ? val[0] : val[1];
-                        float keep = b1 ? val[1] : val[0];
-                        val[0] = keep + __shfl_xor_sync(full, send, 2);
-                    }
-                    val[0] += __shfl_xor_sync(full, val[0], 1);
-                    // slot held by this lane: bit4 -> +8, bit3 -> +4, bit2 -> +2, bit1 -> +1
-                    const int slot = (b4 ? 8 : 0) + (b3 ? 4 : 0) + (b2 ? 2 : 0) + (b1 ? 1 : 0);
-                    if (!(pm.lane & 1) && slot < kSlotsUsed)
-                        atomicAdd(s_acc + g * kGradFloats + (slot < 6 ? slot : slot + 2), val[0]);
-                }
+                for (int v = 0; v < 10; ++v) pp[v * 32] = (v < 6 + GCH) ? val[v] : 0.f;
+                my_slot[gcount] = g;   // same value from every lane: one broadcast store
+                if (++gcount == kGroup) flush_group();
             }
         }
+        if (gcount) flush_group();
         __syncthreads();  // all warps finished batch b: s_acc complete
         if (mine) {
             float4* a4 = reinterpret_cast<float4*>(s_acc + tid * kGradFloats);
-            float4* dst = grads + 3 * (size_t)s_gid[buf][tid];
+            float4* dst = grads + 3 * (size_t)s_gid[buf * kBatch + tid];
             atomicAdd(dst, a4[0]);
             atomicAdd(dst + 1, a4[1]);
             atomicAdd(dst + 2, a4[2]);
@@ -423,13 +434,28 @@ int ts_blend_bwd(int N, int CH, int img_height, int img_width, int tiles_x, int 
     cudaStream_t st = (cudaStream_t)stream;
     TS_CHECK_CUDA(cudaMemsetAsync(grads, 0, sizeof(float) * ts::kGradFloats * (size_t)N, st), "ts_blend_bwd/memset");
     dim3 grid(tiles_x, tiles_y);
-#define TS_LAUNCH_BWD(C) \
-    ts::blend_bwd_kernel<C><<<grid, ts::kBlendThreads, 0, st>>>(img_height, img_width, tiles_x, tile_offsets, ids_sorted, (const float4*)recs, background, final_T, n_contrib, v_out_img, v_out_ch3, split_ch3, v_out_alpha, (float4*)grads)
+    // channels that carry a cotangent: the fused RGB+depth pass without a depth loss skips ch 3
+    const int gch = (CH == 4 && split_ch3 && !v_out_ch3) ? 3 : CH;
+#define TS_LAUNCH_BWD(C, G)                                                                              \
+    do {                                                                                                 \
+        static bool attr_done = false;                                                                   \
+        if (!attr_done) {                                                                                \
+            TS_CHECK_CUDA(cudaFuncSetAttribute(ts::blend_bwd_kernel<C, G>,                               \
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize,              \
+                                               (int)ts::kBwdSmemBytes), "ts_blend_bwd/attr");            \
+            attr_done = true;                                                                            \
+        }                                                                                                \
+        ts::blend_bwd_kernel<C, G><<<grid, ts::kBlendThreads, ts::kBwdSmemBytes, st>>>(                  \
+            img_height, img_width, tiles_x, tile_offsets, ids_sorted, (const float4*)recs, background,   \
+            final_T, n_contrib, v_out_img, v_out_ch3, split_ch3, v_out_alpha, (float4*)grads);           \
+    } while (0)
     switch (CH) {
-        case 1: TS_LAUNCH_BWD(1); break;
-        case 2: TS_LAUNCH_BWD(2); break;
-        case 3: TS_LAUNCH_BWD(3); break;
-        default: TS_LAUNCH_BWD(4); break;
+        case 1: TS_LAUNCH_BWD(1, 1); break;
+        case 2: TS_LAUNCH_BWD(2, 2); break;
+        case 3: TS_LAUNCH_BWD(3, 3); break;
+        default:
+            if (gch == 3) TS_LAUNCH_BWD(4, 3); else TS_LAUNCH_BWD(4, 4);
+            break;
     }
 #undef TS_LAUNCH_BWD
     TS_CHECK_LAUNCH("ts_blend_bwd");

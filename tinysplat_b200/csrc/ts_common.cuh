@@ -121,6 +121,12 @@ __device__ __forceinline__ float ex2_approx(float x) {
     return y;
 }
 
+__device__ __forceinline__ float rcp_approx(float x) {   // MUFU.RCP, <= 1 ulp
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 // 16-byte async global->shared copy (LDGSTS), commit / wait.
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
     uint32_t s = (uint32_t)__cvta_generic_to_shared(smem_dst);

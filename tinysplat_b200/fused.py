@@ -128,6 +128,7 @@ class _RenderFused(Function):
                     tuple(opac_logits.shape), tuple(colors_dc.shape))
         ctx.sink = sink
         ctx.mark_non_differentiable(xys, depths, radii)
+        ctx.set_materialize_grads(False)   # unused outputs (depth, alpha) arrive as None, not zeros
         return rgb, depth_img, 1.0 - final_T, xys, depths, radii
 
     @staticmethod
@@ -139,6 +140,8 @@ class _RenderFused(Function):
         dev = means_c.device
         st = _lib.stream_ptr(dev)
         f32 = dict(device=dev, dtype=torch.float32)
+        if v_rgb is None and v_depth is None and v_alpha is None:
+            return (None,) * 16
         v_rgb = _lib.f32c(v_rgb) if v_rgb is not None else None
         v_depth = _lib.f32c(v_depth) if v_depth is not None else None
         v_alpha = _lib.f32c(v_alpha) if v_alpha is not None else None
