@@ -130,6 +130,28 @@ bin_emit_kernel(int N, const float* __restrict__ depths, const int32_t* __restri
             key = ((uint64_t)__float_as_uint(__ldg(depths + i)) << 32) | (uint32_t)i;
         }
     }
+    // Small footprints (the common case): issue ALL of this Gaussian's return-atomics first,
+    // then the dependent key stores, so the ~600-cycle L2 round trips overlap instead of
+    // serialising (the kernel was long-scoreboard bound at 12% issue utilisation).
+    {
+        const int w = hix - lox, h = hiy - loy;
+        const int n = (w > 0 && h > 0) ? w * h : 0;
+        if (n > 0 && n <= kCoopThreshold) {
+            int slots[kCoopThreshold];
+            int x = lox, y = loy;
+#pragma unroll
+            for (int k = 0; k < kCoopThreshold; ++k) {
+                if (k < n) {
+                    slots[k] = atomicAdd(cursors + y * tbx + x, 1);
+                    if (++x == hix) { x = lox; ++y; }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < kCoopThreshold; ++k)
+                if (k < n) keys[slots[k]] = key;
+            lox = loy = hix = hiy = 0;   // done; nothing left for the cooperative path
+        }
+    }
     for_each_tile(lox, loy, hix, hiy, tbx, (uint32_t)key, (uint32_t)(key >> 32),
                   [&](int tile, uint32_t lo, uint32_t hi) {
                       int slot = atomicAdd(cursors + tile, 1);

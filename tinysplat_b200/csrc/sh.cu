@@ -224,6 +224,144 @@ sh_bwd_kernel(int N, int K, const float* __restrict__ dirs, const float* __restr
     }
 }
 
+// ---- TMA variants for the fused pipeline ------------------------------------------------------
+// Coefficients arrive as (dc[N,3], rest[N,K-1,3]) and the block's rows are one contiguous chunk
+// of global memory, so a single elected thread moves them with cp.async.bulk (UBLKCP) straight
+// into a DENSE shared layout: row stride (K-1)*3 = 45 floats at degree 3 is odd, i.e. already
+// bank-conflict free for the thread-per-row reads — no padding, no per-element index math.
+// The last (partial) block falls back to a plain coalesced copy of the same dense chunk.
+template <int THREADS>
+__device__ __forceinline__ void dense_copy_in(float* s, const float* __restrict__ g, int nfl) {
+    for (int i = threadIdx.x; i < nfl; i += THREADS) s[i] = __ldg(g + i);
+}
+
+template <int DEG>
+__global__ void __launch_bounds__(kShThreads)
+sh_fwd_bulk_kernel(int N, int K, const float* __restrict__ means, const float* __restrict__ viewmat,
+                   const float* __restrict__ dc, const float* __restrict__ rest,
+                   float* __restrict__ colors, int out_stride, const float* __restrict__ ch3,
+                   uint8_t* __restrict__ clamp_mask, int flags) {
+    extern __shared__ __align__(128) float s_sh[];
+    constexpr int NB = (DEG + 1) * (DEG + 1);
+    const int R = (K - 1) * 3;                       // floats per `rest` row
+    float* s_rest = s_sh;                            // [TH][R] dense
+    float* s_dc = s_rest + kShThreads * R;           // [TH*3]
+    float* s_mean = s_dc + kShThreads * 3;           // [TH*3]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(s_mean + kShThreads * 3);
+    const int item0 = blockIdx.x * kShThreads;
+    const int n_valid = min(kShThreads, N - item0);
+    const int tid = threadIdx.x;
+    if (n_valid == kShThreads) {
+        if (tid == 0) {
+            mbar_init(bar, 1);
+            fence_proxy_async();
+            const unsigned b_rest = kShThreads * R * 4, b_3 = kShThreads * 3 * 4;
+            mbar_expect_tx(bar, b_rest + 2 * b_3);
+            bulk_g2s(s_rest, rest + (size_t)item0 * R, b_rest, bar);
+            bulk_g2s(s_dc, dc + (size_t)item0 * 3, b_3, bar);
+            bulk_g2s(s_mean, means + (size_t)item0 * 3, b_3, bar);
+        }
+        __syncthreads();          // barrier init visible before anyone waits
+        mbar_wait(bar, 0);
+    } else {
+        dense_copy_in<kShThreads>(s_rest, rest + (size_t)item0 * R, n_valid * R);
+        dense_copy_in<kShThreads>(s_dc, dc + (size_t)item0 * 3, n_valid * 3);
+        dense_copy_in<kShThreads>(s_mean, means + (size_t)item0 * 3, n_valid * 3);
+        __syncthreads();
+    }
+    if (tid >= n_valid) return;
+    float b[NB];
+    float dx, dy, dz;
+    load_dir(s_mean, tid, flags, viewmat, dx, dy, dz);
+    sh_basis<DEG>(dx, dy, dz, b);
+    float r = b[0] * s_dc[3 * tid], g = b[0] * s_dc[3 * tid + 1], bl = b[0] * s_dc[3 * tid + 2];
+    const float* c = s_rest + tid * R;
+#pragma unroll
+    for (int k = 1; k < NB; ++k) {
+        r = fmaf(b[k], c[3 * (k - 1)], r);
+        g = fmaf(b[k], c[3 * (k - 1) + 1], g);
+        bl = fmaf(b[k], c[3 * (k - 1) + 2], bl);
+    }
+    if (flags & TS_SH_OFFSET_CLAMP) {
+        r += 0.5f; g += 0.5f; bl += 0.5f;
+        unsigned m = (r >= 0.f ? 1u : 0u) | (g >= 0.f ? 2u : 0u) | (bl >= 0.f ? 4u : 0u);
+        r = fmaxf(r, 0.f); g = fmaxf(g, 0.f); bl = fmaxf(bl, 0.f);
+        if (clamp_mask) clamp_mask[item0 + tid] = (uint8_t)m;
+    }
+    float* o = colors + (size_t)out_stride * (item0 + tid);
+    float d = ch3 ? __ldg(ch3 + item0 + tid) : 0.f;
+    if ((out_stride & 3) == 0 && aligned_dev16(colors)) {
+        *reinterpret_cast<float4*>(o) = make_float4(r, g, bl, d);
+    } else {
+        o[0] = r; o[1] = g; o[2] = bl;
+        if (ch3) o[3] = d;
+    }
+}
+
+template <int DEG>
+__global__ void __launch_bounds__(kShThreads)
+sh_bwd_bulk_kernel(int N, int K, const float* __restrict__ means, const float* __restrict__ viewmat,
+                   const float* __restrict__ v_colors, int v_stride,
+                   const uint8_t* __restrict__ clamp_mask, float* __restrict__ v_dc,
+                   float* __restrict__ v_rest, int flags) {
+    extern __shared__ __align__(128) float s_sh[];
+    constexpr int NB = (DEG + 1) * (DEG + 1);
+    const int R = (K - 1) * 3;
+    float* s_rest = s_sh;                            // [TH][R] dense, becomes v_rest rows
+    float* s_dc = s_rest + kShThreads * R;           // [TH*3]
+    const int item0 = blockIdx.x * kShThreads;
+    const int n_valid = min(kShThreads, N - item0);
+    const int tid = threadIdx.x;
+    if (tid < n_valid) {
+        const int i = item0 + tid;
+        float b[NB];
+        float dx = __ldg(means + 3 * (size_t)i), dy = __ldg(means + 3 * (size_t)i + 1), dz = __ldg(means + 3 * (size_t)i + 2);
+        if (flags & TS_SH_DIRS_FROM_MEANS) {
+            dx -= __ldg(viewmat + 3); dy -= __ldg(viewmat + 7); dz -= __ldg(viewmat + 11);
+        }
+        sh_basis<DEG>(dx, dy, dz, b);
+        float vr, vg, vb;
+        const float* v = v_colors + (size_t)v_stride * i;
+        if ((v_stride & 3) == 0 && aligned_dev16(v_colors)) {
+            float4 t = __ldg(reinterpret_cast<const float4*>(v));
+            vr = t.x; vg = t.y; vb = t.z;
+        } else {
+            vr = __ldg(v); vg = __ldg(v + 1); vb = __ldg(v + 2);
+        }
+        if (clamp_mask) {
+            unsigned m = clamp_mask[i];
+            if (!(m & 1u)) vr = 0.f;
+            if (!(m & 2u)) vg = 0.f;
+            if (!(m & 4u)) vb = 0.f;
+        }
+        s_dc[3 * tid] = b[0] * vr; s_dc[3 * tid + 1] = b[0] * vg; s_dc[3 * tid + 2] = b[0] * vb;
+        float* c = s_rest + tid * R;
+#pragma unroll
+        for (int k = 1; k < NB; ++k) {
+            c[3 * (k - 1)] = b[k] * vr;
+            c[3 * (k - 1) + 1] = b[k] * vg;
+            c[3 * (k - 1) + 2] = b[k] * vb;
+        }
+        for (int k = (NB - 1) * 3; k < R; ++k) c[k] = 0.f;   // bases above the active degree
+    }
+    if (n_valid == kShThreads) {
+        fence_proxy_async();      // generic-proxy smem writes -> visible to the copy engine
+        __syncthreads();
+        if (tid == 0) {
+            bulk_s2g(v_rest + (size_t)item0 * R, s_rest, kShThreads * R * 4);
+            bulk_s2g(v_dc + (size_t)item0 * 3, s_dc, kShThreads * 3 * 4);
+            bulk_commit();
+            bulk_wait_read0();    // shared memory must outlive the reads
+        }
+    } else {
+        __syncthreads();
+        float* gr = v_rest + (size_t)item0 * R;
+        for (int i = tid; i < n_valid * R; i += kShThreads) gr[i] = s_rest[i];
+        float* gd = v_dc + (size_t)item0 * 3;
+        for (int i = tid; i < n_valid * 3; i += kShThreads) gd[i] = s_dc[i];
+    }
+}
+
 static inline int sh_stride(int K) { int k3 = K * 3; return (k3 & 1) ? k3 : k3 + 1; }
 
 }  // namespace ts
@@ -245,6 +383,22 @@ int ts_sh_fwd(int N, int degree, int K, const float* dirs, const float* viewmat,
     size_t smem = sizeof(float) * (ts::kShThreads * 3 + 4 + (size_t)ts::kShThreads * sstride);
     int grid = (N + ts::kShThreads - 1) / ts::kShThreads;
     cudaStream_t st = (cudaStream_t)stream;
+    // TMA path: (dc, rest) split, every stored band active, strided output (the fused pipeline)
+    if (coeffs_rest && K == (degree + 1) * (degree + 1) && K > 1 && out_stride != 3 &&
+        ((K - 1) * 3 * 4 * ts::kShThreads) % 16 == 0) {
+        size_t bsmem = sizeof(float) * ts::kShThreads * ((K - 1) * 3 + 6) + 16;
+#define TS_LAUNCH_SH_FWD_BULK(D) \
+    ts::sh_fwd_bulk_kernel<D><<<grid, ts::kShThreads, bsmem, st>>>(N, K, dirs, viewmat, coeffs, coeffs_rest, colors, out_stride, ch3, clamp_mask, flags)
+        switch (degree) {
+            case 1: TS_LAUNCH_SH_FWD_BULK(1); break;
+            case 2: TS_LAUNCH_SH_FWD_BULK(2); break;
+            case 3: TS_LAUNCH_SH_FWD_BULK(3); break;
+            default: TS_LAUNCH_SH_FWD_BULK(4); break;
+        }
+#undef TS_LAUNCH_SH_FWD_BULK
+        TS_CHECK_LAUNCH("ts_sh_fwd/bulk");
+        return TS_OK;
+    }
 #define TS_LAUNCH_SH_FWD(D) \
     ts::sh_fwd_kernel<D><<<grid, ts::kShThreads, smem, st>>>(N, K, dirs, viewmat, coeffs, coeffs_rest, colors, out_stride, ch3, clamp_mask, flags, sstride)
     switch (degree) {
@@ -274,6 +428,21 @@ int ts_sh_bwd(int N, int degree, int K, const float* dirs, const float* viewmat,
     size_t smem = sizeof(float) * (2 * (ts::kShThreads * 3 + 4) + (size_t)ts::kShThreads * sstride);
     int grid = (N + ts::kShThreads - 1) / ts::kShThreads;
     cudaStream_t st = (cudaStream_t)stream;
+    if (v_coeffs_rest && K > 1 && v_stride != 3 && ((K - 1) * 3 * 4 * ts::kShThreads) % 16 == 0) {
+        size_t bsmem = sizeof(float) * ts::kShThreads * ((K - 1) * 3 + 3) + 16;
+#define TS_LAUNCH_SH_BWD_BULK(D) \
+    ts::sh_bwd_bulk_kernel<D><<<grid, ts::kShThreads, bsmem, st>>>(N, K, dirs, viewmat, v_colors, v_stride, clamp_mask, v_coeffs, v_coeffs_rest, flags)
+        switch (degree) {
+            case 0: TS_LAUNCH_SH_BWD_BULK(0); break;
+            case 1: TS_LAUNCH_SH_BWD_BULK(1); break;
+            case 2: TS_LAUNCH_SH_BWD_BULK(2); break;
+            case 3: TS_LAUNCH_SH_BWD_BULK(3); break;
+            default: TS_LAUNCH_SH_BWD_BULK(4); break;
+        }
+#undef TS_LAUNCH_SH_BWD_BULK
+        TS_CHECK_LAUNCH("ts_sh_bwd/bulk");
+        return TS_OK;
+    }
 #define TS_LAUNCH_SH_BWD(D) \
     ts::sh_bwd_kernel<D><<<grid, ts::kShThreads, smem, st>>>(N, K, dirs, viewmat, v_colors, v_stride, clamp_mask, v_coeffs, v_coeffs_rest, flags, sstride)
     switch (degree) {
