@@ -202,6 +202,39 @@ def test_sorted_lists_match_oracle_order():
     assert torch.equal(bins.ids_sorted.cpu().long()[:gid.numel()], gid)
 
 
+def test_sort_every_size_class():
+    """Per-tile lists of chosen lengths hit every sort path (warp/register sort with 2, 4, 8, 16
+    keys per lane; CTA shared-memory classes; lengths at the class edges), with depth ties."""
+    from tinysplat_b200 import rasterize as rz
+    sizes = [0, 1, 2, 3, 31, 32, 33, 64, 65, 127, 128, 129, 255, 256, 257, 300, 511, 512, 513, 700,
+             1024, 2047, 2048, 2049, 3000]
+    W, H = 16 * len(sizes), 16
+    g = torch.Generator().manual_seed(11)
+    xs, tiles = [], []
+    for t, n in enumerate(sizes):
+        xs.append(torch.rand(n, 2, generator=g) * 10 + 3 + torch.tensor([16.0 * t, 0.0]))
+        tiles.append(torch.full((n,), t))
+    xys = torch.cat(xs)
+    tile_of = torch.cat(tiles)
+    N = xys.shape[0]
+    perm = torch.randperm(N, generator=g)
+    xys, tile_of = xys[perm], tile_of[perm]
+    dep = (torch.randint(0, 400, (N,), generator=g).float() + 1) / 16.0     # many exact ties
+    rad = torch.ones(N, dtype=torch.int32)
+    con = torch.tensor([[0.5, 0.0, 0.5]]).repeat(N, 1)
+    rz.clear_bin_cache()
+    recs, bins = rz.pack_and_bin(xys.to(DEV), dep.to(DEV), rad.to(DEV), con.to(DEV), torch.full((N,), 0.5).to(DEV),
+                                 torch.rand(N, 3, generator=g).to(DEV), H, W, cull_mode=0, reuse=False)
+    assert bins.num_intersects == N and bins.max_per_tile == max(sizes)
+    off = bins.tile_offsets.cpu().long()
+    ids = bins.ids_sorted.cpu().long()
+    for t, n in enumerate(sizes):
+        assert off[t + 1] - off[t] == n
+        members = torch.nonzero(tile_of == t).flatten()
+        want = members[torch.argsort(dep[members], stable=True)]      # members ascending -> ties by id
+        assert torch.equal(ids[off[t]:off[t + 1]], want), f"tile {t} (n={n})"
+
+
 def test_big_tile_fallback_sort():
     """A tile list longer than the shared-memory sort capacity goes through the global-memory
     fallback and must still be exactly sorted."""

@@ -249,6 +249,94 @@ bin_sort_kernel(int T, const int32_t* __restrict__ offsets, const uint64_t* __re
     for (int i = threadIdx.x; i < n; i += kSortThreads) ids_sorted[start + i] = (int32_t)(uint32_t)s_keys[i];
 }
 
+// ---- warp-per-tile register sort (lists of up to 512 entries) ---------------------------------
+// Each lane holds E consecutive keys (blocked layout, index = lane*E + slot).  Bitonic stages with
+// stride < E are compare-exchanges between a lane's own registers; strides >= E exchange whole
+// registers with lane ^ (stride/E) through shuffles.  No __syncthreads, no shared-memory traffic
+// inside the network; shared memory is used once to turn the coalesced load into the blocked
+// layout (skewed by one slot per E to stay bank-conflict free) and once for the coalesced store.
+constexpr int kWarpSortMax = 512;
+constexpr int kWarpSortSlice = kWarpSortMax + 32;   // u64 per warp incl. skew
+
+__device__ __forceinline__ void cex(uint64_t& a, uint64_t& b, bool asc) {
+    bool sw = (a > b) == asc;
+    uint64_t lo = sw ? b : a, hi = sw ? a : b;
+    a = lo; b = hi;
+}
+
+template <int E>
+__device__ __forceinline__ void warp_sort_tile(uint64_t* sw, const uint64_t* __restrict__ keys,
+                                               int32_t* __restrict__ out, int start, int n) {
+    constexpr int P = 32 * E;
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    auto phys = [](int idx) { return idx + idx / E; };
+#pragma unroll
+    for (int s = 0; s < E; ++s) {
+        int idx = lane + 32 * s;
+        sw[phys(idx)] = (idx < n) ? keys[start + idx] : ~0ull;
+    }
+    __syncwarp(full);
+    uint64_t v[E];
+#pragma unroll
+    for (int s = 0; s < E; ++s) v[s] = sw[phys(lane * E + s)];
+#pragma unroll
+    for (int k = 2; k <= P; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j < E) {
+#pragma unroll
+                for (int s = 0; s < E; ++s) {
+                    if ((s & j) == 0) {
+                        // direction bit of global index lane*E + s
+                        bool asc = (k < E) ? ((s & k) == 0) : (((lane * E) & k) == 0);
+                        cex(v[s], v[s | j], asc);
+                    }
+                }
+            } else {
+                const int lj = j / E;
+                const bool lower = (lane & lj) == 0;
+                const bool asc = ((lane * E) & k) == 0;
+                const bool keep_min = lower == asc;
+#pragma unroll
+                for (int s = 0; s < E; ++s) {
+                    uint64_t o = __shfl_xor_sync(full, v[s], lj);
+                    uint64_t mn = v[s] < o ? v[s] : o, mx = v[s] < o ? o : v[s];
+                    v[s] = keep_min ? mn : mx;
+                }
+            }
+        }
+    }
+    __syncwarp(full);
+    uint32_t* s32 = reinterpret_cast<uint32_t*>(sw);
+#pragma unroll
+    for (int s = 0; s < E; ++s) s32[lane * E + s + lane] = (uint32_t)v[s];   // skew 1 word per lane
+    __syncwarp(full);
+#pragma unroll
+    for (int s = 0; s < E; ++s) {
+        int idx = lane + 32 * s;
+        if (idx < n) out[start + idx] = (int32_t)s32[idx + idx / E];
+    }
+    __syncwarp(full);
+}
+
+__global__ void __launch_bounds__(256)
+bin_sort_warp_kernel(int T, const int32_t* __restrict__ offsets, const uint64_t* __restrict__ keys,
+                     int32_t* __restrict__ ids_sorted) {
+    __shared__ __align__(16) uint64_t s_keys[8 * kWarpSortSlice];
+    const int tile = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (tile >= T) return;
+    const int start = __ldg(offsets + tile);
+    const int n = __ldg(offsets + tile + 1) - start;
+    if (n <= 0 || n > kWarpSortMax) return;
+    uint64_t* sw = s_keys + (threadIdx.x >> 5) * kWarpSortSlice;
+    if (n == 1) { if ((threadIdx.x & 31) == 0) ids_sorted[start] = (int32_t)(uint32_t)keys[start]; }
+    else if (n <= 64) warp_sort_tile<2>(sw, keys, ids_sorted, start, n);
+    else if (n <= 128) warp_sort_tile<4>(sw, keys, ids_sorted, start, n);
+    else if (n <= 256) warp_sort_tile<8>(sw, keys, ids_sorted, start, n);
+    else warp_sort_tile<16>(sw, keys, ids_sorted, start, n);
+}
+
 // Fallback for tiles whose list exceeds the shared-memory cap: same network, in global scratch.
 __global__ void __launch_bounds__(1024)
 bin_sort_big_kernel(int T, const int32_t* __restrict__ offsets, const uint64_t* __restrict__ keys,
@@ -338,9 +426,12 @@ int ts_bin_sort(int num_tiles, const int32_t* tile_offsets, uint64_t* keys, int3
                                            ts::kSmemSortCap * (int)sizeof(uint64_t)), "ts_bin_sort/attr");
         attr_set = true;
     }
-    // size classes: (0,512], (512,2048], (2048,cap]
-    const int bounds[4] = {0, 512, 2048, ts::kSmemSortCap};
-    for (int c = 0; c < 3; ++c) {
+    // lists of <= 512 entries: one warp per tile, keys in registers
+    ts::bin_sort_warp_kernel<<<(num_tiles + 7) / 8, 256, 0, st>>>(num_tiles, tile_offsets, keys, ids_sorted);
+    TS_CHECK_LAUNCH("ts_bin_sort/warp");
+    // longer lists: one CTA per tile in shared memory, size classes (512,2048], (2048,cap]
+    const int bounds[3] = {ts::kWarpSortMax, 2048, ts::kSmemSortCap};
+    for (int c = 0; c < 2; ++c) {
         if (max_count <= bounds[c]) break;
         size_t smem = sizeof(uint64_t) * (size_t)bounds[c + 1];
         ts::bin_sort_kernel<<<num_tiles, ts::kSortThreads, smem, st>>>(num_tiles, tile_offsets, keys, ids_sorted,

@@ -128,11 +128,13 @@ class _RenderFused(Function):
                     tuple(opac_logits.shape), tuple(colors_dc.shape))
         ctx.sink = sink
         ctx.mark_non_differentiable(xys, depths, radii)
-        ctx.set_materialize_grads(False)   # unused outputs (depth, alpha) arrive as None, not zeros
-        return rgb, depth_img, 1.0 - final_T, xys, depths, radii
+        ctx.set_materialize_grads(False)   # unused outputs (depth, T) arrive as None, not zeros
+        # final_T is returned as is (alpha = 1 - T is the caller's one-liner if it wants it):
+        # no extra kernel for an output the adapter never reads
+        return rgb, depth_img, final_T, xys, depths, radii
 
     @staticmethod
-    def backward(ctx, v_rgb, v_depth, v_alpha, _vx, _vd, _vr):
+    def backward(ctx, v_rgb, v_depth, v_T, _vx, _vd, _vr):
         (means_c, scales_c, quats_c, logit_c, view_c, proj_c, bg_c, radii, recs, offsets, ids_sorted,
          final_T, n_contrib, mask) = ctx.saved_tensors
         N, K, W, H, tx, ty, fx, fy, deg, pflags, sflags, opac_shape, dc_shape = ctx.meta
@@ -140,8 +142,9 @@ class _RenderFused(Function):
         dev = means_c.device
         st = _lib.stream_ptr(dev)
         f32 = dict(device=dev, dtype=torch.float32)
-        if v_rgb is None and v_depth is None and v_alpha is None:
+        if v_rgb is None and v_depth is None and v_T is None:
             return (None,) * 16
+        v_alpha = -v_T if v_T is not None else None     # alpha = 1 - T
         v_rgb = _lib.f32c(v_rgb) if v_rgb is not None else None
         v_depth = _lib.f32c(v_depth) if v_depth is not None else None
         v_alpha = _lib.f32c(v_alpha) if v_alpha is not None else None
@@ -179,7 +182,8 @@ def render_fused(means: Tensor, log_scales: Tensor, quats: Tensor, opacity_logit
 
     Inputs are the raw GaussianModel parameters [REF model_gaussian.py:84-89] and DEVICE camera
     matrices (view 4x4, full projection 4x4).  Returns (rgb[H,W,3] unclamped, depth[H,W],
-    alpha[H,W], xys[N,2], depths[N], radii[N]).  `xys.grad` is populated by backward."""
+    final_T[H,W] (alpha = 1 - final_T), xys[N,2], depths[N], radii[N]).  `xys.grad` is populated
+    by backward."""
     sink = XysSink()
     bg = background.to(means.device).float()
     bg4 = torch.cat([bg, bg[:1]])       # depth is composited over background[0] [REF rasterize.py:48-51]
