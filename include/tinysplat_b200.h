@@ -156,6 +156,9 @@ TS_API int ts_bin_smem_sort_cap(void);
  *   contributing list entry; what backward replays from).  With CH == 4 and out_ch3 != NULL
  *   the output is split: out_img[H,W,3] + out_ch3[H,W] (RGB + depth of the fused pass);
  *   backward mirrors it with split_ch3 = 1 (v_out_img[H,W,3] / v_out_ch3[H,W], NULL = 0).
+ *   clamp_max1 (split mode only) folds the adapter's clamp(rgb, max=1) [REF rasterize.py:45]
+ *   in; the clamped-channel mask rides in bits 28..30 of n_contrib and zeroes those
+ *   cotangents in backward.
  * ts_blend_bwd: replays back to front; accumulates per-Gaussian packed gradients
  *   grads[N, ts_grad_floats()] (zeroed by the callee).  v_out_alpha may be NULL.
  * ts_blend_unpack_grads: packed -> v_xys[N,2], v_conics[N,3], v_colors[N,CH], v_opacity[N]. */
@@ -163,7 +166,7 @@ TS_API int ts_blend_fwd(int CH, int img_height, int img_width, int tiles_x, int 
                         const int32_t* tile_offsets, const int32_t* ids_sorted,
                         const float* recs /*[16B]*/, const float* background,
                         float* out_img, float* out_ch3 /*or NULL*/, float* final_T,
-                        int32_t* n_contrib, ts_stream_t stream);
+                        int32_t* n_contrib, int clamp_max1, ts_stream_t stream);
 TS_API int ts_blend_bwd(int N, int CH, int img_height, int img_width, int tiles_x, int tiles_y,
                         const int32_t* tile_offsets, const int32_t* ids_sorted,
                         const float* recs /*[16B]*/, const float* background,

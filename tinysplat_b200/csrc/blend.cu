@@ -16,6 +16,8 @@ namespace ts {
 
 constexpr int kBlendThreads = 256;
 constexpr int kBatch = 256;
+constexpr int kClampShift = 28;                      // n_contrib bits 28..30: clamped-channel mask
+constexpr int kCountMask = (1 << kClampShift) - 1;
 
 // Geometry of the thread->pixel map shared by forward and backward.
 struct PixMap {
@@ -74,7 +76,7 @@ blend_fwd_kernel(int H, int W, int tbx, const int32_t* __restrict__ tile_offsets
                  const int32_t* __restrict__ ids, const float4* __restrict__ recs,
                  const float* __restrict__ background, float* __restrict__ out_img,
                  float* __restrict__ out_ch3, float* __restrict__ final_T,
-                 int32_t* __restrict__ n_contrib) {
+                 int32_t* __restrict__ n_contrib, int clamp_max1) {
     __shared__ __align__(16) float4 s_rec[2][kBatch * 3];
     __shared__ unsigned s_mask[8][8];  // [sub-block][staging warp]
     const unsigned full = 0xffffffffu;
@@ -159,9 +161,17 @@ blend_fwd_kernel(int H, int W, int tbx, const int32_t* __restrict__ tile_offsets
     if (pm.inside) {
         const size_t pix = (size_t)pm.i * W + pm.j;
         if (CH == 4 && out_ch3) {   // split output: RGB image + separate 4th-channel (depth) map
+            // clamp_max1 folds the adapter's clamp(rgb, max=1) [REF rasterize.py:45] in; which
+            // channels were clamped (zero gradient) is kept in the top bits of n_contrib
+            unsigned cm = 0;
 #pragma unroll
-            for (int c = 0; c < 3; ++c) out_img[pix * 3 + c] = fmaf(T, __ldg(background + c), acc[c]);
+            for (int c = 0; c < 3; ++c) {
+                float o = fmaf(T, __ldg(background + c), acc[c]);
+                if (clamp_max1 && o > 1.f) { o = 1.f; cm |= 1u << c; }
+                out_img[pix * 3 + c] = o;
+            }
             out_ch3[pix] = fmaf(T, __ldg(background + 3), acc[CH - 1]);
+            ncon |= (int)(cm << kClampShift);
         } else {
 #pragma unroll
             for (int c = 0; c < CH; ++c) out_img[pix * CH + c] = fmaf(T, __ldg(background + c), acc[c]);
@@ -215,9 +225,12 @@ blend_bwd_kernel(int H, int W, int tbx, const int32_t* __restrict__ tile_offsets
         const size_t pix = (size_t)pm.i * W + pm.j;
         T_final = __ldg(final_T + pix);
         nc = __ldg(n_contrib + pix);
+        const unsigned cm = (unsigned)nc >> kClampShift;    // channels clamped by forward
+        nc &= kCountMask;
         if (CH == 4 && split_ch3) {
 #pragma unroll
-            for (int c = 0; c < 3; ++c) v_out[c] = v_out_img ? __ldg(v_out_img + pix * 3 + c) : 0.f;
+            for (int c = 0; c < 3; ++c)
+                v_out[c] = (v_out_img && !((cm >> c) & 1u)) ? __ldg(v_out_img + pix * 3 + c) : 0.f;
             if (GCH == 4) v_out[CH - 1] = v_out_ch3 ? __ldg(v_out_ch3 + pix) : 0.f;
         } else {
 #pragma unroll
@@ -402,14 +415,14 @@ extern "C" {
 int ts_blend_fwd(int CH, int img_height, int img_width, int tiles_x, int tiles_y,
                  const int32_t* tile_offsets, const int32_t* ids_sorted, const float* recs,
                  const float* background, float* out_img, float* out_ch3, float* final_T,
-                 int32_t* n_contrib, ts_stream_t stream) {
+                 int32_t* n_contrib, int clamp_max1, ts_stream_t stream) {
     if (CH < 1 || CH > 4 || img_height <= 0 || img_width <= 0 || tiles_x <= 0 || tiles_y <= 0) return TS_ERR_INVALID;
     if (!tile_offsets || !background || !out_img || !final_T || !n_contrib) return TS_ERR_INVALID;
     if (recs && !ts::aligned16(recs)) return TS_ERR_ALIGN;
     dim3 grid(tiles_x, tiles_y);
     cudaStream_t st = (cudaStream_t)stream;
 #define TS_LAUNCH_FWD(C) \
-    ts::blend_fwd_kernel<C><<<grid, ts::kBlendThreads, 0, st>>>(img_height, img_width, tiles_x, tile_offsets, ids_sorted, (const float4*)recs, background, out_img, out_ch3, final_T, n_contrib)
+    ts::blend_fwd_kernel<C><<<grid, ts::kBlendThreads, 0, st>>>(img_height, img_width, tiles_x, tile_offsets, ids_sorted, (const float4*)recs, background, out_img, out_ch3, final_T, n_contrib, clamp_max1)
     switch (CH) {
         case 1: TS_LAUNCH_FWD(1); break;
         case 2: TS_LAUNCH_FWD(2); break;

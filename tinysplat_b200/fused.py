@@ -55,7 +55,7 @@ class XysSink:
 class _RenderFused(Function):
     @staticmethod
     def forward(ctx, means, log_scales, quats, opac_logits, colors_dc, colors_rest, view_dev,
-                fullproj_dev, fx, fy, width, height, sh_degree, bg4, cull_mode, sink):
+                fullproj_dev, fx, fy, width, height, sh_degree, bg4, cull_mode, clamp_rgb, sink):
         _lib.require_cuda(means, log_scales, quats, opac_logits, colors_dc, colors_rest)
         lib = _lib.load()
         dev = means.device
@@ -121,7 +121,8 @@ class _RenderFused(Function):
         final_T = torch.empty(H, W, **f32)
         n_contrib = torch.empty(H, W, **i32)
         _lib.call("ts_blend_fwd", 4, H, W, tx, ty, _lib.ptr(offsets), _lib.ptr(ids_sorted), _lib.ptr(recs),
-                  _lib.ptr(bg_c), _lib.ptr(rgb), _lib.ptr(depth_img), _lib.ptr(final_T), _lib.ptr(n_contrib), st)
+                  _lib.ptr(bg_c), _lib.ptr(rgb), _lib.ptr(depth_img), _lib.ptr(final_T), _lib.ptr(n_contrib),
+                  1 if clamp_rgb else 0, st)
         ctx.save_for_backward(means_c, scales_c, quats_c, logit_c, view_c, proj_c, bg_c, radii, recs,
                               offsets, ids_sorted, final_T, n_contrib, mask)
         ctx.meta = (N, K, W, H, tx, ty, float(fx), float(fy), int(sh_degree), pflags, sflags,
@@ -143,7 +144,7 @@ class _RenderFused(Function):
         st = _lib.stream_ptr(dev)
         f32 = dict(device=dev, dtype=torch.float32)
         if v_rgb is None and v_depth is None and v_T is None:
-            return (None,) * 16
+            return (None,) * 17
         v_alpha = -v_T if v_T is not None else None     # alpha = 1 - T
         v_rgb = _lib.f32c(v_rgb) if v_rgb is not None else None
         v_depth = _lib.f32c(v_depth) if v_depth is not None else None
@@ -171,17 +172,19 @@ class _RenderFused(Function):
         if ctx.sink is not None:
             ctx.sink.deliver(v_xys)
         return (v_means, v_scales, v_quats, v_logit.reshape(opac_shape), v_dc.reshape(dc_shape), v_rest,
-                None, None, None, None, None, None, None, None, None, None)
+                None, None, None, None, None, None, None, None, None, None, None)
 
 
 def render_fused(means: Tensor, log_scales: Tensor, quats: Tensor, opacity_logits: Tensor,
                  colors_dc: Tensor, colors_rest: Tensor, view_matrix: Tensor, full_proj: Tensor,
                  fx: float, fy: float, width: int, height: int, sh_degree: int, background: Tensor,
-                 cull_mode: int = 1) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
+                 cull_mode: int = 1, clamp_rgb: bool = True
+                 ) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
     """Fused equivalent of project -> SH(+0.5, clamp) -> rasterise RGB -> rasterise depth.
 
     Inputs are the raw GaussianModel parameters [REF model_gaussian.py:84-89] and DEVICE camera
-    matrices (view 4x4, full projection 4x4).  Returns (rgb[H,W,3] unclamped, depth[H,W],
+    matrices (view 4x4, full projection 4x4).  Returns (rgb[H,W,3] (clamped to <= 1 like the
+    adapter's output [REF rasterize.py:45] unless clamp_rgb=False), depth[H,W],
     final_T[H,W] (alpha = 1 - final_T), xys[N,2], depths[N], radii[N]).  `xys.grad` is populated
     by backward."""
     sink = XysSink()
@@ -189,6 +192,6 @@ def render_fused(means: Tensor, log_scales: Tensor, quats: Tensor, opacity_logit
     bg4 = torch.cat([bg, bg[:1]])       # depth is composited over background[0] [REF rasterize.py:48-51]
     out = _RenderFused.apply(means, log_scales, quats, opacity_logits, colors_dc, colors_rest,
                              view_matrix, full_proj, fx, fy, width, height, sh_degree, bg4,
-                             cull_mode, sink)
+                             cull_mode, clamp_rgb, sink)
     sink.attach(out[3])
     return out

@@ -114,7 +114,7 @@ class _RasterizeGaussians(Function):
         n_contrib = torch.empty(H, W, device=dev, dtype=torch.int32)
         _lib.call("ts_blend_fwd", CH, H, W, tx, ty, _lib.ptr(bins.tile_offsets),
                                     _lib.ptr(bins.ids_sorted), _lib.ptr(recs), _lib.ptr(bg),
-                  _lib.ptr(out_img), None, _lib.ptr(final_T), _lib.ptr(n_contrib),
+                  _lib.ptr(out_img), None, _lib.ptr(final_T), _lib.ptr(n_contrib), 0,
                   _lib.stream_ptr(dev))
         out_alpha = 1.0 - final_T
         ctx.save_for_backward(recs, bins.tile_offsets, bins.ids_sorted, bg, final_T, n_contrib,

@@ -72,7 +72,7 @@ class GaussianRasterizer:
             camera.f_x, camera.f_y, width, height, sh_degree, m.background)
         extras: Dict = {"depth": depth_img, "radii": radii, "xys": xys,
                         "camera": {"height": camera.height, "width": camera.width}}
-        return torch.clamp(rgb, max=1.0), extras
+        return rgb, extras      # already clamped to <= 1 inside the blend kernel
 
     def __call__(self, camera, dims: Optional[Tuple[int, int]], sh_degree: int):
         m = self.model
