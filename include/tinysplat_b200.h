@@ -42,6 +42,7 @@ enum ts_flags {
     TS_PROJ_LOG_SCALES = 1,   /* scales are log-scales: exp() inside, Jacobian in backward */
     TS_PROJ_RAW_QUATS = 2,    /* quats are unnormalised: q/|q| inside, Jacobian in backward */
     TS_PROJ_DEPTH_CH3 = 4,    /* backward: depth cotangent = colour channel 3 of packed grads */
+    TS_PROJ_OPACITY_LOGIT = 8,/* forward pack+count: `opacity` holds logits: sigmoid() inside */
     TS_SH_DIRS_FROM_MEANS = 1,/* `dirs` holds means3d; dir = mean - viewmat[:3,3] */
     TS_SH_OFFSET_CLAMP = 2,   /* colour = max(sh + 0.5, 0); mask of passing channels saved */
     TS_BIN_OPACITY_LOGIT = 1  /* `opacity` holds logits: sigmoid() inside */
@@ -61,7 +62,12 @@ TS_API int64_t ts_launch_count(void);
  * viewmat: 3x4 (first three rows of the 4x4 world->camera matrix), projmat: 4x4 full
  * projection (proj @ view).  Outputs: xys[N,2], depths[N], radii[N] (int32),
  * conics[N,3], num_tiles_hit[N] (int32), cov3d[N,6].  Culled Gaussians get zeros.
- * flags: TS_PROJ_LOG_SCALES | TS_PROJ_RAW_QUATS (0 = the gsplat contract). */
+ * flags: TS_PROJ_LOG_SCALES | TS_PROJ_RAW_QUATS (0 = the gsplat contract).
+ * Fused pipeline: with recs != NULL the kernel also packs the geometry half of the raster
+ * record (recs[N, ts_rec_floats()], floats 0..7) and counts tile intersections into
+ * tile_counts[T] (zeroed by the callee) exactly like ts_bin_count, from `opacity[N]`
+ * (logits with TS_PROJ_OPACITY_LOGIT) and cull_mode; conics / num_tiles_hit / cov3d may then
+ * be NULL (not written). */
 TS_API int ts_project_fwd(int N,
                           const float* means3d /*[16B]*/, const float* scales /*[16B]*/,
                           float glob_scale, const float* quats /*[16B]*/,
@@ -70,8 +76,11 @@ TS_API int ts_project_fwd(int N,
                           int img_height, int img_width, int tiles_x, int tiles_y,
                           float clip_thresh, int flags,
                           float* xys /*[16B]*/, float* depths, int32_t* radii,
-                          float* conics /*[16B]*/, int32_t* num_tiles_hit,
-                          float* cov3d /*[16B]*/, ts_stream_t stream);
+                          float* conics /*[16B] or NULL*/, int32_t* num_tiles_hit /*or NULL*/,
+                          float* cov3d /*[16B] or NULL*/,
+                          const float* opacity /*or NULL*/, int cull_mode,
+                          float* recs /*[16B] or NULL*/, int32_t* tile_counts /*or NULL*/,
+                          ts_stream_t stream);
 
 /* ---- K6: EWA projection backward ---------------------------------------------------
  * Backward of ts_project_fwd: consumes v_xys[N,2], v_depths[N], v_conics[N,3] (each may be

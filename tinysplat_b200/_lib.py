@@ -25,7 +25,7 @@ _SIGNATURES = {
     "ts_grad_floats": ([], C.c_int),
     "ts_launch_count": ([], C.c_int64),
     "ts_project_fwd": ([_i, _p, _p, _f, _p, _p, _p, _f, _f, _f, _f, _i, _i, _i, _i, _f, _i,
-                        _p, _p, _p, _p, _p, _p, _p], C.c_int),
+                        _p, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p], C.c_int),
     "ts_project_bwd": ([_i, _p, _p, _f, _p, _p, _p, _f, _f, _f, _f, _i, _i, _i,
                         _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p], C.c_int),
     "ts_sh_fwd": ([_i, _i, _i, _p, _p, _p, _p, _p, _i, _p, _p, _i, _p], C.c_int),
@@ -41,7 +41,7 @@ _SIGNATURES = {
 }
 
 # flags (include/tinysplat_b200.h enum ts_flags)
-PROJ_LOG_SCALES, PROJ_RAW_QUATS, PROJ_DEPTH_CH3 = 1, 2, 4
+PROJ_LOG_SCALES, PROJ_RAW_QUATS, PROJ_DEPTH_CH3, PROJ_OPACITY_LOGIT = 1, 2, 4, 8
 SH_DIRS_FROM_MEANS, SH_OFFSET_CLAMP = 1, 2
 BIN_OPACITY_LOGIT = 1
 

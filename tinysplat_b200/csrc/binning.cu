@@ -13,63 +13,13 @@
 //            sort of the emission order), writes the 32-bit id list.
 // Traffic per intersection: 8 B write + 8 B read + 4 B write, vs ~150 B for 6 radix passes.
 #include "ts_common.cuh"
+#include "ts_binning.cuh"
 
 namespace ts {
 
 constexpr int kBinThreads = 256;
 constexpr int kSortThreads = 256;
 constexpr int kSmemSortCap = 16384;  // 128 KB of 64-bit keys
-constexpr int kCoopThreshold = 8;    // rects larger than this are expanded by the whole warp
-
-// Tile rectangle [lo,hi) of a packed record: 3-sigma bbox ∩ opacity-aware footprint.
-__device__ __forceinline__ void tile_rect(float4 q0, float radius, int tbx, int tby, int cull,
-                                          int& lox, int& loy, int& hix, int& hiy) {
-    tile_bbox(q0.x, q0.y, radius, tbx, tby, lox, loy, hix, hiy);
-    if (cull) {
-        // pixel centres of tile t along x: 16t + 0.5 .. 16t + 15.5
-        float fl = ceilf((q0.x - q0.z - 15.5f) * (1.f / kBlock));
-        float fh = floorf((q0.x + q0.z - 0.5f) * (1.f / kBlock));
-        float gl = ceilf((q0.y - q0.w - 15.5f) * (1.f / kBlock));
-        float gh = floorf((q0.y + q0.w - 0.5f) * (1.f / kBlock));
-        fl = fminf(fmaxf(fl, -1.f), 1e9f); gl = fminf(fmaxf(gl, -1.f), 1e9f);
-        fh = fminf(fmaxf(fh, -2.f), 1e9f); gh = fminf(fmaxf(gh, -2.f), 1e9f);
-        lox = max(lox, (int)fl); loy = max(loy, (int)gl);
-        hix = min(hix, (int)fh + 1); hiy = min(hiy, (int)gh + 1);
-        if (hix < lox) hix = lox;
-        if (hiy < loy) hiy = loy;
-    }
-}
-
-// Run f(tile_id, payload) for every tile of every lane's rectangle.  Small rectangles are
-// walked by their own lane; large ones are expanded cooperatively by the whole warp (payload
-// broadcast from the owning lane) so that one screen-filling Gaussian does not serialise
-// thousands of atomics on a single lane.  Must be reached by all 32 lanes.
-template <typename F>
-__device__ __forceinline__ void for_each_tile(int lox, int loy, int hix, int hiy, int tbx,
-                                              uint32_t pay_lo, uint32_t pay_hi, F f) {
-    const unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    int w = hix - lox, h = hiy - loy;
-    int n = (w > 0 && h > 0) ? w * h : 0;
-    if (n > 0 && n <= kCoopThreshold) {
-        for (int y = loy; y < hiy; ++y)
-            for (int x = lox; x < hix; ++x) f(y * tbx + x, pay_lo, pay_hi);
-    }
-    __syncwarp(full);
-    unsigned big = __ballot_sync(full, n > kCoopThreshold);
-    while (big) {
-        int src = __ffs(big) - 1;
-        big &= big - 1;
-        int slox = __shfl_sync(full, lox, src), sloy = __shfl_sync(full, loy, src);
-        int sw = __shfl_sync(full, w, src), sn = __shfl_sync(full, n, src);
-        uint32_t plo = __shfl_sync(full, pay_lo, src), phi = __shfl_sync(full, pay_hi, src);
-        for (int k = lane; k < sn; k += 32) {
-            int y = k / sw, x = k - y * sw;
-            f((sloy + y) * tbx + slox + x, plo, phi);
-        }
-    }
-}
-
 template <int CH>
 __global__ void __launch_bounds__(kBinThreads)
 bin_count_kernel(int N, const float2* __restrict__ xys, const int32_t* __restrict__ radii,
@@ -84,19 +34,8 @@ bin_count_kernel(int N, const float2* __restrict__ xys, const int32_t* __restric
         float a = __ldg(conics + 3 * i), b = __ldg(conics + 3 * i + 1), c = __ldg(conics + 3 * i + 2);
         float op = __ldg(opacity + i);
         if (flags & TS_BIN_OPACITY_LOGIT) op = 1.f / (1.f + expf(-op));   // sigmoid [REF rasterize.py:86]
-        float hx = 1e30f, hy = 1e30f;
-        if (cull) {
-            // footprint of alpha >= 1/255:  sigma <= tau = ln(255*opac);  half extents of the
-            // ellipse's axis-aligned box are sqrt(2*tau*cov_xx), sqrt(2*tau*cov_yy), cov = conic^-1
-            float tau = __logf(255.f * op);
-            float det = a * c - b * b;
-            if (!(op * 255.f >= 1.f)) { hx = -1e30f; hy = -1e30f; }       // can never reach 1/255
-            else if (det > 0.f && a > 0.f && c > 0.f) {
-                float two_tau = 2.f * (tau + 0.01f);
-                hx = sqrtf(two_tau * c / det) * 1.001f + 0.01f;
-                hy = sqrtf(two_tau * a / det) * 1.001f + 0.01f;
-            }
-        }
+        float hx, hy;
+        footprint_extent(a, b, c, op, cull, hx, hy);
         float4 q0 = make_float4(xy.x, xy.y, hx, hy);
         float4 q1 = make_float4(0.5f * kLog2e * a, kLog2e * b, 0.5f * kLog2e * c, op);
         recs[3 * (size_t)i] = q0;

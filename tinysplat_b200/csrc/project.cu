@@ -2,6 +2,7 @@
 // Gaussian, AoS [N,3]/[N,6] arrays staged through shared memory with 128-bit accesses).
 // Replaces gsplat.project_gaussians fwd/bwd  [REF tinysplat/splatting/rasterize.py:32,64-73].
 #include "ts_common.cuh"
+#include "ts_binning.cuh"
 
 namespace ts {
 
@@ -122,7 +123,9 @@ project_fwd_kernel(int N, const float* __restrict__ means, const float* __restri
                    float fx, float fy, float cx, float cy, int H, int W, int tbx, int tby,
                    float clip, int flags, float2* __restrict__ xys, float* __restrict__ depths,
                    int32_t* __restrict__ radii, float* __restrict__ conics,
-                   int32_t* __restrict__ ntiles, float* __restrict__ cov3d) {
+                   int32_t* __restrict__ ntiles, float* __restrict__ cov3d,
+                   const float* __restrict__ opacity, int cull, float4* __restrict__ recs,
+                   int32_t* __restrict__ tile_counts) {
     constexpr int TH = kProjThreads;
     __shared__ __align__(16) float s_buf[TH * 9];
     const int item0 = blockIdx.x * TH;
@@ -178,11 +181,29 @@ project_fwd_kernel(int N, const float* __restrict__ means, const float* __restri
         xys[i] = ok ? make_float2(px, py) : make_float2(0.f, 0.f);
         depths[i] = ok ? st.t[2] : 0.f;
         radii[i] = ok ? (int32_t)radius : 0;
-        ntiles[i] = ok ? area : 0;
+        if (ntiles) ntiles[i] = ok ? area : 0;
+    }
+    if (recs) {
+        // fused pipeline: pack the geometry half of the raster record and count the tiles this
+        // Gaussian's footprint can reach, here, while everything is still in registers
+        // (replaces the separate ts_bin_count pass and its re-read of xys/conics/radii)
+        int rlox = 0, rloy = 0, rhix = 0, rhiy = 0;
+        if (ok) {
+            float op = __ldg(opacity + i);
+            if (flags & TS_PROJ_OPACITY_LOGIT) op = 1.f / (1.f + expf(-op));
+            float hx, hy;
+            footprint_extent(con0, con1, con2, op, cull, hx, hy);
+            const float4 q0 = make_float4(px, py, hx, hy);
+            recs[3 * (size_t)i] = q0;
+            recs[3 * (size_t)i + 1] = make_float4(0.5f * kLog2e * con0, kLog2e * con1, 0.5f * kLog2e * con2, op);
+            tile_rect(q0, radius, tbx, tby, cull, rlox, rloy, rhix, rhiy);
+        }
+        for_each_tile(rlox, rloy, rhix, rhiy, tbx, 0u, 0u,
+                      [&](int tile, uint32_t, uint32_t) { atomicAdd(tile_counts + tile, 1); });
     }
     __syncthreads();
-    block_store<3, TH>(conics, s_buf, item0, N);
-    block_store<6, TH>(cov3d, s_buf + 3 * TH, item0, N);
+    if (conics) block_store<3, TH>(conics, s_buf, item0, N);
+    if (cov3d) block_store<6, TH>(cov3d, s_buf + 3 * TH, item0, N);
 }
 
 __global__ void __launch_bounds__(kProjThreads)
@@ -352,20 +373,27 @@ int ts_project_fwd(int N, const float* means3d, const float* scales, float glob_
                    float fy, float cx, float cy, int img_height, int img_width, int tiles_x,
                    int tiles_y, float clip_thresh, int flags, float* xys, float* depths,
                    int32_t* radii, float* conics, int32_t* num_tiles_hit, float* cov3d,
+                   const float* opacity, int cull_mode, float* recs, int32_t* tile_counts,
                    ts_stream_t stream) {
     if (N < 0 || img_height <= 0 || img_width <= 0 || tiles_x <= 0 || tiles_y <= 0) return TS_ERR_INVALID;
+    if (recs && (!opacity || !tile_counts)) return TS_ERR_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (recs)
+        TS_CHECK_CUDA(cudaMemsetAsync(tile_counts, 0, sizeof(int32_t) * (size_t)tiles_x * tiles_y, st),
+                      "ts_project_fwd/memset");
     if (N == 0) return TS_OK;
-    if (!means3d || !scales || !quats || !viewmat || !projmat || !xys || !depths || !radii ||
-        !conics || !num_tiles_hit || !cov3d)
+    if (!means3d || !scales || !quats || !viewmat || !projmat || !xys || !depths || !radii)
         return TS_ERR_INVALID;
+    if (!recs && (!conics || !num_tiles_hit || !cov3d)) return TS_ERR_INVALID;
     if (!ts::aligned16(means3d) || !ts::aligned16(scales) || !ts::aligned16(quats) ||
-        !ts::aligned16(xys) || !ts::aligned16(conics) || !ts::aligned16(cov3d))
+        !ts::aligned16(xys) || (conics && !ts::aligned16(conics)) || (cov3d && !ts::aligned16(cov3d)) ||
+        (recs && !ts::aligned16(recs)))
         return TS_ERR_ALIGN;
     int grid = (N + ts::kProjThreads - 1) / ts::kProjThreads;
-    ts::project_fwd_kernel<<<grid, ts::kProjThreads, 0, (cudaStream_t)stream>>>(
+    ts::project_fwd_kernel<<<grid, ts::kProjThreads, 0, st>>>(
         N, means3d, scales, glob_scale, (const float4*)quats, viewmat, projmat, fx, fy, cx, cy,
         img_height, img_width, tiles_x, tiles_y, clip_thresh, flags, (float2*)xys, depths, radii,
-        conics, num_tiles_hit, cov3d);
+        conics, num_tiles_hit, cov3d, opacity, cull_mode, (float4*)recs, tile_counts);
     TS_CHECK_LAUNCH("ts_project_fwd");
     return TS_OK;
 }

@@ -77,18 +77,14 @@ class _RenderFused(Function):
         xys = torch.empty(N, 2, **f32)
         depths = torch.empty(N, **f32)
         radii = torch.empty(N, **i32)
-        conics = torch.empty(N, 3, **f32)
-        ntiles = torch.empty(N, **i32)
-        cov3d = torch.empty(N, 6, **f32)
-        _lib.call("ts_project_fwd", N, _lib.ptr(means_c), _lib.ptr(scales_c), 1.0, _lib.ptr(quats_c),
-                  _lib.ptr(view_c), _lib.ptr(proj_c), float(fx), float(fy), W / 2, H / 2, H, W, tx, ty,
-                  0.01, pflags, _lib.ptr(xys), _lib.ptr(depths), _lib.ptr(radii), _lib.ptr(conics),
-                  _lib.ptr(ntiles), _lib.ptr(cov3d), st)
         recs = torch.empty(N, lib.ts_rec_floats(), **f32)
         counts = torch.empty(T, **i32)
-        _lib.call("ts_bin_count", N, 4, _lib.ptr(xys), _lib.ptr(depths), _lib.ptr(radii), _lib.ptr(conics),
-                  _lib.ptr(logit_c), None, H, W, tx, ty, int(cull_mode), _lib.BIN_OPACITY_LOGIT,
-                  _lib.ptr(recs), _lib.ptr(counts), st)
+        # projection + record packing + tile counting in one pass (conics/cov3d/num_tiles_hit are
+        # not materialised: nothing downstream of the fused node reads them)
+        _lib.call("ts_project_fwd", N, _lib.ptr(means_c), _lib.ptr(scales_c), 1.0, _lib.ptr(quats_c),
+                  _lib.ptr(view_c), _lib.ptr(proj_c), float(fx), float(fy), W / 2, H / 2, H, W, tx, ty,
+                  0.01, pflags | _lib.PROJ_OPACITY_LOGIT, _lib.ptr(xys), _lib.ptr(depths), _lib.ptr(radii),
+                  None, None, None, _lib.ptr(logit_c), int(cull_mode), _lib.ptr(recs), _lib.ptr(counts), st)
         offsets = torch.empty(T + 1, **i32)
         stats = torch.empty(4, **i32)
         _lib.call("ts_bin_scan", T, _lib.ptr(counts), _lib.ptr(offsets), _lib.ptr(stats),

@@ -39,7 +39,7 @@ class _ProjectGaussians(Function):
             _lib.ptr(view_c), _lib.ptr(proj_c), args[1], args[2], args[3], args[4], args[5], args[6],
             int(tile_bounds[0]), int(tile_bounds[1]), float(clip_thresh), 0,
             _lib.ptr(xys), _lib.ptr(depths), _lib.ptr(radii), _lib.ptr(conics),
-            _lib.ptr(num_tiles_hit), _lib.ptr(cov3d), _lib.stream_ptr(dev))
+            _lib.ptr(num_tiles_hit), _lib.ptr(cov3d), None, 0, None, None, _lib.stream_ptr(dev))
         ctx.save_for_backward(means_c, scales_c, quats_c, view_c, proj_c, radii)
         ctx.args = args
         ctx.mark_non_differentiable(radii, num_tiles_hit, cov3d)
