@@ -435,6 +435,8 @@ def run_ours(args):
                    "e2e_step": "H2D target image + camera, adapter forward, L1 loss, backward, loss.item()",
                    "parallelism": f"dp{world} over cameras, replica per GPU, NCCL grad all-reduce"
                    if world > 1 and not fwd_only else ("replicas only" if world > 1 else "single GPU"),
+                   "grad_allreduce_collectives_per_step": (reducer.last_num_collectives if reducer else 0),
+                   "grad_allreduce_bytes": (reducer.payload_bytes() if (reducer and world > 1) else 0),
                    "l2": "inputs larger than L2: 236 B/Gaussian parameters + 48 B records + image buffers "
                          "> 126 MB; a different camera every step"},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -151,14 +151,21 @@ class _RenderFused(Function):
                   _lib.ptr(v_alpha), _lib.ptr(grads), st)
         # colours first: the largest gradient (colors_rest) becomes available for its all-reduce
         # while projection-backward is still running (parallel.py)
-        v_dc = torch.empty(N, 1, 3, **f32)
-        v_rest = torch.empty(N, K - 1, 3, **f32)
+        # all six parameter gradients are views of ONE flat buffer: autograd hands the views to
+        # .grad without copying, and the data-parallel reducer (parallel.py) then needs a single
+        # NCCL all-reduce over the flat span instead of six
+        sizes = [(K - 1) * 3 * N, 3 * N, 3 * N, 3 * N, 4 * N, N]      # rest, dc, means, scales, quats, logit
+        offs, total = [], 0
+        for sz in sizes:
+            offs.append(total)
+            total += (sz + 3) // 4 * 4                                # keep every segment 16-byte aligned
+        flat = torch.empty(total, **f32)
+        seg = lambda i, *shape: flat[offs[i]:offs[i] + sizes[i]].view(*shape)
+        v_rest, v_dc = seg(0, N, K - 1, 3), seg(1, N, 1, 3)
+        v_means, v_scales, v_quats, v_logit = seg(2, N, 3), seg(3, N, 3), seg(4, N, 4), seg(5, N)
+        # colours first: the largest gradient is produced before projection-backward runs
         _lib.call("ts_sh_bwd", N, deg, K, _lib.ptr(means_c), _lib.ptr(view_c), grads.data_ptr() + 32, 12,
                   _lib.ptr(mask), _lib.ptr(v_dc), _lib.ptr(v_rest), sflags, st)
-        v_means = torch.empty(N, 3, **f32)
-        v_scales = torch.empty(N, 3, **f32)
-        v_quats = torch.empty(N, 4, **f32)
-        v_logit = torch.empty(N, **f32)
         v_xys = torch.empty(N, 2, **f32)
         _lib.call("ts_project_bwd", N, _lib.ptr(means_c), _lib.ptr(scales_c), 1.0, _lib.ptr(quats_c),
                   _lib.ptr(view_c), _lib.ptr(proj_c), fx, fy, W / 2, H / 2, H, W,

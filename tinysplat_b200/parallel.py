@@ -22,7 +22,12 @@ from torch import Tensor
 
 
 class GradientAllReducer:
-    """Overlapped all-reduce(sum or mean) of .grad for a fixed list of leaf tensors."""
+    """All-reduce (mean or sum) of .grad for a fixed list of leaf tensors.
+
+    Launch happens from the post-accumulate-grad hook of the LAST parameter to receive its
+    gradient, i.e. as early as autograd allows.  Gradients that are views of one flat buffer
+    (the fused node allocates them that way) are reduced with a single collective over the
+    buffer's span; anything else falls back to one collective per tensor."""
 
     def __init__(self, params: Iterable[Tensor], process_group=None, average: bool = True,
                  overlap: bool = True):
@@ -30,10 +35,14 @@ class GradientAllReducer:
         self.group = process_group
         self.average = average
         self.overlap = overlap
-        self._works = []
+        self._works = []       # (tensor that was reduced, work handle)
         self._handles = []
+        self._ready = 0
+        self._launched = False
+        self.last_num_collectives = 0
         self._enabled = dist.is_available() and dist.is_initialized() and \
             dist.get_world_size(process_group) > 1
+        self._native_avg = self._enabled and dist.get_backend(process_group) == "nccl"
         if self._enabled and overlap:
             for p in self.params:
                 self._handles.append(p.register_post_accumulate_grad_hook(self._hook))
@@ -43,23 +52,51 @@ class GradientAllReducer:
         return dist.get_world_size(self.group) if self._enabled else 1
 
     def _hook(self, p: Tensor) -> None:
-        self._works.append((p, dist.all_reduce(p.grad, op=dist.ReduceOp.SUM, group=self.group,
-                                               async_op=True)))
+        self._ready += 1
+        if self._ready == len(self.params):
+            self._launch()
+
+    def _spans(self):
+        """Group gradients by storage; a group whose members tile one span densely becomes one
+        flat tensor over that span."""
+        groups = {}
+        for p in self.params:
+            if p.grad is not None:
+                groups.setdefault(p.grad.untyped_storage().data_ptr(), []).append(p.grad)
+        out = []
+        for grads in groups.values():
+            if len(grads) > 1 and all(g.is_contiguous() for g in grads):
+                lo = min(g.storage_offset() for g in grads)
+                hi = max(g.storage_offset() + g.numel() for g in grads)
+                used = sum(g.numel() for g in grads)
+                if hi - lo <= used + 4 * len(grads):        # only alignment padding in between
+                    flat = torch.empty(0, dtype=grads[0].dtype, device=grads[0].device)
+                    flat.set_(grads[0].untyped_storage(), lo, (hi - lo,))
+                    out.append(flat)
+                    continue
+            out.extend(grads)
+        return out
+
+    def _launch(self) -> None:
+        op = dist.ReduceOp.AVG if (self.average and self._native_avg) else dist.ReduceOp.SUM
+        for t in self._spans():
+            self._works.append((t, dist.all_reduce(t, op=op, group=self.group, async_op=True)))
+        self.last_num_collectives = len(self._works)
+        self._launched = True
 
     def finish(self) -> None:
-        """Wait for the in-flight reductions (or run them now when overlap is off)."""
+        """Wait for the in-flight reductions (launching them now if the hooks did not)."""
         if not self._enabled:
             return
-        if not self.overlap:
-            for p in self.params:
-                if p.grad is not None:
-                    self._works.append((p, dist.all_reduce(p.grad, op=dist.ReduceOp.SUM,
-                                                           group=self.group, async_op=True)))
-        for p, w in self._works:
+        if not self._launched:
+            self._launch()
+        for t, w in self._works:
             w.wait()
-            if self.average:
-                p.grad.div_(self.world_size)
+            if self.average and not self._native_avg:
+                t.div_(self.world_size)
         self._works.clear()
+        self._ready = 0
+        self._launched = False
 
     def payload_bytes(self) -> int:
         return sum(p.numel() * p.element_size() for p in self.params)
