@@ -134,11 +134,12 @@ TS_API int ts_sh_bwd(int N, int degree, int K, const float* dirs /*[16B]*/,
  * ts_bin_count : packs one raster record per Gaussian (recs[N, ts_rec_floats()]; the colour
  *                float4 is skipped when colors == NULL, ts_sh_fwd then writes it) and
  *                counts, per tile, the Gaussians whose footprint can reach a pixel of it
- *                (tile_counts[T], zeroed by the callee).  CH = colour channels (1..4).
+ *                (tile_counts[T * ts_bin_counter_stride()], zeroed by the callee).  CH = colour
+ *                channels (1..4).
  * ts_bin_scan  : exclusive scan -> tile_offsets[T+1]; stats[4] = {total M, max per-tile
  *                count, number of tiles whose count exceeds smem_sort_cap, 0}.
  * ts_bin_emit  : writes keys[M] = depth_bits<<32 | gaussian_id grouped by tile
- *                (cursors[T] is scratch).
+ *                (cursors = the tile_counts buffer after ts_bin_scan).
  * ts_bin_sort  : sorts every tile's keys in place and writes ids_sorted[M] (gaussian ids,
  *                front to back, ties by gaussian id).  big_scratch must hold
  *                n_big_tiles * next_pow2(max_count) uint64 when n_big_tiles > 0. */
@@ -147,7 +148,7 @@ TS_API int ts_bin_count(int N, int CH, const float* xys, const float* depths,
                         const float* colors, int img_height, int img_width,
                         int tiles_x, int tiles_y, int cull_mode, int flags,
                         float* recs /*[16B]*/, int32_t* tile_counts, ts_stream_t stream);
-TS_API int ts_bin_scan(int num_tiles, const int32_t* tile_counts, int32_t* tile_offsets,
+TS_API int ts_bin_scan(int num_tiles, int32_t* tile_counts, int32_t* tile_offsets,
                        int32_t* stats, int smem_sort_cap, ts_stream_t stream);
 TS_API int ts_bin_emit(int N, const float* depths, const int32_t* radii,
                        const float* recs /*[16B]*/, int tiles_x, int tiles_y, int cull_mode,
@@ -156,6 +157,10 @@ TS_API int ts_bin_emit(int N, const float* depths, const int32_t* radii,
 TS_API int ts_bin_sort(int num_tiles, const int32_t* tile_offsets, uint64_t* keys,
                        int32_t* ids_sorted, int max_count, int n_big_tiles,
                        uint64_t* big_scratch, int32_t* big_counter, ts_stream_t stream);
+/* Per-tile counters are strided: tile t's counter is tile_counts[t * ts_bin_counter_stride()]
+ * (one per 128-byte line: L2 serialises atomics per line).  ts_bin_scan rewrites each counter
+ * in place with the tile's exclusive offset, so the same buffer is ts_bin_emit's `cursors`. */
+TS_API int ts_bin_counter_stride(void);
 /* Largest per-tile list ts_bin_sort sorts in shared memory. */
 TS_API int ts_bin_smem_sort_cap(void);
 

@@ -51,7 +51,7 @@ bin_count_kernel(int N, const float2* __restrict__ xys, const int32_t* __restric
         if (r > 0) tile_rect(q0, (float)r, tbx, tby, cull, lox, loy, hix, hiy);
     }
     for_each_tile(lox, loy, hix, hiy, tbx, 0u, 0u,
-                  [&](int tile, uint32_t, uint32_t) { atomicAdd(tile_counts + tile, 1); });
+                  [&](int tile, uint32_t, uint32_t) { atomicAdd(tile_counts + (size_t)tile * kCounterStride, 1); });
 }
 
 __global__ void __launch_bounds__(kBinThreads)
@@ -81,7 +81,7 @@ bin_emit_kernel(int N, const float* __restrict__ depths, const int32_t* __restri
 #pragma unroll
             for (int k = 0; k < kCoopThreshold; ++k) {
                 if (k < n) {
-                    slots[k] = atomicAdd(cursors + y * tbx + x, 1);
+                    slots[k] = atomicAdd(cursors + (size_t)(y * tbx + x) * kCounterStride, 1);
                     if (++x == hix) { x = lox; ++y; }
                 }
             }
@@ -93,14 +93,14 @@ bin_emit_kernel(int N, const float* __restrict__ depths, const int32_t* __restri
     }
     for_each_tile(lox, loy, hix, hiy, tbx, (uint32_t)key, (uint32_t)(key >> 32),
                   [&](int tile, uint32_t lo, uint32_t hi) {
-                      int slot = atomicAdd(cursors + tile, 1);
+                      int slot = atomicAdd(cursors + (size_t)tile * kCounterStride, 1);
                       keys[slot] = ((uint64_t)hi << 32) | lo;
                   });
 }
 
 // Single-CTA exclusive scan over the tile counts + max / oversize statistics.
 __global__ void __launch_bounds__(1024)
-bin_scan_kernel(int T, const int32_t* __restrict__ counts, int32_t* __restrict__ offsets,
+bin_scan_kernel(int T, int32_t* __restrict__ counts, int32_t* __restrict__ offsets,
                 int32_t* __restrict__ stats, int cap) {
     __shared__ int s_warp[32];
     __shared__ int s_carry;
@@ -111,7 +111,7 @@ bin_scan_kernel(int T, const int32_t* __restrict__ counts, int32_t* __restrict__
     int lmax = 0, lbig = 0;
     for (int base = 0; base < T; base += 1024) {
         int idx = base + tid;
-        int v = (idx < T) ? __ldg(counts + idx) : 0;
+        int v = (idx < T) ? counts[(size_t)idx * kCounterStride] : 0;
         lmax = max(lmax, v);
         lbig += (v > cap) ? 1 : 0;
         int x = v;
@@ -135,7 +135,10 @@ bin_scan_kernel(int T, const int32_t* __restrict__ counts, int32_t* __restrict__
         __syncthreads();
         int carry = s_carry;
         int excl = carry + s_warp[warp] + x - v;
-        if (idx < T) offsets[idx] = excl;
+        if (idx < T) {
+            offsets[idx] = excl;
+            counts[(size_t)idx * kCounterStride] = excl;   // the counter becomes the tile's emit cursor
+        }
         __syncthreads();
         if (tid == 1023) s_carry = excl + v;
         __syncthreads();
@@ -219,31 +222,41 @@ __device__ __forceinline__ void warp_sort_tile(uint64_t* sw, const uint64_t* __r
     uint64_t v[E];
 #pragma unroll
     for (int s = 0; s < E; ++s) v[s] = sw[phys(lane * E + s)];
+    // phase 1 (k <= E): every lane sorts its own E keys in registers, fully unrolled
 #pragma unroll
-    for (int k = 2; k <= P; k <<= 1) {
+    for (int k = 2; k <= E; k <<= 1) {
 #pragma unroll
         for (int j = k >> 1; j > 0; j >>= 1) {
-            if (j < E) {
 #pragma unroll
-                for (int s = 0; s < E; ++s) {
-                    if ((s & j) == 0) {
-                        // direction bit of global index lane*E + s
-                        bool asc = (k < E) ? ((s & k) == 0) : (((lane * E) & k) == 0);
-                        cex(v[s], v[s | j], asc);
-                    }
-                }
-            } else {
-                const int lj = j / E;
-                const bool lower = (lane & lj) == 0;
-                const bool asc = ((lane * E) & k) == 0;
-                const bool keep_min = lower == asc;
-#pragma unroll
-                for (int s = 0; s < E; ++s) {
-                    uint64_t o = __shfl_xor_sync(full, v[s], lj);
-                    uint64_t mn = v[s] < o ? v[s] : o, mx = v[s] < o ? o : v[s];
-                    v[s] = keep_min ? mn : mx;
+            for (int s = 0; s < E; ++s) {
+                if ((s & j) == 0) {
+                    // direction = bit k of the global index lane*E + s
+                    bool asc = (k < E) ? ((s & k) == 0) : ((lane & 1) == 0);
+                    cex(v[s], v[s | j], asc);
                 }
             }
+        }
+    }
+    // phase 2 (k = 2E .. P): runtime loops keep the code small (the fully unrolled network
+    // stalled on instruction fetch); each k = cross-lane stages by shuffle + an in-lane merge
+#pragma unroll 1
+    for (int k = 2 * E; k <= P; k <<= 1) {
+        const bool asc = ((lane * E) & k) == 0;
+#pragma unroll 1
+        for (int lj = k / (2 * E); lj > 0; lj >>= 1) {
+            const bool keep_min = ((lane & lj) == 0) == asc;
+#pragma unroll
+            for (int s = 0; s < E; ++s) {
+                uint64_t o = __shfl_xor_sync(full, v[s], lj);
+                uint64_t mn = v[s] < o ? v[s] : o, mx = v[s] < o ? o : v[s];
+                v[s] = keep_min ? mn : mx;
+            }
+        }
+#pragma unroll
+        for (int j = E >> 1; j > 0; j >>= 1) {
+#pragma unroll
+            for (int s = 0; s < E; ++s)
+                if ((s & j) == 0) cex(v[s], v[s | j], asc);
         }
     }
     __syncwarp(full);
@@ -309,7 +322,8 @@ int ts_bin_count(int N, int CH, const float* xys, const float* depths, const int
     if (N < 0 || CH < 1 || CH > 4 || tiles_x <= 0 || tiles_y <= 0) return TS_ERR_INVALID;
     if (!tile_counts) return TS_ERR_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
-    TS_CHECK_CUDA(cudaMemsetAsync(tile_counts, 0, sizeof(int32_t) * (size_t)tiles_x * tiles_y, st), "ts_bin_count/memset");
+    TS_CHECK_CUDA(cudaMemsetAsync(tile_counts, 0, sizeof(int32_t) * ts::kCounterStride * (size_t)tiles_x * tiles_y, st),
+                  "ts_bin_count/memset");
     if (N == 0) return TS_OK;
     if (!xys || !radii || !conics || !opacity || !recs) return TS_ERR_INVALID;
     if (!ts::aligned16(recs) || (reinterpret_cast<uintptr_t>(xys) & 7u)) return TS_ERR_ALIGN;
@@ -327,7 +341,9 @@ int ts_bin_count(int N, int CH, const float* xys, const float* depths, const int
     return TS_OK;
 }
 
-int ts_bin_scan(int num_tiles, const int32_t* tile_counts, int32_t* tile_offsets, int32_t* stats,
+int ts_bin_counter_stride(void) { return ts::kCounterStride; }
+
+int ts_bin_scan(int num_tiles, int32_t* tile_counts, int32_t* tile_offsets, int32_t* stats,
                 int smem_sort_cap, ts_stream_t stream) {
     if (num_tiles <= 0 || !tile_counts || !tile_offsets || !stats) return TS_ERR_INVALID;
     ts::bin_scan_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(num_tiles, tile_counts, tile_offsets, stats, smem_sort_cap);
@@ -343,8 +359,6 @@ int ts_bin_emit(int N, const float* depths, const int32_t* radii, const float* r
     if (!depths || !radii || !recs || !tile_offsets || !cursors || !keys) return TS_ERR_INVALID;
     if (!ts::aligned16(recs)) return TS_ERR_ALIGN;
     cudaStream_t st = (cudaStream_t)stream;
-    TS_CHECK_CUDA(cudaMemcpyAsync(cursors, tile_offsets, sizeof(int32_t) * (size_t)tiles_x * tiles_y,
-                                  cudaMemcpyDeviceToDevice, st), "ts_bin_emit/memcpy");
     int grid = (N + ts::kBinThreads - 1) / ts::kBinThreads;
     ts::bin_emit_kernel<<<grid, ts::kBinThreads, 0, st>>>(N, depths, radii, (const float4*)recs, tiles_x,
                                                           tiles_y, cull_mode, cursors, keys);

@@ -199,7 +199,7 @@ project_fwd_kernel(int N, const float* __restrict__ means, const float* __restri
             tile_rect(q0, radius, tbx, tby, cull, rlox, rloy, rhix, rhiy);
         }
         for_each_tile(rlox, rloy, rhix, rhiy, tbx, 0u, 0u,
-                      [&](int tile, uint32_t, uint32_t) { atomicAdd(tile_counts + tile, 1); });
+                      [&](int tile, uint32_t, uint32_t) { atomicAdd(tile_counts + (size_t)tile * kCounterStride, 1); });
     }
     __syncthreads();
     if (conics) block_store<3, TH>(conics, s_buf, item0, N);
@@ -379,7 +379,7 @@ int ts_project_fwd(int N, const float* means3d, const float* scales, float glob_
     if (recs && (!opacity || !tile_counts)) return TS_ERR_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
     if (recs)
-        TS_CHECK_CUDA(cudaMemsetAsync(tile_counts, 0, sizeof(int32_t) * (size_t)tiles_x * tiles_y, st),
+        TS_CHECK_CUDA(cudaMemsetAsync(tile_counts, 0, sizeof(int32_t) * ts::kCounterStride * (size_t)tiles_x * tiles_y, st),
                       "ts_project_fwd/memset");
     if (N == 0) return TS_OK;
     if (!means3d || !scales || !quats || !viewmat || !projmat || !xys || !depths || !radii)

@@ -5,6 +5,9 @@
 namespace ts {
 
 constexpr int kCoopThreshold = 8;    // rects larger than this are expanded by the whole warp
+// Per-tile counters / cursors live one per 128-byte line: L2 serialises atomics per line, and
+// adjacent 4-byte counters (32 tiles per line) made the count/emit passes contention-bound.
+constexpr int kCounterStride = 32;   // in int32 elements
 
 // Tile rectangle [lo,hi) of a packed record: 3-sigma bbox ∩ opacity-aware footprint.
 __device__ __forceinline__ void tile_rect(float4 q0, float radius, int tbx, int tby, int cull,

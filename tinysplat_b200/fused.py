@@ -78,7 +78,7 @@ class _RenderFused(Function):
         depths = torch.empty(N, **f32)
         radii = torch.empty(N, **i32)
         recs = torch.empty(N, lib.ts_rec_floats(), **f32)
-        counts = torch.empty(T, **i32)
+        counts = torch.empty(T * lib.ts_bin_counter_stride(), **i32)
         # projection + record packing + tile counting in one pass (conics/cov3d/num_tiles_hit are
         # not materialised: nothing downstream of the fused node reads them)
         _lib.call("ts_project_fwd", N, _lib.ptr(means_c), _lib.ptr(scales_c), 1.0, _lib.ptr(quats_c),

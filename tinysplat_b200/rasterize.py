@@ -50,7 +50,7 @@ def pack_and_bin(xys, depths, radii, conics, opacity, colors, H, W, cull_mode=1,
     tx, ty = (W + BLOCK - 1) // BLOCK, (H + BLOCK - 1) // BLOCK
     T = tx * ty
     recs = torch.empty(N, lib.ts_rec_floats(), device=dev, dtype=torch.float32)
-    counts = torch.empty(T, device=dev, dtype=torch.int32)
+    counts = torch.empty(T * lib.ts_bin_counter_stride(), device=dev, dtype=torch.int32)
     _lib.call("ts_bin_count", N, CH, _lib.ptr(xys), _lib.ptr(depths), _lib.ptr(radii),
                                 _lib.ptr(conics), _lib.ptr(opacity), _lib.ptr(colors), H, W, tx, ty,
               cull_mode, 0, _lib.ptr(recs), _lib.ptr(counts), st)
