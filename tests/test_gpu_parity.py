@@ -358,6 +358,67 @@ def test_empty_and_all_culled_scenes():
     assert ins[0].grad.abs().max() == 0
 
 
+def test_fused_pipeline_empty_scene_and_no_grad_outputs():
+    from tinysplat_b200.rasterizer import GaussianRasterizer, ParamModel
+    W, H = 50, 34
+    cam = synthetic.make_camera(W, H)
+    sc = synthetic.make_scene(16, W, H, seed=2)
+    sc["background"] = torch.tensor([0.2, 0.4, 0.6])
+    empty = {k: (v[:0] if k != "background" else v) for k, v in sc.items()}
+    model = ParamModel(empty, DEV, 3)
+    # poison the caching allocator: torch.empty() must not be able to hide a missing memset
+    junk = [torch.full((1 << 18,), 0x7F7F7F7F, dtype=torch.int32, device=DEV) for _ in range(8)]
+    del junk
+    img, ex = GaussianRasterizer(model, None, DEV, "fused")(cam, (W, H), 3)
+    assert torch.allclose(img, sc["background"].to(DEV).expand(H, W, 3))
+    assert torch.allclose(ex["depth"], torch.full((H, W), 0.2, device=DEV))   # depth over background[0]
+    img.sum().backward()
+    assert all(p.grad is not None and p.grad.numel() == 0 for p in model.parameters())
+    # everything behind the camera: zero grads, finite
+    sc["means"][:, 2] = -1.0
+    model = ParamModel(sc, DEV, 3)
+    img, ex = GaussianRasterizer(model, None, DEV, "fused")(cam, (W, H), 3)
+    (img.sum() + ex["depth"].sum()).backward()
+    assert ex["radii"].abs().sum() == 0
+    for p in model.parameters():
+        assert p.grad.abs().max() == 0
+
+
+@pytest.mark.parametrize("pipeline", ["reference", "fused"])
+def test_huge_and_extreme_gaussians_match_oracle(pipeline):
+    """Screen-filling Gaussians (warp-cooperative tile expansion, hundreds of tiles each), nearly
+    opaque and nearly transparent ones, strongly anisotropic ones, mixed with ordinary ones."""
+    from tinysplat_b200.rasterizer import GaussianRasterizer, ParamModel
+    W, H, N = 208, 144, 300
+    cam = synthetic.make_camera(W, H)
+    sc = synthetic.make_scene(N, W, H, seed=31, sh_degree=2)
+    sc["background"] = torch.tensor([0.9, 0.1, 0.5])
+    sc["scales"][:6] += 4.5                     # enormous: cover the whole image
+    sc["scales"][6:12, 0] += 3.0                # long thin needles
+    sc["scales"][6:12, 1] -= 1.5
+    sc["opacities"][12:20] = 9.0                # alpha clamps at 0.999
+    sc["opacities"][20:30] = -6.0               # below 1/255: can never contribute
+    sc["opacities"][:3] = 8.0
+    names = PARAMS
+    model = ParamModel(sc, DEV, 2)
+    img, ex = GaussianRasterizer(model, None, DEV, pipeline)(cam, (W, H), 2)
+    g = torch.Generator().manual_seed(5)
+    wi, wd = torch.rand(H, W, 3, generator=g), torch.rand(H, W, generator=g)
+    ((img * wi.to(DEV)).sum() + 0.1 * (ex["depth"] * wd.to(DEV)).sum()).backward()
+    p = {k: v.double().clone().requires_grad_(k != "background") for k, v in sc.items()}
+    rimg, rex = oracle.render_reference_adapter(p, cam.view_matrix, cam.proj_matrix, cam.f_x, cam.f_y, (W, H), 2)
+    ((rimg * wi.double()).sum() + 0.1 * (rex["depth"] * wd.double()).sum()).backward()
+    assert (ex["radii"].cpu() - rex["radii"]).abs().max().item() <= 1
+    assert ex["radii"].max().item() > 400
+    assert (img.cpu().double() - rimg).abs().max().item() < TOL_IMG
+    assert (ex["depth"].cpu().double() - rex["depth"]).abs().max().item() < 20 * TOL_IMG
+    assert rel_err(ex["xys"].grad, rex["xys"].grad) < TOL_GRAD
+    for k in names:
+        assert torch.isfinite(getattr(model, k).grad).all(), k
+        assert rel_err(getattr(model, k).grad, p[k].grad) < TOL_GRAD, k
+    assert getattr(model, "opacities").grad[20:30].abs().max() == 0     # sub-1/255 opacity: no gradient
+
+
 def test_full_size_properties_1080p():
     """BASELINE-sized run (1M Gaussians, 1080p; too big for the oracle): size-independent
     properties instead — (a) opaque background conservation: out = sum w_i c_i + T*bg, so with all

@@ -98,7 +98,10 @@ bin_emit_kernel(int N, const float* __restrict__ depths, const int32_t* __restri
                   });
 }
 
-// Single-CTA exclusive scan over the tile counts + max / oversize statistics.
+// Single-CTA exclusive scan over the tile counts + max / oversize statistics.  Every thread owns
+// a contiguous chunk of tiles: all of its (strided, one-line-each) counter loads are in flight at
+// once, then one block-wide scan of the 1024 chunk sums.
+constexpr int kScanMaxChunk = 16;    // register-resident chunk; larger grids loop over super-chunks
 __global__ void __launch_bounds__(1024)
 bin_scan_kernel(int T, int32_t* __restrict__ counts, int32_t* __restrict__ offsets,
                 int32_t* __restrict__ stats, int cap) {
@@ -109,12 +112,25 @@ bin_scan_kernel(int T, int32_t* __restrict__ counts, int32_t* __restrict__ offse
     if (tid == 0) { s_carry = 0; s_max = 0; s_big = 0; }
     __syncthreads();
     int lmax = 0, lbig = 0;
-    for (int base = 0; base < T; base += 1024) {
-        int idx = base + tid;
-        int v = (idx < T) ? counts[(size_t)idx * kCounterStride] : 0;
-        lmax = max(lmax, v);
-        lbig += (v > cap) ? 1 : 0;
-        int x = v;
+    const int per_pass = 1024 * kScanMaxChunk;
+    for (int base = 0; base < T; base += per_pass) {
+        const int n_here = min(per_pass, T - base);
+        const int chunk = (n_here + 1023) / 1024;           // <= kScanMaxChunk
+        const int first = base + tid * chunk;
+        int v[kScanMaxChunk];
+        int sum = 0;
+#pragma unroll
+        for (int k = 0; k < kScanMaxChunk; ++k) {
+            int idx = first + k;
+            v[k] = (k < chunk && idx < base + n_here) ? counts[(size_t)idx * kCounterStride] : 0;
+        }
+#pragma unroll
+        for (int k = 0; k < kScanMaxChunk; ++k) {
+            sum += v[k];
+            lmax = max(lmax, v[k]);
+            lbig += (v[k] > cap) ? 1 : 0;
+        }
+        int x = sum;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             int y = __shfl_up_sync(0xffffffffu, x, d);
@@ -133,14 +149,18 @@ bin_scan_kernel(int T, int32_t* __restrict__ counts, int32_t* __restrict__ offse
             s_warp[lane] = xs - wsum;  // exclusive prefix of warp sums
         }
         __syncthreads();
-        int carry = s_carry;
-        int excl = carry + s_warp[warp] + x - v;
-        if (idx < T) {
-            offsets[idx] = excl;
-            counts[(size_t)idx * kCounterStride] = excl;   // the counter becomes the tile's emit cursor
+        int run = s_carry + s_warp[warp] + x - sum;          // exclusive offset of this thread's chunk
+#pragma unroll
+        for (int k = 0; k < kScanMaxChunk; ++k) {
+            int idx = first + k;
+            if (k < chunk && idx < base + n_here) {
+                offsets[idx] = run;
+                counts[(size_t)idx * kCounterStride] = run;   // the counter becomes the tile's emit cursor
+                run += v[k];
+            }
         }
         __syncthreads();
-        if (tid == 1023) s_carry = excl + v;
+        if (tid == 1023) s_carry = run;                       // last thread's running total
         __syncthreads();
     }
     atomicMax(&s_max, lmax);

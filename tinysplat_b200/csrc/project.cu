@@ -376,9 +376,11 @@ int ts_project_fwd(int N, const float* means3d, const float* scales, float glob_
                    const float* opacity, int cull_mode, float* recs, int32_t* tile_counts,
                    ts_stream_t stream) {
     if (N < 0 || img_height <= 0 || img_width <= 0 || tiles_x <= 0 || tiles_y <= 0) return TS_ERR_INVALID;
-    if (recs && (!opacity || !tile_counts)) return TS_ERR_INVALID;
+    // fused pack+count mode is selected by tile_counts (recs may legitimately be NULL when N == 0)
+    if (tile_counts && N > 0 && (!opacity || !recs)) return TS_ERR_INVALID;
+    if (!tile_counts && recs) return TS_ERR_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
-    if (recs)
+    if (tile_counts)
         TS_CHECK_CUDA(cudaMemsetAsync(tile_counts, 0, sizeof(int32_t) * ts::kCounterStride * (size_t)tiles_x * tiles_y, st),
                       "ts_project_fwd/memset");
     if (N == 0) return TS_OK;
