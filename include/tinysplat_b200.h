@@ -136,8 +136,10 @@ TS_API int ts_sh_bwd(int N, int degree, int K, const float* dirs /*[16B]*/,
  *                counts, per tile, the Gaussians whose footprint can reach a pixel of it
  *                (tile_counts[T * ts_bin_counter_stride()], zeroed by the callee).  CH = colour
  *                channels (1..4).
- * ts_bin_scan  : exclusive scan -> tile_offsets[T+1]; stats[4] = {total M, max per-tile
- *                count, number of tiles whose count exceeds smem_sort_cap, 0}.
+ * ts_bin_scan  : exclusive scan -> tile_offsets[T+1]; stats[0..3] = {total M, max per-tile
+ *                count, number of tiles whose count exceeds smem_sort_cap, 0}.  `stats` must
+ *                hold ts_bin_scan_work_ints() int32 (the tail is scan workspace; zeroed by
+ *                the callee).
  * ts_bin_emit  : writes keys[M] = depth_bits<<32 | gaussian_id grouped by tile
  *                (cursors = the tile_counts buffer after ts_bin_scan).
  * ts_bin_sort  : sorts every tile's keys in place and writes ids_sorted[M] (gaussian ids,
@@ -161,6 +163,7 @@ TS_API int ts_bin_sort(int num_tiles, const int32_t* tile_offsets, uint64_t* key
  * (one per 128-byte line: L2 serialises atomics per line).  ts_bin_scan rewrites each counter
  * in place with the tile's exclusive offset, so the same buffer is ts_bin_emit's `cursors`. */
 TS_API int ts_bin_counter_stride(void);
+TS_API int ts_bin_scan_work_ints(void);
 /* Largest per-tile list ts_bin_sort sorts in shared memory. */
 TS_API int ts_bin_smem_sort_cap(void);
 

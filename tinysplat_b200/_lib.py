@@ -36,6 +36,7 @@ _SIGNATURES = {
     "ts_bin_sort": ([_i, _p, _p, _p, _i, _i, _p, _p, _p], C.c_int),
     "ts_bin_smem_sort_cap": ([], C.c_int),
     "ts_bin_counter_stride": ([], C.c_int),
+    "ts_bin_scan_work_ints": ([], C.c_int),
     "ts_blend_fwd": ([_i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _i, _p], C.c_int),
     "ts_blend_bwd": ([_i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p], C.c_int),
     "ts_blend_unpack_grads": ([_i, _i, _p, _p, _p, _p, _p, _p, _p, _p], C.c_int),

@@ -98,80 +98,109 @@ bin_emit_kernel(int N, const float* __restrict__ depths, const int32_t* __restri
                   });
 }
 
-// Single-CTA exclusive scan over the tile counts + max / oversize statistics.  Every thread owns
-// a contiguous chunk of tiles: all of its (strided, one-line-each) counter loads are in flight at
-// once, then one block-wide scan of the 1024 chunk sums.
-constexpr int kScanMaxChunk = 16;    // register-resident chunk; larger grids loop over super-chunks
+// Exclusive scan over the tile counts + max / oversize statistics.  Up to kScanMaxBlocks CTAs of
+// 1024 threads; each thread owns `chunk` consecutive tiles (all of its strided counter loads in
+// flight at once).  A block publishes its aggregate, then sums its predecessors' aggregates in
+// parallel (one thread per predecessor, look-back on a flag): no serial chain, no second launch.
+// Blocks are dispatched in index order and only ever wait on LOWER indices, so the spin cannot
+// deadlock even when other kernels share the GPU.
+constexpr int kScanMaxChunk = 16;
+constexpr int kScanMaxBlocks = 128;
+constexpr int kScanWorkInts = 4 + 2 * kScanMaxBlocks;   // stats[4] | agg[128] | flag[128]
+
 __global__ void __launch_bounds__(1024)
-bin_scan_kernel(int T, int32_t* __restrict__ counts, int32_t* __restrict__ offsets,
-                int32_t* __restrict__ stats, int cap) {
+bin_scan_kernel(int T, int chunk, int32_t* __restrict__ counts, int32_t* __restrict__ offsets,
+                int32_t* __restrict__ work, int cap) {
     __shared__ int s_warp[32];
-    __shared__ int s_carry;
-    __shared__ int s_max, s_big;
+    __shared__ int s_total, s_prefix;
+    int32_t* stats = work;
+    volatile int32_t* agg = work + 4;
+    volatile int32_t* flag = work + 4 + kScanMaxBlocks;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) { s_carry = 0; s_max = 0; s_big = 0; }
+    const int first = (blockIdx.x * 1024 + tid) * chunk;
+    int v[kScanMaxChunk];
+    int sum = 0, lmax = 0, lbig = 0;
+#pragma unroll
+    for (int k = 0; k < kScanMaxChunk; ++k) {
+        int idx = first + k;
+        v[k] = (k < chunk && idx < T) ? counts[(size_t)idx * kCounterStride] : 0;
+    }
+#pragma unroll
+    for (int k = 0; k < kScanMaxChunk; ++k) {
+        sum += v[k];
+        lmax = max(lmax, v[k]);
+        lbig += (v[k] > cap) ? 1 : 0;
+    }
+    // block-wide inclusive scan of the per-thread sums
+    int x = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int y = __shfl_up_sync(0xffffffffu, x, d);
+        if (lane >= d) x += y;
+    }
+    if (lane == 31) s_warp[warp] = x;
     __syncthreads();
-    int lmax = 0, lbig = 0;
-    const int per_pass = 1024 * kScanMaxChunk;
-    for (int base = 0; base < T; base += per_pass) {
-        const int n_here = min(per_pass, T - base);
-        const int chunk = (n_here + 1023) / 1024;           // <= kScanMaxChunk
-        const int first = base + tid * chunk;
-        int v[kScanMaxChunk];
-        int sum = 0;
-#pragma unroll
-        for (int k = 0; k < kScanMaxChunk; ++k) {
-            int idx = first + k;
-            v[k] = (k < chunk && idx < base + n_here) ? counts[(size_t)idx * kCounterStride] : 0;
-        }
-#pragma unroll
-        for (int k = 0; k < kScanMaxChunk; ++k) {
-            sum += v[k];
-            lmax = max(lmax, v[k]);
-            lbig += (v[k] > cap) ? 1 : 0;
-        }
-        int x = sum;
+    if (warp == 0) {
+        int wsum = s_warp[lane];
+        int xs = wsum;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            int y = __shfl_up_sync(0xffffffffu, x, d);
-            if (lane >= d) x += y;
+            int y = __shfl_up_sync(0xffffffffu, xs, d);
+            if (lane >= d) xs += y;
         }
-        if (lane == 31) s_warp[warp] = x;
-        __syncthreads();
-        if (warp == 0) {
-            int wsum = s_warp[lane];
-            int xs = wsum;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                int y = __shfl_up_sync(0xffffffffu, xs, d);
-                if (lane >= d) xs += y;
-            }
-            s_warp[lane] = xs - wsum;  // exclusive prefix of warp sums
-        }
-        __syncthreads();
-        int run = s_carry + s_warp[warp] + x - sum;          // exclusive offset of this thread's chunk
-#pragma unroll
-        for (int k = 0; k < kScanMaxChunk; ++k) {
-            int idx = first + k;
-            if (k < chunk && idx < base + n_here) {
-                offsets[idx] = run;
-                counts[(size_t)idx * kCounterStride] = run;   // the counter becomes the tile's emit cursor
-                run += v[k];
-            }
-        }
-        __syncthreads();
-        if (tid == 1023) s_carry = run;                       // last thread's running total
-        __syncthreads();
+        s_warp[lane] = xs - wsum;
+        if (lane == 31) s_total = xs;
     }
-    atomicMax(&s_max, lmax);
-    atomicAdd(&s_big, lbig);
     __syncthreads();
+    const int excl_in_block = s_warp[warp] + x - sum;
     if (tid == 0) {
-        offsets[T] = s_carry;
-        stats[0] = s_carry;
-        stats[1] = s_max;
-        stats[2] = s_big;
-        stats[3] = 0;
+        agg[blockIdx.x] = s_total;
+        __threadfence();
+        flag[blockIdx.x] = 1;
+    }
+    // look-back: thread t < blockIdx.x fetches predecessor t's aggregate
+    int prev = 0;
+    if (tid < (int)blockIdx.x) {
+        while (flag[tid] == 0) { }
+        __threadfence();
+        prev = agg[tid];
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) prev += __shfl_xor_sync(0xffffffffu, prev, d);
+    __syncthreads();               // s_warp reads above are done
+    if (lane == 0) s_warp[warp] = prev;
+    __syncthreads();
+    if (warp == 0) {
+        int p = s_warp[lane];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) p += __shfl_xor_sync(0xffffffffu, p, d);
+        if (lane == 0) s_prefix = p;
+    }
+    __syncthreads();
+    int run = s_prefix + excl_in_block;
+#pragma unroll
+    for (int k = 0; k < kScanMaxChunk; ++k) {
+        int idx = first + k;
+        if (k < chunk && idx < T) {
+            offsets[idx] = run;
+            counts[(size_t)idx * kCounterStride] = run;   // the counter becomes the tile's emit cursor
+            run += v[k];
+        }
+    }
+    // statistics
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        lmax = max(lmax, __shfl_xor_sync(0xffffffffu, lmax, d));
+        lbig += __shfl_xor_sync(0xffffffffu, lbig, d);
+    }
+    if (lane == 0) {
+        if (lmax > 0) atomicMax(stats + 1, lmax);
+        if (lbig > 0) atomicAdd(stats + 2, lbig);
+    }
+    if (blockIdx.x == gridDim.x - 1 && tid == 0) {
+        int total = s_prefix + s_total;
+        offsets[T] = total;
+        stats[0] = total;
     }
 }
 
@@ -363,10 +392,19 @@ int ts_bin_count(int N, int CH, const float* xys, const float* depths, const int
 
 int ts_bin_counter_stride(void) { return ts::kCounterStride; }
 
+int ts_bin_scan_work_ints(void) { return ts::kScanWorkInts; }
+
 int ts_bin_scan(int num_tiles, int32_t* tile_counts, int32_t* tile_offsets, int32_t* stats,
                 int smem_sort_cap, ts_stream_t stream) {
     if (num_tiles <= 0 || !tile_counts || !tile_offsets || !stats) return TS_ERR_INVALID;
-    ts::bin_scan_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(num_tiles, tile_counts, tile_offsets, stats, smem_sort_cap);
+    // chunk tiles per thread so that the grid stays within kScanMaxBlocks co-resident CTAs
+    int chunk = (num_tiles + 1024 * ts::kScanMaxBlocks - 1) / (1024 * ts::kScanMaxBlocks);
+    if (chunk < 1) chunk = 1;
+    if (chunk > ts::kScanMaxChunk) return TS_ERR_CAPACITY;    // > 2M tiles (a > 500 Mpixel image)
+    int grid = (num_tiles + 1024 * chunk - 1) / (1024 * chunk);
+    cudaStream_t st = (cudaStream_t)stream;
+    TS_CHECK_CUDA(cudaMemsetAsync(stats, 0, sizeof(int32_t) * ts::kScanWorkInts, st), "ts_bin_scan/memset");
+    ts::bin_scan_kernel<<<grid, 1024, 0, st>>>(num_tiles, chunk, tile_counts, tile_offsets, stats, smem_sort_cap);
     TS_CHECK_LAUNCH("ts_bin_scan");
     return TS_OK;
 }

@@ -26,6 +26,15 @@ from . import rasterize as _rz
 
 BLOCK = 16
 _pinned_stats = {}
+_side_streams = {}
+USE_SIDE_STREAM = True     # SH kernels on a second stream, overlapping binning / projection-backward
+
+
+def _side_stream(dev) -> "torch.cuda.Stream":
+    key = str(dev)
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(device=dev)
+    return _side_streams[key]
 
 
 def _stats_buffer(dev) -> Tensor:
@@ -85,18 +94,26 @@ class _RenderFused(Function):
                   _lib.ptr(view_c), _lib.ptr(proj_c), float(fx), float(fy), W / 2, H / 2, H, W, tx, ty,
                   0.01, pflags | _lib.PROJ_OPACITY_LOGIT, _lib.ptr(xys), _lib.ptr(depths), _lib.ptr(radii),
                   None, None, None, _lib.ptr(logit_c), int(cull_mode), _lib.ptr(recs), _lib.ptr(counts), st)
+        # SH colour is independent of the bins: it runs on a side stream (ordered after projection,
+        # which produced `depths` and the geometry half of `recs`), overlapping scan/emit/sort and
+        # keeping the GPU busy while the host waits for the 3 ints below.
+        mask = torch.empty(N, device=dev, dtype=torch.uint8)
+        main = torch.cuda.current_stream(dev)
+        side = _side_stream(dev) if USE_SIDE_STREAM else main
+        if side is not main:
+            side.wait_stream(main)
+        with torch.cuda.stream(side):
+            _lib.call("ts_sh_fwd", N, int(sh_degree), K, _lib.ptr(means_c), _lib.ptr(view_c), _lib.ptr(dc_c),
+                      _lib.ptr(rest_c), recs.data_ptr() + 32, 12, _lib.ptr(depths), _lib.ptr(mask), sflags,
+                      side.cuda_stream)
         offsets = torch.empty(T + 1, **i32)
-        stats = torch.empty(4, **i32)
+        stats = torch.empty(lib.ts_bin_scan_work_ints(), **i32)
         _lib.call("ts_bin_scan", T, _lib.ptr(counts), _lib.ptr(offsets), _lib.ptr(stats),
                   lib.ts_bin_smem_sort_cap(), st)
         host = _stats_buffer(dev)
-        host.copy_(stats, non_blocking=True)
+        host.copy_(stats[:4], non_blocking=True)
         ev = torch.cuda.Event()
         ev.record()
-        # SH (independent of the bins) keeps the GPU busy while the host waits for the 3 ints
-        mask = torch.empty(N, device=dev, dtype=torch.uint8)
-        _lib.call("ts_sh_fwd", N, int(sh_degree), K, _lib.ptr(means_c), _lib.ptr(view_c), _lib.ptr(dc_c),
-                  _lib.ptr(rest_c), recs.data_ptr() + 32, 12, _lib.ptr(depths), _lib.ptr(mask), sflags, st)
         ev.synchronize()
         M, max_count, n_big, _ = host.tolist()
         keys = torch.empty(max(M, 1), device=dev, dtype=torch.int64)
@@ -112,6 +129,8 @@ class _RenderFused(Function):
             _lib.call("ts_bin_sort", T, _lib.ptr(offsets), _lib.ptr(keys), _lib.ptr(ids_sorted), max_count,
                       n_big, _lib.ptr(big_scratch), _lib.ptr(big_counter), st)
         _rz.last_stats.update(num_intersects=M, max_per_tile=max_count, bins_reused=False)
+        if side is not main:
+            main.wait_stream(side)          # colours must be in `recs` before blending
         rgb = torch.empty(H, W, 3, **f32)
         depth_img = torch.empty(H, W, **f32)
         final_T = torch.empty(H, W, **f32)
@@ -163,15 +182,23 @@ class _RenderFused(Function):
         seg = lambda i, *shape: flat[offs[i]:offs[i] + sizes[i]].view(*shape)
         v_rest, v_dc = seg(0, N, K - 1, 3), seg(1, N, 1, 3)
         v_means, v_scales, v_quats, v_logit = seg(2, N, 3), seg(3, N, 3), seg(4, N, 4), seg(5, N)
-        # colours first: the largest gradient is produced before projection-backward runs
-        _lib.call("ts_sh_bwd", N, deg, K, _lib.ptr(means_c), _lib.ptr(view_c), grads.data_ptr() + 32, 12,
-                  _lib.ptr(mask), _lib.ptr(v_dc), _lib.ptr(v_rest), sflags, st)
+        # SH-backward (DRAM-bound) on the side stream, concurrent with projection-backward
+        # (issue-bound); both only read the packed gradients
+        main = torch.cuda.current_stream(dev)
+        side = _side_stream(dev) if USE_SIDE_STREAM else main
+        if side is not main:
+            side.wait_stream(main)
+        with torch.cuda.stream(side):
+            _lib.call("ts_sh_bwd", N, deg, K, _lib.ptr(means_c), _lib.ptr(view_c), grads.data_ptr() + 32, 12,
+                      _lib.ptr(mask), _lib.ptr(v_dc), _lib.ptr(v_rest), sflags, side.cuda_stream)
         v_xys = torch.empty(N, 2, **f32)
         _lib.call("ts_project_bwd", N, _lib.ptr(means_c), _lib.ptr(scales_c), 1.0, _lib.ptr(quats_c),
                   _lib.ptr(view_c), _lib.ptr(proj_c), fx, fy, W / 2, H / 2, H, W,
                   pflags | _lib.PROJ_DEPTH_CH3, _lib.ptr(radii), None, None, None, _lib.ptr(grads),
                   _lib.ptr(logit_c), _lib.ptr(v_means), _lib.ptr(v_scales), _lib.ptr(v_quats),
                   _lib.ptr(v_logit), _lib.ptr(v_xys), st)
+        if side is not main:
+            main.wait_stream(side)
         if ctx.sink is not None:
             ctx.sink.deliver(v_xys)
         return (v_means, v_scales, v_quats, v_logit.reshape(opac_shape), v_dc.reshape(dc_shape), v_rest,

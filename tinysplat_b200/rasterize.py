@@ -60,9 +60,9 @@ def pack_and_bin(xys, depths, radii, conics, opacity, colors, H, W, cull_mode=1,
         return recs, _last_bins
     cap = lib.ts_bin_smem_sort_cap()
     offsets = torch.empty(T + 1, device=dev, dtype=torch.int32)
-    stats = torch.empty(4, device=dev, dtype=torch.int32)
+    stats = torch.empty(lib.ts_bin_scan_work_ints(), device=dev, dtype=torch.int32)
     _lib.call("ts_bin_scan", T, _lib.ptr(counts), _lib.ptr(offsets), _lib.ptr(stats), cap, st)
-    M, max_count, n_big, _ = stats.tolist()   # the one host sync of the path
+    M, max_count, n_big, _ = stats[:4].tolist()   # the one host sync of the path
     keys = torch.empty(max(M, 1), device=dev, dtype=torch.int64)
     ids_sorted = torch.empty(max(M, 1), device=dev, dtype=torch.int32)
     if M > 0:
