@@ -133,12 +133,24 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch, from the `ncu --set full` capture of this
+# same command summarised in profiles/r1_ncu_full_all_kernels.txt (default workload, fused pipeline)
+NCU_TRAFFIC = {
+    "synthetic_1M_1080p": {
+        "ts_blend_bwd": (176.53 + 25.05) * 1e6, "ts_blend_fwd": (62.78 + 21.66) * 1e6,
+        "ts_sh_fwd": (228.81 + 25.18) * 1e6, "ts_sh_bwd": (61.03 + 134.51) * 1e6,
+        "ts_project_fwd": (61.73 + 24.12) * 1e6, "ts_project_bwd": (95.97 + 23.53) * 1e6,
+        "ts_bin_emit": (56.04 + 1.25) * 1e6, "ts_bin_sort": (16.43 + 0.0) * 1e6,
+    }
+}
+
+
 def algorithmic_bytes(name: str, N: int, M: int, P: int, CH: int, K: int, nb: int) -> float:
     """Algorithmic HBM bytes of one launch of C-ABI entry `name` (per-kernel table).
     N Gaussians, M tile intersections, P pixels, CH blended channels, K stored / nb active SH
     bases."""
     table = {
-        "ts_project_fwd": 96 * N,                      # 40 in, 56 out
+        "ts_project_fwd": 96 * N,                      # 40 in, 56 out (fused: 44 in, 48 out, + 4 M count atomics)
         "ts_project_bwd": 108 * N,                     # 68 in, 40 out
         "ts_sh_fwd": (24 + 12 * nb) * N,
         "ts_sh_bwd": (24 + 12 * K) * N,
@@ -417,11 +429,20 @@ def run_ours(args):
     roof = None
     if top:
         a = kern[top]["gbs"]
+        traffic = NCU_TRAFFIC.get(args.workload, {}).get(top) if args.pipeline == "fused" else None
         roof = {"kernel": top, "bound": "hbm", "achieved": a, "peak": peak, "unit": "GB/s",
-                "frac": a / peak, "traffic": None, "peak_source": peak_src,
+                "frac": a / peak, "traffic": traffic, "peak_source": peak_src,
                 "note": "blend kernels are fp32-issue/atomic bound, not HBM bound (DESIGN.md); "
                         "streaming kernels listed in `kernels`"}
 
+    # the best streaming (genuinely HBM-bound) kernel, for a roofline fraction that means something
+    stream_names = [k for k in ("ts_sh_bwd", "ts_sh_fwd", "ts_project_bwd", "ts_project_fwd") if k in kern]
+    best_stream = max(stream_names, key=lambda k: kern[k]["gbs"] or 0) if stream_names else None
+    roof_stream = None
+    if best_stream:
+        roof_stream = {"kernel": best_stream, "bound": "hbm", "achieved": kern[best_stream]["gbs"], "peak": peak,
+                       "unit": "GB/s", "frac": kern[best_stream]["gbs"] / peak,
+                       "traffic": NCU_TRAFFIC.get(args.workload, {}).get(best_stream)}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -444,6 +465,7 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roof,
+        "roofline_streaming": roof_stream,
         "kernels": kern,
     }
     if world == 1 and not args.no_cpu_baseline:
