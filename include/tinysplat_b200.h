@@ -195,6 +195,17 @@ TS_API int ts_blend_unpack_grads(int N, int CH, const int32_t* radii, const floa
                                  const float* grads /*[16B]*/, float* v_xys, float* v_conics,
                                  float* v_colors, float* v_opacity, ts_stream_t stream);
 
+/* ---- fused multi-tensor Adam step ---------------------------------------
+ * One launch updates up to ts_adam_max_tensors() parameter tensors in place, with the exact
+ * arithmetic of torch.optim.Adam (no weight decay, no amsgrad), the optimizer the reference
+ * trains with [REF scripts/train.py:26; model_gaussian.py:112-120].  The pointer tables,
+ * numels[], lrs[] and steps[] (1-based step count AFTER this update) are HOST arrays. */
+TS_API int ts_adam_max_tensors(void);
+TS_API int ts_adam_step(int num_tensors, float* const* params_host, const float* const* grads_host,
+                        float* const* exp_avgs_host, float* const* exp_avg_sqs_host,
+                        const int64_t* numels_host, const float* lrs_host, const int64_t* steps_host,
+                        double beta1, double beta2, double eps, ts_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

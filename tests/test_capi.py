@@ -83,11 +83,21 @@ def test_product_fails_loudly_without_cuda():
                                    torch.zeros(4, dtype=torch.int32), x, torch.zeros(4, 1), 16, 16, torch.zeros(3))
 
 
+def test_fused_adam_fails_loudly_on_cpu_parameters():
+    from tinysplat_b200.optim import FusedAdam
+    from tinysplat_b200._lib import TinysplatError
+    p = torch.nn.Parameter(torch.zeros(4, 3))
+    opt = FusedAdam([{"params": [p], "lr": 0.1, "name": "means"}])
+    p.grad = torch.ones_like(p)
+    with pytest.raises(TinysplatError):
+        opt.step()
+
+
 def test_product_never_imports_the_oracle():
     import subprocess
     import sys
     code = ("import sys; sys.path.insert(0, %r); import gsplat, tinysplat_b200, tinysplat_b200.rasterizer, "
-            "tinysplat_b200.parallel; assert not any(m.split('.')[0] == 'oracle' for m in sys.modules), 'oracle imported'"
+            "tinysplat_b200.parallel, tinysplat_b200.optim; assert not any(m.split('.')[0] == 'oracle' for m in sys.modules), 'oracle imported'"
             % ROOT)
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr

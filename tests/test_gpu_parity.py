@@ -453,3 +453,78 @@ def test_full_size_properties_1080p():
     # d(sum img)/d c_i = sum_pixels w_i ; summed over i and channels = 3 * sum_pixels (1 - T)
     assert abs(c1.grad.sum().item() / (3 * a1.double().sum().item()) - 1) < 1e-3
     assert rz.last_stats["num_intersects"] > N
+
+
+# ---- fused Adam ---------------------------------------------------------------------
+def _param_set(N, seed):
+    g = torch.Generator().manual_seed(seed)
+    shapes = {"means": (N, 3), "colors_dc": (N, 3), "colors_rest": (N, 15, 3), "scales": (N, 3),
+              "quats": (N, 4), "opacities": (N, 1)}
+    lrs = {"means": 0.00016, "colors_dc": 0.0025, "colors_rest": 0.000125, "scales": 0.005,
+           "quats": 0.001, "opacities": 0.05}          # [REF scripts/train.py:183-188]
+    return {k: torch.randn(*s, generator=g) for k, s in shapes.items()}, lrs
+
+
+def _groups(ps, lrs):
+    return [{"params": [p], "lr": lrs[k], "name": k} for k, p in ps.items()]
+
+
+def _surgery(optim, ps, mask, n_new, seed):
+    """The reference's densify/prune optimizer surgery [REF model_gaussian.py:199-242], restated."""
+    g = torch.Generator().manual_seed(seed)
+    for group in optim.param_groups:
+        name = group["name"]
+        old = group["params"][0]
+        new_rows = torch.randn(n_new, *old.shape[1:], generator=g).to(old.device)
+        state = optim.state[old]
+        state["exp_avg"] = torch.cat((state["exp_avg"][~mask], torch.zeros_like(new_rows)))
+        state["exp_avg_sq"] = torch.cat((state["exp_avg_sq"][~mask], torch.zeros_like(new_rows)))
+        del optim.state[old]
+        new = torch.nn.Parameter(torch.cat((old.detach()[~mask], new_rows)))
+        group["params"][0] = new
+        optim.state[new] = state
+        ps[name] = new
+
+
+def test_fused_adam_matches_torch_adam_through_optimizer_surgery():
+    from tinysplat_b200.optim import FusedAdam
+    N = 5003                                   # odd sizes: exercises the scalar tails
+    init, lrs = _param_set(N, 0)
+    pa = {k: torch.nn.Parameter(v.clone().to(DEV)) for k, v in init.items()}
+    pb = {k: torch.nn.Parameter(v.clone().to(DEV)) for k, v in init.items()}
+    ref = torch.optim.Adam(_groups(pa, lrs), foreach=False, fused=False)
+    ours = FusedAdam(_groups(pb, lrs))
+    g = torch.Generator().manual_seed(1)
+
+    def step_both(n_steps):
+        for _ in range(n_steps):
+            for k in pa:
+                gr = torch.randn(*pa[k].shape, generator=g).to(DEV) * (10.0 ** float(torch.randint(-3, 2, (1,), generator=g)))
+                pa[k].grad = gr.clone()
+                pb[k].grad = gr.clone()
+            ref.step()
+            ours.step()
+            for k in pa:
+                # fp32 vs fp32 with possibly different FMA contraction: a few ulp of the tensor's scale
+                sa, sb = ref.state[pa[k]], ours.state[pb[k]]
+                assert float(sa["step"]) == float(sb["step"])
+                errs = (rel_err(pb[k], pa[k]), rel_err(sb["exp_avg"], sa["exp_avg"]),
+                        rel_err(sb["exp_avg_sq"], sa["exp_avg_sq"]))
+                assert max(errs) < 2e-6, (k, errs)
+
+    step_both(4)
+    mask = torch.rand(N, generator=g).to(DEV) < 0.2
+    _surgery(ref, pa, mask, 700, seed=5)
+    _surgery(ours, pb, mask, 700, seed=5)
+    step_both(3)
+    assert pa["means"].shape[0] == N - int(mask.sum()) + 700
+
+
+def test_fused_adam_rejects_unsupported_options():
+    from tinysplat_b200.optim import FusedAdam
+    p = torch.nn.Parameter(torch.zeros(8, 3, device=DEV))
+    opt = FusedAdam([{"params": [p], "lr": 0.1, "name": "x"}])
+    opt.param_groups[0]["weight_decay"] = 0.1
+    p.grad = torch.ones_like(p)
+    with pytest.raises(NotImplementedError):
+        opt.step()

@@ -12,7 +12,7 @@ from typing import Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtinysplat_b200.so")
+LIB_PATH = os.environ.get("TINYSPLAT_B200_LIB") or os.path.join(_HERE, "libtinysplat_b200.so")
 
 _p = C.c_void_p
 _i = C.c_int
@@ -39,6 +39,8 @@ _SIGNATURES = {
     "ts_bin_scan_work_ints": ([], C.c_int),
     "ts_blend_fwd": ([_i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _i, _p], C.c_int),
     "ts_blend_bwd": ([_i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p], C.c_int),
+    "ts_adam_max_tensors": ([], C.c_int),
+    "ts_adam_step": ([_i, _p, _p, _p, _p, _p, _p, _p, C.c_double, C.c_double, C.c_double, _p], C.c_int),
     "ts_blend_unpack_grads": ([_i, _i, _p, _p, _p, _p, _p, _p, _p, _p], C.c_int),
 }
 

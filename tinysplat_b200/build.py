@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtinysplat_b200.so")
-SOURCES = ["capi.cu", "project.cu", "sh.cu", "binning.cu", "blend.cu"]
+SOURCES = ["capi.cu", "project.cu", "sh.cu", "binning.cu", "blend.cu", "adam.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-fvisibility=hidden",
          "-Xptxas", "-v"]
@@ -34,17 +34,19 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not _stale():
+def build(force: bool = False, verbose: bool = False, defines=(), out_path: str = LIB) -> str:
+    """defines/out_path: build an experimental variant (e.g. defines=("TS_BLEND_TMA_GATHER=1",)) into
+    another file; select it at run time with TINYSPLAT_B200_LIB=<path>."""
+    if not force and not defines and not _stale():
         return LIB
     nvcc = _nvcc()
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build" + ("_" + "_".join(d.split("=")[0] for d in defines) if defines else ""))
     os.makedirs(objdir, exist_ok=True)
     objs = []
     procs = []
     for src in SOURCES:
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
-        cmd = [nvcc, *ARCH, *FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *ARCH, *FLAGS, *[f"-D{d}" for d in defines], "-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     log = []
@@ -53,7 +55,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         log.append(f"== {src}\n{out}")
         if p.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}:\n{out}")
-    cmd = [nvcc, *ARCH, "-shared", "-o", LIB, *objs]
+    cmd = [nvcc, *ARCH, "-shared", "-o", out_path, *objs]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}")
@@ -61,7 +63,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         f.write("\n".join(log))
     if verbose:
         print("\n".join(log))
-    return LIB
+    return out_path
 
 
 if __name__ == "__main__":

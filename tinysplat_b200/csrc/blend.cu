@@ -14,6 +14,9 @@
 
 namespace ts {
 
+#ifndef TS_BLEND_TMA_GATHER
+#define TS_BLEND_TMA_GATHER 0
+#endif
 constexpr int kBlendThreads = 256;
 constexpr int kBatch = 256;
 constexpr int kClampShift = 28;                      // n_contrib bits 28..30: clamped-channel mask
@@ -94,8 +97,23 @@ blend_fwd_kernel(int H, int W, int tbx, const int32_t* __restrict__ tile_offsets
     int ncon = 0;
     bool done = !pm.inside;
 
+#if TS_BLEND_TMA_GATHER
+    // experiment: one 48-byte TMA bulk copy per record, completion on a per-buffer mbarrier
+    __shared__ __align__(8) uint64_t s_bar[2];
+    if (tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); fence_proxy_async(); }
+    __syncthreads();
+    int pending = -1;
+#endif
     auto prefetch = [&](int b) {
         int p = b * kBatch + tid;
+#if TS_BLEND_TMA_GATHER
+        if (tid == 0) mbar_expect_tx(&s_bar[b & 1], 48u * (unsigned)min(kBatch, count - b * kBatch));
+        if (p < count) {
+            int g = __ldg(ids + start + p);
+            bulk_g2s(&s_rec[b & 1][tid * 3], recs + 3 * (size_t)g, 48u, &s_bar[b & 1]);
+        }
+        pending = b;
+#else
         if (p < count) {
             int g = __ldg(ids + start + p);
             const float4* src = recs + 3 * (size_t)g;
@@ -104,6 +122,7 @@ blend_fwd_kernel(int H, int W, int tbx, const int32_t* __restrict__ tile_offsets
             cp_async16(dst + 1, src + 1);
             cp_async16(dst + 2, src + 2);
         }
+#endif
     };
     if (nb > 0) prefetch(0);
     cp_async_commit();
@@ -111,8 +130,13 @@ blend_fwd_kernel(int H, int W, int tbx, const int32_t* __restrict__ tile_offsets
     for (int b = 0; b < nb; ++b) {
         const int buf = b & 1;
         if (b + 1 < nb) prefetch(b + 1);
+#if TS_BLEND_TMA_GATHER
+        mbar_wait(&s_bar[buf], (unsigned)(b >> 1) & 1u);
+        if (pending == b) pending = -1;
+#else
         cp_async_commit();
         cp_async_wait<1>();  // batch b (this thread's copies) has landed
+#endif
         unsigned mine = 0;
         if (b * kBatch + tid < count) mine = subblock_mask(s_rec[buf][tid * 3]);
 #pragma unroll
@@ -156,7 +180,11 @@ blend_fwd_kernel(int H, int W, int tbx, const int32_t* __restrict__ tile_offsets
         // also guards reuse of s_rec[buf] / s_mask by the next iterations
         if (__syncthreads_and(warp_done)) break;
     }
+#if TS_BLEND_TMA_GATHER
+    if (pending >= 0) mbar_wait(&s_bar[pending & 1], (unsigned)(pending >> 1) & 1u);   // drain before exit
+#else
     cp_async_wait<0>();
+#endif
 
     if (pm.inside) {
         const size_t pix = (size_t)pm.i * W + pm.j;
