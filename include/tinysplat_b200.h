@@ -206,6 +206,23 @@ TS_API int ts_adam_step(int num_tensors, float* const* params_host, const float*
                         const int64_t* numels_host, const float* lrs_host, const int64_t* steps_host,
                         double beta1, double beta2, double eps, ts_stream_t stream);
 
+/* ---- fused SSIM (11-tap Gaussian window, 'valid' filtering) ---------------
+ * The training loss's (1 - SSIM) term [REF scripts/train.py:60-62; model_gaussian.py:57].
+ * X, Y: [B,C,H,W] addressed through ELEMENT strides (host arrays of 4 int64: b, c, h, w), so an
+ * [H,W,3] image viewed as [1,3,H,W] is read in place.  win11_host: the 11 window weights (host).
+ * ts_ssim_fwd: ssim_sum[B*C] (zeroed by the callee) receives the SUM of the SSIM map per
+ * (batch, channel) over the (H-10)x(W-10) valid outputs; dmu/de11/de12 [B,C,H-10,W-10] (all
+ * three or all NULL) receive dS/d(mu_x), dS/d(E[x^2]), dS/d(E[xy]) for backward.
+ * ts_ssim_bwd: v_X[B,C,H,W] (contiguous) = sum_c v_per_channel[b,c] * d mean_S[b,c] / d X. */
+TS_API int ts_ssim_fwd(int B, int C, int H, int W, const float* X, const int64_t* x_strides_host,
+                       const float* Y, const int64_t* y_strides_host, const float* win11_host,
+                       float C1, float C2, float* ssim_sum, float* dmu, float* de11, float* de12,
+                       ts_stream_t stream);
+TS_API int ts_ssim_bwd(int B, int C, int H, int W, const float* X, const int64_t* x_strides_host,
+                       const float* Y, const int64_t* y_strides_host, const float* win11_host,
+                       const float* dmu, const float* de11, const float* de12,
+                       const float* v_per_channel, float* v_X, ts_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
