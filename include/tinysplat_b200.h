@@ -223,6 +223,13 @@ TS_API int ts_ssim_bwd(int B, int C, int H, int W, const float* X, const int64_t
                        const float* dmu, const float* de11, const float* de12,
                        const float* v_per_channel, float* v_X, ts_stream_t stream);
 
+/* ---- exact K nearest neighbours (density regularizer) ---------------------
+ * Stand-in for pytorch3d.ops.knn_points as called at [REF model_gaussian.py:260,425,519].
+ * queries[P1,3], refs[P2,3] -> dists[P1,K] (squared L2, ascending), idx[P1,K] (int64).
+ * K in {1,2,4,8,16,32}. */
+TS_API int ts_knn_points(int P1, int P2, int K, const float* queries, const float* refs,
+                         float* dists, int64_t* idx, ts_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

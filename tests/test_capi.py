@@ -97,7 +97,7 @@ def test_product_never_imports_the_oracle():
     import subprocess
     import sys
     code = ("import sys; sys.path.insert(0, %r); import gsplat, tinysplat_b200, tinysplat_b200.rasterizer, "
-            "tinysplat_b200.parallel, tinysplat_b200.optim; assert not any(m.split('.')[0] == 'oracle' for m in sys.modules), 'oracle imported'"
+            "tinysplat_b200.parallel, tinysplat_b200.optim, tinysplat_b200.ssim, tinysplat_b200.knn; assert not any(m.split('.')[0] == 'oracle' for m in sys.modules), 'oracle imported'"
             % ROOT)
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr

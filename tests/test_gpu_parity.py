@@ -570,3 +570,22 @@ def test_training_loop_like_train_py_reduces_the_loss():
         losses.append(float(loss))
     assert all(torch.isfinite(p).all() for p in params.values())
     assert losses[-1] < 0.5 * losses[0], (losses[0], losses[-1])
+
+
+@pytest.mark.parametrize("P1,P2,K", [(500, 5000, 16), (33, 1500, 4), (700, 20, 16), (1, 1, 1), (10, 5, 16)])
+def test_knn_points_matches_brute_force(P1, P2, K):
+    """exact KNN as the density regularizer calls it [REF model_gaussian.py:260]."""
+    from tinysplat_b200.knn import knn_points
+    g = torch.Generator().manual_seed(P1 + P2)
+    p1 = torch.randn(P1, 3, generator=g)
+    p2 = torch.randn(P2, 3, generator=g)
+    out = knn_points(p1[None].to(DEV), p2[None].to(DEV), K=K)
+    assert out.idx.shape == (1, P1, K) and out.idx.dtype == torch.int64 and out.dists.shape == (1, P1, K)
+    d = ((p1.double()[:, None, :] - p2.double()[None, :, :]) ** 2).sum(-1)
+    kk = min(K, P2)
+    want_d, want_i = torch.topk(d, kk, dim=1, largest=False, sorted=True)
+    got_d, got_i = out.dists[0].cpu().double()[:, :kk], out.idx[0].cpu()[:, :kk]
+    assert torch.allclose(got_d, want_d, rtol=1e-5, atol=1e-6)
+    assert (got_i == want_i).float().mean().item() > 0.999        # fp32 near-ties may swap neighbours
+    # what the reference does with it: index the means
+    assert p2.to(DEV)[out.idx[0]].shape == (P1, K, 3)

@@ -41,6 +41,7 @@ _SIGNATURES = {
     "ts_blend_bwd": ([_i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p], C.c_int),
     "ts_ssim_fwd": ([_i, _i, _i, _i, _p, _p, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p], C.c_int),
     "ts_ssim_bwd": ([_i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p], C.c_int),
+    "ts_knn_points": ([_i, _i, _i, _p, _p, _p, _p, _p], C.c_int),
     "ts_adam_max_tensors": ([], C.c_int),
     "ts_adam_step": ([_i, _p, _p, _p, _p, _p, _p, _p, C.c_double, C.c_double, C.c_double, _p], C.c_int),
     "ts_blend_unpack_grads": ([_i, _i, _p, _p, _p, _p, _p, _p, _p, _p], C.c_int),
