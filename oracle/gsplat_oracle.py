@@ -28,7 +28,6 @@ the EWA Jacobian.
 """
 from __future__ import annotations
 
-import math
 from typing import Optional, Sequence, Tuple
 
 import torch

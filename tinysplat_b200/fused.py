@@ -15,7 +15,7 @@ while the GPU still has SH work queued, then launches emit/sort/blend before the
 from __future__ import annotations
 
 import weakref
-from typing import Optional, Tuple
+from typing import Tuple
 
 import torch
 from torch import Tensor
