@@ -1,0 +1,208 @@
+// Host SIMT emulator for kernel-logic tests (TEST INFRASTRUCTURE ONLY — never part of the product).
+//
+// A CTA is run as `blockDim` cooperative fibers (ucontext) on ONE host thread.  A fiber runs until
+// it reaches a collective (__syncthreads*, __ballot_sync, __any_sync, __shfl_xor_sync, ...),
+// deposits its operand and yields; the last arriver completes the collective and everybody
+// resumes.  All collectives must be called with the full mask by all 32 lanes of a warp (the
+// kernels under test are written that way); a lane that skips one deadlocks the CTA, which the
+// scheduler reports as an error instead of hanging.  `__shared__` becomes function-local `static`
+// (one CTA runs at a time), atomics are plain read-modify-writes (one fiber runs at a time).
+#pragma once
+#include <ucontext.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <vector>
+
+struct float2 { float x, y; };
+struct alignas(16) float4 { float x, y, z, w; };
+static inline float2 make_float2(float x, float y) { return float2{x, y}; }
+static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+struct dim3 {
+    unsigned x, y, z;
+    dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
+};
+typedef void* cudaStream_t;
+typedef int cudaError_t;
+static inline cudaError_t cudaGetLastError() { return 0; }
+#define cudaSuccess 0
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __launch_bounds__(...)
+#define __shared__ static
+#define __align__(n) __attribute__((aligned(n)))
+
+namespace ts_emu {
+
+constexpr int kMaxThreads = 1024;
+constexpr size_t kStack = 256 * 1024;
+
+struct WarpSync {
+    int arrived = 0, gen = 0;
+    uint32_t in[32];
+    uint32_t out[2][32];
+};
+struct BlockSync {
+    int arrived = 0, gen = 0;
+    int acc_and = 1;
+    int out[2];
+};
+
+struct State {
+    dim3 tid, bid;
+    int nthreads = 0, cur = 0, alive = 0;
+    ucontext_t sched;
+    ucontext_t ctx[kMaxThreads];
+    char* stacks = nullptr;
+    bool done[kMaxThreads];
+    WarpSync ws[kMaxThreads / 32];
+    BlockSync bs;
+    std::function<void()> body;
+    long progress = 0;     // bumped whenever a collective completes or a fiber finishes
+    bool deadlock = false;
+};
+inline State& st() { static State s; return s; }
+
+inline void yield_() {
+    State& s = st();
+    int me = s.cur;
+    swapcontext(&s.ctx[me], &s.sched);
+}
+
+inline void fiber_entry() {
+    State& s = st();
+    s.body();
+    s.done[s.cur] = true;
+    s.alive--;
+    s.progress++;
+    swapcontext(&s.ctx[s.cur], &s.sched);
+}
+
+// Runs `body` once per thread of every block of the grid.  Returns 0, or -1 on a deadlock
+// (some lanes wait in a collective the others never reach).
+inline int launch(dim3 grid, int nthreads, std::function<void()> body) {
+    State& s = st();
+    if (!s.stacks) s.stacks = (char*)malloc(kStack * kMaxThreads);
+    s.body = body;
+    s.nthreads = nthreads;
+    for (unsigned by = 0; by < grid.y; ++by)
+        for (unsigned bx = 0; bx < grid.x; ++bx) {
+            s.bid = dim3(bx, by, 0);
+            s.alive = nthreads;
+            s.bs = BlockSync();
+            for (int w = 0; w < (nthreads + 31) / 32; ++w) s.ws[w] = WarpSync();
+            for (int t = 0; t < nthreads; ++t) {
+                s.done[t] = false;
+                getcontext(&s.ctx[t]);
+                s.ctx[t].uc_stack.ss_sp = s.stacks + kStack * t;
+                s.ctx[t].uc_stack.ss_size = kStack;
+                s.ctx[t].uc_link = &s.sched;
+                makecontext(&s.ctx[t], (void (*)())fiber_entry, 0);
+            }
+            while (s.alive > 0) {
+                long before = s.progress;
+                for (int t = 0; t < nthreads; ++t) {
+                    if (s.done[t]) continue;
+                    s.cur = t;
+                    s.tid = dim3(t, 0, 0);
+                    swapcontext(&s.sched, &s.ctx[t]);
+                }
+                if (s.progress == before) {   // a full round without any collective completing
+                    fprintf(stderr, "[ts_emu] deadlock in block (%u,%u): %d fibers stuck\n", bx, by, s.alive);
+                    s.deadlock = true;
+                    return -1;
+                }
+            }
+        }
+    return 0;
+}
+
+inline const uint32_t* warp_exchange(uint32_t v) {
+    State& s = st();
+    const int t = s.cur, lane = t & 31;
+    WarpSync& w = s.ws[t >> 5];
+    const int g = w.gen;
+    w.in[lane] = v;
+    if (++w.arrived == 32) {
+        memcpy(w.out[g & 1], w.in, sizeof(w.in));
+        w.arrived = 0;
+        w.gen++;
+        s.progress++;
+    } else {
+        while (w.gen == g) yield_();
+    }
+    return w.out[g & 1];
+}
+
+inline int block_barrier(int pred) {
+    State& s = st();
+    BlockSync& b = s.bs;
+    const int g = b.gen;
+    b.acc_and = b.acc_and && pred;
+    if (++b.arrived == s.nthreads) {
+        b.out[g & 1] = b.acc_and;
+        b.acc_and = 1;
+        b.arrived = 0;
+        b.gen++;
+        s.progress++;
+    } else {
+        while (b.gen == g) yield_();
+    }
+    return b.out[g & 1];
+}
+
+}  // namespace ts_emu
+
+#define threadIdx (ts_emu::st().tid)
+#define blockIdx (ts_emu::st().bid)
+
+static inline void emu_require_full(unsigned mask) {
+    if (mask != 0xffffffffu) { fprintf(stderr, "[ts_emu] partial-mask collective not supported\n"); abort(); }
+}
+static inline void __syncthreads() { ts_emu::block_barrier(1); }
+static inline int __syncthreads_and(int p) { return ts_emu::block_barrier(p != 0); }
+static inline void __syncwarp(unsigned mask = 0xffffffffu) { emu_require_full(mask); ts_emu::warp_exchange(0); }
+static inline unsigned __ballot_sync(unsigned mask, int p) {
+    emu_require_full(mask);
+    const uint32_t* v = ts_emu::warp_exchange(p ? 1u : 0u);
+    unsigned r = 0;
+    for (int i = 0; i < 32; ++i) r |= (v[i] & 1u) << i;
+    return r;
+}
+static inline int __any_sync(unsigned mask, int p) { return __ballot_sync(mask, p) != 0u; }
+static inline int __all_sync(unsigned mask, int p) { return __ballot_sync(mask, p) == 0xffffffffu; }
+static inline float __shfl_xor_sync(unsigned mask, float x, int d) {
+    emu_require_full(mask);
+    uint32_t u;
+    memcpy(&u, &x, 4);
+    const uint32_t* v = ts_emu::warp_exchange(u);
+    uint32_t r = v[(ts_emu::st().cur & 31) ^ d];
+    float f;
+    memcpy(&f, &r, 4);
+    return f;
+}
+static inline int __shfl_xor_sync(unsigned mask, int x, int d) {
+    emu_require_full(mask);
+    const uint32_t* v = ts_emu::warp_exchange((uint32_t)x);
+    return (int)v[(ts_emu::st().cur & 31) ^ d];
+}
+static inline int __ffs(unsigned x) { return __builtin_ffs((int)x); }
+template <typename T>
+static inline T __ldg(const T* p) { return *p; }
+static inline float __fsub_rn(float a, float b) { return a - b; }
+static inline float __fmul_rn(float a, float b) { return a * b; }
+static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
+static inline float atomicAdd(float* p, float v) { float o = *p; *p = o + v; return o; }
+static inline int atomicAdd(int* p, int v) { int o = *p; *p = o + v; return o; }
+static inline void atomicAdd(float4* p, float4 v) { p->x += v.x; p->y += v.y; p->z += v.z; p->w += v.w; }
+static inline int atomicMax(int* p, int v) { int o = *p; *p = std::max(o, v); return o; }
+using std::max;
+using std::min;

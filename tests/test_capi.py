@@ -111,3 +111,79 @@ def test_gsplat_surface():
     assert [deg_from_sh(n) for n in (1, 4, 9, 16, 25)] == [0, 1, 2, 3, 4]
     with pytest.raises(ValueError):
         deg_from_sh(7)
+
+
+def _rowmask_case(lib, x, y, cov, op, tile_x, tile_y):
+    """Brute force: every pixel of the tile the blend loop would accept (fp32 arithmetic in the
+    kernels' operation order, without fma — the difference is inside the mask's noise margin)
+    must have its (row, half) bit set in ts_debug_rowmask."""
+    import numpy as np
+    f = np.float32
+    a, b, c = cov
+    det = a * c - b * b
+    con = (c / det, -b / det, a / det)
+    LOG2E = 1.4426950408889634
+    q1 = np.array([0.5 * LOG2E * con[0], LOG2E * con[1], 0.5 * LOG2E * con[2], op], dtype=f)
+    tau = np.log(255.0 * op) + 0.01
+    hx = np.sqrt(2 * tau * a) * 1.001 + 0.01     # cov_xx = a  (cov = conic^-1)
+    hy = np.sqrt(2 * tau * c) * 1.001 + 0.01
+    q0 = np.array([x, y, hx, hy], dtype=f)
+    mask = lib.ts_debug_rowmask(q0.ctypes.data_as(ctypes.c_void_p), q1.ctypes.data_as(ctypes.c_void_p),
+                                tile_x, tile_y)
+    px = (f(tile_x * 16) + np.arange(16, dtype=f) + f(0.5))[None, :]
+    py = (f(tile_y * 16) + np.arange(16, dtype=f) + f(0.5))[:, None]
+    dx = q0[0] - px
+    dy = q0[1] - py
+    t = q1[1] * dy + q1[0] * dx
+    pw = t * dx + (q1[2] * dy) * dy
+    with np.errstate(over="ignore", invalid="ignore"):
+        alpha = np.minimum(f(0.999), q1[3] * np.exp2(-pw.astype(np.float64)).astype(f))
+    lit = (pw >= 0) & (alpha >= f(1.0 / 255.0))
+    bits = np.zeros((16, 2), dtype=bool)
+    for row in range(16):
+        for half in range(2):
+            bits[row, half] = (mask >> (2 * row + half)) & 1
+    need = lit.reshape(16, 2, 8).any(axis=2)
+    return need, bits
+
+
+def test_exact_rowmask_is_a_superset_of_lit_pixels_and_tight(lib):
+    import numpy as np
+    rng = np.random.default_rng(0)
+    missed = 0
+    n_need = n_bits = 0
+    for it in range(3000):
+        kind = it % 3
+        if kind == 0:      # bench-like blobs
+            s1, s2 = np.exp(rng.normal(0.6, 0.5, 2))
+        elif kind == 1:    # needles: one axis huge, one at the blur floor
+            s1, s2 = np.exp(rng.uniform(3, 7)), np.exp(rng.uniform(-3, 0))
+        else:              # big soft splats
+            s1, s2 = np.exp(rng.uniform(2, 5, 2))
+        th = rng.uniform(0, np.pi)
+        R = np.array([[np.cos(th), -np.sin(th)], [np.sin(th), np.cos(th)]])
+        S = R @ np.diag([s1 * s1, s2 * s2]) @ R.T
+        cov = (S[0, 0] + 0.3, S[0, 1], S[1, 1] + 0.3)
+        op = float(np.clip(1 / (1 + np.exp(-rng.normal(0, 1.5))), 1.0 / 255 + 1e-4, 0.9999))
+        tile_x, tile_y = int(rng.integers(0, 120)), int(rng.integers(0, 68))
+        reach = 3.5 * max(s1, s2) if kind != 1 else rng.uniform(0, 3.0 * max(s1, s2))
+        x = tile_x * 16 + 8 + rng.uniform(-1, 1) * (8 + reach)
+        y = tile_y * 16 + 8 + rng.uniform(-1, 1) * (8 + reach)
+        need, bits = _rowmask_case(lib, x, y, cov, op, tile_x, tile_y)
+        missed += int((need & ~bits).sum())
+        if kind == 0:
+            n_need += int(need.sum())
+            n_bits += int(bits.sum())
+    assert missed == 0, f"{missed} lit (row, half) cells are not covered by the exact row mask"
+    # tightness on bench-like Gaussians: the mask is exact up to its safety margins
+    assert n_need > 1000 and n_bits <= 1.10 * n_need, (n_need, n_bits)
+
+
+def test_rowmask_sentinels(lib):
+    import numpy as np
+    f = np.float32
+    q1 = np.array([0.1, 0.0, 0.1, 0.5], dtype=f)
+    for hx, expect in ((1e30, 0xffffffff), (-1e30, 0)):
+        q0 = np.array([8.0, 8.0, hx, hx], dtype=f)
+        assert lib.ts_debug_rowmask(q0.ctypes.data_as(ctypes.c_void_p), q1.ctypes.data_as(ctypes.c_void_p),
+                                    0, 0) == expect

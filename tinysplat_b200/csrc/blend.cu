@@ -11,7 +11,13 @@
 //
 // Not HBM-bound: fp32 FMA/MUFU issue bound (forward at ~89 % of peak issue rate); backward adds a
 // per-warp shared-memory reduction and L2 vector atomics (~72 % of peak issue rate).
-#include "ts_common.cuh"
+#include <cstdlib>
+#include <cstring>
+#include "ts_blend_common.cuh"
+
+#ifndef TS_DEFAULT_BLEND_MODE
+#define TS_DEFAULT_BLEND_MODE 0
+#endif
 
 namespace ts {
 
@@ -20,8 +26,6 @@ namespace ts {
 #endif
 constexpr int kBlendThreads = 256;
 constexpr int kBatch = 256;
-constexpr int kClampShift = 28;                      // n_contrib bits 28..30: clamped-channel mask
-constexpr int kCountMask = (1 << kClampShift) - 1;
 
 // Geometry of the thread->pixel map shared by forward and backward.
 struct PixMap {
@@ -61,17 +65,6 @@ __device__ __forceinline__ unsigned subblock_mask(float4 q0) {
     for (int wy = 0; wy < 4; ++wy)
         if (my & (1u << wy)) m |= mx << (2 * wy);
     return m;  // bit (2*wy + wx) == warp index of that sub-block
-}
-
-// Exponent (in log2 units) of one Gaussian at one pixel.  Written with explicit fma/mul
-// intrinsics so that forward and backward round identically: backward must re-derive exactly
-// the skip decisions (pw < 0, alpha < 1/255) forward took.
-__device__ __forceinline__ float eval_power(const float4& q0, const float4& q1, float px, float py,
-                                            float& dx, float& dy) {
-    dx = __fsub_rn(q0.x, px);
-    dy = __fsub_rn(q0.y, py);
-    float t = __fmaf_rn(q1.y, dy, __fmul_rn(q1.x, dx));
-    return __fmaf_rn(t, dx, __fmul_rn(__fmul_rn(q1.z, dy), dy));
 }
 
 template <int CH>
@@ -437,9 +430,41 @@ unpack_grads_kernel(int N, const int32_t* __restrict__ radii, const float* __res
     if (CH > 3) v_colors[(size_t)CH * i + 3] = g2.w;
 }
 
+// second-generation kernels (blend_group.cu)
+int launch_blend_fwd_group(int CH, int H, int W, int tiles_x, int tiles_y, const int32_t* tile_offsets,
+                           const int32_t* ids, const float* recs, const float* background,
+                           float* out_img, float* out_ch3, float* final_T, int32_t* n_contrib,
+                           int clamp_max1, cudaStream_t st);
+int launch_blend_bwd_group(int CH, int gch, int H, int W, int tiles_x, int tiles_y,
+                           const int32_t* tile_offsets, const int32_t* ids, const float* recs,
+                           const float* background, const float* final_T, const int32_t* n_contrib,
+                           const float* v_out_img, const float* v_out_ch3, int split_ch3,
+                           const float* v_out_alpha, float* grads, cudaStream_t st);
+
+// 0 = first generation (one warp per sub-block), 1 = grouped (blend_group.cu).  Initialised once
+// from TS_BLEND_MODE ("warp" | "group"); ts_set_blend_mode() overrides it (tests, A/B benches).
+constexpr int kDefaultBlendMode = TS_DEFAULT_BLEND_MODE;
+static int g_blend_mode = -1;
+static int blend_mode() {
+    if (g_blend_mode < 0) {
+        const char* e = getenv("TS_BLEND_MODE");
+        if (e && !strcmp(e, "warp")) g_blend_mode = 0;
+        else if (e && !strcmp(e, "group")) g_blend_mode = 1;
+        else g_blend_mode = kDefaultBlendMode;
+    }
+    return g_blend_mode;
+}
+
 }  // namespace ts
 
 extern "C" {
+
+int ts_set_blend_mode(int mode) {
+    if (mode < -1 || mode > 1) return TS_ERR_INVALID;
+    ts::g_blend_mode = mode;      // -1: back to TS_BLEND_MODE / the built-in default
+    return TS_OK;
+}
+int ts_get_blend_mode(void) { return ts::blend_mode(); }
 
 int ts_blend_fwd(int CH, int img_height, int img_width, int tiles_x, int tiles_y,
                  const int32_t* tile_offsets, const int32_t* ids_sorted, const float* recs,
@@ -450,6 +475,12 @@ int ts_blend_fwd(int CH, int img_height, int img_width, int tiles_x, int tiles_y
     if (recs && !ts::aligned16(recs)) return TS_ERR_ALIGN;
     dim3 grid(tiles_x, tiles_y);
     cudaStream_t st = (cudaStream_t)stream;
+    if (ts::blend_mode() == 1) {
+        ts::launch_blend_fwd_group(CH, img_height, img_width, tiles_x, tiles_y, tile_offsets, ids_sorted, recs,
+                                   background, out_img, out_ch3, final_T, n_contrib, clamp_max1, st);
+        TS_CHECK_LAUNCH("ts_blend_fwd/group");
+        return TS_OK;
+    }
 #define TS_LAUNCH_FWD(C) \
     ts::blend_fwd_kernel<C><<<grid, ts::kBlendThreads, 0, st>>>(img_height, img_width, tiles_x, tile_offsets, ids_sorted, (const float4*)recs, background, out_img, out_ch3, final_T, n_contrib, clamp_max1)
     switch (CH) {
@@ -478,6 +509,13 @@ int ts_blend_bwd(int N, int CH, int img_height, int img_width, int tiles_x, int 
     dim3 grid(tiles_x, tiles_y);
     // channels that carry a cotangent: the fused RGB+depth pass without a depth loss skips ch 3
     const int gch = (CH == 4 && split_ch3 && !v_out_ch3) ? 3 : CH;
+    if (ts::blend_mode() == 1) {
+        ts::launch_blend_bwd_group(CH, gch, img_height, img_width, tiles_x, tiles_y, tile_offsets, ids_sorted,
+                                   recs, background, final_T, n_contrib, v_out_img, v_out_ch3, split_ch3,
+                                   v_out_alpha, grads, st);
+        TS_CHECK_LAUNCH("ts_blend_bwd/group");
+        return TS_OK;
+    }
 #define TS_LAUNCH_BWD(C, G)                                                                              \
     do {                                                                                                 \
         static bool attr_done = false;                                                                   \

@@ -1,0 +1,509 @@
+// K4 / K5, second generation — "grouped" blend kernels (default; the first generation in blend.cu
+// stays selectable with ts_set_blend_mode(0) / TS_BLEND_MODE=warp for A/B runs).
+// Behind gsplat.rasterize_gaussians  [REF tinysplat/splatting/rasterize.py:44,50,83-86].
+//
+// Mapping.  One CTA of 64 threads per 16x16 tile [REF rasterize.py:19-20].  The 64 threads form
+// eight 8-lane GROUPS; group s owns the 8x4-pixel sub-block s of the tile, lane = column, and
+// every lane keeps the compositing state of its FOUR rows in registers.  The four groups of a
+// warp walk four DIFFERENT candidate lists in lock-step (per-lane shared-memory addresses), so
+// one warp-instruction evaluates one pixel row of four (sub-block, Gaussian) pairs.
+//
+// Why (measured with tools/cull_stats.py on synthetic_1M_1080p, per fwd or bwd pass):
+//   * culling is exact per pixel row (footprint_rowmask: the interval of each row the ellipse
+//     {alpha >= 1/255} covers), not a bounding box per sub-block: 6.15 M -> 5.31 M
+//     (sub-block, Gaussian) pairs, and rows the ellipse misses are skipped inside a pair;
+//   * backward: a lane first sums its four rows in registers, then ONE 8-lane butterfly
+//     (transpose-reduce, 3 shuffle levels) + one shared atomic per lane finishes a pair —
+//     the first generation paid a 32-lane reduction for every pair;
+//   * candidates are staged once per tile by 64 threads (2 records each), not by 256.
+// Still not HBM-bound: fp32 FMA / MUFU issue.
+#include "ts_blend_common.cuh"
+
+namespace ts {
+
+constexpr int kGThreads = 64;                  // 2 warps = 8 groups of 8 lanes
+constexpr int kGBatch = 128;                   // candidates staged per batch
+constexpr int kGPer = kGBatch / kGThreads;     // records gathered per thread per batch
+constexpr int kGWords = kGBatch / 32;          // candidate-mask words per group per batch
+
+struct GroupMap {
+    int lane, warp, grp, l8, shift;
+    int j, i0;          // pixel column, first of the four rows
+    float px, py0;
+    unsigned inside;    // bit r: pixel (i0 + r, j) is inside the image
+    float X0, Y0;       // pixel centre of the tile's first pixel
+};
+
+__device__ __forceinline__ GroupMap group_map(int H, int W) {
+    GroupMap m;
+    const int tid = threadIdx.x;
+    m.lane = tid & 31;
+    m.warp = tid >> 5;
+    m.grp = tid >> 3;                    // sub-block id: wx = grp & 1, wy = grp >> 1
+    m.l8 = tid & 7;
+    const int wx = m.grp & 1, wy = m.grp >> 1;
+    m.shift = 8 * wy + wx;               // rowmask bit of (row 4wy + r, half wx) = shift + 2r
+    m.j = blockIdx.x * kBlock + wx * 8 + m.l8;
+    m.i0 = blockIdx.y * kBlock + wy * 4;
+    m.px = (float)m.j + kPixCenter;
+    m.py0 = (float)m.i0 + kPixCenter;
+    m.inside = 0u;
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+        if (m.j < W && m.i0 + r < H) m.inside |= 1u << r;
+    m.X0 = (float)(blockIdx.x * kBlock) + kPixCenter;
+    m.Y0 = (float)(blockIdx.y * kBlock) + kPixCenter;
+    return m;
+}
+
+// Stage-time masks of one batch: s_rmask[t] = exact row mask of staged record t,
+// s_cmask[s * kGWords + k] = which of records 32k..32k+31 can reach sub-block s.
+// `valid[jj]`: this thread's record jj of the batch exists.  Must be reached by all 64 threads.
+__device__ __forceinline__ void build_masks(const GroupMap& gm, const float4* rec, const bool (&valid)[kGPer],
+                                            unsigned* s_rmask, unsigned* s_cmask) {
+    const unsigned full = 0xffffffffu;
+#pragma unroll
+    for (int jj = 0; jj < kGPer; ++jj) {
+        const int t = jj * kGThreads + threadIdx.x;
+        unsigned rm = 0u;
+        if (valid[jj]) rm = footprint_rowmask(rec[t * 3], rec[t * 3 + 1], gm.X0, gm.Y0);
+        s_rmask[t] = rm;
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+            const unsigned sel = 0x55u << (8 * (s >> 1) + (s & 1));
+            const unsigned w = __ballot_sync(full, (rm & sel) != 0u);
+            if (gm.lane == 0) s_cmask[s * kGWords + jj * 2 + gm.warp] = w;
+        }
+    }
+}
+
+template <int CH>
+__global__ void __launch_bounds__(kGThreads)
+blend_fwd_group_kernel(int H, int W, int tbx, const int32_t* __restrict__ tile_offsets,
+                       const int32_t* __restrict__ ids, const float4* __restrict__ recs,
+                       const float* __restrict__ background, float* __restrict__ out_img,
+                       float* __restrict__ out_ch3, float* __restrict__ final_T,
+                       int32_t* __restrict__ n_contrib, int clamp_max1) {
+    __shared__ __align__(16) float4 s_rec[2][kGBatch * 3];
+    __shared__ unsigned s_rmask[kGBatch];
+    __shared__ unsigned s_cmask[8 * kGWords];
+    const unsigned full = 0xffffffffu;
+    const GroupMap gm = group_map(H, W);
+    const int tid = threadIdx.x;
+    const int tile = blockIdx.y * tbx + blockIdx.x;
+    const int start = __ldg(tile_offsets + tile);
+    const int count = __ldg(tile_offsets + tile + 1) - start;
+    const int nb = (count + kGBatch - 1) / kGBatch;
+    const unsigned gbits = 0xffu << (gm.lane & 24);      // the lanes of my group
+
+    // T[r] > 0: pixel r still composites; T[r] < 0: finished, |T| is its final transmittance
+    // (pixels outside the image start finished)
+    float T[4], acc[4][CH];
+    int ncon[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        T[r] = ((gm.inside >> r) & 1u) ? 1.f : -1.f;
+        ncon[r] = 0;
+#pragma unroll
+        for (int c = 0; c < CH; ++c) acc[r][c] = 0.f;
+    }
+
+    auto prefetch = [&](int b) {
+#pragma unroll
+        for (int jj = 0; jj < kGPer; ++jj) {
+            const int t = jj * kGThreads + tid;
+            const int p = b * kGBatch + t;
+            if (p < count) {
+                const int g = __ldg(ids + start + p);
+                const float4* src = recs + 3 * (size_t)g;
+                float4* dst = &s_rec[b & 1][t * 3];
+                cp_async16(dst, src);
+                cp_async16(dst + 1, src + 1);
+                cp_async16(dst + 2, src + 2);
+            }
+        }
+    };
+    if (nb > 0) prefetch(0);
+    cp_async_commit();
+
+    for (int b = 0; b < nb; ++b) {
+        const float4* rec = s_rec[b & 1];
+        if (b + 1 < nb) prefetch(b + 1);
+        cp_async_commit();
+        cp_async_wait<1>();       // this thread's copies of batch b have landed
+        bool valid[kGPer];
+#pragma unroll
+        for (int jj = 0; jj < kGPer; ++jj) valid[jj] = b * kGBatch + jj * kGThreads + tid < count;
+        build_masks(gm, rec, valid, s_rmask, s_cmask);
+        __syncthreads();          // records + masks of batch b visible to all
+
+        int k = 0;
+        unsigned m = s_cmask[gm.grp * kGWords];
+        for (;;) {
+            // a group whose 32 pixels are all finished stops walking its list
+            const bool lane_live = fmaxf(fmaxf(T[0], T[1]), fmaxf(T[2], T[3])) > 0.f;
+            if ((__ballot_sync(full, lane_live) & gbits) == 0u) { m = 0u; k = kGWords - 1; }
+            while (m == 0u && k < kGWords - 1) m = s_cmask[gm.grp * kGWords + (++k)];
+            const bool act = (m != 0u);
+            if (!__any_sync(full, act)) break;
+            if (act) {
+                const int c = k * 32 + __ffs(m) - 1;
+                m &= m - 1;
+                const unsigned rm = s_rmask[c] >> gm.shift;
+                const float4 q0 = rec[c * 3];
+                const float4 q1 = rec[c * 3 + 1];
+                const float4 q2 = rec[c * 3 + 2];
+                // branch-free over the four rows: four independent chains for the scheduler
+                float alpha[4];
+                bool ok[4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    float dx, dy;
+                    const float pw = eval_power(q0, q1, gm.px, gm.py0 + (float)r, dx, dy);
+                    alpha[r] = fminf(kAlphaMax, __fmul_rn(q1.w, ex2_approx(-fmaxf(pw, 0.f))));
+                    // row reachable (row mask), pixel still compositing, contribution kept
+                    ok[r] = (rm & (1u << (2 * r))) != 0u && T[r] > 0.f && pw >= 0.f && alpha[r] >= kAlphaMin;
+                }
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const float nT = T[r] * (1.f - alpha[r]);
+                    const bool stop = ok[r] && nT <= kTStop;
+                    const bool upd = ok[r] && !stop;
+                    const float wgt = upd ? alpha[r] * T[r] : 0.f;
+                    acc[r][0] = fmaf(wgt, q2.x, acc[r][0]);
+                    if (CH > 1) acc[r][1] = fmaf(wgt, q2.y, acc[r][1]);
+                    if (CH > 2) acc[r][2] = fmaf(wgt, q2.z, acc[r][2]);
+                    if (CH > 3) acc[r][3] = fmaf(wgt, q2.w, acc[r][3]);
+                    T[r] = upd ? nT : (stop ? -T[r] : T[r]);
+                    ncon[r] = upd ? b * kGBatch + c + 1 : ncon[r];
+                }
+            }
+        }
+        // also guards reuse of s_rec[b & 1] / masks by the next iterations
+        if (__syncthreads_and(!(fmaxf(fmaxf(T[0], T[1]), fmaxf(T[2], T[3])) > 0.f))) break;
+    }
+    cp_async_wait<0>();
+
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        if (!((gm.inside >> r) & 1u)) continue;
+        const size_t pix = (size_t)(gm.i0 + r) * W + gm.j;
+        const float Tf = fabsf(T[r]);
+        int nc = ncon[r];
+        if (CH == 4 && out_ch3) {   // split output: RGB image + separate 4th-channel (depth) map
+            // clamp_max1 folds the adapter's clamp(rgb, max=1) [REF rasterize.py:45] in; which
+            // channels were clamped (zero gradient) is kept in the top bits of n_contrib
+            unsigned cm = 0;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                float o = fmaf(Tf, __ldg(background + c), acc[r][c]);
+                if (clamp_max1 && o > 1.f) { o = 1.f; cm |= 1u << c; }
+                out_img[pix * 3 + c] = o;
+            }
+            out_ch3[pix] = fmaf(Tf, __ldg(background + 3), acc[r][CH - 1]);
+            nc |= (int)(cm << kClampShift);
+        } else {
+#pragma unroll
+            for (int c = 0; c < CH; ++c) out_img[pix * CH + c] = fmaf(Tf, __ldg(background + c), acc[r][c]);
+        }
+        final_T[pix] = Tf;
+        n_contrib[pix] = nc;
+    }
+}
+
+// Sums val[0..NV) over the 8 lanes of each group.  Values 0..7 go through a transpose-reduce
+// (xor 4, 2, 1: every level halves the values a lane carries), after which lane l8 holds the
+// group total of value l8; values 8.. are reduced plainly and returned in `extra` on every lane.
+template <int NV>
+__device__ __forceinline__ float group_reduce(const float (&val)[NV], int l8, float (&extra)[2]) {
+    const unsigned full = 0xffffffffu;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = (i < NV) ? val[i] : 0.f;
+    const bool h4 = (l8 & 4) != 0, h2 = (l8 & 2) != 0, h1 = (l8 & 1) != 0;
+    float w[4], u[2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float send = h4 ? v[i] : v[i + 4];
+        const float keep = h4 ? v[i + 4] : v[i];
+        w[i] = keep + __shfl_xor_sync(full, send, 4);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float send = h2 ? w[i] : w[i + 2];
+        const float keep = h2 ? w[i + 2] : w[i];
+        u[i] = keep + __shfl_xor_sync(full, send, 2);
+    }
+    const float send = h1 ? u[0] : u[1];
+    const float keep = h1 ? u[1] : u[0];
+    const float mine = keep + __shfl_xor_sync(full, send, 1);
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+        float x = (8 + e < NV) ? val[(8 + e < NV) ? 8 + e : 0] : 0.f;
+        if (8 + e < NV) {
+            x += __shfl_xor_sync(full, x, 4);
+            x += __shfl_xor_sync(full, x, 2);
+            x += __shfl_xor_sync(full, x, 1);
+        }
+        extra[e] = x;
+    }
+    return mine;
+}
+
+// GCH = number of colour channels that carry a cotangent (GCH <= CH; the fused RGB+depth pass
+// with no depth loss has CH = 4, GCH = 3 and skips all channel-3 gradient arithmetic).
+template <int CH, int GCH>
+__global__ void __launch_bounds__(kGThreads)
+blend_bwd_group_kernel(int H, int W, int tbx, const int32_t* __restrict__ tile_offsets,
+                       const int32_t* __restrict__ ids, const float4* __restrict__ recs,
+                       const float* __restrict__ background, const float* __restrict__ final_T,
+                       const int32_t* __restrict__ n_contrib, const float* __restrict__ v_out_img,
+                       const float* __restrict__ v_out_ch3, int split_ch3,
+                       const float* __restrict__ v_out_alpha, float4* __restrict__ grads) {
+    constexpr int NV = 6 + GCH;    // values reduced per (sub-block, Gaussian) pair
+    __shared__ __align__(16) float4 s_rec[2][kGBatch * 3];
+    __shared__ __align__(16) float s_acc[kGBatch * kGradFloats];   // per-batch CTA accumulators
+    __shared__ unsigned s_rmask[kGBatch];
+    __shared__ unsigned s_cmask[8 * kGWords];
+    __shared__ int s_nmax;
+    const unsigned full = 0xffffffffu;
+    const GroupMap gm = group_map(H, W);
+    const int tid = threadIdx.x;
+    const int tile = blockIdx.y * tbx + blockIdx.x;
+    const int start = __ldg(tile_offsets + tile);
+
+    // per-pixel state of this lane's four rows
+    float T[4], wfin[4], v_out[4][GCH], buffer[4][GCH];
+    int nc[4];
+    int ncmax = 0;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        float T_final = 1.f, v_oa = 0.f;
+        nc[r] = 0;
+#pragma unroll
+        for (int c = 0; c < GCH; ++c) { v_out[r][c] = 0.f; buffer[r][c] = 0.f; }
+        if ((gm.inside >> r) & 1u) {
+            const size_t pix = (size_t)(gm.i0 + r) * W + gm.j;
+            T_final = __ldg(final_T + pix);
+            int n = __ldg(n_contrib + pix);
+            const unsigned cm = (unsigned)n >> kClampShift;    // channels clamped by forward
+            nc[r] = n & kCountMask;
+            if (CH == 4 && split_ch3) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    v_out[r][c] = (v_out_img && !((cm >> c) & 1u)) ? __ldg(v_out_img + pix * 3 + c) : 0.f;
+                if (GCH == 4) v_out[r][GCH - 1] = v_out_ch3 ? __ldg(v_out_ch3 + pix) : 0.f;
+            } else {
+#pragma unroll
+                for (int c = 0; c < GCH; ++c) v_out[r][c] = __ldg(v_out_img + pix * CH + c);
+            }
+            if (v_out_alpha) v_oa = __ldg(v_out_alpha + pix);
+        }
+        float bgdot = 0.f;
+#pragma unroll
+        for (int c = 0; c < GCH; ++c) bgdot = fmaf(__ldg(background + c), v_out[r][c], bgdot);
+        wfin[r] = T_final * (v_oa - bgdot);
+        T[r] = T_final;
+        ncmax = max(ncmax, nc[r]);
+    }
+
+    if (tid == 0) s_nmax = 0;
+#pragma unroll
+    for (int k = 0; k < kGPer * kGradFloats; ++k) s_acc[k * kGThreads + tid] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) ncmax = max(ncmax, __shfl_xor_sync(full, ncmax, d));
+    if (gm.lane == 0) atomicMax(&s_nmax, ncmax);
+    __syncthreads();
+    const int nmax = s_nmax;   // entries [0, nmax) of the tile list contributed somewhere
+    const int nb = (nmax + kGBatch - 1) / kGBatch;
+
+    // batch b, slot t  <->  list position  p = nmax-1 - (b*kGBatch + t)   (back to front)
+    int gnext[kGPer], gcur[kGPer];
+    auto prefetch = [&](int b) {
+#pragma unroll
+        for (int jj = 0; jj < kGPer; ++jj) {
+            const int t = jj * kGThreads + tid;
+            const int p = nmax - 1 - (b * kGBatch + t);
+            gnext[jj] = -1;
+            if (p >= 0) {
+                const int g = __ldg(ids + start + p);
+                gnext[jj] = g;
+                const float4* src = recs + 3 * (size_t)g;
+                float4* dst = &s_rec[b & 1][t * 3];
+                cp_async16(dst, src);
+                cp_async16(dst + 1, src + 1);
+                cp_async16(dst + 2, src + 2);
+            }
+        }
+    };
+#pragma unroll
+    for (int jj = 0; jj < kGPer; ++jj) gnext[jj] = -1;
+    if (nb > 0) prefetch(0);
+    cp_async_commit();
+
+    // value index -> float offset inside the packed gradient record (colours start at float 8)
+    const int my_off = gm.l8 < 6 ? gm.l8 : gm.l8 + 2;
+
+    for (int b = 0; b < nb; ++b) {
+        const float4* rec = s_rec[b & 1];
+        bool valid[kGPer];
+#pragma unroll
+        for (int jj = 0; jj < kGPer; ++jj) { gcur[jj] = gnext[jj]; valid[jj] = gcur[jj] >= 0; }
+        if (b + 1 < nb) prefetch(b + 1);
+        cp_async_commit();
+        cp_async_wait<1>();
+        build_masks(gm, rec, valid, s_rmask, s_cmask);
+        __syncthreads();
+        const int pbase = nmax - 1 - b * kGBatch;
+
+        int k = 0;
+        unsigned m = s_cmask[gm.grp * kGWords];
+        for (;;) {
+            while (m == 0u && k < kGWords - 1) m = s_cmask[gm.grp * kGWords + (++k)];
+            const bool act = (m != 0u);
+            if (!__any_sync(full, act)) break;
+            int c = 0;
+            float val[NV];
+#pragma unroll
+            for (int v = 0; v < NV; ++v) val[v] = 0.f;
+            bool any = false;
+            if (act) {
+                c = k * 32 + __ffs(m) - 1;
+                m &= m - 1;
+                const int p = pbase - c;
+                const unsigned rm = s_rmask[c] >> gm.shift;
+                const float4 q0 = rec[c * 3];
+                const float4 q1 = rec[c * 3 + 1];
+                const float4 q2 = rec[c * 3 + 2];
+                const float col[4] = {q2.x, q2.y, q2.z, q2.w};
+                // branch-free over the four rows.  A lane is one pixel COLUMN, so dx is common to
+                // its rows and only s0 = sum v_sigma, s1 = sum v_sigma dy, s2 = sum v_sigma dy^2
+                // are accumulated per row; the five geometric sums follow from them below, and
+                // v_opacity = sum vis * v_alpha = -s0 / opacity  (v_sigma = -opacity vis v_alpha).
+                float s0 = 0.f, s1 = 0.f, s2 = 0.f, dxc = 0.f;
+                float vis[4], araw[4], dyr[4];
+                bool ok[4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const float pw = eval_power(q0, q1, gm.px, gm.py0 + (float)r, dxc, dyr[r]);
+                    vis[r] = ex2_approx(-fmaxf(pw, 0.f));
+                    araw[r] = __fmul_rn(q1.w, vis[r]);
+                    ok[r] = (rm & (1u << (2 * r))) != 0u && p < nc[r] && pw >= 0.f &&
+                            fminf(kAlphaMax, araw[r]) >= kAlphaMin;
+                    any = any || ok[r];
+                }
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const float alpha = ok[r] ? fminf(kAlphaMax, araw[r]) : 0.f;
+                    const float ra = rcp_approx(1.f - alpha);          // 1 when !ok
+                    T[r] = ok[r] ? T[r] * ra : T[r];
+                    const float fac = alpha * T[r];                    // 0 when !ok
+                    float v_alpha = wfin[r] * ra;
+#pragma unroll
+                    for (int ch = 0; ch < GCH; ++ch) {
+                        val[6 + ch] = fmaf(fac, v_out[r][ch], val[6 + ch]);
+                        v_alpha = fmaf(col[ch] * T[r] - buffer[r][ch] * ra, v_out[r][ch], v_alpha);
+                        buffer[r][ch] = fmaf(col[ch], fac, buffer[r][ch]);
+                    }
+                    // !ok: no contribution;  clamped alpha: d alpha / d araw = 0
+                    const float v_sig = (ok[r] && !(araw[r] > kAlphaMax)) ? -araw[r] * v_alpha : 0.f;
+                    s0 += v_sig;
+                    s1 = fmaf(v_sig, dyr[r], s1);
+                    s2 = fmaf(v_sig * dyr[r], dyr[r], s2);
+                }
+                val[0] = s0 * dxc;
+                val[1] = s1;
+                val[2] = val[0] * dxc;
+                val[3] = s1 * dxc;
+                val[4] = s2;
+                val[5] = -s0 * rcp_approx(q1.w);
+            }
+            if (!__any_sync(full, any)) continue;
+            float extra[2];
+            const float mine = group_reduce<NV>(val, gm.l8, extra);
+            if (act) {
+                float* a = s_acc + c * kGradFloats;
+                if (gm.l8 < NV && mine != 0.f) atomicAdd(a + my_off, mine);
+                if (NV > 8 && gm.l8 == 0 && extra[0] != 0.f) atomicAdd(a + 10, extra[0]);
+                if (NV > 9 && gm.l8 == 1 && extra[1] != 0.f) atomicAdd(a + 11, extra[1]);
+            }
+        }
+        __syncthreads();  // all groups finished batch b: s_acc complete
+#pragma unroll
+        for (int jj = 0; jj < kGPer; ++jj) {
+            const int t = jj * kGThreads + tid;
+            if (s_rmask[t] != 0u) {
+                float4* a4 = reinterpret_cast<float4*>(s_acc + t * kGradFloats);
+                float4* dst = grads + 3 * (size_t)gcur[jj];
+                atomicAdd(dst, a4[0]);
+                atomicAdd(dst + 1, a4[1]);
+                atomicAdd(dst + 2, a4[2]);
+                a4[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+                a4[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                a4[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        __syncthreads();  // s_acc reset + buffers free before the next batch touches them
+    }
+    cp_async_wait<0>();
+}
+
+#ifndef TS_HOST_EMU
+// ---- launchers (called from the C-ABI entry points in blend.cu) ------------------------------
+int launch_blend_fwd_group(int CH, int H, int W, int tiles_x, int tiles_y, const int32_t* tile_offsets,
+                           const int32_t* ids, const float* recs, const float* background,
+                           float* out_img, float* out_ch3, float* final_T, int32_t* n_contrib,
+                           int clamp_max1, cudaStream_t st) {
+    dim3 grid(tiles_x, tiles_y);
+#define TS_LAUNCH_FWD(C) \
+    blend_fwd_group_kernel<C><<<grid, kGThreads, 0, st>>>(H, W, tiles_x, tile_offsets, ids, (const float4*)recs, background, out_img, out_ch3, final_T, n_contrib, clamp_max1)
+    switch (CH) {
+        case 1: TS_LAUNCH_FWD(1); break;
+        case 2: TS_LAUNCH_FWD(2); break;
+        case 3: TS_LAUNCH_FWD(3); break;
+        default: TS_LAUNCH_FWD(4); break;
+    }
+#undef TS_LAUNCH_FWD
+    return 0;
+}
+
+int launch_blend_bwd_group(int CH, int gch, int H, int W, int tiles_x, int tiles_y,
+                           const int32_t* tile_offsets, const int32_t* ids, const float* recs,
+                           const float* background, const float* final_T, const int32_t* n_contrib,
+                           const float* v_out_img, const float* v_out_ch3, int split_ch3,
+                           const float* v_out_alpha, float* grads, cudaStream_t st) {
+    dim3 grid(tiles_x, tiles_y);
+#define TS_LAUNCH_BWD(C, G)                                                                        \
+    blend_bwd_group_kernel<C, G><<<grid, kGThreads, 0, st>>>(                                      \
+        H, W, tiles_x, tile_offsets, ids, (const float4*)recs, background, final_T, n_contrib,     \
+        v_out_img, v_out_ch3, split_ch3, v_out_alpha, (float4*)grads)
+    switch (CH) {
+        case 1: TS_LAUNCH_BWD(1, 1); break;
+        case 2: TS_LAUNCH_BWD(2, 2); break;
+        case 3: TS_LAUNCH_BWD(3, 3); break;
+        default:
+            if (gch == 3) TS_LAUNCH_BWD(4, 3); else TS_LAUNCH_BWD(4, 4);
+            break;
+    }
+#undef TS_LAUNCH_BWD
+    return 0;
+}
+#endif  // !TS_HOST_EMU
+
+}  // namespace ts
+
+#ifndef TS_HOST_EMU
+extern "C" {
+
+// Host-side evaluation of the exact row mask of one packed record against tile (tile_x, tile_y):
+// the same function the kernels run (test hook: tests/test_capi.py brute-forces it on CPU).
+uint32_t ts_debug_rowmask(const float* q0, const float* q1, int tile_x, int tile_y) {
+    const float4 a = make_float4(q0[0], q0[1], q0[2], q0[3]);
+    const float4 b = make_float4(q1[0], q1[1], q1[2], q1[3]);
+    return ts::footprint_rowmask(a, b, (float)(tile_x * ts::kBlock) + ts::kPixCenter,
+                                 (float)(tile_y * ts::kBlock) + ts::kPixCenter);
+}
+
+}  // extern "C"
+#endif  // !TS_HOST_EMU

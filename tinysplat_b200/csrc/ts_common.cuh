@@ -1,6 +1,13 @@
 // Shared device helpers and constants of the tinysplat_b200 kernels (sm_100a only).
 #pragma once
+// TS_HOST_EMU: tests/emu compiles the grouped blend kernels as HOST code on a fiber-based SIMT
+// emulator (threadIdx, __shared__, warp votes/shuffles, barriers) so that the kernel logic is
+// checked against the oracle without a GPU.  Test infrastructure only; never defined in the product.
+#ifdef TS_HOST_EMU
+#include "ts_emu.h"
+#else
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 #include "../../include/tinysplat_b200.h"
 
@@ -115,6 +122,14 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+#ifdef TS_HOST_EMU
+__device__ __forceinline__ float ex2_approx(float x) { return exp2f(x); }
+__device__ __forceinline__ float rcp_approx(float x) { return 1.f / x; }
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) { memcpy(smem_dst, gmem_src, 16); }
+__device__ __forceinline__ void cp_async_commit() {}
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {}
+#else
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -170,5 +185,7 @@ __device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, u
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
+#endif  // TS_HOST_EMU
 
 }  // namespace ts
