@@ -195,11 +195,13 @@ TS_API int ts_blend_unpack_grads(int N, int CH, const int32_t* radii, const floa
                                  const float* grads /*[16B]*/, float* v_xys, float* v_conics,
                                  float* v_colors, float* v_opacity, ts_stream_t stream);
 /* Two generations of blend kernels sit behind ts_blend_fwd / ts_blend_bwd with identical
- * semantics (same skip decisions, same final_T / n_contrib): mode 0 = one warp per 8x4
- * sub-block, bounding-box culling (blend.cu); mode 1 = one 8-lane group per sub-block, four rows
- * per lane, exact per-row culling (blend_group.cu).  The default comes from the environment
- * variable TS_BLEND_MODE ("warp" | "group") or the built-in default; ts_set_blend_mode(-1)
- * returns to it.  Process-wide, not thread-safe against concurrent launches. */
+ * semantics (same skip decisions, bit-identical images / final_T / n_contrib): first generation
+ * = one warp per 8x4 sub-block, bounding-box culling (blend.cu); grouped = one 8-lane group per
+ * sub-block, four rows per lane, exact per-row culling (blend_group.cu).  mode is a bit mask:
+ * bit 0 = forward grouped, bit 1 = backward grouped (0..3).  The default comes from the
+ * environment variable TS_BLEND_MODE ("warp" = 0 | "group" = 3 | "0".."3") or the built-in
+ * default; ts_set_blend_mode(-1) returns to it.  Process-wide, not thread-safe against
+ * concurrent launches. */
 TS_API int ts_set_blend_mode(int mode);
 TS_API int ts_get_blend_mode(void);
 /* Test hook (host code, no GPU): the exact row mask the mode-1 kernels compute for one packed

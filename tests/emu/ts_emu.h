@@ -203,6 +203,13 @@ static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c);
 static inline float atomicAdd(float* p, float v) { float o = *p; *p = o + v; return o; }
 static inline int atomicAdd(int* p, int v) { int o = *p; *p = o + v; return o; }
 static inline void atomicAdd(float4* p, float4 v) { p->x += v.x; p->y += v.y; p->z += v.z; p->w += v.w; }
+static inline unsigned long long atomicCAS(unsigned long long* p, unsigned long long cmp, unsigned long long v) {
+    unsigned long long o = *p;
+    if (o == cmp) *p = v;
+    return o;
+}
+static inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
+static inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
 static inline int atomicMax(int* p, int v) { int o = *p; *p = std::max(o, v); return o; }
 using std::max;
 using std::min;

@@ -212,3 +212,28 @@ def test_emulator_detects_a_lane_that_skips_a_collective(emu, tmp_path):
     so = tmp_path / "dead.so"
     subprocess.run(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-I" + EMU, "-o", str(so), str(src)], check=True)
     assert C.CDLL(str(so)).run() == -1
+
+
+def test_grouped_backward_zero_opacity_without_culling_stays_finite(emu):
+    """cull_mode = 0 keeps every (Gaussian, tile) pair, including Gaussians whose opacity is
+    exactly 0: v_opacity is formed as -s0 / opacity in the grouped kernel and must not turn a
+    0 * inf into a NaN that a neighbouring group's reduction then spreads."""
+    n, W, H, ch = 200, 32, 32, 3
+    xys, depths, radii, conics, ntiles, colors, opac, tb = _scene(n, W, H, 8, 6.0, ch)
+    opac[::3] = 0.0
+    bg = torch.zeros(ch)
+    rec = _pack(xys, conics, opac, colors, False)
+    offsets, ids = _lists(xys, depths, radii, tb)
+    out = np.zeros((H, W, ch), dtype=np.float32)
+    final_T = np.zeros((H, W), dtype=np.float32)
+    ncon = np.zeros((H, W), dtype=np.int32)
+    bgn = np.ascontiguousarray(bg.numpy())
+    assert emu.emu_blend_fwd(ch, H, W, tb[0], tb[1], _ptr(offsets), _ptr(ids), _ptr(rec), _ptr(bgn), _ptr(out),
+                             None, _ptr(final_T), _ptr(ncon), 0) == 0
+    grads = np.zeros((n, 12), dtype=np.float32)
+    vi = np.ones((H, W, ch), dtype=np.float32)
+    assert emu.emu_blend_bwd(n, ch, H, W, tb[0], tb[1], _ptr(offsets), _ptr(ids), _ptr(rec), _ptr(bgn),
+                             _ptr(final_T), _ptr(ncon), _ptr(vi), None, 0, None, _ptr(grads)) == 0
+    assert np.isfinite(grads).all()
+    assert np.abs(grads[::3]).max() == 0.0
+    assert np.abs(grads).max() > 0.0

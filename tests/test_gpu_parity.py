@@ -35,6 +35,15 @@ def _need_cuda(lib):
         pytest.skip("no CUDA device")
 
 
+@pytest.fixture(params=[0, 3], ids=["blend-warp", "blend-group"])
+def blend_mode(request, lib):
+    """Runs a test once per generation of blend kernels (include/tinysplat_b200.h,
+    ts_set_blend_mode): 0 = one warp per sub-block, 3 = grouped forward + backward."""
+    assert lib.ts_set_blend_mode(request.param) == 0
+    yield request.param
+    lib.ts_set_blend_mode(-1)
+
+
 def rel_err(a, b):
     a, b = a.detach().double().cpu(), b.detach().double().cpu()
     return (a - b).abs().max().item() / max(b.abs().max().item(), 1e-30)
@@ -135,7 +144,7 @@ def _raster_case(N, W, H, seed, CH=3):
 
 @pytest.mark.parametrize("N,W,H,CH", [(256, 128, 128, 3), (3000, 320, 200, 3), (400, 50, 35, 4),
                                       (300, 64, 64, 1), (1500, 96, 96, 2)])
-def test_rasterize_forward_and_backward(N, W, H, CH):
+def test_rasterize_forward_and_backward(N, W, H, CH, blend_mode):
     import gsplat
     xys, dep, rad, con, nt, colors, opac, bg = _raster_case(N, W, H, seed=N + CH, CH=CH)
     leaf = lambda t, dt, dev: t.to(dt).to(dev).clone().requires_grad_(True)
@@ -161,7 +170,7 @@ def test_rasterize_forward_and_backward(N, W, H, CH):
         assert rel_err(a.grad, b.grad) < TOL_GRAD, name
 
 
-def test_footprint_culling_is_result_invariant():
+def test_footprint_culling_is_result_invariant(blend_mode):
     """cull_mode=1 (opacity-aware footprint culling at tile and sub-tile level) must not change
     the image or the gradients relative to the plain 3-sigma-bbox algorithm (cull_mode=0)."""
     import gsplat
@@ -257,7 +266,7 @@ def test_big_tile_fallback_sort():
     assert torch.equal(bins.ids_sorted.cpu().long(), want)
 
 
-def test_full_adapter_matches_golden_config1():
+def test_full_adapter_matches_golden_config1(blend_mode):
     """BASELINE config 1 (256 Gaussians, 128x128) through both pipelines of the adapter mirror,
     against the committed fp64-oracle vectors."""
     from tinysplat_b200.rasterizer import GaussianRasterizer, ParamModel
@@ -280,7 +289,7 @@ def test_full_adapter_matches_golden_config1():
 
 
 @pytest.mark.parametrize("pipeline", ["reference", "fused"])
-def test_no_grad_forward_and_retain_graph(pipeline):
+def test_no_grad_forward_and_retain_graph(pipeline, blend_mode):
     """The viewer renders under no_grad [REF tinysplat/viewer.py:90-93]; training calls
     backward(retain_graph=True) [REF scripts/train.py:94]: a second backward must reproduce the
     first (saved buffers are neither freed nor mutated)."""
@@ -308,7 +317,7 @@ def test_no_grad_forward_and_retain_graph(pipeline):
     assert ex["xys"].grad.norm(dim=-1).shape == (500,)    # what update_grad_accum reads
 
 
-def test_fused_node_matches_unfused_ops_on_a_larger_scene():
+def test_fused_node_matches_unfused_ops_on_a_larger_scene(blend_mode):
     """The single fused autograd node (activations folded into the kernels, packed gradients
     consumed in place) against the composition of the five public ops, 20k Gaussians, with a
     depth loss so the depth cotangent path (colour channel 3 -> v_depths) is live."""
@@ -335,7 +344,7 @@ def test_fused_node_matches_unfused_ops_on_a_larger_scene():
         assert rel_err(gb, ga) < 1e-4, name
 
 
-def test_empty_and_all_culled_scenes():
+def test_empty_and_all_culled_scenes(blend_mode):
     import gsplat
     W, H = 40, 24
     bg = torch.tensor([0.1, 0.6, 0.9], device=DEV)
@@ -358,7 +367,7 @@ def test_empty_and_all_culled_scenes():
     assert ins[0].grad.abs().max() == 0
 
 
-def test_fused_pipeline_empty_scene_and_no_grad_outputs():
+def test_fused_pipeline_empty_scene_and_no_grad_outputs(blend_mode):
     from tinysplat_b200.rasterizer import GaussianRasterizer, ParamModel
     W, H = 50, 34
     cam = synthetic.make_camera(W, H)
@@ -385,7 +394,7 @@ def test_fused_pipeline_empty_scene_and_no_grad_outputs():
 
 
 @pytest.mark.parametrize("pipeline", ["reference", "fused"])
-def test_huge_and_extreme_gaussians_match_oracle(pipeline):
+def test_huge_and_extreme_gaussians_match_oracle(pipeline, blend_mode):
     """Screen-filling Gaussians (warp-cooperative tile expansion, hundreds of tiles each), nearly
     opaque and nearly transparent ones, strongly anisotropic ones, mixed with ordinary ones."""
     from tinysplat_b200.rasterizer import GaussianRasterizer, ParamModel
@@ -453,6 +462,39 @@ def test_full_size_properties_1080p():
     # d(sum img)/d c_i = sum_pixels w_i ; summed over i and channels = 3 * sum_pixels (1 - T)
     assert abs(c1.grad.sum().item() / (3 * a1.double().sum().item()) - 1) < 1e-3
     assert rz.last_stats["num_intersects"] > N
+
+
+def test_blend_generations_agree_at_full_size(lib):
+    """1M Gaussians at 1080p through the fused adapter with both generations of blend kernels:
+    the forward arithmetic per pixel is identical (same order, same skip decisions), so images,
+    depth, final transmittance must be BIT-identical — which also proves on real hardware that
+    the exact per-row culling of the grouped kernels never drops a contribution — and the
+    gradients agree up to the order of the float sums."""
+    from tinysplat_b200.rasterizer import GaussianRasterizer, ParamModel
+    W, H, N = 1920, 1080, 1_000_000
+    cam = synthetic.make_camera(W, H, yaw_deg=2.0)
+    sc = synthetic.make_scene(N, W, H, seed=0)
+    sc["background"] = torch.tensor([0.1, 0.2, 0.3])
+    g = torch.Generator().manual_seed(11)
+    wi = torch.rand(H, W, 3, generator=g).to(DEV)
+    wd = torch.rand(H, W, generator=g).to(DEV)
+    res = {}
+    try:
+        for mode in (0, 3, 1, 2):
+            assert lib.ts_set_blend_mode(mode) == 0
+            model = ParamModel(sc, DEV, 3)
+            img, ex = GaussianRasterizer(model, None, DEV, "fused")(cam, (W, H), 3)
+            ((img * wi).sum() + 0.01 * (ex["depth"] * wd).sum()).backward()
+            res[mode] = (img, ex["depth"], ex["xys"].grad, [p.grad for p in model.parameters()])
+    finally:
+        lib.ts_set_blend_mode(-1)
+    for mode in (3, 1, 2):
+        assert torch.equal(res[0][0], res[mode][0]), f"image differs in mode {mode}"
+        assert torch.equal(res[0][1], res[mode][1]), f"depth differs in mode {mode}"
+        assert rel_err(res[mode][2], res[0][2]) < 1e-4
+        for name, ga, gb in zip(PARAMS, res[0][3], res[mode][3]):
+            assert torch.isfinite(gb).all(), name
+            assert rel_err(gb, ga) < 1e-4, (mode, name)
 
 
 # ---- SURVEY 8(f)-2: fused Adam ---------------------------------------------------------------------

@@ -441,15 +441,17 @@ int launch_blend_bwd_group(int CH, int gch, int H, int W, int tiles_x, int tiles
                            const float* v_out_img, const float* v_out_ch3, int split_ch3,
                            const float* v_out_alpha, float* grads, cudaStream_t st);
 
-// 0 = first generation (one warp per sub-block), 1 = grouped (blend_group.cu).  Initialised once
-// from TS_BLEND_MODE ("warp" | "group"); ts_set_blend_mode() overrides it (tests, A/B benches).
+// Bit 0: forward uses the grouped kernel (blend_group.cu); bit 1: backward does.  0 = first
+// generation for both (one warp per sub-block).  Initialised once from TS_BLEND_MODE ("warp" = 0,
+// "group" = 3, or a number 0..3); ts_set_blend_mode() overrides it (tests, A/B benches).
 constexpr int kDefaultBlendMode = TS_DEFAULT_BLEND_MODE;
 static int g_blend_mode = -1;
 static int blend_mode() {
     if (g_blend_mode < 0) {
         const char* e = getenv("TS_BLEND_MODE");
         if (e && !strcmp(e, "warp")) g_blend_mode = 0;
-        else if (e && !strcmp(e, "group")) g_blend_mode = 1;
+        else if (e && !strcmp(e, "group")) g_blend_mode = 3;
+        else if (e && e[0] >= '0' && e[0] <= '3' && !e[1]) g_blend_mode = e[0] - '0';
         else g_blend_mode = kDefaultBlendMode;
     }
     return g_blend_mode;
@@ -460,7 +462,7 @@ static int blend_mode() {
 extern "C" {
 
 int ts_set_blend_mode(int mode) {
-    if (mode < -1 || mode > 1) return TS_ERR_INVALID;
+    if (mode < -1 || mode > 3) return TS_ERR_INVALID;
     ts::g_blend_mode = mode;      // -1: back to TS_BLEND_MODE / the built-in default
     return TS_OK;
 }
@@ -475,7 +477,7 @@ int ts_blend_fwd(int CH, int img_height, int img_width, int tiles_x, int tiles_y
     if (recs && !ts::aligned16(recs)) return TS_ERR_ALIGN;
     dim3 grid(tiles_x, tiles_y);
     cudaStream_t st = (cudaStream_t)stream;
-    if (ts::blend_mode() == 1) {
+    if (ts::blend_mode() & 1) {
         ts::launch_blend_fwd_group(CH, img_height, img_width, tiles_x, tiles_y, tile_offsets, ids_sorted, recs,
                                    background, out_img, out_ch3, final_T, n_contrib, clamp_max1, st);
         TS_CHECK_LAUNCH("ts_blend_fwd/group");
@@ -509,7 +511,7 @@ int ts_blend_bwd(int N, int CH, int img_height, int img_width, int tiles_x, int 
     dim3 grid(tiles_x, tiles_y);
     // channels that carry a cotangent: the fused RGB+depth pass without a depth loss skips ch 3
     const int gch = (CH == 4 && split_ch3 && !v_out_ch3) ? 3 : CH;
-    if (ts::blend_mode() == 1) {
+    if (ts::blend_mode() & 2) {
         ts::launch_blend_bwd_group(CH, gch, img_height, img_width, tiles_x, tiles_y, tile_offsets, ids_sorted,
                                    recs, background, final_T, n_contrib, v_out_img, v_out_ch3, split_ch3,
                                    v_out_alpha, grads, st);

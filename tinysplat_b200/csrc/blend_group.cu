@@ -211,16 +211,17 @@ blend_fwd_group_kernel(int H, int W, int tbx, const int32_t* __restrict__ tile_o
     }
 }
 
-// Sums val[0..NV) over the 8 lanes of each group.  Values 0..7 go through a transpose-reduce
-// (xor 4, 2, 1: every level halves the values a lane carries), after which lane l8 holds the
-// group total of value l8; values 8.. are reduced plainly and returned in `extra` on every lane.
+// Sums val[0..NV) over the 8 lanes of each group.  Values 0..7 go through a transpose-reduce:
+// levels xor 4 and xor 2 halve the values a lane carries (8 -> 4 -> 2), level xor 1 is a plain
+// butterfly, so both lanes of a pair end with the group totals of values (l8 & 6) and (l8 & 6) + 1.
+// Values 8, 9 are reduced plainly and returned on every lane in `extra`.
 template <int NV>
-__device__ __forceinline__ float group_reduce(const float (&val)[NV], int l8, float (&extra)[2]) {
+__device__ __forceinline__ float2 group_reduce(const float (&val)[NV], int l8, float2& extra) {
     const unsigned full = 0xffffffffu;
     float v[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = (i < NV) ? val[i] : 0.f;
-    const bool h4 = (l8 & 4) != 0, h2 = (l8 & 2) != 0, h1 = (l8 & 1) != 0;
+    for (int i = 0; i < 8; ++i) v[i] = (i < NV) ? val[i < NV ? i : 0] : 0.f;
+    const bool h4 = (l8 & 4) != 0, h2 = (l8 & 2) != 0;
     float w[4], u[2];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -234,20 +235,36 @@ __device__ __forceinline__ float group_reduce(const float (&val)[NV], int l8, fl
         const float keep = h2 ? w[i + 2] : w[i];
         u[i] = keep + __shfl_xor_sync(full, send, 2);
     }
-    const float send = h1 ? u[0] : u[1];
-    const float keep = h1 ? u[1] : u[0];
-    const float mine = keep + __shfl_xor_sync(full, send, 1);
+    u[0] += __shfl_xor_sync(full, u[0], 1);
+    u[1] += __shfl_xor_sync(full, u[1], 1);
+    float e[2] = {0.f, 0.f};
 #pragma unroll
-    for (int e = 0; e < 2; ++e) {
-        float x = (8 + e < NV) ? val[(8 + e < NV) ? 8 + e : 0] : 0.f;
-        if (8 + e < NV) {
+    for (int k = 0; k < 2; ++k) {
+        if (8 + k < NV) {
+            float x = val[8 + k < NV ? 8 + k : 0];
             x += __shfl_xor_sync(full, x, 4);
             x += __shfl_xor_sync(full, x, 2);
             x += __shfl_xor_sync(full, x, 1);
+            e[k] = x;
         }
-        extra[e] = x;
     }
-    return mine;
+    extra = make_float2(e[0], e[1]);
+    return make_float2(u[0], u[1]);
+}
+
+// Adds (a, b) to the two consecutive floats at `addr` (8-byte aligned, shared memory) with one
+// 64-bit compare-and-swap loop (shared memory has no native fp32 add: a scalar atomicAdd is the
+// same loop per float).
+__device__ __forceinline__ void smem_add_pair(float* addr, float a, float b) {
+    unsigned long long* p = reinterpret_cast<unsigned long long*>(addr);
+    unsigned long long old = *p, assumed;
+    do {
+        assumed = old;
+        const float lo = __uint_as_float((unsigned)(assumed & 0xffffffffull)) + a;
+        const float hi = __uint_as_float((unsigned)(assumed >> 32)) + b;
+        const unsigned long long upd = ((unsigned long long)__float_as_uint(hi) << 32) | __float_as_uint(lo);
+        old = atomicCAS(p, assumed, upd);
+    } while (old != assumed);
 }
 
 // GCH = number of colour channels that carry a cotangent (GCH <= CH; the fused RGB+depth pass
@@ -273,7 +290,10 @@ blend_bwd_group_kernel(int H, int W, int tbx, const int32_t* __restrict__ tile_o
     const int start = __ldg(tile_offsets + tile);
 
     // per-pixel state of this lane's four rows
-    float T[4], wfin[4], v_out[4][GCH], buffer[4][GCH];
+    // W = T_final (v_alpha_out - bg.v) - sum_c buffer_c v_c: the colour accumulated BEHIND the
+    // current Gaussian only ever enters through its dot product with the pixel's (fixed)
+    // cotangent, so one scalar per pixel replaces the per-channel buffers.
+    float T[4], Wacc[4], v_out[4][GCH];
     int nc[4];
     int ncmax = 0;
 #pragma unroll
@@ -281,7 +301,7 @@ blend_bwd_group_kernel(int H, int W, int tbx, const int32_t* __restrict__ tile_o
         float T_final = 1.f, v_oa = 0.f;
         nc[r] = 0;
 #pragma unroll
-        for (int c = 0; c < GCH; ++c) { v_out[r][c] = 0.f; buffer[r][c] = 0.f; }
+        for (int c = 0; c < GCH; ++c) v_out[r][c] = 0.f;
         if ((gm.inside >> r) & 1u) {
             const size_t pix = (size_t)(gm.i0 + r) * W + gm.j;
             T_final = __ldg(final_T + pix);
@@ -302,7 +322,7 @@ blend_bwd_group_kernel(int H, int W, int tbx, const int32_t* __restrict__ tile_o
         float bgdot = 0.f;
 #pragma unroll
         for (int c = 0; c < GCH; ++c) bgdot = fmaf(__ldg(background + c), v_out[r][c], bgdot);
-        wfin[r] = T_final * (v_oa - bgdot);
+        Wacc[r] = T_final * (v_oa - bgdot);
         T[r] = T_final;
         ncmax = max(ncmax, nc[r]);
     }
@@ -342,8 +362,8 @@ blend_bwd_group_kernel(int H, int W, int tbx, const int32_t* __restrict__ tile_o
     if (nb > 0) prefetch(0);
     cp_async_commit();
 
-    // value index -> float offset inside the packed gradient record (colours start at float 8)
-    const int my_off = gm.l8 < 6 ? gm.l8 : gm.l8 + 2;
+    // value pair (l8 & 6) -> float offset inside the packed gradient record (colours start at 8)
+    const int pair_off = (gm.l8 & 6) < 6 ? (gm.l8 & 6) : 8;
 
     for (int b = 0; b < nb; ++b) {
         const float4* rec = s_rec[b & 1];
@@ -399,13 +419,13 @@ blend_bwd_group_kernel(int H, int W, int tbx, const int32_t* __restrict__ tile_o
                     const float ra = rcp_approx(1.f - alpha);          // 1 when !ok
                     T[r] = ok[r] ? T[r] * ra : T[r];
                     const float fac = alpha * T[r];                    // 0 when !ok
-                    float v_alpha = wfin[r] * ra;
+                    float cv = col[0] * v_out[r][0];
 #pragma unroll
-                    for (int ch = 0; ch < GCH; ++ch) {
-                        val[6 + ch] = fmaf(fac, v_out[r][ch], val[6 + ch]);
-                        v_alpha = fmaf(col[ch] * T[r] - buffer[r][ch] * ra, v_out[r][ch], v_alpha);
-                        buffer[r][ch] = fmaf(col[ch], fac, buffer[r][ch]);
-                    }
+                    for (int ch = 1; ch < GCH; ++ch) cv = fmaf(col[ch], v_out[r][ch], cv);
+#pragma unroll
+                    for (int ch = 0; ch < GCH; ++ch) val[6 + ch] = fmaf(fac, v_out[r][ch], val[6 + ch]);
+                    const float v_alpha = fmaf(cv, T[r], Wacc[r] * ra);
+                    Wacc[r] = fmaf(-cv, fac, Wacc[r]);
                     // !ok: no contribution;  clamped alpha: d alpha / d araw = 0
                     const float v_sig = (ok[r] && !(araw[r] > kAlphaMax)) ? -araw[r] * v_alpha : 0.f;
                     s0 += v_sig;
@@ -417,17 +437,17 @@ blend_bwd_group_kernel(int H, int W, int tbx, const int32_t* __restrict__ tile_o
                 val[2] = val[0] * dxc;
                 val[3] = s1 * dxc;
                 val[4] = s2;
-                val[5] = -s0 * rcp_approx(q1.w);
+                val[5] = any ? -s0 * rcp_approx(q1.w) : 0.f;   // any => opacity >= 1/255
             }
             if (!__any_sync(full, any)) continue;
-            float extra[2];
-            const float mine = group_reduce<NV>(val, gm.l8, extra);
-            if (act) {
-                float* a = s_acc + c * kGradFloats;
-                if (gm.l8 < NV && mine != 0.f) atomicAdd(a + my_off, mine);
-                if (NV > 8 && gm.l8 == 0 && extra[0] != 0.f) atomicAdd(a + 10, extra[0]);
-                if (NV > 9 && gm.l8 == 1 && extra[1] != 0.f) atomicAdd(a + 11, extra[1]);
-            }
+            float2 extra;
+            const float2 mine = group_reduce<NV>(val, gm.l8, extra);
+            // even lanes own the value pairs (0,1) (2,3) (4,5) (6,7) -> record floats 0,2,4,8;
+            // lane 1 owns values (8,9) -> floats 10,11
+            const bool second = (NV > 8) && gm.l8 == 1;
+            const float2 add = second ? extra : mine;
+            if (act && (second || !(gm.l8 & 1)) && (add.x != 0.f || add.y != 0.f))
+                smem_add_pair(s_acc + c * kGradFloats + (second ? 10 : pair_off), add.x, add.y);
         }
         __syncthreads();  // all groups finished batch b: s_acc complete
 #pragma unroll
