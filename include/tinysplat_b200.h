@@ -198,8 +198,9 @@ TS_API int ts_blend_unpack_grads(int N, int CH, const int32_t* radii, const floa
  * semantics (same skip decisions, bit-identical images / final_T / n_contrib): first generation
  * = one warp per 8x4 sub-block, bounding-box culling (blend.cu); grouped = one 8-lane group per
  * sub-block, four rows per lane, exact per-row culling (blend_group.cu).  mode is a bit mask:
- * bit 0 = forward grouped, bit 1 = backward grouped (0..3).  The default comes from the
- * environment variable TS_BLEND_MODE ("warp" = 0 | "group" = 3 | "0".."3") or the built-in
+ * bit 0 = forward grouped, bit 1 = backward grouped with shared-memory accumulators, bit 2 =
+ * backward grouped with direct global reds (0..7).  The default comes from the
+ * environment variable TS_BLEND_MODE ("warp" = 0 | "group" = 3 | "0".."7") or the built-in
  * default; ts_set_blend_mode(-1) returns to it.  Process-wide, not thread-safe against
  * concurrent launches. */
 TS_API int ts_set_blend_mode(int mode);

@@ -13,12 +13,12 @@ int run_fwd(int H, int W, int tx, int ty, const int32_t* off, const int32_t* ids
                                        n_contrib, clamp);
     });
 }
-template <int CH, int GCH>
+template <int CH, int GCH, bool DIRECT>
 int run_bwd(int H, int W, int tx, int ty, const int32_t* off, const int32_t* ids, const float* recs,
             const float* bg, const float* final_T, const int32_t* n_contrib, const float* v_img,
             const float* v_ch3, int split, const float* v_alpha, float* grads) {
     return ts_emu::launch(dim3(tx, ty), ts::kGThreads, [=]() {
-        ts::blend_bwd_group_kernel<CH, GCH>(H, W, tx, off, ids, (const float4*)recs, bg, final_T, n_contrib,
+        ts::blend_bwd_group_kernel<CH, GCH, DIRECT>(H, W, tx, off, ids, (const float4*)recs, bg, final_T, n_contrib,
                                             v_img, v_ch3, split, v_alpha, (float4*)grads);
     });
 }
@@ -39,15 +39,17 @@ int emu_blend_fwd(int CH, int H, int W, int tx, int ty, const int32_t* off, cons
 
 int emu_blend_bwd(int N, int CH, int H, int W, int tx, int ty, const int32_t* off, const int32_t* ids,
                   const float* recs, const float* bg, const float* final_T, const int32_t* n_contrib,
-                  const float* v_img, const float* v_ch3, int split, const float* v_alpha, float* grads) {
+                  const float* v_img, const float* v_ch3, int split, const float* v_alpha, float* grads, int direct) {
     memset(grads, 0, sizeof(float) * ts::kGradFloats * (size_t)N);
     const int gch = (CH == 4 && split && !v_ch3) ? 3 : CH;
 #define ARGS H, W, tx, ty, off, ids, recs, bg, final_T, n_contrib, v_img, v_ch3, split, v_alpha, grads
     switch (CH) {
-        case 1: return run_bwd<1, 1>(ARGS);
-        case 2: return run_bwd<2, 2>(ARGS);
-        case 3: return run_bwd<3, 3>(ARGS);
-        default: return gch == 3 ? run_bwd<4, 3>(ARGS) : run_bwd<4, 4>(ARGS);
+        case 1: return direct ? run_bwd<1, 1, true>(ARGS) : run_bwd<1, 1, false>(ARGS);
+        case 2: return direct ? run_bwd<2, 2, true>(ARGS) : run_bwd<2, 2, false>(ARGS);
+        case 3: return direct ? run_bwd<3, 3, true>(ARGS) : run_bwd<3, 3, false>(ARGS);
+        default:
+            if (gch == 3) return direct ? run_bwd<4, 3, true>(ARGS) : run_bwd<4, 3, false>(ARGS);
+            return direct ? run_bwd<4, 4, true>(ARGS) : run_bwd<4, 4, false>(ARGS);
     }
 #undef ARGS
 }

@@ -34,7 +34,7 @@ def emu():
     lib = C.CDLL(LIB)
     p, i = C.c_void_p, C.c_int
     lib.emu_blend_fwd.argtypes = [i, i, i, i, i, p, p, p, p, p, p, p, p, i]
-    lib.emu_blend_bwd.argtypes = [i, i, i, i, i, i, p, p, p, p, p, p, p, p, i, p, p]
+    lib.emu_blend_bwd.argtypes = [i, i, i, i, i, i, p, p, p, p, p, p, p, p, i, p, p, i]
     return lib
 
 
@@ -144,16 +144,17 @@ def test_grouped_blend_kernels_match_the_oracle_on_the_emulator(emu, n, W, H, ra
     v_img = torch.rand(H, W, ch, generator=g)
     v_alpha = torch.rand(H, W, generator=g)
     (img * v_img).sum().add((alpha * v_alpha).sum()).backward()
-    grads = np.zeros((n, 12), dtype=np.float32)
     vi = np.ascontiguousarray(v_img.numpy())
     va = np.ascontiguousarray(v_alpha.numpy())
-    assert emu.emu_blend_bwd(n, ch, H, W, tb[0], tb[1], _ptr(offsets), _ptr(ids), _ptr(rec), _ptr(bgn),
-                             _ptr(final_T), _ptr(ncon), _ptr(vi), None, 0, _ptr(va), _ptr(grads)) == 0
-    v_xys, v_conics, v_colors, v_opac = _unpack(grads, conics, ch)
-    assert _rel(v_xys, x.grad.double()) < 1e-4
-    assert _rel(v_conics, cn.grad.double()) < 1e-4
-    assert _rel(v_colors, co.grad.double()) < 1e-4
-    assert _rel(v_opac, o.grad.reshape(-1).double()) < 1e-4
+    for direct in (0, 1):     # shared-memory accumulators / direct global reds
+        grads = np.zeros((n, 12), dtype=np.float32)
+        assert emu.emu_blend_bwd(n, ch, H, W, tb[0], tb[1], _ptr(offsets), _ptr(ids), _ptr(rec), _ptr(bgn),
+                                 _ptr(final_T), _ptr(ncon), _ptr(vi), None, 0, _ptr(va), _ptr(grads), direct) == 0
+        v_xys, v_conics, v_colors, v_opac = _unpack(grads, conics, ch)
+        assert _rel(v_xys, x.grad.double()) < 1e-4
+        assert _rel(v_conics, cn.grad.double()) < 1e-4
+        assert _rel(v_colors, co.grad.double()) < 1e-4
+        assert _rel(v_opac, o.grad.reshape(-1).double()) < 1e-4
 
 
 def test_grouped_split_rgb_depth_pass_with_clamp_on_the_emulator(emu):
@@ -176,7 +177,7 @@ def test_grouped_split_rgb_depth_pass_with_clamp_on_the_emulator(emu):
     g = torch.Generator().manual_seed(2)
     v_img = torch.rand(H, W, 3, generator=g)
     v_dep = torch.rand(H, W, generator=g)
-    for with_depth in (False, True):
+    for with_depth, direct in ((False, 0), (True, 0), (False, 1), (True, 1)):
         x = xys.clone().requires_grad_(True)
         cn = conics.clone().requires_grad_(True)
         co = colors.clone().requires_grad_(True)
@@ -194,7 +195,7 @@ def test_grouped_split_rgb_depth_pass_with_clamp_on_the_emulator(emu):
         vi = np.ascontiguousarray(v_img.numpy())
         vd = np.ascontiguousarray(v_dep.numpy()) if with_depth else None
         assert emu.emu_blend_bwd(n, 4, H, W, tb[0], tb[1], _ptr(offsets), _ptr(ids), _ptr(rec), _ptr(bgn),
-                                 _ptr(final_T), _ptr(ncon), _ptr(vi), _ptr(vd), 1, None, _ptr(grads)) == 0
+                                 _ptr(final_T), _ptr(ncon), _ptr(vi), _ptr(vd), 1, None, _ptr(grads), direct) == 0
         v_xys, v_conics, v_colors, v_opac = _unpack(grads, conics, 4)
         assert _rel(v_xys, x.grad.double()) < 1e-4
         assert _rel(v_conics, cn.grad.double()) < 1e-4
@@ -230,10 +231,11 @@ def test_grouped_backward_zero_opacity_without_culling_stays_finite(emu):
     bgn = np.ascontiguousarray(bg.numpy())
     assert emu.emu_blend_fwd(ch, H, W, tb[0], tb[1], _ptr(offsets), _ptr(ids), _ptr(rec), _ptr(bgn), _ptr(out),
                              None, _ptr(final_T), _ptr(ncon), 0) == 0
-    grads = np.zeros((n, 12), dtype=np.float32)
     vi = np.ones((H, W, ch), dtype=np.float32)
-    assert emu.emu_blend_bwd(n, ch, H, W, tb[0], tb[1], _ptr(offsets), _ptr(ids), _ptr(rec), _ptr(bgn),
-                             _ptr(final_T), _ptr(ncon), _ptr(vi), None, 0, None, _ptr(grads)) == 0
-    assert np.isfinite(grads).all()
-    assert np.abs(grads[::3]).max() == 0.0
-    assert np.abs(grads).max() > 0.0
+    for direct in (0, 1):
+        grads = np.zeros((n, 12), dtype=np.float32)
+        assert emu.emu_blend_bwd(n, ch, H, W, tb[0], tb[1], _ptr(offsets), _ptr(ids), _ptr(rec), _ptr(bgn),
+                                 _ptr(final_T), _ptr(ncon), _ptr(vi), None, 0, None, _ptr(grads), direct) == 0
+        assert np.isfinite(grads).all()
+        assert np.abs(grads[::3]).max() == 0.0
+        assert np.abs(grads).max() > 0.0
