@@ -199,8 +199,9 @@ TS_API int ts_blend_unpack_grads(int N, int CH, const int32_t* radii, const floa
  * = one warp per 8x4 sub-block, bounding-box culling (blend.cu); grouped = one 8-lane group per
  * sub-block, four rows per lane, exact per-row culling (blend_group.cu).  mode is a bit mask:
  * bit 0 = forward grouped, bit 1 = backward grouped with shared-memory accumulators, bit 2 =
- * backward grouped with direct global reds (0..7).  The default comes from the
- * environment variable TS_BLEND_MODE ("warp" = 0 | "group" = 3 | "0".."7") or the built-in
+ * backward grouped with direct global reds, bit 3 = backward with one warp per half tile
+ * (direct reds); 0..15, the highest backward bit wins.  The default comes from the
+ * environment variable TS_BLEND_MODE ("warp" = 0 | "group" = 3 | "0".."15") or the built-in
  * default; ts_set_blend_mode(-1) returns to it.  Process-wide, not thread-safe against
  * concurrent launches. */
 TS_API int ts_set_blend_mode(int mode);
@@ -211,6 +212,9 @@ TS_API int ts_get_blend_mode(void);
  * 8*half..8*half+7, may reach alpha >= 1/255.  Must be a superset of the pixels the blend loop
  * accepts (tests/test_capi.py brute-forces it). */
 TS_API uint32_t ts_debug_rowmask(const float* q0_host, const float* q1_host, int tile_x, int tile_y);
+/* Same, restricted to the 8 rows of the upper (half = 0) or lower (half = 1) half of the tile. */
+TS_API uint32_t ts_debug_rowmask_half(const float* q0_host, const float* q1_host, int tile_x, int tile_y,
+                                      int half);
 
 /* ---- fused multi-tensor Adam step ---------------------------------------
  * One launch updates up to ts_adam_max_tensors() parameter tensors in place, with the exact

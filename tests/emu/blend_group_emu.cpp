@@ -22,6 +22,15 @@ int run_bwd(int H, int W, int tx, int ty, const int32_t* off, const int32_t* ids
                                             v_img, v_ch3, split, v_alpha, (float4*)grads);
     });
 }
+template <int CH, int GCH>
+int run_half(int H, int W, int tx, int ty, const int32_t* off, const int32_t* ids, const float* recs,
+             const float* bg, const float* final_T, const int32_t* n_contrib, const float* v_img,
+             const float* v_ch3, int split, const float* v_alpha, float* grads) {
+    return ts_emu::launch(dim3(tx, 2 * ty), 32, [=]() {
+        ts::blend_bwd_half_kernel<CH, GCH>(H, W, tx, off, ids, (const float4*)recs, bg, final_T, n_contrib,
+                                           v_img, v_ch3, split, v_alpha, (float4*)grads);
+    });
+}
 }  // namespace
 
 extern "C" {
@@ -43,6 +52,14 @@ int emu_blend_bwd(int N, int CH, int H, int W, int tx, int ty, const int32_t* of
     memset(grads, 0, sizeof(float) * ts::kGradFloats * (size_t)N);
     const int gch = (CH == 4 && split && !v_ch3) ? 3 : CH;
 #define ARGS H, W, tx, ty, off, ids, recs, bg, final_T, n_contrib, v_img, v_ch3, split, v_alpha, grads
+    if (direct == 2) {
+        switch (CH) {
+            case 1: return run_half<1, 1>(ARGS);
+            case 2: return run_half<2, 2>(ARGS);
+            case 3: return run_half<3, 3>(ARGS);
+            default: return gch == 3 ? run_half<4, 3>(ARGS) : run_half<4, 4>(ARGS);
+        }
+    }
     switch (CH) {
         case 1: return direct ? run_bwd<1, 1, true>(ARGS) : run_bwd<1, 1, false>(ARGS);
         case 2: return direct ? run_bwd<2, 2, true>(ARGS) : run_bwd<2, 2, false>(ARGS);

@@ -194,6 +194,20 @@ static inline int __shfl_xor_sync(unsigned mask, int x, int d) {
     const uint32_t* v = ts_emu::warp_exchange((uint32_t)x);
     return (int)v[(ts_emu::st().cur & 31) ^ d];
 }
+template <typename T>
+static inline T emu_shfl_idx(T x, int src) {
+    static_assert(sizeof(T) == 4, "32-bit shuffles only");
+    uint32_t u;
+    memcpy(&u, &x, 4);
+    const uint32_t* v = ts_emu::warp_exchange(u);
+    uint32_t r = v[src & 31];
+    T out;
+    memcpy(&out, &r, 4);
+    return out;
+}
+static inline float __shfl_sync(unsigned mask, float x, int src) { emu_require_full(mask); return emu_shfl_idx(x, src); }
+static inline int __shfl_sync(unsigned mask, int x, int src) { emu_require_full(mask); return emu_shfl_idx(x, src); }
+static inline unsigned __shfl_sync(unsigned mask, unsigned x, int src) { emu_require_full(mask); return emu_shfl_idx(x, src); }
 static inline int __ffs(unsigned x) { return __builtin_ffs((int)x); }
 template <typename T>
 static inline T __ldg(const T* p) { return *p; }

@@ -146,7 +146,7 @@ def test_grouped_blend_kernels_match_the_oracle_on_the_emulator(emu, n, W, H, ra
     (img * v_img).sum().add((alpha * v_alpha).sum()).backward()
     vi = np.ascontiguousarray(v_img.numpy())
     va = np.ascontiguousarray(v_alpha.numpy())
-    for direct in (0, 1):     # shared-memory accumulators / direct global reds
+    for direct in (0, 1, 2):  # shared-memory accumulators / direct global reds / one warp per half tile
         grads = np.zeros((n, 12), dtype=np.float32)
         assert emu.emu_blend_bwd(n, ch, H, W, tb[0], tb[1], _ptr(offsets), _ptr(ids), _ptr(rec), _ptr(bgn),
                                  _ptr(final_T), _ptr(ncon), _ptr(vi), None, 0, _ptr(va), _ptr(grads), direct) == 0
@@ -177,7 +177,7 @@ def test_grouped_split_rgb_depth_pass_with_clamp_on_the_emulator(emu):
     g = torch.Generator().manual_seed(2)
     v_img = torch.rand(H, W, 3, generator=g)
     v_dep = torch.rand(H, W, generator=g)
-    for with_depth, direct in ((False, 0), (True, 0), (False, 1), (True, 1)):
+    for with_depth, direct in ((False, 0), (True, 0), (False, 1), (True, 1), (False, 2), (True, 2)):
         x = xys.clone().requires_grad_(True)
         cn = conics.clone().requires_grad_(True)
         co = colors.clone().requires_grad_(True)
@@ -232,7 +232,7 @@ def test_grouped_backward_zero_opacity_without_culling_stays_finite(emu):
     assert emu.emu_blend_fwd(ch, H, W, tb[0], tb[1], _ptr(offsets), _ptr(ids), _ptr(rec), _ptr(bgn), _ptr(out),
                              None, _ptr(final_T), _ptr(ncon), 0) == 0
     vi = np.ones((H, W, ch), dtype=np.float32)
-    for direct in (0, 1):
+    for direct in (0, 1, 2):
         grads = np.zeros((n, 12), dtype=np.float32)
         assert emu.emu_blend_bwd(n, ch, H, W, tb[0], tb[1], _ptr(offsets), _ptr(ids), _ptr(rec), _ptr(bgn),
                                  _ptr(final_T), _ptr(ncon), _ptr(vi), None, 0, None, _ptr(grads), direct) == 0

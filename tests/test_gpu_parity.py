@@ -35,11 +35,12 @@ def _need_cuda(lib):
         pytest.skip("no CUDA device")
 
 
-@pytest.fixture(params=[0, 3, 4], ids=["blend-warp", "blend-group", "blend-bwd-direct"])
+@pytest.fixture(params=[0, 3, 4, 8], ids=["blend-warp", "blend-group", "blend-bwd-direct", "blend-bwd-half"])
 def blend_mode(request, lib):
     """Runs a test once per generation of blend kernels (include/tinysplat_b200.h,
     ts_set_blend_mode): 0 = one warp per sub-block, 3 = grouped forward + backward (shared-memory
-    accumulators), 4 = first-generation forward + grouped backward with direct global reds."""
+    accumulators), 4 = first-generation forward + grouped backward with direct global reds,
+    8 = first-generation forward + one-warp-per-half-tile backward."""
     assert lib.ts_set_blend_mode(request.param) == 0
     yield request.param
     lib.ts_set_blend_mode(-1)
@@ -481,7 +482,7 @@ def test_blend_generations_agree_at_full_size(lib):
     wd = torch.rand(H, W, generator=g).to(DEV)
     res = {}
     try:
-        for mode in (0, 3, 1, 2, 4):
+        for mode in (0, 3, 1, 2, 4, 8):
             assert lib.ts_set_blend_mode(mode) == 0
             model = ParamModel(sc, DEV, 3)
             img, ex = GaussianRasterizer(model, None, DEV, "fused")(cam, (W, H), 3)
@@ -489,7 +490,7 @@ def test_blend_generations_agree_at_full_size(lib):
             res[mode] = (img, ex["depth"], ex["xys"].grad, [p.grad for p in model.parameters()])
     finally:
         lib.ts_set_blend_mode(-1)
-    for mode in (3, 1, 2, 4):
+    for mode in (3, 1, 2, 4, 8):
         assert torch.equal(res[0][0], res[mode][0]), f"image differs in mode {mode}"
         assert torch.equal(res[0][1], res[mode][1]), f"depth differs in mode {mode}"
         assert rel_err(res[mode][2], res[0][2]) < 1e-4

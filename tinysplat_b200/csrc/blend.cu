@@ -442,9 +442,10 @@ int launch_blend_bwd_group(int CH, int gch, int direct, int H, int W, int tiles_
                            const float* v_out_alpha, float* grads, cudaStream_t st);
 
 // Bit 0: forward uses the grouped kernel (blend_group.cu); bit 1: backward does (shared-memory
-// accumulators); bit 2: backward uses the grouped kernel with direct global reds.  0 = first
-// generation for both (one warp per sub-block).  Initialised once from TS_BLEND_MODE ("warp" = 0,
-// "group" = 3, or a number 0..7); ts_set_blend_mode() overrides it (tests, A/B benches).
+// accumulators); bit 2: backward uses the grouped kernel with direct global reds; bit 3: backward
+// uses the one-warp-per-half-tile kernel (direct reds).  0 = first generation for both (one warp
+// per sub-block).  Initialised once from TS_BLEND_MODE ("warp" = 0, "group" = 3, or a number
+// 0..15); ts_set_blend_mode() overrides it (tests, A/B benches).
 constexpr int kDefaultBlendMode = TS_DEFAULT_BLEND_MODE;
 static int g_blend_mode = -1;
 static int blend_mode() {
@@ -452,7 +453,7 @@ static int blend_mode() {
         const char* e = getenv("TS_BLEND_MODE");
         if (e && !strcmp(e, "warp")) g_blend_mode = 0;
         else if (e && !strcmp(e, "group")) g_blend_mode = 3;
-        else if (e && e[0] >= '0' && e[0] <= '7' && !e[1]) g_blend_mode = e[0] - '0';
+        else if (e && e[0] >= '0' && e[0] <= '9') g_blend_mode = atoi(e) & 15;
         else g_blend_mode = kDefaultBlendMode;
     }
     return g_blend_mode;
@@ -463,7 +464,7 @@ static int blend_mode() {
 extern "C" {
 
 int ts_set_blend_mode(int mode) {
-    if (mode < -1 || mode > 7) return TS_ERR_INVALID;
+    if (mode < -1 || mode > 15) return TS_ERR_INVALID;
     ts::g_blend_mode = mode;      // -1: back to TS_BLEND_MODE / the built-in default
     return TS_OK;
 }
@@ -512,8 +513,9 @@ int ts_blend_bwd(int N, int CH, int img_height, int img_width, int tiles_x, int 
     dim3 grid(tiles_x, tiles_y);
     // channels that carry a cotangent: the fused RGB+depth pass without a depth loss skips ch 3
     const int gch = (CH == 4 && split_ch3 && !v_out_ch3) ? 3 : CH;
-    if (ts::blend_mode() & 6) {
-        ts::launch_blend_bwd_group(CH, gch, (ts::blend_mode() & 4) != 0, img_height, img_width, tiles_x, tiles_y, tile_offsets, ids_sorted,
+    if (ts::blend_mode() & 14) {
+        const int variant = (ts::blend_mode() & 8) ? 2 : (ts::blend_mode() & 4) ? 1 : 0;
+        ts::launch_blend_bwd_group(CH, gch, variant, img_height, img_width, tiles_x, tiles_y, tile_offsets, ids_sorted,
                                    recs, background, final_T, n_contrib, v_out_img, v_out_ch3, split_ch3,
                                    v_out_alpha, grads, st);
         TS_CHECK_LAUNCH("ts_blend_bwd/group");

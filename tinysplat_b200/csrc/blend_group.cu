@@ -535,6 +535,194 @@ blend_bwd_group_kernel(int H, int W, int tbx, const int32_t* __restrict__ tile_o
     cp_async_wait<0>();
 }
 
+// ---- backward, third arrangement: ONE WARP PER HALF TILE ---------------------------------------
+// Same 8-lane groups and per-lane four-row state as blend_bwd_group_kernel<.., DIRECT = true>, but
+// a CTA is a single warp that owns the upper or lower 16x8 half of a tile (four sub-blocks):
+//   * twice as many, half as long CTAs: the tail of the grid (SMs idling while the last tiles
+//     finish) halves, and a deep tile no longer couples two warps through barriers;
+//   * no __syncthreads at all (only __syncwarp), no shared-memory masks: the batch is 32
+//     candidates, one per lane; a group's candidate word is a ballot it keeps in a register, and
+//     the row mask / Gaussian id of candidate c are fetched from lane c with a shuffle;
+//   * each half evaluates only its own 8 rows of the exact row mask.
+// The tile's list is staged by both halves (2 x 48 B per pair, L2-resident records).
+constexpr int kHBatch = 32;
+#ifndef TS_HALF_MIN_CTAS
+#define TS_HALF_MIN_CTAS 32      // 32 one-warp CTAs per SM -> at most 64 registers per thread
+#endif
+
+template <int CH, int GCH>
+__global__ void __launch_bounds__(32, TS_HALF_MIN_CTAS)
+blend_bwd_half_kernel(int H, int W, int tbx, const int32_t* __restrict__ tile_offsets,
+                      const int32_t* __restrict__ ids, const float4* __restrict__ recs,
+                      const float* __restrict__ background, const float* __restrict__ final_T,
+                      const int32_t* __restrict__ n_contrib, const float* __restrict__ v_out_img,
+                      const float* __restrict__ v_out_ch3, int split_ch3,
+                      const float* __restrict__ v_out_alpha, float4* __restrict__ grads) {
+    constexpr int NV = 6 + GCH;
+    __shared__ __align__(16) float4 s_rec[2][kHBatch * 3];
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x;
+    const int grp = lane >> 3, l8 = lane & 7;
+    const int tile_y = blockIdx.y >> 1, half = blockIdx.y & 1;
+    const int wx = grp & 1, wy = 2 * half + (grp >> 1);          // sub-block (wx, wy) of the tile
+    const int shift = 8 * wy + wx;                               // rowmask bit of (row 4wy + r, half wx) = shift + 2r
+    const int j = blockIdx.x * kBlock + wx * 8 + l8;
+    const int i0 = tile_y * kBlock + wy * 4;
+    const float px = (float)j + kPixCenter, py0 = (float)i0 + kPixCenter;
+    const float X0 = (float)(blockIdx.x * kBlock) + kPixCenter, Y0 = (float)(tile_y * kBlock) + kPixCenter;
+    const unsigned gbits = 0xffu << (lane & 24);
+    const unsigned gsel = 0x55u << shift;                        // my group's four row bits
+    const int tile = tile_y * tbx + blockIdx.x;
+    const int start = __ldg(tile_offsets + tile);
+
+    float T[4], Wacc[4], v_out[4][GCH];
+    int nc[4];
+    int nmax = 0;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        float T_final = 1.f, v_oa = 0.f;
+        nc[r] = 0;
+#pragma unroll
+        for (int c = 0; c < GCH; ++c) v_out[r][c] = 0.f;
+        if (j < W && i0 + r < H) {
+            const size_t pix = (size_t)(i0 + r) * W + j;
+            T_final = __ldg(final_T + pix);
+            int n = __ldg(n_contrib + pix);
+            const unsigned cm = (unsigned)n >> kClampShift;    // channels clamped by forward
+            nc[r] = n & kCountMask;
+            if (CH == 4 && split_ch3) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    v_out[r][c] = (v_out_img && !((cm >> c) & 1u)) ? __ldg(v_out_img + pix * 3 + c) : 0.f;
+                if (GCH == 4) v_out[r][GCH - 1] = v_out_ch3 ? __ldg(v_out_ch3 + pix) : 0.f;
+            } else {
+#pragma unroll
+                for (int c = 0; c < GCH; ++c) v_out[r][c] = __ldg(v_out_img + pix * CH + c);
+            }
+            if (v_out_alpha) v_oa = __ldg(v_out_alpha + pix);
+        }
+        float bgdot = 0.f;
+#pragma unroll
+        for (int c = 0; c < GCH; ++c) bgdot = fmaf(__ldg(background + c), v_out[r][c], bgdot);
+        Wacc[r] = T_final * (v_oa - bgdot);
+        T[r] = T_final;
+        nmax = max(nmax, nc[r]);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) nmax = max(nmax, __shfl_xor_sync(full, nmax, d));
+    // entries [0, nmax) of the tile list contributed somewhere in this half tile
+    const int nb = (nmax + kHBatch - 1) / kHBatch;
+
+    // batch b, lane t  <->  list position  p = nmax-1 - (b*32 + t)   (back to front)
+    int gnext = -1;
+    auto prefetch = [&](int b) {
+        const int p = nmax - 1 - (b * kHBatch + lane);
+        gnext = -1;
+        if (p >= 0) {
+            const int g = __ldg(ids + start + p);
+            gnext = g;
+            const float4* src = recs + 3 * (size_t)g;
+            float4* dst = &s_rec[b & 1][lane * 3];
+            cp_async16(dst, src);
+            cp_async16(dst + 1, src + 1);
+            cp_async16(dst + 2, src + 2);
+        }
+    };
+    if (nb > 0) prefetch(0);
+    cp_async_commit();
+
+    for (int b = 0; b < nb; ++b) {
+        const float4* rec = s_rec[b & 1];
+        const int gcur = gnext;
+        if (b + 1 < nb) prefetch(b + 1);
+        cp_async_commit();
+        cp_async_wait<1>();
+        unsigned rm_mine = 0u;
+        if (gcur >= 0) rm_mine = footprint_rowmask_rows<8>(rec[lane * 3], rec[lane * 3 + 1], X0, Y0, 8 * half);
+        __syncwarp(full);         // every lane's record of batch b is in shared memory
+        // candidate word of my group: which of the 32 staged records can reach my sub-block
+        unsigned m = 0u;
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            const unsigned sel = 0x55u << (16 * half + 8 * (s >> 1) + (s & 1));
+            const unsigned w = __ballot_sync(full, (rm_mine & sel) != 0u);
+            if (s == grp) m = w;
+        }
+        const int pbase = nmax - 1 - b * kHBatch;
+
+        for (;;) {
+            const bool act = (m != 0u);
+            if (!__any_sync(full, act)) break;
+            const int c = act ? __ffs(m) - 1 : 0;
+            m &= m - 1;
+            const unsigned rm = __shfl_sync(full, rm_mine, c) & gsel;
+            const int gid = __shfl_sync(full, gcur, c);
+            float val[NV];
+#pragma unroll
+            for (int v = 0; v < NV; ++v) val[v] = 0.f;
+            bool any = false;
+            if (act) {
+                const int p = pbase - c;
+                const float4 q0 = rec[c * 3];
+                const float4 q1 = rec[c * 3 + 1];
+                const float4 q2 = rec[c * 3 + 2];
+                const float col[4] = {q2.x, q2.y, q2.z, q2.w};
+                float s0 = 0.f, s1 = 0.f, s2 = 0.f, dxc = 0.f;
+                float vis[4], araw[4], dyr[4];
+                bool ok[4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const float pw = eval_power(q0, q1, px, py0 + (float)r, dxc, dyr[r]);
+                    vis[r] = ex2_approx(-fmaxf(pw, 0.f));
+                    araw[r] = __fmul_rn(q1.w, vis[r]);
+                    ok[r] = ((rm >> (shift + 2 * r)) & 1u) != 0u && p < nc[r] && pw >= 0.f &&
+                            fminf(kAlphaMax, araw[r]) >= kAlphaMin;
+                    any = any || ok[r];
+                }
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const float alpha = ok[r] ? fminf(kAlphaMax, araw[r]) : 0.f;
+                    const float ra = rcp_approx(1.f - alpha);          // 1 when !ok
+                    T[r] = ok[r] ? T[r] * ra : T[r];
+                    const float fac = alpha * T[r];                    // 0 when !ok
+                    float cv = col[0] * v_out[r][0];
+#pragma unroll
+                    for (int ch = 1; ch < GCH; ++ch) cv = fmaf(col[ch], v_out[r][ch], cv);
+#pragma unroll
+                    for (int ch = 0; ch < GCH; ++ch) val[6 + ch] = fmaf(fac, v_out[r][ch], val[6 + ch]);
+                    const float v_alpha = fmaf(cv, T[r], Wacc[r] * ra);
+                    Wacc[r] = fmaf(-cv, fac, Wacc[r]);
+                    const float v_sig = (ok[r] && !(araw[r] > kAlphaMax)) ? -araw[r] * v_alpha : 0.f;
+                    s0 += v_sig;
+                    s1 = fmaf(v_sig, dyr[r], s1);
+                    s2 = fmaf(v_sig * dyr[r], dyr[r], s2);
+                }
+                val[0] = s0 * dxc;
+                val[1] = s1;
+                val[2] = val[0] * dxc;
+                val[3] = s1 * dxc;
+                val[4] = s2;
+                val[5] = any ? -s0 * rcp_approx(q1.w) : 0.f;   // any => opacity >= 1/255
+            }
+            const unsigned anyb = __ballot_sync(full, any);
+            if (anyb == 0u) continue;
+            float2 extra;
+            const float4 q = group_reduce_quad<NV>(val, l8, extra);
+            if (act && (anyb & gbits) != 0u && (l8 & 3) == 0) {
+                float4* dst = grads + 3 * (size_t)gid;
+                if (l8 == 0) {
+                    atomicAdd(dst, q);
+                } else {
+                    atomicAdd(reinterpret_cast<float2*>(dst + 1), make_float2(q.x, q.y));
+                    atomicAdd(dst + 2, make_float4(q.z, q.w, extra.x, extra.y));
+                }
+            }
+        }
+        __syncwarp(full);   // all lanes are done with s_rec[b & 1] before batch b+2 overwrites it
+    }
+    cp_async_wait<0>();
+}
+
 #ifndef TS_HOST_EMU
 // ---- launchers (called from the C-ABI entry points in blend.cu) ------------------------------
 int launch_blend_fwd_group(int CH, int H, int W, int tiles_x, int tiles_y, const int32_t* tile_offsets,
@@ -564,7 +752,11 @@ int launch_blend_bwd_group(int CH, int gch, int direct, int H, int W, int tiles_
     blend_bwd_group_kernel<C, G, D><<<grid, kGThreads, 0, st>>>(                                   \
         H, W, tiles_x, tile_offsets, ids, (const float4*)recs, background, final_T, n_contrib,     \
         v_out_img, v_out_ch3, split_ch3, v_out_alpha, (float4*)grads)
-#define TS_LAUNCH_BWD(C, G) do { if (direct) TS_LAUNCH_BWD_(C, G, true); else TS_LAUNCH_BWD_(C, G, false); } while (0)
+#define TS_LAUNCH_HALF(C, G)                                                                      \
+    blend_bwd_half_kernel<C, G><<<dim3(tiles_x, 2 * tiles_y), 32, 0, st>>>(                        \
+        H, W, tiles_x, tile_offsets, ids, (const float4*)recs, background, final_T, n_contrib,     \
+        v_out_img, v_out_ch3, split_ch3, v_out_alpha, (float4*)grads)
+#define TS_LAUNCH_BWD(C, G) do { if (direct == 2) TS_LAUNCH_HALF(C, G); else if (direct) TS_LAUNCH_BWD_(C, G, true); else TS_LAUNCH_BWD_(C, G, false); } while (0)
     switch (CH) {
         case 1: TS_LAUNCH_BWD(1, 1); break;
         case 2: TS_LAUNCH_BWD(2, 2); break;
@@ -575,6 +767,7 @@ int launch_blend_bwd_group(int CH, int gch, int direct, int H, int W, int tiles_
     }
 #undef TS_LAUNCH_BWD
 #undef TS_LAUNCH_BWD_
+#undef TS_LAUNCH_HALF
     return 0;
 }
 #endif  // !TS_HOST_EMU
@@ -591,6 +784,14 @@ uint32_t ts_debug_rowmask(const float* q0, const float* q1, int tile_x, int tile
     const float4 b = make_float4(q1[0], q1[1], q1[2], q1[3]);
     return ts::footprint_rowmask(a, b, (float)(tile_x * ts::kBlock) + ts::kPixCenter,
                                  (float)(tile_y * ts::kBlock) + ts::kPixCenter);
+}
+
+
+uint32_t ts_debug_rowmask_half(const float* q0, const float* q1, int tile_x, int tile_y, int half) {
+    const float4 a = make_float4(q0[0], q0[1], q0[2], q0[3]);
+    const float4 b = make_float4(q1[0], q1[1], q1[2], q1[3]);
+    return ts::footprint_rowmask_rows<8>(a, b, (float)(tile_x * ts::kBlock) + ts::kPixCenter,
+                                         (float)(tile_y * ts::kBlock) + ts::kPixCenter, 8 * half);
 }
 
 }  // extern "C"
