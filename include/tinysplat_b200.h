@@ -194,27 +194,21 @@ TS_API int ts_blend_bwd(int N, int CH, int img_height, int img_width, int tiles_
 TS_API int ts_blend_unpack_grads(int N, int CH, const int32_t* radii, const float* conics,
                                  const float* grads /*[16B]*/, float* v_xys, float* v_conics,
                                  float* v_colors, float* v_opacity, ts_stream_t stream);
-/* Two generations of blend kernels sit behind ts_blend_fwd / ts_blend_bwd with identical
- * semantics (same skip decisions, bit-identical images / final_T / n_contrib): first generation
- * = one warp per 8x4 sub-block, bounding-box culling (blend.cu); grouped = one 8-lane group per
- * sub-block, four rows per lane, exact per-row culling (blend_group.cu).  mode is a bit mask:
- * bit 0 = forward grouped, bit 1 = backward grouped with shared-memory accumulators, bit 2 =
- * backward grouped with direct global reds, bit 3 = backward with one warp per half tile
- * (direct reds); 0..15, the highest backward bit wins.  The default comes from the
- * environment variable TS_BLEND_MODE ("warp" = 0 | "group" = 3 | "0".."15") or the built-in
- * default; ts_set_blend_mode(-1) returns to it.  Process-wide, not thread-safe against
- * concurrent launches. */
+/* Two backward kernels sit behind ts_blend_bwd with identical semantics: mode 1 (default) =
+ * grouped: one 8-lane group per 8x4 sub-block, four rows per lane, exact per-row culling, group
+ * totals sent to global memory as vector reds (blend_group.cu); mode 0 = first generation: one
+ * warp per sub-block, bounding-box culling, shared-memory group reduction (blend.cu).  The default
+ * comes from the environment variable TS_BLEND_MODE ("warp" | "group") or the built-in default;
+ * ts_set_blend_mode(-1) returns to it.  Process-wide, not thread-safe against concurrent
+ * launches. */
 TS_API int ts_set_blend_mode(int mode);
 TS_API int ts_get_blend_mode(void);
-/* Test hook (host code, no GPU): the exact row mask the mode-1 kernels compute for one packed
+/* Test hook (host code, no GPU): the exact row mask the grouped backward computes for one packed
  * record (q0 = {x, y, hx, hy}, q1 = {A, B, C, opacity}, see ts_rec_floats) against tile
  * (tile_x, tile_y): bit (2*row + half) set = some pixel of tile row `row`, columns
  * 8*half..8*half+7, may reach alpha >= 1/255.  Must be a superset of the pixels the blend loop
  * accepts (tests/test_capi.py brute-forces it). */
 TS_API uint32_t ts_debug_rowmask(const float* q0_host, const float* q1_host, int tile_x, int tile_y);
-/* Same, restricted to the 8 rows of the upper (half = 0) or lower (half = 1) half of the tile. */
-TS_API uint32_t ts_debug_rowmask_half(const float* q0_host, const float* q1_host, int tile_x, int tile_y,
-                                      int half);
 
 /* ---- fused multi-tensor Adam step ---------------------------------------
  * One launch updates up to ts_adam_max_tensors() parameter tensors in place, with the exact

@@ -1,9 +1,10 @@
-"""Kernel-logic parity WITHOUT a GPU: the grouped blend kernels (tinysplat_b200/csrc/blend_group.cu)
-are compiled as host code on the fiber SIMT emulator in tests/emu (threadIdx, __shared__, warp
-votes / shuffles, barriers, cp.async as memcpy) and compared with the oracle on small scenes.
-What this covers: staging, exact row masks, the per-group list walk, T-termination, n_contrib,
-the 8-lane transpose-reduce, the shared accumulators and the flush.  What it cannot cover (memory
-model, real async copies, occupancy) is left to the `-m gpu` tests."""
+"""Kernel-logic parity WITHOUT a GPU: the blend kernels (tinysplat_b200/csrc/blend.cu: forward and
+first-generation backward; blend_group.cu: grouped backward) are compiled as host code on the
+fiber SIMT emulator in tests/emu (threadIdx, __shared__, warp votes / shuffles, barriers, cp.async
+as memcpy) and compared with the oracle on small scenes.  What this covers: staging, sub-block /
+exact row masks, the list walks, T-termination, n_contrib, the shared-memory group reduction and
+the 8-lane transpose-reduce, the packed-gradient layout.  What it cannot cover (memory model,
+real async copies, occupancy) is left to the `-m gpu` tests."""
 import ctypes as C
 import os
 import subprocess
@@ -26,7 +27,7 @@ LOG2E = 1.4426950408889634
 @pytest.fixture(scope="module")
 def emu():
     srcs = [os.path.join(EMU, f) for f in ("blend_group_emu.cpp", "ts_emu.h")] + \
-           [os.path.join(CSRC, f) for f in ("blend_group.cu", "ts_blend_common.cuh", "ts_common.cuh")]
+           [os.path.join(CSRC, f) for f in ("blend.cu", "blend_group.cu", "ts_blend_common.cuh", "ts_common.cuh")]
     if not os.path.exists(LIB) or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in srcs):
         os.makedirs(os.path.dirname(LIB), exist_ok=True)
         subprocess.run(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-I" + EMU,
@@ -118,7 +119,7 @@ CASES = [
 
 
 @pytest.mark.parametrize("n,W,H,radius,ch,cull", CASES)
-def test_grouped_blend_kernels_match_the_oracle_on_the_emulator(emu, n, W, H, radius, ch, cull):
+def test_blend_kernels_match_the_oracle_on_the_emulator(emu, n, W, H, radius, ch, cull):
     xys, depths, radii, conics, ntiles, colors, opac, tb = _scene(n, W, H, 3, radius, ch)
     bg = torch.linspace(0.1, 0.7, ch)
     rec = _pack(xys, conics, opac, colors, cull)
@@ -146,7 +147,7 @@ def test_grouped_blend_kernels_match_the_oracle_on_the_emulator(emu, n, W, H, ra
     (img * v_img).sum().add((alpha * v_alpha).sum()).backward()
     vi = np.ascontiguousarray(v_img.numpy())
     va = np.ascontiguousarray(v_alpha.numpy())
-    for direct in (0, 1, 2):  # shared-memory accumulators / direct global reds / one warp per half tile
+    for direct in (0, 1):     # first-generation backward / grouped backward
         grads = np.zeros((n, 12), dtype=np.float32)
         assert emu.emu_blend_bwd(n, ch, H, W, tb[0], tb[1], _ptr(offsets), _ptr(ids), _ptr(rec), _ptr(bgn),
                                  _ptr(final_T), _ptr(ncon), _ptr(vi), None, 0, _ptr(va), _ptr(grads), direct) == 0
@@ -157,7 +158,7 @@ def test_grouped_blend_kernels_match_the_oracle_on_the_emulator(emu, n, W, H, ra
         assert _rel(v_opac, o.grad.reshape(-1).double()) < 1e-4
 
 
-def test_grouped_split_rgb_depth_pass_with_clamp_on_the_emulator(emu):
+def test_split_rgb_depth_pass_with_clamp_on_the_emulator(emu):
     """The fused pipeline's 4-channel pass: RGB image + separate depth map, clamp(rgb, max=1)
     folded in (clamped channels get no gradient), with and without a depth cotangent."""
     n, W, H = 400, 48, 32
@@ -177,7 +178,7 @@ def test_grouped_split_rgb_depth_pass_with_clamp_on_the_emulator(emu):
     g = torch.Generator().manual_seed(2)
     v_img = torch.rand(H, W, 3, generator=g)
     v_dep = torch.rand(H, W, generator=g)
-    for with_depth, direct in ((False, 0), (True, 0), (False, 1), (True, 1), (False, 2), (True, 2)):
+    for with_depth, direct in ((False, 0), (True, 0), (False, 1), (True, 1)):
         x = xys.clone().requires_grad_(True)
         cn = conics.clone().requires_grad_(True)
         co = colors.clone().requires_grad_(True)
@@ -215,7 +216,7 @@ def test_emulator_detects_a_lane_that_skips_a_collective(emu, tmp_path):
     assert C.CDLL(str(so)).run() == -1
 
 
-def test_grouped_backward_zero_opacity_without_culling_stays_finite(emu):
+def test_backward_zero_opacity_without_culling_stays_finite(emu):
     """cull_mode = 0 keeps every (Gaussian, tile) pair, including Gaussians whose opacity is
     exactly 0: v_opacity is formed as -s0 / opacity in the grouped kernel and must not turn a
     0 * inf into a NaN that a neighbouring group's reduction then spreads."""
@@ -232,7 +233,7 @@ def test_grouped_backward_zero_opacity_without_culling_stays_finite(emu):
     assert emu.emu_blend_fwd(ch, H, W, tb[0], tb[1], _ptr(offsets), _ptr(ids), _ptr(rec), _ptr(bgn), _ptr(out),
                              None, _ptr(final_T), _ptr(ncon), 0) == 0
     vi = np.ones((H, W, ch), dtype=np.float32)
-    for direct in (0, 1, 2):
+    for direct in (0, 1):
         grads = np.zeros((n, 12), dtype=np.float32)
         assert emu.emu_blend_bwd(n, ch, H, W, tb[0], tb[1], _ptr(offsets), _ptr(ids), _ptr(rec), _ptr(bgn),
                                  _ptr(final_T), _ptr(ncon), _ptr(vi), None, 0, None, _ptr(grads), direct) == 0

@@ -130,12 +130,6 @@ def _rowmask_case(lib, x, y, cov, op, tile_x, tile_y):
     q0 = np.array([x, y, hx, hy], dtype=f)
     mask = lib.ts_debug_rowmask(q0.ctypes.data_as(ctypes.c_void_p), q1.ctypes.data_as(ctypes.c_void_p),
                                 tile_x, tile_y)
-    halves = [lib.ts_debug_rowmask_half(q0.ctypes.data_as(ctypes.c_void_p), q1.ctypes.data_as(ctypes.c_void_p),
-                                        tile_x, tile_y, h) for h in (0, 1)]
-    assert halves[0] & 0xffff0000 == 0 and halves[1] & 0x0000ffff == 0
-    # the 8-row windows may differ from the 16-row evaluation only inside the safety margins:
-    # what matters is that each of them is a superset of the lit cells too
-    mask &= halves[0] | halves[1]
     px = (f(tile_x * 16) + np.arange(16, dtype=f) + f(0.5))[None, :]
     py = (f(tile_y * 16) + np.arange(16, dtype=f) + f(0.5))[:, None]
     dx = q0[0] - px

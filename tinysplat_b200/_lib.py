@@ -48,7 +48,6 @@ _SIGNATURES = {
     "ts_set_blend_mode": ([_i], C.c_int),
     "ts_get_blend_mode": ([], C.c_int),
     "ts_debug_rowmask": ([_p, _p, _i, _i], C.c_uint32),
-    "ts_debug_rowmask_half": ([_p, _p, _i, _i, _i], C.c_uint32),
 }
 
 # flags (include/tinysplat_b200.h enum ts_flags)

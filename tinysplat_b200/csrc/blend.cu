@@ -16,7 +16,7 @@
 #include "ts_blend_common.cuh"
 
 #ifndef TS_DEFAULT_BLEND_MODE
-#define TS_DEFAULT_BLEND_MODE 0
+#define TS_DEFAULT_BLEND_MODE 1
 #endif
 
 namespace ts {
@@ -224,7 +224,11 @@ blend_bwd_kernel(int H, int W, int tbx, const int32_t* __restrict__ tile_offsets
                  const int32_t* __restrict__ n_contrib, const float* __restrict__ v_out_img,
                  const float* __restrict__ v_out_ch3, int split_ch3,
                  const float* __restrict__ v_out_alpha, float4* __restrict__ grads) {
+#ifdef TS_HOST_EMU
+    __shared__ __align__(16) unsigned char s_raw[kBwdSmemBytes];              // emulator: static storage
+#else
     extern __shared__ __align__(16) unsigned char s_raw[];
+#endif
     float4* s_rec = reinterpret_cast<float4*>(s_raw);                         // [2][kBatch*3]
     float* s_acc = reinterpret_cast<float*>(s_rec + 2 * kBatch * 3);          // [kBatch*12]
     float* s_part = s_acc + kBatch * kGradFloats;                             // [8][kGroup][320]
@@ -430,41 +434,36 @@ unpack_grads_kernel(int N, const int32_t* __restrict__ radii, const float* __res
     if (CH > 3) v_colors[(size_t)CH * i + 3] = g2.w;
 }
 
-// second-generation kernels (blend_group.cu)
-int launch_blend_fwd_group(int CH, int H, int W, int tiles_x, int tiles_y, const int32_t* tile_offsets,
-                           const int32_t* ids, const float* recs, const float* background,
-                           float* out_img, float* out_ch3, float* final_T, int32_t* n_contrib,
-                           int clamp_max1, cudaStream_t st);
-int launch_blend_bwd_group(int CH, int gch, int direct, int H, int W, int tiles_x, int tiles_y,
+#ifndef TS_HOST_EMU
+// grouped backward (blend_group.cu)
+int launch_blend_bwd_group(int CH, int gch, int H, int W, int tiles_x, int tiles_y,
                            const int32_t* tile_offsets, const int32_t* ids, const float* recs,
                            const float* background, const float* final_T, const int32_t* n_contrib,
                            const float* v_out_img, const float* v_out_ch3, int split_ch3,
                            const float* v_out_alpha, float* grads, cudaStream_t st);
 
-// Bit 0: forward uses the grouped kernel (blend_group.cu); bit 1: backward does (shared-memory
-// accumulators); bit 2: backward uses the grouped kernel with direct global reds; bit 3: backward
-// uses the one-warp-per-half-tile kernel (direct reds).  0 = first generation for both (one warp
-// per sub-block).  Initialised once from TS_BLEND_MODE ("warp" = 0, "group" = 3, or a number
-// 0..15); ts_set_blend_mode() overrides it (tests, A/B benches).
-constexpr int kDefaultBlendMode = TS_DEFAULT_BLEND_MODE;
+// Which backward kernel ts_blend_bwd launches: 0 = first generation (blend_bwd_kernel, one warp
+// per sub-block), 1 = grouped (blend_group.cu; default).  Initialised once from TS_BLEND_MODE
+// ("warp" | "group"); ts_set_blend_mode() overrides it (tests, A/B benches).
 static int g_blend_mode = -1;
 static int blend_mode() {
     if (g_blend_mode < 0) {
         const char* e = getenv("TS_BLEND_MODE");
         if (e && !strcmp(e, "warp")) g_blend_mode = 0;
-        else if (e && !strcmp(e, "group")) g_blend_mode = 3;
-        else if (e && e[0] >= '0' && e[0] <= '9') g_blend_mode = atoi(e) & 15;
-        else g_blend_mode = kDefaultBlendMode;
+        else if (e && !strcmp(e, "group")) g_blend_mode = 1;
+        else g_blend_mode = TS_DEFAULT_BLEND_MODE;
     }
     return g_blend_mode;
 }
+#endif  // !TS_HOST_EMU
 
 }  // namespace ts
 
+#ifndef TS_HOST_EMU
 extern "C" {
 
 int ts_set_blend_mode(int mode) {
-    if (mode < -1 || mode > 15) return TS_ERR_INVALID;
+    if (mode < -1 || mode > 1) return TS_ERR_INVALID;
     ts::g_blend_mode = mode;      // -1: back to TS_BLEND_MODE / the built-in default
     return TS_OK;
 }
@@ -479,12 +478,6 @@ int ts_blend_fwd(int CH, int img_height, int img_width, int tiles_x, int tiles_y
     if (recs && !ts::aligned16(recs)) return TS_ERR_ALIGN;
     dim3 grid(tiles_x, tiles_y);
     cudaStream_t st = (cudaStream_t)stream;
-    if (ts::blend_mode() & 1) {
-        ts::launch_blend_fwd_group(CH, img_height, img_width, tiles_x, tiles_y, tile_offsets, ids_sorted, recs,
-                                   background, out_img, out_ch3, final_T, n_contrib, clamp_max1, st);
-        TS_CHECK_LAUNCH("ts_blend_fwd/group");
-        return TS_OK;
-    }
 #define TS_LAUNCH_FWD(C) \
     ts::blend_fwd_kernel<C><<<grid, ts::kBlendThreads, 0, st>>>(img_height, img_width, tiles_x, tile_offsets, ids_sorted, (const float4*)recs, background, out_img, out_ch3, final_T, n_contrib, clamp_max1)
     switch (CH) {
@@ -513,9 +506,8 @@ int ts_blend_bwd(int N, int CH, int img_height, int img_width, int tiles_x, int 
     dim3 grid(tiles_x, tiles_y);
     // channels that carry a cotangent: the fused RGB+depth pass without a depth loss skips ch 3
     const int gch = (CH == 4 && split_ch3 && !v_out_ch3) ? 3 : CH;
-    if (ts::blend_mode() & 14) {
-        const int variant = (ts::blend_mode() & 8) ? 2 : (ts::blend_mode() & 4) ? 1 : 0;
-        ts::launch_blend_bwd_group(CH, gch, variant, img_height, img_width, tiles_x, tiles_y, tile_offsets, ids_sorted,
+    if (ts::blend_mode() == 1) {
+        ts::launch_blend_bwd_group(CH, gch, img_height, img_width, tiles_x, tiles_y, tile_offsets, ids_sorted,
                                    recs, background, final_T, n_contrib, v_out_img, v_out_ch3, split_ch3,
                                    v_out_alpha, grads, st);
         TS_CHECK_LAUNCH("ts_blend_bwd/group");
@@ -570,3 +562,4 @@ int ts_blend_unpack_grads(int N, int CH, const int32_t* radii, const float* coni
 }
 
 }  // extern "C"
+#endif  // !TS_HOST_EMU

@@ -1,5 +1,5 @@
-// K4 / K5, second generation — "grouped" blend kernels (default; the first generation in blend.cu
-// stays selectable with ts_set_blend_mode(0) / TS_BLEND_MODE=warp for A/B runs).
+// K5, second generation — "grouped" blend-backward (default; the first generation in blend.cu stays
+// selectable with ts_set_blend_mode(0) / TS_BLEND_MODE=warp for A/B runs).
 // Behind gsplat.rasterize_gaussians  [REF tinysplat/splatting/rasterize.py:44,50,83-86].
 //
 // Mapping.  One CTA of 64 threads per 16x16 tile [REF rasterize.py:19-20].  The 64 threads form
@@ -8,14 +8,19 @@
 // warp walk four DIFFERENT candidate lists in lock-step (per-lane shared-memory addresses), so
 // one warp-instruction evaluates one pixel row of four (sub-block, Gaussian) pairs.
 //
-// Why (measured with tools/cull_stats.py on synthetic_1M_1080p, per fwd or bwd pass):
+// Why (tools/cull_stats.py on synthetic_1M_1080p; measured history in profiles/README.md):
 //   * culling is exact per pixel row (footprint_rowmask: the interval of each row the ellipse
 //     {alpha >= 1/255} covers), not a bounding box per sub-block: 6.15 M -> 5.31 M
-//     (sub-block, Gaussian) pairs, and rows the ellipse misses are skipped inside a pair;
-//   * backward: a lane first sums its four rows in registers, then ONE 8-lane butterfly
-//     (transpose-reduce, 3 shuffle levels) + one shared atomic per lane finishes a pair —
-//     the first generation paid a 32-lane reduction for every pair;
-//   * candidates are staged once per tile by 64 threads (2 records each), not by 256.
+//     (sub-block, Gaussian) pairs;
+//   * a lane first sums its four rows in registers (a lane is a pixel column, so dx is shared and
+//     three moments per row suffice), then ONE 8-lane transpose-reduce finishes a pair — the
+//     first generation paid a 32-lane reduction through shared memory for every pair;
+//   * the colour accumulated behind a Gaussian only enters through its dot product with the
+//     pixel's fixed cotangent: one scalar per pixel replaces the per-channel buffers;
+//   * group totals go straight to global memory as red.global.add.v4/.v2.f32 from two lanes of
+//     the group: fire-and-forget, no shared accumulators, no flush phase (shared memory has no
+//     native fp32 add: the accumulator variant spent 27 % of its stall samples in CAS loops);
+//   * 64 registers, 14 KB shared memory -> 15 CTAs (30 warps) per SM.
 // Still not HBM-bound: fp32 FMA / MUFU issue.
 #include "ts_blend_common.cuh"
 
@@ -77,185 +82,10 @@ __device__ __forceinline__ void build_masks(const GroupMap& gm, const float4* re
     }
 }
 
-template <int CH>
-__global__ void __launch_bounds__(kGThreads)
-blend_fwd_group_kernel(int H, int W, int tbx, const int32_t* __restrict__ tile_offsets,
-                       const int32_t* __restrict__ ids, const float4* __restrict__ recs,
-                       const float* __restrict__ background, float* __restrict__ out_img,
-                       float* __restrict__ out_ch3, float* __restrict__ final_T,
-                       int32_t* __restrict__ n_contrib, int clamp_max1) {
-    __shared__ __align__(16) float4 s_rec[2][kGBatch * 3];
-    __shared__ unsigned s_rmask[kGBatch];
-    __shared__ unsigned s_cmask[8 * kGWords];
-    const unsigned full = 0xffffffffu;
-    const GroupMap gm = group_map(H, W);
-    const int tid = threadIdx.x;
-    const int tile = blockIdx.y * tbx + blockIdx.x;
-    const int start = __ldg(tile_offsets + tile);
-    const int count = __ldg(tile_offsets + tile + 1) - start;
-    const int nb = (count + kGBatch - 1) / kGBatch;
-    const unsigned gbits = 0xffu << (gm.lane & 24);      // the lanes of my group
-
-    // T[r] > 0: pixel r still composites; T[r] < 0: finished, |T| is its final transmittance
-    // (pixels outside the image start finished)
-    float T[4], acc[4][CH];
-    int ncon[4];
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        T[r] = ((gm.inside >> r) & 1u) ? 1.f : -1.f;
-        ncon[r] = 0;
-#pragma unroll
-        for (int c = 0; c < CH; ++c) acc[r][c] = 0.f;
-    }
-
-    auto prefetch = [&](int b) {
-#pragma unroll
-        for (int jj = 0; jj < kGPer; ++jj) {
-            const int t = jj * kGThreads + tid;
-            const int p = b * kGBatch + t;
-            if (p < count) {
-                const int g = __ldg(ids + start + p);
-                const float4* src = recs + 3 * (size_t)g;
-                float4* dst = &s_rec[b & 1][t * 3];
-                cp_async16(dst, src);
-                cp_async16(dst + 1, src + 1);
-                cp_async16(dst + 2, src + 2);
-            }
-        }
-    };
-    if (nb > 0) prefetch(0);
-    cp_async_commit();
-
-    for (int b = 0; b < nb; ++b) {
-        const float4* rec = s_rec[b & 1];
-        if (b + 1 < nb) prefetch(b + 1);
-        cp_async_commit();
-        cp_async_wait<1>();       // this thread's copies of batch b have landed
-        bool valid[kGPer];
-#pragma unroll
-        for (int jj = 0; jj < kGPer; ++jj) valid[jj] = b * kGBatch + jj * kGThreads + tid < count;
-        build_masks(gm, rec, valid, s_rmask, s_cmask);
-        __syncthreads();          // records + masks of batch b visible to all
-
-        int k = 0;
-        unsigned m = s_cmask[gm.grp * kGWords];
-        for (;;) {
-            // a group whose 32 pixels are all finished stops walking its list
-            const bool lane_live = fmaxf(fmaxf(T[0], T[1]), fmaxf(T[2], T[3])) > 0.f;
-            if ((__ballot_sync(full, lane_live) & gbits) == 0u) { m = 0u; k = kGWords - 1; }
-            while (m == 0u && k < kGWords - 1) m = s_cmask[gm.grp * kGWords + (++k)];
-            const bool act = (m != 0u);
-            if (!__any_sync(full, act)) break;
-            if (act) {
-                const int c = k * 32 + __ffs(m) - 1;
-                m &= m - 1;
-                const unsigned rm = s_rmask[c] >> gm.shift;
-                const float4 q0 = rec[c * 3];
-                const float4 q1 = rec[c * 3 + 1];
-                const float4 q2 = rec[c * 3 + 2];
-                // branch-free over the four rows: four independent chains for the scheduler
-                float alpha[4];
-                bool ok[4];
-#pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    float dx, dy;
-                    const float pw = eval_power(q0, q1, gm.px, gm.py0 + (float)r, dx, dy);
-                    alpha[r] = fminf(kAlphaMax, __fmul_rn(q1.w, ex2_approx(-fmaxf(pw, 0.f))));
-                    // row reachable (row mask), pixel still compositing, contribution kept
-                    ok[r] = (rm & (1u << (2 * r))) != 0u && T[r] > 0.f && pw >= 0.f && alpha[r] >= kAlphaMin;
-                }
-#pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    const float nT = T[r] * (1.f - alpha[r]);
-                    const bool stop = ok[r] && nT <= kTStop;
-                    const bool upd = ok[r] && !stop;
-                    const float wgt = upd ? alpha[r] * T[r] : 0.f;
-                    acc[r][0] = fmaf(wgt, q2.x, acc[r][0]);
-                    if (CH > 1) acc[r][1] = fmaf(wgt, q2.y, acc[r][1]);
-                    if (CH > 2) acc[r][2] = fmaf(wgt, q2.z, acc[r][2]);
-                    if (CH > 3) acc[r][3] = fmaf(wgt, q2.w, acc[r][3]);
-                    T[r] = upd ? nT : (stop ? -T[r] : T[r]);
-                    ncon[r] = upd ? b * kGBatch + c + 1 : ncon[r];
-                }
-            }
-        }
-        // also guards reuse of s_rec[b & 1] / masks by the next iterations
-        if (__syncthreads_and(!(fmaxf(fmaxf(T[0], T[1]), fmaxf(T[2], T[3])) > 0.f))) break;
-    }
-    cp_async_wait<0>();
-
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        if (!((gm.inside >> r) & 1u)) continue;
-        const size_t pix = (size_t)(gm.i0 + r) * W + gm.j;
-        const float Tf = fabsf(T[r]);
-        int nc = ncon[r];
-        if (CH == 4 && out_ch3) {   // split output: RGB image + separate 4th-channel (depth) map
-            // clamp_max1 folds the adapter's clamp(rgb, max=1) [REF rasterize.py:45] in; which
-            // channels were clamped (zero gradient) is kept in the top bits of n_contrib
-            unsigned cm = 0;
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                float o = fmaf(Tf, __ldg(background + c), acc[r][c]);
-                if (clamp_max1 && o > 1.f) { o = 1.f; cm |= 1u << c; }
-                out_img[pix * 3 + c] = o;
-            }
-            out_ch3[pix] = fmaf(Tf, __ldg(background + 3), acc[r][CH - 1]);
-            nc |= (int)(cm << kClampShift);
-        } else {
-#pragma unroll
-            for (int c = 0; c < CH; ++c) out_img[pix * CH + c] = fmaf(Tf, __ldg(background + c), acc[r][c]);
-        }
-        final_T[pix] = Tf;
-        n_contrib[pix] = nc;
-    }
-}
-
-// Sums val[0..NV) over the 8 lanes of each group.  Values 0..7 go through a transpose-reduce:
-// levels xor 4 and xor 2 halve the values a lane carries (8 -> 4 -> 2), level xor 1 is a plain
-// butterfly, so both lanes of a pair end with the group totals of values (l8 & 6) and (l8 & 6) + 1.
-// Values 8, 9 are reduced plainly and returned on every lane in `extra`.
-template <int NV>
-__device__ __forceinline__ float2 group_reduce(const float (&val)[NV], int l8, float2& extra) {
-    const unsigned full = 0xffffffffu;
-    float v[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = (i < NV) ? val[i < NV ? i : 0] : 0.f;
-    const bool h4 = (l8 & 4) != 0, h2 = (l8 & 2) != 0;
-    float w[4], u[2];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const float send = h4 ? v[i] : v[i + 4];
-        const float keep = h4 ? v[i + 4] : v[i];
-        w[i] = keep + __shfl_xor_sync(full, send, 4);
-    }
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const float send = h2 ? w[i] : w[i + 2];
-        const float keep = h2 ? w[i + 2] : w[i];
-        u[i] = keep + __shfl_xor_sync(full, send, 2);
-    }
-    u[0] += __shfl_xor_sync(full, u[0], 1);
-    u[1] += __shfl_xor_sync(full, u[1], 1);
-    float e[2] = {0.f, 0.f};
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-        if (8 + k < NV) {
-            float x = val[8 + k < NV ? 8 + k : 0];
-            x += __shfl_xor_sync(full, x, 4);
-            x += __shfl_xor_sync(full, x, 2);
-            x += __shfl_xor_sync(full, x, 1);
-            e[k] = x;
-        }
-    }
-    extra = make_float2(e[0], e[1]);
-    return make_float2(u[0], u[1]);
-}
-
-// Variant for the direct-to-global path: level xor 4 transposes (8 -> 4 values per lane), levels
-// xor 2 and xor 1 are plain butterflies, so lanes with l8 < 4 end with the group totals of values
-// 0..3 and lanes with l8 >= 4 with those of values 4..7 — whole float4s of the packed gradient
-// record.  Values 8, 9 are reduced plainly and returned on every lane in `extra`.
+// Sums val[0..NV) over the 8 lanes of each group.  Level xor 4 transposes (8 -> 4 values per
+// lane), levels xor 2 and xor 1 are plain butterflies, so lanes with l8 < 4 end with the group
+// totals of values 0..3 and lanes with l8 >= 4 with those of values 4..7 — whole float4s of the
+// packed gradient record.  Values 8, 9 are reduced plainly and returned on every lane in `extra`.
 template <int NV>
 __device__ __forceinline__ float4 group_reduce_quad(const float (&val)[NV], int l8, float2& extra) {
     const unsigned full = 0xffffffffu;
@@ -289,29 +119,9 @@ __device__ __forceinline__ float4 group_reduce_quad(const float (&val)[NV], int 
     return make_float4(w[0], w[1], w[2], w[3]);
 }
 
-// Adds (a, b) to the two consecutive floats at `addr` (8-byte aligned, shared memory) with one
-// 64-bit compare-and-swap loop (shared memory has no native fp32 add: a scalar atomicAdd is the
-// same loop per float).
-__device__ __forceinline__ void smem_add_pair(float* addr, float a, float b) {
-    unsigned long long* p = reinterpret_cast<unsigned long long*>(addr);
-    unsigned long long old = *p, assumed;
-    do {
-        assumed = old;
-        const float lo = __uint_as_float((unsigned)(assumed & 0xffffffffull)) + a;
-        const float hi = __uint_as_float((unsigned)(assumed >> 32)) + b;
-        const unsigned long long upd = ((unsigned long long)__float_as_uint(hi) << 32) | __float_as_uint(lo);
-        old = atomicCAS(p, assumed, upd);
-    } while (old != assumed);
-}
-
 // GCH = number of colour channels that carry a cotangent (GCH <= CH; the fused RGB+depth pass
 // with no depth loss has CH = 4, GCH = 3 and skips all channel-3 gradient arithmetic).
-// DIRECT = false: per-batch accumulators in shared memory (64-bit CAS adds), flushed to global
-// memory once per (tile, Gaussian) with three vector reds.  DIRECT = true: every (sub-block,
-// Gaussian) total goes straight to global memory as red.global.add.v4/.v2 from two lanes of the
-// group — 2.5x more reds, but they are fire-and-forget (no CAS round trips, no flush phase, one
-// barrier less per batch, 6 KB less shared memory).
-template <int CH, int GCH, bool DIRECT>
+template <int CH, int GCH>
 __global__ void __launch_bounds__(kGThreads)
 blend_bwd_group_kernel(int H, int W, int tbx, const int32_t* __restrict__ tile_offsets,
                        const int32_t* __restrict__ ids, const float4* __restrict__ recs,
@@ -321,8 +131,7 @@ blend_bwd_group_kernel(int H, int W, int tbx, const int32_t* __restrict__ tile_o
                        const float* __restrict__ v_out_alpha, float4* __restrict__ grads) {
     constexpr int NV = 6 + GCH;    // values reduced per (sub-block, Gaussian) pair
     __shared__ __align__(16) float4 s_rec[2][kGBatch * 3];
-    __shared__ __align__(16) float s_acc[DIRECT ? 4 : kGBatch * kGradFloats];   // per-batch CTA accumulators
-    __shared__ int s_gid[DIRECT ? 2 * kGBatch : 1];                // gaussian ids of the staged records
+    __shared__ int s_gid[2 * kGBatch];                             // gaussian ids of the staged records
     __shared__ unsigned s_rmask[kGBatch];
     __shared__ unsigned s_cmask[8 * kGWords];
     __shared__ int s_nmax;
@@ -372,10 +181,6 @@ blend_bwd_group_kernel(int H, int W, int tbx, const int32_t* __restrict__ tile_o
     }
 
     if (tid == 0) s_nmax = 0;
-    if (!DIRECT) {
-#pragma unroll
-        for (int k = 0; k < kGPer * kGradFloats; ++k) s_acc[k * kGThreads + tid] = 0.f;
-    }
     __syncthreads();
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) ncmax = max(ncmax, __shfl_xor_sync(full, ncmax, d));
@@ -385,17 +190,14 @@ blend_bwd_group_kernel(int H, int W, int tbx, const int32_t* __restrict__ tile_o
     const int nb = (nmax + kGBatch - 1) / kGBatch;
 
     // batch b, slot t  <->  list position  p = nmax-1 - (b*kGBatch + t)   (back to front)
-    int gnext[kGPer], gcur[kGPer];
     auto prefetch = [&](int b) {
 #pragma unroll
         for (int jj = 0; jj < kGPer; ++jj) {
             const int t = jj * kGThreads + tid;
             const int p = nmax - 1 - (b * kGBatch + t);
-            gnext[jj] = -1;
             if (p >= 0) {
                 const int g = __ldg(ids + start + p);
-                gnext[jj] = g;
-                if (DIRECT) s_gid[(b & 1) * kGBatch + t] = g;
+                s_gid[(b & 1) * kGBatch + t] = g;
                 const float4* src = recs + 3 * (size_t)g;
                 float4* dst = &s_rec[b & 1][t * 3];
                 cp_async16(dst, src);
@@ -404,19 +206,14 @@ blend_bwd_group_kernel(int H, int W, int tbx, const int32_t* __restrict__ tile_o
             }
         }
     };
-#pragma unroll
-    for (int jj = 0; jj < kGPer; ++jj) gnext[jj] = -1;
     if (nb > 0) prefetch(0);
     cp_async_commit();
-
-    // value pair (l8 & 6) -> float offset inside the packed gradient record (colours start at 8)
-    const int pair_off = (gm.l8 & 6) < 6 ? (gm.l8 & 6) : 8;
 
     for (int b = 0; b < nb; ++b) {
         const float4* rec = s_rec[b & 1];
         bool valid[kGPer];
 #pragma unroll
-        for (int jj = 0; jj < kGPer; ++jj) { gcur[jj] = gnext[jj]; valid[jj] = gcur[jj] >= 0; }
+        for (int jj = 0; jj < kGPer; ++jj) valid[jj] = nmax - 1 - (b * kGBatch + jj * kGThreads + tid) >= 0;
         if (b + 1 < nb) prefetch(b + 1);
         cp_async_commit();
         cp_async_wait<1>();
@@ -430,7 +227,7 @@ blend_bwd_group_kernel(int H, int W, int tbx, const int32_t* __restrict__ tile_o
             while (m == 0u && k < kGWords - 1) m = s_cmask[gm.grp * kGWords + (++k)];
             const bool act = (m != 0u);
             if (!__any_sync(full, act)) break;
-            int c = 0;
+            int c = 0, gid = 0;
             float val[NV];
 #pragma unroll
             for (int v = 0; v < NV; ++v) val[v] = 0.f;
@@ -439,6 +236,7 @@ blend_bwd_group_kernel(int H, int W, int tbx, const int32_t* __restrict__ tile_o
                 c = k * 32 + __ffs(m) - 1;
                 m &= m - 1;
                 const int p = pbase - c;
+                gid = s_gid[(b & 1) * kGBatch + c];     // loaded here: its latency hides behind the rows
                 const unsigned rm = s_rmask[c] >> gm.shift;
                 const float4 q0 = rec[c * 3];
                 const float4 q1 = rec[c * 3 + 1];
@@ -488,229 +286,13 @@ blend_bwd_group_kernel(int H, int W, int tbx, const int32_t* __restrict__ tile_o
             }
             const unsigned anyb = __ballot_sync(full, any);
             if (anyb == 0u) continue;
-            if (DIRECT) {
-                float2 extra;
-                const float4 q = group_reduce_quad<NV>(val, gm.l8, extra);
-                // lane 0 of a group holds packed floats 0..3; lane 4 holds values 4..7 = floats
-                // 4, 5 (S_yy, v_opacity) and the first two colours, which with the extras form g2
-                if (act && (anyb & gbits) != 0u && (gm.l8 & 3) == 0) {
-                    float4* dst = grads + 3 * (size_t)s_gid[(b & 1) * kGBatch + c];
-                    if (gm.l8 == 0) {
-                        atomicAdd(dst, q);
-                    } else {
-                        atomicAdd(reinterpret_cast<float2*>(dst + 1), make_float2(q.x, q.y));
-                        atomicAdd(dst + 2, make_float4(q.z, q.w, extra.x, extra.y));
-                    }
-                }
-            } else {
-                float2 extra;
-                const float2 mine = group_reduce<NV>(val, gm.l8, extra);
-                // even lanes own the value pairs (0,1) (2,3) (4,5) (6,7) -> record floats 0,2,4,8;
-                // lane 1 owns values (8,9) -> floats 10,11
-                const bool second = (NV > 8) && gm.l8 == 1;
-                const float2 add = second ? extra : mine;
-                if (act && (second || !(gm.l8 & 1)) && (add.x != 0.f || add.y != 0.f))
-                    smem_add_pair(s_acc + c * kGradFloats + (second ? 10 : pair_off), add.x, add.y);
-            }
-        }
-        if (!DIRECT) {
-            __syncthreads();  // all groups finished batch b: s_acc complete
-#pragma unroll
-            for (int jj = 0; jj < kGPer; ++jj) {
-                const int t = jj * kGThreads + tid;
-                if (s_rmask[t] != 0u) {
-                    float4* a4 = reinterpret_cast<float4*>(s_acc + t * kGradFloats);
-                    float4* dst = grads + 3 * (size_t)gcur[jj];
-                    atomicAdd(dst, a4[0]);
-                    atomicAdd(dst + 1, a4[1]);
-                    atomicAdd(dst + 2, a4[2]);
-                    a4[0] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    a4[1] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    a4[2] = make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-            }
-        }
-        __syncthreads();  // accumulators reset + buffers free before the next batch touches them
-    }
-    cp_async_wait<0>();
-}
-
-// ---- backward, third arrangement: ONE WARP PER HALF TILE ---------------------------------------
-// Same 8-lane groups and per-lane four-row state as blend_bwd_group_kernel<.., DIRECT = true>, but
-// a CTA is a single warp that owns the upper or lower 16x8 half of a tile (four sub-blocks):
-//   * twice as many, half as long CTAs: the tail of the grid (SMs idling while the last tiles
-//     finish) halves, and a deep tile no longer couples two warps through barriers;
-//   * no __syncthreads at all (only __syncwarp), no shared-memory masks: the batch is 32
-//     candidates, one per lane; a group's candidate word is a ballot it keeps in a register, and
-//     the row mask / Gaussian id of candidate c are fetched from lane c with a shuffle;
-//   * each half evaluates only its own 8 rows of the exact row mask.
-// The tile's list is staged by both halves (2 x 48 B per pair, L2-resident records).
-constexpr int kHBatch = 32;
-#ifndef TS_HALF_MIN_CTAS
-#define TS_HALF_MIN_CTAS 32      // 32 one-warp CTAs per SM -> at most 64 registers per thread
-#endif
-
-template <int CH, int GCH>
-__global__ void __launch_bounds__(32, TS_HALF_MIN_CTAS)
-blend_bwd_half_kernel(int H, int W, int tbx, const int32_t* __restrict__ tile_offsets,
-                      const int32_t* __restrict__ ids, const float4* __restrict__ recs,
-                      const float* __restrict__ background, const float* __restrict__ final_T,
-                      const int32_t* __restrict__ n_contrib, const float* __restrict__ v_out_img,
-                      const float* __restrict__ v_out_ch3, int split_ch3,
-                      const float* __restrict__ v_out_alpha, float4* __restrict__ grads) {
-    constexpr int NV = 6 + GCH;
-    __shared__ __align__(16) float4 s_rec[2][kHBatch * 3];
-    const unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x;
-    const int grp = lane >> 3, l8 = lane & 7;
-    const int tile_y = blockIdx.y >> 1, half = blockIdx.y & 1;
-    const int wx = grp & 1, wy = 2 * half + (grp >> 1);          // sub-block (wx, wy) of the tile
-    const int shift = 8 * wy + wx;                               // rowmask bit of (row 4wy + r, half wx) = shift + 2r
-    const int j = blockIdx.x * kBlock + wx * 8 + l8;
-    const int i0 = tile_y * kBlock + wy * 4;
-    const float px = (float)j + kPixCenter, py0 = (float)i0 + kPixCenter;
-    const float X0 = (float)(blockIdx.x * kBlock) + kPixCenter, Y0 = (float)(tile_y * kBlock) + kPixCenter;
-    const unsigned gbits = 0xffu << (lane & 24);
-    const unsigned gsel = 0x55u << shift;                        // my group's four row bits
-    const int tile = tile_y * tbx + blockIdx.x;
-    const int start = __ldg(tile_offsets + tile);
-
-    float T[4], Wacc[4], v_out[4][GCH];
-    int nc[4];
-    int nmax = 0;
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        float T_final = 1.f, v_oa = 0.f;
-        nc[r] = 0;
-#pragma unroll
-        for (int c = 0; c < GCH; ++c) v_out[r][c] = 0.f;
-        if (j < W && i0 + r < H) {
-            const size_t pix = (size_t)(i0 + r) * W + j;
-            T_final = __ldg(final_T + pix);
-            int n = __ldg(n_contrib + pix);
-            const unsigned cm = (unsigned)n >> kClampShift;    // channels clamped by forward
-            nc[r] = n & kCountMask;
-            if (CH == 4 && split_ch3) {
-#pragma unroll
-                for (int c = 0; c < 3; ++c)
-                    v_out[r][c] = (v_out_img && !((cm >> c) & 1u)) ? __ldg(v_out_img + pix * 3 + c) : 0.f;
-                if (GCH == 4) v_out[r][GCH - 1] = v_out_ch3 ? __ldg(v_out_ch3 + pix) : 0.f;
-            } else {
-#pragma unroll
-                for (int c = 0; c < GCH; ++c) v_out[r][c] = __ldg(v_out_img + pix * CH + c);
-            }
-            if (v_out_alpha) v_oa = __ldg(v_out_alpha + pix);
-        }
-        float bgdot = 0.f;
-#pragma unroll
-        for (int c = 0; c < GCH; ++c) bgdot = fmaf(__ldg(background + c), v_out[r][c], bgdot);
-        Wacc[r] = T_final * (v_oa - bgdot);
-        T[r] = T_final;
-        nmax = max(nmax, nc[r]);
-    }
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) nmax = max(nmax, __shfl_xor_sync(full, nmax, d));
-    // entries [0, nmax) of the tile list contributed somewhere in this half tile
-    const int nb = (nmax + kHBatch - 1) / kHBatch;
-
-    // batch b, lane t  <->  list position  p = nmax-1 - (b*32 + t)   (back to front)
-    int gnext = -1;
-    auto prefetch = [&](int b) {
-        const int p = nmax - 1 - (b * kHBatch + lane);
-        gnext = -1;
-        if (p >= 0) {
-            const int g = __ldg(ids + start + p);
-            gnext = g;
-            const float4* src = recs + 3 * (size_t)g;
-            float4* dst = &s_rec[b & 1][lane * 3];
-            cp_async16(dst, src);
-            cp_async16(dst + 1, src + 1);
-            cp_async16(dst + 2, src + 2);
-        }
-    };
-    if (nb > 0) prefetch(0);
-    cp_async_commit();
-
-    for (int b = 0; b < nb; ++b) {
-        const float4* rec = s_rec[b & 1];
-        const int gcur = gnext;
-        if (b + 1 < nb) prefetch(b + 1);
-        cp_async_commit();
-        cp_async_wait<1>();
-        unsigned rm_mine = 0u;
-        if (gcur >= 0) rm_mine = footprint_rowmask_rows<8>(rec[lane * 3], rec[lane * 3 + 1], X0, Y0, 8 * half);
-        __syncwarp(full);         // every lane's record of batch b is in shared memory
-        // candidate word of my group: which of the 32 staged records can reach my sub-block
-        unsigned m = 0u;
-#pragma unroll
-        for (int s = 0; s < 4; ++s) {
-            const unsigned sel = 0x55u << (16 * half + 8 * (s >> 1) + (s & 1));
-            const unsigned w = __ballot_sync(full, (rm_mine & sel) != 0u);
-            if (s == grp) m = w;
-        }
-        const int pbase = nmax - 1 - b * kHBatch;
-
-        for (;;) {
-            const bool act = (m != 0u);
-            if (!__any_sync(full, act)) break;
-            const int c = act ? __ffs(m) - 1 : 0;
-            m &= m - 1;
-            const unsigned rm = __shfl_sync(full, rm_mine, c) & gsel;
-            const int gid = __shfl_sync(full, gcur, c);
-            float val[NV];
-#pragma unroll
-            for (int v = 0; v < NV; ++v) val[v] = 0.f;
-            bool any = false;
-            if (act) {
-                const int p = pbase - c;
-                const float4 q0 = rec[c * 3];
-                const float4 q1 = rec[c * 3 + 1];
-                const float4 q2 = rec[c * 3 + 2];
-                const float col[4] = {q2.x, q2.y, q2.z, q2.w};
-                float s0 = 0.f, s1 = 0.f, s2 = 0.f, dxc = 0.f;
-                float vis[4], araw[4], dyr[4];
-                bool ok[4];
-#pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    const float pw = eval_power(q0, q1, px, py0 + (float)r, dxc, dyr[r]);
-                    vis[r] = ex2_approx(-fmaxf(pw, 0.f));
-                    araw[r] = __fmul_rn(q1.w, vis[r]);
-                    ok[r] = ((rm >> (shift + 2 * r)) & 1u) != 0u && p < nc[r] && pw >= 0.f &&
-                            fminf(kAlphaMax, araw[r]) >= kAlphaMin;
-                    any = any || ok[r];
-                }
-#pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    const float alpha = ok[r] ? fminf(kAlphaMax, araw[r]) : 0.f;
-                    const float ra = rcp_approx(1.f - alpha);          // 1 when !ok
-                    T[r] = ok[r] ? T[r] * ra : T[r];
-                    const float fac = alpha * T[r];                    // 0 when !ok
-                    float cv = col[0] * v_out[r][0];
-#pragma unroll
-                    for (int ch = 1; ch < GCH; ++ch) cv = fmaf(col[ch], v_out[r][ch], cv);
-#pragma unroll
-                    for (int ch = 0; ch < GCH; ++ch) val[6 + ch] = fmaf(fac, v_out[r][ch], val[6 + ch]);
-                    const float v_alpha = fmaf(cv, T[r], Wacc[r] * ra);
-                    Wacc[r] = fmaf(-cv, fac, Wacc[r]);
-                    const float v_sig = (ok[r] && !(araw[r] > kAlphaMax)) ? -araw[r] * v_alpha : 0.f;
-                    s0 += v_sig;
-                    s1 = fmaf(v_sig, dyr[r], s1);
-                    s2 = fmaf(v_sig * dyr[r], dyr[r], s2);
-                }
-                val[0] = s0 * dxc;
-                val[1] = s1;
-                val[2] = val[0] * dxc;
-                val[3] = s1 * dxc;
-                val[4] = s2;
-                val[5] = any ? -s0 * rcp_approx(q1.w) : 0.f;   // any => opacity >= 1/255
-            }
-            const unsigned anyb = __ballot_sync(full, any);
-            if (anyb == 0u) continue;
             float2 extra;
-            const float4 q = group_reduce_quad<NV>(val, l8, extra);
-            if (act && (anyb & gbits) != 0u && (l8 & 3) == 0) {
+            const float4 q = group_reduce_quad<NV>(val, gm.l8, extra);
+            // lane 0 of a group holds packed floats 0..3; lane 4 holds values 4..7 = floats 4, 5
+            // (S_yy, v_opacity) and the first two colours, which with the extras form g2
+            if (act && (anyb & gbits) != 0u && (gm.l8 & 3) == 0) {
                 float4* dst = grads + 3 * (size_t)gid;
-                if (l8 == 0) {
+                if (gm.l8 == 0) {
                     atomicAdd(dst, q);
                 } else {
                     atomicAdd(reinterpret_cast<float2*>(dst + 1), make_float2(q.x, q.y));
@@ -718,45 +300,23 @@ blend_bwd_half_kernel(int H, int W, int tbx, const int32_t* __restrict__ tile_of
                 }
             }
         }
-        __syncwarp(full);   // all lanes are done with s_rec[b & 1] before batch b+2 overwrites it
+        __syncthreads();  // buffers free before the next batch touches them
     }
     cp_async_wait<0>();
 }
 
 #ifndef TS_HOST_EMU
 // ---- launchers (called from the C-ABI entry points in blend.cu) ------------------------------
-int launch_blend_fwd_group(int CH, int H, int W, int tiles_x, int tiles_y, const int32_t* tile_offsets,
-                           const int32_t* ids, const float* recs, const float* background,
-                           float* out_img, float* out_ch3, float* final_T, int32_t* n_contrib,
-                           int clamp_max1, cudaStream_t st) {
-    dim3 grid(tiles_x, tiles_y);
-#define TS_LAUNCH_FWD(C) \
-    blend_fwd_group_kernel<C><<<grid, kGThreads, 0, st>>>(H, W, tiles_x, tile_offsets, ids, (const float4*)recs, background, out_img, out_ch3, final_T, n_contrib, clamp_max1)
-    switch (CH) {
-        case 1: TS_LAUNCH_FWD(1); break;
-        case 2: TS_LAUNCH_FWD(2); break;
-        case 3: TS_LAUNCH_FWD(3); break;
-        default: TS_LAUNCH_FWD(4); break;
-    }
-#undef TS_LAUNCH_FWD
-    return 0;
-}
-
-int launch_blend_bwd_group(int CH, int gch, int direct, int H, int W, int tiles_x, int tiles_y,
+int launch_blend_bwd_group(int CH, int gch, int H, int W, int tiles_x, int tiles_y,
                            const int32_t* tile_offsets, const int32_t* ids, const float* recs,
                            const float* background, const float* final_T, const int32_t* n_contrib,
                            const float* v_out_img, const float* v_out_ch3, int split_ch3,
                            const float* v_out_alpha, float* grads, cudaStream_t st) {
     dim3 grid(tiles_x, tiles_y);
-#define TS_LAUNCH_BWD_(C, G, D)                                                                    \
-    blend_bwd_group_kernel<C, G, D><<<grid, kGThreads, 0, st>>>(                                   \
+#define TS_LAUNCH_BWD(C, G)                                                                        \
+    blend_bwd_group_kernel<C, G><<<grid, kGThreads, 0, st>>>(                                      \
         H, W, tiles_x, tile_offsets, ids, (const float4*)recs, background, final_T, n_contrib,     \
         v_out_img, v_out_ch3, split_ch3, v_out_alpha, (float4*)grads)
-#define TS_LAUNCH_HALF(C, G)                                                                      \
-    blend_bwd_half_kernel<C, G><<<dim3(tiles_x, 2 * tiles_y), 32, 0, st>>>(                        \
-        H, W, tiles_x, tile_offsets, ids, (const float4*)recs, background, final_T, n_contrib,     \
-        v_out_img, v_out_ch3, split_ch3, v_out_alpha, (float4*)grads)
-#define TS_LAUNCH_BWD(C, G) do { if (direct == 2) TS_LAUNCH_HALF(C, G); else if (direct) TS_LAUNCH_BWD_(C, G, true); else TS_LAUNCH_BWD_(C, G, false); } while (0)
     switch (CH) {
         case 1: TS_LAUNCH_BWD(1, 1); break;
         case 2: TS_LAUNCH_BWD(2, 2); break;
@@ -766,8 +326,6 @@ int launch_blend_bwd_group(int CH, int gch, int direct, int H, int W, int tiles_
             break;
     }
 #undef TS_LAUNCH_BWD
-#undef TS_LAUNCH_BWD_
-#undef TS_LAUNCH_HALF
     return 0;
 }
 #endif  // !TS_HOST_EMU
@@ -786,13 +344,6 @@ uint32_t ts_debug_rowmask(const float* q0, const float* q1, int tile_x, int tile
                                  (float)(tile_y * ts::kBlock) + ts::kPixCenter);
 }
 
-
-uint32_t ts_debug_rowmask_half(const float* q0, const float* q1, int tile_x, int tile_y, int half) {
-    const float4 a = make_float4(q0[0], q0[1], q0[2], q0[3]);
-    const float4 b = make_float4(q1[0], q1[1], q1[2], q1[3]);
-    return ts::footprint_rowmask_rows<8>(a, b, (float)(tile_x * ts::kBlock) + ts::kPixCenter,
-                                         (float)(tile_y * ts::kBlock) + ts::kPixCenter, 8 * half);
-}
 
 }  // extern "C"
 #endif  // !TS_HOST_EMU

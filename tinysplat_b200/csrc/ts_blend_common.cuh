@@ -1,5 +1,5 @@
-// Pieces shared by the two generations of blend kernels (blend.cu: one warp per 8x4 sub-block;
-// blend_group.cu: one 8-lane group per 8x4 sub-block, 4 rows per lane).
+// Pieces shared by the blend kernels (blend.cu: forward and first-generation backward, one warp per
+// 8x4 sub-block; blend_group.cu: grouped backward, one 8-lane group per sub-block, 4 rows per lane).
 #pragma once
 #include "ts_common.cuh"
 
@@ -32,12 +32,9 @@ __device__ __forceinline__ float eval_power(const float4& q0, const float4& q1, 
 // column interval gets 0.02 px + 2^-19 of its magnitude.
 // X0, Y0: pixel-centre coordinates of the tile's first pixel.  q0.z > 1e29 (culling disabled
 // by the caller) -> all bits; q0.z < 0 (opacity below 1/255) -> none.
-// footprint_rowmask_rows<NROWS> evaluates only tile rows row0 .. row0+NROWS-1 (the other bits are 0).
-template <int NROWS>
-__host__ __device__ __forceinline__ unsigned footprint_rowmask_rows(const float4 q0, const float4 q1,
-                                                                    float X0, float Y0, int row0) {
-    const unsigned window = (NROWS == 16 ? 0xffffffffu : ((1u << (2 * NROWS)) - 1u)) << (2 * row0);
-    if (q0.z > 1e29f) return window;
+__host__ __device__ __forceinline__ unsigned footprint_rowmask(const float4 q0, const float4 q1,
+                                                               float X0, float Y0) {
+    if (q0.z > 1e29f) return 0xffffffffu;
     if (q0.z < 0.f) return 0u;
     const float A = q1.x, B = q1.y, C = q1.z;
     const float xr = q0.x - X0, yr = q0.y - Y0;       // centre relative to the tile's first pixel
@@ -55,10 +52,9 @@ __host__ __device__ __forceinline__ unsigned footprint_rowmask_rows(const float4
     // column margin: 0.03 px + rounding of q0.x - px (|x| 2^-23) and of the centre line s*dy
     const float mrg = 0.03f + 2e-6f * (fabsf(q0.x) + fabsf(X0) + fabsf(s) * dym);
     unsigned mask = 0u;
-    const float yr0 = yr - (float)row0;
 #pragma unroll
-    for (int row = 0; row < NROWS; ++row) {
-        const float dy = yr0 - (float)row;
+    for (int row = 0; row < 16; ++row) {
+        const float dy = yr - (float)row;
         const float rem = thr - (D * dy) * dy;        // A (dx + s dy)^2 <= rem
 #ifdef __CUDA_ARCH__
         float w;
@@ -76,12 +72,7 @@ __host__ __device__ __forceinline__ unsigned footprint_rowmask_rows(const float4
         mask |= (miss0 ? 0u : 1u) << (2 * row);
         mask |= (miss1 ? 0u : 2u) << (2 * row);
     }
-    return mask << (2 * row0);
-}
-
-__host__ __device__ __forceinline__ unsigned footprint_rowmask(const float4 q0, const float4 q1,
-                                                               float X0, float Y0) {
-    return footprint_rowmask_rows<16>(q0, q1, X0, Y0, 0);
+    return mask;
 }
 
 }  // namespace ts
