@@ -210,6 +210,37 @@ TS_API int ts_get_blend_mode(void);
  * accepts (tests/test_capi.py brute-forces it). */
 TS_API uint32_t ts_debug_rowmask(const float* q0_host, const float* q1_host, int tile_x, int tile_y);
 
+/* ---- data-parallel gradient exchange in packed form -------------------------
+ * Instead of all-reducing the finished parameter gradients (236 B per Gaussian at SH degree 3),
+ * ranks exchange blend-backward's packed rows (48 B per view and Gaussian): every rank owns a
+ * shard of the Gaussians, receives that shard's rows from all views (all-to-all), runs
+ * projection-/SH-backward for all views on the shard, and the shard results are all-gathered.
+ * ts_dp_prepare: on the rendering rank, makes the packed rows self-contained (exact zeros for
+ *   Gaussians culled in this view, SH clamp mask applied to the colour cotangents) and emits
+ *   this view's d loss / d xy [N,2] (may be NULL).  recs = the packed raster records.
+ * ts_project_bwd_views / ts_sh_bwd_views: backward of a shard of N Gaussians summed over
+ *   n_views views and multiplied by out_scale.  cams[n_views][32] (device): floats 0..11 the
+ *   3x4 view matrix, 12..27 the 4x4 full projection, 28/29 fx/fy.  packed_grads holds view v's
+ *   rows at packed_grads + v * view_stride_floats (+ 12 floats per Gaussian).  flags as
+ *   ts_project_bwd (TS_PROJ_DEPTH_CH3: depth cotangent in packed float 11); the SH view
+ *   direction is mean - camera translation as with TS_SH_DIRS_FROM_MEANS. */
+TS_API int ts_dp_prepare(int N, const int32_t* radii, const uint8_t* clamp_mask /*or NULL*/,
+                         const float* recs /*[16B]*/, float* grads /*[16B] in/out*/,
+                         float* v_xys /*or NULL*/, ts_stream_t stream);
+TS_API int ts_project_bwd_views(int n_views, int N, const float* means3d /*[16B]*/,
+                                const float* scales /*[16B]*/, float glob_scale,
+                                const float* quats /*[16B]*/, const float* cams,
+                                int img_height, int img_width, int flags,
+                                const float* packed_grads /*[16B]*/, int64_t view_stride_floats,
+                                const float* opacity_logits /*or NULL*/, float out_scale,
+                                float* v_means3d /*[16B]*/, float* v_scales /*[16B]*/,
+                                float* v_quats /*[16B]*/, float* v_opacity_logits /*or NULL*/,
+                                ts_stream_t stream);
+TS_API int ts_sh_bwd_views(int n_views, int N, int degree, int K, const float* means,
+                           const float* cams, const float* packed_grads /*[16B]*/,
+                           int64_t view_stride_floats, float out_scale, float* v_dc,
+                           float* v_rest, ts_stream_t stream);
+
 /* ---- fused multi-tensor Adam step ---------------------------------------
  * One launch updates up to ts_adam_max_tensors() parameter tensors in place, with the exact
  * arithmetic of torch.optim.Adam (no weight decay, no amsgrad), the optimizer the reference

@@ -496,6 +496,95 @@ def test_blend_generations_agree_at_full_size(lib):
             assert rel_err(gb, ga) < 1e-4, (mode, name)
 
 
+class _LoopbackExchange:
+    """Single-process stand-in for parallel.PackedGradExchange (world 1): the 'all-to-all' and the
+    'all-gather' are identities, and every packed send buffer + camera row is recorded so that the
+    multi-view shard kernels can be driven by hand afterwards."""
+    world, rank, average = 1, 0, False
+
+    def __init__(self):
+        self.sent, self.cams = [], []
+
+    def shard_rows(self, n):
+        return max(128, (n + 127) // 128 * 128)
+
+    def out_scale(self):
+        return 1.0
+
+    def gather_cameras(self, row):
+        self.cams.append(row.clone())
+        return row.view(1, -1)
+
+    def all_to_all_rows(self, send):
+        self.sent.append(send.clone())
+        return send.view(1, send.shape[0], send.shape[1])
+
+    def all_gather_shards(self, shards):
+        return shards
+
+
+def test_packed_exchange_shard_kernels_match_the_plain_backward(lib):
+    """SURVEY 8e, packed-row gradient exchange: (1) with a loopback exchange the fused node's
+    packed backward (ts_dp_prepare -> ts_project_bwd_views / ts_sh_bwd_views over one view) must
+    reproduce the plain backward; (2) the shard kernels driven with TWO views' recorded rows must
+    equal the sum of the two plain backwards (what the all-reduce strategy delivers)."""
+    from tinysplat_b200 import _lib
+    from tinysplat_b200.rasterizer import GaussianRasterizer, ParamModel
+    W, H, N = 320, 208, 3001                      # N not a multiple of the 128-row shard unit
+    sc = synthetic.make_scene(N, W, H, seed=21, sh_degree=3)
+    sc["background"] = torch.tensor([0.2, 0.4, 0.1])
+    sc["means"][:40, 2] = -1.0                    # culled Gaussians: their packed rows must be inert
+    sc["opacities"][40:60] = 9.0
+    cams = [synthetic.make_camera(W, H, yaw_deg=-4.0, shift=(0.1, 0.0, 0.0)),
+            synthetic.make_camera(W, H, yaw_deg=6.0, shift=(-0.2, 0.05, 0.1))]
+    g = torch.Generator().manual_seed(3)
+    wi = torch.rand(H, W, 3, generator=g).to(DEV)
+    wd = torch.rand(H, W, generator=g).to(DEV)
+
+    def run(cam, exchange):
+        model = ParamModel(sc, DEV, 3)
+        rast = GaussianRasterizer(model, None, DEV, "fused")
+        rast.grad_exchange = exchange
+        img, ex = rast(cam, (W, H), 3)
+        ((img * wi).sum() + 0.05 * (ex["depth"] * wd).sum()).backward()
+        return model, ex["xys"].grad
+
+    plain = [run(c, None) for c in cams]
+    loop = _LoopbackExchange()
+    packed = [run(c, loop) for c in cams]
+    for (mp_, xg_p), (mq, xg_q) in zip(plain, packed):
+        assert rel_err(xg_q, xg_p) < 1e-5
+        for name in PARAMS:
+            a, b = getattr(mq, name).grad, getattr(mp_, name).grad
+            assert a.shape == b.shape and torch.isfinite(a).all(), name
+            assert rel_err(a, b) < 1e-5, name
+
+    # (2) two views at once through the C ABI
+    Ns = loop.shard_rows(N)
+    rows = torch.stack(loop.sent).contiguous()                   # [2, Ns, 12]
+    cam_rows = torch.stack(loop.cams).contiguous()               # [2, 32]
+    m = plain[0][0]
+    K = m.colors_rest.shape[1] + 1
+    f32 = dict(device=DEV, dtype=torch.float32)
+    v_means, v_scales, v_quats, v_logit = (torch.empty(N, 3, **f32), torch.empty(N, 3, **f32),
+                                           torch.empty(N, 4, **f32), torch.empty(N, **f32))
+    v_dc, v_rest = torch.empty(N, 1, 3, **f32), torch.empty(N, K - 1, 3, **f32)
+    st = _lib.stream_ptr(torch.device(DEV))
+    flags = _lib.PROJ_LOG_SCALES | _lib.PROJ_RAW_QUATS | _lib.PROJ_DEPTH_CH3
+    _lib.call("ts_project_bwd_views", 2, N, _lib.ptr(m.means.detach()), _lib.ptr(m.scales.detach()), 1.0,
+              _lib.ptr(m.quats.detach()), _lib.ptr(cam_rows), H, W, flags, _lib.ptr(rows), Ns * 12,
+              _lib.ptr(m.opacities.detach().reshape(-1)), 0.5, _lib.ptr(v_means), _lib.ptr(v_scales),
+              _lib.ptr(v_quats), _lib.ptr(v_logit), st)
+    _lib.call("ts_sh_bwd_views", 2, N, 3, K, _lib.ptr(m.means.detach()), _lib.ptr(cam_rows), _lib.ptr(rows),
+              Ns * 12, 0.5, _lib.ptr(v_dc), _lib.ptr(v_rest), st)
+    got = dict(means=v_means, scales=v_scales, quats=v_quats, opacities=v_logit.reshape(N, 1),
+               colors_dc=v_dc.reshape(m.colors_dc.shape), colors_rest=v_rest)
+    for name in PARAMS:
+        want = 0.5 * (getattr(plain[0][0], name).grad + getattr(plain[1][0], name).grad)
+        assert rel_err(got[name], want) < 1e-5, name
+    assert got["means"][:40].abs().max() == 0
+
+
 # ---- SURVEY 8(f)-2: fused Adam ---------------------------------------------------------------------
 def _param_set(N, seed):
     g = torch.Generator().manual_seed(seed)

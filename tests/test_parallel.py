@@ -79,3 +79,52 @@ def test_single_process_is_a_noop():
     (a * 2).sum().backward()
     red.finish()
     assert red.world_size == 1 and torch.allclose(a.grad, torch.full_like(a, 2.0))
+
+
+# ---- packed-row exchange (PackedGradExchange): the collective plumbing on gloo -----------------
+def _packed_worker(rank, world, port, n_gauss, q):
+    """Each rank holds 'packed rows' P_r[N, 12] of its own view.  A linear stand-in for the shard
+    kernels (sum over views of row * (view + 1)) runs on the rank's shard; after the all-gather
+    every rank must hold sum_r P_r * (r + 1) for ALL Gaussians, scaled by 1/world."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from tinysplat_b200.parallel import PackedGradExchange
+    ex = PackedGradExchange(average=True)
+    N = n_gauss
+    Ns = ex.shard_rows(N)
+    rows = [torch.randn(N, 12, generator=torch.Generator().manual_seed(10 + r)) for r in range(world)]
+    send = torch.zeros(world * Ns, 12)
+    send[:N] = rows[rank]
+    cams = ex.gather_cameras(torch.full((32,), float(rank)))
+    recv = ex.all_to_all_rows(send)
+    s0 = rank * Ns
+    ns = max(0, min(N, s0 + Ns) - s0)
+    shard_a = torch.zeros(Ns, 12)
+    shard_b = torch.zeros(Ns, 3)
+    for v in range(world):
+        shard_a[:ns] += recv[v, :ns] * (cams[v, 0] + 1.0) * ex.out_scale()
+        shard_b[:ns] += recv[v, :ns, :3] * ex.out_scale()
+    full_a, full_b = ex.all_gather_shards([shard_a, shard_b])
+    want_a = sum(rows[r] * (r + 1.0) for r in range(world)) / world
+    want_b = sum(rows[r][:, :3] for r in range(world)) / world
+    ok = torch.allclose(full_a[:N], want_a, atol=1e-6) and torch.allclose(full_b[:N], want_b, atol=1e-6) \
+        and full_a.shape[0] == world * Ns and Ns % 128 == 0 and torch.equal(cams[:, 0], torch.arange(world).float())
+    q.put((rank, bool(ok), ex.last_bytes_sent))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_gauss", [1000, 129, 5])     # ragged last shard; shards past the end
+def test_packed_exchange_collectives_two_ranks_gloo(n_gauss):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_packed_worker, args=(r, 2, port, n_gauss, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok, _ in res), res
+    assert all(b > 0 for _, _, b in res)

@@ -45,6 +45,10 @@ _SIGNATURES = {
     "ts_adam_max_tensors": ([], C.c_int),
     "ts_adam_step": ([_i, _p, _p, _p, _p, _p, _p, _p, C.c_double, C.c_double, C.c_double, _p], C.c_int),
     "ts_blend_unpack_grads": ([_i, _i, _p, _p, _p, _p, _p, _p, _p, _p], C.c_int),
+    "ts_dp_prepare": ([_i, _p, _p, _p, _p, _p, _p], C.c_int),
+    "ts_project_bwd_views": ([_i, _i, _p, _p, _f, _p, _p, _i, _i, _i, _p, C.c_int64, _p, _f, _p, _p, _p, _p, _p],
+                             C.c_int),
+    "ts_sh_bwd_views": ([_i, _i, _i, _i, _p, _p, _p, C.c_int64, _f, _p, _p, _p], C.c_int),
     "ts_set_blend_mode": ([_i], C.c_int),
     "ts_get_blend_mode": ([], C.c_int),
     "ts_debug_rowmask": ([_p, _p, _i, _i], C.c_uint32),

@@ -434,6 +434,41 @@ unpack_grads_kernel(int N, const int32_t* __restrict__ radii, const float* __res
     if (CH > 3) v_colors[(size_t)CH * i + 3] = g2.w;
 }
 
+// Data-parallel exchange: makes blend-backward's packed gradients self-contained
+// before they leave the rank — rows of Gaussians culled in this view become exact zeros, the
+// SH clamp mask [REF rasterize.py:39] is applied to the colour cotangents — and emits this view's
+// d loss / d xy (the densification statistic is per view [REF model_gaussian.py:130-132]).
+__global__ void __launch_bounds__(256)
+dp_prepare_kernel(int N, const int32_t* __restrict__ radii, const uint8_t* __restrict__ clamp_mask,
+                  const float4* __restrict__ recs, float4* __restrict__ grads, float2* __restrict__ v_xys) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= N) return;
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!(__ldg(radii + i) > 0)) {
+        grads[3 * (size_t)i] = zero;
+        grads[3 * (size_t)i + 1] = zero;
+        grads[3 * (size_t)i + 2] = zero;
+        if (v_xys) v_xys[i] = make_float2(0.f, 0.f);
+        return;
+    }
+    if (clamp_mask) {
+        const unsigned m = clamp_mask[i];
+        if ((m & 7u) != 7u) {
+            float4 g2 = grads[3 * (size_t)i + 2];
+            if (!(m & 1u)) g2.x = 0.f;
+            if (!(m & 2u)) g2.y = 0.f;
+            if (!(m & 4u)) g2.z = 0.f;
+            grads[3 * (size_t)i + 2] = g2;
+        }
+    }
+    if (v_xys) {
+        const float4 g0 = grads[3 * (size_t)i];
+        const float4 q1 = __ldg(recs + 3 * (size_t)i + 1);      // {.5 log2e a, log2e b, .5 log2e c, opacity}
+        const float a = q1.x * (2.f / kLog2e), b = q1.y * (1.f / kLog2e), c = q1.z * (2.f / kLog2e);
+        v_xys[i] = make_float2(a * g0.x + b * g0.y, b * g0.x + c * g0.y);
+    }
+}
+
 #ifndef TS_HOST_EMU
 // grouped backward (blend_group.cu)
 int launch_blend_bwd_group(int CH, int gch, int H, int W, int tiles_x, int tiles_y,
@@ -558,6 +593,19 @@ int ts_blend_unpack_grads(int N, int CH, const int32_t* radii, const float* coni
     }
 #undef TS_LAUNCH_UNPACK
     TS_CHECK_LAUNCH("ts_blend_unpack_grads");
+    return TS_OK;
+}
+
+int ts_dp_prepare(int N, const int32_t* radii, const uint8_t* clamp_mask, const float* recs, float* grads,
+                  float* v_xys, ts_stream_t stream) {
+    if (N < 0) return TS_ERR_INVALID;
+    if (N == 0) return TS_OK;
+    if (!radii || !recs || !grads) return TS_ERR_INVALID;
+    if (!ts::aligned16(recs) || !ts::aligned16(grads) || (v_xys && (reinterpret_cast<uintptr_t>(v_xys) & 7u)))
+        return TS_ERR_ALIGN;
+    ts::dp_prepare_kernel<<<(N + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+        N, radii, clamp_mask, (const float4*)recs, (float4*)grads, (float2*)v_xys);
+    TS_CHECK_LAUNCH("ts_dp_prepare");
     return TS_OK;
 }
 

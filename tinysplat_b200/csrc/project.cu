@@ -206,6 +206,118 @@ project_fwd_kernel(int N, const float* __restrict__ means, const float* __restri
     if (cov3d) block_store<6, TH>(cov3d, s_buf + 3 * TH, item0, N);
 }
 
+// Backward of one Gaussian in ONE view: accumulates into vmu / vs / vq (pre-activation: the
+// Jacobians of exp / normalise are applied once by the caller, they do not depend on the view)
+// and vlogit.  Upstream cotangents: (vxy, vdep, vcon) and/or blend-backward's packed record
+// (g0 = {S_x, S_y, S_xx, S_xy}, g1 = {S_yy, v_opacity, .., ..}, depth cotangent `vdep_packed`).
+__device__ __forceinline__ void project_bwd_view(const ProjCam& cam, const float mu[3], const float sc[3],
+                                                 float gs, float4 q, float fx, float fy, int H, int W,
+                                                 float2 vxy, float vdep, float vcon[3], bool has_packed,
+                                                 float4 g0, float4 g1, float vdep_packed, bool has_logit,
+                                                 float opac_logit, float vmu[3], float vs[3], float4& vq,
+                                                 float& vlogit, float2& vxy_total) {
+    ProjState st;
+    project_core(cam, mu, sc, gs, q, fx, fy, H, W, -3.0e38f, st);  // radii>0 => passed the near clip
+    const float* V = cam.V;
+    const float* P = cam.P;
+    float inv = 1.f / st.det;
+    float A = st.c * inv, B = -st.b * inv, C = st.a * inv;   // the conic
+    if (has_packed) {
+        // blend-backward's packed record: S-sums -> cotangents of xy and conic; the fused
+        // pipeline's depth cotangent rides in colour channel 3; v_opacity in g1.y
+        vxy.x += A * g0.x + B * g0.y;
+        vxy.y += B * g0.x + C * g0.y;
+        vcon[0] += 0.5f * g0.z;
+        vcon[1] += g0.w;
+        vcon[2] += 0.5f * g1.x;
+        vdep += vdep_packed;
+        if (has_logit) {
+            float o = 1.f / (1.f + expf(-opac_logit));
+            vlogit += g1.y * o * (1.f - o);
+        }
+    }
+    vxy_total = vxy;
+    // (1) pixel position
+    float vndx = 0.5f * (float)W * vxy.x, vndy = 0.5f * (float)H * vxy.y;
+    float vph0 = vndx * st.rw, vph1 = vndy * st.rw;
+    float vph3 = -(vndx * st.ph[0] + vndy * st.ph[1]) * st.rw * st.rw;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) vmu[k] += P[k] * vph0 + P[4 + k] * vph1 + P[12 + k] * vph3;
+    // (2) depth
+#pragma unroll
+    for (int k = 0; k < 3; ++k) vmu[k] += V[8 + k] * vdep;
+    // (3) conic -> cov2d
+    float va = -A * A * vcon[0] - A * B * vcon[1] - B * B * vcon[2];
+    float vb = -2.f * A * B * vcon[0] - (A * C + B * B) * vcon[1] - 2.f * B * C * vcon[2];
+    float vc = -B * B * vcon[0] - B * C * vcon[1] - C * C * vcon[2];
+    float hb = 0.5f * vb;
+    // (4) cov2d = T Sigma T^T
+    const float* T = st.T;
+    const float* U = st.U;
+    float vT[6];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        vT[k] = 2.f * (va * U[k] + hb * U[3 + k]);
+        vT[3 + k] = 2.f * (hb * U[k] + vc * U[3 + k]);
+    }
+    float vSig[9];
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            vSig[3 * j + k] = T[j] * (va * T[k] + hb * T[3 + k]) + T[3 + j] * (hb * T[k] + vc * T[3 + k]);
+    // v_J = v_T * Rv^T (only the four live entries)
+    float vJ00 = vT[0] * V[0] + vT[1] * V[1] + vT[2] * V[2];
+    float vJ02 = vT[0] * V[8] + vT[1] * V[9] + vT[2] * V[10];
+    float vJ11 = vT[3] * V[4] + vT[4] * V[5] + vT[5] * V[6];
+    float vJ12 = vT[3] * V[8] + vT[4] * V[9] + vT[5] * V[10];
+    float rz = st.rz, rz2 = rz * rz, rz3 = rz2 * rz;
+    float vtxc = -fx * rz2 * vJ02, vtyc = -fy * rz2 * vJ12;
+    float vt[3];
+    vt[2] = -fx * rz2 * vJ00 - fy * rz2 * vJ11 + 2.f * fx * st.txc * rz3 * vJ02 +
+            2.f * fy * st.tyc * rz3 * vJ12;
+    if (st.clampx) { vt[0] = 0.f; vt[2] += (st.txc * rz) * vtxc; } else vt[0] = vtxc;
+    if (st.clampy) { vt[1] = 0.f; vt[2] += (st.tyc * rz) * vtyc; } else vt[1] = vtyc;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) vmu[k] += V[k] * vt[0] + V[4 + k] * vt[1] + V[8 + k] * vt[2];
+    // (5) Sigma = M M^T, M = R diag(s)
+    const float* R = st.R;
+    float vR[9];
+#pragma unroll
+    for (int ii = 0; ii < 3; ++ii)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            float vM = 2.f * (vSig[3 * ii + 0] * R[0 + j] * st.s[j] + vSig[3 * ii + 1] * R[3 + j] * st.s[j] +
+                              vSig[3 * ii + 2] * R[6 + j] * st.s[j]);
+            vR[3 * ii + j] = vM * st.s[j];
+            vs[j] += gs * R[3 * ii + j] * vM;
+        }
+    float w = q.x, x = q.y, y = q.z, z = q.w;
+    vq.x += 2.f * (-z * vR[1] + y * vR[2] + z * vR[3] - x * vR[5] - y * vR[6] + x * vR[7]);
+    vq.y += 2.f * (y * vR[1] + z * vR[2] + y * vR[3] - 2.f * x * vR[4] - w * vR[5] + z * vR[6] +
+                  w * vR[7] - 2.f * x * vR[8]);
+    vq.z += 2.f * (-2.f * y * vR[0] + x * vR[1] + w * vR[2] + x * vR[3] + z * vR[5] - w * vR[6] +
+                  z * vR[7] - 2.f * y * vR[8]);
+    vq.w += 2.f * (-2.f * z * vR[0] - w * vR[1] + x * vR[2] + w * vR[3] - 2.f * z * vR[4] +
+                  y * vR[5] + x * vR[6] + y * vR[7]);
+}
+
+// Jacobians of the activations the fused pipeline folds in (exp of log-scales, q = r/|r|): linear
+// maps that depend on the Gaussian only, applied once after all views have been accumulated.
+__device__ __forceinline__ void project_bwd_activations(int flags, const float sc[3], float4 q, float qn,
+                                                        float vs[3], float4& vq) {
+    if (flags & TS_PROJ_LOG_SCALES) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) vs[k] *= sc[k];           // d exp(l)/dl = exp(l)
+    }
+    if (flags & TS_PROJ_RAW_QUATS) {                           // q = r/|r|
+        float d = vq.x * q.x + vq.y * q.y + vq.z * q.z + vq.w * q.w;
+        float iq = 1.f / qn;
+        vq.x = (vq.x - d * q.x) * iq; vq.y = (vq.y - d * q.y) * iq;
+        vq.z = (vq.z - d * q.z) * iq; vq.w = (vq.w - d * q.w) * iq;
+    }
+}
+
 __global__ void __launch_bounds__(kProjThreads)
 project_bwd_kernel(int N, const float* __restrict__ means, const float* __restrict__ scales,
                    float gs, const float4* __restrict__ quats,
@@ -253,101 +365,17 @@ project_bwd_kernel(int N, const float* __restrict__ means, const float* __restri
     if (ok) {
         ProjCam cam;
         load_cam(viewmat, projmat, cam);
-        ProjState st;
-        project_core(cam, mu, sc, gs, q, fx, fy, H, W, -3.0e38f, st);  // radii>0 => passed the near clip
-        const float* V = cam.V;
-        const float* P = cam.P;
-        float inv = 1.f / st.det;
-        float A = st.c * inv, B = -st.b * inv, C = st.a * inv;   // the conic
+        float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0;
+        float vdep_packed = 0.f, logit = 0.f;
         if (packed) {
-            // blend-backward's packed record: S-sums -> cotangents of xy and conic; the fused
-            // pipeline's depth cotangent rides in colour channel 3; v_opacity in g1.y
-            float4 g0 = __ldg(packed + 3 * (size_t)i), g1 = __ldg(packed + 3 * (size_t)i + 1);
-            vxy.x += A * g0.x + B * g0.y;
-            vxy.y += B * g0.x + C * g0.y;
-            vcon[0] += 0.5f * g0.z;
-            vcon[1] += g0.w;
-            vcon[2] += 0.5f * g1.x;
-            if (flags & TS_PROJ_DEPTH_CH3) vdep += __ldg(reinterpret_cast<const float*>(packed) + 12 * (size_t)i + 11);
-            if (opac_logits) {
-                float o = 1.f / (1.f + expf(-__ldg(opac_logits + i)));
-                vlogit = g1.y * o * (1.f - o);
-            }
+            g0 = __ldg(packed + 3 * (size_t)i);
+            g1 = __ldg(packed + 3 * (size_t)i + 1);
+            if (flags & TS_PROJ_DEPTH_CH3) vdep_packed = __ldg(reinterpret_cast<const float*>(packed) + 12 * (size_t)i + 11);
+            if (opac_logits) logit = __ldg(opac_logits + i);
         }
-        // (1) pixel position
-        float vndx = 0.5f * (float)W * vxy.x, vndy = 0.5f * (float)H * vxy.y;
-        float vph0 = vndx * st.rw, vph1 = vndy * st.rw;
-        float vph3 = -(vndx * st.ph[0] + vndy * st.ph[1]) * st.rw * st.rw;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) vmu[k] = P[k] * vph0 + P[4 + k] * vph1 + P[12 + k] * vph3;
-        // (2) depth
-#pragma unroll
-        for (int k = 0; k < 3; ++k) vmu[k] += V[8 + k] * vdep;
-        // (3) conic -> cov2d
-        float va = -A * A * vcon[0] - A * B * vcon[1] - B * B * vcon[2];
-        float vb = -2.f * A * B * vcon[0] - (A * C + B * B) * vcon[1] - 2.f * B * C * vcon[2];
-        float vc = -B * B * vcon[0] - B * C * vcon[1] - C * C * vcon[2];
-        float hb = 0.5f * vb;
-        // (4) cov2d = T Sigma T^T
-        const float* T = st.T;
-        const float* U = st.U;
-        float vT[6];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            vT[k] = 2.f * (va * U[k] + hb * U[3 + k]);
-            vT[3 + k] = 2.f * (hb * U[k] + vc * U[3 + k]);
-        }
-        float vSig[9];
-#pragma unroll
-        for (int j = 0; j < 3; ++j)
-#pragma unroll
-            for (int k = 0; k < 3; ++k)
-                vSig[3 * j + k] = T[j] * (va * T[k] + hb * T[3 + k]) + T[3 + j] * (hb * T[k] + vc * T[3 + k]);
-        // v_J = v_T * Rv^T (only the four live entries)
-        float vJ00 = vT[0] * V[0] + vT[1] * V[1] + vT[2] * V[2];
-        float vJ02 = vT[0] * V[8] + vT[1] * V[9] + vT[2] * V[10];
-        float vJ11 = vT[3] * V[4] + vT[4] * V[5] + vT[5] * V[6];
-        float vJ12 = vT[3] * V[8] + vT[4] * V[9] + vT[5] * V[10];
-        float rz = st.rz, rz2 = rz * rz, rz3 = rz2 * rz;
-        float vtxc = -fx * rz2 * vJ02, vtyc = -fy * rz2 * vJ12;
-        float vt[3];
-        vt[2] = -fx * rz2 * vJ00 - fy * rz2 * vJ11 + 2.f * fx * st.txc * rz3 * vJ02 +
-                2.f * fy * st.tyc * rz3 * vJ12;
-        if (st.clampx) { vt[0] = 0.f; vt[2] += (st.txc * rz) * vtxc; } else vt[0] = vtxc;
-        if (st.clampy) { vt[1] = 0.f; vt[2] += (st.tyc * rz) * vtyc; } else vt[1] = vtyc;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) vmu[k] += V[k] * vt[0] + V[4 + k] * vt[1] + V[8 + k] * vt[2];
-        // (5) Sigma = M M^T, M = R diag(s)
-        const float* R = st.R;
-        float vR[9];
-#pragma unroll
-        for (int ii = 0; ii < 3; ++ii)
-#pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                float vM = 2.f * (vSig[3 * ii + 0] * R[0 + j] * st.s[j] + vSig[3 * ii + 1] * R[3 + j] * st.s[j] +
-                                  vSig[3 * ii + 2] * R[6 + j] * st.s[j]);
-                vR[3 * ii + j] = vM * st.s[j];
-                vs[j] += gs * R[3 * ii + j] * vM;
-            }
-        float w = q.x, x = q.y, y = q.z, z = q.w;
-        vq.x = 2.f * (-z * vR[1] + y * vR[2] + z * vR[3] - x * vR[5] - y * vR[6] + x * vR[7]);
-        vq.y = 2.f * (y * vR[1] + z * vR[2] + y * vR[3] - 2.f * x * vR[4] - w * vR[5] + z * vR[6] +
-                      w * vR[7] - 2.f * x * vR[8]);
-        vq.z = 2.f * (-2.f * y * vR[0] + x * vR[1] + w * vR[2] + x * vR[3] + z * vR[5] - w * vR[6] +
-                      z * vR[7] - 2.f * y * vR[8]);
-        vq.w = 2.f * (-2.f * z * vR[0] - w * vR[1] + x * vR[2] + w * vR[3] - 2.f * z * vR[4] +
-                      y * vR[5] + x * vR[6] + y * vR[7]);
-        // activation Jacobians of the fused pipeline
-        if (flags & TS_PROJ_LOG_SCALES) {
-#pragma unroll
-            for (int k = 0; k < 3; ++k) vs[k] *= sc[k];           // d exp(l)/dl = exp(l)
-        }
-        if (flags & TS_PROJ_RAW_QUATS) {                           // q = r/|r|
-            float d = vq.x * q.x + vq.y * q.y + vq.z * q.z + vq.w * q.w;
-            float iq = 1.f / qn;
-            vq.x = (vq.x - d * q.x) * iq; vq.y = (vq.y - d * q.y) * iq;
-            vq.z = (vq.z - d * q.z) * iq; vq.w = (vq.w - d * q.w) * iq;
-        }
+        project_bwd_view(cam, mu, sc, gs, q, fx, fy, H, W, vxy, vdep, vcon, packed != nullptr, g0, g1,
+                         vdep_packed, opac_logits != nullptr, logit, vmu, vs, vq, vlogit, vxy);
+        project_bwd_activations(flags, sc, q, qn, vs, vq);
     }
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -358,6 +386,85 @@ project_bwd_kernel(int N, const float* __restrict__ means, const float* __restri
         v_quats[i] = vq;
         if (v_opac_logits) v_opac_logits[i] = vlogit;
         if (v_xys_out) v_xys_out[i] = ok ? vxy : make_float2(0.f, 0.f);
+    }
+    __syncthreads();
+    block_store<3, TH>(v_means, s_buf, item0, N);
+    block_store<3, TH>(v_scales, s_buf + 3 * TH, item0, N);
+}
+
+// ---- data-parallel shard backward ------------------------------------------------
+// One rank owns a SHARD of the Gaussians and receives, from every rank/view v, blend-backward's
+// packed gradient rows of that shard (packed[v * view_stride + 3 i .. +2], already cleaned by
+// ts_dp_prepare: all-zero rows for Gaussians culled in view v).  This kernel runs projection-
+// backward for every view with that view's camera (cams[v]: 3x4 view | 4x4 full projection | fx,
+// fy) and writes the SUM over views times out_scale: the exchanged payload is the 48-byte packed
+// record per (view, Gaussian) instead of an all-reduce over the finished 236-byte gradients.
+constexpr int kCamFloats = 32;
+
+__global__ void __launch_bounds__(kProjThreads)
+project_bwd_views_kernel(int n_views, int N, const float* __restrict__ means,
+                         const float* __restrict__ scales, float gs, const float4* __restrict__ quats,
+                         const float* __restrict__ cams, int H, int W, int flags,
+                         const float4* __restrict__ packed, size_t view_stride4,
+                         const float* __restrict__ opac_logits, float out_scale,
+                         float* __restrict__ v_means, float* __restrict__ v_scales,
+                         float4* __restrict__ v_quats, float* __restrict__ v_opac_logits) {
+    constexpr int TH = kProjThreads;
+    __shared__ __align__(16) float s_buf[TH * 6];
+    const int item0 = blockIdx.x * TH;
+    const int tid = threadIdx.x;
+    block_load<3, TH>(means, s_buf, item0, N);
+    block_load<3, TH>(scales, s_buf + 3 * TH, item0, N);
+    __syncthreads();
+    const int i = item0 + tid;
+    const bool in = i < N;
+    float mu[3] = {0.f, 0.f, 1.f}, sc[3] = {1.f, 1.f, 1.f};
+    float4 q = make_float4(1.f, 0.f, 0.f, 0.f);
+    float logit = 0.f;
+    if (in) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            mu[k] = s_buf[3 * tid + k];
+            sc[k] = s_buf[3 * TH + 3 * tid + k];
+        }
+        q = __ldg(quats + i);
+        if (opac_logits) logit = __ldg(opac_logits + i);
+    }
+    const float qn = apply_activations(flags, sc, q);
+    __syncthreads();
+
+    float vmu[3] = {0.f, 0.f, 0.f}, vs[3] = {0.f, 0.f, 0.f};
+    float4 vq = make_float4(0.f, 0.f, 0.f, 0.f);
+    float vlogit = 0.f;
+    if (in) {
+        for (int v = 0; v < n_views; ++v) {
+            const float4* row = packed + (size_t)v * view_stride4 + 3 * (size_t)i;
+            const float4 g0 = __ldg(row), g1 = __ldg(row + 1);
+            const float vdep_packed = (flags & TS_PROJ_DEPTH_CH3) ? __ldg(reinterpret_cast<const float*>(row) + 11) : 0.f;
+            // culled in this view (ts_dp_prepare zeroed the row) or simply untouched: nothing to
+            // add, and the projection of a culled Gaussian must not be evaluated (0 * inf)
+            if (g0.x == 0.f && g0.y == 0.f && g0.z == 0.f && g0.w == 0.f && g1.x == 0.f && g1.y == 0.f &&
+                vdep_packed == 0.f)
+                continue;
+            const float* cv = cams + (size_t)v * kCamFloats;
+            ProjCam cam;
+            load_cam(cv, cv + 12, cam);
+            float vcon[3] = {0.f, 0.f, 0.f};
+            float2 vxy_unused;
+            project_bwd_view(cam, mu, sc, gs, q, __ldg(cv + 28), __ldg(cv + 29), H, W, make_float2(0.f, 0.f), 0.f,
+                             vcon, true, g0, g1, vdep_packed, opac_logits != nullptr, logit, vmu, vs, vq, vlogit,
+                             vxy_unused);
+        }
+        project_bwd_activations(flags, sc, q, qn, vs, vq);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        s_buf[3 * tid + k] = vmu[k] * out_scale;
+        s_buf[3 * TH + 3 * tid + k] = vs[k] * out_scale;
+    }
+    if (in) {
+        v_quats[i] = make_float4(vq.x * out_scale, vq.y * out_scale, vq.z * out_scale, vq.w * out_scale);
+        if (v_opac_logits) v_opac_logits[i] = vlogit * out_scale;
     }
     __syncthreads();
     block_store<3, TH>(v_means, s_buf, item0, N);
@@ -425,6 +532,30 @@ int ts_project_bwd(int N, const float* means3d, const float* scales, float glob_
         (const float4*)packed_grads, opacity_logits, v_means3d, v_scales, (float4*)v_quats,
         v_opacity_logits, (float2*)v_xys_out);
     TS_CHECK_LAUNCH("ts_project_bwd");
+    return TS_OK;
+}
+
+int ts_project_bwd_views(int n_views, int N, const float* means3d, const float* scales, float glob_scale,
+                         const float* quats, const float* cams, int img_height, int img_width, int flags,
+                         const float* packed_grads, int64_t view_stride_floats, const float* opacity_logits,
+                         float out_scale, float* v_means3d, float* v_scales, float* v_quats,
+                         float* v_opacity_logits, ts_stream_t stream) {
+    if (n_views < 1 || N < 0 || img_height <= 0 || img_width <= 0 || view_stride_floats < 0 ||
+        (view_stride_floats % 4) != 0)
+        return TS_ERR_INVALID;
+    if (N == 0) return TS_OK;
+    if (!means3d || !scales || !quats || !cams || !packed_grads || !v_means3d || !v_scales || !v_quats)
+        return TS_ERR_INVALID;
+    if (!ts::aligned16(means3d) || !ts::aligned16(scales) || !ts::aligned16(quats) ||
+        !ts::aligned16(packed_grads) || !ts::aligned16(v_means3d) || !ts::aligned16(v_scales) ||
+        !ts::aligned16(v_quats))
+        return TS_ERR_ALIGN;
+    int grid = (N + ts::kProjThreads - 1) / ts::kProjThreads;
+    ts::project_bwd_views_kernel<<<grid, ts::kProjThreads, 0, (cudaStream_t)stream>>>(
+        n_views, N, means3d, scales, glob_scale, (const float4*)quats, cams, img_height, img_width, flags,
+        (const float4*)packed_grads, (size_t)(view_stride_floats / 4), opacity_logits, out_scale, v_means3d,
+        v_scales, (float4*)v_quats, v_opacity_logits);
+    TS_CHECK_LAUNCH("ts_project_bwd_views");
     return TS_OK;
 }
 

@@ -362,6 +362,73 @@ sh_bwd_bulk_kernel(int N, int K, const float* __restrict__ means, const float* _
     }
 }
 
+// Data-parallel shard backward (see project_bwd_views_kernel): sums SH-backward over the views
+// whose packed colour cotangents (floats 8..10 of each 12-float packed row, clamp mask already
+// applied by ts_dp_prepare) arrived for this rank's shard.  The view direction of view v is
+// mean - cams[v][3,7,11] like TS_SH_DIRS_FROM_MEANS.  Rows are built in shared memory and leave
+// with a TMA bulk store (full, aligned blocks) exactly like sh_bwd_bulk_kernel.
+template <int DEG>
+__global__ void __launch_bounds__(kShThreads)
+sh_bwd_views_kernel(int n_views, int N, int K, const float* __restrict__ means,
+                    const float* __restrict__ cams, const float* __restrict__ packed, size_t view_stride,
+                    float out_scale, float* __restrict__ v_dc, float* __restrict__ v_rest) {
+    extern __shared__ __align__(128) float s_sh[];
+    constexpr int NB = (DEG + 1) * (DEG + 1);
+    const int R = (K - 1) * 3;
+    float* s_rest = s_sh;                            // [TH][R] dense, becomes v_rest rows
+    float* s_dc = s_rest + kShThreads * R;           // [TH*3]
+    const int item0 = blockIdx.x * kShThreads;
+    const int n_valid = min(kShThreads, N - item0);
+    const int tid = threadIdx.x;
+    if (tid < n_valid) {
+        const int i = item0 + tid;
+        const float mx = __ldg(means + 3 * (size_t)i), my = __ldg(means + 3 * (size_t)i + 1), mz = __ldg(means + 3 * (size_t)i + 2);
+        float acc[NB][3];
+#pragma unroll
+        for (int k = 0; k < NB; ++k) acc[k][0] = acc[k][1] = acc[k][2] = 0.f;
+        for (int v = 0; v < n_views; ++v) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(packed + (size_t)v * view_stride + 12 * (size_t)i + 8));
+            if (t.x == 0.f && t.y == 0.f && t.z == 0.f) continue;
+            const float* cv = cams + (size_t)v * 32;
+            float b[NB];
+            sh_basis<DEG>(mx - __ldg(cv + 3), my - __ldg(cv + 7), mz - __ldg(cv + 11), b);
+#pragma unroll
+            for (int k = 0; k < NB; ++k) {
+                acc[k][0] = fmaf(b[k], t.x, acc[k][0]);
+                acc[k][1] = fmaf(b[k], t.y, acc[k][1]);
+                acc[k][2] = fmaf(b[k], t.z, acc[k][2]);
+            }
+        }
+        s_dc[3 * tid] = acc[0][0] * out_scale; s_dc[3 * tid + 1] = acc[0][1] * out_scale; s_dc[3 * tid + 2] = acc[0][2] * out_scale;
+        float* c = s_rest + tid * R;
+#pragma unroll
+        for (int k = 1; k < NB; ++k) {
+            c[3 * (k - 1)] = acc[k][0] * out_scale;
+            c[3 * (k - 1) + 1] = acc[k][1] * out_scale;
+            c[3 * (k - 1) + 2] = acc[k][2] * out_scale;
+        }
+        for (int k = (NB - 1) * 3; k < R; ++k) c[k] = 0.f;   // bases above the active degree
+    }
+    const bool bulk = n_valid == kShThreads && R > 0 && ((size_t)kShThreads * R * 4) % 16 == 0 &&
+                      aligned_dev16(v_rest + (size_t)item0 * R) && aligned_dev16(v_dc + (size_t)item0 * 3);
+    if (bulk) {
+        fence_proxy_async();      // generic-proxy smem writes -> visible to the copy engine
+        __syncthreads();
+        if (tid == 0) {
+            bulk_s2g(v_rest + (size_t)item0 * R, s_rest, kShThreads * R * 4);
+            bulk_s2g(v_dc + (size_t)item0 * 3, s_dc, kShThreads * 3 * 4);
+            bulk_commit();
+            bulk_wait_read0();    // shared memory must outlive the reads
+        }
+    } else {
+        __syncthreads();
+        float* gr = v_rest + (size_t)item0 * R;
+        for (int i = tid; i < n_valid * R; i += kShThreads) gr[i] = s_rest[i];
+        float* gd = v_dc + (size_t)item0 * 3;
+        for (int i = tid; i < n_valid * 3; i += kShThreads) gd[i] = s_dc[i];
+    }
+}
+
 static inline int sh_stride(int K) { int k3 = K * 3; return (k3 & 1) ? k3 : k3 + 1; }
 
 }  // namespace ts
@@ -454,6 +521,32 @@ int ts_sh_bwd(int N, int degree, int K, const float* dirs, const float* viewmat,
     }
 #undef TS_LAUNCH_SH_BWD
     TS_CHECK_LAUNCH("ts_sh_bwd");
+    return TS_OK;
+}
+
+int ts_sh_bwd_views(int n_views, int N, int degree, int K, const float* means, const float* cams,
+                    const float* packed_grads, int64_t view_stride_floats, float out_scale, float* v_dc,
+                    float* v_rest, ts_stream_t stream) {
+    if (n_views < 1 || N < 0 || degree < 0 || degree > 4 || K < (degree + 1) * (degree + 1) || K > 25 ||
+        view_stride_floats < 0 || (view_stride_floats % 4) != 0)
+        return TS_ERR_INVALID;
+    if (N == 0) return TS_OK;
+    if (!means || !cams || !packed_grads || !v_dc || (K > 1 && !v_rest)) return TS_ERR_INVALID;
+    if (!ts::aligned16(packed_grads)) return TS_ERR_ALIGN;
+    int grid = (N + ts::kShThreads - 1) / ts::kShThreads;
+    size_t bsmem = sizeof(float) * ts::kShThreads * ((K - 1) * 3 + 3) + 16;
+    cudaStream_t st = (cudaStream_t)stream;
+#define TS_LAUNCH_SH_VIEWS(D) \
+    ts::sh_bwd_views_kernel<D><<<grid, ts::kShThreads, bsmem, st>>>(n_views, N, K, means, cams, packed_grads, (size_t)view_stride_floats, out_scale, v_dc, v_rest)
+    switch (degree) {
+        case 0: TS_LAUNCH_SH_VIEWS(0); break;
+        case 1: TS_LAUNCH_SH_VIEWS(1); break;
+        case 2: TS_LAUNCH_SH_VIEWS(2); break;
+        case 3: TS_LAUNCH_SH_VIEWS(3); break;
+        default: TS_LAUNCH_SH_VIEWS(4); break;
+    }
+#undef TS_LAUNCH_SH_VIEWS
+    TS_CHECK_LAUNCH("ts_sh_bwd_views");
     return TS_OK;
 }
 

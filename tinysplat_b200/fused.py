@@ -64,7 +64,7 @@ class XysSink:
 class _RenderFused(Function):
     @staticmethod
     def forward(ctx, means, log_scales, quats, opac_logits, colors_dc, colors_rest, view_dev,
-                fullproj_dev, fx, fy, width, height, sh_degree, bg4, cull_mode, clamp_rgb, sink):
+                fullproj_dev, fx, fy, width, height, sh_degree, bg4, cull_mode, clamp_rgb, sink, dp):
         _lib.require_cuda(means, log_scales, quats, opac_logits, colors_dc, colors_rest)
         lib = _lib.load()
         dev = means.device
@@ -82,6 +82,14 @@ class _RenderFused(Function):
         view_c, proj_c, bg_c = _lib.f32c(view_dev), _lib.f32c(fullproj_dev), _lib.f32c(bg4)
         pflags = _lib.PROJ_LOG_SCALES | _lib.PROJ_RAW_QUATS
         sflags = _lib.SH_DIRS_FROM_MEANS | _lib.SH_OFFSET_CLAMP
+
+        cams_all = None
+        if dp is not None:
+            # every rank needs every view's camera for the shard backward: 32 floats per rank,
+            # gathered here so the collective is long finished when backward starts
+            cam_row = torch.cat([view_c[:3].reshape(-1), proj_c.reshape(-1),
+                                 torch.tensor([float(fx), float(fy), 0.0, 0.0], **f32)])
+            cams_all = dp.gather_cameras(cam_row)
 
         xys = torch.empty(N, 2, **f32)
         depths = torch.empty(N, **f32)
@@ -143,6 +151,8 @@ class _RenderFused(Function):
         ctx.meta = (N, K, W, H, tx, ty, float(fx), float(fy), int(sh_degree), pflags, sflags,
                     tuple(opac_logits.shape), tuple(colors_dc.shape))
         ctx.sink = sink
+        ctx.dp = dp
+        ctx.cams_all = cams_all
         ctx.mark_non_differentiable(xys, depths, radii)
         ctx.set_materialize_grads(False)   # unused outputs (depth, T) arrive as None, not zeros
         # final_T is returned as is (alpha = 1 - T is the caller's one-liner if it wants it):
@@ -159,15 +169,24 @@ class _RenderFused(Function):
         st = _lib.stream_ptr(dev)
         f32 = dict(device=dev, dtype=torch.float32)
         if v_rgb is None and v_depth is None and v_T is None:
-            return (None,) * 17
+            return (None,) * 18
         v_alpha = -v_T if v_T is not None else None     # alpha = 1 - T
         v_rgb = _lib.f32c(v_rgb) if v_rgb is not None else None
         v_depth = _lib.f32c(v_depth) if v_depth is not None else None
         v_alpha = _lib.f32c(v_alpha) if v_alpha is not None else None
-        grads = torch.empty(N, lib.ts_grad_floats(), **f32)
+        dp = ctx.dp
+        n_rows = N
+        if dp is not None:
+            Ns = dp.shard_rows(N)
+            n_rows = dp.world * Ns                 # padded so that the all-to-all splits evenly
+        grads = torch.empty(n_rows, lib.ts_grad_floats(), **f32)
+        if n_rows > N:
+            grads[N:].zero_()
         _lib.call("ts_blend_bwd", N, 4, H, W, tx, ty, _lib.ptr(offsets), _lib.ptr(ids_sorted), _lib.ptr(recs),
                   _lib.ptr(bg_c), _lib.ptr(final_T), _lib.ptr(n_contrib), _lib.ptr(v_rgb), _lib.ptr(v_depth), 1,
                   _lib.ptr(v_alpha), _lib.ptr(grads), st)
+        if dp is not None:
+            return _RenderFused._backward_packed_exchange(ctx, grads, Ns, st)
         # colours first: the largest gradient (colors_rest) becomes available for its all-reduce
         # while projection-backward is still running (parallel.py)
         # all six parameter gradients are views of ONE flat buffer: autograd hands the views to
@@ -202,13 +221,59 @@ class _RenderFused(Function):
         if ctx.sink is not None:
             ctx.sink.deliver(v_xys)
         return (v_means, v_scales, v_quats, v_logit.reshape(opac_shape), v_dc.reshape(dc_shape), v_rest,
-                None, None, None, None, None, None, None, None, None, None, None)
+                None, None, None, None, None, None, None, None, None, None, None, None)
+
+    @staticmethod
+    def _backward_packed_exchange(ctx, grads, Ns, st):
+        """Data-parallel backward (parallel.PackedGradExchange): this rank's packed rows
+        go to the ranks that own the Gaussians (all-to-all, 48 B per Gaussian), the shard backward
+        runs for all views at once, the finished shard gradients are all-gathered.  Returns the
+        view-summed (or averaged) gradients, identical on every rank."""
+        (means_c, scales_c, quats_c, logit_c, view_c, proj_c, bg_c, radii, recs, offsets, ids_sorted,
+         final_T, n_contrib, mask) = ctx.saved_tensors
+        N, K, W, H, tx, ty, fx, fy, deg, pflags, sflags, opac_shape, dc_shape = ctx.meta
+        dp, cams_all = ctx.dp, ctx.cams_all
+        dev = means_c.device
+        f32 = dict(device=dev, dtype=torch.float32)
+        v_xys = torch.empty(N, 2, **f32)
+        _lib.call("ts_dp_prepare", N, _lib.ptr(radii), _lib.ptr(mask), _lib.ptr(recs), _lib.ptr(grads),
+                  _lib.ptr(v_xys), st)
+        recv = dp.all_to_all_rows(grads)                       # [world, Ns, 12]
+        s0 = dp.rank * Ns
+        ns = max(0, min(N, s0 + Ns) - s0)
+        alloc = torch.empty if ns == Ns else torch.zeros       # rows past N must be defined
+        sh_rest, sh_dc = alloc(Ns, K - 1, 3, **f32), alloc(Ns, 1, 3, **f32)
+        sh_means, sh_scales = alloc(Ns, 3, **f32), alloc(Ns, 3, **f32)
+        sh_quats, sh_logit = alloc(Ns, 4, **f32), alloc(Ns, **f32)
+        scale = dp.out_scale()
+        if ns > 0:
+            stride = Ns * 12
+            main = torch.cuda.current_stream(dev)
+            side = _side_stream(dev) if USE_SIDE_STREAM else main
+            if side is not main:
+                side.wait_stream(main)
+            with torch.cuda.stream(side):
+                _lib.call("ts_sh_bwd_views", dp.world, ns, deg, K, _lib.ptr(means_c[s0:s0 + ns]),
+                          _lib.ptr(cams_all), _lib.ptr(recv), stride, scale, _lib.ptr(sh_dc), _lib.ptr(sh_rest),
+                          side.cuda_stream)
+            _lib.call("ts_project_bwd_views", dp.world, ns, _lib.ptr(means_c[s0:s0 + ns]),
+                      _lib.ptr(scales_c[s0:s0 + ns]), 1.0, _lib.ptr(quats_c[s0:s0 + ns]), _lib.ptr(cams_all),
+                      H, W, pflags | _lib.PROJ_DEPTH_CH3, _lib.ptr(recv), stride, _lib.ptr(logit_c[s0:s0 + ns]),
+                      scale, _lib.ptr(sh_means), _lib.ptr(sh_scales), _lib.ptr(sh_quats), _lib.ptr(sh_logit), st)
+            if side is not main:
+                main.wait_stream(side)
+        full = dp.all_gather_shards([sh_rest, sh_dc, sh_means, sh_scales, sh_quats, sh_logit])
+        v_rest, v_dc, v_means, v_scales, v_quats, v_logit = (t[:N] for t in full)
+        if ctx.sink is not None:
+            ctx.sink.deliver(v_xys)
+        return (v_means, v_scales, v_quats, v_logit.reshape(opac_shape), v_dc.reshape(dc_shape), v_rest,
+                None, None, None, None, None, None, None, None, None, None, None, None)
 
 
 def render_fused(means: Tensor, log_scales: Tensor, quats: Tensor, opacity_logits: Tensor,
                  colors_dc: Tensor, colors_rest: Tensor, view_matrix: Tensor, full_proj: Tensor,
                  fx: float, fy: float, width: int, height: int, sh_degree: int, background: Tensor,
-                 cull_mode: int = 1, clamp_rgb: bool = True
+                 cull_mode: int = 1, clamp_rgb: bool = True, grad_exchange=None
                  ) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
     """Fused equivalent of project -> SH(+0.5, clamp) -> rasterise RGB -> rasterise depth.
 
@@ -216,12 +281,14 @@ def render_fused(means: Tensor, log_scales: Tensor, quats: Tensor, opacity_logit
     matrices (view 4x4, full projection 4x4).  Returns (rgb[H,W,3] (clamped to <= 1 like the
     adapter's output [REF rasterize.py:45] unless clamp_rgb=False), depth[H,W],
     final_T[H,W] (alpha = 1 - final_T), xys[N,2], depths[N], radii[N]).  `xys.grad` is populated
-    by backward."""
+    by backward.  grad_exchange: a tinysplat_b200.parallel.PackedGradExchange — backward then
+    exchanges packed gradient rows between the data-parallel ranks and returns the gradients
+    already reduced over all ranks' views (every rank must call with the same N and image size)."""
     sink = XysSink()
     bg = background.to(means.device).float()
     bg4 = torch.cat([bg, bg[:1]])       # depth is composited over background[0] [REF rasterize.py:48-51]
     out = _RenderFused.apply(means, log_scales, quats, opacity_logits, colors_dc, colors_rest,
                              view_matrix, full_proj, fx, fy, width, height, sh_degree, bg4,
-                             cull_mode, clamp_rgb, sink)
+                             cull_mode, clamp_rgb, sink, grad_exchange)
     sink.attach(out[3])
     return out

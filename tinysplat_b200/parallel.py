@@ -9,6 +9,12 @@ the largest payload (colors_rest, 76% of the bytes, ready right after SH-backwar
 NVLink while projection-backward is still running.  Forward-only rendering needs no
 collective at all (replicas only).
 
+Second exchange strategy (`PackedGradExchange`, used through the fused node): instead of
+all-reducing the finished gradients (236 B per Gaussian), ranks exchange blend-backward's packed
+rows (48 B per view and Gaussian) with one all-to-all, every rank runs projection-/SH-backward
+for ALL views on its own shard of the Gaussians, and the shard results are all-gathered: 42 MB +
+206 MB per rank instead of the 413 MB a ring all-reduce of 236 MB moves at 8 ranks.
+
 The densification statistic is the per-view norm of d loss / d xy summed over views
 [REF tinysplat/splatting/model_gaussian.py:130-132] — NOT the norm of the reduced gradient —
 so it gets its own [N] all-reduce (`reduce_densify_stat`)."""
@@ -107,15 +113,83 @@ class GradientAllReducer:
         self._handles.clear()
 
 
+class PackedGradExchange:
+    """Collectives of the packed-row gradient exchange (see module docstring); the shard kernels
+    are launched by the fused autograd node (tinysplat_b200.fused), which receives this object.
+
+    world ranks, rank r owns Gaussians [r*Ns, (r+1)*Ns) with Ns = shard_rows(N) (a multiple of
+    128 so that every shard slice of every parameter stays 16-byte aligned)."""
+
+    CAM_FLOATS = 32      # include/tinysplat_b200.h: 3x4 view | 4x4 full projection | fx fy | pad
+
+    def __init__(self, process_group=None, average: bool = True):
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("PackedGradExchange needs an initialised process group")
+        self.group = process_group
+        self.world = dist.get_world_size(process_group)
+        self.rank = dist.get_rank(process_group)
+        self.average = average
+        self._coalesce = dist.get_backend(process_group) == "nccl"
+        self.last_bytes_sent = 0
+
+    def shard_rows(self, n_gaussians: int) -> int:
+        per = -(-n_gaussians // self.world)
+        return max(128, (per + 127) // 128 * 128)
+
+    def out_scale(self) -> float:
+        return 1.0 / self.world if self.average else 1.0
+
+    def gather_cameras(self, cam_row: Tensor) -> Tensor:
+        """cam_row[32] of this rank's view -> [world, 32] with every rank's camera."""
+        out = torch.empty(self.world * cam_row.numel(), dtype=cam_row.dtype, device=cam_row.device)
+        dist.all_gather_into_tensor(out, cam_row.contiguous().view(-1), group=self.group)
+        return out.view(self.world, cam_row.numel())
+
+    def all_to_all_rows(self, send: Tensor) -> Tensor:
+        """send[world*Ns, F] (row block j goes to rank j) -> recv[world, Ns, F] (block i came from
+        rank i: view i's rows of this rank's shard)."""
+        rows = send.shape[0] // self.world
+        recv = torch.empty(self.world, rows, send.shape[1], dtype=send.dtype, device=send.device)
+        dist.all_to_all_single(recv, send, group=self.group)
+        self.last_bytes_sent = send.numel() * send.element_size() * (self.world - 1) // self.world
+        return recv
+
+    def all_gather_shards(self, shards: List[Tensor]) -> List[Tensor]:
+        """[Ns, ...] per parameter -> [world*Ns, ...] per parameter, one NCCL group call."""
+        outs = [torch.empty((self.world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+                for t in shards]
+        if self._coalesce:
+            with dist._coalescing_manager(group=self.group, device=shards[0].device, async_ops=False):
+                for o, t in zip(outs, shards):
+                    dist.all_gather_into_tensor(o, t, group=self.group)
+        else:
+            for o, t in zip(outs, shards):
+                dist.all_gather_into_tensor(o, t, group=self.group)
+        self.last_bytes_sent += sum(t.numel() * t.element_size() for t in shards) * (self.world - 1)
+        return outs
+
+
 class DataParallelRenderer:
     """rank r renders cameras[r::world] with `rasterizer`, backpropagates `loss_fn`, and leaves
     the view-averaged gradient in every parameter's .grad on every rank."""
 
     def __init__(self, rasterizer: Callable, params: Iterable[Tensor], process_group=None,
-                 average: bool = True, overlap: bool = True):
+                 average: bool = True, overlap: bool = True, strategy: str = "allreduce"):
+        """strategy: "allreduce" (any rasterizer) or "packed" (the fused pipeline of
+        tinysplat_b200.rasterizer.GaussianRasterizer: gradients leave backward already reduced)."""
+        if strategy not in ("allreduce", "packed"):
+            raise ValueError("strategy must be 'allreduce' or 'packed'")
         self.rasterizer = rasterizer
-        self.reducer = GradientAllReducer(params, process_group, average, overlap)
         self.group = process_group
+        self.strategy = strategy
+        enabled = dist.is_available() and dist.is_initialized() and dist.get_world_size(process_group) > 1
+        if strategy == "packed" and enabled:
+            if getattr(rasterizer, "pipeline", None) != "fused":
+                raise ValueError("strategy='packed' needs GaussianRasterizer(pipeline='fused')")
+            rasterizer.grad_exchange = PackedGradExchange(process_group, average)
+            self.reducer = GradientAllReducer([], process_group, average, overlap=False)
+        else:
+            self.reducer = GradientAllReducer(params, process_group, average, overlap)
 
     def step(self, camera, dims, sh_degree: int, loss_fn: Callable[[Tensor, dict], Tensor]):
         img, extras = self.rasterizer(camera, dims, sh_degree)

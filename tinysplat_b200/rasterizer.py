@@ -45,6 +45,9 @@ class GaussianRasterizer:
         self.model = model
         self.device = torch.device(device)
         self.pipeline = pipeline
+        # data-parallel training: a tinysplat_b200.parallel.PackedGradExchange makes the fused
+        # node's backward exchange packed gradient rows and return already-reduced gradients
+        self.grad_exchange = None
 
     # -- shared front end: projection + view-dependent colour ---------------------------------
     def _project(self, camera, width: int, height: int):
@@ -69,7 +72,8 @@ class GaussianRasterizer:
         mats = torch.stack([view, camera.proj_matrix.float() @ view]).to(self.device, non_blocking=True)
         rgb, depth_img, _, xys, _, radii = render_fused(
             m.means, m.scales, m.quats, m.opacities, m.colors_dc, m.colors_rest, mats[0], mats[1],
-            camera.f_x, camera.f_y, width, height, sh_degree, m.background)
+            camera.f_x, camera.f_y, width, height, sh_degree, m.background,
+            grad_exchange=self.grad_exchange if torch.is_grad_enabled() else None)
         extras: Dict = {"depth": depth_img, "radii": radii, "xys": xys,
                         "camera": {"height": camera.height, "width": camera.width}}
         return rgb, extras      # already clamped to <= 1 inside the blend kernel
