@@ -49,6 +49,9 @@ def parse_args():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--pipeline", default="fused", choices=["fused", "reference", "unfused4"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--grad-exchange", default="auto", choices=["auto", "allreduce", "packed"],
+                    help="N > 1: how the per-Gaussian gradients are reduced over the ranks' views "
+                         "(auto = time both strategies during warm-up, keep the faster)")
     ap.add_argument("--cpu-window", type=int, default=8, help="CPU sample: window edge in tiles")
     return ap.parse_args()
 
@@ -246,7 +249,7 @@ def run_reference(args):
 def run_ours(args):
     import torch.distributed as dist
     from tinysplat_b200 import _lib, synthetic, rasterize as rz
-    from tinysplat_b200.parallel import GradientAllReducer
+    from tinysplat_b200.parallel import GradientAllReducer, PackedGradExchange
     from tinysplat_b200.rasterizer import GaussianRasterizer, ParamModel
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -267,6 +270,22 @@ def run_ours(args):
     model = ParamModel(sc, dev, deg, requires_grad=not fwd_only)
     rast = GaussianRasterizer(model, None, dev, args.pipeline)
     reducer = GradientAllReducer(model.parameters(), average=True, overlap=True) if not fwd_only else None
+    exchange = {"name": "allreduce", "probe_ms": None}
+
+    def set_exchange(name: str):
+        """allreduce: NCCL all-reduce of the finished gradients (one flat 236 B/Gaussian span);
+        packed: all-to-all of blend-backward's packed rows + shard backward + all-gather (only the
+        fused pipeline; tinysplat_b200.parallel.PackedGradExchange)."""
+        nonlocal reducer
+        if reducer is not None:
+            reducer.close()
+        if name == "packed":
+            rast.grad_exchange = PackedGradExchange(average=True)
+            reducer = GradientAllReducer([], average=True, overlap=False)
+        else:
+            rast.grad_exchange = None
+            reducer = GradientAllReducer(model.parameters(), average=True, overlap=True)
+        exchange["name"] = name
     g = torch.Generator().manual_seed(100 + rank)
     gt_host = torch.rand(H, W, 3, generator=g).pin_memory()
     gt_dev = gt_host.to(dev)
@@ -328,6 +347,20 @@ def run_ours(args):
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item(), t0, t1
+
+    # ---- N > 1: pick the gradient-exchange strategy (untimed, before the warm-up proper) ------
+    if world > 1 and not fwd_only:
+        choice = args.grad_exchange if args.pipeline == "fused" else "allreduce"
+        if choice == "auto":
+            probe = {}
+            for name in ("allreduce", "packed"):
+                set_exchange(name)
+                for i in range(3):
+                    path_step(i)
+                probe[name] = timed(path_step, 5, 3)[0] / 5      # max over ranks: same on every rank
+            choice = min(probe, key=probe.get)
+            exchange["probe_ms"] = probe
+        set_exchange(choice)
 
     # ---- device-resident arm: `value` -------------------------------------------------------
     for i in range(Wm):
@@ -453,10 +486,16 @@ def run_ours(args):
                    "mode": "fwd" if fwd_only else "fwd+bwd", "depth_loss_weight": depth_w,
                    "value_step": "adapter forward (RGB+depth) + backward from fixed cotangents (SURVEY 8d)",
                    "e2e_step": "H2D target image + camera, adapter forward, L1 loss, backward, loss.item()",
-                   "parallelism": f"dp{world} over cameras, replica per GPU, NCCL grad all-reduce"
+                   "parallelism": (f"dp{world} over cameras, replica per GPU, "
+                                   + ("NCCL all-reduce of the gradients" if exchange["name"] == "allreduce" else
+                                      "packed-row exchange: NCCL all-to-all + shard backward + all-gather"))
                    if world > 1 and not fwd_only else ("replicas only" if world > 1 else "single GPU"),
+                   "grad_exchange": exchange["name"] if (world > 1 and not fwd_only) else None,
+                   "grad_exchange_probe_ms": exchange["probe_ms"],
                    "grad_allreduce_collectives_per_step": (reducer.last_num_collectives if reducer else 0),
                    "grad_allreduce_bytes": (reducer.payload_bytes() if (reducer and world > 1) else 0),
+                   "grad_exchange_bytes_sent_per_rank": (rast.grad_exchange.last_bytes_sent
+                                                         if rast.grad_exchange is not None else None),
                    "l2": "inputs larger than L2: 236 B/Gaussian parameters + 48 B records + image buffers "
                          "> 126 MB; a different camera every step"},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
