@@ -511,6 +511,9 @@ class _LoopbackExchange:
     def out_scale(self):
         return 1.0
 
+    def buffer(self, key, shape, dtype, device, zero=False, tag=None):
+        return (torch.zeros if zero else torch.empty)(shape, dtype=dtype, device=device)
+
     def gather_cameras(self, row):
         self.cams.append(row.clone())
         return row.view(1, -1)

@@ -179,9 +179,11 @@ class _RenderFused(Function):
         if dp is not None:
             Ns = dp.shard_rows(N)
             n_rows = dp.world * Ns                 # padded so that the all-to-all splits evenly
-        grads = torch.empty(n_rows, lib.ts_grad_floats(), **f32)
-        if n_rows > N:
-            grads[N:].zero_()
+        if dp is not None:
+            # persistent, zero-initialised: blend-backward clears rows [0, N), the pad stays zero
+            grads = dp.buffer("send", (n_rows, lib.ts_grad_floats()), torch.float32, dev, zero=True, tag=N)
+        else:
+            grads = torch.empty(n_rows, lib.ts_grad_floats(), **f32)
         _lib.call("ts_blend_bwd", N, 4, H, W, tx, ty, _lib.ptr(offsets), _lib.ptr(ids_sorted), _lib.ptr(recs),
                   _lib.ptr(bg_c), _lib.ptr(final_T), _lib.ptr(n_contrib), _lib.ptr(v_rgb), _lib.ptr(v_depth), 1,
                   _lib.ptr(v_alpha), _lib.ptr(grads), st)
@@ -241,10 +243,11 @@ class _RenderFused(Function):
         recv = dp.all_to_all_rows(grads)                       # [world, Ns, 12]
         s0 = dp.rank * Ns
         ns = max(0, min(N, s0 + Ns) - s0)
-        alloc = torch.empty if ns == Ns else torch.zeros       # rows past N must be defined
-        sh_rest, sh_dc = alloc(Ns, K - 1, 3, **f32), alloc(Ns, 1, 3, **f32)
-        sh_means, sh_scales = alloc(Ns, 3, **f32), alloc(Ns, 3, **f32)
-        sh_quats, sh_logit = alloc(Ns, 4, **f32), alloc(Ns, **f32)
+        # persistent shard buffers (see PackedGradExchange.buffer), zeroed once: the kernels write
+        # rows [0, ns), rows past N stay zero
+        shapes = [(Ns, K - 1, 3), (Ns, 1, 3), (Ns, 3), (Ns, 3), (Ns, 4), (Ns,)]
+        sh_rest, sh_dc, sh_means, sh_scales, sh_quats, sh_logit = (
+            dp.buffer(("shard", i), shp, torch.float32, dev, zero=True, tag=ns) for i, shp in enumerate(shapes))
         scale = dp.out_scale()
         if ns > 0:
             stride = Ns * 12
@@ -263,7 +266,8 @@ class _RenderFused(Function):
             if side is not main:
                 main.wait_stream(side)
         full = dp.all_gather_shards([sh_rest, sh_dc, sh_means, sh_scales, sh_quats, sh_logit])
-        v_rest, v_dc, v_means, v_scales, v_quats, v_logit = (t[:N] for t in full)
+        # the gathered buffers are reused by the next step: hand autograd its own copies
+        v_rest, v_dc, v_means, v_scales, v_quats, v_logit = (t[:N].clone() for t in full)
         if ctx.sink is not None:
             ctx.sink.deliver(v_xys)
         return (v_means, v_scales, v_quats, v_logit.reshape(opac_shape), v_dc.reshape(dc_shape), v_rest,
