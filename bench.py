@@ -136,10 +136,11 @@ class ClockSampler:
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the `ncu --set full` capture of this
-# same command summarised in profiles/r1_ncu_full_all_kernels.txt (default workload, fused pipeline)
+# same command summarised in profiles/r1_ncu_full_all_kernels.txt and, for the blend kernels of the
+# current default (grouped backward), profiles/r1c_ncu_blend_mode4.txt (default workload, fused pipeline)
 NCU_TRAFFIC = {
     "synthetic_1M_1080p": {
-        "ts_blend_bwd": (176.53 + 25.05) * 1e6, "ts_blend_fwd": (62.78 + 21.66) * 1e6,
+        "ts_blend_bwd": (161.48 + 17.17) * 1e6, "ts_blend_fwd": (59.57 + 21.81) * 1e6,
         "ts_sh_fwd": (228.81 + 25.18) * 1e6, "ts_sh_bwd": (61.03 + 134.51) * 1e6,
         "ts_project_fwd": (61.73 + 24.12) * 1e6, "ts_project_bwd": (95.97 + 23.53) * 1e6,
         "ts_bin_emit": (56.04 + 1.25) * 1e6, "ts_bin_sort": (16.43 + 0.0) * 1e6,
