@@ -57,7 +57,7 @@ struct BlockSync {
 };
 
 struct State {
-    dim3 tid, bid;
+    dim3 tid, bid, gdim;
     int nthreads = 0, cur = 0, alive = 0;
     ucontext_t sched;
     ucontext_t ctx[kMaxThreads];
@@ -83,6 +83,14 @@ inline void fiber_entry() {
     s.done[s.cur] = true;
     s.alive--;
     s.progress++;
+    // like the hardware, threads that have exited no longer take part in block barriers
+    BlockSync& b = s.bs;
+    if (b.arrived > 0 && b.arrived >= s.alive) {
+        b.out[b.gen & 1] = b.acc_and;
+        b.acc_and = 1;
+        b.arrived = 0;
+        b.gen++;
+    }
     swapcontext(&s.ctx[s.cur], &s.sched);
 }
 
@@ -93,6 +101,7 @@ inline int launch(dim3 grid, int nthreads, std::function<void()> body) {
     if (!s.stacks) s.stacks = (char*)malloc(kStack * kMaxThreads);
     s.body = body;
     s.nthreads = nthreads;
+    s.gdim = grid;
     for (unsigned by = 0; by < grid.y; ++by)
         for (unsigned bx = 0; bx < grid.x; ++bx) {
             s.bid = dim3(bx, by, 0);
@@ -147,7 +156,7 @@ inline int block_barrier(int pred) {
     BlockSync& b = s.bs;
     const int g = b.gen;
     b.acc_and = b.acc_and && pred;
-    if (++b.arrived == s.nthreads) {
+    if (++b.arrived >= s.alive) {
         b.out[g & 1] = b.acc_and;
         b.acc_and = 1;
         b.arrived = 0;
@@ -163,6 +172,7 @@ inline int block_barrier(int pred) {
 
 #define threadIdx (ts_emu::st().tid)
 #define blockIdx (ts_emu::st().bid)
+#define gridDim (ts_emu::st().gdim)
 
 static inline void emu_require_full(unsigned mask) {
     if (mask != 0xffffffffu) { fprintf(stderr, "[ts_emu] partial-mask collective not supported\n"); abort(); }
@@ -189,6 +199,24 @@ static inline float __shfl_xor_sync(unsigned mask, float x, int d) {
     memcpy(&f, &r, 4);
     return f;
 }
+static inline uint64_t __shfl_xor_sync(unsigned mask, uint64_t x, int d) {
+    // two 32-bit exchanges, like the hardware
+    emu_require_full(mask);
+    const int lane = ts_emu::st().cur & 31;
+    const uint32_t lo = ts_emu::warp_exchange((uint32_t)x)[lane ^ d];
+    const uint32_t hi = ts_emu::warp_exchange((uint32_t)(x >> 32))[lane ^ d];
+    return ((uint64_t)hi << 32) | lo;
+}
+static inline int __shfl_up_sync(unsigned mask, int x, int d) {
+    emu_require_full(mask);
+    const int lane = ts_emu::st().cur & 31;
+    const uint32_t* v = ts_emu::warp_exchange((uint32_t)x);
+    return lane >= d ? (int)v[lane - d] : x;
+}
+static inline void __threadfence() {}
+// glibc declares (but does not export) __logf/__expf: map the CUDA fast-math names with macros
+#define __logf(x) logf(x)
+#define __expf(x) expf(x)
 static inline int __shfl_xor_sync(unsigned mask, int x, int d) {
     emu_require_full(mask);
     const uint32_t* v = ts_emu::warp_exchange((uint32_t)x);

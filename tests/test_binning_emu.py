@@ -1,0 +1,132 @@
+"""Kernel-logic parity WITHOUT a GPU for K3 (tinysplat_b200/csrc/binning.cu: tile count -> look-back
+scan -> emit -> per-tile sort), compiled as host code on the fiber SIMT emulator in tests/emu and
+compared with the oracle's bin_and_sort.  Integer / index work: bit-exact."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from oracle import gsplat_oracle as go
+from tinysplat_b200 import synthetic
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+EMU = os.path.join(HERE, "emu")
+LIB = os.path.join(EMU, "_build", "libbinning_emu.so")
+CSRC = os.path.join(HERE, "..", "tinysplat_b200", "csrc")
+
+
+@pytest.fixture(scope="module")
+def emu():
+    srcs = [os.path.join(EMU, f) for f in ("binning_emu.cpp", "ts_emu.h")] + \
+           [os.path.join(CSRC, f) for f in ("binning.cu", "ts_binning.cuh", "ts_common.cuh")]
+    if not os.path.exists(LIB) or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in srcs):
+        os.makedirs(os.path.dirname(LIB), exist_ok=True)
+        subprocess.run(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-I" + EMU,
+                        "-o", LIB, srcs[0]], check=True)
+    lib = C.CDLL(LIB)
+    p, i = C.c_void_p, C.c_int
+    lib.emu_bin_count.argtypes = [i, i, p, p, p, p, p, i, i, i, i, p, p]
+    lib.emu_bin_scan.argtypes = [i, p, p, p, i]
+    lib.emu_bin_emit.argtypes = [i, p, p, p, i, i, i, p, p]
+    lib.emu_bin_sort.argtypes = [i, p, p, p, i, i, p, p]
+    return lib
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _bin(emu, xys, depths, radii, conics, opac, W, H, cull):
+    n = xys.shape[0]
+    tx, ty = (W + 15) // 16, (H + 15) // 16
+    T = tx * ty
+    stride = emu.emu_bin_counter_stride()
+    xs = np.ascontiguousarray(xys.numpy().astype(np.float32))
+    dp = np.ascontiguousarray(depths.numpy().astype(np.float32))
+    rd = np.ascontiguousarray(radii.numpy().astype(np.int32))
+    cn = np.ascontiguousarray(conics.numpy().astype(np.float32))
+    op = np.ascontiguousarray(opac.reshape(-1).numpy().astype(np.float32))
+    col = np.zeros((n, 3), dtype=np.float32)
+    recs = np.zeros((n, 12), dtype=np.float32)
+    counts = np.full(T * stride, -1, dtype=np.int32)
+    assert emu.emu_bin_count(n, 3, _ptr(xs), _ptr(rd), _ptr(cn), _ptr(op), _ptr(col), tx, ty, cull, 0,
+                             _ptr(recs), _ptr(counts)) == 0
+    per_tile = counts[::stride].copy()
+    offsets = np.zeros(T + 1, dtype=np.int32)
+    stats = np.zeros(emu.emu_bin_scan_work_ints(), dtype=np.int32)
+    assert emu.emu_bin_scan(T, _ptr(counts), _ptr(offsets), _ptr(stats), emu.emu_bin_smem_sort_cap()) == 0
+    M, max_count, n_big = int(stats[0]), int(stats[1]), int(stats[2])
+    assert np.array_equal(offsets[1:], np.cumsum(per_tile)) and offsets[0] == 0 and M == per_tile.sum()
+    assert max_count == (per_tile.max() if T else 0)
+    assert np.array_equal(counts[::stride], offsets[:-1])      # counters rewritten as emit cursors
+    keys = np.zeros(max(M, 1), dtype=np.uint64)
+    ids = np.full(max(M, 1), -1, dtype=np.int32)
+    assert emu.emu_bin_emit(n, _ptr(dp), _ptr(rd), _ptr(recs), tx, ty, cull, _ptr(counts), _ptr(keys)) == 0
+    assert np.array_equal(counts[::stride], offsets[1:])       # every cursor ends at the next offset
+    scratch = cnt = None
+    if n_big:
+        P = 1 << (max_count - 1).bit_length()
+        scratch, cnt = np.zeros(n_big * P, dtype=np.uint64), np.zeros(1, dtype=np.int32)
+    assert emu.emu_bin_sort(T, _ptr(offsets), _ptr(keys), _ptr(ids), max_count, n_big, _ptr(scratch), _ptr(cnt)) == 0
+    return offsets, ids[:M], recs, (tx, ty)
+
+
+def _project(n, W, H, seed, radius):
+    cam = synthetic.make_camera(W, H)
+    sc = synthetic.make_scene(n, W, H, seed=seed, mean_radius_px=radius)
+    tb = ((W + 15) // 16, (H + 15) // 16, 1)
+    with torch.no_grad():
+        xys, depths, radii, conics, ntiles, _ = oracle.project_gaussians(
+            sc["means"], sc["scales"].exp(), 1.0, torch.nn.functional.normalize(sc["quats"], dim=-1),
+            cam.view_matrix[:3], cam.proj_matrix @ cam.view_matrix, cam.f_x, cam.f_y, W / 2, H / 2, H, W, tb)
+    return xys, depths, radii, conics, torch.sigmoid(sc["opacities"]), tb
+
+
+@pytest.mark.parametrize("n,W,H,radius", [
+    (600, 80, 56, 5.0),       # ordinary: warp-per-tile register sort, ragged tile grid
+    (900, 16, 16, 3.0),       # one tile, 513..2048 entries: CTA shared-memory sort, first size class
+    (2600, 16, 16, 3.0),      # one tile, > 2048 entries: second size class
+    (40, 128, 96, 60.0),      # screen-filling Gaussians: warp-cooperative tile expansion
+])
+def test_binning_kernels_reproduce_the_oracle_lists(emu, n, W, H, radius):
+    xys, depths, radii, conics, opac, tb = _project(n, W, H, 11, radius)
+    offsets, ids, recs, _ = _bin(emu, xys, depths, radii, conics, opac, W, H, cull=0)
+    tile, gid = go.bin_and_sort(xys, depths, radii, tb)
+    T = tb[0] * tb[1]
+    want_off = np.zeros(T + 1, dtype=np.int64)
+    want_off[1:] = np.cumsum(np.bincount(tile.numpy(), minlength=T))
+    assert np.array_equal(offsets, want_off.astype(np.int32))
+    assert np.array_equal(ids, gid.numpy().astype(np.int32))       # same order: depth, then id
+
+
+def test_footprint_culling_keeps_a_sorted_superset_of_the_lit_pairs(emu):
+    n, W, H = 500, 96, 64
+    xys, depths, radii, conics, opac, tb = _project(n, W, H, 4, 6.0)
+    opac[::5] = 0.001                                  # below 1/255: never emitted
+    off0, ids0, _, _ = _bin(emu, xys, depths, radii, conics, opac, W, H, cull=0)
+    off1, ids1, _, _ = _bin(emu, xys, depths, radii, conics, opac, W, H, cull=1)
+    assert off1[-1] < off0[-1]
+    T = tb[0] * tb[1]
+    d = depths.numpy()
+    for t in range(T):
+        full = ids0[off0[t]:off0[t + 1]]
+        kept = ids1[off1[t]:off1[t + 1]]
+        assert set(kept.tolist()) <= set(full.tolist())
+        assert np.array_equal(kept, np.array([g for g in full if g in set(kept.tolist())], dtype=np.int32))
+        # every dropped pair is really dark in this tile: alpha < 1/255 at all of its pixel centres
+        ty_, tx_ = divmod(t, tb[0])
+        px = tx_ * 16 + np.arange(16) + 0.5
+        py = ty_ * 16 + np.arange(16) + 0.5
+        for g in set(full.tolist()) - set(kept.tolist()):
+            dx = xys[g, 0].item() - px[None, :]
+            dy = xys[g, 1].item() - py[:, None]
+            a, b, c = conics[g].tolist()
+            sig = 0.5 * (a * dx * dx + c * dy * dy) + b * dx * dy
+            alpha = opac[g].item() * np.exp(-sig)
+            assert (alpha[sig >= 0] < 1.0 / 255.0).all(), (t, g)
+    assert not np.isin(ids1, np.arange(0, n, 5)).any()
+    assert d is not None

@@ -226,7 +226,11 @@ __device__ __forceinline__ void bitonic_sort(Ptr s, int P, int nthreads) {
 __global__ void __launch_bounds__(kSortThreads)
 bin_sort_kernel(int T, const int32_t* __restrict__ offsets, const uint64_t* __restrict__ keys,
                 int32_t* __restrict__ ids_sorted, int lo_count, int hi_count) {
+#ifdef TS_HOST_EMU
+    __shared__ __align__(16) uint64_t s_keys[kSmemSortCap];     // emulator: static storage
+#else
     extern __shared__ __align__(16) uint64_t s_keys[];
+#endif
     const int tile = blockIdx.x;
     const int start = __ldg(offsets + tile);
     const int n = __ldg(offsets + tile + 1) - start;
@@ -359,6 +363,7 @@ bin_sort_big_kernel(int T, const int32_t* __restrict__ offsets, const uint64_t* 
 
 }  // namespace ts
 
+#ifndef TS_HOST_EMU
 extern "C" {
 
 int ts_bin_smem_sort_cap(void) { return ts::kSmemSortCap; }
@@ -462,3 +467,4 @@ int ts_bin_sort(int num_tiles, const int32_t* tile_offsets, uint64_t* keys, int3
 }
 
 }  // extern "C"
+#endif  // !TS_HOST_EMU
