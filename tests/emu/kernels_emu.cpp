@@ -1,0 +1,307 @@
+// Compiles EVERY hot-path kernel of tinysplat_b200/csrc (project.cu, sh.cu, binning.cu, blend.cu,
+// blend_group.cu) unchanged as host code on the fiber SIMT emulator (ts_emu.h) and exposes
+//   * the blend kernels and the binning stages with the argument lists of their C-ABI entry points
+//     (host pointers instead of device pointers; the launch logic mirrors those entry points), and
+//   * emu_render_fused: the whole fused forward + backward of tinysplat_b200/fused.py.
+// TEST INFRASTRUCTURE ONLY (TS_HOST_EMU is never defined in the product build).
+#define TS_HOST_EMU 1
+#include "../../tinysplat_b200/csrc/project.cu"
+#include "../../tinysplat_b200/csrc/sh.cu"
+#include "../../tinysplat_b200/csrc/binning.cu"
+#include "../../tinysplat_b200/csrc/blend.cu"
+#include "../../tinysplat_b200/csrc/blend_group.cu"
+
+#include <vector>
+
+namespace {
+template <int CH>
+int run_fwd(int H, int W, int tx, int ty, const int32_t* off, const int32_t* ids, const float* recs,
+            const float* bg, float* out_img, float* out_ch3, float* final_T, int32_t* n_contrib, int clamp) {
+    return ts_emu::launch(dim3(tx, ty), ts::kBlendThreads, [=]() {
+        ts::blend_fwd_kernel<CH>(H, W, tx, off, ids, (const float4*)recs, bg, out_img, out_ch3, final_T,
+                                 n_contrib, clamp);
+    });
+}
+template <int CH, int GCH>
+int run_bwd(int grouped, int H, int W, int tx, int ty, const int32_t* off, const int32_t* ids, const float* recs,
+            const float* bg, const float* final_T, const int32_t* n_contrib, const float* v_img,
+            const float* v_ch3, int split, const float* v_alpha, float* grads) {
+    if (grouped)
+        return ts_emu::launch(dim3(tx, ty), ts::kGThreads, [=]() {
+            ts::blend_bwd_group_kernel<CH, GCH>(H, W, tx, off, ids, (const float4*)recs, bg, final_T, n_contrib,
+                                                v_img, v_ch3, split, v_alpha, (float4*)grads);
+        });
+    return ts_emu::launch(dim3(tx, ty), ts::kBlendThreads, [=]() {
+        ts::blend_bwd_kernel<CH, GCH>(H, W, tx, off, ids, (const float4*)recs, bg, final_T, n_contrib,
+                                      v_img, v_ch3, split, v_alpha, (float4*)grads);
+    });
+}
+}  // namespace
+
+extern "C" {
+
+int emu_blend_fwd(int CH, int H, int W, int tx, int ty, const int32_t* off, const int32_t* ids,
+                  const float* recs, const float* bg, float* out_img, float* out_ch3, float* final_T,
+                  int32_t* n_contrib, int clamp) {
+    switch (CH) {
+        case 1: return run_fwd<1>(H, W, tx, ty, off, ids, recs, bg, out_img, out_ch3, final_T, n_contrib, clamp);
+        case 2: return run_fwd<2>(H, W, tx, ty, off, ids, recs, bg, out_img, out_ch3, final_T, n_contrib, clamp);
+        case 3: return run_fwd<3>(H, W, tx, ty, off, ids, recs, bg, out_img, out_ch3, final_T, n_contrib, clamp);
+        default: return run_fwd<4>(H, W, tx, ty, off, ids, recs, bg, out_img, out_ch3, final_T, n_contrib, clamp);
+    }
+}
+
+// grouped: 0 = first-generation backward (blend.cu), 1 = grouped backward (blend_group.cu)
+int emu_blend_bwd(int N, int CH, int H, int W, int tx, int ty, const int32_t* off, const int32_t* ids,
+                  const float* recs, const float* bg, const float* final_T, const int32_t* n_contrib,
+                  const float* v_img, const float* v_ch3, int split, const float* v_alpha, float* grads,
+                  int grouped) {
+    memset(grads, 0, sizeof(float) * ts::kGradFloats * (size_t)N);
+    const int gch = (CH == 4 && split && !v_ch3) ? 3 : CH;
+#define ARGS grouped, H, W, tx, ty, off, ids, recs, bg, final_T, n_contrib, v_img, v_ch3, split, v_alpha, grads
+    switch (CH) {
+        case 1: return run_bwd<1, 1>(ARGS);
+        case 2: return run_bwd<2, 2>(ARGS);
+        case 3: return run_bwd<3, 3>(ARGS);
+        default: return gch == 3 ? run_bwd<4, 3>(ARGS) : run_bwd<4, 4>(ARGS);
+    }
+#undef ARGS
+}
+
+}  // extern "C"
+
+
+extern "C" {
+
+int emu_bin_counter_stride(void) { return ts::kCounterStride; }
+int emu_bin_scan_work_ints(void) { return ts::kScanWorkInts; }
+int emu_bin_smem_sort_cap(void) { return ts::kSmemSortCap; }
+
+int emu_bin_count(int N, int CH, const float* xys, const int32_t* radii, const float* conics,
+                  const float* opacity, const float* colors, int tx, int ty, int cull, int flags,
+                  float* recs, int32_t* tile_counts) {
+    memset(tile_counts, 0, sizeof(int32_t) * ts::kCounterStride * (size_t)tx * ty);
+    if (N == 0) return 0;
+    const int grid = (N + ts::kBinThreads - 1) / ts::kBinThreads;
+#define RUN(C)                                                                                           \
+    return ts_emu::launch(dim3(grid), ts::kBinThreads, [=]() {                                           \
+        ts::bin_count_kernel<C>(N, (const float2*)xys, radii, conics, opacity, colors, tx, ty, cull, flags, \
+                                (float4*)recs, tile_counts);                                             \
+    })
+    switch (CH) {
+        case 1: RUN(1);
+        case 2: RUN(2);
+        case 3: RUN(3);
+        default: RUN(4);
+    }
+#undef RUN
+}
+
+int emu_bin_scan(int T, int32_t* tile_counts, int32_t* offsets, int32_t* stats, int cap) {
+    int chunk = (T + 1024 * ts::kScanMaxBlocks - 1) / (1024 * ts::kScanMaxBlocks);
+    if (chunk < 1) chunk = 1;
+    const int grid = (T + 1024 * chunk - 1) / (1024 * chunk);
+    memset(stats, 0, sizeof(int32_t) * ts::kScanWorkInts);
+    return ts_emu::launch(dim3(grid), 1024, [=]() { ts::bin_scan_kernel(T, chunk, tile_counts, offsets, stats, cap); });
+}
+
+int emu_bin_emit(int N, const float* depths, const int32_t* radii, const float* recs, int tx, int ty,
+                 int cull, int32_t* cursors, uint64_t* keys) {
+    if (N == 0) return 0;
+    const int grid = (N + ts::kBinThreads - 1) / ts::kBinThreads;
+    return ts_emu::launch(dim3(grid), ts::kBinThreads, [=]() {
+        ts::bin_emit_kernel(N, depths, radii, (const float4*)recs, tx, ty, cull, cursors, keys);
+    });
+}
+
+int emu_bin_sort(int T, const int32_t* offsets, uint64_t* keys, int32_t* ids_sorted, int max_count,
+                 int n_big, uint64_t* big_scratch, int32_t* big_counter) {
+    if (max_count <= 0) return 0;
+    int rc = ts_emu::launch(dim3((T + 7) / 8), 256, [=]() { ts::bin_sort_warp_kernel(T, offsets, keys, ids_sorted); });
+    const int bounds[3] = {ts::kWarpSortMax, 2048, ts::kSmemSortCap};
+    for (int c = 0; c < 2 && rc == 0; ++c) {
+        if (max_count <= bounds[c]) break;
+        const int lo = bounds[c], hi = bounds[c + 1];
+        rc = ts_emu::launch(dim3(T), ts::kSortThreads, [=]() { ts::bin_sort_kernel(T, offsets, keys, ids_sorted, lo, hi); });
+    }
+    if (n_big > 0 && rc == 0) {
+        int P = 2;
+        while (P < max_count) P <<= 1;
+        *big_counter = 0;
+        rc = ts_emu::launch(dim3(T), 1024, [=]() {
+            ts::bin_sort_big_kernel(T, offsets, keys, ids_sorted, ts::kSmemSortCap, P, big_scratch, big_counter);
+        });
+    }
+    return rc;
+}
+
+}  // extern "C"
+
+// ---- the fused pipeline (tinysplat_b200/fused.py), stage by stage ------------------------------
+namespace {
+
+template <int DEG>
+int sh_fwd_any(bool bulk, int N, int K, const float* means, const float* view, const float* dc, const float* rest,
+               float* colors, int stride, const float* ch3, uint8_t* mask, int flags) {
+    const int grid = (N + ts::kShThreads - 1) / ts::kShThreads;
+    if (bulk)
+        return ts_emu::launch(dim3(grid), ts::kShThreads, [=]() {
+            ts::sh_fwd_bulk_kernel<DEG>(N, K, means, view, dc, rest, colors, stride, ch3, mask, flags);
+        });
+    const int sstride = ts::sh_stride(K);
+    return ts_emu::launch(dim3(grid), ts::kShThreads, [=]() {
+        ts::sh_fwd_kernel<DEG>(N, K, means, view, dc, rest, colors, stride, ch3, mask, flags, sstride);
+    });
+}
+
+template <int DEG>
+int sh_bwd_any(bool bulk, int N, int K, const float* means, const float* view, const float* v_colors, int stride,
+               const uint8_t* mask, float* v_dc, float* v_rest, int flags) {
+    const int grid = (N + ts::kShThreads - 1) / ts::kShThreads;
+    if (bulk)
+        return ts_emu::launch(dim3(grid), ts::kShThreads, [=]() {
+            ts::sh_bwd_bulk_kernel<DEG>(N, K, means, view, v_colors, stride, mask, v_dc, v_rest, flags);
+        });
+    const int sstride = ts::sh_stride(K);
+    return ts_emu::launch(dim3(grid), ts::kShThreads, [=]() {
+        ts::sh_bwd_kernel<DEG>(N, K, means, view, v_colors, stride, mask, v_dc, v_rest, flags, sstride);
+    });
+}
+
+template <int DEG>
+int sh_bwd_views_any(int n_views, int N, int K, const float* means, const float* cams, const float* packed,
+                     size_t view_stride, float scale, float* v_dc, float* v_rest) {
+    const int grid = (N + ts::kShThreads - 1) / ts::kShThreads;
+    return ts_emu::launch(dim3(grid), ts::kShThreads, [=]() {
+        ts::sh_bwd_views_kernel<DEG>(n_views, N, K, means, cams, packed, view_stride, scale, v_dc, v_rest);
+    });
+}
+
+#define TS_EMU_BY_DEG(deg, fn, ...)             \
+    switch (deg) {                              \
+        case 0: return fn<0>(__VA_ARGS__);      \
+        case 1: return fn<1>(__VA_ARGS__);      \
+        case 2: return fn<2>(__VA_ARGS__);      \
+        case 3: return fn<3>(__VA_ARGS__);      \
+        default: return fn<4>(__VA_ARGS__);     \
+    }
+
+}  // namespace
+
+extern "C" {
+
+// Mirrors _RenderFused.forward + backward.  All pointers are host pointers; outputs are written by
+// the kernels exactly as on the device.  v_rgb / v_depth may be NULL (no cotangent).
+// bwd_mode: 0 = first-generation blend-backward, 1 = grouped.  Returns 0, or -1 on an emulator deadlock.
+int emu_render_fused(int N, int K, int deg, int W, int H, const float* means, const float* log_scales,
+                     const float* quats, const float* logits, const float* dc, const float* rest,
+                     const float* view, const float* fullproj, float fx, float fy, const float* bg4, int cull,
+                     int clamp_rgb, const float* v_rgb, const float* v_depth, int bwd_mode,
+                     float* rgb, float* depth_img, float* final_T, float* xys, int32_t* radii, int64_t* stats_out,
+                     float* v_means, float* v_scales, float* v_quats, float* v_logit, float* v_dc, float* v_rest,
+                     float* v_xys) {
+    const int tx = (W + 15) / 16, ty = (H + 15) / 16, T = tx * ty;
+    const int pflags = TS_PROJ_LOG_SCALES | TS_PROJ_RAW_QUATS;
+    const int sflags = TS_SH_DIRS_FROM_MEANS | TS_SH_OFFSET_CLAMP;
+    std::vector<float> depths(N + 1), recs((size_t)N * 12 + 4, 0.f);
+    std::vector<int32_t> counts((size_t)T * ts::kCounterStride, 0), offsets(T + 1, 0), stats(ts::kScanWorkInts, 0);
+    std::vector<uint8_t> mask(N + 1, 0);
+    float* recs_p = (float*)(((uintptr_t)recs.data() + 15) & ~(uintptr_t)15);
+    int rc = 0;
+    // K1 + pack + count
+    if (N > 0) {
+        const int grid = (N + ts::kProjThreads - 1) / ts::kProjThreads;
+        rc = ts_emu::launch(dim3(grid), ts::kProjThreads, [&]() {
+            ts::project_fwd_kernel(N, means, log_scales, 1.0f, (const float4*)quats, view, fullproj, fx, fy, W / 2.f,
+                                   H / 2.f, H, W, tx, ty, 0.01f, pflags | TS_PROJ_OPACITY_LOGIT, (float2*)xys,
+                                   depths.data(), radii, nullptr, nullptr, nullptr, logits, cull, (float4*)recs_p,
+                                   counts.data());
+        });
+        if (rc) return rc;
+        // K2: colours straight into the third float4 of the record, depth as channel 3
+        const bool bulk = K == (deg + 1) * (deg + 1) && K > 1 && ((K - 1) * 3 * 4 * ts::kShThreads) % 16 == 0;
+        auto run = [&]() -> int {
+            TS_EMU_BY_DEG(deg, sh_fwd_any, bulk, N, K, means, view, dc, rest, recs_p + 8, 12, depths.data(), mask.data(), sflags);
+        };
+        rc = run();
+        if (rc) return rc;
+    }
+    // K3
+    rc = emu_bin_scan(T, counts.data(), offsets.data(), stats.data(), ts::kSmemSortCap);
+    if (rc) return rc;
+    const int M = stats[0], max_count = stats[1], n_big = stats[2];
+    stats_out[0] = M; stats_out[1] = max_count; stats_out[2] = n_big;
+    std::vector<uint64_t> keys(M + 1, 0);
+    std::vector<int32_t> ids(M + 1, 0);
+    if (M > 0) {
+        rc = emu_bin_emit(N, depths.data(), radii, recs_p, tx, ty, cull, counts.data(), keys.data());
+        if (rc) return rc;
+        std::vector<uint64_t> scratch;
+        int32_t counter = 0;
+        if (n_big > 0) {
+            int P = 2;
+            while (P < max_count) P <<= 1;
+            scratch.resize((size_t)n_big * P);
+        }
+        rc = emu_bin_sort(T, offsets.data(), keys.data(), ids.data(), max_count, n_big, scratch.data(), &counter);
+        if (rc) return rc;
+    }
+    // K4
+    std::vector<int32_t> ncon((size_t)W * H, 0);
+    rc = emu_blend_fwd(4, H, W, tx, ty, offsets.data(), ids.data(), recs_p, bg4, rgb, depth_img, final_T, ncon.data(),
+                       clamp_rgb);
+    if (rc || (!v_rgb && !v_depth)) return rc;
+    // K5
+    std::vector<float> grads((size_t)N * 12 + 4, 0.f);
+    float* grads_p = (float*)(((uintptr_t)grads.data() + 15) & ~(uintptr_t)15);
+    if (N == 0) return 0;
+    rc = emu_blend_bwd(N, 4, H, W, tx, ty, offsets.data(), ids.data(), recs_p, bg4, final_T, ncon.data(), v_rgb, v_depth,
+                       1, nullptr, grads_p, bwd_mode);
+    if (rc) return rc;
+    // K7, K6
+    {
+        const bool bulk = K > 1 && ((K - 1) * 3 * 4 * ts::kShThreads) % 16 == 0;
+        auto run = [&]() -> int {
+            TS_EMU_BY_DEG(deg, sh_bwd_any, bulk, N, K, means, view, grads_p + 8, 12, mask.data(), v_dc, v_rest, sflags);
+        };
+        rc = run();
+        if (rc) return rc;
+    }
+    const int grid = (N + ts::kProjThreads - 1) / ts::kProjThreads;
+    return ts_emu::launch(dim3(grid), ts::kProjThreads, [&]() {
+        ts::project_bwd_kernel(N, means, log_scales, 1.0f, (const float4*)quats, view, fullproj, fx, fy, W / 2.f, H / 2.f,
+                               H, W, pflags | TS_PROJ_DEPTH_CH3, radii, nullptr, nullptr, nullptr,
+                               (const float4*)grads_p, logits, v_means, v_scales, (float4*)v_quats, v_logit,
+                               (float2*)v_xys);
+    });
+}
+
+// The shard backward of the packed-row gradient exchange (ts_project_bwd_views + ts_sh_bwd_views).
+int emu_shard_bwd_views(int n_views, int N, int K, int deg, int W, int H, const float* means,
+                        const float* log_scales, const float* quats, const float* logits, const float* cams,
+                        const float* packed, int64_t view_stride, float scale, float* v_means, float* v_scales,
+                        float* v_quats, float* v_logit, float* v_dc, float* v_rest) {
+    if (N == 0) return 0;
+    const int flags = TS_PROJ_LOG_SCALES | TS_PROJ_RAW_QUATS | TS_PROJ_DEPTH_CH3;
+    const int grid = (N + ts::kProjThreads - 1) / ts::kProjThreads;
+    int rc = ts_emu::launch(dim3(grid), ts::kProjThreads, [&]() {
+        ts::project_bwd_views_kernel(n_views, N, means, log_scales, 1.0f, (const float4*)quats, cams, H, W, flags,
+                                     (const float4*)packed, (size_t)(view_stride / 4), logits, scale, v_means, v_scales,
+                                     (float4*)v_quats, v_logit);
+    });
+    if (rc) return rc;
+    auto run = [&]() -> int {
+        TS_EMU_BY_DEG(deg, sh_bwd_views_any, n_views, N, K, means, cams, packed, (size_t)view_stride, scale, v_dc, v_rest);
+    };
+    return run();
+}
+
+// ts_dp_prepare on host pointers.
+int emu_dp_prepare(int N, const int32_t* radii, const uint8_t* mask, const float* recs, float* grads, float* v_xys) {
+    if (N == 0) return 0;
+    return ts_emu::launch(dim3((N + 255) / 256), 256, [=]() {
+        ts::dp_prepare_kernel(N, radii, mask, (const float4*)recs, (float4*)grads, (float2*)v_xys);
+    });
+}
+
+}  // extern "C"

@@ -214,6 +214,7 @@ static inline int __shfl_up_sync(unsigned mask, int x, int d) {
     return lane >= d ? (int)v[lane - d] : x;
 }
 static inline void __threadfence() {}
+static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 // glibc declares (but does not export) __logf/__expf: map the CUDA fast-math names with macros
 #define __logf(x) logf(x)
 #define __expf(x) expf(x)

@@ -3,7 +3,7 @@ scan -> emit -> per-tile sort), compiled as host code on the fiber SIMT emulator
 compared with the oracle's bin_and_sort.  Integer / index work: bit-exact."""
 import ctypes as C
 import os
-import subprocess
+import subprocess  # noqa: F401
 
 import numpy as np
 import pytest
@@ -13,27 +13,12 @@ import oracle
 from oracle import gsplat_oracle as go
 from tinysplat_b200 import synthetic
 
-HERE = os.path.dirname(os.path.abspath(__file__))
-EMU = os.path.join(HERE, "emu")
-LIB = os.path.join(EMU, "_build", "libbinning_emu.so")
-CSRC = os.path.join(HERE, "..", "tinysplat_b200", "csrc")
+import emu_lib
 
 
 @pytest.fixture(scope="module")
 def emu():
-    srcs = [os.path.join(EMU, f) for f in ("binning_emu.cpp", "ts_emu.h")] + \
-           [os.path.join(CSRC, f) for f in ("binning.cu", "ts_binning.cuh", "ts_common.cuh")]
-    if not os.path.exists(LIB) or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in srcs):
-        os.makedirs(os.path.dirname(LIB), exist_ok=True)
-        subprocess.run(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-I" + EMU,
-                        "-o", LIB, srcs[0]], check=True)
-    lib = C.CDLL(LIB)
-    p, i = C.c_void_p, C.c_int
-    lib.emu_bin_count.argtypes = [i, i, p, p, p, p, p, i, i, i, i, p, p]
-    lib.emu_bin_scan.argtypes = [i, p, p, p, i]
-    lib.emu_bin_emit.argtypes = [i, p, p, p, i, i, i, p, p]
-    lib.emu_bin_sort.argtypes = [i, p, p, p, i, i, p, p]
-    return lib
+    return emu_lib.load()
 
 
 def _ptr(a):

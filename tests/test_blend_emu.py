@@ -7,7 +7,7 @@ the 8-lane transpose-reduce, the packed-gradient layout.  What it cannot cover (
 real async copies, occupancy) is left to the `-m gpu` tests."""
 import ctypes as C
 import os
-import subprocess
+import subprocess  # noqa: F401
 
 import numpy as np
 import pytest
@@ -17,26 +17,14 @@ import oracle
 from oracle import gsplat_oracle as go
 from tinysplat_b200 import synthetic
 
-HERE = os.path.dirname(os.path.abspath(__file__))
-EMU = os.path.join(HERE, "emu")
-LIB = os.path.join(EMU, "_build", "libblend_group_emu.so")
-CSRC = os.path.join(HERE, "..", "tinysplat_b200", "csrc")
+import emu_lib
+
 LOG2E = 1.4426950408889634
 
 
 @pytest.fixture(scope="module")
 def emu():
-    srcs = [os.path.join(EMU, f) for f in ("blend_group_emu.cpp", "ts_emu.h")] + \
-           [os.path.join(CSRC, f) for f in ("blend.cu", "blend_group.cu", "ts_blend_common.cuh", "ts_common.cuh")]
-    if not os.path.exists(LIB) or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in srcs):
-        os.makedirs(os.path.dirname(LIB), exist_ok=True)
-        subprocess.run(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-I" + EMU,
-                        "-o", LIB, srcs[0]], check=True)
-    lib = C.CDLL(LIB)
-    p, i = C.c_void_p, C.c_int
-    lib.emu_blend_fwd.argtypes = [i, i, i, i, i, p, p, p, p, p, p, p, p, i]
-    lib.emu_blend_bwd.argtypes = [i, i, i, i, i, i, p, p, p, p, p, p, p, p, i, p, p, i]
-    return lib
+    return emu_lib.load()
 
 
 def _ptr(a):
@@ -212,7 +200,7 @@ def test_emulator_detects_a_lane_that_skips_a_collective(emu, tmp_path):
                    'extern "C" int run() { return ts_emu::launch(dim3(1, 1), 32, []() {\n'
                    '  if (threadIdx.x != 5) __ballot_sync(0xffffffffu, 1); }); }\n')
     so = tmp_path / "dead.so"
-    subprocess.run(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-I" + EMU, "-o", str(so), str(src)], check=True)
+    subprocess.run(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-I" + emu_lib.EMU, "-o", str(so), str(src)], check=True)
     assert C.CDLL(str(so)).run() == -1
 
 

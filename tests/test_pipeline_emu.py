@@ -1,0 +1,166 @@
+"""The WHOLE fused hot path on the CPU: projection (+pack+count), SH, scan / emit / sort, blend
+forward, blend backward (both kernels), SH backward and projection backward run as the unchanged
+kernel sources on the host SIMT emulator (tests/emu), in the order tinysplat_b200/fused.py launches
+them, and are compared with the oracle's restatement of the reference adapter — the same check
+__graft_entry__.smoke() makes on the GPU.  Also the shard backward of the packed-row gradient
+exchange (ts_dp_prepare -> ts_project_bwd_views / ts_sh_bwd_views) against the sum of two views."""
+import numpy as np
+import pytest
+import torch
+
+import emu_lib
+import oracle
+from emu_lib import ptr
+from tinysplat_b200 import synthetic
+
+NAMES = ["means", "scales", "quats", "opacities", "colors_dc", "colors_rest"]
+
+
+@pytest.fixture(scope="module")
+def emu():
+    return emu_lib.load()
+
+
+def _c(t):
+    return np.ascontiguousarray(t.detach().numpy().astype(np.float32))
+
+
+def _render(emu, sc, cam, W, H, deg, v_rgb, v_depth, bwd_mode, cull=1):
+    N = sc["means"].shape[0]
+    K = sc["colors_rest"].shape[1] + 1
+    view = cam.view_matrix.float()
+    full = cam.proj_matrix.float() @ view
+    bg = sc["background"].float()
+    bg4 = _c(torch.cat([bg, bg[:1]]))
+    arrs = dict(means=_c(sc["means"]), scales=_c(sc["scales"]), quats=_c(sc["quats"]),
+                logits=_c(sc["opacities"].reshape(-1)), dc=_c(sc["colors_dc"]), rest=_c(sc["colors_rest"]),
+                view=_c(view), full=_c(full))
+    f = np.float32
+    out = dict(rgb=np.zeros((H, W, 3), f), depth=np.zeros((H, W), f), T=np.zeros((H, W), f),
+               xys=np.zeros((N, 2), f), radii=np.zeros(N, np.int32), stats=np.zeros(4, np.int64),
+               means=np.zeros((N, 3), f), scales=np.zeros((N, 3), f), quats=np.zeros((N, 4), f),
+               opacities=np.zeros((N, 1), f), colors_dc=np.zeros((N, 3), f),
+               colors_rest=np.zeros((N, K - 1, 3), f), v_xys=np.zeros((N, 2), f))
+    vr = None if v_rgb is None else _c(v_rgb)
+    vd = None if v_depth is None else _c(v_depth)
+    rc = emu.emu_render_fused(N, K, deg, W, H, ptr(arrs["means"]), ptr(arrs["scales"]), ptr(arrs["quats"]),
+                              ptr(arrs["logits"]), ptr(arrs["dc"]), ptr(arrs["rest"]), ptr(arrs["view"]),
+                              ptr(arrs["full"]), cam.f_x, cam.f_y, ptr(bg4), cull, 1, ptr(vr), ptr(vd), bwd_mode,
+                              ptr(out["rgb"]), ptr(out["depth"]), ptr(out["T"]), ptr(out["xys"]), ptr(out["radii"]),
+                              ptr(out["stats"]), ptr(out["means"]), ptr(out["scales"]), ptr(out["quats"]),
+                              ptr(out["opacities"]), ptr(out["colors_dc"]), ptr(out["colors_rest"]), ptr(out["v_xys"]))
+    assert rc == 0
+    return out
+
+
+def _rel(a, b):
+    a, b = torch.as_tensor(a).double(), b.detach().double()
+    if b.numel() == 0:
+        return 0.0
+    return (a - b).abs().max().item() / max(b.abs().max().item(), 1e-30)
+
+
+@pytest.mark.parametrize("bwd_mode", [0, 1])
+@pytest.mark.parametrize("n,W,H,deg,sh_deg_stored", [(256, 128, 128, 3, 3), (400, 88, 56, 2, 3), (150, 48, 48, 0, 0)])
+def test_fused_pipeline_on_the_emulator_matches_the_oracle(emu, n, W, H, deg, sh_deg_stored, bwd_mode):
+    cam = synthetic.make_camera(W, H, yaw_deg=3.0, shift=(0.05, 0.0, 0.0))
+    sc = synthetic.make_scene(n, W, H, seed=n, sh_degree=sh_deg_stored)
+    sc["background"] = torch.tensor([0.2, 0.5, 0.8])
+    sc["quats"] = sc["quats"] * (0.5 + torch.rand(n, 1, generator=torch.Generator().manual_seed(1)))
+    sc["means"][:5, 2] = -1.0                       # behind the camera
+    g = torch.Generator().manual_seed(5)
+    wi, wd = torch.rand(H, W, 3, generator=g), 0.1 * torch.rand(H, W, generator=g)
+    out = _render(emu, sc, cam, W, H, deg, wi, wd, bwd_mode)
+
+    p = {k: v.clone().requires_grad_(k != "background") for k, v in sc.items()}
+    rimg, rex = oracle.render_reference_adapter(p, cam.view_matrix, cam.proj_matrix, cam.f_x, cam.f_y, (W, H), deg)
+    ((rimg * wi).sum() + (rex["depth"] * wd).sum()).backward()
+    assert np.array_equal(out["radii"], rex["radii"].numpy().astype(np.int32))
+    assert np.abs(out["rgb"] - rimg.detach().numpy()).max() < 5e-5
+    assert np.abs(out["depth"] - rex["depth"].detach().numpy()).max() < 5e-4
+    assert out["stats"][0] > 0
+    assert _rel(out["v_xys"], rex["xys"].grad) < 2e-4
+    for k in NAMES:
+        assert np.isfinite(out[k]).all(), k
+        assert _rel(out[k].reshape(p[k].shape), p[k].grad) < 2e-4, k
+    assert np.abs(out["means"][:5]).max() == 0
+
+
+def test_forward_only_and_empty_scene_on_the_emulator(emu):
+    W, H = 40, 24
+    cam = synthetic.make_camera(W, H)
+    sc = synthetic.make_scene(16, W, H, seed=2)
+    sc["background"] = torch.tensor([0.2, 0.4, 0.6])
+    empty = {k: (v[:0] if k != "background" else v) for k, v in sc.items()}
+    out = _render(emu, empty, cam, W, H, 3, None, None, 1)
+    assert np.allclose(out["rgb"], sc["background"].numpy()[None, None, :])
+    assert np.allclose(out["depth"], 0.2)           # depth is composited over background[0]
+    out = _render(emu, sc, cam, W, H, 3, None, None, 1)
+    rimg, _ = oracle.render_reference_adapter({k: v.clone() for k, v in sc.items()}, cam.view_matrix,
+                                              cam.proj_matrix, cam.f_x, cam.f_y, (W, H), 3)
+    assert np.abs(out["rgb"] - rimg.numpy()).max() < 5e-5
+
+
+def test_packed_exchange_shard_backward_on_the_emulator(emu):
+    """Two views: per view, forward + blend-backward + ts_dp_prepare produce the packed rows a rank
+    would send; the multi-view shard kernels must return the average of the two plain backwards."""
+    n, W, H, deg = 300, 96, 64, 3
+    K = 16
+    sc = synthetic.make_scene(n, W, H, seed=9, sh_degree=3)
+    sc["background"] = torch.tensor([0.1, 0.3, 0.2])
+    sc["means"][:7, 2] = -2.0
+    cams = [synthetic.make_camera(W, H, yaw_deg=-5.0), synthetic.make_camera(W, H, yaw_deg=4.0, shift=(0.1, 0.0, 0.1))]
+    g = torch.Generator().manual_seed(2)
+    wi, wd = torch.rand(H, W, 3, generator=g), 0.1 * torch.rand(H, W, generator=g)
+    plain = [_render(emu, sc, c, W, H, deg, wi, wd, 1) for c in cams]
+
+    # the packed rows of each view, rebuilt from the public stages (what fused.py keeps in `grads`)
+    import test_blend_emu as tb
+    f = np.float32
+    rows, cam_rows = [], []
+    for c in cams:
+        view = c.view_matrix.float()
+        full = c.proj_matrix.float() @ view
+        with torch.no_grad():
+            q = sc["quats"] / sc["quats"].norm(dim=-1, keepdim=True)
+            tbd = ((W + 15) // 16, (H + 15) // 16, 1)
+            xys, depths, radii, conics, nt, _ = oracle.project_gaussians(
+                sc["means"], sc["scales"].exp(), 1.0, q, view[:3], full, c.f_x, c.f_y, W / 2, H / 2, H, W, tbd)
+            dirs = torch.nn.functional.normalize(sc["means"] - view[:3, 3], dim=-1)
+            coeffs = torch.cat([sc["colors_dc"][:, None, :], sc["colors_rest"]], 1)
+            pre = oracle.spherical_harmonics(deg, dirs, coeffs) + 0.5
+            colors = torch.cat([pre.clamp(min=0), depths[:, None]], 1)
+            mask = ((pre[:, 0] >= 0).to(torch.uint8) | ((pre[:, 1] >= 0).to(torch.uint8) << 1)
+                    | ((pre[:, 2] >= 0).to(torch.uint8) << 2))
+            opac = torch.sigmoid(sc["opacities"])
+        rec = tb._pack(xys, conics, opac, colors, True)
+        offsets, ids = tb._lists(xys, depths, radii, tbd)
+        bg4 = _c(torch.cat([sc["background"], sc["background"][:1]]))
+        rgb, dep = np.zeros((H, W, 3), f), np.zeros((H, W), f)
+        T, nc = np.zeros((H, W), f), np.zeros((H, W), np.int32)
+        assert emu.emu_blend_fwd(4, H, W, tbd[0], tbd[1], ptr(offsets), ptr(ids), ptr(rec), ptr(bg4), ptr(rgb), ptr(dep),
+                                 ptr(T), ptr(nc), 1) == 0
+        grads = np.zeros((n, 12), f)
+        vi, vd = _c(wi), _c(wd)
+        assert emu.emu_blend_bwd(n, 4, H, W, tbd[0], tbd[1], ptr(offsets), ptr(ids), ptr(rec), ptr(bg4), ptr(T), ptr(nc),
+                                 ptr(vi), ptr(vd), 1, None, ptr(grads), 1) == 0
+        rd = np.ascontiguousarray(radii.numpy().astype(np.int32))
+        mk = np.ascontiguousarray(mask.numpy())
+        vx = np.zeros((n, 2), f)
+        assert emu.emu_dp_prepare(n, ptr(rd), ptr(mk), ptr(rec), ptr(grads), ptr(vx)) == 0
+        assert np.abs(grads[:7]).max() == 0
+        rows.append(grads)
+        cam_rows.append(np.concatenate([_c(view[:3]).reshape(-1), _c(full).reshape(-1),
+                                        np.array([c.f_x, c.f_y, 0, 0], f)]))
+    packed = np.ascontiguousarray(np.stack(rows))
+    cam_buf = np.ascontiguousarray(np.stack(cam_rows))
+    out = dict(means=np.zeros((n, 3), f), scales=np.zeros((n, 3), f), quats=np.zeros((n, 4), f),
+               opacities=np.zeros((n, 1), f), colors_dc=np.zeros((n, 3), f), colors_rest=np.zeros((n, K - 1, 3), f))
+    a = dict(means=_c(sc["means"]), scales=_c(sc["scales"]), quats=_c(sc["quats"]), logits=_c(sc["opacities"].reshape(-1)))
+    assert emu.emu_shard_bwd_views(2, n, K, deg, W, H, ptr(a["means"]), ptr(a["scales"]), ptr(a["quats"]),
+                                   ptr(a["logits"]), ptr(cam_buf), ptr(packed), n * 12, 0.5, ptr(out["means"]),
+                                   ptr(out["scales"]), ptr(out["quats"]), ptr(out["opacities"]), ptr(out["colors_dc"]),
+                                   ptr(out["colors_rest"])) == 0
+    for k in NAMES:
+        want = 0.5 * (plain[0][k] + plain[1][k])
+        assert _rel(out[k], torch.from_numpy(want)) < 2e-4, k

@@ -226,11 +226,7 @@ __device__ __forceinline__ void bitonic_sort(Ptr s, int P, int nthreads) {
 __global__ void __launch_bounds__(kSortThreads)
 bin_sort_kernel(int T, const int32_t* __restrict__ offsets, const uint64_t* __restrict__ keys,
                 int32_t* __restrict__ ids_sorted, int lo_count, int hi_count) {
-#ifdef TS_HOST_EMU
-    __shared__ __align__(16) uint64_t s_keys[kSmemSortCap];     // emulator: static storage
-#else
-    extern __shared__ __align__(16) uint64_t s_keys[];
-#endif
+    TS_DYN_SMEM(uint64_t, s_keys, 16);
     const int tile = blockIdx.x;
     const int start = __ldg(offsets + tile);
     const int n = __ldg(offsets + tile + 1) - start;

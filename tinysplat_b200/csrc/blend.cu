@@ -224,11 +224,7 @@ blend_bwd_kernel(int H, int W, int tbx, const int32_t* __restrict__ tile_offsets
                  const int32_t* __restrict__ n_contrib, const float* __restrict__ v_out_img,
                  const float* __restrict__ v_out_ch3, int split_ch3,
                  const float* __restrict__ v_out_alpha, float4* __restrict__ grads) {
-#ifdef TS_HOST_EMU
-    __shared__ __align__(16) unsigned char s_raw[kBwdSmemBytes];              // emulator: static storage
-#else
-    extern __shared__ __align__(16) unsigned char s_raw[];
-#endif
+    TS_DYN_SMEM(unsigned char, s_raw, 16);
     float4* s_rec = reinterpret_cast<float4*>(s_raw);                         // [2][kBatch*3]
     float* s_acc = reinterpret_cast<float*>(s_rec + 2 * kBatch * 3);          // [kBatch*12]
     float* s_part = s_acc + kBatch * kGradFloats;                             // [8][kGroup][320]

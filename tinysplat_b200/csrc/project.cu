@@ -473,6 +473,7 @@ project_bwd_views_kernel(int n_views, int N, const float* __restrict__ means,
 
 }  // namespace ts
 
+#ifndef TS_HOST_EMU
 extern "C" {
 
 int ts_project_fwd(int N, const float* means3d, const float* scales, float glob_scale,
@@ -560,3 +561,4 @@ int ts_project_bwd_views(int n_views, int N, const float* means3d, const float* 
 }
 
 }  // extern "C"
+#endif  // !TS_HOST_EMU

@@ -112,7 +112,7 @@ sh_fwd_kernel(int N, int K, const float* __restrict__ dirs, const float* __restr
               const float* __restrict__ coeffs, const float* __restrict__ coeffs_rest,
               float* __restrict__ colors, int out_stride, const float* __restrict__ ch3,
               uint8_t* __restrict__ clamp_mask, int flags, int sstride) {
-    extern __shared__ __align__(16) float s_sh[];
+    TS_DYN_SMEM(float, s_sh, 16);
     constexpr int NB = (DEG + 1) * (DEG + 1);
     float* s_dir = s_sh;                        // [TH*3], reused for the colour output
     float* s_co = s_sh + kShThreads * 3 + 4;    // [TH][sstride]
@@ -172,7 +172,7 @@ sh_bwd_kernel(int N, int K, const float* __restrict__ dirs, const float* __restr
               const float* __restrict__ v_colors, int v_stride,
               const uint8_t* __restrict__ clamp_mask, float* __restrict__ v_coeffs,
               float* __restrict__ v_coeffs_rest, int flags, int sstride) {
-    extern __shared__ __align__(16) float s_sh[];
+    TS_DYN_SMEM(float, s_sh, 16);
     constexpr int NB = (DEG + 1) * (DEG + 1);
     float* s_dir = s_sh;                          // [TH*3]
     float* s_vc = s_sh + kShThreads * 3 + 4;      // [TH*3]
@@ -241,7 +241,7 @@ sh_fwd_bulk_kernel(int N, int K, const float* __restrict__ means, const float* _
                    const float* __restrict__ dc, const float* __restrict__ rest,
                    float* __restrict__ colors, int out_stride, const float* __restrict__ ch3,
                    uint8_t* __restrict__ clamp_mask, int flags) {
-    extern __shared__ __align__(128) float s_sh[];
+    TS_DYN_SMEM(float, s_sh, 128);
     constexpr int NB = (DEG + 1) * (DEG + 1);
     const int R = (K - 1) * 3;                       // floats per `rest` row
     float* s_rest = s_sh;                            // [TH][R] dense
@@ -304,7 +304,7 @@ sh_bwd_bulk_kernel(int N, int K, const float* __restrict__ means, const float* _
                    const float* __restrict__ v_colors, int v_stride,
                    const uint8_t* __restrict__ clamp_mask, float* __restrict__ v_dc,
                    float* __restrict__ v_rest, int flags) {
-    extern __shared__ __align__(128) float s_sh[];
+    TS_DYN_SMEM(float, s_sh, 128);
     constexpr int NB = (DEG + 1) * (DEG + 1);
     const int R = (K - 1) * 3;
     float* s_rest = s_sh;                            // [TH][R] dense, becomes v_rest rows
@@ -372,7 +372,7 @@ __global__ void __launch_bounds__(kShThreads)
 sh_bwd_views_kernel(int n_views, int N, int K, const float* __restrict__ means,
                     const float* __restrict__ cams, const float* __restrict__ packed, size_t view_stride,
                     float out_scale, float* __restrict__ v_dc, float* __restrict__ v_rest) {
-    extern __shared__ __align__(128) float s_sh[];
+    TS_DYN_SMEM(float, s_sh, 128);
     constexpr int NB = (DEG + 1) * (DEG + 1);
     const int R = (K - 1) * 3;
     float* s_rest = s_sh;                            // [TH][R] dense, becomes v_rest rows
@@ -433,6 +433,7 @@ static inline int sh_stride(int K) { int k3 = K * 3; return (k3 & 1) ? k3 : k3 +
 
 }  // namespace ts
 
+#ifndef TS_HOST_EMU
 extern "C" {
 
 int ts_sh_fwd(int N, int degree, int K, const float* dirs, const float* viewmat, const float* coeffs,
@@ -551,3 +552,4 @@ int ts_sh_bwd_views(int n_views, int N, int degree, int K, const float* means, c
 }
 
 }  // extern "C"
+#endif  // !TS_HOST_EMU

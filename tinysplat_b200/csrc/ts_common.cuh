@@ -11,6 +11,15 @@
 #include <stdint.h>
 #include "../../include/tinysplat_b200.h"
 
+// Dynamic shared memory of a kernel.  The emulator has no launch-time size: it gets a static
+// buffer of the largest size any kernel asks for.
+#ifdef TS_HOST_EMU
+#define TS_DYN_SMEM(type, name, align) \
+    static __attribute__((aligned(align))) type name[(160 * 1024) / sizeof(type)]
+#else
+#define TS_DYN_SMEM(type, name, align) extern __shared__ __align__(align) type name[]
+#endif
+
 namespace ts {
 
 // ---- constants of the stated algorithm (mirrored in oracle/gsplat_oracle.py) --------------
@@ -129,6 +138,16 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 __device__ __forceinline__ void cp_async_commit() {}
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {}
+// TMA bulk copies: executed synchronously by the issuing thread, so every wait is trivially
+// satisfied once the block barrier that follows the issue has been passed
+__device__ __forceinline__ void mbar_init(uint64_t*, unsigned) {}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t*, unsigned) {}
+__device__ __forceinline__ void mbar_wait(uint64_t*, unsigned) {}
+__device__ __forceinline__ void fence_proxy_async() {}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, uint64_t*) { memcpy(smem_dst, gmem_src, bytes); }
+__device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, unsigned bytes) { memcpy(gmem_dst, smem_src, bytes); }
+__device__ __forceinline__ void bulk_commit() {}
+__device__ __forceinline__ void bulk_wait_read0() {}
 #else
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
