@@ -27,7 +27,10 @@
 namespace ts {
 
 constexpr int kGThreads = 64;                  // 2 warps = 8 groups of 8 lanes
-constexpr int kGBatch = 128;                   // candidates staged per batch
+#ifndef TS_GBATCH
+#define TS_GBATCH 128
+#endif
+constexpr int kGBatch = TS_GBATCH;             // candidates staged per batch (64, 128 or 256)
 constexpr int kGPer = kGBatch / kGThreads;     // records gathered per thread per batch
 constexpr int kGWords = kGBatch / 32;          // candidate-mask words per group per batch
 
