@@ -355,12 +355,17 @@ def run_ours(args):
         if choice == "auto":
             probe = {}
             for name in ("allreduce", "packed"):
-                set_exchange(name)
-                for i in range(3):
-                    path_step(i)
-                probe[name] = timed(path_step, 5, 3)[0] / 5      # max over ranks: same on every rank
+                try:
+                    set_exchange(name)
+                    for i in range(3):
+                        path_step(i)
+                    probe[name] = timed(path_step, 5, 3)[0] / 5  # max over ranks: same on every rank
+                except Exception as e:                           # deterministic errors hit every rank alike
+                    probe[name] = float("inf")
+                    exchange["probe_error"] = f"{name}: {type(e).__name__}: {e}"[:200]
+                    model.zero_grad()
             choice = min(probe, key=probe.get)
-            exchange["probe_ms"] = probe
+            exchange["probe_ms"] = {k: (v if v != float("inf") else None) for k, v in probe.items()}
         set_exchange(choice)
 
     # ---- device-resident arm: `value` -------------------------------------------------------
@@ -493,6 +498,7 @@ def run_ours(args):
                    if world > 1 and not fwd_only else ("replicas only" if world > 1 else "single GPU"),
                    "grad_exchange": exchange["name"] if (world > 1 and not fwd_only) else None,
                    "grad_exchange_probe_ms": exchange["probe_ms"],
+                   "grad_exchange_probe_error": exchange.get("probe_error"),
                    "grad_allreduce_collectives_per_step": (reducer.last_num_collectives if reducer else 0),
                    "grad_allreduce_bytes": (reducer.payload_bytes() if (reducer and world > 1) else 0),
                    "grad_exchange_bytes_sent_per_rank": (rast.grad_exchange.last_bytes_sent

@@ -6,7 +6,9 @@ bounding-box test and how many an exact ellipse test would keep.  Used to decide
 refinements pay before spending GPU time.  Imports the oracle's projection
 only as a measuring instrument; nothing here ships.
 
-    python tools/cull_stats.py [--n 1000000] [--sample 40000]
+    python tests/analysis/cull_stats.py [--n 1000000] [--sample 40000]
+
+Lives under tests/ because it imports the oracle (test infrastructure; the product never does).
 """
 import argparse
 import math
@@ -16,7 +18,7 @@ import sys
 import numpy as np
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import oracle  # noqa: E402
 from tinysplat_b200 import synthetic  # noqa: E402
 

@@ -8,7 +8,7 @@
 // warp walk four DIFFERENT candidate lists in lock-step (per-lane shared-memory addresses), so
 // one warp-instruction evaluates one pixel row of four (sub-block, Gaussian) pairs.
 //
-// Why (tools/cull_stats.py on synthetic_1M_1080p; measured history in profiles/README.md):
+// Why (tests/analysis/cull_stats.py on synthetic_1M_1080p; measured history in profiles/README.md):
 //   * culling is exact per pixel row (footprint_rowmask: the interval of each row the ellipse
 //     {alpha >= 1/255} covers), not a bounding box per sub-block: 6.15 M -> 5.31 M
 //     (sub-block, Gaussian) pairs;
