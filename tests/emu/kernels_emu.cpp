@@ -2,7 +2,8 @@
 // blend_group.cu) unchanged as host code on the fiber SIMT emulator (ts_emu.h) and exposes
 //   * the blend kernels and the binning stages with the argument lists of their C-ABI entry points
 //     (host pointers instead of device pointers; the launch logic mirrors those entry points), and
-//   * emu_render_fused: the whole fused forward + backward of tinysplat_b200/fused.py.
+//   * emu_render_fused: the whole fused forward + backward of tinysplat_b200/fused.py,
+//   * the SURVEY 8(f) widenings: fused Adam, fused SSIM forward/backward, brute-force knn_points.
 // TEST INFRASTRUCTURE ONLY (TS_HOST_EMU is never defined in the product build).
 #define TS_HOST_EMU 1
 #include "../../tinysplat_b200/csrc/project.cu"
@@ -10,6 +11,9 @@
 #include "../../tinysplat_b200/csrc/binning.cu"
 #include "../../tinysplat_b200/csrc/blend.cu"
 #include "../../tinysplat_b200/csrc/blend_group.cu"
+#include "../../tinysplat_b200/csrc/adam.cu"
+#include "../../tinysplat_b200/csrc/ssim.cu"
+#include "../../tinysplat_b200/csrc/knn.cu"
 
 #include <vector>
 
@@ -302,6 +306,64 @@ int emu_dp_prepare(int N, const int32_t* radii, const uint8_t* mask, const float
     return ts_emu::launch(dim3((N + 255) / 256), 256, [=]() {
         ts::dp_prepare_kernel(N, radii, mask, (const float4*)recs, (float4*)grads, (float2*)v_xys);
     });
+}
+
+}  // extern "C"
+
+// ---- Adam, SSIM, knn_points -----------------------------------------------------
+extern "C" {
+
+int emu_adam_step(int num_tensors, float* const* params, const float* const* grads, float* const* exp_avgs,
+                  float* const* exp_avg_sqs, const int64_t* numels, const float* lrs, const int64_t* steps,
+                  double beta1, double beta2, double eps) {
+    ts::AdamTensors t;
+    int blocks = 0;
+    int rc = ts::adam_build(num_tensors, params, grads, exp_avgs, exp_avg_sqs, numels, lrs, steps, beta1, beta2, t,
+                            blocks);
+    if (rc != 0 || blocks == 0) return rc;
+    const float omb1 = (float)(1.0 - beta1), b2 = (float)beta2, omb2 = (float)(1.0 - beta2), e = (float)eps;
+    return ts_emu::launch(dim3(blocks), ts::kAdamThreads, [=]() { ts::adam_multi_kernel(t, omb1, b2, omb2, e); });
+}
+
+int emu_ssim_fwd(int B, int C, int H, int W, const float* X, const int64_t* xs, const float* Y, const int64_t* ys,
+                 const float* win11, float C1, float C2, float* ssim_sum, float* dmu, float* de11, float* de12) {
+    memset(ssim_sum, 0, sizeof(float) * (size_t)B * C);
+    ts::SsimWin win;
+    for (int k = 0; k < ts::kWin; ++k) win.w[k] = win11[k];
+    ts::Strides sx{xs[0], xs[1], xs[2], xs[3]}, sy{ys[0], ys[1], ys[2], ys[3]};
+    const int Ho = H - ts::kHalo, Wo = W - ts::kHalo;
+    dim3 grid((Wo + ts::kST - 1) / ts::kST, (Ho + ts::kST - 1) / ts::kST, B * C), block(ts::kST, ts::kST);
+    return ts_emu::launch(grid, block, [=]() {
+        ts::ssim_fwd_kernel(C, H, W, X, Y, sx, sy, win, C1, C2, ssim_sum, dmu, de11, de12);
+    });
+}
+
+int emu_ssim_bwd(int B, int C, int H, int W, const float* X, const int64_t* xs, const float* Y, const int64_t* ys,
+                 const float* win11, const float* dmu, const float* de11, const float* de12, const float* v_pc,
+                 float* v_X) {
+    ts::SsimWin win;
+    for (int k = 0; k < ts::kWin; ++k) win.w[k] = win11[k];
+    ts::Strides sx{xs[0], xs[1], xs[2], xs[3]}, sy{ys[0], ys[1], ys[2], ys[3]};
+    dim3 grid((W + ts::kST - 1) / ts::kST, (H + ts::kST - 1) / ts::kST, B * C), block(ts::kST, ts::kST);
+    return ts_emu::launch(grid, block, [=]() {
+        ts::ssim_bwd_kernel(C, H, W, X, Y, sx, sy, win, dmu, de11, de12, v_pc, v_X);
+    });
+}
+
+int emu_knn_points(int P1, int P2, int K, const float* q, const float* ref, float* dists, int64_t* idx) {
+    if (P1 == 0) return 0;
+    const int grid = (P1 + ts::kKnnThreads - 1) / ts::kKnnThreads;
+#define RUN(KK) return ts_emu::launch(dim3(grid), ts::kKnnThreads, [=]() { ts::knn_kernel<KK>(P1, P2, q, ref, dists, idx); })
+    switch (K) {
+        case 1: RUN(1);
+        case 2: RUN(2);
+        case 4: RUN(4);
+        case 8: RUN(8);
+        case 16: RUN(16);
+        case 32: RUN(32);
+        default: return -1;
+    }
+#undef RUN
 }
 
 }  // extern "C"

@@ -57,7 +57,7 @@ struct BlockSync {
 };
 
 struct State {
-    dim3 tid, bid, gdim;
+    dim3 tid, bid, gdim, bdim;
     int nthreads = 0, cur = 0, alive = 0;
     ucontext_t sched;
     ucontext_t ctx[kMaxThreads];
@@ -96,15 +96,18 @@ inline void fiber_entry() {
 
 // Runs `body` once per thread of every block of the grid.  Returns 0, or -1 on a deadlock
 // (some lanes wait in a collective the others never reach).
-inline int launch(dim3 grid, int nthreads, std::function<void()> body) {
+inline int launch(dim3 grid, dim3 block, std::function<void()> body) {
     State& s = st();
     if (!s.stacks) s.stacks = (char*)malloc(kStack * kMaxThreads);
+    const int nthreads = (int)(block.x * block.y * block.z);
     s.body = body;
     s.nthreads = nthreads;
     s.gdim = grid;
+    s.bdim = block;
+    for (unsigned bz = 0; bz < grid.z; ++bz)
     for (unsigned by = 0; by < grid.y; ++by)
         for (unsigned bx = 0; bx < grid.x; ++bx) {
-            s.bid = dim3(bx, by, 0);
+            s.bid = dim3(bx, by, bz);
             s.alive = nthreads;
             s.bs = BlockSync();
             for (int w = 0; w < (nthreads + 31) / 32; ++w) s.ws[w] = WarpSync();
@@ -121,7 +124,7 @@ inline int launch(dim3 grid, int nthreads, std::function<void()> body) {
                 for (int t = 0; t < nthreads; ++t) {
                     if (s.done[t]) continue;
                     s.cur = t;
-                    s.tid = dim3(t, 0, 0);
+                    s.tid = dim3(t % block.x, (t / block.x) % block.y, t / (block.x * block.y));
                     swapcontext(&s.sched, &s.ctx[t]);
                 }
                 if (s.progress == before) {   // a full round without any collective completing
@@ -166,6 +169,10 @@ inline int block_barrier(int pred) {
         while (b.gen == g) yield_();
     }
     return b.out[g & 1];
+}
+
+inline int launch(dim3 grid, int nthreads, std::function<void()> body) {
+    return launch(grid, dim3((unsigned)nthreads), body);
 }
 
 }  // namespace ts_emu
@@ -252,6 +259,7 @@ static inline unsigned long long atomicCAS(unsigned long long* p, unsigned long 
     if (o == cmp) *p = v;
     return o;
 }
+static inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
 static inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
 static inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
 static inline int atomicMax(int* p, int v) { int o = *p; *p = std::max(o, v); return o; }

@@ -5,6 +5,7 @@
 // tensors: 16 B read + 12 B written per element (param, grad, exp_avg, exp_avg_sq), 128-bit
 // accesses, grid-stride over a flat (tensor, chunk) work list.  Arithmetic follows
 // torch.optim.Adam (no weight decay, no amsgrad) operation for operation.
+#include <cmath>
 #include "ts_common.cuh"
 
 namespace ts {
@@ -77,21 +78,16 @@ adam_multi_kernel(AdamTensors t, float omb1, float b2, float omb2, float eps) {
     }
 }
 
-}  // namespace ts
-
-extern "C" {
-
-int ts_adam_max_tensors(void) { return ts::kAdamMaxTensors; }
-
-int ts_adam_step(int num_tensors, float* const* params, const float* const* grads, float* const* exp_avgs,
-                 float* const* exp_avg_sqs, const int64_t* numels, const float* lrs, const int64_t* steps,
-                 double beta1, double beta2, double eps, ts_stream_t stream) {
-    if (num_tensors < 0 || num_tensors > ts::kAdamMaxTensors) return TS_ERR_INVALID;
+// Host side of ts_adam_step: validates the arguments and builds the flat (tensor, block) work list.
+// Returns TS_OK with blocks == 0 when there is nothing to do.
+static int adam_build(int num_tensors, float* const* params, const float* const* grads, float* const* exp_avgs,
+                      float* const* exp_avg_sqs, const int64_t* numels, const float* lrs, const int64_t* steps,
+                      double beta1, double beta2, AdamTensors& t, int& blocks) {
+    blocks = 0;
+    t.count = 0;
+    if (num_tensors < 0 || num_tensors > kAdamMaxTensors) return TS_ERR_INVALID;
     if (num_tensors == 0) return TS_OK;
     if (!params || !grads || !exp_avgs || !exp_avg_sqs || !numels || !lrs || !steps) return TS_ERR_INVALID;
-    ts::AdamTensors t;
-    t.count = 0;
-    int blocks = 0;
     for (int k = 0; k < num_tensors; ++k) {
         if (numels[k] < 0 || steps[k] < 1) return TS_ERR_INVALID;
         if (numels[k] == 0) continue;
@@ -104,11 +100,28 @@ int ts_adam_step(int num_tensors, float* const* params, const float* const* grad
         t.step_size[c] = (float)((double)lrs[k] / bc1);
         t.sqrt_bc2[c] = (float)sqrt(bc2);
         t.first_block[c] = blocks;
-        blocks += (int)((numels[k] + ts::kAdamChunk - 1) / ts::kAdamChunk);
+        blocks += (int)((numels[k] + kAdamChunk - 1) / kAdamChunk);
     }
     t.first_block[t.count] = blocks;
-    for (int c = t.count + 1; c <= ts::kAdamMaxTensors; ++c) t.first_block[c] = blocks;
-    if (blocks == 0) return TS_OK;
+    for (int c = t.count + 1; c <= kAdamMaxTensors; ++c) t.first_block[c] = blocks;
+    return TS_OK;
+}
+
+}  // namespace ts
+
+#ifndef TS_HOST_EMU
+extern "C" {
+
+int ts_adam_max_tensors(void) { return ts::kAdamMaxTensors; }
+
+int ts_adam_step(int num_tensors, float* const* params, const float* const* grads, float* const* exp_avgs,
+                 float* const* exp_avg_sqs, const int64_t* numels, const float* lrs, const int64_t* steps,
+                 double beta1, double beta2, double eps, ts_stream_t stream) {
+    ts::AdamTensors t;
+    int blocks = 0;
+    int rc = ts::adam_build(num_tensors, params, grads, exp_avgs, exp_avg_sqs, numels, lrs, steps, beta1, beta2, t,
+                            blocks);
+    if (rc != TS_OK || blocks == 0) return rc;
     ts::adam_multi_kernel<<<blocks, ts::kAdamThreads, 0, (cudaStream_t)stream>>>(
         t, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), (float)eps);
     TS_CHECK_LAUNCH("ts_adam_step");
@@ -116,3 +129,4 @@ int ts_adam_step(int num_tensors, float* const* params, const float* const* grad
 }
 
 }  // extern "C"
+#endif  // !TS_HOST_EMU

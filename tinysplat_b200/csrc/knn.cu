@@ -59,6 +59,7 @@ knn_kernel(int P1, int P2, const float* __restrict__ q, const float* __restrict_
 
 }  // namespace ts
 
+#ifndef TS_HOST_EMU
 extern "C" {
 
 int ts_knn_points(int P1, int P2, int K, const float* queries, const float* refs, float* dists, int64_t* idx,
@@ -84,3 +85,4 @@ int ts_knn_points(int P1, int P2, int K, const float* queries, const float* refs
 }
 
 }  // extern "C"
+#endif  // !TS_HOST_EMU

@@ -144,6 +144,7 @@ ssim_bwd_kernel(int C, int H, int W, const float* __restrict__ X, const float* _
 
 }  // namespace ts
 
+#ifndef TS_HOST_EMU
 extern "C" {
 
 int ts_ssim_fwd(int B, int C, int H, int W, const float* X, const int64_t* x_strides, const float* Y,
@@ -183,3 +184,4 @@ int ts_ssim_bwd(int B, int C, int H, int W, const float* X, const int64_t* x_str
 }
 
 }  // extern "C"
+#endif  // !TS_HOST_EMU
