@@ -187,3 +187,17 @@ def test_rowmask_sentinels(lib):
         q0 = np.array([8.0, 8.0, hx, hx], dtype=f)
         assert lib.ts_debug_rowmask(q0.ctypes.data_as(ctypes.c_void_p), q1.ctypes.data_as(ctypes.c_void_p),
                                     0, 0) == expect
+
+
+def test_optional_import_name_shims_resolve_to_the_fused_ops():
+    """shims/ provides the import names of two of the reference's absent third-party dependencies
+    (pytorch_msssim.SSIM, pytorch3d.ops.knn_points) on top of the fused kernels; opt-in via sys.path."""
+    import subprocess
+    import sys
+    code = ("import sys; sys.path[:0] = [%r, %r]; "
+            "from pytorch_msssim import SSIM; from pytorch3d.ops import knn_points, ball_query; "
+            "import tinysplat_b200.ssim as s, tinysplat_b200.knn as k; "
+            "assert SSIM is s.SSIM and knn_points is k.knn_points; "
+            "m = SSIM(data_range=1.0, size_average=True, channel=3)" % (ROOT, os.path.join(ROOT, "shims")))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
