@@ -182,6 +182,12 @@ def test_exact_rowmask_is_a_superset_of_lit_pixels_and_tight(lib):
 def test_rowmask_sentinels(lib):
     import numpy as np
     f = np.float32
+    # a conic that is not positive along x (broken covariance) or NaN: no culling at all
+    q0 = np.array([100.0, 40.0, 5.0, 5.0], dtype=f)
+    for A in (0.0, -0.3, float("nan")):
+        q1 = np.array([A, 0.1, 0.2, 0.5], dtype=f)
+        assert lib.ts_debug_rowmask(q0.ctypes.data_as(ctypes.c_void_p), q1.ctypes.data_as(ctypes.c_void_p),
+                                    0, 0) == 0xffffffff
     q1 = np.array([0.1, 0.0, 0.1, 0.5], dtype=f)
     for hx, expect in ((1e30, 0xffffffff), (-1e30, 0)):
         q0 = np.array([8.0, 8.0, hx, hx], dtype=f)

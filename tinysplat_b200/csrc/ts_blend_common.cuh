@@ -37,6 +37,9 @@ __host__ __device__ __forceinline__ unsigned footprint_rowmask(const float4 q0, 
     if (q0.z > 1e29f) return 0xffffffffu;
     if (q0.z < 0.f) return 0u;
     const float A = q1.x, B = q1.y, C = q1.z;
+    // a conic that is not positive along x (numerically broken covariance, NaN): no culling — the
+    // blend loop's own pw >= 0 / alpha >= 1/255 tests decide, exactly as without the mask
+    if (!(A > 0.f)) return 0xffffffffu;
     const float xr = q0.x - X0, yr = q0.y - Y0;       // centre relative to the tile's first pixel
     const float dxm = fmaxf(fabsf(xr), fabsf(xr - 15.f));
     const float dym = fmaxf(fabsf(yr), fabsf(yr - 15.f));
