@@ -57,7 +57,7 @@ def main():
     hy = np.sqrt(2 * tau * a / det)
 
     tot = dict(tile_3sigma=0, tile_bbox=0, tile_exact=0, sub_bbox=0, sub_exact=0, sub4_bbox=0,
-               sub4_exact=0, pix=0, row8_exact=0)
+               sub4_exact=0, pix=0, row8_exact=0, sub4x8_exact=0, row4_in_4x8=0, sub8x8_exact=0, sub8x2_exact=0)
     R = 64  # half window in pixels (Gaussians larger than this are clipped; rare at 6 px mean)
     for k in range(idx.numel()):
         x, y = xy[k]
@@ -106,7 +106,15 @@ def main():
         tot["sub4_bbox"] += sub4_b.sum()
         lit_4 = lit.reshape(n * 4, 4, n * 4, 4).any(axis=(1, 3)) & np.repeat(np.repeat(tile_ok, 4, 0), 4, 1)
         tot["sub4_exact"] += lit_4.sum()
+        # alternative group shapes for the grouped backward: 4 wide x 8 tall, 8 x 8, 8 x 2
+        lit_48 = lit.reshape(n * 2, 8, n * 4, 4).any(axis=(1, 3)) & np.repeat(np.repeat(tile_ok, 2, 0), 4, 1)
+        tot["sub4x8_exact"] += lit_48.sum()
+        lit_88 = lit.reshape(n * 2, 8, n * 2, 8).any(axis=(1, 3)) & np.repeat(np.repeat(tile_ok, 2, 0), 2, 1)
+        tot["sub8x8_exact"] += lit_88.sum()
+        lit_82 = lit.reshape(n * 8, 2, n * 2, 8).any(axis=(1, 3)) & np.repeat(np.repeat(tile_ok, 8, 0), 2, 1)
+        tot["sub8x2_exact"] += lit_82.sum()
         lit_in = lit & np.repeat(np.repeat(tile_ok, 16, 0), 16, 1)
+        tot["row4_in_4x8"] += lit_in.reshape(n * 16, n * 4, 4).any(axis=2).sum()
         tot["pix"] += lit_in.sum()
         tot["row8_exact"] += lit_in.reshape(n * 16, n * 2, 8).any(axis=2).sum()
 
@@ -118,6 +126,17 @@ def main():
     print(f"  lanes/iter bbox 4x4 : {tot['pix'] / (16 * tot['sub4_bbox']):.3f}")
     print(f"  lanes/iter exact 4x4: {tot['pix'] / (16 * tot['sub4_exact']):.3f}")
     print(f"  lanes/iter exact row8: {tot['pix'] / (8 * tot['row8_exact']):.3f}")
+    print(f"  lanes/iter exact row4: {tot['pix'] / (4 * tot['row4_in_4x8']):.3f}")
+    # instruction model of the grouped backward (per warp-iteration: head 32 + rows * 39 + reduce + reds),
+    # groups of a warp in lock-step (imbalance ~1.1 for 4 groups, ~1.2 for 8)
+    sc = scale / 1e6
+    for name, pairs, groups, rows, reduce, imb in (("8x4 (built)", tot["sub_exact"], 4, 4, 46, 1.1),
+                                                   ("8x2", tot["sub8x2_exact"], 4, 2, 46, 1.1),
+                                                   ("8x8", tot["sub8x8_exact"], 4, 8, 46, 1.1),
+                                                   ("4x8 (4-lane groups)", tot["sub4x8_exact"], 8, 8, 36, 1.2)):
+        iters = pairs * sc / groups * imb
+        print(f"  model {name:22s}: {pairs * sc:6.2f} M pairs, {iters:5.2f} M warp-iterations, "
+              f"{iters * (32 + rows * 39 + reduce + 14):6.0f} M warp-instructions")
 
 
 if __name__ == "__main__":
