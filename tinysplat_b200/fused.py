@@ -14,6 +14,7 @@ while the GPU still has SH work queued, then launches emit/sort/blend before the
 """
 from __future__ import annotations
 
+import os
 import weakref
 from typing import Tuple
 
@@ -28,6 +29,13 @@ BLOCK = 16
 _pinned_stats = {}
 _side_streams = {}
 USE_SIDE_STREAM = True     # SH kernels on a second stream, overlapping binning / projection-backward
+# Experiment for the next GPU session (off by default, unmeasured): run SH-BACKWARD on a
+# high-priority stream.  At equal priority projection-backward (77 registers, 3 CTAs fill an SM's
+# register file) reaches the SMs first and leaves room for one SH CTA, so the pair takes the sum of
+# its parts (91 us); with priority the DRAM-bound SH grid (32 registers) gets its slots as they free
+# up and one projection CTA still fits beside it.  TINYSPLAT_B200_SH_BWD_PRIORITY=1 enables it.
+SH_BWD_HIGH_PRIORITY = os.environ.get("TINYSPLAT_B200_SH_BWD_PRIORITY", "0") == "1"
+_prio_streams = {}
 
 
 def _side_stream(dev) -> "torch.cuda.Stream":
@@ -35,6 +43,15 @@ def _side_stream(dev) -> "torch.cuda.Stream":
     if key not in _side_streams:
         _side_streams[key] = torch.cuda.Stream(device=dev)
     return _side_streams[key]
+
+
+def _sh_bwd_stream(dev) -> "torch.cuda.Stream":
+    if not SH_BWD_HIGH_PRIORITY:
+        return _side_stream(dev)
+    key = str(dev)
+    if key not in _prio_streams:
+        _prio_streams[key] = torch.cuda.Stream(device=dev, priority=-1)
+    return _prio_streams[key]
 
 
 def _stats_buffer(dev) -> Tensor:
@@ -206,7 +223,7 @@ class _RenderFused(Function):
         # SH-backward (DRAM-bound) on the side stream, concurrent with projection-backward
         # (issue-bound); both only read the packed gradients
         main = torch.cuda.current_stream(dev)
-        side = _side_stream(dev) if USE_SIDE_STREAM else main
+        side = _sh_bwd_stream(dev) if USE_SIDE_STREAM else main
         if side is not main:
             side.wait_stream(main)
         with torch.cuda.stream(side):
