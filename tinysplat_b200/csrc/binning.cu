@@ -321,7 +321,13 @@ __device__ __forceinline__ void warp_sort_tile(uint64_t* sw, const uint64_t* __r
     __syncwarp(full);
 }
 
+// -DTS_SORT_MIN_CTAS=3 (compile-time experiment, unmeasured): the kernel uses 108 registers -> 2 CTAs
+// (16 warps) per SM; capped at 80 registers (16 bytes of spill) 3 CTAs fit.
+#ifdef TS_SORT_MIN_CTAS
+__global__ void __launch_bounds__(256, TS_SORT_MIN_CTAS)
+#else
 __global__ void __launch_bounds__(256)
+#endif
 bin_sort_warp_kernel(int T, const int32_t* __restrict__ offsets, const uint64_t* __restrict__ keys,
                      int32_t* __restrict__ ids_sorted) {
     __shared__ __align__(16) uint64_t s_keys[8 * kWarpSortSlice];
