@@ -300,6 +300,35 @@ int emu_shard_bwd_views(int n_views, int N, int K, int deg, int W, int H, const 
     return run();
 }
 
+// ts_project_fwd (gsplat contract: no packing / counting) on host pointers.
+int emu_project_fwd(int N, const float* means, const float* scales, const float* quats, const float* view,
+                    const float* fullproj, float fx, float fy, int W, int H, int flags, float* xys, float* depths,
+                    int32_t* radii, float* conics, int32_t* ntiles, float* cov3d) {
+    if (N == 0) return 0;
+    const int tx = (W + 15) / 16, ty = (H + 15) / 16;
+    const int grid = (N + ts::kProjThreads - 1) / ts::kProjThreads;
+    return ts_emu::launch(dim3(grid), ts::kProjThreads, [=]() {
+        ts::project_fwd_kernel(N, means, scales, 1.0f, (const float4*)quats, view, fullproj, fx, fy, W / 2.f, H / 2.f, H,
+                               W, tx, ty, 0.01f, flags, (float2*)xys, depths, radii, conics, ntiles, cov3d, nullptr, 0,
+                               nullptr, nullptr);
+    });
+}
+
+// ts_project_bwd on host pointers (explicit cotangents and/or packed rows, like the C-ABI entry).
+int emu_project_bwd(int N, const float* means, const float* scales, const float* quats, const float* view,
+                    const float* fullproj, float fx, float fy, int W, int H, int flags, const int32_t* radii,
+                    const float* v_xys, const float* v_depths, const float* v_conics, const float* packed,
+                    const float* logits, float* v_means, float* v_scales, float* v_quats, float* v_logit,
+                    float* v_xys_out) {
+    if (N == 0) return 0;
+    const int grid = (N + ts::kProjThreads - 1) / ts::kProjThreads;
+    return ts_emu::launch(dim3(grid), ts::kProjThreads, [=]() {
+        ts::project_bwd_kernel(N, means, scales, 1.0f, (const float4*)quats, view, fullproj, fx, fy, W / 2.f, H / 2.f, H,
+                               W, flags, radii, (const float2*)v_xys, v_depths, v_conics, (const float4*)packed, logits,
+                               v_means, v_scales, (float4*)v_quats, v_logit, (float2*)v_xys_out);
+    });
+}
+
 // ts_dp_prepare on host pointers.
 int emu_dp_prepare(int N, const int32_t* radii, const uint8_t* mask, const float* recs, float* grads, float* v_xys) {
     if (N == 0) return 0;

@@ -172,13 +172,11 @@ def test_fused_pipeline_on_the_emulator_with_extreme_gaussians(emu, seed):
     un-normalised quaternions, ragged image sizes: the grouped backward (exact row culling) and the
     first-generation backward (bounding-box culling) must both match the oracle.
 
-    Tolerances: image, colour and opacity gradients are tight.  The geometric gradients of the
-    screen-filling Gaussians are ill-conditioned in fp32 — projection-backward maps the conic
-    cotangent through v_cov = -X v_conic X, whose three terms nearly cancel for conics of 1e-4, so
-    the ~2e-5 relative error of blend-backward's sums (approximate reciprocal / exp2, fp32 sums of
-    thousands of signed pixel terms) is amplified a few hundred times — and are held to 5 % of the
-    tensor's largest gradient here (the two backward kernels, whose sums differ only in order, are
-    themselves 5e-3 apart after that amplification)."""
+    This test found the one numerical weakness of the first implementation: projection-backward
+    mapped the conic cotangent to the covariance as -X v X in conic space, which loses the long-axis
+    component of needle-shaped Gaussians to fp32 cancellation (30 % error on d/d log-scale of the
+    long axis, 1e-2 of the tensor's largest gradient).  It is evaluated in covariance space now
+    (csrc/project.cu, step (3)) and all gradients are held to 5e-4 here."""
     g = torch.Generator().manual_seed(seed)
     W = int(torch.randint(40, 100, (1,), generator=g))
     H = int(torch.randint(30, 80, (1,), generator=g))
@@ -206,9 +204,7 @@ def test_fused_pipeline_on_the_emulator_with_extreme_gaussians(emu, seed):
         assert _rel(out["v_xys"], rex["xys"].grad) < 5e-4
         for k in NAMES:
             assert np.isfinite(out[k]).all(), (bwd_mode, k)
-            tol = 5e-2 if k in ("means", "scales", "quats") else 5e-4
-            assert _rel(out[k].reshape(p[k].shape), p[k].grad) < tol, (bwd_mode, k)
+            assert _rel(out[k].reshape(p[k].shape), p[k].grad) < 5e-4, (bwd_mode, k)
         assert np.abs(out["opacities"][25:40]).max() == 0
     for k in NAMES:
-        tol = 2e-2 if k in ("means", "scales", "quats") else 1e-4
-        assert _rel(outs[1][k], torch.from_numpy(outs[0][k])) < tol, k
+        assert _rel(outs[1][k], torch.from_numpy(outs[0][k])) < 5e-4, k
