@@ -208,3 +208,48 @@ def test_fused_pipeline_on_the_emulator_with_extreme_gaussians(emu, seed):
         assert np.abs(out["opacities"][25:40]).max() == 0
     for k in NAMES:
         assert _rel(outs[1][k], torch.from_numpy(outs[0][k])) < 5e-4, k
+
+
+def test_projection_kernels_on_the_emulator_cover_the_frustum_clamp_and_culling(emu):
+    """K1 / K6 alone (gsplat contract: unit quaternions, linear scales, explicit cotangents): Gaussians
+    far outside the frustum (the EWA Jacobian's 1.3x frustum clamp is active and has zero gradient),
+    behind the camera and at the near plane, against the oracle."""
+    n, W, H = 400, 96, 64
+    cam = synthetic.make_camera(W, H)
+    sc = synthetic.make_scene(n, W, H, seed=77)
+    sc["means"][:80, 0] *= 6.0          # far to the sides: clamp in x
+    sc["means"][80:140, 1] *= 6.0       # clamp in y
+    sc["means"][140:160, 2] = -0.5      # behind the camera
+    sc["means"][160:170, 2] = 0.0101    # just past the near plane (0.01)
+    view = cam.view_matrix.float()
+    full = cam.proj_matrix.float() @ view
+    q = torch.nn.functional.normalize(sc["quats"], dim=-1)
+    scales = sc["scales"].exp()
+    tbd = ((W + 15) // 16, (H + 15) // 16, 1)
+    P = [sc["means"].double().requires_grad_(True), scales.double().requires_grad_(True), q.double().requires_grad_(True)]
+    xys, depths, radii, conics, nt, cov3d = oracle.project_gaussians(P[0], P[1], 1.0, P[2], view[:3].double(), full.double(),
+                                                                     cam.f_x, cam.f_y, W / 2, H / 2, H, W, tbd)
+    f = np.float32
+    a = dict(means=_c(sc["means"]), scales=_c(scales), quats=_c(q), view=_c(view), full=_c(full))
+    o = dict(xys=np.zeros((n, 2), f), dep=np.zeros(n, f), rad=np.zeros(n, np.int32), con=np.zeros((n, 3), f),
+             nt=np.zeros(n, np.int32), cov=np.zeros((n, 6), f))
+    assert emu.emu_project_fwd(n, ptr(a["means"]), ptr(a["scales"]), ptr(a["quats"]), ptr(a["view"]), ptr(a["full"]),
+                               cam.f_x, cam.f_y, W, H, 0, ptr(o["xys"]), ptr(o["dep"]), ptr(o["rad"]), ptr(o["con"]),
+                               ptr(o["nt"]), ptr(o["cov"])) == 0
+    assert np.abs(o["rad"] - radii.numpy()).max() <= 1 and (o["rad"][140:160] == 0).all()
+    same = o["rad"] == radii.numpy()
+    assert same.mean() > 0.99
+    assert _rel(o["xys"][same], xys.detach()[torch.from_numpy(same)]) < 1e-5
+    assert _rel(o["con"][same], conics.detach()[torch.from_numpy(same)]) < 1e-4
+    assert np.array_equal(o["nt"][same], nt.numpy()[same].astype(np.int32))
+    g = torch.Generator().manual_seed(1)
+    cx, cc, cd = torch.randn(n, 2, generator=g), torch.randn(n, 3, generator=g), torch.randn(n, generator=g)
+    torch.autograd.backward([xys, conics, depths], [cx.double(), cc.double(), cd.double()])
+    out = dict(means=np.zeros((n, 3), f), scales=np.zeros((n, 3), f), quats=np.zeros((n, 4), f))
+    rd = np.ascontiguousarray(radii.numpy().astype(np.int32))
+    assert emu.emu_project_bwd(n, ptr(a["means"]), ptr(a["scales"]), ptr(a["quats"]), ptr(a["view"]), ptr(a["full"]),
+                               cam.f_x, cam.f_y, W, H, 0, ptr(rd), ptr(_c(cx)), ptr(_c(cd)), ptr(_c(cc)), None, None,
+                               ptr(out["means"]), ptr(out["scales"]), ptr(out["quats"]), None, None) == 0
+    for k, ref in zip(("means", "scales", "quats"), P):
+        assert _rel(out[k], ref.grad) < 2e-4, k
+    assert np.abs(out["means"][140:160]).max() == 0

@@ -30,7 +30,7 @@ _pinned_stats = {}
 _side_streams = {}
 USE_SIDE_STREAM = True     # SH kernels on a second stream, overlapping binning / projection-backward
 # Experiment for the next GPU session (off by default, unmeasured): run SH-BACKWARD on a
-# high-priority stream.  At equal priority projection-backward (77 registers, 3 CTAs fill an SM's
+# high-priority stream.  At equal priority projection-backward (74 registers, 3 CTAs fill an SM's
 # register file) reaches the SMs first and leaves room for one SH CTA, so the pair takes the sum of
 # its parts (91 us); with priority the DRAM-bound SH grid (32 registers) gets its slots as they free
 # up and one projection CTA still fits beside it.  TINYSPLAT_B200_SH_BWD_PRIORITY=1 enables it.
