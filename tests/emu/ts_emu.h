@@ -67,6 +67,8 @@ struct State {
     BlockSync bs;
     std::function<void()> body;
     long progress = 0;     // bumped whenever a collective completes or a fiber finishes
+    int order = 0;         // 0 forward, 1 reverse, 2 random, 3 warpfirst, 4 warplast, 5/6 the same with lanes reversed
+    unsigned long long rng = 12345;
     bool deadlock = false;
 };
 inline State& st() { static State s; return s; }
@@ -98,7 +100,13 @@ inline void fiber_entry() {
 // (some lanes wait in a collective the others never reach).
 inline int launch(dim3 grid, dim3 block, std::function<void()> body) {
     State& s = st();
-    if (!s.stacks) s.stacks = (char*)malloc(kStack * kMaxThreads);
+    if (!s.stacks) {
+        s.stacks = (char*)malloc(kStack * kMaxThreads);
+        const char* o = getenv("TS_EMU_ORDER");
+        s.order = !o ? 0 : !strcmp(o, "reverse") ? 1 : !strcmp(o, "random") ? 2 : !strcmp(o, "warpfirst") ? 3
+                  : !strcmp(o, "warplast") ? 4 : !strcmp(o, "warpfirst-lanerev") ? 5
+                  : !strcmp(o, "warplast-lanerev") ? 6 : 0;
+    }
     const int nthreads = (int)(block.x * block.y * block.z);
     s.body = body;
     s.nthreads = nthreads;
@@ -119,13 +127,56 @@ inline int launch(dim3 grid, dim3 block, std::function<void()> body) {
                 s.ctx[t].uc_link = &s.sched;
                 makecontext(&s.ctx[t], (void (*)())fiber_entry, 0);
             }
+            auto resume = [&](int t) {
+                s.cur = t;
+                s.tid = dim3(t % block.x, (t / block.x) % block.y, t / (block.x * block.y));
+                swapcontext(&s.sched, &s.ctx[t]);
+            };
+            // Scheduling order (TS_EMU_ORDER).  Fibers only yield at collectives, so a kernel that reads
+            // shared memory another warp (or lane) writes WITHOUT a barrier / __syncwarp in between
+            // can still see the right data under one order and stale data under another.
+            //   forward / reverse / random : every round resumes every fiber once, in that order (warps
+            //                                stay within one collective of each other);
+            //   warpfirst / warplast       : one warp at a time runs as far as it can (until all of
+            //                                its lanes wait at a block barrier or have exited), lowest
+            //                                or highest warp first: the maximal skew between warps,
+            //                                which is what exposes a missing __syncthreads;
+            //   warpfirst-lanerev / warplast-lanerev : the same with the lanes of a warp resumed 31..0
+            //                                (a missing __syncwarp between a lane's shared-memory
+            //                                write and another lane's read).
+            const int nwarps = (nthreads + 31) / 32;
             while (s.alive > 0) {
                 long before = s.progress;
-                for (int t = 0; t < nthreads; ++t) {
-                    if (s.done[t]) continue;
-                    s.cur = t;
-                    s.tid = dim3(t % block.x, (t / block.x) % block.y, t / (block.x * block.y));
-                    swapcontext(&s.sched, &s.ctx[t]);
+                if (s.order >= 3) {
+                    for (int wi = 0; wi < nwarps; ++wi) {
+                        const int w = (s.order & 1) ? wi : nwarps - 1 - wi;     // 3, 5: lowest warp first
+                        for (;;) {      // run warp w while its own lanes keep completing collectives
+                            long b2 = s.progress;
+                            for (int li = 0; li < 32; ++li) {
+                                const int l = s.order >= 5 ? 31 - li : li;          // 5, 6: lanes in reverse
+                                const int t = w * 32 + l;
+                                if (t < nthreads && !s.done[t]) resume(t);
+                            }
+                            if (s.progress == b2) break;
+                        }
+                    }
+                } else {
+                    // random order: a fresh permutation per round (start + slot * odd stride modulo the
+                    // next power of two, skipping indices past the block)
+                    unsigned pow2 = 1;
+                    while ((int)pow2 < nthreads) pow2 <<= 1;
+                    s.rng = s.rng * 6364136223846793005ull + 1442695040888963407ull;
+                    const unsigned start = (unsigned)(s.rng >> 33) & (pow2 - 1), stride = ((unsigned)(s.rng >> 13) & (pow2 - 1)) | 1u;
+                    for (int slot = 0; slot < (s.order == 2 ? (int)pow2 : nthreads); ++slot) {
+                        int t = slot;
+                        if (s.order == 1) t = nthreads - 1 - slot;
+                        else if (s.order == 2) {
+                            t = (int)((start + (unsigned)slot * stride) & (pow2 - 1));
+                            if (t >= nthreads) continue;
+                        }
+                        if (s.done[t]) continue;
+                        resume(t);
+                    }
                 }
                 if (s.progress == before) {   // a full round without any collective completing
                     fprintf(stderr, "[ts_emu] deadlock in block (%u,%u): %d fibers stuck\n", bx, by, s.alive);

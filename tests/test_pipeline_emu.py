@@ -286,3 +286,28 @@ def test_fused_pipeline_on_the_emulator_random_audit(emu, seed):
     assert np.abs(out["rgb"] - rimg.detach().numpy()).max() < 2e-4
     for k_ in NAMES:
         assert _rel(out[k_].reshape(p[k_].shape), p[k_].grad) < 5e-4, k_
+
+
+@pytest.mark.parametrize("order", ["warpfirst", "warplast-lanerev", "random"])
+def test_kernels_do_not_depend_on_the_emulators_thread_order(order):
+    """A poor man's race check.  Emulator fibers yield only at collectives; by default every round
+    resumes every fiber once in thread order, so a kernel that reads shared memory written by
+    another warp (or lane) WITHOUT a barrier (or __syncwarp) in between would still see the right
+    data.  TS_EMU_ORDER re-runs kernel tests with one warp at a time running as far ahead as it can
+    (lowest or highest warp first, lanes optionally 31..0) and with random rounds; removing the
+    __syncthreads after the mask build of the grouped backward, for one, fails under the warp-skewed
+    orders and under none of the round-based ones."""
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    env = dict(os.environ, TS_EMU_ORDER=order)
+    sel = ("test_blend_kernels_match_the_oracle_on_the_emulator or test_split_rgb_depth or "
+           "test_binning_kernels_reproduce or (test_fused_pipeline_on_the_emulator_matches_the_oracle and 256) or "
+           "test_packed_exchange_shard_backward or test_fused_ssim or test_fused_adam")
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-p", "no:cacheprovider",
+                        os.path.join(here, "test_blend_emu.py"), os.path.join(here, "test_binning_emu.py"),
+                        os.path.join(here, "test_pipeline_emu.py"), os.path.join(here, "test_widenings_emu.py"),
+                        "-k", sel], capture_output=True, text=True, env=env, cwd=os.path.dirname(here))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout
