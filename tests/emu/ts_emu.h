@@ -295,6 +295,7 @@ static inline T emu_shfl_idx(T x, int src) {
 static inline float __shfl_sync(unsigned mask, float x, int src) { emu_require_full(mask); return emu_shfl_idx(x, src); }
 static inline int __shfl_sync(unsigned mask, int x, int src) { emu_require_full(mask); return emu_shfl_idx(x, src); }
 static inline unsigned __shfl_sync(unsigned mask, unsigned x, int src) { emu_require_full(mask); return emu_shfl_idx(x, src); }
+static inline int __popc(unsigned x) { return __builtin_popcount(x); }
 static inline int __ffs(unsigned x) { return __builtin_ffs((int)x); }
 template <typename T>
 static inline T __ldg(const T* p) { return *p; }

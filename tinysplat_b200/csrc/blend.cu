@@ -24,6 +24,13 @@ namespace ts {
 #ifndef TS_BLEND_TMA_GATHER
 #define TS_BLEND_TMA_GATHER 0
 #endif
+// -DTS_FWD_LISTS=1 (compile-time experiment, unmeasured; checked on the emulator): blend-forward turns
+// its warp's eight candidate-mask words into a byte list of staged indices once per batch (one POPC
+// pair per word) and walks that list, instead of BREV + FLO + two ALU ops per candidate.  ncu shows
+// the XU pipe (MUFU.EX2, BREV, FLO, POPC) at 46 % in this kernel.
+#ifndef TS_FWD_LISTS
+#define TS_FWD_LISTS 0
+#endif
 constexpr int kBlendThreads = 256;
 constexpr int kBatch = 256;
 
@@ -76,6 +83,9 @@ blend_fwd_kernel(int H, int W, int tbx, const int32_t* __restrict__ tile_offsets
                  int32_t* __restrict__ n_contrib, int clamp_max1) {
     __shared__ __align__(16) float4 s_rec[2][kBatch * 3];
     __shared__ unsigned s_mask[8][8];  // [sub-block][staging warp]
+#if TS_FWD_LISTS
+    __shared__ unsigned char s_list[8][kBatch];   // [sub-block][i]: staged index of its i-th candidate
+#endif
     const unsigned full = 0xffffffffu;
     const PixMap pm = pix_map(H, W);
     const int tid = threadIdx.x;
@@ -140,6 +150,46 @@ blend_fwd_kernel(int H, int W, int tbx, const int32_t* __restrict__ tile_offsets
         }
         __syncthreads();  // records + masks of batch b visible to all
         bool warp_done = __all_sync(full, done);
+#if TS_FWD_LISTS
+        if (!warp_done) {
+            int nlist = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const unsigned word = s_mask[pm.warp][k];
+                if ((word >> pm.lane) & 1u)
+                    s_list[pm.warp][nlist + __popc(word & ((1u << pm.lane) - 1u))] = (unsigned char)(k * 32 + pm.lane);
+                nlist += __popc(word);
+            }
+            __syncwarp(full);
+            for (int base = 0; base < nlist && !warp_done; base += 32) {
+              const int end = min(nlist, base + 32);
+              for (int i = base; i < end; ++i) {
+                const int g = s_list[pm.warp][i];
+                const float4 q0 = s_rec[buf][g * 3];
+                const float4 q1 = s_rec[buf][g * 3 + 1];
+                float dx, dy;
+                float pw = eval_power(q0, q1, pm.px, pm.py, dx, dy);
+                float alpha = fminf(kAlphaMax, __fmul_rn(q1.w, ex2_approx(-pw)));
+                if (!done && pw >= 0.f && alpha >= kAlphaMin) {
+                    float nT = T * (1.f - alpha);
+                    if (nT <= kTStop) {
+                        done = true;
+                    } else {
+                        const float4 q2 = s_rec[buf][g * 3 + 2];
+                        float wgt = alpha * T;
+                        acc[0] = fmaf(wgt, q2.x, acc[0]);
+                        if (CH > 1) acc[1] = fmaf(wgt, q2.y, acc[1]);
+                        if (CH > 2) acc[2] = fmaf(wgt, q2.z, acc[2]);
+                        if (CH > 3) acc[3] = fmaf(wgt, q2.w, acc[3]);
+                        T = nT;
+                        ncon = b * kBatch + g + 1;
+                    }
+                }
+              }
+              warp_done = __all_sync(full, done);
+            }
+        }
+#else
         if (!warp_done) {
             for (int k = 0; k < 8 && !warp_done; ++k) {
                 unsigned m = s_mask[pm.warp][k];
@@ -171,6 +221,7 @@ blend_fwd_kernel(int H, int W, int tbx, const int32_t* __restrict__ tile_offsets
                 warp_done = __all_sync(full, done);
             }
         }
+#endif
         // also guards reuse of s_rec[buf] / s_mask by the next iterations
         if (__syncthreads_and(warp_done)) break;
     }
