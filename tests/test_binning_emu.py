@@ -2,8 +2,6 @@
 scan -> emit -> per-tile sort), compiled as host code on the fiber SIMT emulator in tests/emu and
 compared with the oracle's bin_and_sort.  Integer / index work: bit-exact."""
 import ctypes as C
-import os
-import subprocess  # noqa: F401
 
 import numpy as np
 import pytest

@@ -6,8 +6,7 @@ exact row masks, the list walks, T-termination, n_contrib, the shared-memory gro
 the 8-lane transpose-reduce, the packed-gradient layout.  What it cannot cover (memory model,
 real async copies, occupancy) is left to the `-m gpu` tests."""
 import ctypes as C
-import os
-import subprocess  # noqa: F401
+import subprocess
 
 import numpy as np
 import pytest
