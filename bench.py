@@ -34,10 +34,17 @@ WORKLOADS = {
     "synthetic_500k_1080p": (500_000, 1920, 1080, 3, 0.0, False),
     "synthetic_2M_1080p_depthreg": (2_000_000, 1920, 1080, 3, 0.2, False),
     "synthetic_4M_4k_fwd": (4_000_000, 3840, 2160, 3, 0.0, True),
+    # dense stand-in for real captures (mean projected radius ~20 px instead of ~6: tile lists in the
+    # thousands, several staged batches per tile in the blend kernels, the CTA sort classes of K3)
+    "synthetic_dense_1M_1080p": (1_000_000, 1920, 1080, 3, 0.0, False),
     # small case for quick checks
     "synthetic_100k_720p": (100_000, 1280, 720, 3, 0.0, False),
 }
+SCENE_KW = {"synthetic_dense_1M_1080p": {"mean_radius_px": 20.0}}
 DEFAULT_WORKLOAD = "synthetic_1M_1080p"
+# extra measurements carried by the default single-GPU line (bench.py with no --workload/--pipeline):
+EXTRA_WORKLOADS = ["synthetic_500k_1080p", "synthetic_2M_1080p_depthreg", "synthetic_4M_4k_fwd",
+                   "synthetic_dense_1M_1080p"]
 
 
 def parse_args():
@@ -49,9 +56,13 @@ def parse_args():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--pipeline", default="fused", choices=["fused", "reference", "unfused4"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--grad-exchange", default="auto", choices=["auto", "allreduce", "packed"],
+    ap.add_argument("--grad-exchange", default="auto", choices=["auto", "allreduce", "packed", "peer"],
                     help="N > 1: how the per-Gaussian gradients are reduced over the ranks' views "
-                         "(auto = time both strategies during warm-up, keep the faster)")
+                         "(auto = time every strategy during warm-up, keep the fastest)")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the drop-in / other-workload measurements of the default single-GPU line")
+    ap.add_argument("--sustained-s", type=float, default=3.0,
+                    help="single GPU: also loop the step for this many seconds (0 = off)")
     ap.add_argument("--cpu-window", type=int, default=8, help="CPU sample: window edge in tiles")
     return ap.parse_args()
 
@@ -138,6 +149,8 @@ class ClockSampler:
 # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the `ncu --set full` capture of this
 # same command summarised in profiles/r1_ncu_full_all_kernels.txt and, for the blend kernels of the
 # current default (grouped backward), profiles/r1c_ncu_blend_mode4.txt (default workload, fused pipeline)
+NCU_TRAFFIC_SOURCE = ("constant from one `ncu --set full` capture of this command (profiles/), per launch; "
+                      "not re-measured in this run")
 NCU_TRAFFIC = {
     "synthetic_1M_1080p": {
         "ts_blend_bwd": (161.48 + 17.17) * 1e6, "ts_blend_fwd": (59.57 + 21.81) * 1e6,
@@ -169,6 +182,27 @@ def algorithmic_bytes(name: str, N: int, M: int, P: int, CH: int, K: int, nb: in
 
 
 # ---------------------------------------------------------------------------------------------
+def host_threads() -> int:
+    """The host threads this process may use.  torchrun exports OMP_NUM_THREADS=1 to its workers, so
+    the CPU arms set the thread count explicitly instead of inheriting it."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def static_config(workload: str, world: int) -> dict:
+    """The part of `config` that names the workload: identical in our arm and in --impl reference."""
+    N, W, H, deg, depth_w, fwd_only = WORKLOADS[workload]
+    return {"workload": workload, "gaussians": N, "width": W, "height": H, "sh_degree": deg,
+            "views_per_step": world, "mode": "fwd" if fwd_only else "fwd+bwd", "depth_loss_weight": depth_w,
+            "mean_radius_px": SCENE_KW.get(workload, {}).get("mean_radius_px", 6.0),
+            "parallelism": ("single GPU" if world == 1 else
+                            (f"replicas only x{world}" if fwd_only else f"dp{world} over cameras, replica per GPU")),
+            "l2": "inputs larger than L2: 236 B/Gaussian parameters + 48 B records + image buffers "
+                  "> 126 MB; a different camera every step"}
+
+
 def cpu_sample(workload: str, window_tiles: int, steps: int, warmup: int, threads: int | None = None):
     """Times the CPU oracle (our PyTorch restatement — the reference has no CPU rasterizer) on a
     bounded sample of the workload: the central window of `window_tiles`^2 tiles, with the
@@ -176,11 +210,10 @@ def cpu_sample(workload: str, window_tiles: int, steps: int, warmup: int, thread
     import oracle  # the checker, used here only as the reported CPU baseline
     from tinysplat_b200 import synthetic
     N, W, H, deg, depth_w, fwd_only = WORKLOADS[workload]
-    if threads:
-        torch.set_num_threads(threads)
+    torch.set_num_threads(threads or host_threads())
     cores = torch.get_num_threads()
     cam = synthetic.make_camera(W, H)
-    sc = synthetic.make_scene(N, W, H, seed=0)
+    sc = synthetic.make_scene(N, W, H, seed=0, **SCENE_KW.get(workload, {}))
     tbx, tby = (W + 15) // 16, (H + 15) // 16
     tx0, ty0 = (tbx - window_tiles) // 2, (tby - window_tiles) // 2
     win = (tx0, ty0, tx0 + window_tiles, ty0 + window_tiles)
@@ -217,29 +250,29 @@ def cpu_sample(workload: str, window_tiles: int, steps: int, warmup: int, thread
     sec = statistics.mean(times)
     desc = (f"central {window_tiles}x{window_tiles}-tile window ({window_tiles * 16}^2 px) of {workload}, "
             f"{n_sub} Gaussians reaching it, full adapter op sequence "
-            f"({'fwd' if fwd_only else 'fwd+bwd'}), fp32 torch CPU, {steps} steps")
+            f"({'fwd' if fwd_only else 'fwd+bwd'}), fp32 torch CPU, {cores} threads, {steps} steps")
     return pix / sec / 1e6, desc, cores, sec
 
 
 def run_reference(args):
     """--impl reference: the reference has no CPU (or any in-tree) implementation of this path —
     its arithmetic is the absent gsplat package — so this arm times our CPU restatement (the
-    oracle, kind "port") on the host cores, on a bounded sample of the same workload."""
+    oracle, kind "port") on the host cores, on a bounded sample of the same workload: each step
+    renders the central 8x8-tile window fwd+bwd (about 0.3 s), K steps after W warm-up steps."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    N, W, H, deg, depth_w, fwd_only = WORKLOADS[args.workload]
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
     steps, warmup = max(1, args.steps), max(0, args.warmup)
-    # bound the work: each sample step is O(1 s); keep the whole run within a few minutes
-    steps_eff, warm_eff = min(steps, 20), min(warmup, 3)
-    val, desc, cores, sec = cpu_sample(args.workload, args.cpu_window, steps_eff, warm_eff)
+    val, desc, cores, sec = cpu_sample(args.workload, args.cpu_window, steps, warmup, threads=host_threads())
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": steps_eff, "warmup": warm_eff, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "gaussians": N, "width": W, "height": H, "sh_degree": deg,
-                   "views_per_step": 1, "note": "CPU restatement on a bounded sample; host cores only"},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+        "config": static_config(args.workload, world),
+        "note": "CPU restatement (oracle) on a bounded sample; host cores only; the reference has no CPU path",
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc,
+                         "host_cpu_count": os.cpu_count(), "omp_num_threads_env": os.environ.get("OMP_NUM_THREADS")},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -247,149 +280,141 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------
-def run_ours(args):
-    import torch.distributed as dist
-    from tinysplat_b200 import _lib, synthetic, rasterize as rz
-    from tinysplat_b200.parallel import GradientAllReducer, PackedGradExchange
-    from tinysplat_b200.rasterizer import GaussianRasterizer, ParamModel
+class Arm:
+    """One (workload, pipeline) instance on this rank: the parameter replica, the adapter, the
+    gradient exchange and the two kinds of step the bench times."""
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise RuntimeError("bench.py (our arm) needs a CUDA device; there is no CPU fallback")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
-    _lib.load()
+    def __init__(self, workload: str, pipeline: str, dev, rank: int, world: int):
+        from tinysplat_b200 import synthetic
+        from tinysplat_b200.parallel import GradientAllReducer
+        from tinysplat_b200.rasterizer import GaussianRasterizer, ParamModel
+        self.workload, self.pipeline, self.dev, self.rank, self.world = workload, pipeline, dev, rank, world
+        self.N, self.W, self.H, self.deg, self.depth_w, self.fwd_only = WORKLOADS[workload]
+        self.P = self.W * self.H
+        sc = synthetic.make_scene(self.N, self.W, self.H, seed=0, **SCENE_KW.get(workload, {}))
+        self.model = ParamModel(sc, dev, self.deg, requires_grad=not self.fwd_only)   # same replica on every rank
+        self.rast = GaussianRasterizer(self.model, None, dev, pipeline)
+        self.reducer = None if self.fwd_only else GradientAllReducer(self.model.parameters(), average=True, overlap=True)
+        self.exchange = {"name": "allreduce" if (world > 1 and not self.fwd_only) else None}
+        # fixed cotangents for the device-resident arm (SURVEY.md 8d: "fixed cotangent v_out ~ U(0,1)
+        # so backward cost is content-independent"); the loss arithmetic is not part of the hot path
+        H, W, P = self.H, self.W, self.P
+        self.cot_img = torch.rand(H, W, 3, generator=torch.Generator().manual_seed(7)).to(dev) / (3 * P)
+        self.cot_depth = (self.depth_w * torch.rand(H, W, generator=torch.Generator().manual_seed(8)).to(dev) / P) \
+            if self.depth_w else None
 
-    N, W, H, deg, depth_w, fwd_only = WORKLOADS[args.workload]
-    P = W * H
-    sc = synthetic.make_scene(N, W, H, seed=0)          # every rank holds the same replica
-    model = ParamModel(sc, dev, deg, requires_grad=not fwd_only)
-    rast = GaussianRasterizer(model, None, dev, args.pipeline)
-    reducer = GradientAllReducer(model.parameters(), average=True, overlap=True) if not fwd_only else None
-    exchange = {"name": "allreduce", "probe_ms": None}
-
-    def set_exchange(name: str):
+    def set_exchange(self, name: str):
         """allreduce: NCCL all-reduce of the finished gradients (one flat 236 B/Gaussian span);
-        packed: all-to-all of blend-backward's packed rows + shard backward + all-gather (only the
-        fused pipeline; tinysplat_b200.parallel.PackedGradExchange)."""
-        nonlocal reducer
-        if reducer is not None:
-            reducer.close()
-        if name == "packed":
-            rast.grad_exchange = PackedGradExchange(average=True)
-            reducer = GradientAllReducer([], average=True, overlap=False)
+        packed: NCCL all-to-all of blend-backward's packed rows + shard backward + all-gather;
+        peer: the same shard backward with both transfers done by the kernels themselves over
+        NVLink peer memory (tinysplat_b200.parallel).  Fused pipeline only."""
+        from tinysplat_b200 import parallel
+        if self.reducer is not None:
+            self.reducer.close()
+        if name == "allreduce":
+            self.rast.grad_exchange = None
+            self.reducer = parallel.GradientAllReducer(self.model.parameters(), average=True, overlap=True)
         else:
-            rast.grad_exchange = None
-            reducer = GradientAllReducer(model.parameters(), average=True, overlap=True)
-        exchange["name"] = name
-    g = torch.Generator().manual_seed(100 + rank)
-    gt_host = torch.rand(H, W, 3, generator=g).pin_memory()
-    gt_dev = gt_host.to(dev)
-    K, Wm = max(1, args.steps), max(3, args.warmup)
+            cls = parallel.PackedGradExchange if name == "packed" else parallel.PeerGradExchange
+            self.rast.grad_exchange = cls(average=True)
+            self.reducer = parallel.GradientAllReducer([], average=True, overlap=False)
+        self.exchange["name"] = name
 
-    # fixed cotangents for the device-resident arm (SURVEY.md 8d: "fixed cotangent v_out ~ U(0,1)
-    # so backward cost is content-independent"); the loss arithmetic is not part of the hot path
-    cot_img = torch.rand(H, W, 3, generator=torch.Generator().manual_seed(7)).to(dev) / (3 * P)
-    cot_depth = (depth_w * torch.rand(H, W, generator=torch.Generator().manual_seed(8)).to(dev) / P) \
-        if depth_w else None
-
-    def path_step(i: int):
+    def path_step(self, i: int):
         """`value`: the hot path alone — adapter forward, backward from fixed cotangents."""
-        cam = view_for(i, rank, W, H)
-        if fwd_only:
+        cam = view_for(i, self.rank, self.W, self.H)
+        if self.fwd_only:
             with torch.no_grad():
-                rast(cam, (W, H), deg)
+                self.rast(cam, (self.W, self.H), self.deg)
             return
-        img, ex = rast(cam, (W, H), deg)
-        if cot_depth is not None:
-            torch.autograd.backward([img, ex["depth"]], [cot_img, cot_depth])
+        img, ex = self.rast(cam, (self.W, self.H), self.deg)
+        if self.cot_depth is not None:
+            torch.autograd.backward([img, ex["depth"]], [self.cot_img, self.cot_depth])
         else:
-            img.backward(cot_img)
-        reducer.finish()
-        model.zero_grad()
+            img.backward(self.cot_img)
+        self.reducer.finish()
+        self.model.zero_grad()
 
-    def one_step(i: int, gt: torch.Tensor):
+    def one_step(self, i: int, gt: torch.Tensor):
         """`e2e`: a training step as a user writes it — render, L1 (+depth) loss, backward."""
-        cam = view_for(i, rank, W, H)
-        if fwd_only:
+        cam = view_for(i, self.rank, self.W, self.H)
+        if self.fwd_only:
             with torch.no_grad():
-                img, ex = rast(cam, (W, H), deg)
+                img, ex = self.rast(cam, (self.W, self.H), self.deg)
             return img.mean()
-        img, ex = rast(cam, (W, H), deg)
+        img, ex = self.rast(cam, (self.W, self.H), self.deg)
         loss = (img - gt).abs().mean()
-        if depth_w:
-            loss = loss + depth_w * ex["depth"].abs().mean()
+        if self.depth_w:
+            loss = loss + self.depth_w * ex["depth"].abs().mean()
         loss.backward()
-        reducer.finish()
-        model.zero_grad()
+        self.reducer.finish()
+        self.model.zero_grad()
         return loss.detach()
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    def close(self):
+        if self.reducer is not None:
+            self.reducer.close()
+        ge = getattr(self.rast, "grad_exchange", None)
+        if ge is not None and hasattr(ge, "close"):
+            ge.close()
+        self.model = self.rast = self.reducer = None
+        torch.cuda.empty_cache()
 
-    def timed(fn, steps, first_index):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0 = time.time()
-        e0.record()
-        for i in range(steps):
-            fn(first_index + i)
-        e1.record()
-        barrier()
-        t1 = time.time()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return ms.item(), t0, t1
 
-    # ---- N > 1: pick the gradient-exchange strategy (untimed, before the warm-up proper) ------
-    if world > 1 and not fwd_only:
-        choice = args.grad_exchange if args.pipeline == "fused" else "allreduce"
-        if choice == "auto":
-            probe = {}
-            for name in ("allreduce", "packed"):
-                try:
-                    set_exchange(name)
-                    for i in range(3):
-                        path_step(i)
-                    probe[name] = timed(path_step, 5, 3)[0] / 5  # max over ranks: same on every rank
-                except Exception as e:                           # deterministic errors hit every rank alike
-                    probe[name] = float("inf")
-                    exchange["probe_error"] = f"{name}: {type(e).__name__}: {e}"[:200]
-                    model.zero_grad()
-            choice = min(probe, key=probe.get)
-            exchange["probe_ms"] = {k: (v if v != float("inf") else None) for k, v in probe.items()}
-        set_exchange(choice)
+def _barrier(world):
+    import torch.distributed as dist
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
 
-    # ---- device-resident arm: `value` -------------------------------------------------------
+
+def timed(fn, steps: int, first_index: int, world: int, dev):
+    """K steps bracketed by barrier + synchronize, CUDA events, max over ranks.  -> (ms, t0, t1)."""
+    import torch.distributed as dist
+    _barrier(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    e0.record()
+    for i in range(steps):
+        fn(first_index + i)
+    e1.record()
+    _barrier(world)
+    t1 = time.time()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return ms.item(), t0, t1
+
+
+def measure_value(arm: Arm, K: int, Wm: int, local: int, sample_clocks: bool):
+    """Device-resident arm.  -> dict(ms_step, value, prof, launches, clocks, M, max_per_tile)."""
+    from tinysplat_b200 import _lib, rasterize as rz
     for i in range(Wm):
-        path_step(i)
-    sampler = ClockSampler(local)
-    if rank == 0:
+        arm.path_step(i)
+    sampler = ClockSampler(local) if sample_clocks else None
+    if sampler:
         sampler.start()
     n0 = _lib.launch_count()
     _lib.profile_start()
-    ms_total, t0, t1 = timed(path_step, K, Wm)
+    ms_total, t0, t1 = timed(arm.path_step, K, Wm, arm.world, arm.dev)
     prof = _lib.profile_stop()
     launches = _lib.launch_count() - n0
-    clocks = sampler.stop(t0, t1) if rank == 0 else None
-    M = rz.last_stats["num_intersects"]
+    clocks = sampler.stop(t0, t1) if sampler else None
     ms_step = ms_total / K
-    value = world * P / (ms_step * 1e-3) / 1e6
+    return {"ms_step": ms_step, "ms_total": ms_total, "value": arm.world * arm.P / (ms_step * 1e-3) / 1e6,
+            "prof": prof, "launches": int(launches), "clocks": clocks,
+            "M": rz.last_stats["num_intersects"], "max_per_tile": rz.last_stats["max_per_tile"]}
 
-    # ---- end-to-end arm: host buffers in, loss out -------------------------------------------
-    # Every step copies ITS target image (pinned host -> device) and reads its loss back.  Like a
-    # training data loader, step i+1's image is prefetched on a copy stream while step i renders;
-    # all copies happen inside the timed region.
+
+def measure_e2e(arm: Arm, K: int):
+    """End-to-end arm: host buffers in, loss out.  Every step copies ITS target image (pinned host ->
+    device) and reads its loss back.  Like a training data loader, step i+1's image is prefetched on a
+    copy stream while step i renders; all copies happen inside the timed region."""
+    dev, H, W = arm.dev, arm.H, arm.W
+    g = torch.Generator().manual_seed(100 + arm.rank)
+    gt_host = torch.rand(H, W, 3, generator=g).pin_memory()
     copy_stream = torch.cuda.Stream(device=dev)
-    gt_bufs = [torch.empty_like(gt_dev), torch.empty_like(gt_dev)]
+    gt_bufs = [torch.empty(H, W, 3, device=dev), torch.empty(H, W, 3, device=dev)]
     copied = [torch.cuda.Event(), torch.cuda.Event()]      # H2D of buffer k finished
     consumed = [None, None]                                 # compute that read buffer k finished
     host_loss = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
@@ -419,7 +444,7 @@ def run_ours(args):
         issue_copy(i)
         issue_copy(i + 1)                                    # H2D of the next step's target image
         torch.cuda.current_stream().wait_event(copied[k])
-        loss = one_step(i, gt_bufs[k])
+        loss = arm.one_step(i, gt_bufs[k])
         consumed[k] = torch.cuda.Event()
         consumed[k].record()
         collect(k)                                           # (buffer k's previous loss, two steps ago)
@@ -430,12 +455,146 @@ def run_ours(args):
 
     for i in range(3):
         e2e_step(1000 + i)
-    ms_e2e, _, _ = timed(e2e_step, K, 2000)   # timed() ends with a device sync: every loss has landed
+    ms_e2e, _, _ = timed(e2e_step, K, 2000, arm.world, dev)   # ends with a device sync: every loss has landed
     collect(0)
     collect(1)
-    e2e_val = world * P / (ms_e2e / K * 1e-3) / 1e6
-    h2d = gt_host.numel() * 4 + 2 * 16 * 4                  # target image + view/proj matrices
-    d2h = 4 + 16                                            # loss scalar + binning stats (4 x int32)
+    return {"value": arm.world * arm.P / (ms_e2e / K * 1e-3) / 1e6, "unit": UNIT,
+            "h2d_bytes_per_step": gt_host.numel() * 4 + 2 * 16 * 4,      # target image + view/proj matrices
+            "d2h_bytes_per_step": 4 + 16,                                 # loss scalar + binning stats (4 x int32)
+            "ms_per_step": ms_e2e / K}
+
+
+def measure_sustained(arm: Arm, seconds: float, local: int):
+    """The device-resident step looped for >= `seconds` of wall time with the NVML clock / power
+    record: the burst-clock figure of the K-step region next to what the GPU holds under load."""
+    sampler = ClockSampler(local, period_s=0.02)
+    sampler.start()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    e0.record()
+    n = 0
+    while True:
+        for _ in range(50):
+            arm.path_step(5000 + n)
+            n += 1
+        if time.time() - t0 >= seconds:       # the host runs at most one step ahead (mid-step stats read)
+            break
+    e1.record()
+    torch.cuda.synchronize()
+    t1 = time.time()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop(t0, t1)
+    sm = sorted(x[1] for x in sampler.samples if t0 <= x[0] <= t1)
+    if sm:
+        clocks["sm_mhz_min"] = sm[0]
+        clocks["sm_mhz_p10"] = sm[len(sm) // 10]
+    return {"seconds": ms * 1e-3, "steps": n, "ms_per_step": ms / n, "value": arm.P / (ms / n * 1e-3) / 1e6,
+            "unit": UNIT, "clocks": clocks}
+
+
+def kernel_table(prof: dict, ms_total: float, K: int, N, M, P, CH, Kb, nb):
+    kern = {}
+    for name, ms_list in prof.items():
+        tot = sum(ms_list)
+        per = tot / len(ms_list)
+        by = algorithmic_bytes(name, N, M, P, CH, Kb, nb)
+        kern[name] = {"launches_per_step": len(ms_list) / K, "ms_per_launch": per, "ms_per_step": tot / K,
+                      "share": tot / ms_total, "algorithmic_bytes": by,
+                      "gbs": by / (per * 1e-3) / 1e9 if per > 0 else None}
+    return kern
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from tinysplat_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (our arm) needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+    K, Wm = max(1, args.steps), max(3, args.warmup)
+
+    arm = Arm(args.workload, args.pipeline, dev, rank, world)
+    N, W, H, deg, depth_w, fwd_only = WORKLOADS[args.workload]
+    P = W * H
+    probe = {}
+
+    # ---- N > 1: pick the gradient-exchange strategy (untimed, before the warm-up proper) ------
+    if world > 1 and not fwd_only:
+        choice = args.grad_exchange if args.pipeline == "fused" else "allreduce"
+        if choice == "auto":
+            for name in ("allreduce", "packed", "peer"):
+                try:
+                    arm.set_exchange(name)
+                    for i in range(3):
+                        arm.path_step(i)
+                    probe[name] = timed(arm.path_step, 5, 3, world, dev)[0] / 5   # max over ranks: same everywhere
+                except Exception as e:                           # deterministic errors hit every rank alike
+                    probe[name] = float("inf")
+                    probe[name + "_error"] = f"{type(e).__name__}: {e}"[:200]
+                    arm.model.zero_grad()
+            # every rank must take the same decision: rank 0's (the timings are max-reduced, but a
+            # failure on one rank only must not split the job)
+            best = min((n for n in ("allreduce", "packed", "peer")), key=lambda n: probe[n])
+            pick = torch.tensor([("allreduce", "packed", "peer").index(best)], device=dev)
+            dist.broadcast(pick, 0)
+            choice = ("allreduce", "packed", "peer")[int(pick.item())]
+        arm.set_exchange(choice)
+
+    main = measure_value(arm, K, Wm, local, sample_clocks=(rank == 0))
+    e2e = measure_e2e(arm, K)
+    sustained = None
+    if world == 1 and args.sustained_s > 0:
+        sustained = measure_sustained(arm, args.sustained_s, local)
+    exch_name = arm.exchange["name"]
+    exch_bytes = getattr(arm.rast.grad_exchange, "last_bytes_sent", None) if arm.rast.grad_exchange is not None else None
+    n_coll = arm.reducer.last_num_collectives if arm.reducer else 0
+    allreduce_bytes = arm.reducer.payload_bytes() if (arm.reducer and world > 1) else 0
+    arm.close()
+
+    # ---- the rest of the default single-GPU line: drop-in surface, other workloads ------------
+    default_line = (world == 1 and args.workload == DEFAULT_WORKLOAD and args.pipeline == "fused"
+                    and not args.no_extras)
+    dropin, workloads = None, None
+    if default_line:
+        try:
+            a = Arm(DEFAULT_WORKLOAD, "reference", dev, rank, world)
+            mv = measure_value(a, K, Wm, local, sample_clocks=False)
+            me = measure_e2e(a, K)
+            kt = kernel_table(mv["prof"], mv["ms_total"], K, N, mv["M"], P, 3, 16, (deg + 1) ** 2)
+            dropin = {"what": "the reference adapter's own op sequence through the five gsplat symbols "
+                              "(project_gaussians, sh.spherical_harmonics, rasterize_gaussians x2 + torch glue), "
+                              "no change to the reference [REF rasterize.py:26-62]",
+                      "value": mv["value"], "unit": UNIT, "ms_per_step": mv["ms_step"], "e2e": me["value"],
+                      "e2e_ms_per_step": me["ms_per_step"], "gpu_launches": mv["launches"],
+                      "intersections_M": mv["M"], "raster_passes_per_render": 2,
+                      "ts_kernels_ms_per_step": sum(v["ms_per_step"] for v in kt.values()),
+                      "kernels_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in kt.items()}}
+            a.close()
+        except Exception as exc:
+            dropin = {"error": repr(exc)[:300]}
+        workloads = {}
+        for wname in EXTRA_WORKLOADS:
+            try:
+                a = Arm(wname, "fused", dev, rank, world)
+                mv = measure_value(a, 10, 3, local, sample_clocks=False)
+                kt = kernel_table(mv["prof"], mv["ms_total"], 10, a.N, mv["M"], a.P, 4, 16, (a.deg + 1) ** 2)
+                workloads[wname] = {"value": mv["value"], "unit": UNIT, "ms_per_step": mv["ms_step"], "steps": 10,
+                                    "warmup": 3, "mode": "fwd" if a.fwd_only else "fwd+bwd",
+                                    "gaussians": a.N, "width": a.W, "height": a.H, "depth_loss_weight": a.depth_w,
+                                    "intersections_M": mv["M"], "max_per_tile": mv["max_per_tile"],
+                                    "kernels_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in kt.items()}}
+                a.close()
+            except Exception as exc:
+                workloads[wname] = {"error": repr(exc)[:300]}
 
     if world > 1:
         dist.barrier()
@@ -455,14 +614,8 @@ def run_ours(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-    kern = {}
-    for name, ms_list in prof.items():
-        tot = sum(ms_list)
-        per = tot / len(ms_list)
-        by = algorithmic_bytes(name, N, M, P, CH, Kb, nb)
-        kern[name] = {"launches_per_step": len(ms_list) / K, "ms_per_launch": per, "ms_per_step": tot / K,
-                      "share": tot / ms_total, "algorithmic_bytes": by,
-                      "gbs": by / (per * 1e-3) / 1e9 if per > 0 else None}
+    M = main["M"]
+    kern = kernel_table(main["prof"], main["ms_total"], K, N, M, P, CH, Kb, nb)
     top = max(kern, key=lambda k: kern[k]["ms_per_step"]) if kern else None
     roof = None
     if top:
@@ -470,9 +623,9 @@ def run_ours(args):
         traffic = NCU_TRAFFIC.get(args.workload, {}).get(top) if args.pipeline == "fused" else None
         roof = {"kernel": top, "bound": "hbm", "achieved": a, "peak": peak, "unit": "GB/s",
                 "frac": a / peak, "traffic": traffic, "peak_source": peak_src,
+                "traffic_source": NCU_TRAFFIC_SOURCE if traffic else None,
                 "note": "blend kernels are fp32-issue/atomic bound, not HBM bound (DESIGN.md); "
                         "streaming kernels listed in `kernels`"}
-
     # the best streaming (genuinely HBM-bound) kernel, for a roofline fraction that means something
     stream_names = [k for k in ("ts_sh_bwd", "ts_sh_fwd", "ts_project_bwd", "ts_project_fwd") if k in kern]
     best_stream = max(stream_names, key=lambda k: kern[k]["gbs"] or 0) if stream_names else None
@@ -481,38 +634,55 @@ def run_ours(args):
         roof_stream = {"kernel": best_stream, "bound": "hbm", "achieved": kern[best_stream]["gbs"], "peak": peak,
                        "unit": "GB/s", "frac": kern[best_stream]["gbs"] / peak,
                        "traffic": NCU_TRAFFIC.get(args.workload, {}).get(best_stream)}
+    cfg = static_config(args.workload, world)
+    run_info = {"pipeline": args.pipeline, "intersections_M": M, "max_per_tile": main["max_per_tile"],
+                "raster_passes_per_render": 2 if args.pipeline == "reference" else 1,
+                "value_step": "adapter forward (RGB+depth) + backward from fixed cotangents (SURVEY 8d)"
+                              + (" + gradient exchange" if world > 1 and not fwd_only else ""),
+                "e2e_step": "H2D target image + camera, adapter forward, L1 loss, backward, loss.item()",
+                "grad_exchange": exch_name,
+                "grad_exchange_what": {None: None,
+                                       "allreduce": "NCCL all-reduce of the finished gradients (one flat span)",
+                                       "packed": "NCCL all-to-all of packed rows + shard backward + NCCL all-gather",
+                                       "peer": "rank-structured exchange by the kernels themselves over NVLink peer "
+                                               "memory: packed geometry rows to the owner, colour cotangents to "
+                                               "every rank, shard projection-backward stores into every rank's "
+                                               "gradient buffer; no NCCL call in the step"}[exch_name],
+                "probe_allreduce_ms": probe.get("allreduce"), "probe_packed_ms": probe.get("packed"),
+                "probe_peer_ms": probe.get("peer"),
+                "probe_errors": {k: v for k, v in probe.items() if k.endswith("_error")} or None,
+                "grad_allreduce_collectives_per_step": n_coll, "grad_allreduce_bytes": allreduce_bytes,
+                "grad_exchange_bytes_sent_per_rank": exch_bytes}
+    for k in ("probe_allreduce_ms", "probe_packed_ms", "probe_peer_ms"):
+        if run_info[k] == float("inf"):
+            run_info[k] = None
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
-        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "metric": METRIC, "value": main["value"], "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
+        "ms_per_step": main["ms_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "gaussians": N, "width": W, "height": H, "sh_degree": deg,
-                   "views_per_step": world, "pipeline": args.pipeline, "intersections_M": M,
-                   "max_per_tile": rz.last_stats["max_per_tile"],
-                   "raster_passes_per_render": 2 if args.pipeline == "reference" else 1,
-                   "mode": "fwd" if fwd_only else "fwd+bwd", "depth_loss_weight": depth_w,
-                   "value_step": "adapter forward (RGB+depth) + backward from fixed cotangents (SURVEY 8d)",
-                   "e2e_step": "H2D target image + camera, adapter forward, L1 loss, backward, loss.item()",
-                   "parallelism": (f"dp{world} over cameras, replica per GPU, "
-                                   + ("NCCL all-reduce of the gradients" if exchange["name"] == "allreduce" else
-                                      "packed-row exchange: NCCL all-to-all + shard backward + all-gather"))
-                   if world > 1 and not fwd_only else ("replicas only" if world > 1 else "single GPU"),
-                   "grad_exchange": exchange["name"] if (world > 1 and not fwd_only) else None,
-                   "grad_exchange_probe_ms": exchange["probe_ms"],
-                   "grad_exchange_probe_error": exchange.get("probe_error"),
-                   "grad_allreduce_collectives_per_step": (reducer.last_num_collectives if reducer else 0),
-                   "grad_allreduce_bytes": (reducer.payload_bytes() if (reducer and world > 1) else 0),
-                   "grad_exchange_bytes_sent_per_rank": (rast.grad_exchange.last_bytes_sent
-                                                         if rast.grad_exchange is not None else None),
-                   "l2": "inputs larger than L2: 236 B/Gaussian parameters + 48 B records + image buffers "
-                         "> 126 MB; a different camera every step"},
-        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": ms_e2e / K},
-        "gpu_launches": int(launches),
-        "clocks": clocks,
+        "config": cfg,
+        "e2e": e2e,
+        "gpu_launches": main["launches"],
+        "clocks": main["clocks"],
         "roofline": roof,
         "roofline_streaming": roof_stream,
+        "run_info": run_info,
+        # flat copies of the exchange facts (nested dicts were dropped from the driver's record in round 1)
+        "grad_exchange": exch_name, "probe_allreduce_ms": run_info["probe_allreduce_ms"],
+        "probe_packed_ms": run_info["probe_packed_ms"], "probe_peer_ms": run_info["probe_peer_ms"],
         "kernels": kern,
     }
+    if sustained is not None:
+        sustained["burst_value"] = main["value"]
+        sustained["ratio_to_burst"] = sustained["value"] / main["value"]
+        line["sustained"] = sustained
+        line["sustained_value"] = sustained["value"]
+    if dropin is not None:
+        line["dropin"] = dropin
+        line["dropin_value"] = dropin.get("value")
+        line["dropin_e2e"] = dropin.get("e2e")
+    if workloads is not None:
+        line["workloads"] = workloads
     if world == 1 and not args.no_cpu_baseline:
         try:
             v, desc, cores, sec = cpu_sample(args.workload, args.cpu_window, 8, 2)

@@ -214,7 +214,9 @@ def project_gaussians(means3d: Tensor, scales: Tensor, glob_scale: float, quats:
         xy_safe = torch.nan_to_num(xy.detach(), nan=0.0, posinf=1e9, neginf=-1e9)
         lo, hi = tile_bbox(xy_safe, radius, tile_bounds)
         area = (hi[:, 0] - lo[:, 0]) * (hi[:, 1] - lo[:, 1])
-        ok = near_ok & det_ok & w_ok & (area > 0)
+        # a NaN covariance (zero-norm / NaN quaternion, NaN log-scale) passes det != 0 and has
+        # radius 0: culled like every other Gaussian that cannot reach a tile
+        ok = near_ok & det_ok & w_ok & (area > 0) & (radius > 0) & (det.detach() == det.detach())
 
     zt = torch.zeros((), dtype=dt)
     xys = torch.where(ok[:, None], xy, zt)

@@ -101,6 +101,36 @@ def test_forward_only_and_empty_scene_on_the_emulator(emu):
     assert np.abs(out["rgb"] - rimg.numpy()).max() < 5e-5
 
 
+def test_nan_covariance_gaussians_are_culled_consistently(emu):
+    """A zero-norm quaternion or a NaN log-scale gives a NaN 2D covariance: det != 0 holds for NaN,
+    the radius becomes 0 and its tile box still has area 1.  The fused projection must cull such a
+    Gaussian exactly where ts_bin_emit (radii > 0) skips it, otherwise the tile count exceeds the
+    emitted keys and an unwritten key slot is blended as a phantom Gaussian."""
+    n, W, H, deg = 200, 64, 48, 3
+    cam = synthetic.make_camera(W, H)
+    sc = synthetic.make_scene(n, W, H, seed=21)
+    sc["background"] = torch.tensor([0.3, 0.1, 0.6])
+    bad = [3, 50, 51, 120]
+    sc["quats"][3] = 0.0
+    sc["quats"][50, 1] = float("nan")
+    sc["scales"][51, 0] = float("nan")
+    sc["scales"][120] = float("inf")
+    keep = torch.ones(n, dtype=torch.bool)
+    keep[bad] = False
+    clean = {k: (v[keep].clone() if k != "background" else v) for k, v in sc.items()}
+    g = torch.Generator().manual_seed(3)
+    wi = torch.rand(H, W, 3, generator=g)
+    for mode in (0, 1):
+        a = _render(emu, sc, cam, W, H, deg, wi, None, mode)
+        b = _render(emu, clean, cam, W, H, deg, wi, None, mode)
+        assert a["stats"][0] == b["stats"][0]           # same number of (tile, Gaussian) pairs
+        assert (a["radii"][bad] == 0).all()
+        assert np.array_equal(a["rgb"], b["rgb"])
+        for k in ("means", "scales", "quats", "opacities", "colors_dc", "colors_rest"):
+            assert np.abs(a[k][bad]).max() == 0, k      # culled: zero gradients, not NaN
+            assert np.allclose(a[k][keep.numpy()], b[k], rtol=1e-5, atol=1e-9), k
+
+
 def test_packed_exchange_shard_backward_on_the_emulator(emu):
     """Two views: per view, forward + blend-backward + ts_dp_prepare produce the packed rows a rank
     would send; the multi-view shard kernels must return the average of the two plain backwards."""

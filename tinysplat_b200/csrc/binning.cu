@@ -438,12 +438,9 @@ int ts_bin_sort(int num_tiles, const int32_t* tile_offsets, uint64_t* keys, int3
     if (max_count <= 0) return TS_OK;
     if (!keys || !ids_sorted) return TS_ERR_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
-    static bool attr_set = false;
-    if (!attr_set) {
-        TS_CHECK_CUDA(cudaFuncSetAttribute(ts::bin_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           ts::kSmemSortCap * (int)sizeof(uint64_t)), "ts_bin_sort/attr");
-        attr_set = true;
-    }
+    // per device and context, cheap: set on every call (a process may drive several GPUs)
+    TS_CHECK_CUDA(cudaFuncSetAttribute(ts::bin_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       ts::kSmemSortCap * (int)sizeof(uint64_t)), "ts_bin_sort/attr");
     // lists of <= 512 entries: one warp per tile, keys in registers
     ts::bin_sort_warp_kernel<<<(num_tiles + 7) / 8, 256, 0, st>>>(num_tiles, tile_offsets, keys, ids_sorted);
     TS_CHECK_LAUNCH("ts_bin_sort/warp");

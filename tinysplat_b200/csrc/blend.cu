@@ -597,13 +597,10 @@ int ts_blend_bwd(int N, int CH, int img_height, int img_width, int tiles_x, int 
     }
 #define TS_LAUNCH_BWD(C, G)                                                                              \
     do {                                                                                                 \
-        static bool attr_done = false;                                                                   \
-        if (!attr_done) {                                                                                \
-            TS_CHECK_CUDA(cudaFuncSetAttribute(ts::blend_bwd_kernel<C, G>,                               \
-                                               cudaFuncAttributeMaxDynamicSharedMemorySize,              \
-                                               (int)ts::kBwdSmemBytes), "ts_blend_bwd/attr");            \
-            attr_done = true;                                                                            \
-        }                                                                                                \
+        /* per device and context, cheap: set on every call (a process may drive several GPUs) */       \
+        TS_CHECK_CUDA(cudaFuncSetAttribute(ts::blend_bwd_kernel<C, G>,                                   \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize,                  \
+                                           (int)ts::kBwdSmemBytes), "ts_blend_bwd/attr");                \
         ts::blend_bwd_kernel<C, G><<<grid, ts::kBlendThreads, ts::kBwdSmemBytes, st>>>(                  \
             img_height, img_width, tiles_x, tile_offsets, ids_sorted, (const float4*)recs, background,   \
             final_T, n_contrib, v_out_img, v_out_ch3, split_ch3, v_out_alpha, (float4*)grads);           \

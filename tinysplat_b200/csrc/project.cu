@@ -170,7 +170,11 @@ project_fwd_kernel(int N, const float* __restrict__ means, const float* __restri
     int lox, loy, hix, hiy;
     tile_bbox(bx, by, radius, tbx, tby, lox, loy, hix, hiy);
     int area = (hix - lox) * (hiy - loy);
-    bool ok = in && st.near_ok && st.det_ok && st.w_ok && (area > 0);
+    // radius > 0 and det == det: a NaN covariance (zero-norm / NaN quaternion, NaN log-scale) passes
+    // det != 0 and gives radius 0, whose tile box still has area 1; such a Gaussian is culled HERE,
+    // exactly where ts_bin_emit (radii > 0) skips it — otherwise the fused tile count and the
+    // emitted keys disagree and one key slot stays unwritten
+    bool ok = in && st.near_ok && st.det_ok && st.w_ok && (area > 0) && (radius > 0.f) && (st.det == st.det);
 
     s_buf[3 * tid + 0] = ok ? con0 : 0.f;
     s_buf[3 * tid + 1] = ok ? con1 : 0.f;

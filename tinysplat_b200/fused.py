@@ -36,6 +36,7 @@ USE_SIDE_STREAM = True     # SH kernels on a second stream, overlapping binning 
 # up and one projection CTA still fits beside it.  TINYSPLAT_B200_SH_BWD_PRIORITY=1 enables it.
 SH_BWD_HIGH_PRIORITY = os.environ.get("TINYSPLAT_B200_SH_BWD_PRIORITY", "0") == "1"
 _prio_streams = {}
+last_bins = None           # (tile_offsets, ids_sorted, M) of the most recent fused forward
 
 
 def _side_stream(dev) -> "torch.cuda.Stream":
@@ -136,9 +137,11 @@ class _RenderFused(Function):
         _lib.call("ts_bin_scan", T, _lib.ptr(counts), _lib.ptr(offsets), _lib.ptr(stats),
                   lib.ts_bin_smem_sort_cap(), st)
         host = _stats_buffer(dev)
-        host.copy_(stats[:4], non_blocking=True)
+        main_stream = torch.cuda.current_stream(dev)     # the tensors' device, not the current one
+        with torch.cuda.stream(main_stream):
+            host.copy_(stats[:4], non_blocking=True)
         ev = torch.cuda.Event()
-        ev.record()
+        ev.record(main_stream)
         ev.synchronize()
         M, max_count, n_big, _ = host.tolist()
         keys = torch.empty(max(M, 1), device=dev, dtype=torch.int64)
@@ -154,6 +157,8 @@ class _RenderFused(Function):
             _lib.call("ts_bin_sort", T, _lib.ptr(offsets), _lib.ptr(keys), _lib.ptr(ids_sorted), max_count,
                       n_big, _lib.ptr(big_scratch), _lib.ptr(big_counter), st)
         _rz.last_stats.update(num_intersects=M, max_per_tile=max_count, bins_reused=False)
+        global last_bins
+        last_bins = (offsets, ids_sorted, M)      # inspection hook (parity tests read the tile lists)
         if side is not main:
             main.wait_stream(side)          # colours must be in `recs` before blending
         rgb = torch.empty(H, W, 3, **f32)
