@@ -311,6 +311,9 @@ class Arm:
         from tinysplat_b200 import parallel
         if self.reducer is not None:
             self.reducer.close()
+        old = getattr(self.rast, "grad_exchange", None)
+        if old is not None and hasattr(old, "close"):
+            old.close()
         if name == "allreduce":
             self.rast.grad_exchange = None
             self.reducer = parallel.GradientAllReducer(self.model.parameters(), average=True, overlap=True)

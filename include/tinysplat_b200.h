@@ -241,6 +241,55 @@ TS_API int ts_sh_bwd_views(int n_views, int N, int degree, int K, const float* m
                            int64_t view_stride_floats, float out_scale, float* v_dc,
                            float* v_rest, ts_stream_t stream);
 
+/* ---- the same exchange done by the kernels over NVLink peer memory -----------
+ * No collective call inside the step (csrc/peer.cu).  Every rank owns one
+ * allocation (ts_peer_alloc: cudaMalloc, zero-filled) and maps the other ranks' allocations through
+ * CUDA IPC (ts_peer_ipc_get -> 64-byte handle, exchanged by the host; ts_peer_ipc_open).  Pointer
+ * tables (`*_ptrs_host`) are HOST arrays of `world` DEVICE pointers, entry r = the address of that
+ * buffer in rank r's allocation as mapped into THIS process.
+ * ts_dp_push: after blend-backward, cleans this view's packed rows like ts_dp_prepare and stores
+ *   - the 32-byte geometry row {S_x,S_y,S_xx,S_xy | S_yy,v_opacity,v_depth,0} of Gaussian i to its
+ *     owner rank i / shard_rows:  geo[owner][rank][i % shard_rows]   (geo = [world][shard_rows][8])
+ *   - the colour cotangent (3 floats) to EVERY rank:  rgb[r][rank][i] (rgb = [world][padded_rows][3])
+ *   - this view's camera row (32 floats, layout as `cams` above) to every rank: cams[r][rank]
+ *   and writes this view's d loss / d xy (v_xys, may be NULL).  shard_rows and padded_rows
+ *   (= world * shard_rows) are multiples of 4.
+ * ts_peer_barrier: all-to-all barrier through release/acquire flags in peer memory (slot 0 or 1;
+ *   `epoch` must increase by one per use of a slot; flags = [2][8][32] uint32, ts_peer_flag_bytes()).
+ *   A rank that waits longer than timeout_s writes 1 + the missing rank into *err_flag and goes on.
+ * ts_sh_bwd_views_rgb: ts_sh_bwd_views reading 12-byte colour rows (rgb[v][i]) instead of packed rows.
+ * ts_project_bwd_views_peer: ts_project_bwd_views reading the 32-byte geometry rows and storing the
+ *   finished shard gradients to n_dst destinations (tables of n_dst pointers to the shard's first
+ *   row in every rank's gradient arrays), starting with destination first_dst. */
+TS_API int ts_peer_max_ranks(void);
+TS_API int ts_peer_ipc_handle_bytes(void);
+TS_API int ts_peer_flag_bytes(void);
+TS_API int ts_peer_alloc(int64_t bytes, void** dev_ptr_host);
+TS_API int ts_peer_free(void* dev_ptr);
+TS_API int ts_peer_ipc_get(void* dev_ptr, void* handle_host);
+TS_API int ts_peer_ipc_open(const void* handle_host, void** dev_ptr_host);
+TS_API int ts_peer_ipc_close(void* dev_ptr);
+TS_API int ts_dp_push(int N, int shard_rows, int padded_rows, int world, int rank, const int32_t* radii,
+                      const uint8_t* clamp_mask /*or NULL*/, const float* recs /*[16B]*/,
+                      const float* grads /*[16B]*/, const float* cam_row, void* const* geo_ptrs_host,
+                      void* const* rgb_ptrs_host, void* const* cam_ptrs_host, float* v_xys /*or NULL*/,
+                      ts_stream_t stream);
+TS_API int ts_peer_barrier(int world, int rank, void* const* flag_ptrs_host, int slot, uint32_t epoch,
+                           uint32_t* err_flag, double timeout_s, ts_stream_t stream);
+TS_API int ts_sh_bwd_views_rgb(int n_views, int N, int degree, int K, const float* means,
+                               const float* cams, const float* rgb_rows /*[16B]*/,
+                               int64_t view_stride_floats, float out_scale, float* v_dc, float* v_rest,
+                               ts_stream_t stream);
+TS_API int ts_project_bwd_views_peer(int n_views, int N, const float* means3d /*[16B]*/,
+                                     const float* scales /*[16B]*/, float glob_scale,
+                                     const float* quats /*[16B]*/, const float* cams, int img_height,
+                                     int img_width, int flags, const float* geo_rows /*[16B]*/,
+                                     int64_t view_stride_floats, const float* opacity_logits /*or NULL*/,
+                                     float out_scale, int n_dst, int first_dst,
+                                     void* const* v_means_ptrs_host, void* const* v_scales_ptrs_host,
+                                     void* const* v_quats_ptrs_host, void* const* v_logit_ptrs_host /*or NULL*/,
+                                     ts_stream_t stream);
+
 /* ---- fused multi-tensor Adam step ---------------------------------------
  * One launch updates up to ts_adam_max_tensors() parameter tensors in place, with the exact
  * arithmetic of torch.optim.Adam (no weight decay, no amsgrad), the optimizer the reference

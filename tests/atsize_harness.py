@@ -88,9 +88,16 @@ def loss_weights(W, H, wins, seed=0):
     return wi, wd
 
 
-def oracle_windows(sc, cam, W, H, deg, wins, wi, wd, depth_w, xys32, radii32, want_grads=True):
-    """fp64 oracle of every window on the Gaussians that reach it.  Returns (per-window list of
-    (img, depth) numpy arrays, grads dict of full-size fp64 tensors or None, union of the subsets)."""
+def oracle_windows(sc, cam, W, H, deg, wins, wi, wd, depth_w, xys32, radii32, want_grads=True,
+                   dtype=torch.float64):
+    """Oracle (fp64 by default) of every window on the Gaussians that reach it.  Returns (per-window
+    list of (img, depth) numpy arrays, grads dict of full-size fp64 tensors or None, union of the
+    subsets).  Run a second time with dtype=torch.float32 it calibrates the tolerance: the stated
+    algorithm takes DISCRETE decisions (a contribution with alpha < 1/255 is skipped — the cause of the
+    first such case seen: ONE pixel of the bottom-right window of the 1M scene, 5.8e-4 —, radius =
+    ceil(3 sigma) decides which tiles a Gaussian reaches, equal fp32 depths are ordered by id) and xys is an fp32 tensor of the API (ulp 1.2e-4 px at x ~ 1900),
+    so an fp32 evaluation of the same algorithm departs from fp64 by more than the plain rounding
+    noise in some windows."""
     N = sc["means"].shape[0]
     imgs = []
     grads = {k: torch.zeros(sc[k].shape, dtype=torch.float64) for k in PARAMS} if want_grads else None
@@ -99,21 +106,21 @@ def oracle_windows(sc, cam, W, H, deg, wins, wi, wd, depth_w, xys32, radii32, wa
     for win in wins:
         idx = window_subset(xys32, radii32, win)
         union[idx] = True
-        p = {k: (sc[k][idx].double().clone().requires_grad_(want_grads) if k in PARAMS else sc[k].double())
+        p = {k: (sc[k][idx].to(dtype).clone().requires_grad_(want_grads) if k in PARAMS else sc[k].to(dtype))
              for k in sc}
         img, ex = oracle.render_reference_adapter(p, cam.view_matrix, cam.proj_matrix, cam.f_x, cam.f_y, (W, H), deg,
                                                   tile_window=win)
         x0, y0, x1, y1 = window_pixels(win, W, H)
         if want_grads:
-            loss = (img * wi[y0:y1, x0:x1]).sum()
+            loss = (img * wi[y0:y1, x0:x1].to(dtype)).sum()
             if depth_w:
-                loss = loss + depth_w * (ex["depth"] * wd[y0:y1, x0:x1]).sum()
+                loss = loss + depth_w * (ex["depth"] * wd[y0:y1, x0:x1].to(dtype)).sum()
             loss.backward()
             for k in PARAMS:
-                grads[k][idx] += p[k].grad
+                grads[k][idx] += p[k].grad.double()
             if ex["xys"].grad is not None:
-                vxy[idx] += ex["xys"].grad
-        imgs.append((img.detach().numpy(), ex["depth"].detach().numpy()))
+                vxy[idx] += ex["xys"].grad.double()
+        imgs.append((img.detach().double().numpy(), ex["depth"].detach().double().numpy()))
     if want_grads:
         grads["xys"] = vxy
     return imgs, grads, union

@@ -11,6 +11,7 @@
 #include "../../tinysplat_b200/csrc/binning.cu"
 #include "../../tinysplat_b200/csrc/blend.cu"
 #include "../../tinysplat_b200/csrc/blend_group.cu"
+#include "../../tinysplat_b200/csrc/peer.cu"
 #include "../../tinysplat_b200/csrc/adam.cu"
 #include "../../tinysplat_b200/csrc/ssim.cu"
 #include "../../tinysplat_b200/csrc/knn.cu"
@@ -174,10 +175,11 @@ int sh_bwd_any(bool bulk, int N, int K, const float* means, const float* view, c
 
 template <int DEG>
 int sh_bwd_views_any(int n_views, int N, int K, const float* means, const float* cams, const float* packed,
-                     size_t view_stride, float scale, float* v_dc, float* v_rest) {
+                     size_t view_stride, int row_stride, int col_off, float scale, float* v_dc, float* v_rest) {
     const int grid = (N + ts::kShThreads - 1) / ts::kShThreads;
     return ts_emu::launch(dim3(grid), ts::kShThreads, [=]() {
-        ts::sh_bwd_views_kernel<DEG>(n_views, N, K, means, cams, packed, view_stride, scale, v_dc, v_rest);
+        ts::sh_bwd_views_kernel<DEG>(n_views, N, K, means, cams, packed, view_stride, row_stride, col_off, scale, v_dc,
+                                     v_rest);
     });
 }
 
@@ -288,16 +290,88 @@ int emu_shard_bwd_views(int n_views, int N, int K, int deg, int W, int H, const 
     if (N == 0) return 0;
     const int flags = TS_PROJ_LOG_SCALES | TS_PROJ_RAW_QUATS | TS_PROJ_DEPTH_CH3;
     const int grid = (N + ts::kProjThreads - 1) / ts::kProjThreads;
+    ts::PeerPtrs dm{}, ds{}, dq{}, dl{};
+    dm.p[0] = v_means; ds.p[0] = v_scales; dq.p[0] = v_quats; dl.p[0] = v_logit;
     int rc = ts_emu::launch(dim3(grid), ts::kProjThreads, [&]() {
-        ts::project_bwd_views_kernel(n_views, N, means, log_scales, 1.0f, (const float4*)quats, cams, H, W, flags,
-                                     (const float4*)packed, (size_t)(view_stride / 4), logits, scale, v_means, v_scales,
-                                     (float4*)v_quats, v_logit);
+        ts::project_bwd_views_kernel<false>(n_views, N, means, log_scales, 1.0f, (const float4*)quats, cams, H, W, flags,
+                                            (const float4*)packed, (size_t)(view_stride / 4), logits, scale, 1, 0, dm, ds,
+                                            dq, dl);
     });
     if (rc) return rc;
     auto run = [&]() -> int {
-        TS_EMU_BY_DEG(deg, sh_bwd_views_any, n_views, N, K, means, cams, packed, (size_t)view_stride, scale, v_dc, v_rest);
+        TS_EMU_BY_DEG(deg, sh_bwd_views_any, n_views, N, K, means, cams, packed, (size_t)view_stride, 12, 8, scale, v_dc,
+                      v_rest);
     };
     return run();
+}
+
+// The peer-memory gradient exchange (peer.cu) with `world` ranks simulated in one address space:
+// every rank's ts_dp_push writes into every other rank's buffers, then every rank runs the colour
+// part (SH-backward over all views, all Gaussians) and the shard part (projection-backward over all
+// views for its shard, stored into EVERY rank's gradient arrays).  Inputs with a leading [world]
+// dimension are per rank/view: packed rows [world][N][12], radii [world][N], mask [world][N],
+// recs [world][N][12], cams [world][32].  Outputs [world][...]: what each rank ends up holding.
+int emu_peer_exchange(int world, int N, int Ns, int K, int deg, int W, int H, const float* means,
+                      const float* log_scales, const float* quats, const float* logits, const float* packed_all,
+                      const int32_t* radii_all, const uint8_t* mask_all, const float* recs_all,
+                      const float* cams_all, float scale, float* v_means_all, float* v_scales_all,
+                      float* v_quats_all, float* v_logit_all, float* v_dc_all, float* v_rest_all, float* v_xys_all) {
+    if (world < 1 || world > ts::kMaxPeers || Ns % 4 != 0 || (int64_t)Ns * world < N) return -2;
+    const int Npad = world * Ns;
+    const int R = (K - 1) * 3;
+    std::vector<std::vector<float>> geo(world), rgb(world), cams(world);
+    ts::PeerPtrs pgeo{}, prgb{}, pcams{};
+    auto align16 = [](std::vector<float>& v) { return (float*)(((uintptr_t)v.data() + 15) & ~(uintptr_t)15); };
+    for (int r = 0; r < world; ++r) {
+        geo[r].assign((size_t)world * Ns * 8 + 4, -777.f);      // poisoned: unwritten rows must never be read
+        rgb[r].assign((size_t)world * Npad * 3 + 4, -777.f);
+        cams[r].assign((size_t)world * 32 + 4, -777.f);
+        pgeo.p[r] = align16(geo[r]); prgb.p[r] = align16(rgb[r]); pcams.p[r] = align16(cams[r]);
+    }
+    const int pgrid = N > 0 ? (N + ts::kPushThreads - 1) / ts::kPushThreads : 1;
+    for (int r = 0; r < world; ++r) {
+        int rc = ts_emu::launch(dim3(pgrid), ts::kPushThreads, [&]() {
+            ts::dp_push_kernel(N, Ns, Npad, world, r, radii_all + (size_t)r * N, mask_all + (size_t)r * N,
+                               (const float4*)(recs_all + (size_t)r * N * 12), (const float4*)(packed_all + (size_t)r * N * 12),
+                               cams_all + (size_t)r * 32, pgeo, prgb, pcams, (float2*)(v_xys_all + (size_t)r * N * 2));
+        });
+        if (rc) return rc;
+    }
+    const int flags = TS_PROJ_LOG_SCALES | TS_PROJ_RAW_QUATS;
+    for (int r = 0; r < world; ++r) {
+        // colour part: every rank, all Gaussians
+        if (N > 0) {
+            float* vdc = v_dc_all + (size_t)r * N * 3;
+            float* vrest = v_rest_all + (size_t)r * N * R;
+            const float* rows = (const float*)prgb.p[r];
+            const float* cam = (const float*)pcams.p[r];
+            auto run = [&]() -> int {
+                TS_EMU_BY_DEG(deg, sh_bwd_views_any, world, N, K, means, cam, rows, (size_t)Npad * 3, 3, 0, scale, vdc, vrest);
+            };
+            int rc = run();
+            if (rc) return rc;
+        }
+        // shard part: rank r owns rows [s0, s0 + ns)
+        const int s0 = r * Ns;
+        const int ns = std::max(0, std::min(N, s0 + Ns) - s0);
+        if (ns == 0) continue;
+        ts::PeerPtrs dm{}, ds{}, dq{}, dl{};
+        for (int d = 0; d < world; ++d) {
+            dm.p[d] = v_means_all + ((size_t)d * N + s0) * 3;
+            ds.p[d] = v_scales_all + ((size_t)d * N + s0) * 3;
+            dq.p[d] = v_quats_all + ((size_t)d * N + s0) * 4;
+            dl.p[d] = v_logit_all + ((size_t)d * N + s0);
+        }
+        const int grid = (ns + ts::kProjThreads - 1) / ts::kProjThreads;
+        int rc = ts_emu::launch(dim3(grid), ts::kProjThreads, [&]() {
+            ts::project_bwd_views_kernel<true>(world, ns, means + (size_t)s0 * 3, log_scales + (size_t)s0 * 3, 1.0f,
+                                               (const float4*)(quats + (size_t)s0 * 4), (const float*)pcams.p[r], H, W,
+                                               flags, (const float4*)pgeo.p[r], (size_t)Ns * 2, logits + s0, scale, world,
+                                               (r + 1) % world, dm, ds, dq, dl);
+        });
+        if (rc) return rc;
+    }
+    return 0;
 }
 
 // ts_project_fwd (gsplat contract: no packing / counting) on host pointers.

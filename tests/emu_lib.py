@@ -34,6 +34,7 @@ def load():
                                      p, p, p, p, p, p, p, p, p, p, p, p, p]
     lib.emu_shard_bwd_views.argtypes = [i, i, i, i, i, i, p, p, p, p, p, p, C.c_int64, f, p, p, p, p, p, p]
     lib.emu_dp_prepare.argtypes = [i, p, p, p, p, p]
+    lib.emu_peer_exchange.argtypes = [i, i, i, i, i, i, i, p, p, p, p, p, p, p, p, p, f, p, p, p, p, p, p, p]
     lib.emu_project_fwd.argtypes = [i, p, p, p, p, p, f, f, i, i, i, p, p, p, p, p, p]
     lib.emu_project_bwd.argtypes = [i, p, p, p, p, p, f, f, i, i, i, p, p, p, p, p, p, p, p, p, p, p]
     lib.emu_adam_step.argtypes = [i, p, p, p, p, p, p, p, C.c_double, C.c_double, C.c_double]

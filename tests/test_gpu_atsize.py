@@ -7,6 +7,10 @@ longest list) with the fp64 CPU oracle run on the Gaussians that reach each wind
   * image and depth inside the windows: <= 2e-4 / 4e-3 absolute (depth values are up to ~10);
   * gradients of a window-restricted loss: <= 1e-3 of each tensor's largest entry, and EXACTLY zero
     for every Gaussian that reaches no window;
+    (each bound is widened to twice the gap between the fp32 and the fp64 evaluation of the ORACLE on
+    the same window where that is larger: first measured on the B200 at the bottom-right corner of
+    the 1M scene, GPU 5.79e-4 vs fp64, fp32 oracle 5.79e-4 vs fp64 — the discrete decisions of the
+    stated algorithm, not the kernels; every figure is printed)
   * the per-tile depth-sorted id lists of the window tiles: bit-exact against the oracle's order with
     culling off; with culling on a subsequence of it whose dropped entries cannot light a pixel;
   * PSNR(GPU, oracle) printed, and PSNR against a synthetic target image equal within 0.01 dB
@@ -81,29 +85,37 @@ def test_windows_of_baseline_workloads_match_the_oracle(name, pipeline):
         loss.backward()
     imgs, grads, union = ah.oracle_windows(sc, cam, W, H, deg, wins, wi, wd, dw, xys32, rad32,
                                            want_grads=not fwd_only)
+    # calibration: the same oracle evaluated in fp32 (see atsize_harness.oracle_windows)
+    imgs32, grads32, _ = ah.oracle_windows(sc, cam, W, H, deg, wins, wi, wd, dw, xys32, rad32,
+                                           want_grads=not fwd_only, dtype=torch.float32)
     img_c, dep_c = img.detach().cpu().double().numpy(), ex["depth"].detach().cpu().double().numpy()
     gt = torch.rand(H, W, 3, generator=torch.Generator().manual_seed(9), dtype=torch.float64).numpy()
-    for win, (oimg, odep) in zip(wins, imgs):
+    for win, (oimg, odep), (oimg32, odep32) in zip(wins, imgs, imgs32):
         x0, y0, x1, y1 = ah.window_pixels(win, W, H)
         g = img_c[y0:y1, x0:x1]
         e_img = np.abs(g - oimg).max()
         e_dep = np.abs(dep_c[y0:y1, x0:x1] - odep).max()
+        gap_img, gap_dep = np.abs(oimg32 - oimg).max(), np.abs(odep32 - odep).max()
         p_go = ah.psnr(g, oimg)
         p_g, p_o = ah.psnr(g, gt[y0:y1, x0:x1]), ah.psnr(oimg, gt[y0:y1, x0:x1])
-        print(f"{name} {pipeline} window {win}: longest list {int(counts.max())}, img err {e_img:.2e}, depth err "
-              f"{e_dep:.2e}, PSNR(gpu,oracle) {p_go:.1f} dB, PSNR vs target gpu {p_g:.4f} / oracle {p_o:.4f} dB")
-        assert e_img < TOL_IMG, (win, e_img)
-        assert e_dep < TOL_DEPTH, (win, e_dep)
+        print(f"{name} {pipeline} window {win}: longest list {int(counts.max())}, img err {e_img:.2e} (fp32-oracle gap "
+              f"{gap_img:.2e}), depth err {e_dep:.2e} (gap {gap_dep:.2e}), PSNR(gpu,oracle) {p_go:.1f} dB, "
+              f"PSNR vs target gpu {p_g:.4f} / oracle {p_o:.4f} dB")
+        assert e_img < max(TOL_IMG, 2 * gap_img), (win, e_img, gap_img)
+        assert e_dep < max(TOL_DEPTH, 2 * gap_dep), (win, e_dep, gap_dep)
         assert p_go > 80.0
         assert abs(p_g - p_o) < 0.01
     if fwd_only:
         return
-    for k in ah.PARAMS:
-        got = getattr(model, k).grad
+    for k in ah.PARAMS + ["xys"]:
+        got = ex["xys"].grad if k == "xys" else getattr(model, k).grad
         assert torch.isfinite(got).all(), k
-        assert _rel(got, grads[k]) < TOL_GRAD, k
-        assert got.cpu()[~union].abs().max().item() == 0.0, k      # untouched Gaussians: exactly zero
-    assert _rel(ex["xys"].grad, grads["xys"]) < TOL_GRAD
+        gap = _rel(grads32[k], grads[k])
+        err = _rel(got, grads[k])
+        print(f"{name} {pipeline} grad {k}: rel err {err:.2e} (fp32-oracle gap {gap:.2e})")
+        assert err < max(TOL_GRAD, 2 * gap), (k, err, gap)
+        if k != "xys":
+            assert got.cpu()[~union].abs().max().item() == 0.0, k      # untouched Gaussians: exactly zero
 
 
 @pytest.mark.parametrize("name", list(ah.CONFIGS))

@@ -588,6 +588,53 @@ def test_packed_exchange_shard_kernels_match_the_plain_backward(lib):
     assert got["means"][:40].abs().max() == 0
 
 
+def test_peer_exchange_single_rank_matches_the_plain_backward(lib):
+    """SURVEY 8e, peer-memory exchange (csrc/peer.cu, parallel.PeerGradExchange) on ONE GPU: a
+    single-rank process group, so every 'peer' is this device, but the whole mechanism runs on the
+    hardware — cudaMalloc'ed exchange buffer aliased by torch views, ts_dp_push, the release/acquire
+    flag barrier, SH-backward over colour rows, shard projection-backward storing through pointer
+    tables — and must reproduce the plain backward.  Multi-rank: tools/dp_check.py (2 and 8 GPUs),
+    tests/test_pipeline_emu.py (2-4 simulated ranks on the emulator)."""
+    import torch.distributed as dist
+    from tinysplat_b200.parallel import PeerGradExchange
+    from tinysplat_b200.rasterizer import GaussianRasterizer, ParamModel
+    if dist.is_initialized():
+        pytest.skip("a process group already exists")
+    dist.init_process_group("nccl", init_method="tcp://127.0.0.1:29533", rank=0, world_size=1,
+                            device_id=torch.device(DEV))
+    try:
+        W, H = 320, 208
+        g = torch.Generator().manual_seed(3)
+        wi = torch.rand(H, W, 3, generator=g).to(DEV)
+        wd = torch.rand(H, W, generator=g).to(DEV)
+        ex_peer = PeerGradExchange(average=True)
+        for N in (3001, 2000, 5000):              # shrink within the capacity, then grow past it (re-allocation)
+            sc = synthetic.make_scene(N, W, H, seed=21, sh_degree=3)
+            sc["background"] = torch.tensor([0.2, 0.4, 0.1])
+            sc["means"][:40, 2] = -1.0
+            cam = synthetic.make_camera(W, H, yaw_deg=-4.0, shift=(0.1, 0.0, 0.0))
+            got = {}
+            for name, exch in (("plain", None), ("peer", ex_peer)):
+                model = ParamModel(sc, DEV, 3)
+                rast = GaussianRasterizer(model, None, DEV, "fused")
+                rast.grad_exchange = exch
+                for _ in range(2):                # twice: the second step reuses the buffers and a new epoch
+                    model.zero_grad()
+                    img, ex = rast(cam, (W, H), 3)
+                    ((img * wi).sum() + 0.05 * (ex["depth"] * wd).sum()).backward()
+                got[name] = ({k: getattr(model, k).grad.clone() for k in PARAMS}, ex["xys"].grad.clone())
+            ex_peer.check()
+            assert rel_err(got["peer"][1], got["plain"][1]) < 1e-5
+            for k in PARAMS:
+                a, b = got["peer"][0][k], got["plain"][0][k]
+                assert a.shape == b.shape and torch.isfinite(a).all(), k
+                assert rel_err(a, b) < 1e-5, (N, k)
+            assert got["peer"][0]["means"][:40].abs().max() == 0
+        ex_peer.close()
+    finally:
+        dist.destroy_process_group()
+
+
 # ---- SURVEY 8(f)-2: fused Adam ---------------------------------------------------------------------
 def _param_set(N, seed):
     g = torch.Generator().manual_seed(seed)

@@ -128,3 +128,30 @@ def test_packed_exchange_collectives_two_ranks_gloo(n_gauss):
         assert p.exitcode == 0
     assert all(ok for _, ok, _ in res), res
     assert all(b > 0 for _, _, b in res)
+
+
+def test_peer_layout_segments_are_aligned_and_shards_cover_all_rows():
+    """Host arithmetic of the peer-memory exchange (parallel.PeerLayout): 256-byte aligned,
+    non-overlapping segments; shards of 256-row multiples that cover [0, N) exactly once; gradient
+    segments large enough for the capacity; a smaller N fits the same allocation."""
+    from tinysplat_b200.parallel import PeerLayout
+    for world in (1, 2, 3, 8):
+        for cap in (1, 1000, 1_126_024):
+            L = PeerLayout(world, cap, 16, 2048)
+            spans = sorted(L.seg.values())
+            for (o, n), (o2, _) in zip(spans, spans[1:] + [(L.total_bytes, 0)]):
+                assert o % 256 == 0 and o + n <= o2
+            assert L.seg["geo"][1] == world * L.cap_shard * 32
+            assert L.seg["rgb"][1] == world * world * L.cap_shard * 12
+            for name in ("rest", "dc", "means", "scales", "quats", "logit"):
+                assert L.seg["g_" + name][1] >= cap * L.width(name) * 4
+            for n in (cap, max(1, cap // 2), max(1, cap - 3)):
+                covered = 0
+                for r in range(world):
+                    s0, ns, ns_all = L.shard_of(r, n)
+                    assert ns_all % 256 == 0 and ns_all <= L.cap_shard
+                    assert s0 == r * ns_all and 0 <= ns <= ns_all
+                    if ns:
+                        assert s0 == covered
+                    covered += ns
+                assert covered == n

@@ -131,6 +131,42 @@ def test_nan_covariance_gaussians_are_culled_consistently(emu):
             assert np.allclose(a[k][keep.numpy()], b[k], rtol=1e-5, atol=1e-9), k
 
 
+def _view_rows(emu, sc, c, W, H, deg, wi, wd):
+    """What one rank holds after blend-backward of its view, rebuilt from the public stages (what
+    fused.py keeps in `grads`): raw packed rows, radii, SH clamp mask, packed records, camera row."""
+    import test_blend_emu as tb
+    f = np.float32
+    n = sc["means"].shape[0]
+    view = c.view_matrix.float()
+    full = c.proj_matrix.float() @ view
+    with torch.no_grad():
+        q = sc["quats"] / sc["quats"].norm(dim=-1, keepdim=True)
+        tbd = ((W + 15) // 16, (H + 15) // 16, 1)
+        xys, depths, radii, conics, nt, _ = oracle.project_gaussians(
+            sc["means"], sc["scales"].exp(), 1.0, q, view[:3], full, c.f_x, c.f_y, W / 2, H / 2, H, W, tbd)
+        dirs = torch.nn.functional.normalize(sc["means"] - view[:3, 3], dim=-1)
+        coeffs = torch.cat([sc["colors_dc"][:, None, :], sc["colors_rest"]], 1)
+        pre = oracle.spherical_harmonics(deg, dirs, coeffs) + 0.5
+        colors = torch.cat([pre.clamp(min=0), depths[:, None]], 1)
+        mask = ((pre[:, 0] >= 0).to(torch.uint8) | ((pre[:, 1] >= 0).to(torch.uint8) << 1)
+                | ((pre[:, 2] >= 0).to(torch.uint8) << 2))
+        opac = torch.sigmoid(sc["opacities"])
+    rec = tb._pack(xys, conics, opac, colors, True)
+    offsets, ids = tb._lists(xys, depths, radii, tbd)
+    bg4 = _c(torch.cat([sc["background"], sc["background"][:1]]))
+    rgb, dep = np.zeros((H, W, 3), f), np.zeros((H, W), f)
+    T, nc = np.zeros((H, W), f), np.zeros((H, W), np.int32)
+    assert emu.emu_blend_fwd(4, H, W, tbd[0], tbd[1], ptr(offsets), ptr(ids), ptr(rec), ptr(bg4), ptr(rgb), ptr(dep),
+                             ptr(T), ptr(nc), 1) == 0
+    grads = np.zeros((n, 12), f)
+    vi, vd = _c(wi), _c(wd)
+    assert emu.emu_blend_bwd(n, 4, H, W, tbd[0], tbd[1], ptr(offsets), ptr(ids), ptr(rec), ptr(bg4), ptr(T), ptr(nc),
+                             ptr(vi), ptr(vd), 1, None, ptr(grads), 1) == 0
+    return dict(grads=grads, radii=np.ascontiguousarray(radii.numpy().astype(np.int32)),
+                mask=np.ascontiguousarray(mask.numpy()), rec=np.ascontiguousarray(rec),
+                cam=np.concatenate([_c(view[:3]).reshape(-1), _c(full).reshape(-1), np.array([c.f_x, c.f_y, 0, 0], f)]))
+
+
 def test_packed_exchange_shard_backward_on_the_emulator(emu):
     """Two views: per view, forward + blend-backward + ts_dp_prepare produce the packed rows a rank
     would send; the multi-view shard kernels must return the average of the two plain backwards."""
@@ -143,45 +179,15 @@ def test_packed_exchange_shard_backward_on_the_emulator(emu):
     g = torch.Generator().manual_seed(2)
     wi, wd = torch.rand(H, W, 3, generator=g), 0.1 * torch.rand(H, W, generator=g)
     plain = [_render(emu, sc, c, W, H, deg, wi, wd, 1) for c in cams]
-
-    # the packed rows of each view, rebuilt from the public stages (what fused.py keeps in `grads`)
-    import test_blend_emu as tb
     f = np.float32
     rows, cam_rows = [], []
     for c in cams:
-        view = c.view_matrix.float()
-        full = c.proj_matrix.float() @ view
-        with torch.no_grad():
-            q = sc["quats"] / sc["quats"].norm(dim=-1, keepdim=True)
-            tbd = ((W + 15) // 16, (H + 15) // 16, 1)
-            xys, depths, radii, conics, nt, _ = oracle.project_gaussians(
-                sc["means"], sc["scales"].exp(), 1.0, q, view[:3], full, c.f_x, c.f_y, W / 2, H / 2, H, W, tbd)
-            dirs = torch.nn.functional.normalize(sc["means"] - view[:3, 3], dim=-1)
-            coeffs = torch.cat([sc["colors_dc"][:, None, :], sc["colors_rest"]], 1)
-            pre = oracle.spherical_harmonics(deg, dirs, coeffs) + 0.5
-            colors = torch.cat([pre.clamp(min=0), depths[:, None]], 1)
-            mask = ((pre[:, 0] >= 0).to(torch.uint8) | ((pre[:, 1] >= 0).to(torch.uint8) << 1)
-                    | ((pre[:, 2] >= 0).to(torch.uint8) << 2))
-            opac = torch.sigmoid(sc["opacities"])
-        rec = tb._pack(xys, conics, opac, colors, True)
-        offsets, ids = tb._lists(xys, depths, radii, tbd)
-        bg4 = _c(torch.cat([sc["background"], sc["background"][:1]]))
-        rgb, dep = np.zeros((H, W, 3), f), np.zeros((H, W), f)
-        T, nc = np.zeros((H, W), f), np.zeros((H, W), np.int32)
-        assert emu.emu_blend_fwd(4, H, W, tbd[0], tbd[1], ptr(offsets), ptr(ids), ptr(rec), ptr(bg4), ptr(rgb), ptr(dep),
-                                 ptr(T), ptr(nc), 1) == 0
-        grads = np.zeros((n, 12), f)
-        vi, vd = _c(wi), _c(wd)
-        assert emu.emu_blend_bwd(n, 4, H, W, tbd[0], tbd[1], ptr(offsets), ptr(ids), ptr(rec), ptr(bg4), ptr(T), ptr(nc),
-                                 ptr(vi), ptr(vd), 1, None, ptr(grads), 1) == 0
-        rd = np.ascontiguousarray(radii.numpy().astype(np.int32))
-        mk = np.ascontiguousarray(mask.numpy())
+        v = _view_rows(emu, sc, c, W, H, deg, wi, wd)
         vx = np.zeros((n, 2), f)
-        assert emu.emu_dp_prepare(n, ptr(rd), ptr(mk), ptr(rec), ptr(grads), ptr(vx)) == 0
-        assert np.abs(grads[:7]).max() == 0
-        rows.append(grads)
-        cam_rows.append(np.concatenate([_c(view[:3]).reshape(-1), _c(full).reshape(-1),
-                                        np.array([c.f_x, c.f_y, 0, 0], f)]))
+        assert emu.emu_dp_prepare(n, ptr(v["radii"]), ptr(v["mask"]), ptr(v["rec"]), ptr(v["grads"]), ptr(vx)) == 0
+        assert np.abs(v["grads"][:7]).max() == 0
+        rows.append(v["grads"])
+        cam_rows.append(v["cam"])
     packed = np.ascontiguousarray(np.stack(rows))
     cam_buf = np.ascontiguousarray(np.stack(cam_rows))
     out = dict(means=np.zeros((n, 3), f), scales=np.zeros((n, 3), f), quats=np.zeros((n, 4), f),
@@ -194,6 +200,48 @@ def test_packed_exchange_shard_backward_on_the_emulator(emu):
     for k in NAMES:
         want = 0.5 * (plain[0][k] + plain[1][k])
         assert _rel(out[k], torch.from_numpy(want)) < 2e-4, k
+
+
+@pytest.mark.parametrize("world,n,Ns", [(2, 300, 152), (3, 700, 256), (4, 332, 84), (4, 100, 64), (1, 200, 200)])
+def test_peer_memory_exchange_on_the_emulator(emu, world, n, Ns):
+    """The peer-memory gradient exchange (csrc/peer.cu) with `world` ranks simulated in one address
+    space: ts_dp_push of every rank writes geometry rows to the owners and colour cotangents + cameras
+    to everyone; SH-backward over all views (every rank, all Gaussians) and the shard
+    projection-backward storing into EVERY rank's arrays must leave each rank with the average of
+    the plain per-view backwards — and this view's d loss / d xy.  Ragged shards (n not a multiple of
+    Ns), Gaussians culled in some views, shards that are entirely padding (world * Ns >> n).  n is a
+    multiple of 4 here only because the test packs every rank's outputs into one [world, n, ...] array
+    (the kernels store 128-bit vectors; the product's per-rank buffers are 16-byte aligned)."""
+    W, H, deg, K = 96, 64, 3, 16
+    sc = synthetic.make_scene(n, W, H, seed=9 + world, sh_degree=3)
+    sc["background"] = torch.tensor([0.1, 0.3, 0.2])
+    sc["means"][:7, 2] = -2.0                                  # behind every camera
+    cams = [synthetic.make_camera(W, H, yaw_deg=-6.0 + 4.0 * r, shift=(0.05 * r, 0.0, 0.03 * r)) for r in range(world)]
+    g = torch.Generator().manual_seed(2)
+    wi, wd = torch.rand(H, W, 3, generator=g), 0.1 * torch.rand(H, W, generator=g)
+    plain = [_render(emu, sc, c, W, H, deg, wi, wd, 1) for c in cams]
+    views = [_view_rows(emu, sc, c, W, H, deg, wi, wd) for c in cams]
+    f = np.float32
+    stack = lambda key: np.ascontiguousarray(np.stack([v[key] for v in views]))
+    packed, radii, mask, recs, cam_buf = stack("grads"), stack("radii"), stack("mask"), stack("rec"), stack("cam")
+    out = dict(means=np.full((world, n, 3), 7.0, f), scales=np.full((world, n, 3), 7.0, f),
+               quats=np.full((world, n, 4), 7.0, f), opacities=np.full((world, n, 1), 7.0, f),
+               colors_dc=np.full((world, n, 3), 7.0, f), colors_rest=np.full((world, n, K - 1, 3), 7.0, f))
+    vxy = np.full((world, n, 2), 7.0, f)
+    a = dict(means=_c(sc["means"]), scales=_c(sc["scales"]), quats=_c(sc["quats"]), logits=_c(sc["opacities"].reshape(-1)))
+    rc = emu.emu_peer_exchange(world, n, Ns, K, deg, W, H, ptr(a["means"]), ptr(a["scales"]), ptr(a["quats"]),
+                               ptr(a["logits"]), ptr(packed), ptr(radii), ptr(mask), ptr(recs), ptr(cam_buf),
+                               1.0 / world, ptr(out["means"]), ptr(out["scales"]), ptr(out["quats"]),
+                               ptr(out["opacities"]), ptr(out["colors_dc"]), ptr(out["colors_rest"]), ptr(vxy))
+    assert rc == 0
+    for k in NAMES:
+        want = sum(p[k] for p in plain) / world
+        for r in range(world):
+            assert np.isfinite(out[k][r]).all(), (k, r)
+            assert _rel(out[k][r].reshape(want.shape), torch.from_numpy(want)) < 2e-4, (k, r)
+        assert all(np.array_equal(out[k][0], out[k][r]) for r in range(1, world)), k     # bit-identical replicas
+    for r in range(world):
+        assert _rel(vxy[r], torch.from_numpy(plain[r]["v_xys"])) < 2e-4
 
 
 @pytest.mark.parametrize("seed", [101, 202, 303, 404])

@@ -49,6 +49,19 @@ _SIGNATURES = {
     "ts_project_bwd_views": ([_i, _i, _p, _p, _f, _p, _p, _i, _i, _i, _p, C.c_int64, _p, _f, _p, _p, _p, _p, _p],
                              C.c_int),
     "ts_sh_bwd_views": ([_i, _i, _i, _i, _p, _p, _p, C.c_int64, _f, _p, _p, _p], C.c_int),
+    "ts_sh_bwd_views_rgb": ([_i, _i, _i, _i, _p, _p, _p, C.c_int64, _f, _p, _p, _p], C.c_int),
+    "ts_project_bwd_views_peer": ([_i, _i, _p, _p, _f, _p, _p, _i, _i, _i, _p, C.c_int64, _p, _f, _i, _i,
+                                   _p, _p, _p, _p, _p], C.c_int),
+    "ts_dp_push": ([_i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p], C.c_int),
+    "ts_peer_barrier": ([_i, _i, _p, _i, C.c_uint32, _p, C.c_double, _p], C.c_int),
+    "ts_peer_max_ranks": ([], C.c_int),
+    "ts_peer_ipc_handle_bytes": ([], C.c_int),
+    "ts_peer_flag_bytes": ([], C.c_int),
+    "ts_peer_alloc": ([C.c_int64, _p], C.c_int),
+    "ts_peer_free": ([_p], C.c_int),
+    "ts_peer_ipc_get": ([_p, _p], C.c_int),
+    "ts_peer_ipc_open": ([_p, _p], C.c_int),
+    "ts_peer_ipc_close": ([_p], C.c_int),
     "ts_set_blend_mode": ([_i], C.c_int),
     "ts_get_blend_mode": ([], C.c_int),
     "ts_debug_rowmask": ([_p, _p, _i, _i], C.c_uint32),

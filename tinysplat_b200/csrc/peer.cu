@@ -1,0 +1,215 @@
+// SURVEY 8(e) — data-parallel gradient exchange done by the kernels themselves over NVLink peer
+// memory (no NCCL call inside the step).  [The reference renders one camera per step on one device,
+// REF scripts/train.py:54-55; the camera-sharded batch is this repo's addition.]
+//
+// Rank-structured exchange.  After blend-backward every rank holds, for ITS view, one packed
+// 48-byte gradient row per Gaussian.  Everything downstream is a per-Gaussian function of those rows
+// and the views' cameras, so instead of all-reducing the finished 236-byte gradients:
+//   * geometry (S-sums, v_opacity, depth cotangent: 32 B) goes only to the rank that OWNS the
+//     Gaussian (a shard of N/world rows): projection-backward is linear in nothing, it has to be
+//     evaluated per view, and the owner does that for all views (ts_project_bwd_views) and stores
+//     the finished 44 B of mean/scale/quat/opacity gradient straight into EVERY rank's buffer;
+//   * colour cotangents (12 B) go to EVERY rank: the SH gradient is a sum over views of
+//     basis(dir_view) x v_rgb_view, rank <= world, so shipping the factors (12 B per view) and
+//     rebuilding the 192-byte SH gradient locally moves half of what shipping the product would.
+// Per rank and Gaussian at 8 ranks: 28 + 84 + 38.5 = 150 B over NVLink instead of the 413 B a ring
+// all-reduce of 236 B moves; at 2 ranks 50 B instead of 236 B.
+//
+// Kernels here: ts_dp_push (cleans the rows like ts_dp_prepare and pushes them with coalesced
+// 128-bit stores to peer-mapped addresses), ts_peer_barrier (system-scope release/acquire flags in
+// peer memory).  Peer buffers are plain cudaMalloc allocations shared through CUDA IPC handles.
+#include "ts_common.cuh"
+#include "ts_peer.cuh"
+
+namespace ts {
+
+constexpr int kPushThreads = 256;
+
+__global__ void __launch_bounds__(kPushThreads)
+dp_push_kernel(int N, int Ns, int Npad, int world, int rank, const int32_t* __restrict__ radii,
+               const uint8_t* __restrict__ clamp_mask, const float4* __restrict__ recs,
+               const float4* __restrict__ grads, const float* __restrict__ cam_row, PeerPtrs geo,
+               PeerPtrs rgb, PeerPtrs cams, float2* __restrict__ v_xys) {
+    __shared__ __align__(16) float s_rgb[kPushThreads * 3];
+    const int tid = threadIdx.x;
+    const int item0 = blockIdx.x * kPushThreads;
+    const int i = item0 + tid;
+    float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0, g2 = g0;
+    if (i < N) {
+        const bool live = __ldg(radii + i) > 0;     // culled in this view: an exact zero row
+        if (live) {
+            g0 = __ldg(grads + 3 * (size_t)i);
+            g1 = __ldg(grads + 3 * (size_t)i + 1);
+            g2 = __ldg(grads + 3 * (size_t)i + 2);
+            if (clamp_mask) {                       // SH clamp(rgb + 0.5, min=0) [REF rasterize.py:39]
+                const unsigned m = clamp_mask[i];
+                if (!(m & 1u)) g2.x = 0.f;
+                if (!(m & 2u)) g2.y = 0.f;
+                if (!(m & 4u)) g2.z = 0.f;
+            }
+        }
+        if (v_xys) {                                // this view's d loss / d xy (densification statistic)
+            float2 v = make_float2(0.f, 0.f);
+            if (live) {
+                const float4 q1 = __ldg(recs + 3 * (size_t)i + 1);   // {.5 log2e a, log2e b, .5 log2e c, opacity}
+                const float a = q1.x * (2.f / kLog2e), b = q1.y * (1.f / kLog2e), c = q1.z * (2.f / kLog2e);
+                v = make_float2(a * g0.x + b * g0.y, b * g0.x + c * g0.y);
+            }
+            v_xys[i] = v;
+        }
+        // geometry row -> the owner's buffer, slot [rank][local row]
+        const int owner = i / Ns, il = i - owner * Ns;
+        float4* dst = reinterpret_cast<float4*>(geo.p[owner]) + ((size_t)rank * Ns + il) * 2;
+        dst[0] = g0;
+        dst[1] = make_float4(g1.x, g1.y, g2.w, 0.f);
+    }
+    s_rgb[3 * tid] = g2.x; s_rgb[3 * tid + 1] = g2.y; s_rgb[3 * tid + 2] = g2.z;
+    __syncthreads();
+    // colour cotangents -> every rank's rgb[rank][3 i ..]: the block's rows are one contiguous,
+    // 16-byte aligned span (256 rows x 12 B); destinations start at the next rank to spread the links
+    const int nfl = min(kPushThreads, N - item0) * 3;
+    const int nv4 = nfl >> 2;
+    const size_t off = (size_t)rank * Npad * 3 + (size_t)item0 * 3;
+    for (int idx = tid; idx < nv4 * world; idx += kPushThreads) {
+        const int d = idx / nv4, k = idx - d * nv4;
+        const int r = (rank + 1 + d) % world;
+        reinterpret_cast<float4*>(reinterpret_cast<float*>(rgb.p[r]) + off)[k] = reinterpret_cast<const float4*>(s_rgb)[k];
+    }
+    const int ntail = nfl - (nv4 << 2);
+    for (int idx = tid; idx < ntail * world; idx += kPushThreads) {
+        const int d = idx / ntail, k = (nv4 << 2) + idx - d * ntail;
+        const int r = (rank + 1 + d) % world;
+        (reinterpret_cast<float*>(rgb.p[r]) + off)[k] = s_rgb[k];
+    }
+    if (blockIdx.x == 0) {                          // this view's camera -> every rank's cams[rank]
+        for (int idx = tid; idx < kCamRowFloats * world; idx += kPushThreads) {
+            const int r = idx / kCamRowFloats, k = idx - r * kCamRowFloats;
+            (reinterpret_cast<float*>(cams.p[r]) + (size_t)rank * kCamRowFloats)[k] = __ldg(cam_row + k);
+        }
+    }
+}
+
+// Flags live one per 128-byte line: flags[slot][source rank][32 words].
+__global__ void peer_barrier_kernel(int world, int rank, PeerPtrs flags, int slot, uint32_t epoch,
+                                    uint32_t* __restrict__ err, unsigned long long timeout_ns) {
+    const int t = threadIdx.x;
+    if (t >= world) return;
+#ifndef TS_HOST_EMU
+    __threadfence_system();     // everything this stream wrote before (also to peers) is ordered before the signal
+    uint32_t* remote = reinterpret_cast<uint32_t*>(flags.p[t]) + ((size_t)slot * kMaxPeers + rank) * 32;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(remote), "r"(epoch) : "memory");
+    const uint32_t* local = reinterpret_cast<const uint32_t*>(flags.p[rank]) + ((size_t)slot * kMaxPeers + t) * 32;
+    unsigned long long t0, now;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+        uint32_t v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(local) : "memory");
+        if ((int32_t)(v - epoch) >= 0) break;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (now - t0 > timeout_ns) {    // a peer never arrived: report instead of hanging the GPU
+            atomicExch(err, 1u + (uint32_t)t);
+            break;
+        }
+        __nanosleep(200);
+    }
+    __threadfence_system();
+#else
+    (void)flags; (void)slot; (void)epoch; (void)err; (void)timeout_ns; (void)rank;
+#endif
+}
+
+}  // namespace ts
+
+#ifndef TS_HOST_EMU
+extern "C" {
+
+int ts_peer_max_ranks(void) { return ts::kMaxPeers; }
+int ts_peer_ipc_handle_bytes(void) { return (int)sizeof(cudaIpcMemHandle_t); }
+
+int ts_peer_alloc(int64_t bytes, void** dev_ptr_host) {
+    if (bytes <= 0 || !dev_ptr_host) return TS_ERR_INVALID;
+    void* p = nullptr;
+    TS_CHECK_CUDA(cudaMalloc(&p, (size_t)bytes), "ts_peer_alloc/cudaMalloc");
+    cudaError_t e = cudaMemset(p, 0, (size_t)bytes);
+    if (e != cudaSuccess) { cudaFree(p); ts::set_last_error("ts_peer_alloc/memset", e); return TS_ERR_CUDA; }
+    *dev_ptr_host = p;
+    return TS_OK;
+}
+
+int ts_peer_free(void* dev_ptr) {
+    if (!dev_ptr) return TS_OK;
+    TS_CHECK_CUDA(cudaFree(dev_ptr), "ts_peer_free");
+    return TS_OK;
+}
+
+int ts_peer_ipc_get(void* dev_ptr, void* handle_host) {
+    if (!dev_ptr || !handle_host) return TS_ERR_INVALID;
+    cudaIpcMemHandle_t h;
+    TS_CHECK_CUDA(cudaIpcGetMemHandle(&h, dev_ptr), "ts_peer_ipc_get");
+    memcpy(handle_host, &h, sizeof(h));
+    return TS_OK;
+}
+
+int ts_peer_ipc_open(const void* handle_host, void** dev_ptr_host) {
+    if (!handle_host || !dev_ptr_host) return TS_ERR_INVALID;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle_host, sizeof(h));
+    void* p = nullptr;
+    TS_CHECK_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess), "ts_peer_ipc_open");
+    *dev_ptr_host = p;
+    return TS_OK;
+}
+
+int ts_peer_ipc_close(void* dev_ptr) {
+    if (!dev_ptr) return TS_OK;
+    TS_CHECK_CUDA(cudaIpcCloseMemHandle(dev_ptr), "ts_peer_ipc_close");
+    return TS_OK;
+}
+
+int ts_dp_push(int N, int shard_rows, int padded_rows, int world, int rank, const int32_t* radii,
+               const uint8_t* clamp_mask, const float* recs, const float* grads, const float* cam_row,
+               void* const* geo_ptrs_host, void* const* rgb_ptrs_host, void* const* cam_ptrs_host,
+               float* v_xys, ts_stream_t stream) {
+    if (N < 0 || world < 1 || world > ts::kMaxPeers || rank < 0 || rank >= world || shard_rows <= 0 ||
+        (shard_rows % 4) != 0 || padded_rows < N || (padded_rows % 4) != 0 ||
+        (int64_t)shard_rows * world < N)
+        return TS_ERR_INVALID;
+    if (!geo_ptrs_host || !rgb_ptrs_host || !cam_ptrs_host || !cam_row) return TS_ERR_INVALID;
+    ts::PeerPtrs geo{}, rgb{}, cams{};
+    for (int r = 0; r < world; ++r) {
+        geo.p[r] = geo_ptrs_host[r]; rgb.p[r] = rgb_ptrs_host[r]; cams.p[r] = cam_ptrs_host[r];
+        if (!geo.p[r] || !rgb.p[r] || !cams.p[r]) return TS_ERR_INVALID;
+        if (!ts::aligned16(geo.p[r]) || !ts::aligned16(rgb.p[r])) return TS_ERR_ALIGN;
+    }
+    if (N > 0 && (!radii || !recs || !grads)) return TS_ERR_INVALID;
+    if (N > 0 && (!ts::aligned16(recs) || !ts::aligned16(grads) || (v_xys && (reinterpret_cast<uintptr_t>(v_xys) & 7u))))
+        return TS_ERR_ALIGN;
+    const int grid = N > 0 ? (N + ts::kPushThreads - 1) / ts::kPushThreads : 1;   // block 0 always ships the camera
+    ts::dp_push_kernel<<<grid, ts::kPushThreads, 0, (cudaStream_t)stream>>>(
+        N, shard_rows, padded_rows, world, rank, radii, clamp_mask, (const float4*)recs, (const float4*)grads,
+        cam_row, geo, rgb, cams, (float2*)v_xys);
+    TS_CHECK_LAUNCH("ts_dp_push");
+    return TS_OK;
+}
+
+int ts_peer_barrier(int world, int rank, void* const* flag_ptrs_host, int slot, uint32_t epoch,
+                    uint32_t* err_flag, double timeout_s, ts_stream_t stream) {
+    if (world < 1 || world > ts::kMaxPeers || rank < 0 || rank >= world || slot < 0 || slot >= ts::kBarrierSlots ||
+        !flag_ptrs_host || !err_flag)
+        return TS_ERR_INVALID;
+    ts::PeerPtrs flags{};
+    for (int r = 0; r < world; ++r) {
+        flags.p[r] = flag_ptrs_host[r];
+        if (!flags.p[r]) return TS_ERR_INVALID;
+    }
+    if (!(timeout_s > 0)) timeout_s = 10.0;
+    ts::peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(world, rank, flags, slot, epoch, err_flag,
+                                                                 (unsigned long long)(timeout_s * 1e9));
+    TS_CHECK_LAUNCH("ts_peer_barrier");
+    return TS_OK;
+}
+
+int ts_peer_flag_bytes(void) { return ts::kBarrierSlots * ts::kMaxPeers * 32 * (int)sizeof(uint32_t); }
+
+}  // extern "C"
+#endif  // !TS_HOST_EMU

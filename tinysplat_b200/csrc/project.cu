@@ -3,6 +3,7 @@
 // Replaces gsplat.project_gaussians fwd/bwd  [REF tinysplat/splatting/rasterize.py:32,64-73].
 #include "ts_common.cuh"
 #include "ts_binning.cuh"
+#include "ts_peer.cuh"
 
 namespace ts {
 
@@ -410,17 +411,23 @@ project_bwd_kernel(int N, const float* __restrict__ means, const float* __restri
 // backward for every view with that view's camera (cams[v]: 3x4 view | 4x4 full projection | fx,
 // fy) and writes the SUM over views times out_scale: the exchanged payload is the 48-byte packed
 // record per (view, Gaussian) instead of an all-reduce over the finished 236-byte gradients.
-constexpr int kCamFloats = 32;
+constexpr int kCamFloats = kCamRowFloats;
 
+// COMPACT: rows are the 32-byte geometry rows of the peer exchange ({S_x, S_y, S_xx, S_xy},
+// {S_yy, v_opacity, v_depth, 0}; peer.cu) instead of the full 48-byte packed record.
+// The finished shard gradients are stored to n_dst destinations (the same rows of every rank's
+// gradient buffer, reached through NVLink peer mappings: the all-gather of the exchange happens
+// in this epilogue, tile by tile, instead of as a separate collective).
+template <bool COMPACT>
 __global__ void __launch_bounds__(kProjThreads)
 project_bwd_views_kernel(int n_views, int N, const float* __restrict__ means,
                          const float* __restrict__ scales, float gs, const float4* __restrict__ quats,
                          const float* __restrict__ cams, int H, int W, int flags,
                          const float4* __restrict__ packed, size_t view_stride4,
-                         const float* __restrict__ opac_logits, float out_scale,
-                         float* __restrict__ v_means, float* __restrict__ v_scales,
-                         float4* __restrict__ v_quats, float* __restrict__ v_opac_logits) {
+                         const float* __restrict__ opac_logits, float out_scale, int n_dst, int first_dst,
+                         PeerPtrs d_means, PeerPtrs d_scales, PeerPtrs d_quats, PeerPtrs d_logits) {
     constexpr int TH = kProjThreads;
+    constexpr int ROW4 = COMPACT ? 2 : 3;
     __shared__ __align__(16) float s_buf[TH * 6];
     const int item0 = blockIdx.x * TH;
     const int tid = threadIdx.x;
@@ -449,10 +456,16 @@ project_bwd_views_kernel(int n_views, int N, const float* __restrict__ means,
     float vlogit = 0.f;
     if (in) {
         for (int v = 0; v < n_views; ++v) {
-            const float4* row = packed + (size_t)v * view_stride4 + 3 * (size_t)i;
-            const float4 g0 = __ldg(row), g1 = __ldg(row + 1);
-            const float vdep_packed = (flags & TS_PROJ_DEPTH_CH3) ? __ldg(reinterpret_cast<const float*>(row) + 11) : 0.f;
-            // culled in this view (ts_dp_prepare zeroed the row) or simply untouched: nothing to
+            const float4* row = packed + (size_t)v * view_stride4 + ROW4 * (size_t)i;
+            const float4 g0 = __ldg(row);
+            float4 g1 = __ldg(row + 1);
+            float vdep_packed;
+            if (COMPACT) {
+                vdep_packed = g1.z;
+            } else {
+                vdep_packed = (flags & TS_PROJ_DEPTH_CH3) ? __ldg(reinterpret_cast<const float*>(row) + 11) : 0.f;
+            }
+            // culled in this view (the row was zeroed) or simply untouched: nothing to
             // add, and the projection of a culled Gaussian must not be evaluated (0 * inf)
             if (g0.x == 0.f && g0.y == 0.f && g0.z == 0.f && g0.w == 0.f && g1.x == 0.f && g1.y == 0.f &&
                 vdep_packed == 0.f)
@@ -473,13 +486,18 @@ project_bwd_views_kernel(int n_views, int N, const float* __restrict__ means,
         s_buf[3 * tid + k] = vmu[k] * out_scale;
         s_buf[3 * TH + 3 * tid + k] = vs[k] * out_scale;
     }
-    if (in) {
-        v_quats[i] = make_float4(vq.x * out_scale, vq.y * out_scale, vq.z * out_scale, vq.w * out_scale);
-        if (v_opac_logits) v_opac_logits[i] = vlogit * out_scale;
-    }
+    const float4 vq_out = make_float4(vq.x * out_scale, vq.y * out_scale, vq.z * out_scale, vq.w * out_scale);
+    const float vl_out = vlogit * out_scale;
     __syncthreads();
-    block_store<3, TH>(v_means, s_buf, item0, N);
-    block_store<3, TH>(v_scales, s_buf + 3 * TH, item0, N);
+    for (int d = 0; d < n_dst; ++d) {
+        const int r = (first_dst + d) % n_dst;      // start at the neighbour: spreads the NVLink traffic
+        if (in) {
+            reinterpret_cast<float4*>(d_quats.p[r])[i] = vq_out;
+            if (d_logits.p[r]) reinterpret_cast<float*>(d_logits.p[r])[i] = vl_out;
+        }
+        block_store<3, TH>(reinterpret_cast<float*>(d_means.p[r]), s_buf, item0, N);
+        block_store<3, TH>(reinterpret_cast<float*>(d_scales.p[r]), s_buf + 3 * TH, item0, N);
+    }
 }
 
 }  // namespace ts
@@ -547,28 +565,67 @@ int ts_project_bwd(int N, const float* means3d, const float* scales, float glob_
     return TS_OK;
 }
 
+static int launch_project_bwd_views(bool compact, int n_views, int N, const float* means3d, const float* scales,
+                                    float glob_scale, const float* quats, const float* cams, int img_height,
+                                    int img_width, int flags, const float* rows, int64_t view_stride_floats,
+                                    const float* opacity_logits, float out_scale, int n_dst, int first_dst,
+                                    const ts::PeerPtrs& dm, const ts::PeerPtrs& ds, const ts::PeerPtrs& dq,
+                                    const ts::PeerPtrs& dl, ts_stream_t stream) {
+    if (n_views < 1 || N < 0 || img_height <= 0 || img_width <= 0 || view_stride_floats < 0 ||
+        (view_stride_floats % 4) != 0 || n_dst < 1 || n_dst > ts::kMaxPeers)
+        return TS_ERR_INVALID;
+    if (N == 0) return TS_OK;
+    if (!means3d || !scales || !quats || !cams || !rows) return TS_ERR_INVALID;
+    if (!ts::aligned16(means3d) || !ts::aligned16(scales) || !ts::aligned16(quats) || !ts::aligned16(rows))
+        return TS_ERR_ALIGN;
+    for (int d = 0; d < n_dst; ++d) {
+        if (!dm.p[d] || !ds.p[d] || !dq.p[d]) return TS_ERR_INVALID;
+        if (!ts::aligned16(dm.p[d]) || !ts::aligned16(ds.p[d]) || !ts::aligned16(dq.p[d])) return TS_ERR_ALIGN;
+    }
+    int grid = (N + ts::kProjThreads - 1) / ts::kProjThreads;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (compact)
+        ts::project_bwd_views_kernel<true><<<grid, ts::kProjThreads, 0, st>>>(
+            n_views, N, means3d, scales, glob_scale, (const float4*)quats, cams, img_height, img_width, flags,
+            (const float4*)rows, (size_t)(view_stride_floats / 4), opacity_logits, out_scale, n_dst, first_dst,
+            dm, ds, dq, dl);
+    else
+        ts::project_bwd_views_kernel<false><<<grid, ts::kProjThreads, 0, st>>>(
+            n_views, N, means3d, scales, glob_scale, (const float4*)quats, cams, img_height, img_width, flags,
+            (const float4*)rows, (size_t)(view_stride_floats / 4), opacity_logits, out_scale, n_dst, first_dst,
+            dm, ds, dq, dl);
+    TS_CHECK_LAUNCH("ts_project_bwd_views");
+    return TS_OK;
+}
+
 int ts_project_bwd_views(int n_views, int N, const float* means3d, const float* scales, float glob_scale,
                          const float* quats, const float* cams, int img_height, int img_width, int flags,
                          const float* packed_grads, int64_t view_stride_floats, const float* opacity_logits,
                          float out_scale, float* v_means3d, float* v_scales, float* v_quats,
                          float* v_opacity_logits, ts_stream_t stream) {
-    if (n_views < 1 || N < 0 || img_height <= 0 || img_width <= 0 || view_stride_floats < 0 ||
-        (view_stride_floats % 4) != 0)
+    ts::PeerPtrs dm{}, ds{}, dq{}, dl{};
+    dm.p[0] = v_means3d; ds.p[0] = v_scales; dq.p[0] = v_quats; dl.p[0] = v_opacity_logits;
+    return launch_project_bwd_views(false, n_views, N, means3d, scales, glob_scale, quats, cams, img_height,
+                                    img_width, flags, packed_grads, view_stride_floats, opacity_logits, out_scale,
+                                    1, 0, dm, ds, dq, dl, stream);
+}
+
+int ts_project_bwd_views_peer(int n_views, int N, const float* means3d, const float* scales, float glob_scale,
+                              const float* quats, const float* cams, int img_height, int img_width, int flags,
+                              const float* geo_rows, int64_t view_stride_floats, const float* opacity_logits,
+                              float out_scale, int n_dst, int first_dst, void* const* v_means_ptrs_host,
+                              void* const* v_scales_ptrs_host, void* const* v_quats_ptrs_host,
+                              void* const* v_logit_ptrs_host, ts_stream_t stream) {
+    if (n_dst < 1 || n_dst > ts::kMaxPeers || !v_means_ptrs_host || !v_scales_ptrs_host || !v_quats_ptrs_host)
         return TS_ERR_INVALID;
-    if (N == 0) return TS_OK;
-    if (!means3d || !scales || !quats || !cams || !packed_grads || !v_means3d || !v_scales || !v_quats)
-        return TS_ERR_INVALID;
-    if (!ts::aligned16(means3d) || !ts::aligned16(scales) || !ts::aligned16(quats) ||
-        !ts::aligned16(packed_grads) || !ts::aligned16(v_means3d) || !ts::aligned16(v_scales) ||
-        !ts::aligned16(v_quats))
-        return TS_ERR_ALIGN;
-    int grid = (N + ts::kProjThreads - 1) / ts::kProjThreads;
-    ts::project_bwd_views_kernel<<<grid, ts::kProjThreads, 0, (cudaStream_t)stream>>>(
-        n_views, N, means3d, scales, glob_scale, (const float4*)quats, cams, img_height, img_width, flags,
-        (const float4*)packed_grads, (size_t)(view_stride_floats / 4), opacity_logits, out_scale, v_means3d,
-        v_scales, (float4*)v_quats, v_opacity_logits);
-    TS_CHECK_LAUNCH("ts_project_bwd_views");
-    return TS_OK;
+    ts::PeerPtrs dm{}, ds{}, dq{}, dl{};
+    for (int d = 0; d < n_dst; ++d) {
+        dm.p[d] = v_means_ptrs_host[d]; ds.p[d] = v_scales_ptrs_host[d]; dq.p[d] = v_quats_ptrs_host[d];
+        dl.p[d] = v_logit_ptrs_host ? v_logit_ptrs_host[d] : nullptr;
+    }
+    return launch_project_bwd_views(true, n_views, N, means3d, scales, glob_scale, quats, cams, img_height,
+                                    img_width, flags, geo_rows, view_stride_floats, opacity_logits, out_scale,
+                                    n_dst, first_dst, dm, ds, dq, dl, stream);
 }
 
 }  // extern "C"

@@ -371,7 +371,8 @@ template <int DEG>
 __global__ void __launch_bounds__(kShThreads)
 sh_bwd_views_kernel(int n_views, int N, int K, const float* __restrict__ means,
                     const float* __restrict__ cams, const float* __restrict__ packed, size_t view_stride,
-                    float out_scale, float* __restrict__ v_dc, float* __restrict__ v_rest) {
+                    int row_stride, int col_off, float out_scale, float* __restrict__ v_dc,
+                    float* __restrict__ v_rest) {
     TS_DYN_SMEM(float, s_sh, 128);
     constexpr int NB = (DEG + 1) * (DEG + 1);
     const int R = (K - 1) * 3;
@@ -387,7 +388,15 @@ sh_bwd_views_kernel(int n_views, int N, int K, const float* __restrict__ means,
 #pragma unroll
         for (int k = 0; k < NB; ++k) acc[k][0] = acc[k][1] = acc[k][2] = 0.f;
         for (int v = 0; v < n_views; ++v) {
-            const float4 t = __ldg(reinterpret_cast<const float4*>(packed + (size_t)v * view_stride + 12 * (size_t)i + 8));
+            // colour cotangents of view v: floats col_off..col_off+2 of the row (packed record: 12 / 8,
+            // one 128-bit load; colour rows of the peer exchange: 3 / 0)
+            const float* src = packed + (size_t)v * view_stride + (size_t)row_stride * i + col_off;
+            float4 t;
+            if (((row_stride | col_off) & 3) == 0) {
+                t = __ldg(reinterpret_cast<const float4*>(src));
+            } else {
+                t.x = __ldg(src); t.y = __ldg(src + 1); t.z = __ldg(src + 2); t.w = 0.f;
+            }
             if (t.x == 0.f && t.y == 0.f && t.z == 0.f) continue;
             const float* cv = cams + (size_t)v * 32;
             float b[NB];
@@ -525,20 +534,20 @@ int ts_sh_bwd(int N, int degree, int K, const float* dirs, const float* viewmat,
     return TS_OK;
 }
 
-int ts_sh_bwd_views(int n_views, int N, int degree, int K, const float* means, const float* cams,
-                    const float* packed_grads, int64_t view_stride_floats, float out_scale, float* v_dc,
-                    float* v_rest, ts_stream_t stream) {
+static int launch_sh_bwd_views(int n_views, int N, int degree, int K, const float* means, const float* cams,
+                               const float* rows, int64_t view_stride_floats, int row_stride, int col_off,
+                               float out_scale, float* v_dc, float* v_rest, ts_stream_t stream) {
     if (n_views < 1 || N < 0 || degree < 0 || degree > 4 || K < (degree + 1) * (degree + 1) || K > 25 ||
-        view_stride_floats < 0 || (view_stride_floats % 4) != 0)
+        view_stride_floats < 0 || (view_stride_floats % 4) != 0 || row_stride < 3 || col_off < 0)
         return TS_ERR_INVALID;
     if (N == 0) return TS_OK;
-    if (!means || !cams || !packed_grads || !v_dc || (K > 1 && !v_rest)) return TS_ERR_INVALID;
-    if (!ts::aligned16(packed_grads)) return TS_ERR_ALIGN;
+    if (!means || !cams || !rows || !v_dc || (K > 1 && !v_rest)) return TS_ERR_INVALID;
+    if (!ts::aligned16(rows)) return TS_ERR_ALIGN;
     int grid = (N + ts::kShThreads - 1) / ts::kShThreads;
     size_t bsmem = sizeof(float) * ts::kShThreads * ((K - 1) * 3 + 3) + 16;
     cudaStream_t st = (cudaStream_t)stream;
 #define TS_LAUNCH_SH_VIEWS(D) \
-    ts::sh_bwd_views_kernel<D><<<grid, ts::kShThreads, bsmem, st>>>(n_views, N, K, means, cams, packed_grads, (size_t)view_stride_floats, out_scale, v_dc, v_rest)
+    ts::sh_bwd_views_kernel<D><<<grid, ts::kShThreads, bsmem, st>>>(n_views, N, K, means, cams, rows, (size_t)view_stride_floats, row_stride, col_off, out_scale, v_dc, v_rest)
     switch (degree) {
         case 0: TS_LAUNCH_SH_VIEWS(0); break;
         case 1: TS_LAUNCH_SH_VIEWS(1); break;
@@ -549,6 +558,20 @@ int ts_sh_bwd_views(int n_views, int N, int degree, int K, const float* means, c
 #undef TS_LAUNCH_SH_VIEWS
     TS_CHECK_LAUNCH("ts_sh_bwd_views");
     return TS_OK;
+}
+
+int ts_sh_bwd_views(int n_views, int N, int degree, int K, const float* means, const float* cams,
+                    const float* packed_grads, int64_t view_stride_floats, float out_scale, float* v_dc,
+                    float* v_rest, ts_stream_t stream) {
+    return launch_sh_bwd_views(n_views, N, degree, K, means, cams, packed_grads, view_stride_floats, 12, 8,
+                               out_scale, v_dc, v_rest, stream);
+}
+
+int ts_sh_bwd_views_rgb(int n_views, int N, int degree, int K, const float* means, const float* cams,
+                        const float* rgb_rows, int64_t view_stride_floats, float out_scale, float* v_dc,
+                        float* v_rest, ts_stream_t stream) {
+    return launch_sh_bwd_views(n_views, N, degree, K, means, cams, rgb_rows, view_stride_floats, 3, 0,
+                               out_scale, v_dc, v_rest, stream);
 }
 
 }  // extern "C"

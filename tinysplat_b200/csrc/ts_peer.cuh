@@ -1,0 +1,16 @@
+// Pointer tables of the peer-memory gradient exchange (peer.cu, project.cu): one pointer per
+// data-parallel rank, passed to the kernels by value.
+#pragma once
+#include "ts_common.cuh"
+
+namespace ts {
+
+constexpr int kMaxPeers = 8;          // one NVSwitch domain of a B200 box
+constexpr int kBarrierSlots = 2;      // A: rows pushed, B: shard gradients stored
+constexpr int kCamRowFloats = 32;     // 3x4 view | 4x4 full projection | fx fy | pad
+
+struct PeerPtrs {
+    void* p[kMaxPeers];
+};
+
+}  // namespace ts

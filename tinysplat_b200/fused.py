@@ -82,7 +82,7 @@ class XysSink:
 class _RenderFused(Function):
     @staticmethod
     def forward(ctx, means, log_scales, quats, opac_logits, colors_dc, colors_rest, view_dev,
-                fullproj_dev, fx, fy, width, height, sh_degree, bg4, cull_mode, clamp_rgb, sink, dp):
+                fullproj_dev, fx, fy, width, height, sh_degree, bg4, cull_mode, clamp_rgb, sink, dp, cam_row=None):
         _lib.require_cuda(means, log_scales, quats, opac_logits, colors_dc, colors_rest)
         lib = _lib.load()
         dev = means.device
@@ -103,11 +103,16 @@ class _RenderFused(Function):
 
         cams_all = None
         if dp is not None:
-            # every rank needs every view's camera for the shard backward: 32 floats per rank,
-            # gathered here so the collective is long finished when backward starts
-            cam_row = torch.cat([view_c[:3].reshape(-1), proj_c.reshape(-1),
-                                 torch.tensor([float(fx), float(fy), 0.0, 0.0], **f32)])
-            cams_all = dp.gather_cameras(cam_row)
+            # every rank needs every view's camera for the shard backward: 32 floats per rank
+            if cam_row is None:
+                cam_row = torch.cat([view_c[:3].reshape(-1), proj_c.reshape(-1),
+                                     torch.tensor([float(fx), float(fy), 0.0, 0.0], **f32)])
+            cam_row = _lib.f32c(cam_row)
+            if getattr(dp, "peer", False):
+                cams_all = cam_row            # pushed to the peers by ts_dp_push in backward
+            else:
+                # gathered here so the collective is long finished when backward starts
+                cams_all = dp.gather_cameras(cam_row)
 
         xys = torch.empty(N, 2, **f32)
         depths = torch.empty(N, **f32)
@@ -191,17 +196,18 @@ class _RenderFused(Function):
         st = _lib.stream_ptr(dev)
         f32 = dict(device=dev, dtype=torch.float32)
         if v_rgb is None and v_depth is None and v_T is None:
-            return (None,) * 18
+            return (None,) * 19
         v_alpha = -v_T if v_T is not None else None     # alpha = 1 - T
         v_rgb = _lib.f32c(v_rgb) if v_rgb is not None else None
         v_depth = _lib.f32c(v_depth) if v_depth is not None else None
         v_alpha = _lib.f32c(v_alpha) if v_alpha is not None else None
         dp = ctx.dp
         n_rows = N
-        if dp is not None:
+        peer = dp is not None and getattr(dp, "peer", False)
+        if dp is not None and not peer:
             Ns = dp.shard_rows(N)
             n_rows = dp.world * Ns                 # padded so that the all-to-all splits evenly
-        if dp is not None:
+        if dp is not None and not peer:
             # persistent, zero-initialised: blend-backward clears rows [0, N), the pad stays zero
             grads = dp.buffer("send", (n_rows, lib.ts_grad_floats()), torch.float32, dev, zero=True, tag=N)
         else:
@@ -209,6 +215,8 @@ class _RenderFused(Function):
         _lib.call("ts_blend_bwd", N, 4, H, W, tx, ty, _lib.ptr(offsets), _lib.ptr(ids_sorted), _lib.ptr(recs),
                   _lib.ptr(bg_c), _lib.ptr(final_T), _lib.ptr(n_contrib), _lib.ptr(v_rgb), _lib.ptr(v_depth), 1,
                   _lib.ptr(v_alpha), _lib.ptr(grads), st)
+        if peer:
+            return _RenderFused._backward_peer_exchange(ctx, grads, st)
         if dp is not None:
             return _RenderFused._backward_packed_exchange(ctx, grads, Ns, st)
         # colours first: the largest gradient (colors_rest) becomes available for its all-reduce
@@ -245,7 +253,7 @@ class _RenderFused(Function):
         if ctx.sink is not None:
             ctx.sink.deliver(v_xys)
         return (v_means, v_scales, v_quats, v_logit.reshape(opac_shape), v_dc.reshape(dc_shape), v_rest,
-                None, None, None, None, None, None, None, None, None, None, None, None)
+                None, None, None, None, None, None, None, None, None, None, None, None, None)
 
     @staticmethod
     def _backward_packed_exchange(ctx, grads, Ns, st):
@@ -293,13 +301,68 @@ class _RenderFused(Function):
         if ctx.sink is not None:
             ctx.sink.deliver(v_xys)
         return (v_means, v_scales, v_quats, v_logit.reshape(opac_shape), v_dc.reshape(dc_shape), v_rest,
-                None, None, None, None, None, None, None, None, None, None, None, None)
+                None, None, None, None, None, None, None, None, None, None, None, None, None)
+
+
+def _backward_peer_exchange(ctx, grads, st):
+    """Data-parallel backward over NVLink peer memory (parallel.PeerGradExchange,
+    csrc/peer.cu): no collective call.  ts_dp_push stores this view's geometry rows into the owner
+    ranks' buffers and its colour cotangents + camera into every rank's; after a flag barrier every
+    rank rebuilds the SH gradient of ALL Gaussians from all views' colour cotangents and runs
+    projection-backward over all views for ITS shard, storing the result into every rank's gradient
+    segment; a second barrier, and the six gradients are views of the local segment."""
+    (means_c, scales_c, quats_c, logit_c, view_c, proj_c, bg_c, radii, recs, offsets, ids_sorted,
+     final_T, n_contrib, mask) = ctx.saved_tensors
+    N, K, W, H, tx, ty, fx, fy, deg, pflags, sflags, opac_shape, dc_shape = ctx.meta
+    dp, cam_row = ctx.dp, ctx.cams_all
+    dev = means_c.device
+    world, rank = dp.world, dp.rank
+    L = dp.ensure(N, K, dev)
+    s0, ns, Ns = L.shard_of(rank, N)
+    Npad = world * Ns
+    v_xys = torch.empty(N, 2, device=dev, dtype=torch.float32)
+    _lib.call("ts_dp_push", N, Ns, Npad, world, rank, _lib.ptr(radii), _lib.ptr(mask), _lib.ptr(recs),
+              _lib.ptr(grads), _lib.ptr(cam_row), dp.seg_ptrs("geo"), dp.seg_ptrs("rgb"), dp.seg_ptrs("cams"),
+              _lib.ptr(v_xys), st)
+    epoch = dp.next_epoch()
+    dp.barrier(0, epoch, st)                      # every rank's rows, colours and camera have landed here
+    scale = dp.out_scale()
+    main = torch.cuda.current_stream(dev)
+    side = _side_stream(dev) if USE_SIDE_STREAM else main
+    if N > 0:
+        if side is not main:
+            side.wait_stream(main)
+        with torch.cuda.stream(side):
+            _lib.call("ts_sh_bwd_views_rgb", world, N, deg, K, _lib.ptr(means_c), dp.local_ptr("cams"),
+                      dp.local_ptr("rgb"), Npad * 3, scale, dp.local_ptr("g_dc"), dp.local_ptr("g_rest"),
+                      side.cuda_stream)
+        if ns > 0:
+            dst = [dp.seg_ptrs("g_" + n, s0 * L.width(n) * 4) for n in ("means", "scales", "quats", "logit")]
+            _lib.call("ts_project_bwd_views_peer", world, ns, _lib.ptr(means_c[s0:s0 + ns]),
+                      _lib.ptr(scales_c[s0:s0 + ns]), 1.0, _lib.ptr(quats_c[s0:s0 + ns]), dp.local_ptr("cams"),
+                      H, W, pflags, dp.local_ptr("geo"), Ns * 8, _lib.ptr(logit_c[s0:s0 + ns]), scale, world,
+                      (rank + 1) % world, dst[0], dst[1], dst[2], dst[3], st)
+        if side is not main:
+            main.wait_stream(side)
+    dp.barrier(1, epoch, st)                      # every shard's gradients have landed in my segment
+    # bytes this rank sent over NVLink: geometry rows + colours + finished shard gradients
+    dp.last_bytes_sent = (N * 32 * (world - 1)) // world + N * 12 * (world - 1) + ns * 44 * (world - 1)
+    v_rest, v_dc = dp.local_view("g_rest", N, K - 1, 3), dp.local_view("g_dc", N, 3)
+    v_means, v_scales = dp.local_view("g_means", N, 3), dp.local_view("g_scales", N, 3)
+    v_quats, v_logit = dp.local_view("g_quats", N, 4), dp.local_view("g_logit", N)
+    if ctx.sink is not None:
+        ctx.sink.deliver(v_xys)
+    return (v_means, v_scales, v_quats, v_logit.reshape(opac_shape), v_dc.reshape(dc_shape), v_rest,
+            None, None, None, None, None, None, None, None, None, None, None, None, None)
+
+
+_RenderFused._backward_peer_exchange = staticmethod(_backward_peer_exchange)
 
 
 def render_fused(means: Tensor, log_scales: Tensor, quats: Tensor, opacity_logits: Tensor,
                  colors_dc: Tensor, colors_rest: Tensor, view_matrix: Tensor, full_proj: Tensor,
                  fx: float, fy: float, width: int, height: int, sh_degree: int, background: Tensor,
-                 cull_mode: int = 1, clamp_rgb: bool = True, grad_exchange=None
+                 cull_mode: int = 1, clamp_rgb: bool = True, grad_exchange=None, cam_row=None
                  ) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
     """Fused equivalent of project -> SH(+0.5, clamp) -> rasterise RGB -> rasterise depth.
 
@@ -309,12 +372,15 @@ def render_fused(means: Tensor, log_scales: Tensor, quats: Tensor, opacity_logit
     final_T[H,W] (alpha = 1 - final_T), xys[N,2], depths[N], radii[N]).  `xys.grad` is populated
     by backward.  grad_exchange: a tinysplat_b200.parallel.PackedGradExchange — backward then
     exchanges packed gradient rows between the data-parallel ranks and returns the gradients
-    already reduced over all ranks' views (every rank must call with the same N and image size)."""
+    already reduced over all ranks' views (every rank must call with the same N and image size);
+    or a parallel.PeerGradExchange — the same over NVLink peer memory without collective calls.
+    cam_row: optional device tensor of 32 floats (3x4 view | 4x4 full projection | fx fy 0 0) for
+    the exchange; built on the device when absent."""
     sink = XysSink()
     bg = background.to(means.device).float()
     bg4 = torch.cat([bg, bg[:1]])       # depth is composited over background[0] [REF rasterize.py:48-51]
     out = _RenderFused.apply(means, log_scales, quats, opacity_logits, colors_dc, colors_rest,
                              view_matrix, full_proj, fx, fy, width, height, sh_degree, bg4,
-                             cull_mode, clamp_rgb, sink, grad_exchange)
+                             cull_mode, clamp_rgb, sink, grad_exchange, cam_row)
     sink.attach(out[3])
     return out

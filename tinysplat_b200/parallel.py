@@ -188,24 +188,221 @@ class PackedGradExchange:
         return outs
 
 
+class PeerLayout:
+    """Byte layout of one rank's peer-visible allocation (identical on every rank) for a capacity of
+    `cap_rows` Gaussians with K stored SH bases at `world` ranks.  Pure host arithmetic.
+
+        flags | err | cams[world][32] | geo[world][Ns][8] | rgb[world][world*Ns][3] |
+        v_rest[(K-1)*3 per row] | v_dc[3] | v_means[3] | v_scales[3] | v_quats[4] | v_logit[1]
+
+    Every segment starts on a 256-byte boundary; the gradient segments are sized for cap_rows rows
+    so that the six parameter gradients handed to autograd are views of this buffer."""
+
+    SHARD_ALIGN = 256          # rows; keeps every shard slice of every tensor 16-byte aligned
+
+    def __init__(self, world: int, cap_rows: int, K: int, flag_bytes: int):
+        self.world, self.cap_rows, self.K = world, cap_rows, K
+        self.cap_shard = self.shard_rows(cap_rows, world)
+        seg = {}
+        off = 0
+
+        def add(name, nbytes):
+            nonlocal off
+            seg[name] = (off, nbytes)
+            off += (nbytes + 255) // 256 * 256
+        add("flags", flag_bytes)
+        add("err", 256)
+        add("cams", world * PackedGradExchange.CAM_FLOATS * 4)
+        add("geo", world * self.cap_shard * 8 * 4)
+        add("rgb", world * world * self.cap_shard * 3 * 4)
+        for name, width in (("rest", (K - 1) * 3), ("dc", 3), ("means", 3), ("scales", 3), ("quats", 4), ("logit", 1)):
+            add("g_" + name, max(1, cap_rows * width) * 4)
+        self.seg = seg
+        self.total_bytes = off
+
+    @classmethod
+    def shard_rows(cls, n_gaussians: int, world: int) -> int:
+        per = -(-max(n_gaussians, 1) // world)
+        return (per + cls.SHARD_ALIGN - 1) // cls.SHARD_ALIGN * cls.SHARD_ALIGN
+
+    def shard_of(self, rank: int, n_gaussians: int):
+        """(first row, rows) of `rank`'s shard for the CURRENT number of Gaussians."""
+        ns_all = self.shard_rows(n_gaussians, self.world)
+        s0 = rank * ns_all
+        return s0, max(0, min(n_gaussians, s0 + ns_all) - s0), ns_all
+
+    GRAD_WIDTH = {"rest": None, "dc": 3, "means": 3, "scales": 3, "quats": 4, "logit": 1}
+
+    def width(self, name: str) -> int:
+        return (self.K - 1) * 3 if name == "rest" else self.GRAD_WIDTH[name]
+
+
+class _DeviceSpan:
+    """Exposes a raw device allocation through __cuda_array_interface__ (torch.as_tensor aliases it)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False),
+                                         "version": 3, "strides": None}
+
+
+class PeerGradExchange:
+    """Gradient exchange over NVLink peer memory, done by the kernels themselves (csrc/peer.cu): no
+    collective call inside the step.  Used through the fused autograd node like PackedGradExchange.
+
+    Every rank owns one cudaMalloc allocation laid out by PeerLayout and maps every other rank's
+    allocation through CUDA IPC (handles exchanged once per (re)allocation over the process group).
+    Per backward: ts_dp_push (geometry rows -> owner, colour cotangents + camera -> everyone),
+    ts_peer_barrier, SH-backward over all views (local), shard projection-backward with stores into
+    every rank's gradient segment, ts_peer_barrier.  The gradients handed to autograd are views of
+    the local segment: they are overwritten by the next backward (consume or copy them before)."""
+
+    peer = True
+
+    def __init__(self, process_group=None, average: bool = True, headroom: float = 0.125,
+                 timeout_s: float = 20.0):
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("PeerGradExchange needs an initialised process group")
+        from . import _lib
+        self._lib = _lib
+        self.group = process_group
+        self.world = dist.get_world_size(process_group)
+        self.rank = dist.get_rank(process_group)
+        if self.world > _lib.load().ts_peer_max_ranks():
+            raise RuntimeError(f"PeerGradExchange supports up to {_lib.load().ts_peer_max_ranks()} ranks")
+        self.average = average
+        self.headroom = headroom
+        self.timeout_s = timeout_s
+        self.layout: Optional[PeerLayout] = None
+        self.device = None
+        self._base = None            # my allocation
+        self._peer_bases: List[int] = []
+        self._opened: List[int] = []
+        self._span = None            # torch uint8 view of my allocation
+        self._tables = {}
+        self.epoch = 0
+        self.last_bytes_sent = 0
+
+    def out_scale(self) -> float:
+        return 1.0 / self.world if self.average else 1.0
+
+    # -- allocation + rendezvous --------------------------------------------------------------
+    def ensure(self, n_gaussians: int, K: int, device) -> PeerLayout:
+        """(Re)allocates and re-maps when the capacity or K changes; every rank must call this with
+        the same arguments in the same step (N changes only when the model densifies)."""
+        L = self.layout
+        if L is not None and L.K == K and n_gaussians <= L.cap_rows and device == self.device:
+            return L
+        import ctypes as C
+        lib = self._lib.load()
+        self.close()
+        cap = int(n_gaussians * (1.0 + self.headroom)) + 1024
+        L = PeerLayout(self.world, cap, K, lib.ts_peer_flag_bytes())
+        with torch.cuda.device(device):
+            base = C.c_void_p()
+            self._lib.check(lib.ts_peer_alloc(L.total_bytes, C.byref(base)), "ts_peer_alloc")
+            hbytes = lib.ts_peer_ipc_handle_bytes()
+            hbuf = (C.c_ubyte * hbytes)()
+            self._lib.check(lib.ts_peer_ipc_get(base, hbuf), "ts_peer_ipc_get")
+            mine = torch.tensor(list(hbuf), dtype=torch.uint8, device=device)
+            every = torch.empty(self.world * hbytes, dtype=torch.uint8, device=device)
+            dist.all_gather_into_tensor(every, mine, group=self.group)
+            every = every.cpu().view(self.world, hbytes)
+            bases, opened = [], []
+            for r in range(self.world):
+                if r == self.rank:
+                    bases.append(base.value)
+                    continue
+                h = (C.c_ubyte * hbytes)(*every[r].tolist())
+                p = C.c_void_p()
+                self._lib.check(lib.ts_peer_ipc_open(h, C.byref(p)), "ts_peer_ipc_open")
+                bases.append(p.value)
+                opened.append(p.value)
+            torch.cuda.synchronize(device)
+            dist.barrier(group=self.group)      # everybody mapped everybody before the first push
+        self.layout, self.device = L, device
+        self._base, self._peer_bases, self._opened = base.value, bases, opened
+        self._span = torch.as_tensor(_DeviceSpan(base.value, L.total_bytes), device=device)
+        self.epoch = 0
+        self._tables = {}
+        return L
+
+    def _table(self, key, ptrs):
+        import ctypes as C
+        t = self._tables.get(key)
+        if t is None:
+            t = (C.c_void_p * len(ptrs))(*ptrs)
+            self._tables[key] = t
+        return t
+
+    def seg_ptrs(self, name: str, row_offset_bytes: int = 0):
+        """ctypes table: the address of segment `name` (+ offset) in every rank's allocation."""
+        off = self.layout.seg[name][0] + row_offset_bytes
+        return self._table((name, row_offset_bytes), [b + off for b in self._peer_bases])
+
+    def local_ptr(self, name: str) -> int:
+        return self._base + self.layout.seg[name][0]
+
+    def local_view(self, name: str, n_rows: int, *shape) -> Tensor:
+        """fp32 view [n_rows, *shape] of one of my gradient segments."""
+        off, _ = self.layout.seg[name]
+        numel = n_rows
+        for d in shape:
+            numel *= d
+        return self._span[off:off + 4 * numel].view(torch.float32).view(n_rows, *shape)
+
+    def next_epoch(self) -> int:
+        self.epoch += 1
+        return self.epoch
+
+    def barrier(self, slot: int, epoch: int, stream_ptr: int) -> None:
+        lib = self._lib.load()
+        self._lib.check(lib.ts_peer_barrier(self.world, self.rank, self.seg_ptrs("flags"), slot, epoch,
+                                            self.local_ptr("err"), float(self.timeout_s), stream_ptr),
+                        "ts_peer_barrier")
+
+    def check(self) -> None:
+        """Raises when a barrier timed out (a peer never arrived).  Synchronises the device."""
+        if self._span is None:
+            return
+        off, _ = self.layout.seg["err"]
+        code = int(self._span[off:off + 4].view(torch.int32).item())
+        if code != 0:
+            raise RuntimeError(f"peer barrier timed out waiting for rank {code - 1} (rank {self.rank})")
+
+    def close(self) -> None:
+        if self._base is None:
+            return
+        lib = self._lib.load()
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=self.group)      # nobody is still writing into a buffer about to go away
+            self._span = None
+            for p in self._opened:
+                lib.ts_peer_ipc_close(p)
+            lib.ts_peer_free(self._base)
+        self._base, self._peer_bases, self._opened, self.layout, self._tables = None, [], [], None, {}
+
+
 class DataParallelRenderer:
     """rank r renders cameras[r::world] with `rasterizer`, backpropagates `loss_fn`, and leaves
     the view-averaged gradient in every parameter's .grad on every rank."""
 
     def __init__(self, rasterizer: Callable, params: Iterable[Tensor], process_group=None,
                  average: bool = True, overlap: bool = True, strategy: str = "allreduce"):
-        """strategy: "allreduce" (any rasterizer) or "packed" (the fused pipeline of
-        tinysplat_b200.rasterizer.GaussianRasterizer: gradients leave backward already reduced)."""
-        if strategy not in ("allreduce", "packed"):
-            raise ValueError("strategy must be 'allreduce' or 'packed'")
+        """strategy: "allreduce" (any rasterizer), "packed" or "peer" (the fused pipeline of
+        tinysplat_b200.rasterizer.GaussianRasterizer: gradients leave backward already reduced;
+        "peer" moves the data with the kernels' own NVLink stores instead of NCCL calls)."""
+        if strategy not in ("allreduce", "packed", "peer"):
+            raise ValueError("strategy must be 'allreduce', 'packed' or 'peer'")
         self.rasterizer = rasterizer
         self.group = process_group
         self.strategy = strategy
         enabled = dist.is_available() and dist.is_initialized() and dist.get_world_size(process_group) > 1
-        if strategy == "packed" and enabled:
+        if strategy in ("packed", "peer") and enabled:
             if getattr(rasterizer, "pipeline", None) != "fused":
-                raise ValueError("strategy='packed' needs GaussianRasterizer(pipeline='fused')")
-            rasterizer.grad_exchange = PackedGradExchange(process_group, average)
+                raise ValueError(f"strategy='{strategy}' needs GaussianRasterizer(pipeline='fused')")
+            cls = PackedGradExchange if strategy == "packed" else PeerGradExchange
+            rasterizer.grad_exchange = cls(process_group, average)
             self.reducer = GradientAllReducer([], process_group, average, overlap=False)
         else:
             self.reducer = GradientAllReducer(params, process_group, average, overlap)

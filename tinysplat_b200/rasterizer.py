@@ -69,11 +69,21 @@ class GaussianRasterizer:
         m = self.model
         # one small H2D for both matrices (full projection composed on the host)
         view = camera.view_matrix.float()
-        mats = torch.stack([view, camera.proj_matrix.float() @ view]).to(self.device, non_blocking=True)
+        full = camera.proj_matrix.float() @ view
+        exchange = self.grad_exchange if torch.is_grad_enabled() else None
+        if exchange is None:
+            mats = torch.stack([view, full]).to(self.device, non_blocking=True)
+            view_d, full_d, cam_row = mats[0], mats[1], None
+        else:
+            # + the 32-float camera row of the data-parallel exchange, in the same small H2D copy
+            host = torch.cat([view.reshape(-1), full.reshape(-1), view[:3].reshape(-1), full.reshape(-1),
+                              torch.tensor([float(camera.f_x), float(camera.f_y), 0.0, 0.0])])
+            dev_buf = host.to(self.device, non_blocking=True)
+            view_d, full_d, cam_row = dev_buf[:16].view(4, 4), dev_buf[16:32].view(4, 4), dev_buf[32:64]
         rgb, depth_img, _, xys, _, radii = render_fused(
-            m.means, m.scales, m.quats, m.opacities, m.colors_dc, m.colors_rest, mats[0], mats[1],
+            m.means, m.scales, m.quats, m.opacities, m.colors_dc, m.colors_rest, view_d, full_d,
             camera.f_x, camera.f_y, width, height, sh_degree, m.background,
-            grad_exchange=self.grad_exchange if torch.is_grad_enabled() else None)
+            grad_exchange=exchange, cam_row=cam_row)
         extras: Dict = {"depth": depth_img, "radii": radii, "xys": xys,
                         "camera": {"height": camera.height, "width": camera.width}}
         return rgb, extras      # already clamped to <= 1 inside the blend kernel

@@ -1,6 +1,7 @@
-"""Multi-GPU check of the two gradient-exchange strategies (run under torchrun, one rank per GPU):
-renders one view per rank through the fused adapter with strategy "allreduce" and with strategy
-"packed" and compares the reduced gradients; then times both.  Prints one JSON line on rank 0.
+"""Multi-GPU check of the gradient-exchange strategies (run under torchrun, one rank per GPU):
+renders one view per rank through the fused adapter with strategy "allreduce", "packed" (NCCL
+all-to-all + shard backward + all-gather) and "peer" (the kernels' own NVLink stores, no collective
+call) and compares the reduced gradients; then times each.  Prints one JSON line on rank 0.
 
   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
       --master-port 29511 tools/dp_check.py [--n 1000000]"""
@@ -33,7 +34,7 @@ def main():
     cot_d = torch.rand(H, W, generator=torch.Generator().manual_seed(8)).to(dev) / (W * H)
     names = ["means", "scales", "quats", "opacities", "colors_dc", "colors_rest"]
     out, ms = {}, {}
-    for strategy in ("allreduce", "packed"):
+    for strategy in ("allreduce", "packed", "peer"):
         model = ParamModel(sc, dev, 3)
         rast = GaussianRasterizer(model, None, dev, "fused")
         dp = DataParallelRenderer(rast, model.parameters(), average=True, strategy=strategy)
@@ -64,20 +65,35 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms[strategy] = t.item()
         dp.reducer.close()
-    errs = {}
-    for k, a, b in zip(names + ["xys"], out["allreduce"], out["packed"]):
-        errs[k] = ((a - b).abs().max() / a.abs().max().clamp_min(1e-30)).item()
-    worst = torch.tensor([max(errs.values())], device=dev)
-    dist.all_reduce(worst, op=dist.ReduceOp.MAX)
-    # every rank must hold the same reduced gradient
-    chk = out["packed"][0].double().sum().reshape(1)
-    lo, hi = chk.clone(), chk.clone()
-    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
-    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        if rast.grad_exchange is not None and hasattr(rast.grad_exchange, "check"):
+            rast.grad_exchange.check()          # raises if a peer barrier timed out
+            sent = rast.grad_exchange.last_bytes_sent
+            rast.grad_exchange.close()
+        elif rast.grad_exchange is not None:
+            sent = rast.grad_exchange.last_bytes_sent
+        else:
+            sent = None
+        ms[strategy + "_bytes_sent_per_rank"] = sent
+    report = {"world": world, "gaussians": N, "ms_per_step": ms}
+    ok = True
+    for strategy in ("packed", "peer"):
+        errs = {}
+        for k, a, b in zip(names + ["xys"], out["allreduce"], out[strategy]):
+            errs[k] = ((a - b).abs().max() / a.abs().max().clamp_min(1e-30)).item()
+        worst = torch.tensor([max(errs.values())], device=dev)
+        dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+        # every rank must hold the same reduced gradient (bit for bit: same shard kernel output everywhere)
+        chk = torch.stack([t.double().sum() for t in out[strategy][:6]])
+        lo, hi = chk.clone(), chk.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        report[f"rel_err_{strategy}_vs_allreduce"] = errs
+        report[f"{strategy}_worst_over_ranks"] = worst.item()
+        report[f"{strategy}_identical_across_ranks"] = bool((hi - lo).abs().max().item() == 0.0)
+        ok = ok and worst.item() < 1e-4 and report[f"{strategy}_identical_across_ranks"]
+    report["ok"] = bool(ok)
     if rank == 0:
-        print(json.dumps({"world": world, "gaussians": N, "ms_per_step": ms, "rel_err_packed_vs_allreduce": errs,
-                          "worst_over_ranks": worst.item(), "identical_across_ranks": bool((hi - lo).abs().item() == 0.0),
-                          "ok": bool(worst.item() < 1e-4)}), flush=True)
+        print(json.dumps(report), flush=True)
     dist.destroy_process_group()
 
 

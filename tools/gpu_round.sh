@@ -15,7 +15,7 @@ AB="--steps 30 --warmup 5 --no-cpu-baseline --no-extras --sustained-s 0"
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.max.sm,clocks.sm,power.limit --format=csv > gpurun_out/${TAG}_gpu.txt 2>&1
 if [ "$TESTS" = "1" ]; then
-  ( time timeout 900 python -m pytest tests -q -m gpu -x -s ) > gpurun_out/${TAG}_tests_gpu.log 2>&1
+  ( time timeout 900 python -m pytest tests -q -m gpu -s ) > gpurun_out/${TAG}_tests_gpu.log 2>&1
   tail -5 gpurun_out/${TAG}_tests_gpu.log
 fi
 timeout 400 python bench.py > gpurun_out/${TAG}_bench_default.json 2> gpurun_out/${TAG}_bench_default.err
