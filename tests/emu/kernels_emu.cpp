@@ -183,6 +183,15 @@ int sh_bwd_views_any(int n_views, int N, int K, const float* means, const float*
     });
 }
 
+template <int DEG>
+int sh_bwd_views_rgb_any(int n_views, int N, int K, const float* means, const float* cams, const float* rgb,
+                         size_t view_stride, float scale, float* v_dc, float* v_rest) {
+    const int grid = (N + ts::kShThreads - 1) / ts::kShThreads;
+    return ts_emu::launch(dim3(grid), ts::kShThreads, [=]() {
+        ts::sh_bwd_views_rgb_kernel<DEG>(n_views, N, K, means, cams, rgb, view_stride, scale, v_dc, v_rest);
+    });
+}
+
 #define TS_EMU_BY_DEG(deg, fn, ...)             \
     switch (deg) {                              \
         case 0: return fn<0>(__VA_ARGS__);      \
@@ -346,7 +355,7 @@ int emu_peer_exchange(int world, int N, int Ns, int K, int deg, int W, int H, co
             const float* rows = (const float*)prgb.p[r];
             const float* cam = (const float*)pcams.p[r];
             auto run = [&]() -> int {
-                TS_EMU_BY_DEG(deg, sh_bwd_views_any, world, N, K, means, cam, rows, (size_t)Npad * 3, 3, 0, scale, vdc, vrest);
+                TS_EMU_BY_DEG(deg, sh_bwd_views_rgb_any, world, N, K, means, cam, rows, (size_t)Npad * 3, scale, vdc, vrest);
             };
             int rc = run();
             if (rc) return rc;

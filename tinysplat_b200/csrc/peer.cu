@@ -30,7 +30,8 @@ dp_push_kernel(int N, int Ns, int Npad, int world, int rank, const int32_t* __re
                const uint8_t* __restrict__ clamp_mask, const float4* __restrict__ recs,
                const float4* __restrict__ grads, const float* __restrict__ cam_row, PeerPtrs geo,
                PeerPtrs rgb, PeerPtrs cams, float2* __restrict__ v_xys) {
-    __shared__ __align__(16) float s_rgb[kPushThreads * 3];
+    __shared__ __align__(128) float4 s_geo[kPushThreads * 2];     // the block's geometry rows, 8 KB
+    __shared__ __align__(128) float s_rgb[kPushThreads * 3];      // the block's colour rows, 3 KB
     const int tid = threadIdx.x;
     const int item0 = blockIdx.x * kPushThreads;
     const int i = item0 + tid;
@@ -57,29 +58,51 @@ dp_push_kernel(int N, int Ns, int Npad, int world, int rank, const int32_t* __re
             }
             v_xys[i] = v;
         }
-        // geometry row -> the owner's buffer, slot [rank][local row]
-        const int owner = i / Ns, il = i - owner * Ns;
-        float4* dst = reinterpret_cast<float4*>(geo.p[owner]) + ((size_t)rank * Ns + il) * 2;
-        dst[0] = g0;
-        dst[1] = make_float4(g1.x, g1.y, g2.w, 0.f);
     }
+    s_geo[2 * tid] = g0;
+    s_geo[2 * tid + 1] = make_float4(g1.x, g1.y, g2.w, 0.f);
     s_rgb[3 * tid] = g2.x; s_rgb[3 * tid + 1] = g2.y; s_rgb[3 * tid + 2] = g2.z;
-    __syncthreads();
-    // colour cotangents -> every rank's rgb[rank][3 i ..]: the block's rows are one contiguous,
-    // 16-byte aligned span (256 rows x 12 B); destinations start at the next rank to spread the links
-    const int nfl = min(kPushThreads, N - item0) * 3;
-    const int nv4 = nfl >> 2;
-    const size_t off = (size_t)rank * Npad * 3 + (size_t)item0 * 3;
-    for (int idx = tid; idx < nv4 * world; idx += kPushThreads) {
-        const int d = idx / nv4, k = idx - d * nv4;
-        const int r = (rank + 1 + d) % world;
-        reinterpret_cast<float4*>(reinterpret_cast<float*>(rgb.p[r]) + off)[k] = reinterpret_cast<const float4*>(s_rgb)[k];
-    }
-    const int ntail = nfl - (nv4 << 2);
-    for (int idx = tid; idx < ntail * world; idx += kPushThreads) {
-        const int d = idx / ntail, k = (nv4 << 2) + idx - d * ntail;
-        const int r = (rank + 1 + d) % world;
-        (reinterpret_cast<float*>(rgb.p[r]) + off)[k] = s_rgb[k];
+    const int nvalid = min(kPushThreads, N - item0);
+    const size_t rgb_off = (size_t)rank * Npad * 3 + (size_t)item0 * 3;      // floats, in every rank's rgb buffer
+    const int owner0 = item0 / Ns;
+    // A full block whose rows have ONE owner (always, when shard_rows is a multiple of 256) ships as
+    // TMA bulk stores: one 8 KB copy of geometry rows to the owner, one 3 KB copy of colour rows per
+    // rank, issued by one thread — the copy engine generates the NVLink traffic, not 10 stores per lane.
+    const bool bulk = nvalid == kPushThreads && owner0 == (item0 + kPushThreads - 1) / Ns;
+    if (bulk) {
+        fence_proxy_async();        // generic-proxy smem writes -> visible to the copy engine
+        __syncthreads();
+        if (tid == 0) {
+            float4* gdst = reinterpret_cast<float4*>(geo.p[owner0]) + ((size_t)rank * Ns + (item0 - owner0 * Ns)) * 2;
+            bulk_s2g(gdst, s_geo, kPushThreads * 32);
+            for (int d = 0; d < world; ++d) {       // start at the next rank: spreads the links
+                const int r = (rank + 1 + d) % world;
+                bulk_s2g(reinterpret_cast<float*>(rgb.p[r]) + rgb_off, s_rgb, kPushThreads * 12);
+            }
+            bulk_commit();
+            bulk_wait0();           // performed, not just read: the flag barrier that follows publishes them
+        }
+    } else {
+        __syncthreads();
+        if (i < N) {
+            const int owner = i / Ns, il = i - owner * Ns;
+            float4* dst = reinterpret_cast<float4*>(geo.p[owner]) + ((size_t)rank * Ns + il) * 2;
+            dst[0] = s_geo[2 * tid];
+            dst[1] = s_geo[2 * tid + 1];
+        }
+        const int nfl = nvalid * 3;
+        const int nv4 = nfl >> 2;
+        for (int idx = tid; idx < nv4 * world; idx += kPushThreads) {
+            const int d = idx / nv4, k = idx - d * nv4;
+            const int r = (rank + 1 + d) % world;
+            reinterpret_cast<float4*>(reinterpret_cast<float*>(rgb.p[r]) + rgb_off)[k] = reinterpret_cast<const float4*>(s_rgb)[k];
+        }
+        const int ntail = nfl - (nv4 << 2);
+        for (int idx = tid; idx < ntail * world; idx += kPushThreads) {
+            const int d = idx / ntail, k = (nv4 << 2) + idx - d * ntail;
+            const int r = (rank + 1 + d) % world;
+            (reinterpret_cast<float*>(rgb.p[r]) + rgb_off)[k] = s_rgb[k];
+        }
     }
     if (blockIdx.x == 0) {                          // this view's camera -> every rank's cams[rank]
         for (int idx = tid; idx < kCamRowFloats * world; idx += kPushThreads) {

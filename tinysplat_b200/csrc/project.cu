@@ -428,7 +428,7 @@ project_bwd_views_kernel(int n_views, int N, const float* __restrict__ means,
                          PeerPtrs d_means, PeerPtrs d_scales, PeerPtrs d_quats, PeerPtrs d_logits) {
     constexpr int TH = kProjThreads;
     constexpr int ROW4 = COMPACT ? 2 : 3;
-    __shared__ __align__(16) float s_buf[TH * 6];
+    __shared__ __align__(128) float s_buf[TH * 11];     // means 3 | scales 3 | quats 4 | logit 1 (output staging)
     const int item0 = blockIdx.x * TH;
     const int tid = threadIdx.x;
     block_load<3, TH>(means, s_buf, item0, N);
@@ -488,9 +488,33 @@ project_bwd_views_kernel(int n_views, int N, const float* __restrict__ means,
     }
     const float4 vq_out = make_float4(vq.x * out_scale, vq.y * out_scale, vq.z * out_scale, vq.w * out_scale);
     const float vl_out = vlogit * out_scale;
+    reinterpret_cast<float4*>(s_buf + 6 * TH)[tid] = vq_out;
+    s_buf[10 * TH + tid] = vl_out;
+    // Full blocks leave as TMA bulk stores (3 + 3 + 4 + 1 KB per destination, one issuing thread):
+    // with n_dst > 1 the destinations are peer-mapped buffers and the copy engine drives NVLink.
+    bool bulk = (N - item0) >= TH;
+    for (int d = 0; d < n_dst && bulk; ++d)
+        bulk = aligned_dev16(d_means.p[d]) && aligned_dev16(d_scales.p[d]) && aligned_dev16(d_quats.p[d]) &&
+               (!d_logits.p[d] || aligned_dev16(d_logits.p[d]));
+    if (bulk) {
+        fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) {
+            for (int d = 0; d < n_dst; ++d) {
+                const int r = (first_dst + d) % n_dst;      // start at the neighbour: spreads the NVLink traffic
+                bulk_s2g(reinterpret_cast<float*>(d_means.p[r]) + (size_t)item0 * 3, s_buf, TH * 12);
+                bulk_s2g(reinterpret_cast<float*>(d_scales.p[r]) + (size_t)item0 * 3, s_buf + 3 * TH, TH * 12);
+                bulk_s2g(reinterpret_cast<float*>(d_quats.p[r]) + (size_t)item0 * 4, s_buf + 6 * TH, TH * 16);
+                if (d_logits.p[r]) bulk_s2g(reinterpret_cast<float*>(d_logits.p[r]) + item0, s_buf + 10 * TH, TH * 4);
+            }
+            bulk_commit();
+            bulk_wait0();
+        }
+        return;
+    }
     __syncthreads();
     for (int d = 0; d < n_dst; ++d) {
-        const int r = (first_dst + d) % n_dst;      // start at the neighbour: spreads the NVLink traffic
+        const int r = (first_dst + d) % n_dst;
         if (in) {
             reinterpret_cast<float4*>(d_quats.p[r])[i] = vq_out;
             if (d_logits.p[r]) reinterpret_cast<float*>(d_logits.p[r])[i] = vl_out;

@@ -438,6 +438,96 @@ sh_bwd_views_kernel(int n_views, int N, int K, const float* __restrict__ means,
     }
 }
 
+// The same sum over views for the peer-memory exchange (peer.cu): the colour cotangents arrive as
+// dense 12-byte rows rgb[v][i][3] in THIS rank's buffer, so the block's rows of every view (and its
+// means) are contiguous chunks: one elected thread pulls them with TMA bulk loads (n_views + 1 copies,
+// one mbarrier), the 128 threads build the 192-byte SH gradient rows in shared memory and they leave
+// with TMA bulk stores.  Every rank runs this for ALL Gaussians (the SH gradient is rebuilt from its
+// rank-<=world factors instead of being shipped: half the NVLink bytes).
+template <int DEG>
+__global__ void __launch_bounds__(kShThreads)
+sh_bwd_views_rgb_kernel(int n_views, int N, int K, const float* __restrict__ means,
+                        const float* __restrict__ cams, const float* __restrict__ rgb, size_t view_stride,
+                        float out_scale, float* __restrict__ v_dc, float* __restrict__ v_rest) {
+    TS_DYN_SMEM(float, s_sh, 128);
+    constexpr int NB = (DEG + 1) * (DEG + 1);
+    constexpr int TH = kShThreads;
+    const int R = (K - 1) * 3;
+    float* s_rest = s_sh;                            // [TH][R] dense, becomes v_rest rows
+    float* s_dc = s_rest + TH * R;                   // [TH*3]
+    float* s_mean = s_dc + TH * 3;                   // [TH*3]
+    float* s_rgb = s_mean + TH * 3;                  // [n_views][TH*3]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(s_rgb + (size_t)n_views * TH * 3);
+    const int item0 = blockIdx.x * TH;
+    const int n_valid = min(TH, N - item0);
+    const int tid = threadIdx.x;
+    const bool full = n_valid == TH && aligned_dev16(means) && aligned_dev16(rgb) && (view_stride & 3) == 0;
+    if (full) {
+        if (tid == 0) {
+            mbar_init(bar, 1);
+            fence_proxy_async();
+            mbar_expect_tx(bar, (unsigned)((n_views + 1) * TH * 12));
+            bulk_g2s(s_mean, means + (size_t)item0 * 3, TH * 12, bar);
+            for (int v = 0; v < n_views; ++v)
+                bulk_g2s(s_rgb + (size_t)v * TH * 3, rgb + (size_t)v * view_stride + (size_t)item0 * 3, TH * 12, bar);
+        }
+        __syncthreads();          // barrier init visible before anyone waits
+        mbar_wait(bar, 0);
+    } else {
+        dense_copy_in<TH>(s_mean, means + (size_t)item0 * 3, n_valid * 3);
+        for (int v = 0; v < n_views; ++v)
+            dense_copy_in<TH>(s_rgb + (size_t)v * TH * 3, rgb + (size_t)v * view_stride + (size_t)item0 * 3, n_valid * 3);
+        __syncthreads();
+    }
+    if (tid < n_valid) {
+        const float mx = s_mean[3 * tid], my = s_mean[3 * tid + 1], mz = s_mean[3 * tid + 2];
+        float acc[NB][3];
+#pragma unroll
+        for (int k = 0; k < NB; ++k) acc[k][0] = acc[k][1] = acc[k][2] = 0.f;
+        for (int v = 0; v < n_views; ++v) {
+            const float* t = s_rgb + (size_t)v * TH * 3 + 3 * tid;     // stride 3: bank-conflict free
+            const float tx = t[0], ty = t[1], tz = t[2];
+            if (tx == 0.f && ty == 0.f && tz == 0.f) continue;
+            const float* cv = cams + (size_t)v * 32;
+            float b[NB];
+            sh_basis<DEG>(mx - __ldg(cv + 3), my - __ldg(cv + 7), mz - __ldg(cv + 11), b);
+#pragma unroll
+            for (int k = 0; k < NB; ++k) {
+                acc[k][0] = fmaf(b[k], tx, acc[k][0]);
+                acc[k][1] = fmaf(b[k], ty, acc[k][1]);
+                acc[k][2] = fmaf(b[k], tz, acc[k][2]);
+            }
+        }
+        s_dc[3 * tid] = acc[0][0] * out_scale; s_dc[3 * tid + 1] = acc[0][1] * out_scale; s_dc[3 * tid + 2] = acc[0][2] * out_scale;
+        float* c = s_rest + tid * R;
+#pragma unroll
+        for (int k = 1; k < NB; ++k) {
+            c[3 * (k - 1)] = acc[k][0] * out_scale;
+            c[3 * (k - 1) + 1] = acc[k][1] * out_scale;
+            c[3 * (k - 1) + 2] = acc[k][2] * out_scale;
+        }
+        for (int k = (NB - 1) * 3; k < R; ++k) c[k] = 0.f;   // bases above the active degree
+    }
+    const bool bulk = n_valid == TH && R > 0 && ((size_t)TH * R * 4) % 16 == 0 &&
+                      aligned_dev16(v_rest + (size_t)item0 * R) && aligned_dev16(v_dc + (size_t)item0 * 3);
+    if (bulk) {
+        fence_proxy_async();      // generic-proxy smem writes -> visible to the copy engine
+        __syncthreads();
+        if (tid == 0) {
+            bulk_s2g(v_rest + (size_t)item0 * R, s_rest, TH * R * 4);
+            bulk_s2g(v_dc + (size_t)item0 * 3, s_dc, TH * 3 * 4);
+            bulk_commit();
+            bulk_wait_read0();    // shared memory must outlive the reads
+        }
+    } else {
+        __syncthreads();
+        float* gr = v_rest + (size_t)item0 * R;
+        for (int i = tid; i < n_valid * R; i += TH) gr[i] = s_rest[i];
+        float* gd = v_dc + (size_t)item0 * 3;
+        for (int i = tid; i < n_valid * 3; i += TH) gd[i] = s_dc[i];
+    }
+}
+
 static inline int sh_stride(int K) { int k3 = K * 3; return (k3 & 1) ? k3 : k3 + 1; }
 
 }  // namespace ts
@@ -570,8 +660,33 @@ int ts_sh_bwd_views(int n_views, int N, int degree, int K, const float* means, c
 int ts_sh_bwd_views_rgb(int n_views, int N, int degree, int K, const float* means, const float* cams,
                         const float* rgb_rows, int64_t view_stride_floats, float out_scale, float* v_dc,
                         float* v_rest, ts_stream_t stream) {
-    return launch_sh_bwd_views(n_views, N, degree, K, means, cams, rgb_rows, view_stride_floats, 3, 0,
-                               out_scale, v_dc, v_rest, stream);
+    if (n_views < 1 || n_views > 64 || N < 0 || degree < 0 || degree > 4 || K < (degree + 1) * (degree + 1) ||
+        K > 25 || view_stride_floats < 0 || (view_stride_floats % 4) != 0)
+        return TS_ERR_INVALID;
+    if (N == 0) return TS_OK;
+    if (!means || !cams || !rgb_rows || !v_dc || (K > 1 && !v_rest)) return TS_ERR_INVALID;
+    if (!ts::aligned16(rgb_rows)) return TS_ERR_ALIGN;
+    int grid = (N + ts::kShThreads - 1) / ts::kShThreads;
+    size_t bsmem = sizeof(float) * ts::kShThreads * ((K - 1) * 3 + 6 + 3 * n_views) + 16;
+    cudaStream_t st = (cudaStream_t)stream;
+#define TS_LAUNCH_SH_VIEWS_RGB(D)                                                                             \
+    do {                                                                                                      \
+        TS_CHECK_CUDA(cudaFuncSetAttribute(ts::sh_bwd_views_rgb_kernel<D>,                                    \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem),          \
+                      "ts_sh_bwd_views_rgb/attr");                                                            \
+        ts::sh_bwd_views_rgb_kernel<D><<<grid, ts::kShThreads, bsmem, st>>>(                                  \
+            n_views, N, K, means, cams, rgb_rows, (size_t)view_stride_floats, out_scale, v_dc, v_rest);      \
+    } while (0)
+    switch (degree) {
+        case 0: TS_LAUNCH_SH_VIEWS_RGB(0); break;
+        case 1: TS_LAUNCH_SH_VIEWS_RGB(1); break;
+        case 2: TS_LAUNCH_SH_VIEWS_RGB(2); break;
+        case 3: TS_LAUNCH_SH_VIEWS_RGB(3); break;
+        default: TS_LAUNCH_SH_VIEWS_RGB(4); break;
+    }
+#undef TS_LAUNCH_SH_VIEWS_RGB
+    TS_CHECK_LAUNCH("ts_sh_bwd_views_rgb");
+    return TS_OK;
 }
 
 }  // extern "C"
