@@ -142,9 +142,15 @@ TS_API int ts_sh_bwd(int N, int degree, int K, const float* dirs /*[16B]*/,
  *                the callee).
  * ts_bin_emit  : writes keys[M] = depth_bits<<32 | gaussian_id grouped by tile
  *                (cursors = the tile_counts buffer after ts_bin_scan).
- * ts_bin_sort  : sorts every tile's keys in place and writes ids_sorted[M] (gaussian ids,
- *                front to back, ties by gaussian id).  big_scratch must hold
- *                n_big_tiles * next_pow2(max_count) uint64 when n_big_tiles > 0. */
+ * ts_bin_sort  : sorts every tile's keys and writes ids_sorted[M] (gaussian ids, front to back,
+ *                ties by gaussian id).  max_count / n_big_tiles select the kernels to launch (an
+ *                upper bound is fine; a tile longer than max_count is left unsorted).  big_scratch
+ *                must hold n_big_tiles * next_pow2(max_count) uint64 when n_big_tiles > 0.
+ * `capacity` (ts_bin_emit, ts_bin_sort, ts_blend_fwd): number of entries the caller's keys /
+ *   ids_sorted buffers hold, or 0 = exactly M.  A caller that sizes the buffers BEFORE it has read
+ *   M back (from an earlier step, with headroom) passes the capacity: entries past it are never
+ *   written or read; if M turns out larger the results are void and the caller must enlarge the
+ *   buffers, restore the cursors (ts_bin_reset_cursors) and run emit / sort / blend again. */
 TS_API int ts_bin_count(int N, int CH, const float* xys, const float* depths,
                         const int32_t* radii, const float* conics, const float* opacity,
                         const float* colors, int img_height, int img_width,
@@ -155,10 +161,13 @@ TS_API int ts_bin_scan(int num_tiles, int32_t* tile_counts, int32_t* tile_offset
 TS_API int ts_bin_emit(int N, const float* depths, const int32_t* radii,
                        const float* recs /*[16B]*/, int tiles_x, int tiles_y, int cull_mode,
                        const int32_t* tile_offsets, int32_t* cursors, uint64_t* keys,
-                       ts_stream_t stream);
+                       int capacity, ts_stream_t stream);
+TS_API int ts_bin_reset_cursors(int num_tiles, const int32_t* tile_offsets, int32_t* cursors,
+                                ts_stream_t stream);
 TS_API int ts_bin_sort(int num_tiles, const int32_t* tile_offsets, uint64_t* keys,
                        int32_t* ids_sorted, int max_count, int n_big_tiles,
-                       uint64_t* big_scratch, int32_t* big_counter, ts_stream_t stream);
+                       uint64_t* big_scratch, int32_t* big_counter, int capacity,
+                       ts_stream_t stream);
 /* Per-tile counters are strided: tile t's counter is tile_counts[t * ts_bin_counter_stride()]
  * (one per 128-byte line: L2 serialises atomics per line).  ts_bin_scan rewrites each counter
  * in place with the tile's exclusive offset, so the same buffer is ts_bin_emit's `cursors`. */
@@ -183,7 +192,7 @@ TS_API int ts_blend_fwd(int CH, int img_height, int img_width, int tiles_x, int 
                         const int32_t* tile_offsets, const int32_t* ids_sorted,
                         const float* recs /*[16B]*/, const float* background,
                         float* out_img, float* out_ch3 /*or NULL*/, float* final_T,
-                        int32_t* n_contrib, int clamp_max1, ts_stream_t stream);
+                        int32_t* n_contrib, int clamp_max1, int capacity, ts_stream_t stream);
 TS_API int ts_blend_bwd(int N, int CH, int img_height, int img_width, int tiles_x, int tiles_y,
                         const int32_t* tile_offsets, const int32_t* ids_sorted,
                         const float* recs /*[16B]*/, const float* background,

@@ -17,6 +17,9 @@
 #include "../../tinysplat_b200/csrc/knn.cu"
 
 #include <vector>
+#include <climits>
+
+static int g_emu_key_cap = INT32_MAX;
 
 namespace {
 template <int CH>
@@ -24,7 +27,7 @@ int run_fwd(int H, int W, int tx, int ty, const int32_t* off, const int32_t* ids
             const float* bg, float* out_img, float* out_ch3, float* final_T, int32_t* n_contrib, int clamp) {
     return ts_emu::launch(dim3(tx, ty), ts::kBlendThreads, [=]() {
         ts::blend_fwd_kernel<CH>(H, W, tx, off, ids, (const float4*)recs, bg, out_img, out_ch3, final_T,
-                                 n_contrib, clamp);
+                                 n_contrib, clamp, g_emu_key_cap);
     });
 }
 template <int CH, int GCH>
@@ -115,26 +118,34 @@ int emu_bin_emit(int N, const float* depths, const int32_t* radii, const float* 
     if (N == 0) return 0;
     const int grid = (N + ts::kBinThreads - 1) / ts::kBinThreads;
     return ts_emu::launch(dim3(grid), ts::kBinThreads, [=]() {
-        ts::bin_emit_kernel(N, depths, radii, (const float4*)recs, tx, ty, cull, cursors, keys);
+        ts::bin_emit_kernel(N, depths, radii, (const float4*)recs, tx, ty, cull, cursors, keys, g_emu_key_cap);
     });
+}
+
+// capacity of the key / id buffers seen by emit, sort and blend-forward (tests of the overflow guards)
+void emu_set_key_capacity(int cap) { g_emu_key_cap = cap > 0 ? cap : INT32_MAX; }
+
+int emu_bin_reset_cursors(int T, const int32_t* offsets, int32_t* cursors) {
+    return ts_emu::launch(dim3((T + 255) / 256), 256, [=]() { ts::bin_reset_cursors_kernel(T, offsets, cursors); });
 }
 
 int emu_bin_sort(int T, const int32_t* offsets, uint64_t* keys, int32_t* ids_sorted, int max_count,
                  int n_big, uint64_t* big_scratch, int32_t* big_counter) {
     if (max_count <= 0) return 0;
-    int rc = ts_emu::launch(dim3((T + 7) / 8), 256, [=]() { ts::bin_sort_warp_kernel(T, offsets, keys, ids_sorted); });
-    const int bounds[3] = {ts::kWarpSortMax, 2048, ts::kSmemSortCap};
-    for (int c = 0; c < 2 && rc == 0; ++c) {
-        if (max_count <= bounds[c]) break;
-        const int lo = bounds[c], hi = bounds[c + 1];
-        rc = ts_emu::launch(dim3(T), ts::kSortThreads, [=]() { ts::bin_sort_kernel(T, offsets, keys, ids_sorted, lo, hi); });
-    }
+    const int cap = g_emu_key_cap;
+    int rc = ts_emu::launch(dim3((T + 7) / 8), 256, [=]() { ts::bin_sort_warp_kernel(T, offsets, keys, ids_sorted, cap, n_big > 0 ? INT32_MAX : (max_count < ts::kSmemSortCap ? max_count : ts::kSmemSortCap)); });
+    if (rc == 0 && max_count > ts::kWarpSortMax)
+        rc = ts_emu::launch(dim3(T), 256, [=]() { ts::bin_sort_cta_kernel<256, 4, 8>(T, offsets, keys, ids_sorted, ts::kWarpSortMax, cap); });
+    if (rc == 0 && max_count > 2048)
+        rc = ts_emu::launch(dim3(T), 512, [=]() { ts::bin_sort_cta_kernel<512, 8, 16>(T, offsets, keys, ids_sorted, 2048, cap); });
+    if (rc == 0 && max_count > 8192)
+        rc = ts_emu::launch(dim3(T), 1024, [=]() { ts::bin_sort_cta_kernel<1024, 16, 16>(T, offsets, keys, ids_sorted, 8192, cap); });
     if (n_big > 0 && rc == 0) {
         int P = 2;
         while (P < max_count) P <<= 1;
         *big_counter = 0;
         rc = ts_emu::launch(dim3(T), 1024, [=]() {
-            ts::bin_sort_big_kernel(T, offsets, keys, ids_sorted, ts::kSmemSortCap, P, big_scratch, big_counter);
+            ts::bin_sort_big_kernel(T, offsets, keys, ids_sorted, ts::kSmemSortCap, P, big_scratch, big_counter, cap);
         });
     }
     return rc;

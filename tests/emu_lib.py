@@ -30,6 +30,9 @@ def load():
     lib.emu_bin_scan.argtypes = [i, p, p, p, i]
     lib.emu_bin_emit.argtypes = [i, p, p, p, i, i, i, p, p]
     lib.emu_bin_sort.argtypes = [i, p, p, p, i, i, p, p]
+    lib.emu_set_key_capacity.argtypes = [i]
+    lib.emu_set_key_capacity.restype = None
+    lib.emu_bin_reset_cursors.argtypes = [i, p, p]
     lib.emu_render_fused.argtypes = [i, i, i, i, i, p, p, p, p, p, p, p, p, f, f, p, i, i, p, p, i,
                                      p, p, p, p, p, p, p, p, p, p, p, p, p]
     lib.emu_shard_bwd_views.argtypes = [i, i, i, i, i, i, p, p, p, p, p, p, C.c_int64, f, p, p, p, p, p, p]

@@ -769,3 +769,73 @@ def test_knn_points_matches_brute_force(P1, P2, K):
     assert (got_i == want_i).float().mean().item() > 0.999        # fp32 near-ties may swap neighbours
     # what the reference does with it: index the means
     assert p2.to(DEV)[out.idx[0]].shape == (P1, K, 3)
+
+
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("pipeline", ["reference", "fused"])
+def test_guessed_buffer_sizes_never_change_the_result(pipeline):
+    """emit / sort / blend are queued before the host knows the intersection count, with buffers sized
+    from earlier calls (tinysplat_b200/binning.py).  A sparse scene first, then a much denser one at the
+    same image size (the guess is too small -> the pass is repeated), then the dense one again (the
+    guess fits): every render must equal the one made with exact sizes."""
+    from tinysplat_b200 import binning, rasterize as rz
+    from tinysplat_b200.rasterizer import GaussianRasterizer, ParamModel
+    W, H = 208, 112
+    cam = synthetic.make_camera(W, H)
+    sparse = synthetic.make_scene(300, W, H, seed=1, mean_radius_px=3.0)
+    dense = synthetic.make_scene(6000, W, H, seed=2, mean_radius_px=14.0)
+
+    def render(sc):
+        model = ParamModel(sc, DEV, 3)
+        rz.clear_bin_cache()
+        img, ex = GaussianRasterizer(model, None, DEV, pipeline)(cam, (W, H), 3)
+        (img.sum() + 0.1 * ex["depth"].sum()).backward()
+        return img.detach().clone(), ex["depth"].detach().clone(), [p.grad.clone() for p in model.parameters()], \
+            rz.last_stats["num_intersects"]
+
+    binning.reset_state()
+    exact = render(dense)                      # first call of this image size: sized exactly
+    binning.reset_state()
+    before = dict(binning.stats)
+    render(sparse)                             # seeds a small guess
+    redone = render(dense)                     # guess too small: repeated with exact sizes
+    assert binning.stats["redone"] > before["redone"]
+    n_redone = binning.stats["redone"]
+    again = render(dense)                      # guess fits now
+    assert binning.stats["redone"] == n_redone and binning.stats["speculative"] > before["speculative"]
+    for got in (redone, again):
+        assert got[3] == exact[3]
+        assert torch.equal(got[0], exact[0]) and torch.equal(got[1], exact[1])
+        for a, b in zip(got[2], exact[2]):
+            assert rel_err(a, b) < 1e-5        # float atomics reorder the sums
+
+
+def test_depth_pass_reuses_the_tile_lists_of_the_rgb_pass():
+    """The reference rasterises RGB and then depth over the same geometry, building a FRESH
+    torch.sigmoid(model.opacities) for each call [REF rasterize.py:44-51,86]: the second call must find
+    the first call's tile lists although its opacity tensor is a new one."""
+    import gsplat
+    from gsplat.sh import spherical_harmonics
+    from tinysplat_b200 import rasterize as rz
+    from tinysplat_b200.rasterizer import ParamModel
+    W, H = 160, 96
+    cam = synthetic.make_camera(W, H)
+    sc = synthetic.make_scene(2000, W, H, seed=9)
+    model = ParamModel(sc, DEV, 3)
+    xys, depths, radii, conics, num_tiles, _ = gsplat.project_gaussians(*proj_inputs(
+        {k: getattr(model, k) for k in ("means", "scales", "quats")}, cam, W, H, device=DEV))
+    dirs = torch.nn.functional.normalize(model.means - cam.view_matrix[:3, 3].to(DEV), dim=-1)
+    rgbs = torch.clamp(spherical_harmonics(3, dirs, torch.cat([model.colors_dc[:, None], model.colors_rest], 1)) + 0.5, min=0)
+    rz.clear_bin_cache()
+    bg = torch.zeros(3, device=DEV)
+    img, _ = gsplat.rasterize_gaussians(xys, depths, radii, conics, num_tiles, rgbs, torch.sigmoid(model.opacities), H, W, bg)
+    assert rz.last_stats["bins_reused"] is False
+    dimg, _ = gsplat.rasterize_gaussians(xys, depths, radii, conics, num_tiles, depths[:, None].repeat(1, 3),
+                                         torch.sigmoid(model.opacities), H, W, bg)
+    assert rz.last_stats["bins_reused"] is True
+    # a changed opacity must NOT reuse them (the footprint culling depends on it)
+    with torch.no_grad():
+        model.opacities.add_(0.5)
+    img2, _ = gsplat.rasterize_gaussians(xys, depths, radii, conics, num_tiles, rgbs, torch.sigmoid(model.opacities), H, W, bg)
+    assert rz.last_stats["bins_reused"] is False
+    assert (img2 - img).abs().max().item() > 0

@@ -32,12 +32,13 @@ _SIGNATURES = {
     "ts_sh_bwd": ([_i, _i, _i, _p, _p, _p, _i, _p, _p, _p, _i, _p], C.c_int),
     "ts_bin_count": ([_i, _i, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p], C.c_int),
     "ts_bin_scan": ([_i, _p, _p, _p, _i, _p], C.c_int),
-    "ts_bin_emit": ([_i, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p], C.c_int),
-    "ts_bin_sort": ([_i, _p, _p, _p, _i, _i, _p, _p, _p], C.c_int),
+    "ts_bin_emit": ([_i, _p, _p, _p, _i, _i, _i, _p, _p, _p, _i, _p], C.c_int),
+    "ts_bin_reset_cursors": ([_i, _p, _p, _p], C.c_int),
+    "ts_bin_sort": ([_i, _p, _p, _p, _i, _i, _p, _p, _i, _p], C.c_int),
     "ts_bin_smem_sort_cap": ([], C.c_int),
     "ts_bin_counter_stride": ([], C.c_int),
     "ts_bin_scan_work_ints": ([], C.c_int),
-    "ts_blend_fwd": ([_i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _i, _p], C.c_int),
+    "ts_blend_fwd": ([_i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p], C.c_int),
     "ts_blend_bwd": ([_i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p], C.c_int),
     "ts_ssim_fwd": ([_i, _i, _i, _i, _p, _p, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p], C.c_int),
     "ts_ssim_bwd": ([_i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p], C.c_int),

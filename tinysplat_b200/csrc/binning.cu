@@ -8,17 +8,19 @@
 //            the same pass packs the 48-byte raster record the blend kernels gather.
 //   scan   : exclusive scan of per-tile counts (single CTA; T <= ~130k tiles).
 //   emit   : scatter key = depth_bits<<32 | gaussian_id into the tile's bucket.
-//   sort   : one CTA per tile sorts its bucket in SHARED memory (bitonic on 64-bit keys: unique
-//            keys -> deterministic, ties in depth resolved by gaussian id exactly like a stable
-//            sort of the emission order), writes the 32-bit id list.
+//   sort   : per tile, on 64-bit keys (unique -> deterministic, ties in depth resolved by gaussian id
+//            exactly like a stable sort of the emission order): lists of <= 512 entries by ONE WARP
+//            in registers; longer lists by one CTA — every warp sorts a chunk in registers, then
+//            log2(#warps) merge-path levels in shared memory (O(n log n) instead of the O(n log^2 n)
+//            of a shared-memory bitonic network); writes the 32-bit id list.
 // Traffic per intersection: 8 B write + 8 B read + 4 B write, vs ~150 B for 6 radix passes.
+#include <climits>
 #include "ts_common.cuh"
 #include "ts_binning.cuh"
 
 namespace ts {
 
 constexpr int kBinThreads = 256;
-constexpr int kSortThreads = 256;
 constexpr int kSmemSortCap = 16384;  // 128 KB of 64-bit keys
 template <int CH>
 __global__ void __launch_bounds__(kBinThreads)
@@ -57,7 +59,7 @@ bin_count_kernel(int N, const float2* __restrict__ xys, const int32_t* __restric
 __global__ void __launch_bounds__(kBinThreads)
 bin_emit_kernel(int N, const float* __restrict__ depths, const int32_t* __restrict__ radii,
                 const float4* __restrict__ recs, int tbx, int tby, int cull,
-                int32_t* __restrict__ cursors, uint64_t* __restrict__ keys) {
+                int32_t* __restrict__ cursors, uint64_t* __restrict__ keys, int cap) {
     const int i = blockIdx.x * kBinThreads + threadIdx.x;
     int lox = 0, loy = 0, hix = 0, hiy = 0;
     uint64_t key = 0;
@@ -87,14 +89,14 @@ bin_emit_kernel(int N, const float* __restrict__ depths, const int32_t* __restri
             }
 #pragma unroll
             for (int k = 0; k < kCoopThreshold; ++k)
-                if (k < n) keys[slots[k]] = key;
+                if (k < n && slots[k] < cap) keys[slots[k]] = key;     // cap: see ts_bin_emit
             lox = loy = hix = hiy = 0;   // done; nothing left for the cooperative path
         }
     }
     for_each_tile(lox, loy, hix, hiy, tbx, (uint32_t)key, (uint32_t)(key >> 32),
                   [&](int tile, uint32_t lo, uint32_t hi) {
                       int slot = atomicAdd(cursors + (size_t)tile * kCounterStride, 1);
-                      keys[slot] = ((uint64_t)hi << 32) | lo;
+                      if (slot < cap) keys[slot] = ((uint64_t)hi << 32) | lo;
                   });
 }
 
@@ -221,31 +223,10 @@ __device__ __forceinline__ void bitonic_sort(Ptr s, int P, int nthreads) {
     }
 }
 
-// One CTA per tile; only tiles with lo_count < n <= hi_count are handled by this launch
-// (size classes keep shared memory per CTA, and so occupancy, matched to the list length).
-__global__ void __launch_bounds__(kSortThreads)
-bin_sort_kernel(int T, const int32_t* __restrict__ offsets, const uint64_t* __restrict__ keys,
-                int32_t* __restrict__ ids_sorted, int lo_count, int hi_count) {
-    TS_DYN_SMEM(uint64_t, s_keys, 16);
-    const int tile = blockIdx.x;
-    const int start = __ldg(offsets + tile);
-    const int n = __ldg(offsets + tile + 1) - start;
-    if (n <= lo_count || n > hi_count) return;
-    int P = 2;
-    while (P < n) P <<= 1;
-    for (int i = threadIdx.x; i < P; i += kSortThreads)
-        s_keys[i] = (i < n) ? keys[start + i] : ~0ull;
-    __syncthreads();
-    bitonic_sort(s_keys, P, kSortThreads);
-    for (int i = threadIdx.x; i < n; i += kSortThreads) ids_sorted[start + i] = (int32_t)(uint32_t)s_keys[i];
-}
-
-// ---- warp-per-tile register sort (lists of up to 512 entries) ---------------------------------
-// Each lane holds E consecutive keys (blocked layout, index = lane*E + slot).  Bitonic stages with
-// stride < E are compare-exchanges between a lane's own registers; strides >= E exchange whole
-// registers with lane ^ (stride/E) through shuffles.  No __syncthreads, no shared-memory traffic
-// inside the network; shared memory is used once to turn the coalesced load into the blocked
-// layout (skewed by one slot per E to stay bank-conflict free) and once for the coalesced store.
+// ---- register sort network of one warp -----------------------------------------------------------
+// Each lane holds E consecutive keys (blocked layout, index = lane*E + slot) of a 32*E-key chunk.
+// Bitonic stages with stride < E are compare-exchanges between a lane's own registers; strides >= E
+// exchange whole registers with lane ^ (stride/E) through shuffles.  No barriers, no shared memory.
 constexpr int kWarpSortMax = 512;
 constexpr int kWarpSortSlice = kWarpSortMax + 32;   // u64 per warp incl. skew
 
@@ -256,21 +237,10 @@ __device__ __forceinline__ void cex(uint64_t& a, uint64_t& b, bool asc) {
 }
 
 template <int E>
-__device__ __forceinline__ void warp_sort_tile(uint64_t* sw, const uint64_t* __restrict__ keys,
-                                               int32_t* __restrict__ out, int start, int n) {
+__device__ __forceinline__ void warp_sort_regs(uint64_t (&v)[E]) {
     constexpr int P = 32 * E;
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    auto phys = [](int idx) { return idx + idx / E; };
-#pragma unroll
-    for (int s = 0; s < E; ++s) {
-        int idx = lane + 32 * s;
-        sw[phys(idx)] = (idx < n) ? keys[start + idx] : ~0ull;
-    }
-    __syncwarp(full);
-    uint64_t v[E];
-#pragma unroll
-    for (int s = 0; s < E; ++s) v[s] = sw[phys(lane * E + s)];
     // phase 1 (k <= E): every lane sorts its own E keys in registers, fully unrolled
 #pragma unroll
     for (int k = 2; k <= E; k <<= 1) {
@@ -308,6 +278,27 @@ __device__ __forceinline__ void warp_sort_tile(uint64_t* sw, const uint64_t* __r
                 if ((s & j) == 0) cex(v[s], v[s | j], asc);
         }
     }
+}
+
+// ---- warp-per-tile sort (lists of up to 512 entries) --------------------------------------------
+// Shared memory is used once to turn the coalesced load into the blocked layout (skewed by one slot
+// per E to stay bank-conflict free) and once for the coalesced store.
+template <int E>
+__device__ __forceinline__ void warp_sort_tile(uint64_t* sw, const uint64_t* __restrict__ keys,
+                                               int32_t* __restrict__ out, int start, int n) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    auto phys = [](int idx) { return idx + idx / E; };
+#pragma unroll
+    for (int s = 0; s < E; ++s) {
+        int idx = lane + 32 * s;
+        sw[phys(idx)] = (idx < n) ? keys[start + idx] : ~0ull;
+    }
+    __syncwarp(full);
+    uint64_t v[E];
+#pragma unroll
+    for (int s = 0; s < E; ++s) v[s] = sw[phys(lane * E + s)];
+    warp_sort_regs<E>(v);
     __syncwarp(full);
     uint32_t* s32 = reinterpret_cast<uint32_t*>(sw);
 #pragma unroll
@@ -321,21 +312,23 @@ __device__ __forceinline__ void warp_sort_tile(uint64_t* sw, const uint64_t* __r
     __syncwarp(full);
 }
 
-// -DTS_SORT_MIN_CTAS=3 (compile-time experiment, unmeasured): the kernel uses 108 registers -> 2 CTAs
-// (16 warps) per SM; capped at 80 registers (16 bytes of spill) 3 CTAs fit.
-#ifdef TS_SORT_MIN_CTAS
-__global__ void __launch_bounds__(256, TS_SORT_MIN_CTAS)
-#else
 __global__ void __launch_bounds__(256)
-#endif
 bin_sort_warp_kernel(int T, const int32_t* __restrict__ offsets, const uint64_t* __restrict__ keys,
-                     int32_t* __restrict__ ids_sorted) {
+                     int32_t* __restrict__ ids_sorted, int cap, int max_sorted) {
     __shared__ __align__(16) uint64_t s_keys[8 * kWarpSortSlice];
     const int tile = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (tile >= T) return;
     const int start = __ldg(offsets + tile);
     const int n = __ldg(offsets + tile + 1) - start;
-    if (n <= 0 || n > kWarpSortMax) return;
+    if (n <= 0 || start + n > cap) return;                         // cap: see ts_bin_emit
+    if (n > max_sorted) {
+        // longer than any size class this call launches (the host's bound was a guess): the list stays
+        // unsorted, but it must hold VALID ids — the blend kernel queued behind us gathers through it
+        // before the host has noticed and repeated the pass
+        for (int i = threadIdx.x & 31; i < n; i += 32) ids_sorted[start + i] = (int32_t)(uint32_t)keys[start + i];
+        return;
+    }
+    if (n > kWarpSortMax) return;
     uint64_t* sw = s_keys + (threadIdx.x >> 5) * kWarpSortSlice;
     if (n == 1) { if ((threadIdx.x & 31) == 0) ids_sorted[start] = (int32_t)(uint32_t)keys[start]; }
     else if (n <= 64) warp_sort_tile<2>(sw, keys, ids_sorted, start, n);
@@ -344,16 +337,88 @@ bin_sort_warp_kernel(int T, const int32_t* __restrict__ offsets, const uint64_t*
     else warp_sort_tile<16>(sw, keys, ids_sorted, start, n);
 }
 
+// ---- CTA-per-tile merge sort (lists of 513 .. 16384 entries) -------------------------------------
+// NT threads sort P = NT*E keys.  Thread t owns positions [t*E, (t+1)*E) throughout: (1) each warp
+// sorts its 32*E-key chunk with the register network above; (2) log2(NT/32) merge levels: the keys go
+// to shared memory, every thread finds where ITS E outputs start in the two runs being merged (merge
+// path: a binary search along the cross diagonal), merges E keys serially into registers, and the
+// registers go back to shared memory for the next level.  O(n log n) compares and 2 barriers per
+// level; the shared-memory bitonic network this replaces did log^2 n / 2 barrier-separated stages
+// (0.056 -> 0.234 ms for 2x the pairs on the 2M scene, 0.39 ms on the dense 1M scene).
+// Index skew (one slot per E) keeps the stride-E accesses of the owners bank-conflict free.
+template <int E, int NT>
+__device__ __forceinline__ void cta_merge_sort_tile(uint64_t* s, const uint64_t* __restrict__ keys,
+                                                    int32_t* __restrict__ out, int start, int n) {
+    constexpr int P = NT * E;
+    const int tid = threadIdx.x;
+    auto phys = [](int idx) { return idx + idx / E; };
+    for (int i = tid; i < P; i += NT) s[phys(i)] = (i < n) ? keys[start + i] : ~0ull;
+    __syncthreads();
+    uint64_t v[E];
+#pragma unroll
+    for (int k = 0; k < E; ++k) v[k] = s[phys(tid * E + k)];
+    warp_sort_regs<E>(v);
+#pragma unroll 1
+    for (int L = 32 * E; L < P; L <<= 1) {
+        __syncthreads();                                   // the previous level's reads are done
+#pragma unroll
+        for (int k = 0; k < E; ++k) s[phys(tid * E + k)] = v[k];
+        __syncthreads();
+        const int o0 = tid * E;
+        const int base = o0 & ~(2 * L - 1);                // the pair of runs [base, base+L) and [base+L, base+2L)
+        const int d = o0 - base;                           // this thread's outputs start at rank d of the merged pair
+        auto A = [&](int i) { return s[phys(base + i)]; };
+        auto B = [&](int i) { return s[phys(base + L + i)]; };
+        int lo = max(0, d - L), hi = min(d, L);
+        while (lo < hi) {                                  // ties take A first (as the serial merge below)
+            const int mid = (lo + hi) >> 1;
+            if (A(mid) <= B(d - 1 - mid)) lo = mid + 1; else hi = mid;
+        }
+        int a = lo, b = d - lo;
+        uint64_t ka = (a < L) ? A(a) : ~0ull, kb = (b < L) ? B(b) : ~0ull;
+#pragma unroll
+        for (int k = 0; k < E; ++k) {
+            const bool take_a = (b >= L) || (a < L && ka <= kb);
+            v[k] = take_a ? ka : kb;
+            if (take_a) { ++a; ka = (a < L) ? A(a) : ~0ull; }
+            else        { ++b; kb = (b < L) ? B(b) : ~0ull; }
+        }
+    }
+    __syncthreads();
+    uint32_t* s32 = reinterpret_cast<uint32_t*>(s);
+#pragma unroll
+    for (int k = 0; k < E; ++k) s32[tid * E + k + tid] = (uint32_t)v[k];     // skew 1 word per thread
+    __syncthreads();
+    for (int i = tid; i < n; i += NT) out[start + i] = (int32_t)s32[i + i / E];
+}
+
+// One CTA per tile; a launch handles the tiles with lo_count < n <= NT*E_HI (size classes keep the
+// threads, shared memory and occupancy of a CTA matched to the list length).
+template <int NT, int E_LO, int E_HI>
+__global__ void __launch_bounds__(NT)
+bin_sort_cta_kernel(int T, const int32_t* __restrict__ offsets, const uint64_t* __restrict__ keys,
+                    int32_t* __restrict__ ids_sorted, int lo_count, int cap) {
+    TS_DYN_SMEM(uint64_t, s_keys, 16);
+    const int tile = blockIdx.x;
+    const int start = __ldg(offsets + tile);
+    const int n = __ldg(offsets + tile + 1) - start;
+    if (n <= lo_count || n > NT * E_HI || start + n > cap) return;
+    if (E_LO != E_HI && n <= NT * E_LO) cta_merge_sort_tile<E_LO, NT>(s_keys, keys, ids_sorted, start, n);
+    else cta_merge_sort_tile<E_HI, NT>(s_keys, keys, ids_sorted, start, n);
+}
+
+constexpr size_t cta_sort_smem(int NT, int E) { return sizeof(uint64_t) * ((size_t)NT * E + NT); }
+
 // Fallback for tiles whose list exceeds the shared-memory cap: same network, in global scratch.
 __global__ void __launch_bounds__(1024)
 bin_sort_big_kernel(int T, const int32_t* __restrict__ offsets, const uint64_t* __restrict__ keys,
                     int32_t* __restrict__ ids_sorted, int cap, int P, uint64_t* __restrict__ scratch,
-                    int32_t* __restrict__ counter) {
+                    int32_t* __restrict__ counter, int key_cap) {
     __shared__ int s_slot;
     const int tile = blockIdx.x;
     const int start = __ldg(offsets + tile);
     const int n = __ldg(offsets + tile + 1) - start;
-    if (n <= cap) return;
+    if (n <= cap || n > P || start + n > key_cap) return;
     if (threadIdx.x == 0) s_slot = atomicAdd(counter, 1);
     __syncthreads();
     uint64_t* buf = scratch + (size_t)s_slot * P;
@@ -361,6 +426,13 @@ bin_sort_big_kernel(int T, const int32_t* __restrict__ offsets, const uint64_t* 
     __syncthreads();
     bitonic_sort(buf, P, 1024);
     for (int i = threadIdx.x; i < n; i += 1024) ids_sorted[start + i] = (int32_t)(uint32_t)buf[i];
+}
+
+// emit advanced the cursors; a host that has to repeat emit (its key buffer was too small) restores them
+__global__ void __launch_bounds__(kBinThreads)
+bin_reset_cursors_kernel(int T, const int32_t* __restrict__ offsets, int32_t* __restrict__ cursors) {
+    const int t = blockIdx.x * kBinThreads + threadIdx.x;
+    if (t < T) cursors[(size_t)t * kCounterStride] = offsets[t];
 }
 
 }  // namespace ts
@@ -418,7 +490,7 @@ int ts_bin_scan(int num_tiles, int32_t* tile_counts, int32_t* tile_offsets, int3
 
 int ts_bin_emit(int N, const float* depths, const int32_t* radii, const float* recs, int tiles_x,
                 int tiles_y, int cull_mode, const int32_t* tile_offsets, int32_t* cursors,
-                uint64_t* keys, ts_stream_t stream) {
+                uint64_t* keys, int capacity, ts_stream_t stream) {
     if (N < 0 || tiles_x <= 0 || tiles_y <= 0) return TS_ERR_INVALID;
     if (N == 0) return TS_OK;
     if (!depths || !radii || !recs || !tile_offsets || !cursors || !keys) return TS_ERR_INVALID;
@@ -426,32 +498,55 @@ int ts_bin_emit(int N, const float* depths, const int32_t* radii, const float* r
     cudaStream_t st = (cudaStream_t)stream;
     int grid = (N + ts::kBinThreads - 1) / ts::kBinThreads;
     ts::bin_emit_kernel<<<grid, ts::kBinThreads, 0, st>>>(N, depths, radii, (const float4*)recs, tiles_x,
-                                                          tiles_y, cull_mode, cursors, keys);
+                                                          tiles_y, cull_mode, cursors, keys,
+                                                          capacity > 0 ? capacity : INT32_MAX);
     TS_CHECK_LAUNCH("ts_bin_emit");
+    return TS_OK;
+}
+
+int ts_bin_reset_cursors(int num_tiles, const int32_t* tile_offsets, int32_t* cursors, ts_stream_t stream) {
+    if (num_tiles <= 0 || !tile_offsets || !cursors) return TS_ERR_INVALID;
+    ts::bin_reset_cursors_kernel<<<(num_tiles + ts::kBinThreads - 1) / ts::kBinThreads, ts::kBinThreads, 0, (cudaStream_t)stream>>>(num_tiles, tile_offsets, cursors);
+    TS_CHECK_LAUNCH("ts_bin_reset_cursors");
     return TS_OK;
 }
 
 int ts_bin_sort(int num_tiles, const int32_t* tile_offsets, uint64_t* keys, int32_t* ids_sorted,
                 int max_count, int n_big_tiles, uint64_t* big_scratch, int32_t* big_counter,
-                ts_stream_t stream) {
+                int capacity, ts_stream_t stream) {
     if (num_tiles <= 0 || !tile_offsets) return TS_ERR_INVALID;
     if (max_count <= 0) return TS_OK;
     if (!keys || !ids_sorted) return TS_ERR_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
-    // per device and context, cheap: set on every call (a process may drive several GPUs)
-    TS_CHECK_CUDA(cudaFuncSetAttribute(ts::bin_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       ts::kSmemSortCap * (int)sizeof(uint64_t)), "ts_bin_sort/attr");
+    const int cap = capacity > 0 ? capacity : INT32_MAX;
     // lists of <= 512 entries: one warp per tile, keys in registers
-    ts::bin_sort_warp_kernel<<<(num_tiles + 7) / 8, 256, 0, st>>>(num_tiles, tile_offsets, keys, ids_sorted);
+    ts::bin_sort_warp_kernel<<<(num_tiles + 7) / 8, 256, 0, st>>>(num_tiles, tile_offsets, keys, ids_sorted, cap,
+                                                                  n_big_tiles > 0 ? INT32_MAX : min(max_count, ts::kSmemSortCap));
     TS_CHECK_LAUNCH("ts_bin_sort/warp");
-    // longer lists: one CTA per tile in shared memory, size classes (512,2048], (2048,cap]
-    const int bounds[3] = {ts::kWarpSortMax, 2048, ts::kSmemSortCap};
-    for (int c = 0; c < 2; ++c) {
-        if (max_count <= bounds[c]) break;
-        size_t smem = sizeof(uint64_t) * (size_t)bounds[c + 1];
-        ts::bin_sort_kernel<<<num_tiles, ts::kSortThreads, smem, st>>>(num_tiles, tile_offsets, keys, ids_sorted,
-                                                                      bounds[c], bounds[c + 1]);
-        TS_CHECK_LAUNCH("ts_bin_sort");
+    // longer lists: one CTA per tile (register chunk sort + merge-path levels); a class is launched
+    // only when max_count says some tile can need it
+    if (max_count > ts::kWarpSortMax) {
+        constexpr size_t smem = ts::cta_sort_smem(256, 8);
+        ts::bin_sort_cta_kernel<256, 4, 8><<<num_tiles, 256, smem, st>>>(num_tiles, tile_offsets, keys, ids_sorted,
+                                                                       ts::kWarpSortMax, cap);
+        TS_CHECK_LAUNCH("ts_bin_sort/cta256");
+    }
+    if (max_count > 2048) {
+        constexpr size_t smem = ts::cta_sort_smem(512, 16);
+        // per device and context, cheap: set on every call (a process may drive several GPUs)
+        TS_CHECK_CUDA(cudaFuncSetAttribute(ts::bin_sort_cta_kernel<512, 8, 16>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "ts_bin_sort/attr");
+        ts::bin_sort_cta_kernel<512, 8, 16><<<num_tiles, 512, smem, st>>>(num_tiles, tile_offsets, keys, ids_sorted,
+                                                                        2048, cap);
+        TS_CHECK_LAUNCH("ts_bin_sort/cta512");
+    }
+    if (max_count > 8192) {
+        constexpr size_t smem = ts::cta_sort_smem(1024, 16);
+        TS_CHECK_CUDA(cudaFuncSetAttribute(ts::bin_sort_cta_kernel<1024, 16, 16>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "ts_bin_sort/attr");
+        ts::bin_sort_cta_kernel<1024, 16, 16><<<num_tiles, 1024, smem, st>>>(num_tiles, tile_offsets, keys, ids_sorted,
+                                                                           8192, cap);
+        TS_CHECK_LAUNCH("ts_bin_sort/cta1024");
     }
     if (n_big_tiles > 0) {
         if (!big_scratch || !big_counter) return TS_ERR_CAPACITY;
@@ -459,7 +554,7 @@ int ts_bin_sort(int num_tiles, const int32_t* tile_offsets, uint64_t* keys, int3
         while (P < max_count) P <<= 1;
         TS_CHECK_CUDA(cudaMemsetAsync(big_counter, 0, sizeof(int32_t), st), "ts_bin_sort/memset");
         ts::bin_sort_big_kernel<<<num_tiles, 1024, 0, st>>>(num_tiles, tile_offsets, keys, ids_sorted,
-                                                            ts::kSmemSortCap, P, big_scratch, big_counter);
+                                                            ts::kSmemSortCap, P, big_scratch, big_counter, cap);
         TS_CHECK_LAUNCH("ts_bin_sort/big");
     }
     return TS_OK;

@@ -11,6 +11,7 @@
 //
 // Not HBM-bound: fp32 FMA/MUFU issue bound (forward at ~89 % of peak issue rate); backward adds a
 // per-warp shared-memory reduction and L2 vector atomics (~72 % of peak issue rate).
+#include <climits>
 #include <cstdlib>
 #include <cstring>
 #include "ts_blend_common.cuh"
@@ -80,7 +81,7 @@ blend_fwd_kernel(int H, int W, int tbx, const int32_t* __restrict__ tile_offsets
                  const int32_t* __restrict__ ids, const float4* __restrict__ recs,
                  const float* __restrict__ background, float* __restrict__ out_img,
                  float* __restrict__ out_ch3, float* __restrict__ final_T,
-                 int32_t* __restrict__ n_contrib, int clamp_max1) {
+                 int32_t* __restrict__ n_contrib, int clamp_max1, int cap) {
     __shared__ __align__(16) float4 s_rec[2][kBatch * 3];
     __shared__ unsigned s_mask[8][8];  // [sub-block][staging warp]
 #if TS_FWD_LISTS
@@ -91,7 +92,11 @@ blend_fwd_kernel(int H, int W, int tbx, const int32_t* __restrict__ tile_offsets
     const int tid = threadIdx.x;
     const int tile = blockIdx.y * tbx + blockIdx.x;
     const int start = __ldg(tile_offsets + tile);
-    const int count = __ldg(tile_offsets + tile + 1) - start;
+    // cap = capacity of the id list: when the host sized it from an earlier step and this step needs
+    // more (ts_bin_emit), a list that does not fit was neither filled nor sorted: skip the tile — the
+    // host detects the overflow and renders again
+    const int end = __ldg(tile_offsets + tile + 1);
+    const int count = end <= cap ? end - start : 0;
     const int nb = (count + kBatch - 1) / kBatch;
 
     float T = 1.f;
@@ -554,14 +559,15 @@ int ts_get_blend_mode(void) { return ts::blend_mode(); }
 int ts_blend_fwd(int CH, int img_height, int img_width, int tiles_x, int tiles_y,
                  const int32_t* tile_offsets, const int32_t* ids_sorted, const float* recs,
                  const float* background, float* out_img, float* out_ch3, float* final_T,
-                 int32_t* n_contrib, int clamp_max1, ts_stream_t stream) {
+                 int32_t* n_contrib, int clamp_max1, int capacity, ts_stream_t stream) {
     if (CH < 1 || CH > 4 || img_height <= 0 || img_width <= 0 || tiles_x <= 0 || tiles_y <= 0) return TS_ERR_INVALID;
     if (!tile_offsets || !background || !out_img || !final_T || !n_contrib) return TS_ERR_INVALID;
     if (recs && !ts::aligned16(recs)) return TS_ERR_ALIGN;
     dim3 grid(tiles_x, tiles_y);
     cudaStream_t st = (cudaStream_t)stream;
+    const int cap = capacity > 0 ? capacity : INT32_MAX;
 #define TS_LAUNCH_FWD(C) \
-    ts::blend_fwd_kernel<C><<<grid, ts::kBlendThreads, 0, st>>>(img_height, img_width, tiles_x, tile_offsets, ids_sorted, (const float4*)recs, background, out_img, out_ch3, final_T, n_contrib, clamp_max1)
+    ts::blend_fwd_kernel<C><<<grid, ts::kBlendThreads, 0, st>>>(img_height, img_width, tiles_x, tile_offsets, ids_sorted, (const float4*)recs, background, out_img, out_ch3, final_T, n_contrib, clamp_max1, cap)
     switch (CH) {
         case 1: TS_LAUNCH_FWD(1); break;
         case 2: TS_LAUNCH_FWD(2); break;

@@ -8,9 +8,9 @@ SH colour is written straight into the packed raster record, RGB and depth share
 4-channel blend pass, and blend-backward's packed gradients are consumed directly by
 projection-backward and SH-backward.  Forward = 7-8 launches, backward = 3 + one memset.
 
-The single device->host read (3 ints: intersection count, max list length, oversize tiles) is
-issued right after the tile scan and hidden behind the SH kernel: the host waits on an event
-while the GPU still has SH work queued, then launches emit/sort/blend before the GPU drains.
+The single device->host read (3 ints: intersection count, max list length, oversize tiles) no
+longer stalls the step: emit / sort / blend are launched with buffers sized from earlier steps and
+the read happens after the blend kernel has been queued (tinysplat_b200/binning.py).
 """
 from __future__ import annotations
 
@@ -23,10 +23,10 @@ from torch import Tensor
 from torch.autograd import Function
 
 from . import _lib
+from . import binning as _binning
 from . import rasterize as _rz
 
 BLOCK = 16
-_pinned_stats = {}
 _side_streams = {}
 USE_SIDE_STREAM = True     # SH kernels on a second stream, overlapping binning / projection-backward
 # Experiment for the next GPU session (off by default, unmeasured): run SH-BACKWARD on a
@@ -53,13 +53,6 @@ def _sh_bwd_stream(dev) -> "torch.cuda.Stream":
     if key not in _prio_streams:
         _prio_streams[key] = torch.cuda.Stream(device=dev, priority=-1)
     return _prio_streams[key]
-
-
-def _stats_buffer(dev) -> Tensor:
-    key = str(dev)
-    if key not in _pinned_stats:
-        _pinned_stats[key] = torch.empty(4, dtype=torch.int32).pin_memory()
-    return _pinned_stats[key]
 
 
 class XysSink:
@@ -141,38 +134,26 @@ class _RenderFused(Function):
         stats = torch.empty(lib.ts_bin_scan_work_ints(), **i32)
         _lib.call("ts_bin_scan", T, _lib.ptr(counts), _lib.ptr(offsets), _lib.ptr(stats),
                   lib.ts_bin_smem_sort_cap(), st)
-        host = _stats_buffer(dev)
-        main_stream = torch.cuda.current_stream(dev)     # the tensors' device, not the current one
-        with torch.cuda.stream(main_stream):
-            host.copy_(stats[:4], non_blocking=True)
-        ev = torch.cuda.Event()
-        ev.record(main_stream)
-        ev.synchronize()
-        M, max_count, n_big, _ = host.tolist()
-        keys = torch.empty(max(M, 1), device=dev, dtype=torch.int64)
-        ids_sorted = torch.empty(max(M, 1), **i32)
-        if M > 0:
-            _lib.call("ts_bin_emit", N, _lib.ptr(depths), _lib.ptr(radii), _lib.ptr(recs), tx, ty,
-                      int(cull_mode), _lib.ptr(offsets), _lib.ptr(counts), _lib.ptr(keys), st)
-            big_scratch = big_counter = None
-            if n_big > 0:
-                P = 1 << (max_count - 1).bit_length()
-                big_scratch = torch.empty(n_big * P, device=dev, dtype=torch.int64)
-                big_counter = torch.empty(1, **i32)
-            _lib.call("ts_bin_sort", T, _lib.ptr(offsets), _lib.ptr(keys), _lib.ptr(ids_sorted), max_count,
-                      n_big, _lib.ptr(big_scratch), _lib.ptr(big_counter), st)
-        _rz.last_stats.update(num_intersects=M, max_per_tile=max_count, bins_reused=False)
-        global last_bins
-        last_bins = (offsets, ids_sorted, M)      # inspection hook (parity tests read the tile lists)
+        # emit + sort are launched at once with buffers sized from earlier steps; the 3 ints that say
+        # whether that was enough are read after the blend kernel has been queued (binning.py)
+        bins = _binning.emit_and_sort(N, T, tx, ty, int(cull_mode), depths, radii, recs, offsets, counts, stats, st)
         if side is not main:
             main.wait_stream(side)          # colours must be in `recs` before blending
         rgb = torch.empty(H, W, 3, **f32)
         depth_img = torch.empty(H, W, **f32)
         final_T = torch.empty(H, W, **f32)
         n_contrib = torch.empty(H, W, **i32)
-        _lib.call("ts_blend_fwd", 4, H, W, tx, ty, _lib.ptr(offsets), _lib.ptr(ids_sorted), _lib.ptr(recs),
-                  _lib.ptr(bg_c), _lib.ptr(rgb), _lib.ptr(depth_img), _lib.ptr(final_T), _lib.ptr(n_contrib),
-                  1 if clamp_rgb else 0, st)
+
+        def blend():
+            _lib.call("ts_blend_fwd", 4, H, W, tx, ty, _lib.ptr(offsets), _lib.ptr(bins.ids_sorted), _lib.ptr(recs),
+                      _lib.ptr(bg_c), _lib.ptr(rgb), _lib.ptr(depth_img), _lib.ptr(final_T), _lib.ptr(n_contrib),
+                      1 if clamp_rgb else 0, bins.cap_arg, st)
+        blend()
+        bins.validate(blend)                # exact lists + a second blend if the capacity was too small
+        ids_sorted = bins.ids_sorted
+        _rz.last_stats.update(num_intersects=bins.M, max_per_tile=bins.max_count, bins_reused=False)
+        global last_bins
+        last_bins = (offsets, ids_sorted, bins.M)      # inspection hook (parity tests read the tile lists)
         ctx.save_for_backward(means_c, scales_c, quats_c, logit_c, view_c, proj_c, bg_c, radii, recs,
                               offsets, ids_sorted, final_T, n_contrib, mask)
         ctx.meta = (N, K, W, H, tx, ty, float(fx), float(fy), int(sh_degree), pflags, sflags,

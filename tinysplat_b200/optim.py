@@ -71,4 +71,10 @@ class FusedAdam(Adam):
                           (C.c_float * n)(*[lr for _, _, _, lr in chunk]),
                           (C.c_int64 * n)(*[int(s["step"].item()) for _, _, s, _ in chunk]),
                           b1, b2, eps, _lib.stream_ptr(chunk[0][0].device))
+                # the kernel wrote through raw pointers: tell autograd (and every cache keyed on
+                # Tensor._version, e.g. the tile-bin cache) that these tensors changed
+                for p, _, s, _ in chunk:
+                    torch.autograd.graph.increment_version(p)
+                    torch.autograd.graph.increment_version(s["exp_avg"])
+                    torch.autograd.graph.increment_version(s["exp_avg_sq"])
         return loss

@@ -1,8 +1,9 @@
 """gsplat.rasterize_gaussians drop-in  [REF tinysplat/splatting/rasterize.py:4,44,50,83-86].
 
 Host-side orchestration of K3 (count -> scan -> emit -> per-tile sort) and K4/K5 (blend).
-One device->host read of 3 ints per binning (the intersection count sizes the key buffer);
-binning is reused when the same geometry is rasterised again (the reference rasterises RGB
+The key / id buffers are sized from earlier calls and the 3 ints that confirm the size are read
+after the blend kernel has been queued (binning.py): the host does not drain the GPU mid-pass.
+Binning is reused when the same geometry is rasterised again (the reference rasterises RGB
 and then depth over identical xys/radii/conics [REF rasterize.py:42-50])."""
 from __future__ import annotations
 
@@ -13,35 +14,67 @@ from torch import Tensor
 from torch.autograd import Function
 
 from . import _lib
+from . import binning as _binning
 
 BLOCK = 16
 
 
 class TileBins:
     """Result of K3 for one (geometry, opacity, image size)."""
-    __slots__ = ("tile_offsets", "ids_sorted", "num_intersects", "max_per_tile", "tiles", "key",
-                 "_keepalive")
+    __slots__ = ("tile_offsets", "pending", "tiles", "key", "_keepalive")
 
-    def __init__(self, tile_offsets, ids_sorted, num_intersects, max_per_tile, tiles, key):
+    def __init__(self, tile_offsets, pending, tiles, key):
         self.tile_offsets = tile_offsets
-        self.ids_sorted = ids_sorted
-        self.num_intersects = num_intersects
-        self.max_per_tile = max_per_tile
+        self.pending = pending          # binning.PendingBins: ids_sorted / M are final after validate()
         self.tiles = tiles
         self.key = key
+
+    # reading any of these confirms the guessed buffer sizes first (a no-op once validated)
+    @property
+    def ids_sorted(self):
+        self.pending.validate()
+        return self.pending.ids_sorted[:max(self.pending.M, 1)]
+
+    @property
+    def num_intersects(self):
+        self.pending.validate()
+        return self.pending.M
+
+    @property
+    def max_per_tile(self):
+        self.pending.validate()
+        return self.pending.max_count
 
 
 _last_bins: Optional[TileBins] = None
 last_stats = {"num_intersects": 0, "max_per_tile": 0, "bins_reused": False}
 
 
-def _bins_key(xys, depths, radii, conics, opacity, H, W, cull):
-    return tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in (xys, depths, radii, conics, opacity)) \
-        + (H, W, cull)
+def _ident(t):
+    return (t.data_ptr(), t._version, tuple(t.shape))
 
 
-def pack_and_bin(xys, depths, radii, conics, opacity, colors, H, W, cull_mode=1, reuse=True):
-    """K3.  Returns (recs[N,12], TileBins).  recs always re-packed (colours differ per call)."""
+def opacity_identity(opacity: Tensor):
+    """What the bin cache compares instead of the opacity VALUES.  The reference builds a fresh
+    `torch.sigmoid(model.opacities)` for every rasterize call [REF rasterize.py:86], so the tensor
+    itself is new each time although its content is not: when the tensor is the sigmoid of a leaf,
+    the leaf (storage, version) identifies the content.  Otherwise the tensor's own identity."""
+    fn = opacity.grad_fn
+    if fn is not None and fn.name() == "SigmoidBackward0" and len(fn.next_functions) == 1:
+        src = fn.next_functions[0][0]
+        leaf = getattr(src, "variable", None)
+        if leaf is not None:
+            return ("sigmoid",) + _ident(leaf)
+    return _ident(opacity)
+
+
+def _bins_key(xys, depths, radii, conics, opac_id, H, W, cull):
+    return tuple(_ident(t) for t in (xys, depths, radii, conics)) + (opac_id, H, W, cull)
+
+
+def pack_and_bin(xys, depths, radii, conics, opacity, colors, H, W, cull_mode=1, reuse=True, opac_id=None):
+    """K3.  Returns (recs[N,12], TileBins).  recs always re-packed (colours differ per call).  The
+    caller must run `bins.pending.validate(rerun)` after queueing its blend kernel."""
     global _last_bins
     lib = _lib.load()
     dev = xys.device
@@ -54,7 +87,8 @@ def pack_and_bin(xys, depths, radii, conics, opacity, colors, H, W, cull_mode=1,
     _lib.call("ts_bin_count", N, CH, _lib.ptr(xys), _lib.ptr(depths), _lib.ptr(radii),
                                 _lib.ptr(conics), _lib.ptr(opacity), _lib.ptr(colors), H, W, tx, ty,
               cull_mode, 0, _lib.ptr(recs), _lib.ptr(counts), st)
-    key = _bins_key(xys, depths, radii, conics, opacity, H, W, cull_mode)
+    key = _bins_key(xys, depths, radii, conics, opac_id if opac_id is not None else _ident(opacity),
+                    H, W, cull_mode)
     if reuse and _last_bins is not None and _last_bins.key == key:
         last_stats["bins_reused"] = True
         return recs, _last_bins
@@ -62,21 +96,9 @@ def pack_and_bin(xys, depths, radii, conics, opacity, colors, H, W, cull_mode=1,
     offsets = torch.empty(T + 1, device=dev, dtype=torch.int32)
     stats = torch.empty(lib.ts_bin_scan_work_ints(), device=dev, dtype=torch.int32)
     _lib.call("ts_bin_scan", T, _lib.ptr(counts), _lib.ptr(offsets), _lib.ptr(stats), cap, st)
-    M, max_count, n_big, _ = stats[:4].tolist()   # the one host sync of the path
-    keys = torch.empty(max(M, 1), device=dev, dtype=torch.int64)
-    ids_sorted = torch.empty(max(M, 1), device=dev, dtype=torch.int32)
-    if M > 0:
-        _lib.call("ts_bin_emit", N, _lib.ptr(depths), _lib.ptr(radii), _lib.ptr(recs), tx, ty,
-                                   cull_mode, _lib.ptr(offsets), _lib.ptr(counts), _lib.ptr(keys), st)
-        big_scratch = big_counter = None
-        if n_big > 0:
-            P = 1 << (max_count - 1).bit_length()
-            big_scratch = torch.empty(n_big * P, device=dev, dtype=torch.int64)
-            big_counter = torch.empty(1, device=dev, dtype=torch.int32)
-        _lib.call("ts_bin_sort", T, _lib.ptr(offsets), _lib.ptr(keys), _lib.ptr(ids_sorted),
-                                   max_count, n_big, _lib.ptr(big_scratch), _lib.ptr(big_counter), st)
-    bins = TileBins(offsets, ids_sorted, M, max_count, (tx, ty), key)
-    last_stats.update(num_intersects=M, max_per_tile=max_count, bins_reused=False)
+    pending = _binning.emit_and_sort(N, T, tx, ty, int(cull_mode), depths, radii, recs, offsets, counts, stats, st)
+    bins = TileBins(offsets, pending, (tx, ty), key)
+    last_stats["bins_reused"] = False
     # hold references so data_ptr-based keys cannot alias freed memory
     bins._keepalive = (xys, depths, radii, conics, opacity)
     _last_bins = bins
@@ -91,7 +113,7 @@ def clear_bin_cache() -> None:
 class _RasterizeGaussians(Function):
     @staticmethod
     def forward(ctx, xys, depths, radii, conics, num_tiles_hit, colors, opacity, img_height,
-                img_width, background, cull_mode):
+                img_width, background, cull_mode, opac_id=None):
         _lib.require_cuda(xys, colors, opacity)
         lib = _lib.load()
         dev = xys.device
@@ -107,15 +129,21 @@ class _RasterizeGaussians(Function):
         radii_c = radii.detach().to(torch.int32).contiguous()
         bg = _lib.f32c(background.detach().to(dev))
         recs, bins = pack_and_bin(xys_c, depths_c, radii_c, conics_c, opac_c, colors_c, H, W,
-                                  cull_mode=cull_mode)
+                                  cull_mode=cull_mode, opac_id=opac_id)
         tx, ty = bins.tiles
         out_img = torch.empty(H, W, CH, device=dev, dtype=torch.float32)
         final_T = torch.empty(H, W, device=dev, dtype=torch.float32)
         n_contrib = torch.empty(H, W, device=dev, dtype=torch.int32)
-        _lib.call("ts_blend_fwd", CH, H, W, tx, ty, _lib.ptr(bins.tile_offsets),
-                                    _lib.ptr(bins.ids_sorted), _lib.ptr(recs), _lib.ptr(bg),
-                  _lib.ptr(out_img), None, _lib.ptr(final_T), _lib.ptr(n_contrib), 0,
-                  _lib.stream_ptr(dev))
+        pending = bins.pending
+
+        def blend():
+            _lib.call("ts_blend_fwd", CH, H, W, tx, ty, _lib.ptr(bins.tile_offsets),
+                      _lib.ptr(pending.ids_sorted), _lib.ptr(recs), _lib.ptr(bg),
+                      _lib.ptr(out_img), None, _lib.ptr(final_T), _lib.ptr(n_contrib), 0,
+                      pending.cap_arg, _lib.stream_ptr(dev))
+        blend()
+        pending.validate(blend)         # exact lists + a second blend if the guessed capacity was short
+        last_stats.update(num_intersects=pending.M, max_per_tile=pending.max_count)
         out_alpha = 1.0 - final_T
         ctx.save_for_backward(recs, bins.tile_offsets, bins.ids_sorted, bg, final_T, n_contrib,
                               radii_c, conics_c)
@@ -145,7 +173,7 @@ class _RasterizeGaussians(Function):
                                              _lib.ptr(grads), _lib.ptr(v_xys), _lib.ptr(v_conics),
                                              _lib.ptr(v_colors), _lib.ptr(v_opacity), st)
         return (v_xys, None, None, v_conics, None, v_colors, v_opacity.reshape(opac_shape),
-                None, None, None, None)
+                None, None, None, None, None)
 
 
 def rasterize_gaussians(xys: Tensor, depths: Tensor, radii: Tensor, conics: Tensor,
@@ -169,4 +197,5 @@ def rasterize_gaussians(xys: Tensor, depths: Tensor, radii: Tensor, conics: Tens
     elif background.shape[0] != colors.shape[-1]:
         raise ValueError("background must have one entry per colour channel")
     return _RasterizeGaussians.apply(xys, depths, radii, conics, num_tiles_hit, colors, opacity,
-                                     img_height, img_width, background, int(cull_mode))
+                                     img_height, img_width, background, int(cull_mode),
+                                     opacity_identity(opacity))
