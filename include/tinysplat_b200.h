@@ -212,12 +212,21 @@ TS_API int ts_blend_unpack_grads(int N, int CH, const int32_t* radii, const floa
  * launches. */
 TS_API int ts_set_blend_mode(int mode);
 TS_API int ts_get_blend_mode(void);
+/* Which kernel ts_blend_fwd launches: 0 = first generation (one pixel per lane), 1 = row pairs (two
+ * pixels per lane, packed fp32; default), -1 = back to the TS_BLEND_FWD environment variable / default.
+ * Both produce bit-identical images. */
+TS_API int ts_set_blend_fwd_mode(int mode);
+TS_API int ts_get_blend_fwd_mode(void);
 /* Test hook (host code, no GPU): the exact row mask the grouped backward computes for one packed
  * record (q0 = {x, y, hx, hy}, q1 = {A, B, C, opacity}, see ts_rec_floats) against tile
  * (tile_x, tile_y): bit (2*row + half) set = some pixel of tile row `row`, columns
  * 8*half..8*half+7, may reach alpha >= 1/255.  Must be a superset of the pixels the blend loop
  * accepts (tests/test_capi.py brute-forces it). */
 TS_API uint32_t ts_debug_rowmask(const float* q0_host, const float* q1_host, int tile_x, int tile_y);
+/* Test hook (device): rcp_out[i] = MUFU.RCP(x[i]), ex2_out[i] = MUFU.EX2(x[i]) as the blend kernels
+ * evaluate them.  Blend-backward relies on rcp(1) == 1 exactly (a pixel a Gaussian does not reach
+ * keeps its transmittance through T * rcp(1 - 0)); the GPU tests assert it. */
+TS_API int ts_debug_approx(int n, const float* x, float* rcp_out, float* ex2_out, ts_stream_t stream);
 
 /* ---- data-parallel gradient exchange in packed form -------------------------
  * Instead of all-reducing the finished parameter gradients (236 B per Gaussian at SH degree 3),

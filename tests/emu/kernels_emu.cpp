@@ -1,5 +1,5 @@
 // Compiles EVERY hot-path kernel of tinysplat_b200/csrc (project.cu, sh.cu, binning.cu, blend.cu,
-// blend_group.cu) unchanged as host code on the fiber SIMT emulator (ts_emu.h) and exposes
+// blend_pair.cu, blend_group.cu) unchanged as host code on the fiber SIMT emulator (ts_emu.h) and exposes
 //   * the blend kernels and the binning stages with the argument lists of their C-ABI entry points
 //     (host pointers instead of device pointers; the launch logic mirrors those entry points), and
 //   * emu_render_fused: the whole fused forward + backward of tinysplat_b200/fused.py,
@@ -10,6 +10,7 @@
 #include "../../tinysplat_b200/csrc/sh.cu"
 #include "../../tinysplat_b200/csrc/binning.cu"
 #include "../../tinysplat_b200/csrc/blend.cu"
+#include "../../tinysplat_b200/csrc/blend_pair.cu"
 #include "../../tinysplat_b200/csrc/blend_group.cu"
 #include "../../tinysplat_b200/csrc/peer.cu"
 #include "../../tinysplat_b200/csrc/adam.cu"
@@ -20,11 +21,17 @@
 #include <climits>
 
 static int g_emu_key_cap = INT32_MAX;
+static int g_emu_fwd_pair = 1;      // which blend-forward generation emu_blend_fwd runs (1 = row pairs, the default)
 
 namespace {
 template <int CH>
 int run_fwd(int H, int W, int tx, int ty, const int32_t* off, const int32_t* ids, const float* recs,
             const float* bg, float* out_img, float* out_ch3, float* final_T, int32_t* n_contrib, int clamp) {
+    if (g_emu_fwd_pair)
+        return ts_emu::launch(dim3(tx, ty), ts::kPThreads, [=]() {
+            ts::blend_fwd_pair_kernel<CH>(H, W, tx, off, ids, (const float4*)recs, bg, out_img, out_ch3, final_T,
+                                          n_contrib, clamp, g_emu_key_cap);
+        });
     return ts_emu::launch(dim3(tx, ty), ts::kBlendThreads, [=]() {
         ts::blend_fwd_kernel<CH>(H, W, tx, off, ids, (const float4*)recs, bg, out_img, out_ch3, final_T,
                                  n_contrib, clamp, g_emu_key_cap);
@@ -47,6 +54,8 @@ int run_bwd(int grouped, int H, int W, int tx, int ty, const int32_t* off, const
 }  // namespace
 
 extern "C" {
+
+void emu_set_fwd_mode(int pair) { g_emu_fwd_pair = pair; }
 
 int emu_blend_fwd(int CH, int H, int W, int tx, int ty, const int32_t* off, const int32_t* ids,
                   const float* recs, const float* bg, float* out_img, float* out_ch3, float* final_T,

@@ -326,8 +326,8 @@ def test_fused_node_matches_unfused_ops_on_a_larger_scene(blend_mode):
     cam = synthetic.make_camera(W, H, yaw_deg=5.0, shift=(0.1, 0.05, 0.0))
     sc = synthetic.make_scene(N, W, H, seed=12, sh_degree=3)
     sc["background"] = torch.tensor([0.3, 0.1, 0.7])
-    sc["quats"] = sc["quats"] * (0.5 + torch.rand(N, 1))        # un-normalised on purpose
     g = torch.Generator().manual_seed(3)
+    sc["quats"] = sc["quats"] * (0.5 + torch.rand(N, 1, generator=g))        # un-normalised on purpose
     wi = torch.rand(H, W, 3, generator=g).to(DEV)
     wd = torch.rand(H, W, generator=g).to(DEV)
     res = {}
@@ -338,7 +338,9 @@ def test_fused_node_matches_unfused_ops_on_a_larger_scene(blend_mode):
         res[pipeline] = (img, ex["depth"], ex["xys"].grad, [p.grad for p in model.parameters()], ex["radii"])
     a, b = res["reference"], res["fused"]
     assert torch.equal(a[4], b[4])
-    assert (a[0] - b[0]).abs().max().item() < 1e-5 and (a[1] - b[1]).abs().max().item() < 1e-4
+    # the two pipelines round differently BEFORE the blend (exp / normalise / sigmoid in torch vs folded
+    # into the kernels): xys and conics differ by an ulp, the image by a few 1e-5 (seen: 2.9e-5)
+    assert (a[0] - b[0]).abs().max().item() < TOL_IMG / 4 and (a[1] - b[1]).abs().max().item() < 1e-4
     assert rel_err(b[2], a[2]) < 1e-4
     for name, ga, gb in zip(PARAMS, a[3], b[3]):
         assert rel_err(gb, ga) < 1e-4, name
@@ -839,3 +841,39 @@ def test_depth_pass_reuses_the_tile_lists_of_the_rgb_pass():
     img2, _ = gsplat.rasterize_gaussians(xys, depths, radii, conics, num_tiles, rgbs, torch.sigmoid(model.opacities), H, W, bg)
     assert rz.last_stats["bins_reused"] is False
     assert (img2 - img).abs().max().item() > 0
+
+
+def test_device_approximations_the_blend_kernels_rely_on(lib):
+    """Blend-backward multiplies every row's transmittance by rcp(1 - alpha) with alpha = 0 where the
+    Gaussian does not reach the pixel: MUFU.RCP(1) must be exactly 1 (and stay within an ulp or two
+    elsewhere); MUFU.EX2 within 2 ulp + the documented 2^-22 relative error."""
+    from tinysplat_b200 import _lib
+    x = torch.cat([torch.tensor([1.0, 2.0, 0.5, 0.25, 4.0]), torch.linspace(0.001, 1.0, 4000)]).to(DEV)
+    rcp, ex2 = torch.empty_like(x), torch.empty_like(x)
+    _lib.call("ts_debug_approx", x.numel(), _lib.ptr(x), _lib.ptr(rcp), _lib.ptr(ex2), _lib.stream_ptr(x.device))
+    torch.cuda.synchronize()
+    assert rcp[0].item() == 1.0 and rcp[1].item() == 0.5 and rcp[2].item() == 2.0
+    assert ((rcp - 1.0 / x.double()).abs() / (1.0 / x.double())).max().item() < 2.5e-7
+    assert ((ex2 - torch.exp2(x.double())).abs() / torch.exp2(x.double())).max().item() < 5e-7
+
+
+@pytest.mark.parametrize("ch", [1, 3, 4])
+def test_both_forward_generations_give_the_same_bits(lib, ch):
+    """Row-pair forward (default) vs the first-generation forward: image, final T and n_contrib must be
+    bit-identical (packed fp32 pairs round like the scalar instructions, same operation order)."""
+    import gsplat
+    from tinysplat_b200 import rasterize as rz
+    N, W, H = 30000, 500, 300
+    xys, dep, rad, con, nt, colors, opac, bg = _raster_case(N, W, H, seed=5, CH=ch)
+    args = [t.to(DEV) for t in (xys, dep, rad, con, nt, colors, opac)]
+    res = []
+    for mode in (1, 0):
+        assert lib.ts_set_blend_fwd_mode(mode) == 0
+        try:
+            rz.clear_bin_cache()
+            with torch.no_grad():
+                img, alpha = gsplat.rasterize_gaussians(*args, H, W, bg.to(DEV))
+            res.append((img.clone(), alpha.clone()))
+        finally:
+            lib.ts_set_blend_fwd_mode(-1)
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])

@@ -65,7 +65,10 @@ _SIGNATURES = {
     "ts_peer_ipc_close": ([_p], C.c_int),
     "ts_set_blend_mode": ([_i], C.c_int),
     "ts_get_blend_mode": ([], C.c_int),
+    "ts_set_blend_fwd_mode": ([_i], C.c_int),
+    "ts_get_blend_fwd_mode": ([], C.c_int),
     "ts_debug_rowmask": ([_p, _p, _i, _i], C.c_uint32),
+    "ts_debug_approx": ([_i, _p, _p, _p, _p], C.c_int),
 }
 
 # flags (include/tinysplat_b200.h enum ts_flags)

@@ -529,6 +529,24 @@ int launch_blend_bwd_group(int CH, int gch, int H, int W, int tiles_x, int tiles
                            const float* v_out_img, const float* v_out_ch3, int split_ch3,
                            const float* v_out_alpha, float* grads, cudaStream_t st);
 
+// row-pair forward (blend_pair.cu)
+int launch_blend_fwd_pair(int CH, int H, int W, int tiles_x, int tiles_y, const int32_t* tile_offsets,
+                          const int32_t* ids, const float* recs, const float* background, float* out_img,
+                          float* out_ch3, float* final_T, int32_t* n_contrib, int clamp_max1, int cap,
+                          cudaStream_t st);
+
+// Which forward kernel ts_blend_fwd launches: 0 = first generation (blend_fwd_kernel, one pixel per
+// lane), 1 = row pairs (blend_pair.cu; default).  TS_BLEND_FWD ("warp" | "pair"), ts_set_blend_fwd_mode().
+static int g_blend_fwd_mode = -1;
+static int blend_fwd_mode() {
+    if (g_blend_fwd_mode < 0) {
+        const char* e = getenv("TS_BLEND_FWD");
+        if (e && !strcmp(e, "warp")) g_blend_fwd_mode = 0;
+        else g_blend_fwd_mode = 1;
+    }
+    return g_blend_fwd_mode;
+}
+
 // Which backward kernel ts_blend_bwd launches: 0 = first generation (blend_bwd_kernel, one warp
 // per sub-block), 1 = grouped (blend_group.cu; default).  Initialised once from TS_BLEND_MODE
 // ("warp" | "group"); ts_set_blend_mode() overrides it (tests, A/B benches).
@@ -555,6 +573,12 @@ int ts_set_blend_mode(int mode) {
     return TS_OK;
 }
 int ts_get_blend_mode(void) { return ts::blend_mode(); }
+int ts_set_blend_fwd_mode(int mode) {
+    if (mode < -1 || mode > 1) return TS_ERR_INVALID;
+    ts::g_blend_fwd_mode = mode;  // -1: back to TS_BLEND_FWD / the built-in default
+    return TS_OK;
+}
+int ts_get_blend_fwd_mode(void) { return ts::blend_fwd_mode(); }
 
 int ts_blend_fwd(int CH, int img_height, int img_width, int tiles_x, int tiles_y,
                  const int32_t* tile_offsets, const int32_t* ids_sorted, const float* recs,
@@ -566,6 +590,12 @@ int ts_blend_fwd(int CH, int img_height, int img_width, int tiles_x, int tiles_y
     dim3 grid(tiles_x, tiles_y);
     cudaStream_t st = (cudaStream_t)stream;
     const int cap = capacity > 0 ? capacity : INT32_MAX;
+    if (ts::blend_fwd_mode() == 1) {
+        ts::launch_blend_fwd_pair(CH, img_height, img_width, tiles_x, tiles_y, tile_offsets, ids_sorted, recs,
+                                  background, out_img, out_ch3, final_T, n_contrib, clamp_max1, cap, st);
+        TS_CHECK_LAUNCH("ts_blend_fwd/pair");
+        return TS_OK;
+    }
 #define TS_LAUNCH_FWD(C) \
     ts::blend_fwd_kernel<C><<<grid, ts::kBlendThreads, 0, st>>>(img_height, img_width, tiles_x, tile_offsets, ids_sorted, (const float4*)recs, background, out_img, out_ch3, final_T, n_contrib, clamp_max1, cap)
     switch (CH) {

@@ -23,6 +23,7 @@
 //   * 64 registers, 14 KB shared memory -> 15 CTAs (30 warps) per SM.
 // Still not HBM-bound: fp32 FMA / MUFU issue.
 #include "ts_blend_common.cuh"
+#include "ts_f32x2.cuh"
 
 namespace ts {
 
@@ -96,17 +97,23 @@ __device__ __forceinline__ float4 group_reduce_quad(const float (&val)[NV], int 
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = (i < NV) ? val[i < NV ? i : 0] : 0.f;
     const bool h4 = (l8 & 4) != 0;
-    float w[4];
+    float keep[4], recv[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const float send = h4 ? v[i] : v[i + 4];
-        const float keep = h4 ? v[i + 4] : v[i];
-        w[i] = keep + __shfl_xor_sync(full, send, 4);
+        keep[i] = h4 ? v[i + 4] : v[i];
+        recv[i] = __shfl_xor_sync(full, send, 4);
     }
+    // the four running sums live in two packed pairs: one FADD2 adds both halves
+    f32x2 w01 = add2(pack2(keep[0], keep[1]), pack2(recv[0], recv[1]));
+    f32x2 w23 = add2(pack2(keep[2], keep[3]), pack2(recv[2], recv[3]));
 #pragma unroll
-    for (int i = 0; i < 4; ++i) w[i] += __shfl_xor_sync(full, w[i], 2);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) w[i] += __shfl_xor_sync(full, w[i], 1);
+    for (int d = 2; d > 0; d >>= 1) {
+        const float a = __shfl_xor_sync(full, lo2(w01), d), b = __shfl_xor_sync(full, hi2(w01), d);
+        const float c = __shfl_xor_sync(full, lo2(w23), d), e = __shfl_xor_sync(full, hi2(w23), d);
+        w01 = add2(w01, pack2(a, b));
+        w23 = add2(w23, pack2(c, e));
+    }
     float e[2] = {0.f, 0.f};
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
@@ -119,13 +126,16 @@ __device__ __forceinline__ float4 group_reduce_quad(const float (&val)[NV], int 
         }
     }
     extra = make_float2(e[0], e[1]);
-    return make_float4(w[0], w[1], w[2], w[3]);
+    return make_float4(lo2(w01), hi2(w01), lo2(w23), hi2(w23));
 }
 
 // GCH = number of colour channels that carry a cotangent (GCH <= CH; the fused RGB+depth pass
 // with no depth loss has CH = 4, GCH = 3 and skips all channel-3 gradient arithmetic).
+#ifndef TS_GROUP_MIN_CTAS
+#define TS_GROUP_MIN_CTAS 1
+#endif
 template <int CH, int GCH>
-__global__ void __launch_bounds__(kGThreads)
+__global__ void __launch_bounds__(kGThreads, TS_GROUP_MIN_CTAS)
 blend_bwd_group_kernel(int H, int W, int tbx, const int32_t* __restrict__ tile_offsets,
                        const int32_t* __restrict__ ids, const float4* __restrict__ recs,
                        const float* __restrict__ background, const float* __restrict__ final_T,
@@ -181,6 +191,18 @@ blend_bwd_group_kernel(int H, int W, int tbx, const int32_t* __restrict__ tile_o
         Wacc[r] = T_final * (v_oa - bgdot);
         T[r] = T_final;
         ncmax = max(ncmax, nc[r]);
+    }
+
+    // rows (0,1) and (2,3) of the column as packed pairs: every per-row fp32 operation of the loop
+    // below is issued once per PAIR (FFMA2 / FMUL2 / FADD2)
+    f32x2 T2[2], W2[2], vo2[2][GCH], py2[2];
+#pragma unroll
+    for (int P = 0; P < 2; ++P) {
+        T2[P] = pack2(T[2 * P], T[2 * P + 1]);
+        W2[P] = pack2(Wacc[2 * P], Wacc[2 * P + 1]);
+        py2[P] = pack2(gm.py0 + (float)(2 * P), gm.py0 + (float)(2 * P + 1));
+#pragma unroll
+        for (int c = 0; c < GCH; ++c) vo2[P][c] = pack2(v_out[2 * P][c], v_out[2 * P + 1][c]);
     }
 
     if (tid == 0) s_nmax = 0;
@@ -245,41 +267,50 @@ blend_bwd_group_kernel(int H, int W, int tbx, const int32_t* __restrict__ tile_o
                 const float4 q1 = rec[c * 3 + 1];
                 const float4 q2 = rec[c * 3 + 2];
                 const float col[4] = {q2.x, q2.y, q2.z, q2.w};
-                // branch-free over the four rows.  A lane is one pixel COLUMN, so dx is common to
-                // its rows and only s0 = sum v_sigma, s1 = sum v_sigma dy, s2 = sum v_sigma dy^2
+                // branch-free over the four rows, two at a time.  A lane is one pixel COLUMN, so dx is
+                // common to its rows and only s0 = sum v_sigma, s1 = sum v_sigma dy, s2 = sum v_sigma dy^2
                 // are accumulated per row; the five geometric sums follow from them below, and
                 // v_opacity = sum vis * v_alpha = -s0 / opacity  (v_sigma = -opacity vis v_alpha).
-                float s0 = 0.f, s1 = 0.f, s2 = 0.f, dxc = 0.f;
-                float vis[4], araw[4], dyr[4];
-                bool ok[4];
+                // The accumulators hold -s0, -s1, -s2 (the sign is applied once, after the rows).
+                const float dxc = __fsub_rn(q0.x, gm.px);
+                const float axd = __fmul_rn(q1.x, dxc);
+                f32x2 n0, n1, n2, vc[GCH];
 #pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    const float pw = eval_power(q0, q1, gm.px, gm.py0 + (float)r, dxc, dyr[r]);
-                    vis[r] = ex2_approx(-fmaxf(pw, 0.f));
-                    araw[r] = __fmul_rn(q1.w, vis[r]);
-                    ok[r] = (rm & (1u << (2 * r))) != 0u && p < nc[r] && pw >= 0.f &&
-                            fminf(kAlphaMax, araw[r]) >= kAlphaMin;
-                    any = any || ok[r];
-                }
+                for (int P = 0; P < 2; ++P) {
+                    f32x2 dy;
+                    const f32x2 pw = eval_power2(dxc, axd, q0.y, q1.y, q1.z, py2[P], dy);
+                    const float pwa = lo2(pw), pwb = hi2(pw);
+                    const f32x2 araw = mul2(bcast2(q1.w), pack2(ex2_approx(-fmaxf(pwa, 0.f)), ex2_approx(-fmaxf(pwb, 0.f))));
+                    const float ara = lo2(araw), arb = hi2(araw);
+                    const float ama = fminf(kAlphaMax, ara), amb = fminf(kAlphaMax, arb);
+                    const bool oka = (rm & (1u << (4 * P))) != 0u && p < nc[2 * P] && pwa >= 0.f && ama >= kAlphaMin;
+                    const bool okb = (rm & (4u << (4 * P))) != 0u && p < nc[2 * P + 1] && pwb >= 0.f && amb >= kAlphaMin;
+                    any = any || oka || okb;
+                    const f32x2 alpha = pack2(oka ? ama : 0.f, okb ? amb : 0.f);
+                    const f32x2 oma = sub2(bcast2(1.f), alpha);
+                    // rcp_approx(1) == 1 exactly (checked on the device by the tests): a row that does
+                    // not contribute keeps its T
+                    const f32x2 ra = pack2(rcp_approx(lo2(oma)), rcp_approx(hi2(oma)));
+                    T2[P] = mul2(T2[P], ra);
+                    const f32x2 fac = mul2(alpha, T2[P]);                  // 0 when !ok
+                    f32x2 cv = mul2(bcast2(col[0]), vo2[P][0]);
 #pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    const float alpha = ok[r] ? fminf(kAlphaMax, araw[r]) : 0.f;
-                    const float ra = rcp_approx(1.f - alpha);          // 1 when !ok
-                    T[r] = ok[r] ? T[r] * ra : T[r];
-                    const float fac = alpha * T[r];                    // 0 when !ok
-                    float cv = col[0] * v_out[r][0];
+                    for (int ch = 1; ch < GCH; ++ch) cv = fma2(bcast2(col[ch]), vo2[P][ch], cv);
 #pragma unroll
-                    for (int ch = 1; ch < GCH; ++ch) cv = fmaf(col[ch], v_out[r][ch], cv);
-#pragma unroll
-                    for (int ch = 0; ch < GCH; ++ch) val[6 + ch] = fmaf(fac, v_out[r][ch], val[6 + ch]);
-                    const float v_alpha = fmaf(cv, T[r], Wacc[r] * ra);
-                    Wacc[r] = fmaf(-cv, fac, Wacc[r]);
+                    for (int ch = 0; ch < GCH; ++ch) vc[ch] = (P == 0) ? mul2(fac, vo2[P][ch]) : fma2(fac, vo2[P][ch], vc[ch]);
+                    const f32x2 v_alpha = fma2(cv, T2[P], mul2(W2[P], ra));
+                    W2[P] = fma2(neg2(cv), fac, W2[P]);
                     // !ok: no contribution;  clamped alpha: d alpha / d araw = 0
-                    const float v_sig = (ok[r] && !(araw[r] > kAlphaMax)) ? -araw[r] * v_alpha : 0.f;
-                    s0 += v_sig;
-                    s1 = fmaf(v_sig, dyr[r], s1);
-                    s2 = fmaf(v_sig * dyr[r], dyr[r], s2);
+                    const f32x2 ng = mul2(pack2((oka && !(ara > kAlphaMax)) ? ara : 0.f,
+                                                (okb && !(arb > kAlphaMax)) ? arb : 0.f), v_alpha);   // -v_sigma
+                    const f32x2 ngdy = mul2(ng, dy);
+                    n0 = (P == 0) ? ng : add2(n0, ng);
+                    n1 = (P == 0) ? ngdy : add2(n1, ngdy);
+                    n2 = (P == 0) ? mul2(ngdy, dy) : fma2(ngdy, dy, n2);
                 }
+                const float s0 = -hsum2(n0), s1 = -hsum2(n1), s2 = -hsum2(n2);
+#pragma unroll
+                for (int ch = 0; ch < GCH; ++ch) val[6 + ch] = hsum2(vc[ch]);
                 val[0] = s0 * dxc;
                 val[1] = s1;
                 val[2] = val[0] * dxc;
@@ -331,12 +362,25 @@ int launch_blend_bwd_group(int CH, int gch, int H, int W, int tiles_x, int tiles
 #undef TS_LAUNCH_BWD
     return 0;
 }
+
+// test hook: the device's approximate-math results the blend kernels build on
+__global__ void debug_approx_kernel(int n, const float* __restrict__ x, float* __restrict__ rcp, float* __restrict__ ex2) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { rcp[i] = rcp_approx(x[i]); ex2[i] = ex2_approx(x[i]); }
+}
 #endif  // !TS_HOST_EMU
 
 }  // namespace ts
 
 #ifndef TS_HOST_EMU
 extern "C" {
+
+int ts_debug_approx(int n, const float* x, float* rcp_out, float* ex2_out, ts_stream_t stream) {
+    if (n <= 0 || !x || !rcp_out || !ex2_out) return TS_ERR_INVALID;
+    ts::debug_approx_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(n, x, rcp_out, ex2_out);
+    TS_CHECK_LAUNCH("ts_debug_approx");
+    return TS_OK;
+}
 
 // Host-side evaluation of the exact row mask of one packed record against tile (tile_x, tile_y):
 // the same function the kernels run (test hook: tests/test_capi.py brute-forces it on CPU).

@@ -37,6 +37,12 @@ if [ "$NCU_LIST" = "1" ]; then
       --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-extras --sustained-s 0 \
       > gpurun_out/${TAG}_ncu_launches.log 2>&1
 fi
+if [ -n "${NCU_FULL:-}" ]; then   # e.g. NCU_FULL="blend_fwd_pair|blend_bwd_group": one --set full capture of the first launches
+  timeout 400 ncu --set full --clock-control none --import-source on -k "regex:$NCU_FULL" -s ${NCU_SKIP:-8} -c ${NCU_COUNT:-2} \
+      -f -o gpurun_out/${TAG}_full python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-extras --sustained-s 0 \
+      > gpurun_out/${TAG}_ncu_full.log 2>&1
+  ncu -i gpurun_out/${TAG}_full.ncu-rep --page details --csv > gpurun_out/${TAG}_full_details.csv 2>/dev/null
+fi
 for pipe in $TORCH_PROFILE; do
   timeout 120 python tools/torch_profile.py synthetic_1M_1080p $pipe > gpurun_out/${TAG}_torch_profile_$pipe.txt 2>&1
 done
