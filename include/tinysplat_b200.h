@@ -164,6 +164,10 @@ TS_API int ts_bin_emit(int N, const float* depths, const int32_t* radii,
                        int capacity, ts_stream_t stream);
 TS_API int ts_bin_reset_cursors(int num_tiles, const int32_t* tile_offsets, int32_t* cursors,
                                 ts_stream_t stream);
+/* tile_order[num_tiles]: a permutation of the tiles by descending list length (256 length classes),
+ * the launch order of the blend kernels (see ts_blend_fwd). */
+TS_API int ts_bin_tile_order(int num_tiles, const int32_t* tile_offsets, int32_t* tile_order,
+                             ts_stream_t stream);
 TS_API int ts_bin_sort(int num_tiles, const int32_t* tile_offsets, uint64_t* keys,
                        int32_t* ids_sorted, int max_count, int n_big_tiles,
                        uint64_t* big_scratch, int32_t* big_counter, int capacity,
@@ -187,19 +191,24 @@ TS_API int ts_bin_smem_sort_cap(void);
  *   cotangents in backward.
  * ts_blend_bwd: replays back to front; accumulates per-Gaussian packed gradients
  *   grads[N, ts_grad_floats()] (zeroed by the callee).  v_out_alpha may be NULL.
- * ts_blend_unpack_grads: packed -> v_xys[N,2], v_conics[N,3], v_colors[N,CH], v_opacity[N]. */
+ * ts_blend_unpack_grads: packed -> v_xys[N,2], v_conics[N,3], v_colors[N,CH], v_opacity[N].
+ * tile_order (both blend calls): ts_bin_tile_order's permutation — CTA i works on tile
+ *   tile_order[i], longest lists first, so the grid's tail is made of cheap tiles; NULL = raster
+ *   order.  The results do not depend on it. */
 TS_API int ts_blend_fwd(int CH, int img_height, int img_width, int tiles_x, int tiles_y,
                         const int32_t* tile_offsets, const int32_t* ids_sorted,
                         const float* recs /*[16B]*/, const float* background,
                         float* out_img, float* out_ch3 /*or NULL*/, float* final_T,
-                        int32_t* n_contrib, int clamp_max1, int capacity, ts_stream_t stream);
+                        int32_t* n_contrib, int clamp_max1, int capacity,
+                        const int32_t* tile_order /*or NULL*/, ts_stream_t stream);
 TS_API int ts_blend_bwd(int N, int CH, int img_height, int img_width, int tiles_x, int tiles_y,
                         const int32_t* tile_offsets, const int32_t* ids_sorted,
                         const float* recs /*[16B]*/, const float* background,
                         const float* final_T, const int32_t* n_contrib,
                         const float* v_out_img, const float* v_out_ch3 /*or NULL*/,
                         int split_ch3, const float* v_out_alpha /*or NULL*/,
-                        float* grads /*[16B]*/, ts_stream_t stream);
+                        float* grads /*[16B]*/, const int32_t* tile_order /*or NULL*/,
+                        ts_stream_t stream);
 TS_API int ts_blend_unpack_grads(int N, int CH, const int32_t* radii, const float* conics,
                                  const float* grads /*[16B]*/, float* v_xys, float* v_conics,
                                  float* v_colors, float* v_opacity, ts_stream_t stream);
@@ -212,11 +221,6 @@ TS_API int ts_blend_unpack_grads(int N, int CH, const int32_t* radii, const floa
  * launches. */
 TS_API int ts_set_blend_mode(int mode);
 TS_API int ts_get_blend_mode(void);
-/* Which kernel ts_blend_fwd launches: 0 = first generation (one pixel per lane), 1 = row pairs (two
- * pixels per lane, packed fp32; default), -1 = back to the TS_BLEND_FWD environment variable / default.
- * Both produce bit-identical images. */
-TS_API int ts_set_blend_fwd_mode(int mode);
-TS_API int ts_get_blend_fwd_mode(void);
 /* Test hook (host code, no GPU): the exact row mask the grouped backward computes for one packed
  * record (q0 = {x, y, hx, hy}, q1 = {A, B, C, opacity}, see ts_rec_floats) against tile
  * (tile_x, tile_y): bit (2*row + half) set = some pixel of tile row `row`, columns

@@ -1,5 +1,5 @@
 // Compiles EVERY hot-path kernel of tinysplat_b200/csrc (project.cu, sh.cu, binning.cu, blend.cu,
-// blend_pair.cu, blend_group.cu) unchanged as host code on the fiber SIMT emulator (ts_emu.h) and exposes
+// blend_group.cu) unchanged as host code on the fiber SIMT emulator (ts_emu.h) and exposes
 //   * the blend kernels and the binning stages with the argument lists of their C-ABI entry points
 //     (host pointers instead of device pointers; the launch logic mirrors those entry points), and
 //   * emu_render_fused: the whole fused forward + backward of tinysplat_b200/fused.py,
@@ -10,7 +10,6 @@
 #include "../../tinysplat_b200/csrc/sh.cu"
 #include "../../tinysplat_b200/csrc/binning.cu"
 #include "../../tinysplat_b200/csrc/blend.cu"
-#include "../../tinysplat_b200/csrc/blend_pair.cu"
 #include "../../tinysplat_b200/csrc/blend_group.cu"
 #include "../../tinysplat_b200/csrc/peer.cu"
 #include "../../tinysplat_b200/csrc/adam.cu"
@@ -21,41 +20,43 @@
 #include <climits>
 
 static int g_emu_key_cap = INT32_MAX;
-static int g_emu_fwd_pair = 1;      // which blend-forward generation emu_blend_fwd runs (1 = row pairs, the default)
+static const int32_t* g_emu_tile_order = nullptr;   // launch order of the blend kernels (nullptr = raster order)
 
 namespace {
 template <int CH>
 int run_fwd(int H, int W, int tx, int ty, const int32_t* off, const int32_t* ids, const float* recs,
             const float* bg, float* out_img, float* out_ch3, float* final_T, int32_t* n_contrib, int clamp) {
-    if (g_emu_fwd_pair)
-        return ts_emu::launch(dim3(tx, ty), ts::kPThreads, [=]() {
-            ts::blend_fwd_pair_kernel<CH>(H, W, tx, off, ids, (const float4*)recs, bg, out_img, out_ch3, final_T,
-                                          n_contrib, clamp, g_emu_key_cap);
-        });
-    return ts_emu::launch(dim3(tx, ty), ts::kBlendThreads, [=]() {
+    const int32_t* order = g_emu_tile_order;
+    return ts_emu::launch(dim3(tx * ty), ts::kBlendThreads, [=]() {
         ts::blend_fwd_kernel<CH>(H, W, tx, off, ids, (const float4*)recs, bg, out_img, out_ch3, final_T,
-                                 n_contrib, clamp, g_emu_key_cap);
+                                 n_contrib, clamp, g_emu_key_cap, order);
     });
 }
 template <int CH, int GCH>
 int run_bwd(int grouped, int H, int W, int tx, int ty, const int32_t* off, const int32_t* ids, const float* recs,
             const float* bg, const float* final_T, const int32_t* n_contrib, const float* v_img,
             const float* v_ch3, int split, const float* v_alpha, float* grads) {
+    const int32_t* order = g_emu_tile_order;
     if (grouped)
-        return ts_emu::launch(dim3(tx, ty), ts::kGThreads, [=]() {
+        return ts_emu::launch(dim3(tx * ty), ts::kGThreads, [=]() {
             ts::blend_bwd_group_kernel<CH, GCH>(H, W, tx, off, ids, (const float4*)recs, bg, final_T, n_contrib,
-                                                v_img, v_ch3, split, v_alpha, (float4*)grads);
+                                                v_img, v_ch3, split, v_alpha, (float4*)grads, order);
         });
-    return ts_emu::launch(dim3(tx, ty), ts::kBlendThreads, [=]() {
+    return ts_emu::launch(dim3(tx * ty), ts::kBlendThreads, [=]() {
         ts::blend_bwd_kernel<CH, GCH>(H, W, tx, off, ids, (const float4*)recs, bg, final_T, n_contrib,
-                                      v_img, v_ch3, split, v_alpha, (float4*)grads);
+                                      v_img, v_ch3, split, v_alpha, (float4*)grads, order);
     });
 }
 }  // namespace
 
 extern "C" {
 
-void emu_set_fwd_mode(int pair) { g_emu_fwd_pair = pair; }
+// the blend kernels launched after this call take their tiles in this order (nullptr: raster order)
+void emu_set_tile_order(const int32_t* order) { g_emu_tile_order = order; }
+
+int emu_bin_tile_order(int T, const int32_t* offsets, int32_t* order) {
+    return ts_emu::launch(dim3(1), ts::kOrderThreads, [=]() { ts::bin_tile_order_kernel(T, offsets, order); });
+}
 
 int emu_blend_fwd(int CH, int H, int W, int tx, int ty, const int32_t* off, const int32_t* ids,
                   const float* recs, const float* bg, float* out_img, float* out_ch3, float* final_T,
@@ -281,6 +282,14 @@ int emu_render_fused(int N, int K, int deg, int W, int H, const float* means, co
         rc = emu_bin_sort(T, offsets.data(), keys.data(), ids.data(), max_count, n_big, scratch.data(), &counter);
         if (rc) return rc;
     }
+    // launch order of the blend kernels, as tinysplat_b200/binning.py computes it
+    std::vector<int32_t> order(T, 0);
+    rc = emu_bin_tile_order(T, offsets.data(), order.data());
+    if (rc) return rc;
+    struct OrderScope {
+        explicit OrderScope(const int32_t* o) { g_emu_tile_order = o; }
+        ~OrderScope() { g_emu_tile_order = nullptr; }
+    } order_scope(order.data());
     // K4
     std::vector<int32_t> ncon((size_t)W * H, 0);
     rc = emu_blend_fwd(4, H, W, tx, ty, offsets.data(), ids.data(), recs_p, bg4, rgb, depth_img, final_T, ncon.data(),

@@ -30,8 +30,9 @@ def load():
     lib.emu_bin_scan.argtypes = [i, p, p, p, i]
     lib.emu_bin_emit.argtypes = [i, p, p, p, i, i, i, p, p]
     lib.emu_bin_sort.argtypes = [i, p, p, p, i, i, p, p]
-    lib.emu_set_fwd_mode.argtypes = [i]
-    lib.emu_set_fwd_mode.restype = None
+    lib.emu_set_tile_order.argtypes = [p]
+    lib.emu_set_tile_order.restype = None
+    lib.emu_bin_tile_order.argtypes = [i, p, p]
     lib.emu_set_key_capacity.argtypes = [i]
     lib.emu_set_key_capacity.restype = None
     lib.emu_bin_reset_cursors.argtypes = [i, p, p]

@@ -127,15 +127,20 @@ def test_blend_kernels_match_the_oracle_on_the_emulator(emu, n, W, H, radius, ch
     assert np.abs(out - img.detach().numpy()).max() < 2e-5
     assert np.abs((1.0 - final_T) - alpha.detach().numpy()).max() < 2e-5
     assert np.array_equal(ncon, aux["n_contrib"].numpy().astype(np.int32))
-    # the first-generation forward (one pixel per lane, scalar fp32) is bit-identical to the row-pair
-    # forward above: same operations in the same order, only issued as packed pairs
+    # launch order: longest tile lists first (ts_bin_tile_order) must give the same bits as raster order
+    T = tb[0] * tb[1]
+    order = np.full(T, -1, dtype=np.int32)
+    assert emu.emu_bin_tile_order(T, _ptr(offsets), _ptr(order)) == 0
+    assert np.array_equal(np.sort(order), np.arange(T))                      # a permutation
+    counts = np.diff(offsets)[order]
+    assert (np.diff(np.minimum(counts, 2047) // 8) <= 0).all()               # by descending length class
     out1, T1, nc1 = np.full_like(out, -7.0), np.full_like(final_T, -7.0), np.full_like(ncon, -7)
-    emu.emu_set_fwd_mode(0)
+    emu.emu_set_tile_order(_ptr(order))
     try:
         assert emu.emu_blend_fwd(ch, H, W, tb[0], tb[1], _ptr(offsets), _ptr(ids), _ptr(rec), _ptr(bgn), _ptr(out1),
                                  None, _ptr(T1), _ptr(nc1), 0) == 0
     finally:
-        emu.emu_set_fwd_mode(1)
+        emu.emu_set_tile_order(None)
     assert np.array_equal(out1, out) and np.array_equal(T1, final_T) and np.array_equal(nc1, ncon)
 
     g = torch.Generator().manual_seed(9)

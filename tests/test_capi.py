@@ -52,7 +52,7 @@ def test_invalid_arguments_are_rejected_before_any_cuda_call(lib):
                               N, N, N, N, N, N, N, 0, N, N, N) == -1
     assert lib.ts_sh_fwd(4, 5, 16, N, N, N, N, N, 3, N, N, 0, N) == -1        # degree > 4
     assert lib.ts_sh_fwd(4, 3, 9, N, N, N, N, N, 3, N, N, 0, N) == -1         # K too small
-    assert lib.ts_blend_fwd(7, 16, 16, 1, 1, N, N, N, N, N, N, N, N, 0, 0, N) == -1  # 7 channels
+    assert lib.ts_blend_fwd(7, 16, 16, 1, 1, N, N, N, N, N, N, N, N, 0, 0, N, N) == -1  # 7 channels
     assert lib.ts_bin_scan(0, N, N, N, 1, N) == -1
     # N == 0 is a valid no-op everywhere
     assert lib.ts_project_bwd(0, N, N, 1.0, N, N, N, 1.0, 1.0, 0.0, 0.0, 16, 16, 0,

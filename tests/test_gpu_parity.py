@@ -858,22 +858,26 @@ def test_device_approximations_the_blend_kernels_rely_on(lib):
 
 
 @pytest.mark.parametrize("ch", [1, 3, 4])
-def test_both_forward_generations_give_the_same_bits(lib, ch):
-    """Row-pair forward (default) vs the first-generation forward: image, final T and n_contrib must be
-    bit-identical (packed fp32 pairs round like the scalar instructions, same operation order)."""
+def test_tile_launch_order_does_not_change_the_result(lib, ch):
+    """The blend kernels take their tiles longest-list-first (ts_bin_tile_order); image, alpha and the
+    gradients must equal the raster-order launch (forward bit for bit, backward up to the order of the
+    float atomics)."""
     import gsplat
-    from tinysplat_b200 import rasterize as rz
+    from tinysplat_b200 import binning, rasterize as rz
     N, W, H = 30000, 500, 300
     xys, dep, rad, con, nt, colors, opac, bg = _raster_case(N, W, H, seed=5, CH=ch)
-    args = [t.to(DEV) for t in (xys, dep, rad, con, nt, colors, opac)]
     res = []
-    for mode in (1, 0):
-        assert lib.ts_set_blend_fwd_mode(mode) == 0
+    for use in (True, False):
+        binning.USE_TILE_ORDER = use
         try:
             rz.clear_bin_cache()
-            with torch.no_grad():
-                img, alpha = gsplat.rasterize_gaussians(*args, H, W, bg.to(DEV))
-            res.append((img.clone(), alpha.clone()))
+            leaves = [t.to(DEV).requires_grad_(True) for t in (xys, con, colors, opac)]
+            img, alpha = gsplat.rasterize_gaussians(leaves[0], dep.to(DEV), rad.to(DEV), leaves[1], nt.to(DEV),
+                                                    leaves[2], leaves[3], H, W, bg.to(DEV))
+            (img.square().sum() + alpha.sum()).backward()
+            res.append((img.detach(), alpha.detach(), [l.grad for l in leaves]))
         finally:
-            lib.ts_set_blend_fwd_mode(-1)
+            binning.USE_TILE_ORDER = True
     assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+    for a, b in zip(res[0][2], res[1][2]):
+        assert rel_err(a, b) < 1e-5

@@ -38,8 +38,9 @@ _SIGNATURES = {
     "ts_bin_smem_sort_cap": ([], C.c_int),
     "ts_bin_counter_stride": ([], C.c_int),
     "ts_bin_scan_work_ints": ([], C.c_int),
-    "ts_blend_fwd": ([_i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p], C.c_int),
-    "ts_blend_bwd": ([_i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p], C.c_int),
+    "ts_bin_tile_order": ([_i, _p, _p, _p], C.c_int),
+    "ts_blend_fwd": ([_i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p, _p], C.c_int),
+    "ts_blend_bwd": ([_i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p], C.c_int),
     "ts_ssim_fwd": ([_i, _i, _i, _i, _p, _p, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p], C.c_int),
     "ts_ssim_bwd": ([_i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p], C.c_int),
     "ts_knn_points": ([_i, _i, _i, _p, _p, _p, _p, _p], C.c_int),
@@ -65,8 +66,6 @@ _SIGNATURES = {
     "ts_peer_ipc_close": ([_p], C.c_int),
     "ts_set_blend_mode": ([_i], C.c_int),
     "ts_get_blend_mode": ([], C.c_int),
-    "ts_set_blend_fwd_mode": ([_i], C.c_int),
-    "ts_get_blend_fwd_mode": ([], C.c_int),
     "ts_debug_rowmask": ([_p, _p, _i, _i], C.c_uint32),
     "ts_debug_approx": ([_i, _p, _p, _p, _p], C.c_int),
 }

@@ -12,6 +12,7 @@ microseconds of queued work while the host runs ahead.  If the step did need mor
 """
 from __future__ import annotations
 
+import os
 from typing import Callable, Dict, Optional, Tuple
 
 import torch
@@ -24,6 +25,8 @@ _state: Dict[Tuple[int, int], list] = {}
 _pinned: Dict[int, list] = {}
 stats = {"speculative": 0, "exact_first": 0, "redone": 0}      # counters (tests, bench run_info)
 
+# A/B switch (bench only): TINYSPLAT_B200_TILE_ORDER=0 launches the blend kernels in raster order
+USE_TILE_ORDER = os.environ.get("TINYSPLAT_B200_TILE_ORDER", "1") != "0"
 HEADROOM = 1.25
 SLACK = 4096
 
@@ -46,8 +49,8 @@ class PendingBins:
     """Tile lists of one binning; `validate()` must be called (after the consumer kernel has been
     queued) before anything else trusts M — it reads the counts back and, if the speculative
     capacity was too small, rebuilds the lists exactly and asks the caller to run its consumer again."""
-    __slots__ = ("offsets", "ids_sorted", "keys", "M", "max_count", "capacity", "cap_arg", "_ev", "_redo", "_host",
-                 "_key")
+    __slots__ = ("offsets", "ids_sorted", "keys", "order", "M", "max_count", "capacity", "cap_arg", "_ev", "_redo",
+                 "_host", "_key")
 
     def __init__(self):
         self.M = None
@@ -115,6 +118,11 @@ def emit_and_sort(N: int, T: int, tx: int, ty: int, cull_mode: int, depths: Tens
         b.capacity, b.cap_arg = (M, max_count), 0
 
     bins._redo = redo
+    # launch order of the blend kernels (longest lists first); depends on the offsets only
+    bins.order = None
+    if USE_TILE_ORDER:
+        bins.order = torch.empty(T, **i32)
+        _lib.call("ts_bin_tile_order", T, _lib.ptr(offsets), _lib.ptr(bins.order), stream_ptr)
     st = _state.get(key)
     if st is None or st[2] > 0:
         # first binning of this (device, image size): nothing to extrapolate from — size exactly

@@ -435,6 +435,36 @@ bin_reset_cursors_kernel(int T, const int32_t* __restrict__ offsets, int32_t* __
     if (t < T) cursors[(size_t)t * kCounterStride] = offsets[t];
 }
 
+// ---- launch order of the blend kernels: tiles by descending list length ---------------------------
+// One CTA, counting sort on 256 length classes (class = min(n, 2047) / 8, longest first).  The blend
+// grids are a few waves of CTAs whose cost is proportional to the list length; in raster order the
+// last wave can hold long lists and the SMs that finish early idle (10 % of blend-backward's time at
+// 1M Gaussians / 1080p).  Longest first, the tail is made of the cheapest tiles.
+constexpr int kOrderThreads = 1024;
+constexpr int kOrderClasses = 256;
+__device__ __forceinline__ int order_class(int n) { return kOrderClasses - 1 - (min(n, 2047) >> 3); }
+
+__global__ void __launch_bounds__(kOrderThreads)
+bin_tile_order_kernel(int T, const int32_t* __restrict__ offsets, int32_t* __restrict__ order) {
+    __shared__ int s_hist[kOrderClasses];
+    __shared__ int s_base[kOrderClasses];
+    const int tid = threadIdx.x;
+    if (tid < kOrderClasses) s_hist[tid] = 0;
+    __syncthreads();
+    for (int t = tid; t < T; t += kOrderThreads)
+        atomicAdd(&s_hist[order_class(__ldg(offsets + t + 1) - __ldg(offsets + t))], 1);
+    __syncthreads();
+    if (tid == 0) {
+        int run = 0;
+        for (int c = 0; c < kOrderClasses; ++c) { s_base[c] = run; run += s_hist[c]; }
+    }
+    __syncthreads();
+    for (int t = tid; t < T; t += kOrderThreads) {
+        const int c = order_class(__ldg(offsets + t + 1) - __ldg(offsets + t));
+        order[atomicAdd(&s_base[c], 1)] = t;
+    }
+}
+
 }  // namespace ts
 
 #ifndef TS_HOST_EMU
@@ -508,6 +538,13 @@ int ts_bin_reset_cursors(int num_tiles, const int32_t* tile_offsets, int32_t* cu
     if (num_tiles <= 0 || !tile_offsets || !cursors) return TS_ERR_INVALID;
     ts::bin_reset_cursors_kernel<<<(num_tiles + ts::kBinThreads - 1) / ts::kBinThreads, ts::kBinThreads, 0, (cudaStream_t)stream>>>(num_tiles, tile_offsets, cursors);
     TS_CHECK_LAUNCH("ts_bin_reset_cursors");
+    return TS_OK;
+}
+
+int ts_bin_tile_order(int num_tiles, const int32_t* tile_offsets, int32_t* tile_order, ts_stream_t stream) {
+    if (num_tiles <= 0 || !tile_offsets || !tile_order) return TS_ERR_INVALID;
+    ts::bin_tile_order_kernel<<<1, ts::kOrderThreads, 0, (cudaStream_t)stream>>>(num_tiles, tile_offsets, tile_order);
+    TS_CHECK_LAUNCH("ts_bin_tile_order");
     return TS_OK;
 }
 

@@ -22,15 +22,8 @@
 
 namespace ts {
 
-#ifndef TS_BLEND_TMA_GATHER
-#define TS_BLEND_TMA_GATHER 0
-#endif
-// -DTS_FWD_LISTS=1 (compile-time experiment, unmeasured; checked on the emulator): blend-forward turns
-// its warp's eight candidate-mask words into a byte list of staged indices once per batch (one POPC
-// pair per word) and walks that list, instead of BREV + FLO + two ALU ops per candidate.  ncu shows
-// the XU pipe (MUFU.EX2, BREV, FLO, POPC) at 46 % in this kernel.
-#ifndef TS_FWD_LISTS
-#define TS_FWD_LISTS 0
+#ifndef TS_FWD_ROWMASK
+#define TS_FWD_ROWMASK 0
 #endif
 constexpr int kBlendThreads = 256;
 constexpr int kBatch = 256;
@@ -42,13 +35,13 @@ struct PixMap {
     float px, py;
 };
 
-__device__ __forceinline__ PixMap pix_map(int H, int W) {
+__device__ __forceinline__ PixMap pix_map(int H, int W, int bx, int by) {
     PixMap m;
     m.warp = threadIdx.x >> 5;
     m.lane = threadIdx.x & 31;
     int wx = m.warp & 1, wy = m.warp >> 1, lx = m.lane & 7, ly = m.lane >> 3;
-    m.j = blockIdx.x * kBlock + wx * 8 + lx;
-    m.i = blockIdx.y * kBlock + wy * 4 + ly;
+    m.j = bx * kBlock + wx * 8 + lx;
+    m.i = by * kBlock + wy * 4 + ly;
     m.inside = (m.i < H) && (m.j < W);
     m.px = (float)m.j + kPixCenter;
     m.py = (float)m.i + kPixCenter;
@@ -56,9 +49,9 @@ __device__ __forceinline__ PixMap pix_map(int H, int W) {
 }
 
 // 8-bit mask: which of the tile's 8 sub-blocks (8 wide x 4 tall) the footprint box can reach.
-__device__ __forceinline__ unsigned subblock_mask(float4 q0) {
-    const float X0 = (float)(blockIdx.x * kBlock) + kPixCenter;
-    const float Y0 = (float)(blockIdx.y * kBlock) + kPixCenter;
+__device__ __forceinline__ unsigned subblock_mask(float4 q0, int bx, int by) {
+    const float X0 = (float)(bx * kBlock) + kPixCenter;
+    const float Y0 = (float)(by * kBlock) + kPixCenter;
     float xl = q0.x - q0.z, xh = q0.x + q0.z, yl = q0.y - q0.w, yh = q0.y + q0.w;
     unsigned mx = 0, my = 0;
     // columns: sub-block wx covers pixel centres [X0+8wx, X0+8wx+7]
@@ -81,16 +74,19 @@ blend_fwd_kernel(int H, int W, int tbx, const int32_t* __restrict__ tile_offsets
                  const int32_t* __restrict__ ids, const float4* __restrict__ recs,
                  const float* __restrict__ background, float* __restrict__ out_img,
                  float* __restrict__ out_ch3, float* __restrict__ final_T,
-                 int32_t* __restrict__ n_contrib, int clamp_max1, int cap) {
+                 int32_t* __restrict__ n_contrib, int clamp_max1, int cap,
+                 const int32_t* __restrict__ order) {
     __shared__ __align__(16) float4 s_rec[2][kBatch * 3];
     __shared__ unsigned s_mask[8][8];  // [sub-block][staging warp]
-#if TS_FWD_LISTS
-    __shared__ unsigned char s_list[8][kBatch];   // [sub-block][i]: staged index of its i-th candidate
-#endif
+    // [sub-block][i]: staged index of the sub-block's i-th candidate.  The warp turns its eight mask words
+    // into this byte list once per batch (one POPC pair per word) and walks it, instead of BREV + FLO +
+    // two ALU operations per candidate (the XU pipe — MUFU.EX2, BREV, FLO, POPC — was at 46 %): -4 %
+    __shared__ unsigned char s_list[8][kBatch];
     const unsigned full = 0xffffffffu;
-    const PixMap pm = pix_map(H, W);
+    const TileId tl = tile_id(order, tbx);
+    const PixMap pm = pix_map(H, W, tl.bx, tl.by);
     const int tid = threadIdx.x;
-    const int tile = blockIdx.y * tbx + blockIdx.x;
+    const int tile = tl.tile;
     const int start = __ldg(tile_offsets + tile);
     // cap = capacity of the id list: when the host sized it from an earlier step and this step needs
     // more (ts_bin_emit), a list that does not fit was neither filled nor sorted: skip the tile — the
@@ -106,23 +102,8 @@ blend_fwd_kernel(int H, int W, int tbx, const int32_t* __restrict__ tile_offsets
     int ncon = 0;
     bool done = !pm.inside;
 
-#if TS_BLEND_TMA_GATHER
-    // experiment: one 48-byte TMA bulk copy per record, completion on a per-buffer mbarrier
-    __shared__ __align__(8) uint64_t s_bar[2];
-    if (tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); fence_proxy_async(); }
-    __syncthreads();
-    int pending = -1;
-#endif
     auto prefetch = [&](int b) {
         int p = b * kBatch + tid;
-#if TS_BLEND_TMA_GATHER
-        if (tid == 0) mbar_expect_tx(&s_bar[b & 1], 48u * (unsigned)min(kBatch, count - b * kBatch));
-        if (p < count) {
-            int g = __ldg(ids + start + p);
-            bulk_g2s(&s_rec[b & 1][tid * 3], recs + 3 * (size_t)g, 48u, &s_bar[b & 1]);
-        }
-        pending = b;
-#else
         if (p < count) {
             int g = __ldg(ids + start + p);
             const float4* src = recs + 3 * (size_t)g;
@@ -131,7 +112,6 @@ blend_fwd_kernel(int H, int W, int tbx, const int32_t* __restrict__ tile_offsets
             cp_async16(dst + 1, src + 1);
             cp_async16(dst + 2, src + 2);
         }
-#endif
     };
     if (nb > 0) prefetch(0);
     cp_async_commit();
@@ -139,15 +119,22 @@ blend_fwd_kernel(int H, int W, int tbx, const int32_t* __restrict__ tile_offsets
     for (int b = 0; b < nb; ++b) {
         const int buf = b & 1;
         if (b + 1 < nb) prefetch(b + 1);
-#if TS_BLEND_TMA_GATHER
-        mbar_wait(&s_bar[buf], (unsigned)(b >> 1) & 1u);
-        if (pending == b) pending = -1;
-#else
         cp_async_commit();
         cp_async_wait<1>();  // batch b (this thread's copies) has landed
-#endif
         unsigned mine = 0;
-        if (b * kBatch + tid < count) mine = subblock_mask(s_rec[buf][tid * 3]);
+#if TS_FWD_ROWMASK
+        // exact culling: the rows of each sub-block the ellipse {alpha >= 1/255} really reaches
+        // (footprint_rowmask, as blend-backward), instead of the bounding box of the footprint
+        if (b * kBatch + tid < count) {
+            const unsigned rm = footprint_rowmask(s_rec[buf][tid * 3], s_rec[buf][tid * 3 + 1],
+                                                  (float)(tl.bx * kBlock) + kPixCenter, (float)(tl.by * kBlock) + kPixCenter);
+#pragma unroll
+            for (int s = 0; s < 8; ++s)
+                if (rm & (0x55u << (8 * (s >> 1) + (s & 1)))) mine |= 1u << s;
+        }
+#else
+        if (b * kBatch + tid < count) mine = subblock_mask(s_rec[buf][tid * 3], tl.bx, tl.by);
+#endif
 #pragma unroll
         for (int s = 0; s < 8; ++s) {
             unsigned m = __ballot_sync(full, (mine >> s) & 1u);
@@ -155,7 +142,6 @@ blend_fwd_kernel(int H, int W, int tbx, const int32_t* __restrict__ tile_offsets
         }
         __syncthreads();  // records + masks of batch b visible to all
         bool warp_done = __all_sync(full, done);
-#if TS_FWD_LISTS
         if (!warp_done) {
             int nlist = 0;
 #pragma unroll
@@ -194,47 +180,10 @@ blend_fwd_kernel(int H, int W, int tbx, const int32_t* __restrict__ tile_offsets
               warp_done = __all_sync(full, done);
             }
         }
-#else
-        if (!warp_done) {
-            for (int k = 0; k < 8 && !warp_done; ++k) {
-                unsigned m = s_mask[pm.warp][k];
-                while (m) {
-                    int bit = __ffs(m) - 1;
-                    m &= m - 1;
-                    const int g = k * 32 + bit;
-                    const float4 q0 = s_rec[buf][g * 3];
-                    const float4 q1 = s_rec[buf][g * 3 + 1];
-                    float dx, dy;
-                    float pw = eval_power(q0, q1, pm.px, pm.py, dx, dy);
-                    float alpha = fminf(kAlphaMax, __fmul_rn(q1.w, ex2_approx(-pw)));
-                    if (!done && pw >= 0.f && alpha >= kAlphaMin) {
-                        float nT = T * (1.f - alpha);
-                        if (nT <= kTStop) {
-                            done = true;
-                        } else {
-                            const float4 q2 = s_rec[buf][g * 3 + 2];
-                            float wgt = alpha * T;
-                            acc[0] = fmaf(wgt, q2.x, acc[0]);
-                            if (CH > 1) acc[1] = fmaf(wgt, q2.y, acc[1]);
-                            if (CH > 2) acc[2] = fmaf(wgt, q2.z, acc[2]);
-                            if (CH > 3) acc[3] = fmaf(wgt, q2.w, acc[3]);
-                            T = nT;
-                            ncon = b * kBatch + g + 1;
-                        }
-                    }
-                }
-                warp_done = __all_sync(full, done);
-            }
-        }
-#endif
         // also guards reuse of s_rec[buf] / s_mask by the next iterations
         if (__syncthreads_and(warp_done)) break;
     }
-#if TS_BLEND_TMA_GATHER
-    if (pending >= 0) mbar_wait(&s_bar[pending & 1], (unsigned)(pending >> 1) & 1u);   // drain before exit
-#else
     cp_async_wait<0>();
-#endif
 
     if (pm.inside) {
         const size_t pix = (size_t)pm.i * W + pm.j;
@@ -279,7 +228,8 @@ blend_bwd_kernel(int H, int W, int tbx, const int32_t* __restrict__ tile_offsets
                  const float* __restrict__ background, const float* __restrict__ final_T,
                  const int32_t* __restrict__ n_contrib, const float* __restrict__ v_out_img,
                  const float* __restrict__ v_out_ch3, int split_ch3,
-                 const float* __restrict__ v_out_alpha, float4* __restrict__ grads) {
+                 const float* __restrict__ v_out_alpha, float4* __restrict__ grads,
+                 const int32_t* __restrict__ order) {
     TS_DYN_SMEM(unsigned char, s_raw, 16);
     float4* s_rec = reinterpret_cast<float4*>(s_raw);                         // [2][kBatch*3]
     float* s_acc = reinterpret_cast<float*>(s_rec + 2 * kBatch * 3);          // [kBatch*12]
@@ -289,9 +239,10 @@ blend_bwd_kernel(int H, int W, int tbx, const int32_t* __restrict__ tile_offsets
     int* s_slot = reinterpret_cast<int*>(s_mask + 64);                        // [8 warps][4]
     int* s_nmax = s_slot + 32;
     const unsigned full = 0xffffffffu;
-    const PixMap pm = pix_map(H, W);
+    const TileId tl = tile_id(order, tbx);
+    const PixMap pm = pix_map(H, W, tl.bx, tl.by);
     const int tid = threadIdx.x;
-    const int tile = blockIdx.y * tbx + blockIdx.x;
+    const int tile = tl.tile;
     const int start = __ldg(tile_offsets + tile);
 
     float T_final = 1.f, v_oa = 0.f;
@@ -367,7 +318,7 @@ blend_bwd_kernel(int H, int W, int tbx, const int32_t* __restrict__ tile_offsets
         const int pbase = nmax - 1 - b * kBatch;
         const int my_p = pbase - tid;
         unsigned mine = 0;
-        if (my_p >= 0) mine = subblock_mask(rec[tid * 3]);
+        if (my_p >= 0) mine = subblock_mask(rec[tid * 3], tl.bx, tl.by);
 #pragma unroll
         for (int s = 0; s < 8; ++s) {
             unsigned m = __ballot_sync(full, (mine >> s) & 1u);
@@ -527,25 +478,7 @@ int launch_blend_bwd_group(int CH, int gch, int H, int W, int tiles_x, int tiles
                            const int32_t* tile_offsets, const int32_t* ids, const float* recs,
                            const float* background, const float* final_T, const int32_t* n_contrib,
                            const float* v_out_img, const float* v_out_ch3, int split_ch3,
-                           const float* v_out_alpha, float* grads, cudaStream_t st);
-
-// row-pair forward (blend_pair.cu)
-int launch_blend_fwd_pair(int CH, int H, int W, int tiles_x, int tiles_y, const int32_t* tile_offsets,
-                          const int32_t* ids, const float* recs, const float* background, float* out_img,
-                          float* out_ch3, float* final_T, int32_t* n_contrib, int clamp_max1, int cap,
-                          cudaStream_t st);
-
-// Which forward kernel ts_blend_fwd launches: 0 = first generation (blend_fwd_kernel, one pixel per
-// lane), 1 = row pairs (blend_pair.cu; default).  TS_BLEND_FWD ("warp" | "pair"), ts_set_blend_fwd_mode().
-static int g_blend_fwd_mode = -1;
-static int blend_fwd_mode() {
-    if (g_blend_fwd_mode < 0) {
-        const char* e = getenv("TS_BLEND_FWD");
-        if (e && !strcmp(e, "warp")) g_blend_fwd_mode = 0;
-        else g_blend_fwd_mode = 1;
-    }
-    return g_blend_fwd_mode;
-}
+                           const float* v_out_alpha, float* grads, const int32_t* order, cudaStream_t st);
 
 // Which backward kernel ts_blend_bwd launches: 0 = first generation (blend_bwd_kernel, one warp
 // per sub-block), 1 = grouped (blend_group.cu; default).  Initialised once from TS_BLEND_MODE
@@ -573,31 +506,20 @@ int ts_set_blend_mode(int mode) {
     return TS_OK;
 }
 int ts_get_blend_mode(void) { return ts::blend_mode(); }
-int ts_set_blend_fwd_mode(int mode) {
-    if (mode < -1 || mode > 1) return TS_ERR_INVALID;
-    ts::g_blend_fwd_mode = mode;  // -1: back to TS_BLEND_FWD / the built-in default
-    return TS_OK;
-}
-int ts_get_blend_fwd_mode(void) { return ts::blend_fwd_mode(); }
 
 int ts_blend_fwd(int CH, int img_height, int img_width, int tiles_x, int tiles_y,
                  const int32_t* tile_offsets, const int32_t* ids_sorted, const float* recs,
                  const float* background, float* out_img, float* out_ch3, float* final_T,
-                 int32_t* n_contrib, int clamp_max1, int capacity, ts_stream_t stream) {
+                 int32_t* n_contrib, int clamp_max1, int capacity, const int32_t* tile_order,
+                 ts_stream_t stream) {
     if (CH < 1 || CH > 4 || img_height <= 0 || img_width <= 0 || tiles_x <= 0 || tiles_y <= 0) return TS_ERR_INVALID;
     if (!tile_offsets || !background || !out_img || !final_T || !n_contrib) return TS_ERR_INVALID;
     if (recs && !ts::aligned16(recs)) return TS_ERR_ALIGN;
-    dim3 grid(tiles_x, tiles_y);
+    dim3 grid(tiles_x * tiles_y);
     cudaStream_t st = (cudaStream_t)stream;
     const int cap = capacity > 0 ? capacity : INT32_MAX;
-    if (ts::blend_fwd_mode() == 1) {
-        ts::launch_blend_fwd_pair(CH, img_height, img_width, tiles_x, tiles_y, tile_offsets, ids_sorted, recs,
-                                  background, out_img, out_ch3, final_T, n_contrib, clamp_max1, cap, st);
-        TS_CHECK_LAUNCH("ts_blend_fwd/pair");
-        return TS_OK;
-    }
 #define TS_LAUNCH_FWD(C) \
-    ts::blend_fwd_kernel<C><<<grid, ts::kBlendThreads, 0, st>>>(img_height, img_width, tiles_x, tile_offsets, ids_sorted, (const float4*)recs, background, out_img, out_ch3, final_T, n_contrib, clamp_max1, cap)
+    ts::blend_fwd_kernel<C><<<grid, ts::kBlendThreads, 0, st>>>(img_height, img_width, tiles_x, tile_offsets, ids_sorted, (const float4*)recs, background, out_img, out_ch3, final_T, n_contrib, clamp_max1, cap, tile_order)
     switch (CH) {
         case 1: TS_LAUNCH_FWD(1); break;
         case 2: TS_LAUNCH_FWD(2); break;
@@ -613,7 +535,7 @@ int ts_blend_bwd(int N, int CH, int img_height, int img_width, int tiles_x, int 
                  const int32_t* tile_offsets, const int32_t* ids_sorted, const float* recs,
                  const float* background, const float* final_T, const int32_t* n_contrib,
                  const float* v_out_img, const float* v_out_ch3, int split_ch3,
-                 const float* v_out_alpha, float* grads, ts_stream_t stream) {
+                 const float* v_out_alpha, float* grads, const int32_t* tile_order, ts_stream_t stream) {
     if (N < 0 || CH < 1 || CH > 4 || img_height <= 0 || img_width <= 0 || tiles_x <= 0 || tiles_y <= 0) return TS_ERR_INVALID;
     if (N == 0) return TS_OK;
     if (!tile_offsets || !background || !final_T || !n_contrib || !grads) return TS_ERR_INVALID;
@@ -621,13 +543,13 @@ int ts_blend_bwd(int N, int CH, int img_height, int img_width, int tiles_x, int 
     if (!ts::aligned16(grads) || (recs && !ts::aligned16(recs))) return TS_ERR_ALIGN;
     cudaStream_t st = (cudaStream_t)stream;
     TS_CHECK_CUDA(cudaMemsetAsync(grads, 0, sizeof(float) * ts::kGradFloats * (size_t)N, st), "ts_blend_bwd/memset");
-    dim3 grid(tiles_x, tiles_y);
+    dim3 grid(tiles_x * tiles_y);
     // channels that carry a cotangent: the fused RGB+depth pass without a depth loss skips ch 3
     const int gch = (CH == 4 && split_ch3 && !v_out_ch3) ? 3 : CH;
     if (ts::blend_mode() == 1) {
         ts::launch_blend_bwd_group(CH, gch, img_height, img_width, tiles_x, tiles_y, tile_offsets, ids_sorted,
                                    recs, background, final_T, n_contrib, v_out_img, v_out_ch3, split_ch3,
-                                   v_out_alpha, grads, st);
+                                   v_out_alpha, grads, tile_order, st);
         TS_CHECK_LAUNCH("ts_blend_bwd/group");
         return TS_OK;
     }
@@ -639,7 +561,7 @@ int ts_blend_bwd(int N, int CH, int img_height, int img_width, int tiles_x, int 
                                            (int)ts::kBwdSmemBytes), "ts_blend_bwd/attr");                \
         ts::blend_bwd_kernel<C, G><<<grid, ts::kBlendThreads, ts::kBwdSmemBytes, st>>>(                  \
             img_height, img_width, tiles_x, tile_offsets, ids_sorted, (const float4*)recs, background,   \
-            final_T, n_contrib, v_out_img, v_out_ch3, split_ch3, v_out_alpha, (float4*)grads);           \
+            final_T, n_contrib, v_out_img, v_out_ch3, split_ch3, v_out_alpha, (float4*)grads, tile_order); \
     } while (0)
     switch (CH) {
         case 1: TS_LAUNCH_BWD(1, 1); break;

@@ -43,7 +43,7 @@ struct GroupMap {
     float X0, Y0;       // pixel centre of the tile's first pixel
 };
 
-__device__ __forceinline__ GroupMap group_map(int H, int W) {
+__device__ __forceinline__ GroupMap group_map(int H, int W, int bx, int by) {
     GroupMap m;
     const int tid = threadIdx.x;
     m.lane = tid & 31;
@@ -52,16 +52,16 @@ __device__ __forceinline__ GroupMap group_map(int H, int W) {
     m.l8 = tid & 7;
     const int wx = m.grp & 1, wy = m.grp >> 1;
     m.shift = 8 * wy + wx;               // rowmask bit of (row 4wy + r, half wx) = shift + 2r
-    m.j = blockIdx.x * kBlock + wx * 8 + m.l8;
-    m.i0 = blockIdx.y * kBlock + wy * 4;
+    m.j = bx * kBlock + wx * 8 + m.l8;
+    m.i0 = by * kBlock + wy * 4;
     m.px = (float)m.j + kPixCenter;
     m.py0 = (float)m.i0 + kPixCenter;
     m.inside = 0u;
 #pragma unroll
     for (int r = 0; r < 4; ++r)
         if (m.j < W && m.i0 + r < H) m.inside |= 1u << r;
-    m.X0 = (float)(blockIdx.x * kBlock) + kPixCenter;
-    m.Y0 = (float)(blockIdx.y * kBlock) + kPixCenter;
+    m.X0 = (float)(bx * kBlock) + kPixCenter;
+    m.Y0 = (float)(by * kBlock) + kPixCenter;
     return m;
 }
 
@@ -131,17 +131,17 @@ __device__ __forceinline__ float4 group_reduce_quad(const float (&val)[NV], int 
 
 // GCH = number of colour channels that carry a cotangent (GCH <= CH; the fused RGB+depth pass
 // with no depth loss has CH = 4, GCH = 3 and skips all channel-3 gradient arithmetic).
-#ifndef TS_GROUP_MIN_CTAS
-#define TS_GROUP_MIN_CTAS 1
-#endif
+// 16 CTAs per SM = a 64-register budget (measured: the packed-pair loop compiles to 72 registers without
+// the bound and is 6 % slower at the lower occupancy)
 template <int CH, int GCH>
-__global__ void __launch_bounds__(kGThreads, TS_GROUP_MIN_CTAS)
+__global__ void __launch_bounds__(kGThreads, 16)
 blend_bwd_group_kernel(int H, int W, int tbx, const int32_t* __restrict__ tile_offsets,
                        const int32_t* __restrict__ ids, const float4* __restrict__ recs,
                        const float* __restrict__ background, const float* __restrict__ final_T,
                        const int32_t* __restrict__ n_contrib, const float* __restrict__ v_out_img,
                        const float* __restrict__ v_out_ch3, int split_ch3,
-                       const float* __restrict__ v_out_alpha, float4* __restrict__ grads) {
+                       const float* __restrict__ v_out_alpha, float4* __restrict__ grads,
+                       const int32_t* __restrict__ order) {
     constexpr int NV = 6 + GCH;    // values reduced per (sub-block, Gaussian) pair
     __shared__ __align__(16) float4 s_rec[2][kGBatch * 3];
     __shared__ int s_gid[2 * kGBatch];                             // gaussian ids of the staged records
@@ -149,9 +149,10 @@ blend_bwd_group_kernel(int H, int W, int tbx, const int32_t* __restrict__ tile_o
     __shared__ unsigned s_cmask[8 * kGWords];
     __shared__ int s_nmax;
     const unsigned full = 0xffffffffu;
-    const GroupMap gm = group_map(H, W);
+    const TileId tl = tile_id(order, tbx);
+    const GroupMap gm = group_map(H, W, tl.bx, tl.by);
     const int tid = threadIdx.x;
-    const int tile = blockIdx.y * tbx + blockIdx.x;
+    const int tile = tl.tile;
     const int start = __ldg(tile_offsets + tile);
     const unsigned gbits = 0xffu << (gm.lane & 24);      // the lanes of my group
 
@@ -345,12 +346,12 @@ int launch_blend_bwd_group(int CH, int gch, int H, int W, int tiles_x, int tiles
                            const int32_t* tile_offsets, const int32_t* ids, const float* recs,
                            const float* background, const float* final_T, const int32_t* n_contrib,
                            const float* v_out_img, const float* v_out_ch3, int split_ch3,
-                           const float* v_out_alpha, float* grads, cudaStream_t st) {
-    dim3 grid(tiles_x, tiles_y);
+                           const float* v_out_alpha, float* grads, const int32_t* order, cudaStream_t st) {
+    dim3 grid(tiles_x * tiles_y);
 #define TS_LAUNCH_BWD(C, G)                                                                        \
     blend_bwd_group_kernel<C, G><<<grid, kGThreads, 0, st>>>(                                      \
         H, W, tiles_x, tile_offsets, ids, (const float4*)recs, background, final_T, n_contrib,     \
-        v_out_img, v_out_ch3, split_ch3, v_out_alpha, (float4*)grads)
+        v_out_img, v_out_ch3, split_ch3, v_out_alpha, (float4*)grads, order)
     switch (CH) {
         case 1: TS_LAUNCH_BWD(1, 1); break;
         case 2: TS_LAUNCH_BWD(2, 2); break;

@@ -5,6 +5,19 @@
 
 namespace ts {
 
+// Which tile a CTA works on.  The blend kernels run on a 1-D grid of T CTAs; `order` (ts_bin_tile_order:
+// tiles by descending list length) makes the CTAs that start first take the longest lists, so the
+// grid's tail consists of the cheapest tiles instead of whichever tiles the raster order put last.
+// order == nullptr: CTA i works on tile i.
+struct TileId { int tile, bx, by; };
+__device__ __forceinline__ TileId tile_id(const int32_t* __restrict__ order, int tbx) {
+    TileId t;
+    t.tile = order ? __ldg(order + blockIdx.x) : (int)blockIdx.x;
+    t.by = t.tile / tbx;
+    t.bx = t.tile - t.by * tbx;
+    return t;
+}
+
 constexpr int kClampShift = 28;                      // n_contrib bits 28..30: clamped-channel mask
 constexpr int kCountMask = (1 << kClampShift) - 1;
 

@@ -14,7 +14,6 @@ the read happens after the blend kernel has been queued (tinysplat_b200/binning.
 """
 from __future__ import annotations
 
-import os
 import weakref
 from typing import Tuple
 
@@ -29,13 +28,6 @@ from . import rasterize as _rz
 BLOCK = 16
 _side_streams = {}
 USE_SIDE_STREAM = True     # SH kernels on a second stream, overlapping binning / projection-backward
-# Experiment for the next GPU session (off by default, unmeasured): run SH-BACKWARD on a
-# high-priority stream.  At equal priority projection-backward (74 registers, 3 CTAs fill an SM's
-# register file) reaches the SMs first and leaves room for one SH CTA, so the pair takes the sum of
-# its parts (91 us); with priority the DRAM-bound SH grid (32 registers) gets its slots as they free
-# up and one projection CTA still fits beside it.  TINYSPLAT_B200_SH_BWD_PRIORITY=1 enables it.
-SH_BWD_HIGH_PRIORITY = os.environ.get("TINYSPLAT_B200_SH_BWD_PRIORITY", "0") == "1"
-_prio_streams = {}
 last_bins = None           # (tile_offsets, ids_sorted, M) of the most recent fused forward
 
 
@@ -44,15 +36,6 @@ def _side_stream(dev) -> "torch.cuda.Stream":
     if key not in _side_streams:
         _side_streams[key] = torch.cuda.Stream(device=dev)
     return _side_streams[key]
-
-
-def _sh_bwd_stream(dev) -> "torch.cuda.Stream":
-    if not SH_BWD_HIGH_PRIORITY:
-        return _side_stream(dev)
-    key = str(dev)
-    if key not in _prio_streams:
-        _prio_streams[key] = torch.cuda.Stream(device=dev, priority=-1)
-    return _prio_streams[key]
 
 
 class XysSink:
@@ -147,7 +130,7 @@ class _RenderFused(Function):
         def blend():
             _lib.call("ts_blend_fwd", 4, H, W, tx, ty, _lib.ptr(offsets), _lib.ptr(bins.ids_sorted), _lib.ptr(recs),
                       _lib.ptr(bg_c), _lib.ptr(rgb), _lib.ptr(depth_img), _lib.ptr(final_T), _lib.ptr(n_contrib),
-                      1 if clamp_rgb else 0, bins.cap_arg, st)
+                      1 if clamp_rgb else 0, bins.cap_arg, _lib.ptr(bins.order), st)
         blend()
         bins.validate(blend)                # exact lists + a second blend if the capacity was too small
         ids_sorted = bins.ids_sorted
@@ -156,6 +139,7 @@ class _RenderFused(Function):
         last_bins = (offsets, ids_sorted, bins.M)      # inspection hook (parity tests read the tile lists)
         ctx.save_for_backward(means_c, scales_c, quats_c, logit_c, view_c, proj_c, bg_c, radii, recs,
                               offsets, ids_sorted, final_T, n_contrib, mask)
+        ctx.tile_order = bins.order
         ctx.meta = (N, K, W, H, tx, ty, float(fx), float(fy), int(sh_degree), pflags, sflags,
                     tuple(opac_logits.shape), tuple(colors_dc.shape))
         ctx.sink = sink
@@ -195,7 +179,7 @@ class _RenderFused(Function):
             grads = torch.empty(n_rows, lib.ts_grad_floats(), **f32)
         _lib.call("ts_blend_bwd", N, 4, H, W, tx, ty, _lib.ptr(offsets), _lib.ptr(ids_sorted), _lib.ptr(recs),
                   _lib.ptr(bg_c), _lib.ptr(final_T), _lib.ptr(n_contrib), _lib.ptr(v_rgb), _lib.ptr(v_depth), 1,
-                  _lib.ptr(v_alpha), _lib.ptr(grads), st)
+                  _lib.ptr(v_alpha), _lib.ptr(grads), _lib.ptr(ctx.tile_order), st)
         if peer:
             return _RenderFused._backward_peer_exchange(ctx, grads, st)
         if dp is not None:
@@ -217,7 +201,7 @@ class _RenderFused(Function):
         # SH-backward (DRAM-bound) on the side stream, concurrent with projection-backward
         # (issue-bound); both only read the packed gradients
         main = torch.cuda.current_stream(dev)
-        side = _sh_bwd_stream(dev) if USE_SIDE_STREAM else main
+        side = _side_stream(dev) if USE_SIDE_STREAM else main
         if side is not main:
             side.wait_stream(main)
         with torch.cuda.stream(side):

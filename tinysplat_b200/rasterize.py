@@ -140,7 +140,7 @@ class _RasterizeGaussians(Function):
             _lib.call("ts_blend_fwd", CH, H, W, tx, ty, _lib.ptr(bins.tile_offsets),
                       _lib.ptr(pending.ids_sorted), _lib.ptr(recs), _lib.ptr(bg),
                       _lib.ptr(out_img), None, _lib.ptr(final_T), _lib.ptr(n_contrib), 0,
-                      pending.cap_arg, _lib.stream_ptr(dev))
+                      pending.cap_arg, _lib.ptr(pending.order), _lib.stream_ptr(dev))
         blend()
         pending.validate(blend)         # exact lists + a second blend if the guessed capacity was short
         last_stats.update(num_intersects=pending.M, max_per_tile=pending.max_count)
@@ -148,6 +148,7 @@ class _RasterizeGaussians(Function):
         ctx.save_for_backward(recs, bins.tile_offsets, bins.ids_sorted, bg, final_T, n_contrib,
                               radii_c, conics_c)
         ctx.meta = (N, CH, H, W, tx, ty, tuple(opacity.shape))
+        ctx.tile_order = pending.order
         return out_img, out_alpha
 
     @staticmethod
@@ -164,7 +165,7 @@ class _RasterizeGaussians(Function):
         _lib.call("ts_blend_bwd", N, CH, H, W, tx, ty, _lib.ptr(offsets), _lib.ptr(ids_sorted),
                                     _lib.ptr(recs), _lib.ptr(bg), _lib.ptr(final_T),
                                     _lib.ptr(n_contrib), _lib.ptr(v_img), None, 0, _lib.ptr(v_alpha),
-                  _lib.ptr(grads), st)
+                  _lib.ptr(grads), _lib.ptr(ctx.tile_order), st)
         v_xys = torch.empty(N, 2, device=dev, dtype=torch.float32)
         v_conics = torch.empty(N, 3, device=dev, dtype=torch.float32)
         v_colors = torch.empty(N, CH, device=dev, dtype=torch.float32)
