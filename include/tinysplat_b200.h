@@ -276,8 +276,11 @@ TS_API int ts_sh_bwd_views(int n_views, int N, int degree, int K, const float* m
  *   - this view's camera row (32 floats, layout as `cams` above) to every rank: cams[r][rank]
  *   and writes this view's d loss / d xy (v_xys, may be NULL).  shard_rows and padded_rows
  *   (= world * shard_rows) are multiples of 4.
- * ts_peer_barrier: all-to-all barrier through release/acquire flags in peer memory (slot 0 or 1;
- *   `epoch` must increase by one per use of a slot; flags = [2][8][32] uint32, ts_peer_flag_bytes()).
+ * ts_peer_barrier: all-to-all barrier through release/acquire flags in peer memory (slot <
+ *   ts_peer_barrier_slots(); `epoch` must increase per use of a slot; flags = [slots][8][32] uint32,
+ *   ts_peer_flag_bytes()).  mode 1 = signal only (everything this stream did before is visible to a
+ *   rank that later waits), 2 = wait only (until every rank has signalled `epoch`), 3 = both.  Signal
+ *   and wait may be queued on different streams: a stream that only pushes never blocks on a peer.
  *   A rank that waits longer than timeout_s writes 1 + the missing rank into *err_flag and goes on.
  * ts_sh_bwd_views_rgb: ts_sh_bwd_views reading 12-byte colour rows (rgb[v][i]) instead of packed rows.
  * ts_project_bwd_views_peer: ts_project_bwd_views reading the 32-byte geometry rows and storing the
@@ -297,7 +300,8 @@ TS_API int ts_dp_push(int N, int shard_rows, int padded_rows, int world, int ran
                       void* const* rgb_ptrs_host, void* const* cam_ptrs_host, float* v_xys /*or NULL*/,
                       ts_stream_t stream);
 TS_API int ts_peer_barrier(int world, int rank, void* const* flag_ptrs_host, int slot, uint32_t epoch,
-                           uint32_t* err_flag, double timeout_s, ts_stream_t stream);
+                           uint32_t* err_flag, double timeout_s, int mode, ts_stream_t stream);
+TS_API int ts_peer_barrier_slots(void);
 TS_API int ts_sh_bwd_views_rgb(int n_views, int N, int degree, int K, const float* means,
                                const float* cams, const float* rgb_rows /*[16B]*/,
                                int64_t view_stride_floats, float out_scale, float* v_dc, float* v_rest,

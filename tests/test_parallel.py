@@ -141,7 +141,7 @@ def test_peer_layout_segments_are_aligned_and_shards_cover_all_rows():
             spans = sorted(L.seg.values())
             for (o, n), (o2, _) in zip(spans, spans[1:] + [(L.total_bytes, 0)]):
                 assert o % 256 == 0 and o + n <= o2
-            assert L.seg["geo"][1] == world * L.cap_shard * 32
+            assert L.seg["geo"][1] == world * (L.cap_shard + L.MAX_CHUNKS * L.SHARD_ALIGN) * 32
             assert L.seg["rgb"][1] == world * world * L.cap_shard * 12
             for name in ("rest", "dc", "means", "scales", "quats", "logit"):
                 assert L.seg["g_" + name][1] >= cap * L.width(name) * 4
@@ -155,3 +155,19 @@ def test_peer_layout_segments_are_aligned_and_shards_cover_all_rows():
                         assert s0 == covered
                     covered += ns
                 assert covered == n
+                # the same rows pushed in pieces (PeerLayout.chunks): contiguous pieces that cover [0, n),
+                # every piece sharded on its own in 256-row multiples, the pieces' geometry blocks
+                # disjoint and inside the geo segment
+                for k in (1, 3, 4, 8, 50):
+                    pieces = L.chunks(n, k)
+                    assert 1 <= len(pieces) <= min(k, L.MAX_CHUNKS)
+                    row, geo_rows = 0, 0
+                    for r0, rows, ns_c, g0 in pieces:
+                        assert r0 == row and rows > 0 and r0 % (world * 256) == 0
+                        assert ns_c % 256 == 0 and ns_c * world >= rows and g0 == geo_rows
+                        mine = sum(max(0, min(rows, (r + 1) * ns_c) - r * ns_c) for r in range(world))
+                        assert mine == rows
+                        row += rows
+                        geo_rows += ns_c
+                    assert row == n
+                    assert world * geo_rows * 32 <= L.seg["geo"][1]

@@ -78,10 +78,16 @@ class PendingBins:
         return True
 
 
+_order_streams: Dict[int, "torch.cuda.Stream"] = {}
+
+
 def emit_and_sort(N: int, T: int, tx: int, ty: int, cull_mode: int, depths: Tensor, radii: Tensor,
-                  recs: Tensor, offsets: Tensor, counts: Tensor, scan_stats: Tensor, stream_ptr: int) -> PendingBins:
+                  recs: Tensor, offsets: Tensor, counts: Tensor, scan_stats: Tensor, stream_ptr: int,
+                  order_stream=None) -> PendingBins:
     """Launches ts_bin_emit + ts_bin_sort for the scanned tile counts.  `counts` holds the emit cursors
-    (ts_bin_scan turned the counters into cursors), `scan_stats` the scan's device-side statistics."""
+    (ts_bin_scan turned the counters into cursors), `scan_stats` the scan's device-side statistics.
+    The blend kernels' launch order (ts_bin_tile_order, one small CTA) runs beside emit / sort on
+    `order_stream` (default: a stream of this module); the caller's stream is made to wait for it."""
     lib = _lib.load()
     dev = depths.device
     main = torch.cuda.current_stream(dev)
@@ -120,9 +126,18 @@ def emit_and_sort(N: int, T: int, tx: int, ty: int, cull_mode: int, depths: Tens
     bins._redo = redo
     # launch order of the blend kernels (longest lists first); depends on the offsets only
     bins.order = None
+    order_done = None
     if USE_TILE_ORDER:
         bins.order = torch.empty(T, **i32)
-        _lib.call("ts_bin_tile_order", T, _lib.ptr(offsets), _lib.ptr(bins.order), stream_ptr)
+        if order_stream is None:
+            order_stream = _order_streams.get(key[0])
+            if order_stream is None:
+                order_stream = _order_streams[key[0]] = torch.cuda.Stream(device=dev)
+        order_stream.wait_event(ev)            # the scan has produced the offsets
+        _lib.call("ts_bin_tile_order", T, _lib.ptr(offsets), _lib.ptr(bins.order), order_stream.cuda_stream)
+        bins.order.record_stream(order_stream)
+        order_done = torch.cuda.Event()
+        order_done.record(order_stream)
     st = _state.get(key)
     if st is None or st[2] > 0:
         # first binning of this (device, image size): nothing to extrapolate from — size exactly
@@ -135,9 +150,13 @@ def emit_and_sort(N: int, T: int, tx: int, ty: int, cull_mode: int, depths: Tens
         launch(bins, M, max_count, n_big, True)
         prev = st or [0, 0, 0]
         _state[key] = [max(prev[0], int(M * HEADROOM) + SLACK), max(prev[1], int(max_count * HEADROOM) + 1), n_big]
+        if order_done is not None:
+            main.wait_event(order_done)
         return bins
     stats["speculative"] += 1
     bins._ev = ev
     bins.capacity, bins.cap_arg = (st[0], st[1]), st[0]      # cap_arg: what ts_blend_fwd must be told (0 = exact)
     launch(bins, st[0], st[1], 0, False)
+    if order_done is not None:
+        main.wait_event(order_done)
     return bins

@@ -22,9 +22,6 @@
 
 namespace ts {
 
-#ifndef TS_FWD_ROWMASK
-#define TS_FWD_ROWMASK 0
-#endif
 constexpr int kBlendThreads = 256;
 constexpr int kBatch = 256;
 
@@ -122,19 +119,7 @@ blend_fwd_kernel(int H, int W, int tbx, const int32_t* __restrict__ tile_offsets
         cp_async_commit();
         cp_async_wait<1>();  // batch b (this thread's copies) has landed
         unsigned mine = 0;
-#if TS_FWD_ROWMASK
-        // exact culling: the rows of each sub-block the ellipse {alpha >= 1/255} really reaches
-        // (footprint_rowmask, as blend-backward), instead of the bounding box of the footprint
-        if (b * kBatch + tid < count) {
-            const unsigned rm = footprint_rowmask(s_rec[buf][tid * 3], s_rec[buf][tid * 3 + 1],
-                                                  (float)(tl.bx * kBlock) + kPixCenter, (float)(tl.by * kBlock) + kPixCenter);
-#pragma unroll
-            for (int s = 0; s < 8; ++s)
-                if (rm & (0x55u << (8 * (s >> 1) + (s & 1)))) mine |= 1u << s;
-        }
-#else
         if (b * kBatch + tid < count) mine = subblock_mask(s_rec[buf][tid * 3], tl.bx, tl.by);
-#endif
 #pragma unroll
         for (int s = 0; s < 8; ++s) {
             unsigned m = __ballot_sync(full, (mine >> s) & 1u);

@@ -113,14 +113,20 @@ dp_push_kernel(int N, int Ns, int Npad, int world, int rank, const int32_t* __re
 }
 
 // Flags live one per 128-byte line: flags[slot][source rank][32 words].
+// mode bit 0: SIGNAL (tell every rank that everything this stream did before has happened);
+// mode bit 1: WAIT (until every rank has signalled `epoch` in this slot).  Signal and wait may sit on
+// different streams: the pushing stream only signals and never blocks on a peer, the consuming stream waits.
 __global__ void peer_barrier_kernel(int world, int rank, PeerPtrs flags, int slot, uint32_t epoch,
-                                    uint32_t* __restrict__ err, unsigned long long timeout_ns) {
+                                    uint32_t* __restrict__ err, unsigned long long timeout_ns, int mode) {
     const int t = threadIdx.x;
     if (t >= world) return;
 #ifndef TS_HOST_EMU
-    __threadfence_system();     // everything this stream wrote before (also to peers) is ordered before the signal
-    uint32_t* remote = reinterpret_cast<uint32_t*>(flags.p[t]) + ((size_t)slot * kMaxPeers + rank) * 32;
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(remote), "r"(epoch) : "memory");
+    if (mode & 1) {
+        __threadfence_system();     // everything this stream wrote before (also to peers) is ordered before the signal
+        uint32_t* remote = reinterpret_cast<uint32_t*>(flags.p[t]) + ((size_t)slot * kMaxPeers + rank) * 32;
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(remote), "r"(epoch) : "memory");
+    }
+    if (!(mode & 2)) return;
     const uint32_t* local = reinterpret_cast<const uint32_t*>(flags.p[rank]) + ((size_t)slot * kMaxPeers + t) * 32;
     unsigned long long t0, now;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
@@ -137,7 +143,7 @@ __global__ void peer_barrier_kernel(int world, int rank, PeerPtrs flags, int slo
     }
     __threadfence_system();
 #else
-    (void)flags; (void)slot; (void)epoch; (void)err; (void)timeout_ns; (void)rank;
+    (void)flags; (void)slot; (void)epoch; (void)err; (void)timeout_ns; (void)rank; (void)mode;
 #endif
 }
 
@@ -216,9 +222,9 @@ int ts_dp_push(int N, int shard_rows, int padded_rows, int world, int rank, cons
 }
 
 int ts_peer_barrier(int world, int rank, void* const* flag_ptrs_host, int slot, uint32_t epoch,
-                    uint32_t* err_flag, double timeout_s, ts_stream_t stream) {
+                    uint32_t* err_flag, double timeout_s, int mode, ts_stream_t stream) {
     if (world < 1 || world > ts::kMaxPeers || rank < 0 || rank >= world || slot < 0 || slot >= ts::kBarrierSlots ||
-        !flag_ptrs_host || !err_flag)
+        !flag_ptrs_host || !err_flag || mode < 1 || mode > 3)
         return TS_ERR_INVALID;
     ts::PeerPtrs flags{};
     for (int r = 0; r < world; ++r) {
@@ -227,11 +233,12 @@ int ts_peer_barrier(int world, int rank, void* const* flag_ptrs_host, int slot, 
     }
     if (!(timeout_s > 0)) timeout_s = 10.0;
     ts::peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(world, rank, flags, slot, epoch, err_flag,
-                                                                 (unsigned long long)(timeout_s * 1e9));
+                                                                 (unsigned long long)(timeout_s * 1e9), mode);
     TS_CHECK_LAUNCH("ts_peer_barrier");
     return TS_OK;
 }
 
+int ts_peer_barrier_slots(void) { return ts::kBarrierSlots; }
 int ts_peer_flag_bytes(void) { return ts::kBarrierSlots * ts::kMaxPeers * 32 * (int)sizeof(uint32_t); }
 
 }  // extern "C"

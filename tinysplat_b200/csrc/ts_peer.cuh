@@ -6,7 +6,7 @@
 namespace ts {
 
 constexpr int kMaxPeers = 8;          // one NVSwitch domain of a B200 box
-constexpr int kBarrierSlots = 2;      // A: rows pushed, B: shard gradients stored
+constexpr int kBarrierSlots = 16;     // one per pushed chunk of rows + one for the stored shard gradients
 constexpr int kCamRowFloats = 32;     // 3x4 view | 4x4 full projection | fx fy | pad
 
 struct PeerPtrs {

@@ -31,8 +31,8 @@ USE_SIDE_STREAM = True     # SH kernels on a second stream, overlapping binning 
 last_bins = None           # (tile_offsets, ids_sorted, M) of the most recent fused forward
 
 
-def _side_stream(dev) -> "torch.cuda.Stream":
-    key = str(dev)
+def _side_stream(dev, which: int = 0) -> "torch.cuda.Stream":
+    key = (str(dev), which)
     if key not in _side_streams:
         _side_streams[key] = torch.cuda.Stream(device=dev)
     return _side_streams[key]
@@ -271,11 +271,16 @@ class _RenderFused(Function):
 
 def _backward_peer_exchange(ctx, grads, st):
     """Data-parallel backward over NVLink peer memory (parallel.PeerGradExchange,
-    csrc/peer.cu): no collective call.  ts_dp_push stores this view's geometry rows into the owner
-    ranks' buffers and its colour cotangents + camera into every rank's; after a flag barrier every
-    rank rebuilds the SH gradient of ALL Gaussians from all views' colour cotangents and runs
-    projection-backward over all views for ITS shard, storing the result into every rank's gradient
-    segment; a second barrier, and the six gradients are views of the local segment."""
+    csrc/peer.cu): no collective call.  The rows are handled in pieces (PeerLayout.chunks), each
+    sharded over the ranks on its own, as a three-stream pipeline:
+      main   : ts_dp_push(piece c) — this view's geometry rows to the ranks that own them, its colour
+               cotangents + camera to every rank — then SIGNAL(slot c); never waits for a peer;
+      side   : WAIT(slot c): every rank's rows of piece c have landed here -> SH gradient of the
+               piece's Gaussians rebuilt from all views' colour cotangents (local, HBM-bound);
+      side 2 : projection-backward over all views for MY shard of piece c, stored straight into every
+               rank's gradient segment (issue-bound + NVLink stores).
+    The NVLink transfer of piece c+1 runs under the shard backward of piece c.  A final barrier: every
+    shard's gradients have landed in my segment, and the six gradients are views of it."""
     (means_c, scales_c, quats_c, logit_c, view_c, proj_c, bg_c, radii, recs, offsets, ids_sorted,
      final_T, n_contrib, mask) = ctx.saved_tensors
     N, K, W, H, tx, ty, fx, fy, deg, pflags, sflags, opac_shape, dc_shape = ctx.meta
@@ -283,35 +288,55 @@ def _backward_peer_exchange(ctx, grads, st):
     dev = means_c.device
     world, rank = dp.world, dp.rank
     L = dp.ensure(N, K, dev)
-    s0, ns, Ns = L.shard_of(rank, N)
+    _, _, Ns = L.shard_of(rank, N)
     Npad = world * Ns
+    R = (K - 1) * 3
     v_xys = torch.empty(N, 2, device=dev, dtype=torch.float32)
-    _lib.call("ts_dp_push", N, Ns, Npad, world, rank, _lib.ptr(radii), _lib.ptr(mask), _lib.ptr(recs),
-              _lib.ptr(grads), _lib.ptr(cam_row), dp.seg_ptrs("geo"), dp.seg_ptrs("rgb"), dp.seg_ptrs("cams"),
-              _lib.ptr(v_xys), st)
     epoch = dp.next_epoch()
-    dp.barrier(0, epoch, st)                      # every rank's rows, colours and camera have landed here
     scale = dp.out_scale()
     main = torch.cuda.current_stream(dev)
-    side = _side_stream(dev) if USE_SIDE_STREAM else main
-    if N > 0:
-        if side is not main:
-            side.wait_stream(main)
+    side, side2 = (_side_stream(dev), _side_stream(dev, 1)) if USE_SIDE_STREAM else (main, main)
+    if side is not main:
+        side.wait_stream(main)       # whoever read last step's gradients (views of my segment) is done
+        side2.wait_stream(main)
+    pieces = L.chunks(N, dp.n_chunks) if N > 0 else []
+    final_slot = L.MAX_CHUNKS
+    if not pieces:                   # nothing to push, but the camera and the barriers keep the ranks in step
+        _lib.call("ts_dp_push", 0, Ns, Npad, world, rank, None, None, None, None, _lib.ptr(cam_row),
+                  dp.seg_ptrs("geo"), dp.seg_ptrs("rgb"), dp.seg_ptrs("cams"), None, st)
+    sent = 0
+    for c, (r0, n, ns_c, g0) in enumerate(pieces):
+        geo_off = world * g0 * 32
+        _lib.call("ts_dp_push", n, ns_c, Npad, world, rank, radii.data_ptr() + 4 * r0, mask.data_ptr() + r0,
+                  recs.data_ptr() + 48 * r0, grads.data_ptr() + 48 * r0, _lib.ptr(cam_row),
+                  dp.seg_ptrs("geo", geo_off), dp.seg_ptrs("rgb", 12 * r0), dp.seg_ptrs("cams"),
+                  v_xys.data_ptr() + 8 * r0, st)
+        dp.barrier(c, epoch, st, dp.SIGNAL)
         with torch.cuda.stream(side):
-            _lib.call("ts_sh_bwd_views_rgb", world, N, deg, K, _lib.ptr(means_c), dp.local_ptr("cams"),
-                      dp.local_ptr("rgb"), Npad * 3, scale, dp.local_ptr("g_dc"), dp.local_ptr("g_rest"),
-                      side.cuda_stream)
+            dp.barrier(c, epoch, side.cuda_stream, dp.WAIT)      # every rank's rows of this piece have landed here
+            landed = torch.cuda.Event()
+            landed.record(side)
+            _lib.call("ts_sh_bwd_views_rgb", world, n, deg, K, means_c.data_ptr() + 12 * r0, dp.local_ptr("cams"),
+                      dp.local_ptr("rgb") + 12 * r0, Npad * 3, scale, dp.local_ptr("g_dc") + 12 * r0,
+                      dp.local_ptr("g_rest") + 4 * R * r0, side.cuda_stream)
+        s0 = r0 + rank * ns_c                                     # my shard of this piece (global rows)
+        ns = max(0, min(n, (rank + 1) * ns_c) - rank * ns_c)
         if ns > 0:
-            dst = [dp.seg_ptrs("g_" + n, s0 * L.width(n) * 4) for n in ("means", "scales", "quats", "logit")]
-            _lib.call("ts_project_bwd_views_peer", world, ns, _lib.ptr(means_c[s0:s0 + ns]),
-                      _lib.ptr(scales_c[s0:s0 + ns]), 1.0, _lib.ptr(quats_c[s0:s0 + ns]), dp.local_ptr("cams"),
-                      H, W, pflags, dp.local_ptr("geo"), Ns * 8, _lib.ptr(logit_c[s0:s0 + ns]), scale, world,
-                      (rank + 1) % world, dst[0], dst[1], dst[2], dst[3], st)
-        if side is not main:
-            main.wait_stream(side)
-    dp.barrier(1, epoch, st)                      # every shard's gradients have landed in my segment
-    # bytes this rank sent over NVLink: geometry rows + colours + finished shard gradients
-    dp.last_bytes_sent = (N * 32 * (world - 1)) // world + N * 12 * (world - 1) + ns * 44 * (world - 1)
+            with torch.cuda.stream(side2):
+                side2.wait_event(landed)
+                dst = [dp.seg_ptrs("g_" + nm, s0 * L.width(nm) * 4) for nm in ("means", "scales", "quats", "logit")]
+                _lib.call("ts_project_bwd_views_peer", world, ns, means_c.data_ptr() + 12 * s0,
+                          scales_c.data_ptr() + 12 * s0, 1.0, quats_c.data_ptr() + 16 * s0, dp.local_ptr("cams"),
+                          H, W, pflags, dp.local_ptr("geo") + geo_off, ns_c * 8, logit_c.data_ptr() + 4 * s0,
+                          scale, world, (rank + 1) % world, dst[0], dst[1], dst[2], dst[3], side2.cuda_stream)
+        sent += (n * 32 * (world - 1)) // world + n * 12 * (world - 1) + ns * 44 * (world - 1)
+    if side is not main:
+        side.wait_stream(side2)
+    with torch.cuda.stream(side):
+        dp.barrier(final_slot, epoch, side.cuda_stream)          # every shard's gradients have landed in my segment
+    if side is not main:
+        main.wait_stream(side)
+    dp.last_bytes_sent = sent        # bytes this rank sent over NVLink: geometry rows + colours + finished shard gradients
     v_rest, v_dc = dp.local_view("g_rest", N, K - 1, 3), dp.local_view("g_dc", N, 3)
     v_means, v_scales = dp.local_view("g_means", N, 3), dp.local_view("g_scales", N, 3)
     v_quats, v_logit = dp.local_view("g_quats", N, 4), dp.local_view("g_logit", N)

@@ -20,6 +20,8 @@ The densification statistic is the per-view norm of d loss / d xy summed over vi
 so it gets its own [N] all-reduce (`reduce_densify_stat`)."""
 from __future__ import annotations
 
+import os
+
 from typing import Callable, Iterable, List, Optional
 
 import torch
@@ -199,6 +201,7 @@ class PeerLayout:
     so that the six parameter gradients handed to autograd are views of this buffer."""
 
     SHARD_ALIGN = 256          # rows; keeps every shard slice of every tensor 16-byte aligned
+    MAX_CHUNKS = 8             # the rows are pushed in up to this many chunks (one barrier slot each)
 
     def __init__(self, world: int, cap_rows: int, K: int, flag_bytes: int):
         self.world, self.cap_rows, self.K = world, cap_rows, K
@@ -213,7 +216,8 @@ class PeerLayout:
         add("flags", flag_bytes)
         add("err", 256)
         add("cams", world * PackedGradExchange.CAM_FLOATS * 4)
-        add("geo", world * self.cap_shard * 8 * 4)
+        # geometry rows are laid out per pushed chunk, each chunk padded to its own shard size
+        add("geo", world * (self.cap_shard + self.MAX_CHUNKS * self.SHARD_ALIGN) * 8 * 4)
         add("rgb", world * world * self.cap_shard * 3 * 4)
         for name, width in (("rest", (K - 1) * 3), ("dc", 3), ("means", 3), ("scales", 3), ("quats", 4), ("logit", 1)):
             add("g_" + name, max(1, cap_rows * width) * 4)
@@ -230,6 +234,24 @@ class PeerLayout:
         ns_all = self.shard_rows(n_gaussians, self.world)
         s0 = rank * ns_all
         return s0, max(0, min(n_gaussians, s0 + ns_all) - s0), ns_all
+
+    def chunks(self, n_gaussians: int, n_chunks: int):
+        """Splits the rows into <= n_chunks pieces that are pushed, signalled and consumed one after the
+        other (the transfer of piece c+1 overlaps the shard backward of piece c).  Every piece is sharded
+        over the ranks on its own.  -> [(first row, rows, shard rows of the piece, first row of the
+        piece's geometry block in the geo segment)], piece sizes multiples of world * SHARD_ALIGN."""
+        n_chunks = max(1, min(int(n_chunks), self.MAX_CHUNKS))
+        unit = self.world * self.SHARD_ALIGN
+        per = -(-max(n_gaussians, 1) // n_chunks)
+        per = (per + unit - 1) // unit * unit
+        out, r0, g0 = [], 0, 0
+        while r0 < n_gaussians:
+            n = min(per, n_gaussians - r0)
+            ns = self.shard_rows(n, self.world)
+            out.append((r0, n, ns, g0))
+            r0 += n
+            g0 += ns          # rows per source rank; the block of a piece holds world * ns rows
+        return out
 
     GRAD_WIDTH = {"rest": None, "dc": 3, "means": 3, "scales": 3, "quats": 4, "logit": 1}
 
@@ -259,7 +281,7 @@ class PeerGradExchange:
     peer = True
 
     def __init__(self, process_group=None, average: bool = True, headroom: float = 0.125,
-                 timeout_s: float = 20.0):
+                 timeout_s: float = 20.0, n_chunks: Optional[int] = None):
         if not (dist.is_available() and dist.is_initialized()):
             raise RuntimeError("PeerGradExchange needs an initialised process group")
         from . import _lib
@@ -272,6 +294,8 @@ class PeerGradExchange:
         self.average = average
         self.headroom = headroom
         self.timeout_s = timeout_s
+        # pieces the rows are pushed in (the transfer of one overlaps the shard backward of the previous)
+        self.n_chunks = int(n_chunks if n_chunks is not None else os.environ.get("TINYSPLAT_B200_PEER_CHUNKS", "4"))
         self.layout: Optional[PeerLayout] = None
         self.device = None
         self._base = None            # my allocation
@@ -330,6 +354,8 @@ class PeerGradExchange:
         import ctypes as C
         t = self._tables.get(key)
         if t is None:
+            if len(self._tables) > 4096:      # offsets change with N (densification): do not grow for ever
+                self._tables.clear()
             t = (C.c_void_p * len(ptrs))(*ptrs)
             self._tables[key] = t
         return t
@@ -354,10 +380,14 @@ class PeerGradExchange:
         self.epoch += 1
         return self.epoch
 
-    def barrier(self, slot: int, epoch: int, stream_ptr: int) -> None:
+    SIGNAL, WAIT = 1, 2
+
+    def barrier(self, slot: int, epoch: int, stream_ptr: int, mode: int = 3) -> None:
+        """mode: SIGNAL (what this stream did so far is visible to ranks that wait for `epoch`), WAIT
+        (until every rank has signalled), or both.  The two halves may sit on different streams."""
         lib = self._lib.load()
         self._lib.check(lib.ts_peer_barrier(self.world, self.rank, self.seg_ptrs("flags"), slot, epoch,
-                                            self.local_ptr("err"), float(self.timeout_s), stream_ptr),
+                                            self.local_ptr("err"), float(self.timeout_s), int(mode), stream_ptr),
                         "ts_peer_barrier")
 
     def check(self) -> None:
