@@ -302,6 +302,27 @@ TS_API int ts_dp_push(int N, int shard_rows, int padded_rows, int world, int ran
 TS_API int ts_peer_barrier(int world, int rank, void* const* flag_ptrs_host, int slot, uint32_t epoch,
                            uint32_t* err_flag, double timeout_s, int mode, ts_stream_t stream);
 TS_API int ts_peer_barrier_slots(void);
+/* The whole data-parallel backward tail after ts_blend_bwd as one call: a three-stream pipeline over
+ * n_pieces (< ts_peer_barrier_slots()) pieces of the rows.  piece_plan_host[c] = {first row, rows, shard
+ * rows of the piece, first geometry row of the piece per source rank} (each piece is sharded over the
+ * ranks on its own; sizes multiples of 256).  Per piece:
+ *   main stream  : ts_dp_push(piece) + signal(slot c)              — never waits for a peer
+ *   side stream  : wait(slot c) + ts_sh_bwd_views_rgb(piece)        — local, HBM-bound
+ *   side2 stream : ts_project_bwd_views_peer(my shard of the piece) — stores into every rank
+ * so the NVLink transfer of piece c+1 runs under the shard backward of piece c; then a barrier in the
+ * last slot and the main stream joins.  peer_bases_host[world]: every rank's allocation;
+ * seg_offsets_host[11]: byte offsets of the segments {flags, err, cams, geo, rgb, g_rest, g_dc, g_means,
+ * g_scales, g_quats, g_logit} inside an allocation (tinysplat_b200/parallel.py PeerLayout).  The host
+ * side is pure launch logic; issuing it from native code instead of Python keeps it off the critical path. */
+TS_API int ts_dp_exchange_peer(int N, int K, int degree, int world, int rank, int n_pieces,
+                               const int32_t* piece_plan_host, int padded_rows, const int32_t* radii,
+                               const uint8_t* clamp_mask /*or NULL*/, const float* recs /*[16B]*/,
+                               const float* grads /*[16B]*/, const float* cam_row, const float* means3d,
+                               const float* scales, const float* quats, const float* opacity_logits,
+                               void* const* peer_bases_host, const int64_t* seg_offsets_host,
+                               int img_height, int img_width, int proj_flags, float out_scale,
+                               uint32_t epoch, double timeout_s, float* v_xys /*or NULL*/,
+                               ts_stream_t main_stream, ts_stream_t side_stream, ts_stream_t side2_stream);
 TS_API int ts_sh_bwd_views_rgb(int n_views, int N, int degree, int K, const float* means,
                                const float* cams, const float* rgb_rows /*[16B]*/,
                                int64_t view_stride_floats, float out_scale, float* v_dc, float* v_rest,

@@ -21,6 +21,10 @@
 #include "ts_common.cuh"
 #include "ts_peer.cuh"
 
+#ifndef TS_PEER_WAIT_READ
+#define TS_PEER_WAIT_READ 0
+#endif
+
 namespace ts {
 
 constexpr int kPushThreads = 256;
@@ -80,7 +84,11 @@ dp_push_kernel(int N, int Ns, int Npad, int world, int rank, const int32_t* __re
                 bulk_s2g(reinterpret_cast<float*>(rgb.p[r]) + rgb_off, s_rgb, kPushThreads * 12);
             }
             bulk_commit();
+#if TS_PEER_WAIT_READ
+            bulk_wait_read0();      // experiment: only the shared-memory reads; the kernel boundary completes the writes
+#else
             bulk_wait0();           // performed, not just read: the flag barrier that follows publishes them
+#endif
         }
     } else {
         __syncthreads();
@@ -239,6 +247,126 @@ int ts_peer_barrier(int world, int rank, void* const* flag_ptrs_host, int slot, 
 }
 
 int ts_peer_barrier_slots(void) { return ts::kBarrierSlots; }
+
+// ---- the whole data-parallel backward tail as ONE call --------------------------------------------
+// A three-stream pipeline over row pieces (see the header).  Everything here is host-side launch
+// logic: the ~30 launches, event records and stream waits of a 4-piece exchange cost ~0.1 ms issued
+// from here and ~0.4 ms issued one by one from Python — more than blend-backward leaves the CPU.
+namespace {
+struct EventPool {          // per device; events are reused round-robin (disable-timing: cheap to record)
+    static constexpr int kN = 64;
+    cudaEvent_t ev[kN];
+    int next = 0;
+    bool ready = false;
+};
+EventPool g_pools[16];
+
+cudaEvent_t pool_event(int dev) {
+    EventPool& P = g_pools[dev & 15];
+    if (!P.ready) {
+        for (int i = 0; i < EventPool::kN; ++i) cudaEventCreateWithFlags(&P.ev[i], cudaEventDisableTiming);
+        P.ready = true;
+    }
+    cudaEvent_t e = P.ev[P.next];
+    P.next = (P.next + 1) % EventPool::kN;
+    return e;
+}
+}  // namespace
+
+int ts_dp_exchange_peer(int N, int K, int degree, int world, int rank, int n_pieces, const int32_t* piece_plan_host,
+                        int padded_rows, const int32_t* radii, const uint8_t* clamp_mask, const float* recs,
+                        const float* grads, const float* cam_row, const float* means3d, const float* scales,
+                        const float* quats, const float* opacity_logits, void* const* peer_bases_host,
+                        const int64_t* seg_offsets_host, int img_height, int img_width, int proj_flags,
+                        float out_scale, uint32_t epoch, double timeout_s, float* v_xys, ts_stream_t main_stream,
+                        ts_stream_t side_stream, ts_stream_t side2_stream) {
+    if (N < 0 || world < 1 || world > ts::kMaxPeers || rank < 0 || rank >= world || n_pieces < 0 ||
+        n_pieces >= ts::kBarrierSlots || !peer_bases_host || !seg_offsets_host || !cam_row || (n_pieces > 0 && !piece_plan_host))
+        return TS_ERR_INVALID;
+    enum { SEG_FLAGS, SEG_ERR, SEG_CAMS, SEG_GEO, SEG_RGB, SEG_REST, SEG_DC, SEG_MEANS, SEG_SCALES, SEG_QUATS, SEG_LOGIT };
+    cudaStream_t sm = (cudaStream_t)main_stream, s1 = (cudaStream_t)side_stream, s2 = (cudaStream_t)side2_stream;
+    int dev = 0;
+    TS_CHECK_CUDA(cudaGetDevice(&dev), "ts_dp_exchange_peer/device");
+    auto seg = [&](int r, int which, int64_t byte_off) -> void* {
+        return (void*)((char*)peer_bases_host[r] + seg_offsets_host[which] + byte_off);
+    };
+    auto table = [&](void** t, int which, int64_t byte_off) { for (int r = 0; r < world; ++r) t[r] = seg(r, which, byte_off); };
+    void *t_flags[ts::kMaxPeers], *t_geo[ts::kMaxPeers], *t_rgb[ts::kMaxPeers], *t_cams[ts::kMaxPeers];
+    void *t_m[ts::kMaxPeers], *t_s[ts::kMaxPeers], *t_q[ts::kMaxPeers], *t_l[ts::kMaxPeers];
+    table(t_flags, SEG_FLAGS, 0);
+    table(t_cams, SEG_CAMS, 0);
+    uint32_t* err = (uint32_t*)seg(rank, SEG_ERR, 0);
+    const float* cams_local = (const float*)seg(rank, SEG_CAMS, 0);
+    const int R = (K - 1) * 3;
+    int rc;
+    // whoever read last step's gradients (views of my segment) on the main stream is done
+    cudaEvent_t e0 = pool_event(dev);
+    TS_CHECK_CUDA(cudaEventRecord(e0, sm), "ts_dp_exchange_peer/event");
+    if (s1 != sm) TS_CHECK_CUDA(cudaStreamWaitEvent(s1, e0, 0), "ts_dp_exchange_peer/wait");
+    if (s2 != sm && s2 != s1) TS_CHECK_CUDA(cudaStreamWaitEvent(s2, e0, 0), "ts_dp_exchange_peer/wait");
+    if (n_pieces == 0) {    // nothing to push, but the camera and the barrier keep the ranks in step
+        table(t_geo, SEG_GEO, 0);
+        table(t_rgb, SEG_RGB, 0);
+        rc = ts_dp_push(0, 4, padded_rows > 0 ? padded_rows : 4 * world, world, rank, nullptr, nullptr, nullptr, nullptr,
+                        cam_row, t_geo, t_rgb, t_cams, nullptr, main_stream);
+        if (rc != TS_OK) return rc;
+    }
+    for (int c = 0; c < n_pieces; ++c) {
+        const int64_t r0 = piece_plan_host[4 * c], n = piece_plan_host[4 * c + 1], ns_c = piece_plan_host[4 * c + 2],
+                      g0 = piece_plan_host[4 * c + 3];
+        if (r0 < 0 || n <= 0 || r0 + n > N || ns_c <= 0) return TS_ERR_INVALID;
+        const int64_t geo_off = (int64_t)world * g0 * 32;
+        table(t_geo, SEG_GEO, geo_off);
+        table(t_rgb, SEG_RGB, 12 * r0);
+        // main: push the piece, signal; never waits for a peer
+        rc = ts_dp_push((int)n, (int)ns_c, padded_rows, world, rank, radii + r0, clamp_mask ? clamp_mask + r0 : nullptr,
+                        recs + 12 * r0, grads + 12 * r0, cam_row, t_geo, t_rgb, t_cams, v_xys ? v_xys + 2 * r0 : nullptr,
+                        main_stream);
+        if (rc != TS_OK) return rc;
+        rc = ts_peer_barrier(world, rank, t_flags, c, epoch, err, timeout_s, 1, main_stream);
+        if (rc != TS_OK) return rc;
+        // side: every rank's rows of this piece have landed here -> SH gradient of the piece (local)
+        rc = ts_peer_barrier(world, rank, t_flags, c, epoch, err, timeout_s, 2, side_stream);
+        if (rc != TS_OK) return rc;
+        cudaEvent_t landed = pool_event(dev);
+        TS_CHECK_CUDA(cudaEventRecord(landed, s1), "ts_dp_exchange_peer/event");
+        rc = ts_sh_bwd_views_rgb(world, (int)n, degree, K, means3d + 3 * r0, cams_local,
+                                 (const float*)seg(rank, SEG_RGB, 12 * r0), (int64_t)padded_rows * 3, out_scale,
+                                 (float*)seg(rank, SEG_DC, 12 * r0), (float*)seg(rank, SEG_REST, 4 * (int64_t)R * r0),
+                                 side_stream);
+        if (rc != TS_OK) return rc;
+        // side 2: projection-backward over all views for MY shard of the piece, stored into every rank
+        const int64_t s0 = r0 + (int64_t)rank * ns_c;
+        int64_t ns = (int64_t)(rank + 1) * ns_c < n ? ns_c : n - (int64_t)rank * ns_c;
+        if (ns > 0) {
+            if (s2 != s1) TS_CHECK_CUDA(cudaStreamWaitEvent(s2, landed, 0), "ts_dp_exchange_peer/wait");
+            table(t_m, SEG_MEANS, 12 * s0);
+            table(t_s, SEG_SCALES, 12 * s0);
+            table(t_q, SEG_QUATS, 16 * s0);
+            table(t_l, SEG_LOGIT, 4 * s0);
+            rc = ts_project_bwd_views_peer(world, (int)ns, means3d + 3 * s0, scales + 3 * s0, 1.0f, quats + 4 * s0,
+                                           cams_local, img_height, img_width, proj_flags,
+                                           (const float*)seg(rank, SEG_GEO, geo_off), ns_c * 8,
+                                           opacity_logits ? opacity_logits + s0 : nullptr, out_scale, world,
+                                           (rank + 1) % world, t_m, t_s, t_q, t_l, side2_stream);
+            if (rc != TS_OK) return rc;
+        }
+    }
+    // every shard's gradients have landed in my segment: final barrier on the side stream, then main joins
+    if (s2 != s1) {
+        cudaEvent_t e2 = pool_event(dev);
+        TS_CHECK_CUDA(cudaEventRecord(e2, s2), "ts_dp_exchange_peer/event");
+        TS_CHECK_CUDA(cudaStreamWaitEvent(s1, e2, 0), "ts_dp_exchange_peer/wait");
+    }
+    rc = ts_peer_barrier(world, rank, t_flags, ts::kBarrierSlots - 1, epoch, err, timeout_s, 3, side_stream);
+    if (rc != TS_OK) return rc;
+    if (s1 != sm) {
+        cudaEvent_t e1 = pool_event(dev);
+        TS_CHECK_CUDA(cudaEventRecord(e1, s1), "ts_dp_exchange_peer/event");
+        TS_CHECK_CUDA(cudaStreamWaitEvent(sm, e1, 0), "ts_dp_exchange_peer/wait");
+    }
+    return TS_OK;
+}
 int ts_peer_flag_bytes(void) { return ts::kBarrierSlots * ts::kMaxPeers * 32 * (int)sizeof(uint32_t); }
 
 }  // extern "C"

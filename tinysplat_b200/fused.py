@@ -289,53 +289,18 @@ def _backward_peer_exchange(ctx, grads, st):
     world, rank = dp.world, dp.rank
     L = dp.ensure(N, K, dev)
     _, _, Ns = L.shard_of(rank, N)
-    Npad = world * Ns
-    R = (K - 1) * 3
     v_xys = torch.empty(N, 2, device=dev, dtype=torch.float32)
-    epoch = dp.next_epoch()
-    scale = dp.out_scale()
     main = torch.cuda.current_stream(dev)
     side, side2 = (_side_stream(dev), _side_stream(dev, 1)) if USE_SIDE_STREAM else (main, main)
-    if side is not main:
-        side.wait_stream(main)       # whoever read last step's gradients (views of my segment) is done
-        side2.wait_stream(main)
-    pieces = L.chunks(N, dp.n_chunks) if N > 0 else []
-    final_slot = L.MAX_CHUNKS
-    if not pieces:                   # nothing to push, but the camera and the barriers keep the ranks in step
-        _lib.call("ts_dp_push", 0, Ns, Npad, world, rank, None, None, None, None, _lib.ptr(cam_row),
-                  dp.seg_ptrs("geo"), dp.seg_ptrs("rgb"), dp.seg_ptrs("cams"), None, st)
-    sent = 0
-    for c, (r0, n, ns_c, g0) in enumerate(pieces):
-        geo_off = world * g0 * 32
-        _lib.call("ts_dp_push", n, ns_c, Npad, world, rank, radii.data_ptr() + 4 * r0, mask.data_ptr() + r0,
-                  recs.data_ptr() + 48 * r0, grads.data_ptr() + 48 * r0, _lib.ptr(cam_row),
-                  dp.seg_ptrs("geo", geo_off), dp.seg_ptrs("rgb", 12 * r0), dp.seg_ptrs("cams"),
-                  v_xys.data_ptr() + 8 * r0, st)
-        dp.barrier(c, epoch, st, dp.SIGNAL)
-        with torch.cuda.stream(side):
-            dp.barrier(c, epoch, side.cuda_stream, dp.WAIT)      # every rank's rows of this piece have landed here
-            landed = torch.cuda.Event()
-            landed.record(side)
-            _lib.call("ts_sh_bwd_views_rgb", world, n, deg, K, means_c.data_ptr() + 12 * r0, dp.local_ptr("cams"),
-                      dp.local_ptr("rgb") + 12 * r0, Npad * 3, scale, dp.local_ptr("g_dc") + 12 * r0,
-                      dp.local_ptr("g_rest") + 4 * R * r0, side.cuda_stream)
-        s0 = r0 + rank * ns_c                                     # my shard of this piece (global rows)
-        ns = max(0, min(n, (rank + 1) * ns_c) - rank * ns_c)
-        if ns > 0:
-            with torch.cuda.stream(side2):
-                side2.wait_event(landed)
-                dst = [dp.seg_ptrs("g_" + nm, s0 * L.width(nm) * 4) for nm in ("means", "scales", "quats", "logit")]
-                _lib.call("ts_project_bwd_views_peer", world, ns, means_c.data_ptr() + 12 * s0,
-                          scales_c.data_ptr() + 12 * s0, 1.0, quats_c.data_ptr() + 16 * s0, dp.local_ptr("cams"),
-                          H, W, pflags, dp.local_ptr("geo") + geo_off, ns_c * 8, logit_c.data_ptr() + 4 * s0,
-                          scale, world, (rank + 1) % world, dst[0], dst[1], dst[2], dst[3], side2.cuda_stream)
-        sent += (n * 32 * (world - 1)) // world + n * 12 * (world - 1) + ns * 44 * (world - 1)
-    if side is not main:
-        side.wait_stream(side2)
-    with torch.cuda.stream(side):
-        dp.barrier(final_slot, epoch, side.cuda_stream)          # every shard's gradients have landed in my segment
-    if side is not main:
-        main.wait_stream(side)
+    plan, n_pieces, sent = dp.piece_plan(N)
+    # one native call issues the whole pipeline (ts_dp_exchange_peer, csrc/peer.cu): ~30 launches, event
+    # records and stream waits that would take longer to issue from Python than blend-backward runs
+    _lib.call("ts_dp_exchange_peer", N, K, deg, world, rank, n_pieces, plan, world * Ns,
+              _lib.ptr(radii), _lib.ptr(mask), _lib.ptr(recs), _lib.ptr(grads), _lib.ptr(cam_row),
+              _lib.ptr(means_c), _lib.ptr(scales_c), _lib.ptr(quats_c), _lib.ptr(logit_c),
+              dp.bases_table(), dp.seg_offsets_table(), H, W, pflags, dp.out_scale(), dp.next_epoch(),
+              float(dp.timeout_s), _lib.ptr(v_xys), main.cuda_stream, side.cuda_stream, side2.cuda_stream)
+    # (the main stream has joined the side streams when the call returns: no record_stream needed)
     dp.last_bytes_sent = sent        # bytes this rank sent over NVLink: geometry rows + colours + finished shard gradients
     v_rest, v_dc = dp.local_view("g_rest", N, K - 1, 3), dp.local_view("g_dc", N, 3)
     v_means, v_scales = dp.local_view("g_means", N, 3), dp.local_view("g_scales", N, 3)

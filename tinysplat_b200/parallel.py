@@ -376,6 +376,40 @@ class PeerGradExchange:
             numel *= d
         return self._span[off:off + 4 * numel].view(torch.float32).view(n_rows, *shape)
 
+    SEGMENTS = ("flags", "err", "cams", "geo", "rgb", "g_rest", "g_dc", "g_means", "g_scales", "g_quats", "g_logit")
+
+    def bases_table(self):
+        """ctypes table of every rank's allocation base (ts_dp_exchange_peer)."""
+        return self._table("bases", self._peer_bases)
+
+    def seg_offsets_table(self):
+        import ctypes as C
+        t = self._tables.get("seg_offsets")
+        if t is None:
+            t = (C.c_int64 * len(self.SEGMENTS))(*[self.layout.seg[n][0] for n in self.SEGMENTS])
+            self._tables["seg_offsets"] = t
+        return t
+
+    def piece_plan(self, n_gaussians: int):
+        """(ctypes int32 [pieces][4] = first row, rows, shard rows, first geometry row per source rank;
+        number of pieces; bytes this rank sends over NVLink: geometry rows + colours + shard gradients)."""
+        import ctypes as C
+        key = ("plan", n_gaussians, self.n_chunks)
+        hit = self._tables.get(key)
+        if hit is None:
+            pieces = self.layout.chunks(n_gaussians, self.n_chunks) if n_gaussians > 0 else []
+            flat, sent, w = [], 0, self.world
+            for r0, n, ns_c, g0 in pieces:
+                flat += [r0, n, ns_c, g0]
+                ns = max(0, min(n, (self.rank + 1) * ns_c) - self.rank * ns_c)
+                sent += (n * 32 * (w - 1)) // w + n * 12 * (w - 1) + ns * 44 * (w - 1)
+            hit = ((C.c_int32 * max(len(flat), 1))(*flat), len(flat), sent)
+            if len(self._tables) > 4096:
+                self._tables.clear()
+            self._tables[key] = hit
+        arr, nflat, sent = hit
+        return arr, nflat // 4, sent
+
     def next_epoch(self) -> int:
         self.epoch += 1
         return self.epoch

@@ -4,7 +4,7 @@ all-to-all + shard backward + all-gather) and "peer" (the kernels' own NVLink st
 call) and compares the reduced gradients; then times each.  Prints one JSON line on rank 0.
 
   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
-      --master-port 29511 tools/dp_check.py [--n 1000000]"""
+      --master-port 29511 tools/dp_check.py [--gaussians 1000000]"""
 import argparse
 import json
 import os
@@ -21,14 +21,14 @@ from tinysplat_b200.rasterizer import GaussianRasterizer, ParamModel  # noqa: E4
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, default=1_000_000)
+    ap.add_argument("--gaussians", type=int, default=1_000_000)
     ap.add_argument("--steps", type=int, default=20)
     args = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
-    W, H, N = 1920, 1080, args.n
+    W, H, N = 1920, 1080, args.gaussians
     sc = synthetic.make_scene(N, W, H, seed=0)
     cot = torch.rand(H, W, 3, generator=torch.Generator().manual_seed(7)).to(dev) / (3 * W * H)
     cot_d = torch.rand(H, W, generator=torch.Generator().manual_seed(8)).to(dev) / (W * H)
