@@ -21,10 +21,6 @@
 #include "ts_common.cuh"
 #include "ts_peer.cuh"
 
-#ifndef TS_PEER_WAIT_READ
-#define TS_PEER_WAIT_READ 0
-#endif
-
 namespace ts {
 
 constexpr int kPushThreads = 256;
@@ -84,11 +80,7 @@ dp_push_kernel(int N, int Ns, int Npad, int world, int rank, const int32_t* __re
                 bulk_s2g(reinterpret_cast<float*>(rgb.p[r]) + rgb_off, s_rgb, kPushThreads * 12);
             }
             bulk_commit();
-#if TS_PEER_WAIT_READ
-            bulk_wait_read0();      // experiment: only the shared-memory reads; the kernel boundary completes the writes
-#else
             bulk_wait0();           // performed, not just read: the flag barrier that follows publishes them
-#endif
         }
     } else {
         __syncthreads();

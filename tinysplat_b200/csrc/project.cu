@@ -5,10 +5,6 @@
 #include "ts_binning.cuh"
 #include "ts_peer.cuh"
 
-#ifndef TS_PEER_WAIT_READ
-#define TS_PEER_WAIT_READ 0
-#endif
-
 namespace ts {
 
 constexpr int kProjThreads = 256;
@@ -512,11 +508,7 @@ project_bwd_views_kernel(int n_views, int N, const float* __restrict__ means,
                 if (d_logits.p[r]) bulk_s2g(reinterpret_cast<float*>(d_logits.p[r]) + item0, s_buf + 10 * TH, TH * 4);
             }
             bulk_commit();
-#if TS_PEER_WAIT_READ
-            bulk_wait_read0();
-#else
             bulk_wait0();
-#endif
         }
         return;
     }

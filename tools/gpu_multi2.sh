@@ -6,10 +6,12 @@ TAG="${TAG:-r2i}"; NG="${NG:-2}"; PORT=29700
 mkdir -p gpurun_out
 run() { timeout ${TMO:-240} python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port $((PORT++)) "$@"; }
 if [ "${DPCHECK:-1}" = "1" ]; then
-  run tools/dp_check.py --steps 20 > gpurun_out/${TAG}_dp_check_${NG}gpu.json 2> gpurun_out/${TAG}_dp_check_${NG}gpu.err
+  run tools/dp_check.py --steps ${DPSTEPS:-20} > gpurun_out/${TAG}_dp_check_${NG}gpu.json 2> gpurun_out/${TAG}_dp_check_${NG}gpu.err
   tail -c 700 gpurun_out/${TAG}_dp_check_${NG}gpu.json; tail -3 gpurun_out/${TAG}_dp_check_${NG}gpu.err
-  run tools/dp_check.py --steps 5 --gaussians 777777 > gpurun_out/${TAG}_dp_check_${NG}gpu_ragged.json 2> gpurun_out/${TAG}_dp_check_${NG}gpu_ragged.err
-  tail -c 400 gpurun_out/${TAG}_dp_check_${NG}gpu_ragged.json; tail -3 gpurun_out/${TAG}_dp_check_${NG}gpu_ragged.err
+  if [ "${RAGGED:-1}" = "1" ]; then
+    run tools/dp_check.py --steps 5 --gaussians 777777 > gpurun_out/${TAG}_dp_check_${NG}gpu_ragged.json 2> gpurun_out/${TAG}_dp_check_${NG}gpu_ragged.err
+    tail -c 400 gpurun_out/${TAG}_dp_check_${NG}gpu_ragged.json; tail -3 gpurun_out/${TAG}_dp_check_${NG}gpu_ragged.err
+  fi
 fi
 for c in ${CHUNKS:-4 1 2}; do
   TINYSPLAT_B200_PEER_CHUNKS=$c run bench.py --gpus $NG --steps 30 --warmup 5 --grad-exchange peer --no-extras --sustained-s 0 \
