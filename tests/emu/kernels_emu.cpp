@@ -366,7 +366,9 @@ int emu_peer_exchange(int world, int N, int Ns, int K, int deg, int W, int H, co
         cams[r].assign((size_t)world * 32 + 4, -777.f);
         pgeo.p[r] = align16(geo[r]); prgb.p[r] = align16(rgb[r]); pcams.p[r] = align16(cams[r]);
     }
-    const int pgrid = N > 0 ? (N + ts::kPushThreads - 1) / ts::kPushThreads : 1;
+    // persistent grid: fewer CTAs than 256-row blocks, so that every CTA iterates and reuses both of its buffers
+    const int pblocks = (N + ts::kPushRows - 1) / ts::kPushRows;
+    const int pgrid = pblocks > 3 ? (pblocks + 2) / 3 : 1;
     for (int r = 0; r < world; ++r) {
         int rc = ts_emu::launch(dim3(pgrid), ts::kPushThreads, [&]() {
             ts::dp_push_kernel(N, Ns, Npad, world, r, radii_all + (size_t)r * N, mask_all + (size_t)r * N,

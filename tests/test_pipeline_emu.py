@@ -202,7 +202,8 @@ def test_packed_exchange_shard_backward_on_the_emulator(emu):
         assert _rel(out[k], torch.from_numpy(want)) < 2e-4, k
 
 
-@pytest.mark.parametrize("world,n,Ns", [(2, 300, 152), (3, 700, 256), (4, 332, 84), (4, 100, 64), (1, 200, 200)])
+@pytest.mark.parametrize("world,n,Ns", [(2, 300, 152), (3, 700, 256), (4, 332, 84), (4, 100, 64), (1, 200, 200),
+                                         (2, 2048, 1024)])     # 8 full blocks on 3 persistent CTAs: both buffers reused
 def test_peer_memory_exchange_on_the_emulator(emu, world, n, Ns):
     """The peer-memory gradient exchange (csrc/peer.cu) with `world` ranks simulated in one address
     space: ts_dp_push of every rank writes geometry rows to the owners and colour cotangents + cameras

@@ -23,93 +23,120 @@
 
 namespace ts {
 
-constexpr int kPushThreads = 256;
+constexpr int kPushThreads = 128;      // threads per CTA
+constexpr int kPushRows = 256;         // rows per block of work (two per thread): one owner, one set of bulk stores
+constexpr int kPushCtasPerSm = 4;      // resident footprint of the push grid: 512 threads, 44 KB of shared memory per SM
 
+// Persistent: a grid of at most (#SMs x kPushCtasPerSm) CTAs walks the 256-row blocks.  The kernel is
+// NVLink-bound and its CTAs spend their life waiting for remote stores; a grid that fills the SMs with
+// such waiters (the first version: 8 x 256 threads per SM) keeps the kernels of the other streams —
+// the shard backward of the PREVIOUS piece — off the machine, and the pipeline of ts_dp_exchange_peer
+// degenerates into a sequence.  Here a CTA keeps its stores in flight across iterations (it waits only
+// until the copy engine has READ the shared buffer before refilling it, and for completion once, at the end).
 __global__ void __launch_bounds__(kPushThreads)
 dp_push_kernel(int N, int Ns, int Npad, int world, int rank, const int32_t* __restrict__ radii,
                const uint8_t* __restrict__ clamp_mask, const float4* __restrict__ recs,
                const float4* __restrict__ grads, const float* __restrict__ cam_row, PeerPtrs geo,
                PeerPtrs rgb, PeerPtrs cams, float2* __restrict__ v_xys) {
-    __shared__ __align__(128) float4 s_geo[kPushThreads * 2];     // the block's geometry rows, 8 KB
-    __shared__ __align__(128) float s_rgb[kPushThreads * 3];      // the block's colour rows, 3 KB
+    __shared__ __align__(128) float4 s_geo[2][kPushRows * 2];     // the block's geometry rows, 2 x 8 KB
+    __shared__ __align__(128) float s_rgb[2][kPushRows * 3];      // the block's colour rows, 2 x 3 KB
     const int tid = threadIdx.x;
-    const int item0 = blockIdx.x * kPushThreads;
-    const int i = item0 + tid;
-    float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0, g2 = g0;
-    if (i < N) {
-        const bool live = __ldg(radii + i) > 0;     // culled in this view: an exact zero row
-        if (live) {
-            g0 = __ldg(grads + 3 * (size_t)i);
-            g1 = __ldg(grads + 3 * (size_t)i + 1);
-            g2 = __ldg(grads + 3 * (size_t)i + 2);
-            if (clamp_mask) {                       // SH clamp(rgb + 0.5, min=0) [REF rasterize.py:39]
-                const unsigned m = clamp_mask[i];
-                if (!(m & 1u)) g2.x = 0.f;
-                if (!(m & 2u)) g2.y = 0.f;
-                if (!(m & 4u)) g2.z = 0.f;
-            }
-        }
-        if (v_xys) {                                // this view's d loss / d xy (densification statistic)
-            float2 v = make_float2(0.f, 0.f);
-            if (live) {
-                const float4 q1 = __ldg(recs + 3 * (size_t)i + 1);   // {.5 log2e a, log2e b, .5 log2e c, opacity}
-                const float a = q1.x * (2.f / kLog2e), b = q1.y * (1.f / kLog2e), c = q1.z * (2.f / kLog2e);
-                v = make_float2(a * g0.x + b * g0.y, b * g0.x + c * g0.y);
-            }
-            v_xys[i] = v;
-        }
-    }
-    s_geo[2 * tid] = g0;
-    s_geo[2 * tid + 1] = make_float4(g1.x, g1.y, g2.w, 0.f);
-    s_rgb[3 * tid] = g2.x; s_rgb[3 * tid + 1] = g2.y; s_rgb[3 * tid + 2] = g2.z;
-    const int nvalid = min(kPushThreads, N - item0);
-    const size_t rgb_off = (size_t)rank * Npad * 3 + (size_t)item0 * 3;      // floats, in every rank's rgb buffer
-    const int owner0 = item0 / Ns;
-    // A full block whose rows have ONE owner (always, when shard_rows is a multiple of 256) ships as
-    // TMA bulk stores: one 8 KB copy of geometry rows to the owner, one 3 KB copy of colour rows per
-    // rank, issued by one thread — the copy engine generates the NVLink traffic, not 10 stores per lane.
-    const bool bulk = nvalid == kPushThreads && owner0 == (item0 + kPushThreads - 1) / Ns;
-    if (bulk) {
-        fence_proxy_async();        // generic-proxy smem writes -> visible to the copy engine
-        __syncthreads();
-        if (tid == 0) {
-            float4* gdst = reinterpret_cast<float4*>(geo.p[owner0]) + ((size_t)rank * Ns + (item0 - owner0 * Ns)) * 2;
-            bulk_s2g(gdst, s_geo, kPushThreads * 32);
-            for (int d = 0; d < world; ++d) {       // start at the next rank: spreads the links
-                const int r = (rank + 1 + d) % world;
-                bulk_s2g(reinterpret_cast<float*>(rgb.p[r]) + rgb_off, s_rgb, kPushThreads * 12);
-            }
-            bulk_commit();
-            bulk_wait0();           // performed, not just read: the flag barrier that follows publishes them
-        }
-    } else {
-        __syncthreads();
-        if (i < N) {
-            const int owner = i / Ns, il = i - owner * Ns;
-            float4* dst = reinterpret_cast<float4*>(geo.p[owner]) + ((size_t)rank * Ns + il) * 2;
-            dst[0] = s_geo[2 * tid];
-            dst[1] = s_geo[2 * tid + 1];
-        }
-        const int nfl = nvalid * 3;
-        const int nv4 = nfl >> 2;
-        for (int idx = tid; idx < nv4 * world; idx += kPushThreads) {
-            const int d = idx / nv4, k = idx - d * nv4;
-            const int r = (rank + 1 + d) % world;
-            reinterpret_cast<float4*>(reinterpret_cast<float*>(rgb.p[r]) + rgb_off)[k] = reinterpret_cast<const float4*>(s_rgb)[k];
-        }
-        const int ntail = nfl - (nv4 << 2);
-        for (int idx = tid; idx < ntail * world; idx += kPushThreads) {
-            const int d = idx / ntail, k = (nv4 << 2) + idx - d * ntail;
-            const int r = (rank + 1 + d) % world;
-            (reinterpret_cast<float*>(rgb.p[r]) + rgb_off)[k] = s_rgb[k];
-        }
-    }
     if (blockIdx.x == 0) {                          // this view's camera -> every rank's cams[rank]
         for (int idx = tid; idx < kCamRowFloats * world; idx += kPushThreads) {
             const int r = idx / kCamRowFloats, k = idx - r * kCamRowFloats;
             (reinterpret_cast<float*>(cams.p[r]) + (size_t)rank * kCamRowFloats)[k] = __ldg(cam_row + k);
         }
     }
+    const int nblocks = (N + kPushRows - 1) / kPushRows;
+    int it = 0;
+    for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const int item0 = blk * kPushRows;
+        // the bulk stores issued two iterations ago read this buffer: wait until at most ONE group
+        // (the previous iteration's) is still reading
+        if (it >= 2) {
+            if (tid == 0) bulk_wait_read1();
+            __syncthreads();
+        }
+#pragma unroll
+        for (int h = 0; h < kPushRows / kPushThreads; ++h) {
+            const int t = h * kPushThreads + tid;
+            const int i = item0 + t;
+            float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0, g2 = g0;
+            if (i < N) {
+                const bool live = __ldg(radii + i) > 0;     // culled in this view: an exact zero row
+                if (live) {
+                    g0 = __ldg(grads + 3 * (size_t)i);
+                    g1 = __ldg(grads + 3 * (size_t)i + 1);
+                    g2 = __ldg(grads + 3 * (size_t)i + 2);
+                    if (clamp_mask) {                       // SH clamp(rgb + 0.5, min=0) [REF rasterize.py:39]
+                        const unsigned m = clamp_mask[i];
+                        if (!(m & 1u)) g2.x = 0.f;
+                        if (!(m & 2u)) g2.y = 0.f;
+                        if (!(m & 4u)) g2.z = 0.f;
+                    }
+                }
+                if (v_xys) {                                // this view's d loss / d xy (densification statistic)
+                    float2 v = make_float2(0.f, 0.f);
+                    if (live) {
+                        const float4 q1 = __ldg(recs + 3 * (size_t)i + 1);   // {.5 log2e a, log2e b, .5 log2e c, opacity}
+                        const float a = q1.x * (2.f / kLog2e), b = q1.y * (1.f / kLog2e), c = q1.z * (2.f / kLog2e);
+                        v = make_float2(a * g0.x + b * g0.y, b * g0.x + c * g0.y);
+                    }
+                    v_xys[i] = v;
+                }
+            }
+            s_geo[buf][2 * t] = g0;
+            s_geo[buf][2 * t + 1] = make_float4(g1.x, g1.y, g2.w, 0.f);
+            s_rgb[buf][3 * t] = g2.x; s_rgb[buf][3 * t + 1] = g2.y; s_rgb[buf][3 * t + 2] = g2.z;
+        }
+        const int nvalid = min(kPushRows, N - item0);
+        const size_t rgb_off = (size_t)rank * Npad * 3 + (size_t)item0 * 3;      // floats, in every rank's rgb buffer
+        const int owner0 = item0 / Ns;
+        // A full block whose rows have ONE owner (always, when shard_rows is a multiple of 256) ships as
+        // TMA bulk stores: one 8 KB copy of geometry rows to the owner, one 3 KB copy of colour rows per
+        // rank, issued by one thread — the copy engine generates the NVLink traffic, not 10 stores per lane.
+        const bool bulk = nvalid == kPushRows && owner0 == (item0 + kPushRows - 1) / Ns;
+        if (bulk) {
+            fence_proxy_async();        // generic-proxy smem writes -> visible to the copy engine
+            __syncthreads();
+            if (tid == 0) {
+                float4* gdst = reinterpret_cast<float4*>(geo.p[owner0]) + ((size_t)rank * Ns + (item0 - owner0 * Ns)) * 2;
+                bulk_s2g(gdst, s_geo[buf], kPushRows * 32);
+                for (int d = 0; d < world; ++d) {       // start at the next rank: spreads the links
+                    const int r = (rank + 1 + d) % world;
+                    bulk_s2g(reinterpret_cast<float*>(rgb.p[r]) + rgb_off, s_rgb[buf], kPushRows * 12);
+                }
+            }
+            if (tid == 0) bulk_commit();                // one group per iteration (empty groups complete at once)
+        } else {
+            __syncthreads();
+            for (int t = tid; t < nvalid; t += kPushThreads) {
+                const int i = item0 + t;
+                const int owner = i / Ns, il = i - owner * Ns;
+                float4* dst = reinterpret_cast<float4*>(geo.p[owner]) + ((size_t)rank * Ns + il) * 2;
+                dst[0] = s_geo[buf][2 * t];
+                dst[1] = s_geo[buf][2 * t + 1];
+            }
+            const int nfl = nvalid * 3;
+            const int nv4 = nfl >> 2;
+            for (int idx = tid; idx < nv4 * world; idx += kPushThreads) {
+                const int d = idx / nv4, k = idx - d * nv4;
+                const int r = (rank + 1 + d) % world;
+                reinterpret_cast<float4*>(reinterpret_cast<float*>(rgb.p[r]) + rgb_off)[k] = reinterpret_cast<const float4*>(s_rgb[buf])[k];
+            }
+            const int ntail = nfl - (nv4 << 2);
+            for (int idx = tid; idx < ntail * world; idx += kPushThreads) {
+                const int d = idx / ntail, k = (nv4 << 2) + idx - d * ntail;
+                const int r = (rank + 1 + d) % world;
+                (reinterpret_cast<float*>(rgb.p[r]) + rgb_off)[k] = s_rgb[buf][k];
+            }
+            if (tid == 0) bulk_commit();
+            __syncthreads();            // the generic stores above read the buffer: done before it is refilled
+        }
+    }
+    // performed, not just read: the flag signal that follows the kernel publishes them
+    if (tid == 0) bulk_wait0();
 }
 
 // Flags live one per 128-byte line: flags[slot][source rank][32 words].
@@ -213,7 +240,11 @@ int ts_dp_push(int N, int shard_rows, int padded_rows, int world, int rank, cons
     if (N > 0 && (!radii || !recs || !grads)) return TS_ERR_INVALID;
     if (N > 0 && (!ts::aligned16(recs) || !ts::aligned16(grads) || (v_xys && (reinterpret_cast<uintptr_t>(v_xys) & 7u))))
         return TS_ERR_ALIGN;
-    const int grid = N > 0 ? (N + ts::kPushThreads - 1) / ts::kPushThreads : 1;   // block 0 always ships the camera
+    int dev = 0, sms = 148;
+    TS_CHECK_CUDA(cudaGetDevice(&dev), "ts_dp_push/device");
+    TS_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev), "ts_dp_push/attr");
+    const int nblocks = (N + ts::kPushRows - 1) / ts::kPushRows;
+    const int grid = max(1, min(nblocks, sms * ts::kPushCtasPerSm));               // block 0 always ships the camera
     ts::dp_push_kernel<<<grid, ts::kPushThreads, 0, (cudaStream_t)stream>>>(
         N, shard_rows, padded_rows, world, rank, radii, clamp_mask, (const float4*)recs, (const float4*)grads,
         cam_row, geo, rgb, cams, (float2*)v_xys);

@@ -148,6 +148,7 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
 __device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, unsigned bytes) { memcpy(gmem_dst, smem_src, bytes); }
 __device__ __forceinline__ void bulk_commit() {}
 __device__ __forceinline__ void bulk_wait_read0() {}
+__device__ __forceinline__ void bulk_wait_read1() {}
 __device__ __forceinline__ void bulk_wait0() {}
 #else
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -205,6 +206,8 @@ __device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, u
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// at most one bulk group of this thread may still be reading its shared-memory source
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 // all bulk groups of this thread have COMPLETED (writes performed), not merely read their source
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
