@@ -314,6 +314,10 @@ TS_API int ts_peer_barrier_slots(void);
  * seg_offsets_host[11]: byte offsets of the segments {flags, err, cams, geo, rgb, g_rest, g_dc, g_means,
  * g_scales, g_quats, g_logit} inside an allocation (tinysplat_b200/parallel.py PeerLayout).  The host
  * side is pure launch logic; issuing it from native code instead of Python keeps it off the critical path. */
+/* Debug timeline of ts_dp_exchange_peer: enable, run, synchronize the device, read "label ms" lines
+ * (ms since the start of the last exchange; events recorded between the launches on each stream). */
+TS_API int ts_dp_exchange_timeline(int enable);
+TS_API int ts_dp_exchange_timeline_read(char* buf, int buf_bytes);
 TS_API int ts_dp_exchange_peer(int N, int K, int degree, int world, int rank, int n_pieces,
                                const int32_t* piece_plan_host, int padded_rows, const int32_t* radii,
                                const uint8_t* clamp_mask /*or NULL*/, const float* recs /*[16B]*/,

@@ -57,6 +57,8 @@ _SIGNATURES = {
     "ts_dp_push": ([_i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p], C.c_int),
     "ts_peer_barrier": ([_i, _i, _p, _i, C.c_uint32, _p, C.c_double, _i, _p], C.c_int),
     "ts_peer_barrier_slots": ([], C.c_int),
+    "ts_dp_exchange_timeline": ([_i], C.c_int),
+    "ts_dp_exchange_timeline_read": ([C.c_char_p, _i], C.c_int),
     "ts_dp_exchange_peer": ([_i, _i, _i, _i, _i, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _f,
                              C.c_uint32, C.c_double, _p, _p, _p, _p], C.c_int),
     "ts_peer_max_ranks": ([], C.c_int),

@@ -18,6 +18,7 @@
 // Kernels here: ts_dp_push (cleans the rows like ts_dp_prepare and pushes them with coalesced
 // 128-bit stores to peer-mapped addresses), ts_peer_barrier (system-scope release/acquire flags in
 // peer memory).  Peer buffers are plain cudaMalloc allocations shared through CUDA IPC handles.
+#include <cstdio>
 #include "ts_common.cuh"
 #include "ts_peer.cuh"
 
@@ -48,9 +49,13 @@ dp_push_kernel(int N, int Ns, int Npad, int world, int rank, const int32_t* __re
         }
     }
     const int nblocks = (N + kPushRows - 1) / kPushRows;
+    // every rank starts with the blocks its NEXT neighbour owns: at any moment the ranks' geometry rows
+    // go to different owners (in plain block order all of them would hit owner 0, then owner 1, ...)
+    const int rot = (int)(((long long)((rank + 1) % world) * Ns) / kPushRows) % max(nblocks, 1);
     int it = 0;
-    for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x, ++it) {
+    for (int b0 = blockIdx.x; b0 < nblocks; b0 += gridDim.x, ++it) {
         const int buf = it & 1;
+        const int blk = b0 + rot < nblocks ? b0 + rot : b0 + rot - nblocks;
         const int item0 = blk * kPushRows;
         // the bulk stores issued two iterations ago read this buffer: wait until at most ONE group
         // (the previous iteration's) is still reading
@@ -284,6 +289,27 @@ struct EventPool {          // per device; events are reused round-robin (disabl
 };
 EventPool g_pools[16];
 
+// Optional timeline of one exchange (ts_dp_exchange_timeline): timing events recorded between the
+// launches on each stream; read back by ts_dp_exchange_timeline_read after a device synchronize.
+struct Timeline {
+    static constexpr int kMax = 64;
+    bool on = false, ready = false;
+    int n = 0;
+    cudaEvent_t ev[kMax];
+    char label[kMax][24];
+};
+Timeline g_tl;
+
+void tl_mark(cudaStream_t st, const char* what, int piece) {
+    if (!g_tl.on || g_tl.n >= Timeline::kMax) return;
+    if (!g_tl.ready) {
+        for (int i = 0; i < Timeline::kMax; ++i) cudaEventCreate(&g_tl.ev[i]);
+        g_tl.ready = true;
+    }
+    snprintf(g_tl.label[g_tl.n], sizeof(g_tl.label[0]), "%s%d", what, piece);
+    cudaEventRecord(g_tl.ev[g_tl.n++], st);
+}
+
 cudaEvent_t pool_event(int dev) {
     EventPool& P = g_pools[dev & 15];
     if (!P.ready) {
@@ -295,6 +321,24 @@ cudaEvent_t pool_event(int dev) {
     return e;
 }
 }  // namespace
+
+// Debug: ts_dp_exchange_timeline(1) makes every following ts_dp_exchange_peer record timing events
+// between its launches; after a device synchronize ts_dp_exchange_timeline_read returns the number of
+// marks of the LAST exchange and writes "label ms-since-start" lines into buf.
+int ts_dp_exchange_timeline(int enable) { g_tl.on = enable != 0; return TS_OK; }
+int ts_dp_exchange_timeline_read(char* buf, int buf_bytes) {
+    if (!buf || buf_bytes <= 0) return TS_ERR_INVALID;
+    int used = 0;
+    buf[0] = 0;
+    for (int i = 1; i < g_tl.n; ++i) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, g_tl.ev[0], g_tl.ev[i]) != cudaSuccess) { cudaGetLastError(); continue; }
+        int w = snprintf(buf + used, (size_t)(buf_bytes - used), "%s %.4f\n", g_tl.label[i], ms);
+        if (w < 0 || w >= buf_bytes - used) break;
+        used += w;
+    }
+    return g_tl.n;
+}
 
 int ts_dp_exchange_peer(int N, int K, int degree, int world, int rank, int n_pieces, const int32_t* piece_plan_host,
                         int padded_rows, const int32_t* radii, const uint8_t* clamp_mask, const float* recs,
@@ -322,6 +366,8 @@ int ts_dp_exchange_peer(int N, int K, int degree, int world, int rank, int n_pie
     const float* cams_local = (const float*)seg(rank, SEG_CAMS, 0);
     const int R = (K - 1) * 3;
     int rc;
+    g_tl.n = 0;
+    tl_mark(sm, "start", 0);
     // whoever read last step's gradients (views of my segment) on the main stream is done
     cudaEvent_t e0 = pool_event(dev);
     TS_CHECK_CUDA(cudaEventRecord(e0, sm), "ts_dp_exchange_peer/event");
@@ -346,6 +392,7 @@ int ts_dp_exchange_peer(int N, int K, int degree, int world, int rank, int n_pie
                         recs + 12 * r0, grads + 12 * r0, cam_row, t_geo, t_rgb, t_cams, v_xys ? v_xys + 2 * r0 : nullptr,
                         main_stream);
         if (rc != TS_OK) return rc;
+        tl_mark(sm, "pushed", c);
         rc = ts_peer_barrier(world, rank, t_flags, c, epoch, err, timeout_s, 1, main_stream);
         if (rc != TS_OK) return rc;
         // side: every rank's rows of this piece have landed here -> SH gradient of the piece (local)
@@ -353,11 +400,13 @@ int ts_dp_exchange_peer(int N, int K, int degree, int world, int rank, int n_pie
         if (rc != TS_OK) return rc;
         cudaEvent_t landed = pool_event(dev);
         TS_CHECK_CUDA(cudaEventRecord(landed, s1), "ts_dp_exchange_peer/event");
+        tl_mark(s1, "landed", c);
         rc = ts_sh_bwd_views_rgb(world, (int)n, degree, K, means3d + 3 * r0, cams_local,
                                  (const float*)seg(rank, SEG_RGB, 12 * r0), (int64_t)padded_rows * 3, out_scale,
                                  (float*)seg(rank, SEG_DC, 12 * r0), (float*)seg(rank, SEG_REST, 4 * (int64_t)R * r0),
                                  side_stream);
         if (rc != TS_OK) return rc;
+        tl_mark(s1, "sh_done", c);
         // side 2: projection-backward over all views for MY shard of the piece, stored into every rank
         const int64_t s0 = r0 + (int64_t)rank * ns_c;
         int64_t ns = (int64_t)(rank + 1) * ns_c < n ? ns_c : n - (int64_t)rank * ns_c;
@@ -373,6 +422,7 @@ int ts_dp_exchange_peer(int N, int K, int degree, int world, int rank, int n_pie
                                            opacity_logits ? opacity_logits + s0 : nullptr, out_scale, world,
                                            (rank + 1) % world, t_m, t_s, t_q, t_l, side2_stream);
             if (rc != TS_OK) return rc;
+            tl_mark(s2, "proj_done", c);
         }
     }
     // every shard's gradients have landed in my segment: final barrier on the side stream, then main joins
@@ -383,6 +433,7 @@ int ts_dp_exchange_peer(int N, int K, int degree, int world, int rank, int n_pie
     }
     rc = ts_peer_barrier(world, rank, t_flags, ts::kBarrierSlots - 1, epoch, err, timeout_s, 3, side_stream);
     if (rc != TS_OK) return rc;
+    tl_mark(s1, "all_landed", 0);
     if (s1 != sm) {
         cudaEvent_t e1 = pool_event(dev);
         TS_CHECK_CUDA(cudaEventRecord(e1, s1), "ts_dp_exchange_peer/event");

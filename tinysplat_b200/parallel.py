@@ -295,7 +295,8 @@ class PeerGradExchange:
         self.headroom = headroom
         self.timeout_s = timeout_s
         # pieces the rows are pushed in (the transfer of one overlaps the shard backward of the previous)
-        self.n_chunks = int(n_chunks if n_chunks is not None else os.environ.get("TINYSPLAT_B200_PEER_CHUNKS", "4"))
+        # (measured on 2 and 8 B200s: 1, 2 and 4 pieces are within 1 % of each other — profiles/README.md)
+        self.n_chunks = int(n_chunks if n_chunks is not None else os.environ.get("TINYSPLAT_B200_PEER_CHUNKS", "1"))
         self.layout: Optional[PeerLayout] = None
         self.device = None
         self._base = None            # my allocation
