@@ -339,14 +339,19 @@ class Arm:
         self.model.zero_grad()
 
     def one_step(self, i: int, gt: torch.Tensor):
-        """`e2e`: a training step as a user writes it — render, L1 (+depth) loss, backward."""
+        """`e2e`: a training step as a user writes it — render, L1 (+depth) loss, backward.  gt: the uint8
+        image as loaded from disk (tinysplat_b200.loss.l1_loss) or the float32 tensor the reference uploads."""
+        from tinysplat_b200.loss import l1_loss
         cam = view_for(i, self.rank, self.W, self.H)
         if self.fwd_only:
             with torch.no_grad():
                 img, ex = self.rast(cam, (self.W, self.H), self.deg)
             return img.mean()
         img, ex = self.rast(cam, (self.W, self.H), self.deg)
-        loss = (img - gt).abs().mean()
+        if gt.dtype == torch.uint8:
+            loss = l1_loss(img, gt)                      # fused: value + gradient in one pass, u8 / 255 in the kernel
+        else:
+            loss = (img - gt).abs().mean()               # the reference's expression [REF scripts/train.py:59]
         if self.depth_w:
             loss = loss + self.depth_w * ex["depth"].abs().mean()
         loss.backward()
@@ -409,15 +414,20 @@ def measure_value(arm: Arm, K: int, Wm: int, local: int, sample_clocks: bool):
             "M": rz.last_stats["num_intersects"], "max_per_tile": rz.last_stats["max_per_tile"]}
 
 
-def measure_e2e(arm: Arm, K: int):
+def measure_e2e(arm: Arm, K: int, gt_u8: bool = True):
     """End-to-end arm: host buffers in, loss out.  Every step copies ITS target image (pinned host ->
     device) and reads its loss back.  Like a training data loader, step i+1's image is prefetched on a
-    copy stream while step i renders; all copies happen inside the timed region."""
+    copy stream while step i renders; all copies happen inside the timed region.  gt_u8: the target
+    travels as the uint8 image it is stored as (6.2 MB at 1080p) and the fused L1 loss forms u8 / 255;
+    otherwise as the float32 tensor the reference uploads (24.9 MB) with the loss written in torch."""
     dev, H, W = arm.dev, arm.H, arm.W
     g = torch.Generator().manual_seed(100 + arm.rank)
-    gt_host = torch.rand(H, W, 3, generator=g).pin_memory()
+    if gt_u8:
+        gt_host = torch.randint(0, 256, (H, W, 3), generator=g, dtype=torch.uint8).pin_memory()
+    else:
+        gt_host = torch.rand(H, W, 3, generator=g).pin_memory()
     copy_stream = torch.cuda.Stream(device=dev)
-    gt_bufs = [torch.empty(H, W, 3, device=dev), torch.empty(H, W, 3, device=dev)]
+    gt_bufs = [torch.empty(H, W, 3, device=dev, dtype=gt_host.dtype) for _ in range(2)]
     copied = [torch.cuda.Event(), torch.cuda.Event()]      # H2D of buffer k finished
     consumed = [None, None]                                 # compute that read buffer k finished
     host_loss = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
@@ -462,7 +472,8 @@ def measure_e2e(arm: Arm, K: int):
     collect(0)
     collect(1)
     return {"value": arm.world * arm.P / (ms_e2e / K * 1e-3) / 1e6, "unit": UNIT,
-            "h2d_bytes_per_step": gt_host.numel() * 4 + 2 * 16 * 4,      # target image + view/proj matrices
+            "h2d_bytes_per_step": gt_host.numel() * gt_host.element_size() + 2 * 16 * 4,   # target image + view/proj matrices
+            "target": "uint8 image, fused L1 loss (tinysplat_b200.loss)" if gt_u8 else "float32 image, torch L1 loss",
             "d2h_bytes_per_step": 4 + 16,                                 # loss scalar + binning stats (4 x int32)
             "ms_per_step": ms_e2e / K}
 
@@ -554,6 +565,10 @@ def run_ours(args):
 
     main = measure_value(arm, K, Wm, local, sample_clocks=(rank == 0))
     e2e = measure_e2e(arm, K)
+    if not arm.fwd_only:
+        # the same step fed the way the reference feeds it (float32 image uploaded, loss written in torch)
+        ref_style = measure_e2e(arm, K, gt_u8=False)
+        e2e["float32_target_torch_loss"] = {k: ref_style[k] for k in ("value", "ms_per_step", "h2d_bytes_per_step")}
     sustained = None
     if world == 1 and args.sustained_s > 0:
         sustained = measure_sustained(arm, args.sustained_s, local)
@@ -571,7 +586,7 @@ def run_ours(args):
         try:
             a = Arm(DEFAULT_WORKLOAD, "reference", dev, rank, world)
             mv = measure_value(a, K, Wm, local, sample_clocks=False)
-            me = measure_e2e(a, K)
+            me = measure_e2e(a, K, gt_u8=False)          # fed the reference's way: float32 image, torch loss
             kt = kernel_table(mv["prof"], mv["ms_total"], K, N, mv["M"], P, 3, 16, (deg + 1) ** 2)
             dropin = {"what": "the reference adapter's own op sequence through the five gsplat symbols "
                               "(project_gaussians, sh.spherical_harmonics, rasterize_gaussians x2 + torch glue), "

@@ -232,6 +232,16 @@ TS_API uint32_t ts_debug_rowmask(const float* q0_host, const float* q1_host, int
  * keeps its transmittance through T * rcp(1 - 0)); the GPU tests assert it. */
 TS_API int ts_debug_approx(int n, const float* x, float* rcp_out, float* ex2_out, ts_stream_t stream);
 
+/* ---- fused L1 image loss, forward + gradient in one pass (csrc/loss.cu) --------
+ * loss[0] = loss_scale * sum_i |img[i] - target[i]|,  grad[i] = grad_scale * sign(img[i] - target[i])
+ * (grad may be NULL).  target: float32, or uint8 meaning value / 255 (target_is_u8).  work: a device
+ * buffer of ts_l1_loss_work_floats() floats, zeroed ONCE by the caller and then reusable by calls on
+ * the same stream.  Deterministic.  [REF scripts/train.py:58-59] */
+TS_API int ts_l1_loss_work_floats(void);
+TS_API int ts_l1_loss(int64_t n, const float* img /*[16B]*/, const void* target, int target_is_u8,
+                      float grad_scale, float loss_scale, float* grad /*[16B] or NULL*/, float* work,
+                      float* loss, ts_stream_t stream);
+
 /* ---- data-parallel gradient exchange in packed form -------------------------
  * Instead of all-reducing the finished parameter gradients (236 B per Gaussian at SH degree 3),
  * ranks exchange blend-backward's packed rows (48 B per view and Gaussian): every rank owns a

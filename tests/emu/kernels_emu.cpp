@@ -15,6 +15,7 @@
 #include "../../tinysplat_b200/csrc/adam.cu"
 #include "../../tinysplat_b200/csrc/ssim.cu"
 #include "../../tinysplat_b200/csrc/knn.cu"
+#include "../../tinysplat_b200/csrc/loss.cu"
 
 #include <vector>
 #include <climits>
@@ -492,6 +493,20 @@ int emu_ssim_bwd(int B, int C, int H, int W, const float* X, const int64_t* xs, 
         ts::ssim_bwd_kernel(C, H, W, X, Y, sx, sy, win, dmu, de11, de12, v_pc, v_X);
     });
 }
+
+// fused L1 loss: `blocks` CTAs grid-stride over the image, the last one to finish sums the partials
+int emu_l1_loss(long long n, const float* img, const void* target, int is_u8, float grad_scale, float loss_scale,
+                float* grad, float* work, float* loss, int blocks) {
+    unsigned int* counter = reinterpret_cast<unsigned int*>(work + ts::kLossMaxBlocks);
+    if (is_u8)
+        return ts_emu::launch(dim3(blocks), ts::kLossThreads, [=]() {
+            ts::l1_loss_kernel<uint8_t>((size_t)n, img, (const uint8_t*)target, grad_scale, loss_scale, grad, work, counter, loss);
+        });
+    return ts_emu::launch(dim3(blocks), ts::kLossThreads, [=]() {
+        ts::l1_loss_kernel<float>((size_t)n, img, (const float*)target, grad_scale, loss_scale, grad, work, counter, loss);
+    });
+}
+int emu_l1_loss_work_floats() { return ts::kLossMaxBlocks + 4; }
 
 int emu_knn_points(int P1, int P2, int K, const float* q, const float* ref, float* dists, int64_t* idx) {
     if (P1 == 0) return 0;

@@ -301,9 +301,12 @@ template <typename T>
 static inline T __ldg(const T* p) { return *p; }
 static inline float __fsub_rn(float a, float b) { return a - b; }
 static inline float __fmul_rn(float a, float b) { return a * b; }
+static inline float __fdiv_rn(float a, float b) { return a / b; }
+struct uchar4 { unsigned char x, y, z, w; };
 static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
 static inline float atomicAdd(float* p, float v) { float o = *p; *p = o + v; return o; }
 static inline int atomicAdd(int* p, int v) { int o = *p; *p = o + v; return o; }
+static inline unsigned atomicAdd(unsigned* p, unsigned v) { unsigned o = *p; *p = o + v; return o; }
 static inline void atomicAdd(float2* p, float2 v) { p->x += v.x; p->y += v.y; }
 static inline void atomicAdd(float4* p, float4 v) { p->x += v.x; p->y += v.y; p->z += v.z; p->w += v.w; }
 static inline unsigned long long atomicCAS(unsigned long long* p, unsigned long long cmp, unsigned long long v) {

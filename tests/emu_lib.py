@@ -47,6 +47,7 @@ def load():
     lib.emu_ssim_fwd.argtypes = [i, i, i, i, p, p, p, p, p, f, f, p, p, p, p]
     lib.emu_ssim_bwd.argtypes = [i, i, i, i, p, p, p, p, p, p, p, p, p, p]
     lib.emu_knn_points.argtypes = [i, i, i, p, p, p, p]
+    lib.emu_l1_loss.argtypes = [C.c_longlong, p, p, i, f, f, p, p, p, i]
     _lib = lib
     return lib
 

@@ -881,3 +881,25 @@ def test_tile_launch_order_does_not_change_the_result(lib, ch):
     assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
     for a, b in zip(res[0][2], res[1][2]):
         assert rel_err(a, b) < 1e-5
+
+
+@pytest.mark.parametrize("shape,u8", [((1080, 1920, 3), True), ((1080, 1920, 3), False), ((37, 21, 3), True), ((5,), False)])
+def test_fused_l1_loss_matches_torch(shape, u8):
+    """tinysplat_b200.loss.l1_loss (one pass: value + gradient; uint8 ground truth = value / 255) against
+    the reference's expression `(rendered - gt).abs().mean()` [REF scripts/train.py:58-59]."""
+    from tinysplat_b200.loss import l1_loss
+    g = torch.Generator().manual_seed(5)
+    img = torch.rand(*shape, generator=g).to(DEV).requires_grad_(True)
+    raw = torch.randint(0, 256, shape, generator=g, dtype=torch.uint8).to(DEV) if u8 else torch.rand(*shape, generator=g).to(DEV)
+    gt = raw / 255 if u8 else raw                       # what the reference uploads
+    want = (img - gt).abs().mean()
+    (want * 3.0).backward()
+    want_grad, img.grad = img.grad.clone(), None
+    for _ in range(2):                                  # twice: the kernel's block counter must reset itself
+        got = l1_loss(img, raw)
+        (got * 3.0).backward()
+        assert abs(got.item() - want.item()) < 1e-6
+        assert torch.equal(img.grad, want_grad)
+        img.grad = None
+    with torch.no_grad():
+        assert abs(l1_loss(img, raw).item() - want.item()) < 1e-6

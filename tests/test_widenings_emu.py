@@ -98,3 +98,28 @@ def test_knn_points_on_the_emulator_matches_exhaustive_search(emu, P1, P2, K):
     assert np.allclose(full.gather(1, torch.from_numpy(idx[:, :k])).numpy(), wd.numpy(), rtol=1e-5, atol=1e-6)
     if k < K:
         assert (idx[:, k:] == 0).all() and (d[:, k:] == 0).all()
+
+
+@pytest.mark.parametrize("n,blocks,u8", [(37 * 21 * 3, 3, False), (64 * 48 * 3, 5, True), (7, 1, True), (4096, 1, False)])
+def test_fused_l1_loss_on_the_emulator(emu, n, blocks, u8):
+    """csrc/loss.cu: mean |img - target| and its gradient in one pass, float32 or uint8 (/255) target,
+    ragged tail, several blocks with the last-block fixed-order sum, the counter left at zero."""
+    rng = np.random.default_rng(n)
+    img = rng.random(n, dtype=np.float32)
+    if u8:
+        raw = rng.integers(0, 256, size=n, dtype=np.uint8)
+        raw[: n // 3] = np.round(img[: n // 3] * 255).astype(np.uint8)       # some exact ties and near ties
+        tgt = raw.astype(np.float32) / np.float32(255)
+    else:
+        raw = rng.random(n, dtype=np.float32)
+        raw[::5] = img[::5]                                                   # exact zeros of the difference
+        tgt = raw
+    grad = np.full(n, 7.0, dtype=np.float32)
+    work = np.zeros(emu.emu_l1_loss_work_floats(), dtype=np.float32)
+    loss = np.zeros(1, dtype=np.float32)
+    for _ in range(2):      # twice: the counter must have been reset
+        assert emu.emu_l1_loss(n, emu_lib.ptr(img), emu_lib.ptr(raw), int(u8), 1.0 / n, 1.0 / n, emu_lib.ptr(grad),
+                               emu_lib.ptr(work), emu_lib.ptr(loss), blocks) == 0
+        d = img.astype(np.float64) - tgt.astype(np.float64)
+        assert abs(loss[0] - np.abs(d).mean()) < 1e-6
+        assert np.array_equal(grad, (np.sign(img - tgt) * np.float32(1.0 / n)).astype(np.float32))

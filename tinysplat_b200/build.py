@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtinysplat_b200.so")
-SOURCES = ["capi.cu", "project.cu", "sh.cu", "binning.cu", "blend.cu", "blend_group.cu", "peer.cu", "adam.cu", "ssim.cu", "knn.cu"]
+SOURCES = ["capi.cu", "project.cu", "sh.cu", "binning.cu", "blend.cu", "blend_group.cu", "peer.cu", "adam.cu", "ssim.cu", "knn.cu", "loss.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-fvisibility=hidden",
          "-Xptxas", "-v"]
