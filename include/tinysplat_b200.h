@@ -45,7 +45,8 @@ enum ts_flags {
     TS_PROJ_OPACITY_LOGIT = 8,/* forward pack+count: `opacity` holds logits: sigmoid() inside */
     TS_SH_DIRS_FROM_MEANS = 1,/* `dirs` holds means3d; dir = mean - viewmat[:3,3] */
     TS_SH_OFFSET_CLAMP = 2,   /* colour = max(sh + 0.5, 0); mask of passing channels saved */
-    TS_BIN_OPACITY_LOGIT = 1  /* `opacity` holds logits: sigmoid() inside */
+    TS_BIN_OPACITY_LOGIT = 1, /* `opacity` holds logits: sigmoid() inside */
+    TS_BIN_PACK_ONLY = 2      /* ts_bin_count: only pack the records (the caller reuses tile lists it already has) */
 };
 
 /* Library version (major*10000 + minor*100 + patch) and last CUDA error text. */

@@ -50,8 +50,9 @@ bin_count_kernel(int N, const float2* __restrict__ xys, const int32_t* __restric
             if (CH > 3) q2.w = __ldg(colors + (size_t)CH * i + 3);
             recs[3 * (size_t)i + 2] = q2;
         }
-        if (r > 0) tile_rect(q0, (float)r, tbx, tby, cull, lox, loy, hix, hiy);
+        if (r > 0 && !(flags & TS_BIN_PACK_ONLY)) tile_rect(q0, (float)r, tbx, tby, cull, lox, loy, hix, hiy);
     }
+    if (flags & TS_BIN_PACK_ONLY) return;       // uniform: the tile lists of an earlier call are reused
     for_each_tile(lox, loy, hix, hiy, tbx, 0u, 0u,
                   [&](int tile, uint32_t, uint32_t) { atomicAdd(tile_counts + (size_t)tile * kCounterStride, 1); });
 }
@@ -478,10 +479,12 @@ int ts_bin_count(int N, int CH, const float* xys, const float* depths, const int
                  int32_t* tile_counts, ts_stream_t stream) {
     (void)depths; (void)img_height; (void)img_width;
     if (N < 0 || CH < 1 || CH > 4 || tiles_x <= 0 || tiles_y <= 0) return TS_ERR_INVALID;
-    if (!tile_counts) return TS_ERR_INVALID;
+    const bool pack_only = (flags & TS_BIN_PACK_ONLY) != 0;
+    if (!tile_counts && !pack_only) return TS_ERR_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
-    TS_CHECK_CUDA(cudaMemsetAsync(tile_counts, 0, sizeof(int32_t) * ts::kCounterStride * (size_t)tiles_x * tiles_y, st),
-                  "ts_bin_count/memset");
+    if (!pack_only)
+        TS_CHECK_CUDA(cudaMemsetAsync(tile_counts, 0, sizeof(int32_t) * ts::kCounterStride * (size_t)tiles_x * tiles_y, st),
+                      "ts_bin_count/memset");
     if (N == 0) return TS_OK;
     if (!xys || !radii || !conics || !opacity || !recs) return TS_ERR_INVALID;
     if (!ts::aligned16(recs) || (reinterpret_cast<uintptr_t>(xys) & 7u)) return TS_ERR_ALIGN;
