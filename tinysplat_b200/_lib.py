@@ -123,11 +123,15 @@ def check(status: int, what: str) -> None:
 
 # ---- optional per-call CUDA-event timing (bench.py's live per-kernel breakdown) ---------------
 _profile = None
+_profile_only = None
 
 
-def profile_start() -> None:
-    global _profile
+def profile_start(only=None) -> None:
+    """only: entry-point names to time (None = every call).  Timing a call costs two event records on
+    its stream; a bench that wants an undisturbed step times only the kernel it reports."""
+    global _profile, _profile_only
     _profile = []
+    _profile_only = None if only is None else frozenset(only)
 
 
 def profile_stop():
@@ -145,7 +149,7 @@ def call(name: str, *args) -> None:
     """Invoke C-ABI entry `name`; raise on a non-zero status.  Events go on the current stream,
     which is the stream every kernel is launched on."""
     fn = getattr(load(), name)
-    if _profile is None:
+    if _profile is None or (_profile_only is not None and name not in _profile_only):
         check(fn(*args), name)
         return
     s = torch.cuda.Event(enable_timing=True)
