@@ -152,6 +152,8 @@ class ClockSampler:
 # profiles/r2g_ncu_blend_fwd_bwd.txt (default workload, fused pipeline)
 NCU_TRAFFIC_SOURCE = ("constant from one `ncu --set full` capture of this command (profiles/), per launch; "
                       "not re-measured in this run")
+# sm__inst_issued.avg.pct_of_peak_sustained_active of the same capture: the blend kernels' real limiter
+NCU_ISSUE_PCT = {"ts_blend_bwd": 77.7, "ts_blend_fwd": 87.8}
 NCU_TRAFFIC = {
     "synthetic_1M_1080p": {
         "ts_blend_bwd": (184.47 + 22.49) * 1e6, "ts_blend_fwd": (62.70 + 19.58) * 1e6,
@@ -491,6 +493,46 @@ def measure_e2e(arm: Arm, K: int, gt_u8: bool = True):
             "ms_per_step": ms_e2e / K}
 
 
+def measure_train_step(dev, steps: int = 15):
+    """The whole training step of scripts/train.py at the default workload, built from this repo's pieces:
+    fused adapter, 0.8 L1 + 0.2 (1 - SSIM) with the fused losses, backward, FusedAdam over the six
+    parameter groups [REF scripts/train.py:54-100; model_gaussian.py:112-120].  Device-timed."""
+    from tinysplat_b200 import synthetic
+    from tinysplat_b200.loss import l1_loss
+    from tinysplat_b200.optim import FusedAdam
+    from tinysplat_b200.rasterizer import GaussianRasterizer, ParamModel
+    from tinysplat_b200.ssim import SSIM
+    N, W, H, deg, _, _ = WORKLOADS[DEFAULT_WORKLOAD]
+    names = ["means", "scales", "quats", "opacities", "colors_dc", "colors_rest"]
+    lrs = dict(means=0.00016, colors_dc=0.0025, colors_rest=0.000125, scales=0.005, quats=0.001, opacities=0.05)
+    model = ParamModel(synthetic.make_scene(N, W, H, seed=0), dev, deg)
+    params = {k: torch.nn.Parameter(getattr(model, k).detach()) for k in names}
+    for k, p in params.items():
+        setattr(model, k, p)
+    opt = FusedAdam([{"params": [params[k]], "lr": lrs[k], "name": k} for k in names])
+    ssim = SSIM(data_range=1.0, channel=3)
+    rast = GaussianRasterizer(model, None, dev, "fused")
+    gt_u8 = torch.randint(0, 256, (H, W, 3), generator=torch.Generator().manual_seed(3), dtype=torch.uint8).to(dev)
+    gt_chw = (gt_u8.float() / 255).permute(2, 0, 1)[None]
+
+    def step(i):
+        img, _ = rast(view_for(i, 0, W, H), None, deg)
+        loss = 0.8 * l1_loss(img, gt_u8) + 0.2 * (1 - ssim(img.permute(2, 0, 1)[None], gt_chw))
+        loss.backward()
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+
+    for i in range(4):
+        step(i)
+    ms, _, _ = timed(step, steps, 100, 1, dev)
+    ms /= steps
+    del model, params, opt, rast
+    torch.cuda.empty_cache()
+    return {"what": "render (fused adapter) + 0.8 L1 + 0.2 (1 - SSIM) (fused losses) + backward + FusedAdam, "
+                    "1M Gaussians / 1080p, device-resident ground truth",
+            "ms_per_step": ms, "value": W * H / (ms * 1e-3) / 1e6, "unit": UNIT, "steps": steps}
+
+
 def measure_sustained(arm: Arm, seconds: float, local: int):
     """The device-resident step looped for >= `seconds` of wall time with the NVML clock / power
     record: the burst-clock figure of the K-step region next to what the GPU holds under load."""
@@ -594,8 +636,12 @@ def run_ours(args):
     # ---- the rest of the default single-GPU line: drop-in surface, other workloads ------------
     default_line = (world == 1 and args.workload == DEFAULT_WORKLOAD and args.pipeline == "fused"
                     and not args.no_extras)
-    dropin, workloads = None, None
+    dropin, workloads, train_step = None, None, None
     if default_line:
+        try:
+            train_step = measure_train_step(dev)
+        except Exception as exc:
+            train_step = {"error": repr(exc)[:300]}
         try:
             a = Arm(DEFAULT_WORKLOAD, "reference", dev, rank, world)
             mv = measure_value(a, K, Wm, local, sample_clocks=False)
@@ -656,7 +702,9 @@ def run_ours(args):
                 "frac": a / peak, "traffic": traffic, "peak_source": peak_src,
                 "traffic_source": NCU_TRAFFIC_SOURCE if traffic else None,
                 "note": "blend kernels are fp32-issue/atomic bound, not HBM bound (DESIGN.md); "
-                        "streaming kernels listed in `kernels`"}
+                        "streaming kernels listed in `kernels`",
+                # what does bound it (one `ncu --set full` capture of this command, profiles/r2g_ncu_blend_fwd_bwd.txt)
+                "issue_slots_busy_pct_ncu": NCU_ISSUE_PCT.get(top) if args.pipeline == "fused" else None}
     # the best streaming (genuinely HBM-bound) kernel, for a roofline fraction that means something
     stream_names = [k for k in ("ts_sh_bwd", "ts_sh_fwd", "ts_project_bwd", "ts_project_fwd") if k in kern]
     best_stream = max(stream_names, key=lambda k: kern[k]["gbs"] or 0) if stream_names else None
@@ -717,6 +765,8 @@ def run_ours(args):
         line["dropin_e2e"] = dropin.get("e2e")
     if workloads is not None:
         line["workloads"] = workloads
+    if train_step is not None:
+        line["train_step"] = train_step
     if world == 1 and not args.no_cpu_baseline:
         try:
             v, desc, cores, sec = cpu_sample(args.workload, args.cpu_window, 8, 2)
