@@ -581,15 +581,7 @@ int ts_project_bwd(int N, const float* means3d, const float* scales, float glob_
         (v_xys_out && (reinterpret_cast<uintptr_t>(v_xys_out) & 7u)))
         return TS_ERR_ALIGN;
     int grid = (N + ts::kProjThreads - 1) / ts::kProjThreads;
-    // Occupancy cap (experiment, TS_PROJ_BWD_PAD_KB): unused dynamic shared memory limits the resident
-    // CTAs of this issue-bound kernel so that the DRAM-bound SH-backward on the side stream gets SM slots
-    // from the start instead of after it (the pair takes the sum of its parts otherwise).
-    static int pad_kb = -1;
-    if (pad_kb < 0) { const char* e = getenv("TS_PROJ_BWD_PAD_KB"); pad_kb = e ? atoi(e) : 0; }
-    if (pad_kb > 48)
-        TS_CHECK_CUDA(cudaFuncSetAttribute(ts::project_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           pad_kb * 1024), "ts_project_bwd/attr");
-    ts::project_bwd_kernel<<<grid, ts::kProjThreads, (size_t)pad_kb * 1024, (cudaStream_t)stream>>>(
+    ts::project_bwd_kernel<<<grid, ts::kProjThreads, 0, (cudaStream_t)stream>>>(
         N, means3d, scales, glob_scale, (const float4*)quats, viewmat, projmat, fx, fy, cx, cy,
         img_height, img_width, flags, radii, (const float2*)v_xys, v_depths, v_conics,
         (const float4*)packed_grads, opacity_logits, v_means3d, v_scales, (float4*)v_quats,
