@@ -233,6 +233,20 @@ TS_API uint32_t ts_debug_rowmask(const float* q0_host, const float* q1_host, int
  * keeps its transmittance through T * rcp(1 - 0)); the GPU tests assert it. */
 TS_API int ts_debug_approx(int n, const float* x, float* rcp_out, float* ex2_out, ts_stream_t stream);
 
+/* ---- K6 + K7 in one launch (fused pipeline, single GPU) -----------------------------------------
+ * ts_project_bwd (packed-gradient form, TS_PROJ_* flags as there) and ts_sh_bwd (view direction from
+ * the mean, colour cotangent = floats 8..10 of the packed row, optional clamp mask) for the same N
+ * Gaussians: every CTA builds the SH rows of its Gaussians in shared memory, sends them off as TMA bulk
+ * stores and runs the EWA algebra while they drain.  Same results as the two separate calls. */
+TS_API int ts_project_sh_bwd(int N, int degree, int K, const float* means3d /*[16B]*/,
+                             const float* scales /*[16B]*/, float glob_scale, const float* quats /*[16B]*/,
+                             const float* viewmat, const float* projmat, float fx, float fy, float cx,
+                             float cy, int img_height, int img_width, int flags, const int32_t* radii,
+                             const float* packed_grads /*[16B]*/, const float* opacity_logits /*or NULL*/,
+                             const uint8_t* clamp_mask /*or NULL*/, float* v_means3d, float* v_scales,
+                             float* v_quats, float* v_opacity_logits /*or NULL*/, float* v_xys_out /*or NULL*/,
+                             float* v_dc, float* v_rest, ts_stream_t stream);
+
 /* ---- fused L1 image loss, forward + gradient in one pass (csrc/loss.cu) --------
  * loss[0] = loss_scale * sum_i |img[i] - target[i]|,  grad[i] = grad_scale * sign(img[i] - target[i])
  * (grad may be NULL).  target: float32, or uint8 meaning value / 255 (target_is_u8).  work: a device

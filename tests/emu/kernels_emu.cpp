@@ -214,6 +214,19 @@ int sh_bwd_views_rgb_any(int n_views, int N, int K, const float* means, const fl
     });
 }
 
+template <int DEG>
+int project_sh_bwd_any(int grid, int N, int K, const float* means, const float* log_scales, const float* quats,
+                       const float* view, const float* fullproj, float fx, float fy, int W, int H, int flags,
+                       const int32_t* radii, const float* grads, const float* logits, const uint8_t* mask,
+                       float* v_means, float* v_scales, float* v_quats, float* v_logit, float* v_xys, float* v_dc,
+                       float* v_rest) {
+    return ts_emu::launch(dim3(grid), ts::kProjThreads, [=]() {
+        ts::project_sh_bwd_kernel<DEG>(N, K, means, log_scales, 1.0f, (const float4*)quats, view, fullproj, fx, fy,
+                                       W / 2.f, H / 2.f, H, W, flags, radii, (const float4*)grads, logits, mask, v_means,
+                                       v_scales, (float4*)v_quats, v_logit, (float2*)v_xys, v_dc, v_rest);
+    });
+}
+
 #define TS_EMU_BY_DEG(deg, fn, ...)             \
     switch (deg) {                              \
         case 0: return fn<0>(__VA_ARGS__);      \
@@ -229,7 +242,8 @@ extern "C" {
 
 // Mirrors _RenderFused.forward + backward.  All pointers are host pointers; outputs are written by
 // the kernels exactly as on the device.  v_rgb / v_depth may be NULL (no cotangent).
-// bwd_mode: 0 = first-generation blend-backward, 1 = grouped.  Returns 0, or -1 on an emulator deadlock.
+// bwd_mode bit 0: 0 = first-generation blend-backward, 1 = grouped; bit 1: K7 and K6 as two kernels instead of
+// the fused ts_project_sh_bwd kernel (the product default).  Returns 0, or -1 on an emulator deadlock.
 int emu_render_fused(int N, int K, int deg, int W, int H, const float* means, const float* log_scales,
                      const float* quats, const float* logits, const float* dc, const float* rest,
                      const float* view, const float* fullproj, float fx, float fy, const float* bg4, int cull,
@@ -301,8 +315,18 @@ int emu_render_fused(int N, int K, int deg, int W, int H, const float* means, co
     float* grads_p = (float*)(((uintptr_t)grads.data() + 15) & ~(uintptr_t)15);
     if (N == 0) return 0;
     rc = emu_blend_bwd(N, 4, H, W, tx, ty, offsets.data(), ids.data(), recs_p, bg4, final_T, ncon.data(), v_rgb, v_depth,
-                       1, nullptr, grads_p, bwd_mode);
+                       1, nullptr, grads_p, bwd_mode & 1);
     if (rc) return rc;
+    // K6 + K7 as one kernel (fused.py FUSED_TAIL)
+    if (!(bwd_mode & 2)) {
+        const int grid = (N + ts::kProjThreads - 1) / ts::kProjThreads;
+        auto run = [&]() -> int {
+            TS_EMU_BY_DEG(deg, project_sh_bwd_any, grid, N, K, means, log_scales, quats, view, fullproj, fx, fy, W, H,
+                          pflags | TS_PROJ_DEPTH_CH3, radii, grads_p, logits, mask.data(), v_means, v_scales, v_quats,
+                          v_logit, v_xys, v_dc, v_rest);
+        };
+        return run();
+    }
     // K7, K6
     {
         const bool bulk = K > 1 && ((K - 1) * 3 * 4 * ts::kShThreads) % 16 == 0;

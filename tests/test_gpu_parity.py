@@ -903,3 +903,29 @@ def test_fused_l1_loss_matches_torch(shape, u8):
         img.grad = None
     with torch.no_grad():
         assert abs(l1_loss(img, raw).item() - want.item()) < 1e-6
+
+
+def test_fused_backward_tail_equals_the_two_kernel_tail():
+    """ts_project_sh_bwd (projection-backward + SH-backward in one kernel, the single-GPU default) against
+    ts_project_bwd and ts_sh_bwd on two streams: the same arithmetic, so the same bits."""
+    from tinysplat_b200 import fused
+    from tinysplat_b200.rasterizer import GaussianRasterizer, ParamModel
+    W, H, N = 320, 200, 70001                      # a ragged last block
+    cam = synthetic.make_camera(W, H, yaw_deg=2.0)
+    sc = synthetic.make_scene(N, W, H, seed=21, sh_degree=3)
+    g = torch.Generator().manual_seed(4)
+    wi, wd = torch.rand(H, W, 3, generator=g).to(DEV), torch.rand(H, W, generator=g).to(DEV)
+    res = []
+    for deg in (3, 1):
+        for tail in (True, False):
+            fused.FUSED_TAIL = tail
+            try:
+                model = ParamModel(sc, DEV, 3)
+                img, ex = GaussianRasterizer(model, None, DEV, "fused")(cam, (W, H), deg)
+                ((img * wi).sum() + 0.1 * (ex["depth"] * wd).sum()).backward()
+                res.append([p.grad.clone() for p in model.parameters()] + [ex["xys"].grad.clone()])
+            finally:
+                fused.FUSED_TAIL = True
+        # blend-backward's float atomics reorder sums between the two runs: compare to their noise level
+        for a, b in zip(res[-2], res[-1]):
+            assert rel_err(a, b) < 1e-5

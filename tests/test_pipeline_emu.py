@@ -60,7 +60,7 @@ def _rel(a, b):
     return (a - b).abs().max().item() / max(b.abs().max().item(), 1e-30)
 
 
-@pytest.mark.parametrize("bwd_mode", [0, 1])
+@pytest.mark.parametrize("bwd_mode", [0, 1, 3])     # bit 0: grouped blend-backward; bit 1: K7 and K6 as two kernels
 @pytest.mark.parametrize("n,W,H,deg,sh_deg_stored", [(256, 128, 128, 3, 3), (400, 88, 56, 2, 3), (150, 48, 48, 0, 0)])
 def test_fused_pipeline_on_the_emulator_matches_the_oracle(emu, n, W, H, deg, sh_deg_stored, bwd_mode):
     cam = synthetic.make_camera(W, H, yaw_deg=3.0, shift=(0.05, 0.0, 0.0))

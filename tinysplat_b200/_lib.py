@@ -71,6 +71,8 @@ _SIGNATURES = {
     "ts_peer_ipc_close": ([_p], C.c_int),
     "ts_set_blend_mode": ([_i], C.c_int),
     "ts_get_blend_mode": ([], C.c_int),
+    "ts_project_sh_bwd": ([_i, _i, _i, _p, _p, _f, _p, _p, _p, _f, _f, _f, _f, _i, _i, _i, _p, _p, _p, _p,
+                           _p, _p, _p, _p, _p, _p, _p, _p], C.c_int),
     "ts_l1_loss_work_floats": ([], C.c_int),
     "ts_l1_loss": ([C.c_int64, _p, _p, _i, _f, _f, _p, _p, _p, _p], C.c_int),
     "ts_debug_rowmask": ([_p, _p, _i, _i], C.c_uint32),

@@ -3,6 +3,7 @@
 // Replaces gsplat.project_gaussians fwd/bwd  [REF tinysplat/splatting/rasterize.py:32,64-73].
 #include <cstdlib>
 #include "ts_common.cuh"
+#include "ts_sh_basis.cuh"
 #include "ts_binning.cuh"
 #include "ts_peer.cuh"
 
@@ -405,6 +406,128 @@ project_bwd_kernel(int N, const float* __restrict__ means, const float* __restri
     block_store<3, TH>(v_scales, s_buf + 3 * TH, item0, N);
 }
 
+// ---- K6 + K7 in one kernel (fused pipeline, single GPU) ------------------------------------------
+// Projection-backward is issue-bound (74 registers, ~1000 instructions per Gaussian), SH-backward is
+// DRAM-bound (192 B of coefficient gradient written per Gaussian).  As two kernels on two streams they
+// take the SUM of their times: projection-backward reaches the SMs first and its 3 CTAs per SM leave
+// room for one SH CTA (a priority stream or an occupancy cap did not help: profiles/README.md).  Here
+// every CTA does both for its 256 Gaussians: the EWA algebra, then the SH rows built in shared memory
+// leave as TMA bulk stores while other warps still compute — the copy engine and the issue slots overlap
+// inside the kernel instead of depending on the block scheduler.
+template <int DEG>
+__global__ void __launch_bounds__(kProjThreads)
+project_sh_bwd_kernel(int N, int K, const float* __restrict__ means, const float* __restrict__ scales,
+                      float gs, const float4* __restrict__ quats, const float* __restrict__ viewmat,
+                      const float* __restrict__ projmat, float fx, float fy, float cx, float cy, int H, int W,
+                      int flags, const int32_t* __restrict__ radii, const float4* __restrict__ packed,
+                      const float* __restrict__ opac_logits, const uint8_t* __restrict__ clamp_mask,
+                      float* __restrict__ v_means, float* __restrict__ v_scales, float4* __restrict__ v_quats,
+                      float* __restrict__ v_opac_logits, float2* __restrict__ v_xys_out,
+                      float* __restrict__ v_dc, float* __restrict__ v_rest) {
+    constexpr int TH = kProjThreads;
+    constexpr int NB = (DEG + 1) * (DEG + 1);
+    TS_DYN_SMEM(float, s_dyn, 128);
+    const int R = (K - 1) * 3;
+    float* s_rest = s_dyn;                       // [TH][R] dense, becomes v_rest rows
+    float* s_dc = s_rest + TH * R;               // [TH*3]
+    float* s_buf = s_dc + TH * 3;                // [TH*6]: means | scales in, their gradients out
+    const int item0 = blockIdx.x * TH;
+    const int tid = threadIdx.x;
+    const int n_valid = min(TH, N - item0);
+    block_load<3, TH>(means, s_buf, item0, N);
+    block_load<3, TH>(scales, s_buf + 3 * TH, item0, N);
+    __syncthreads();
+    const int i = item0 + tid;
+    const bool in = i < N;
+    float mu[3] = {0.f, 0.f, 1.f}, sc[3] = {1.f, 1.f, 1.f}, vcon[3] = {0.f, 0.f, 0.f};
+    float4 q = make_float4(1.f, 0.f, 0.f, 0.f);
+    float2 vxy = make_float2(0.f, 0.f);
+    bool ok = false;
+    if (in) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            mu[k] = s_buf[3 * tid + k];
+            sc[k] = s_buf[3 * TH + 3 * tid + k];
+        }
+        q = __ldg(quats + i);
+        ok = __ldg(radii + i) > 0;
+    }
+    const float qn = apply_activations(flags, sc, q);
+    __syncthreads();
+
+    // ---- K7: the SH rows of this Gaussian (colour cotangent = floats 8..10 of its packed row; a culled
+    // Gaussian's row is all zero, so its SH rows are zero as in sh_bwd_bulk_kernel)
+    if (in) {
+        float4 g2 = __ldg(packed + 3 * (size_t)i + 2);
+        if (clamp_mask) {                        // SH clamp(rgb + 0.5, min=0) [REF rasterize.py:39]
+            const unsigned m = clamp_mask[i];
+            if (!(m & 1u)) g2.x = 0.f;
+            if (!(m & 2u)) g2.y = 0.f;
+            if (!(m & 4u)) g2.z = 0.f;
+        }
+        float b[NB];
+        // view direction as the reference adapter forms it: mean - view-matrix translation column
+        sh_basis<DEG>(mu[0] - __ldg(viewmat + 3), mu[1] - __ldg(viewmat + 7), mu[2] - __ldg(viewmat + 11), b);
+        s_dc[3 * tid] = b[0] * g2.x; s_dc[3 * tid + 1] = b[0] * g2.y; s_dc[3 * tid + 2] = b[0] * g2.z;
+        float* c = s_rest + tid * R;
+#pragma unroll
+        for (int k = 1; k < NB; ++k) {
+            c[3 * (k - 1)] = b[k] * g2.x;
+            c[3 * (k - 1) + 1] = b[k] * g2.y;
+            c[3 * (k - 1) + 2] = b[k] * g2.z;
+        }
+        for (int k = (NB - 1) * 3; k < R; ++k) c[k] = 0.f;   // bases above the active degree
+    }
+    const bool bulk = n_valid == TH && R > 0 && ((size_t)TH * R * 4) % 16 == 0 &&
+                      aligned_dev16(v_rest + (size_t)item0 * R) && aligned_dev16(v_dc + (size_t)item0 * 3);
+    if (bulk) {
+        fence_proxy_async();          // generic-proxy smem writes -> visible to the copy engine
+        __syncthreads();
+        if (tid == 0) {               // the copies run while the block does the EWA algebra below
+            bulk_s2g(v_rest + (size_t)item0 * R, s_rest, TH * R * 4);
+            bulk_s2g(v_dc + (size_t)item0 * 3, s_dc, TH * 3 * 4);
+            bulk_commit();
+        }
+    } else {
+        __syncthreads();
+        float* gr = v_rest + (size_t)item0 * R;
+        for (int k = tid; k < n_valid * R; k += TH) gr[k] = s_rest[k];
+        float* gd = v_dc + (size_t)item0 * 3;
+        for (int k = tid; k < n_valid * 3; k += TH) gd[k] = s_dc[k];
+    }
+
+    // ---- K6: projection-backward of this Gaussian
+    float vmu[3] = {0.f, 0.f, 0.f}, vs[3] = {0.f, 0.f, 0.f};
+    float4 vq = make_float4(0.f, 0.f, 0.f, 0.f);
+    float vlogit = 0.f;
+    if (ok) {
+        ProjCam cam;
+        load_cam(viewmat, projmat, cam);
+        const float4 g0 = __ldg(packed + 3 * (size_t)i);
+        const float4 g1 = __ldg(packed + 3 * (size_t)i + 1);
+        float vdep_packed = 0.f, logit = 0.f;
+        if (flags & TS_PROJ_DEPTH_CH3) vdep_packed = __ldg(reinterpret_cast<const float*>(packed) + 12 * (size_t)i + 11);
+        if (opac_logits) logit = __ldg(opac_logits + i);
+        project_bwd_view(cam, mu, sc, gs, q, fx, fy, H, W, vxy, 0.f, vcon, true, g0, g1, vdep_packed,
+                         opac_logits != nullptr, logit, vmu, vs, vq, vlogit, vxy);
+        project_bwd_activations(flags, sc, q, qn, vs, vq);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        s_buf[3 * tid + k] = vmu[k];
+        s_buf[3 * TH + 3 * tid + k] = vs[k];
+    }
+    if (in) {
+        v_quats[i] = vq;
+        if (v_opac_logits) v_opac_logits[i] = vlogit;
+        if (v_xys_out) v_xys_out[i] = ok ? vxy : make_float2(0.f, 0.f);
+    }
+    __syncthreads();
+    block_store<3, TH>(v_means, s_buf, item0, N);
+    block_store<3, TH>(v_scales, s_buf + 3 * TH, item0, N);
+    if (bulk && tid == 0) bulk_wait_read0();     // shared memory must outlive the copy engine's reads
+}
+
 // ---- data-parallel shard backward ------------------------------------------------
 // One rank owns a SHARD of the Gaussians and receives, from every rank/view v, blend-backward's
 // packed gradient rows of that shard (packed[v * view_stride + 3 i .. +2], already cleaned by
@@ -587,6 +710,47 @@ int ts_project_bwd(int N, const float* means3d, const float* scales, float glob_
         (const float4*)packed_grads, opacity_logits, v_means3d, v_scales, (float4*)v_quats,
         v_opacity_logits, (float2*)v_xys_out);
     TS_CHECK_LAUNCH("ts_project_bwd");
+    return TS_OK;
+}
+
+int ts_project_sh_bwd(int N, int degree, int K, const float* means3d, const float* scales, float glob_scale,
+                      const float* quats, const float* viewmat, const float* projmat, float fx, float fy,
+                      float cx, float cy, int img_height, int img_width, int flags, const int32_t* radii,
+                      const float* packed_grads, const float* opacity_logits, const uint8_t* clamp_mask,
+                      float* v_means3d, float* v_scales, float* v_quats, float* v_opacity_logits,
+                      float* v_xys_out, float* v_dc, float* v_rest, ts_stream_t stream) {
+    if (N < 0 || img_height <= 0 || img_width <= 0 || degree < 0 || degree > 4 || K < (degree + 1) * (degree + 1) || K > 25)
+        return TS_ERR_INVALID;
+    if (N == 0) return TS_OK;
+    if (!means3d || !scales || !quats || !viewmat || !projmat || !radii || !packed_grads || !v_means3d || !v_scales ||
+        !v_quats || !v_dc || (K > 1 && !v_rest))
+        return TS_ERR_INVALID;
+    if (!ts::aligned16(means3d) || !ts::aligned16(scales) || !ts::aligned16(quats) || !ts::aligned16(packed_grads) ||
+        !ts::aligned16(v_means3d) || !ts::aligned16(v_scales) || !ts::aligned16(v_quats) ||
+        (v_xys_out && (reinterpret_cast<uintptr_t>(v_xys_out) & 7u)))
+        return TS_ERR_ALIGN;
+    const int grid = (N + ts::kProjThreads - 1) / ts::kProjThreads;
+    const size_t smem = sizeof(float) * ts::kProjThreads * ((size_t)(K - 1) * 3 + 3 + 6) + 16;
+    cudaStream_t st = (cudaStream_t)stream;
+#define TS_LAUNCH_PSB(D)                                                                                        \
+    do {                                                                                                        \
+        TS_CHECK_CUDA(cudaFuncSetAttribute(ts::project_sh_bwd_kernel<D>,                                        \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),             \
+                      "ts_project_sh_bwd/attr");                                                                \
+        ts::project_sh_bwd_kernel<D><<<grid, ts::kProjThreads, smem, st>>>(                                     \
+            N, K, means3d, scales, glob_scale, (const float4*)quats, viewmat, projmat, fx, fy, cx, cy,          \
+            img_height, img_width, flags, radii, (const float4*)packed_grads, opacity_logits, clamp_mask,       \
+            v_means3d, v_scales, (float4*)v_quats, v_opacity_logits, (float2*)v_xys_out, v_dc, v_rest);         \
+    } while (0)
+    switch (degree) {
+        case 0: TS_LAUNCH_PSB(0); break;
+        case 1: TS_LAUNCH_PSB(1); break;
+        case 2: TS_LAUNCH_PSB(2); break;
+        case 3: TS_LAUNCH_PSB(3); break;
+        default: TS_LAUNCH_PSB(4); break;
+    }
+#undef TS_LAUNCH_PSB
+    TS_CHECK_LAUNCH("ts_project_sh_bwd");
     return TS_OK;
 }
 

@@ -14,6 +14,7 @@ the read happens after the blend kernel has been queued (tinysplat_b200/binning.
 """
 from __future__ import annotations
 
+import os
 import weakref
 from typing import Tuple
 
@@ -28,6 +29,9 @@ from . import rasterize as _rz
 BLOCK = 16
 _side_streams = {}
 USE_SIDE_STREAM = True     # SH kernels on a second stream, overlapping binning / projection-backward
+# single-GPU backward tail: projection-backward and SH-backward as ONE kernel (ts_project_sh_bwd) instead of
+# two kernels on two streams.  TINYSPLAT_B200_FUSED_TAIL=0 selects the two-kernel form (A/B).
+FUSED_TAIL = os.environ.get("TINYSPLAT_B200_FUSED_TAIL", "1") != "0"
 last_bins = None           # (tile_offsets, ids_sorted, M) of the most recent fused forward
 
 
@@ -198,23 +202,31 @@ class _RenderFused(Function):
         seg = lambda i, *shape: flat[offs[i]:offs[i] + sizes[i]].view(*shape)
         v_rest, v_dc = seg(0, N, K - 1, 3), seg(1, N, 1, 3)
         v_means, v_scales, v_quats, v_logit = seg(2, N, 3), seg(3, N, 3), seg(4, N, 4), seg(5, N)
-        # SH-backward (DRAM-bound) on the side stream, concurrent with projection-backward
-        # (issue-bound); both only read the packed gradients
-        main = torch.cuda.current_stream(dev)
-        side = _side_stream(dev) if USE_SIDE_STREAM else main
-        if side is not main:
-            side.wait_stream(main)
-        with torch.cuda.stream(side):
-            _lib.call("ts_sh_bwd", N, deg, K, _lib.ptr(means_c), _lib.ptr(view_c), grads.data_ptr() + 32, 12,
-                      _lib.ptr(mask), _lib.ptr(v_dc), _lib.ptr(v_rest), sflags, side.cuda_stream)
         v_xys = torch.empty(N, 2, **f32)
-        _lib.call("ts_project_bwd", N, _lib.ptr(means_c), _lib.ptr(scales_c), 1.0, _lib.ptr(quats_c),
-                  _lib.ptr(view_c), _lib.ptr(proj_c), fx, fy, W / 2, H / 2, H, W,
-                  pflags | _lib.PROJ_DEPTH_CH3, _lib.ptr(radii), None, None, None, _lib.ptr(grads),
-                  _lib.ptr(logit_c), _lib.ptr(v_means), _lib.ptr(v_scales), _lib.ptr(v_quats),
-                  _lib.ptr(v_logit), _lib.ptr(v_xys), st)
-        if side is not main:
-            main.wait_stream(side)
+        if FUSED_TAIL:
+            # K6 + K7 in one launch: the SH rows leave as TMA bulk stores while the CTA runs the EWA algebra
+            _lib.call("ts_project_sh_bwd", N, deg, K, _lib.ptr(means_c), _lib.ptr(scales_c), 1.0, _lib.ptr(quats_c),
+                      _lib.ptr(view_c), _lib.ptr(proj_c), fx, fy, W / 2, H / 2, H, W, pflags | _lib.PROJ_DEPTH_CH3,
+                      _lib.ptr(radii), _lib.ptr(grads), _lib.ptr(logit_c), _lib.ptr(mask), _lib.ptr(v_means),
+                      _lib.ptr(v_scales), _lib.ptr(v_quats), _lib.ptr(v_logit), _lib.ptr(v_xys), _lib.ptr(v_dc),
+                      _lib.ptr(v_rest), st)
+        else:
+            # SH-backward (DRAM-bound) on the side stream, concurrent with projection-backward
+            # (issue-bound); both only read the packed gradients
+            main = torch.cuda.current_stream(dev)
+            side = _side_stream(dev) if USE_SIDE_STREAM else main
+            if side is not main:
+                side.wait_stream(main)
+            with torch.cuda.stream(side):
+                _lib.call("ts_sh_bwd", N, deg, K, _lib.ptr(means_c), _lib.ptr(view_c), grads.data_ptr() + 32, 12,
+                          _lib.ptr(mask), _lib.ptr(v_dc), _lib.ptr(v_rest), sflags, side.cuda_stream)
+            _lib.call("ts_project_bwd", N, _lib.ptr(means_c), _lib.ptr(scales_c), 1.0, _lib.ptr(quats_c),
+                      _lib.ptr(view_c), _lib.ptr(proj_c), fx, fy, W / 2, H / 2, H, W,
+                      pflags | _lib.PROJ_DEPTH_CH3, _lib.ptr(radii), None, None, None, _lib.ptr(grads),
+                      _lib.ptr(logit_c), _lib.ptr(v_means), _lib.ptr(v_scales), _lib.ptr(v_quats),
+                      _lib.ptr(v_logit), _lib.ptr(v_xys), st)
+            if side is not main:
+                main.wait_stream(side)
         if ctx.sink is not None:
             ctx.sink.deliver(v_xys)
         return (v_means, v_scales, v_quats, v_logit.reshape(opac_shape), v_dc.reshape(dc_shape), v_rest,

@@ -35,7 +35,11 @@ class GradientAllReducer:
     Launch happens from the post-accumulate-grad hook of the LAST parameter to receive its
     gradient, i.e. as early as autograd allows.  Gradients that are views of one flat buffer
     (the fused node allocates them that way) are reduced with a single collective over the
-    buffer's span; anything else falls back to one collective per tensor."""
+    buffer's span; anything else falls back to one collective per tensor.
+
+    Contract: exactly ONE backward per finish().  A second backward before finish() (gradient
+    accumulation, retain_graph) would add into gradients that are already being reduced — it raises
+    instead.  A parameter that receives no gradient in a step simply leaves the launch to finish()."""
 
     def __init__(self, params: Iterable[Tensor], process_group=None, average: bool = True,
                  overlap: bool = True):
@@ -60,6 +64,9 @@ class GradientAllReducer:
         return dist.get_world_size(self.group) if self._enabled else 1
 
     def _hook(self, p: Tensor) -> None:
+        if self._launched:
+            raise RuntimeError("GradientAllReducer: a gradient arrived while the all-reduce of this step is in "
+                               "flight — call finish() after every backward (one backward per finish())")
         self._ready += 1
         if self._ready == len(self.params):
             self._launch()
