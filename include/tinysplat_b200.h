@@ -46,7 +46,9 @@ enum ts_flags {
     TS_SH_DIRS_FROM_MEANS = 1,/* `dirs` holds means3d; dir = mean - viewmat[:3,3] */
     TS_SH_OFFSET_CLAMP = 2,   /* colour = max(sh + 0.5, 0); mask of passing channels saved */
     TS_BIN_OPACITY_LOGIT = 1, /* `opacity` holds logits: sigmoid() inside */
-    TS_BIN_PACK_ONLY = 2      /* ts_bin_count: only pack the records (the caller reuses tile lists it already has) */
+    TS_BIN_PACK_ONLY = 2,     /* ts_bin_count: only pack the records (the caller reuses tile lists it already has) */
+    TS_BLEND_GRADS_ZEROED = 2 /* ts_blend_bwd, or-ed into split_ch3: the caller has already zeroed `grads` (e.g. on an
+                                 idle stream during the forward pass); the callee then skips its memset */
 };
 
 /* Library version (major*10000 + minor*100 + patch) and last CUDA error text. */
@@ -191,7 +193,8 @@ TS_API int ts_bin_smem_sort_cap(void);
  *   in; the clamped-channel mask rides in bits 28..30 of n_contrib and zeroes those
  *   cotangents in backward.
  * ts_blend_bwd: replays back to front; accumulates per-Gaussian packed gradients
- *   grads[N, ts_grad_floats()] (zeroed by the callee).  v_out_alpha may be NULL.
+ *   grads[N, ts_grad_floats()] (zeroed by the callee unless split_ch3 carries TS_BLEND_GRADS_ZEROED).
+ *   v_out_alpha may be NULL.
  * ts_blend_unpack_grads: packed -> v_xys[N,2], v_conics[N,3], v_colors[N,CH], v_opacity[N].
  * tile_order (both blend calls): ts_bin_tile_order's permutation — CTA i works on tile
  *   tile_order[i], longest lists first, so the grid's tail is made of cheap tiles; NULL = raster

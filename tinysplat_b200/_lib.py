@@ -84,6 +84,7 @@ PROJ_LOG_SCALES, PROJ_RAW_QUATS, PROJ_DEPTH_CH3, PROJ_OPACITY_LOGIT = 1, 2, 4, 8
 SH_DIRS_FROM_MEANS, SH_OFFSET_CLAMP = 1, 2
 BIN_OPACITY_LOGIT = 1
 BIN_PACK_ONLY = 2
+BLEND_GRADS_ZEROED = 2
 
 _STATUS = {0: "TS_OK", -1: "TS_ERR_INVALID", -2: "TS_ERR_ALIGN", -3: "TS_ERR_CUDA",
            -4: "TS_ERR_CAPACITY"}

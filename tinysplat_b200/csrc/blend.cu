@@ -519,15 +519,18 @@ int ts_blend_fwd(int CH, int img_height, int img_width, int tiles_x, int tiles_y
 int ts_blend_bwd(int N, int CH, int img_height, int img_width, int tiles_x, int tiles_y,
                  const int32_t* tile_offsets, const int32_t* ids_sorted, const float* recs,
                  const float* background, const float* final_T, const int32_t* n_contrib,
-                 const float* v_out_img, const float* v_out_ch3, int split_ch3,
+                 const float* v_out_img, const float* v_out_ch3, int split_ch3_flags,
                  const float* v_out_alpha, float* grads, const int32_t* tile_order, ts_stream_t stream) {
+    const int split_ch3 = split_ch3_flags & 1;
+    const bool prezeroed = (split_ch3_flags & TS_BLEND_GRADS_ZEROED) != 0;
     if (N < 0 || CH < 1 || CH > 4 || img_height <= 0 || img_width <= 0 || tiles_x <= 0 || tiles_y <= 0) return TS_ERR_INVALID;
     if (N == 0) return TS_OK;
     if (!tile_offsets || !background || !final_T || !n_contrib || !grads) return TS_ERR_INVALID;
     if (!v_out_img && !(CH == 4 && split_ch3)) return TS_ERR_INVALID;
     if (!ts::aligned16(grads) || (recs && !ts::aligned16(recs))) return TS_ERR_ALIGN;
     cudaStream_t st = (cudaStream_t)stream;
-    TS_CHECK_CUDA(cudaMemsetAsync(grads, 0, sizeof(float) * ts::kGradFloats * (size_t)N, st), "ts_blend_bwd/memset");
+    if (!prezeroed)
+        TS_CHECK_CUDA(cudaMemsetAsync(grads, 0, sizeof(float) * ts::kGradFloats * (size_t)N, st), "ts_blend_bwd/memset");
     dim3 grid(tiles_x * tiles_y);
     // channels that carry a cotangent: the fused RGB+depth pass without a depth loss skips ch 3
     const int gch = (CH == 4 && split_ch3 && !v_out_ch3) ? 3 : CH;

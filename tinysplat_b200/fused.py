@@ -32,6 +32,8 @@ USE_SIDE_STREAM = True     # SH kernels on a second stream, overlapping binning 
 # single-GPU backward tail: projection-backward and SH-backward as ONE kernel (ts_project_sh_bwd) instead of
 # two kernels on two streams.  TINYSPLAT_B200_FUSED_TAIL=0 selects the two-kernel form (A/B).
 FUSED_TAIL = os.environ.get("TINYSPLAT_B200_FUSED_TAIL", "1") != "0"
+# the packed-gradient buffer of blend-backward is zeroed during forward on the side stream (A/B: =0)
+PREZERO_GRADS = os.environ.get("TINYSPLAT_B200_PREZERO_GRADS", "1") != "0"
 last_bins = None           # (tile_offsets, ids_sorted, M) of the most recent fused forward
 
 
@@ -144,6 +146,15 @@ class _RenderFused(Function):
         ctx.save_for_backward(means_c, scales_c, quats_c, logit_c, view_c, proj_c, bg_c, radii, recs,
                               offsets, ids_sorted, final_T, n_contrib, mask)
         ctx.tile_order = bins.order
+        # blend-backward accumulates into a zeroed [N,12] buffer (48 MB at 1M): zero it NOW on the side
+        # stream, idle while the blend kernel runs, instead of at the head of backward's critical path
+        ctx.prezeroed = None
+        if PREZERO_GRADS and dp is None and side is not main and any(ctx.needs_input_grad[:6]):
+            with torch.cuda.stream(side):
+                buf = torch.zeros(N, lib.ts_grad_floats(), **f32)
+                ev = torch.cuda.Event()
+                ev.record(side)
+            ctx.prezeroed = (buf, ev)
         ctx.meta = (N, K, W, H, tx, ty, float(fx), float(fy), int(sh_degree), pflags, sflags,
                     tuple(opac_logits.shape), tuple(colors_dc.shape))
         ctx.sink = sink
@@ -176,13 +187,20 @@ class _RenderFused(Function):
         if dp is not None and not peer:
             Ns = dp.shard_rows(N)
             n_rows = dp.world * Ns                 # padded so that the all-to-all splits evenly
+        split = 1
         if dp is not None and not peer:
             # persistent, zero-initialised: blend-backward clears rows [0, N), the pad stays zero
             grads = dp.buffer("send", (n_rows, lib.ts_grad_floats()), torch.float32, dev, zero=True, tag=N)
+        elif getattr(ctx, "prezeroed", None) is not None:
+            grads, zeroed = ctx.prezeroed          # zeroed during forward on the side stream
+            ctx.prezeroed = None                   # (a second backward of a retained graph allocates its own)
+            torch.cuda.current_stream(dev).wait_event(zeroed)
+            grads.record_stream(torch.cuda.current_stream(dev))
+            split |= _lib.BLEND_GRADS_ZEROED
         else:
             grads = torch.empty(n_rows, lib.ts_grad_floats(), **f32)
         _lib.call("ts_blend_bwd", N, 4, H, W, tx, ty, _lib.ptr(offsets), _lib.ptr(ids_sorted), _lib.ptr(recs),
-                  _lib.ptr(bg_c), _lib.ptr(final_T), _lib.ptr(n_contrib), _lib.ptr(v_rgb), _lib.ptr(v_depth), 1,
+                  _lib.ptr(bg_c), _lib.ptr(final_T), _lib.ptr(n_contrib), _lib.ptr(v_rgb), _lib.ptr(v_depth), split,
                   _lib.ptr(v_alpha), _lib.ptr(grads), _lib.ptr(ctx.tile_order), st)
         if peer:
             return _RenderFused._backward_peer_exchange(ctx, grads, st)
