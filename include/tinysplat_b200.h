@@ -326,7 +326,7 @@ TS_API int ts_dp_push(int N, int shard_rows, int padded_rows, int world, int ran
                       const uint8_t* clamp_mask /*or NULL*/, const float* recs /*[16B]*/,
                       const float* grads /*[16B]*/, const float* cam_row, void* const* geo_ptrs_host,
                       void* const* rgb_ptrs_host, void* const* cam_ptrs_host, float* v_xys /*or NULL*/,
-                      ts_stream_t stream);
+                      int what /*1 geometry rows + camera + v_xys, 2 colour rows, 3 both*/, ts_stream_t stream);
 TS_API int ts_peer_barrier(int world, int rank, void* const* flag_ptrs_host, int slot, uint32_t epoch,
                            uint32_t* err_flag, double timeout_s, int mode, ts_stream_t stream);
 TS_API int ts_peer_barrier_slots(void);
@@ -338,12 +338,15 @@ TS_API int ts_peer_barrier_slots(void);
  *   side stream  : wait(slot c) + ts_sh_bwd_views_rgb(piece)        — local, HBM-bound
  *   side2 stream : ts_project_bwd_views_peer(my shard of the piece) — stores into every rank
  * so the NVLink transfer of piece c+1 runs under the shard backward of piece c; then a barrier in the
- * last slot and the main stream joins.  peer_bases_host[world]: every rank's allocation;
+ * last slot and the main stream joins.  By default (ts_dp_exchange_split) the geometry rows of a piece
+ * are pushed and signalled before its colour rows (two slots per piece): the shard projection-backward,
+ * which needs only the geometry, runs under the three times larger colour transfer.  peer_bases_host[world]: every rank's allocation;
  * seg_offsets_host[11]: byte offsets of the segments {flags, err, cams, geo, rgb, g_rest, g_dc, g_means,
  * g_scales, g_quats, g_logit} inside an allocation (tinysplat_b200/parallel.py PeerLayout).  The host
  * side is pure launch logic; issuing it from native code instead of Python keeps it off the critical path. */
 /* Debug timeline of ts_dp_exchange_peer: enable, run, synchronize the device, read "label ms" lines
  * (ms since the start of the last exchange; events recorded between the launches on each stream). */
+TS_API int ts_dp_exchange_split(int mode /*-1 default/env TINYSPLAT_B200_PEER_SPLIT, 0 off, 1 on*/);
 TS_API int ts_dp_exchange_timeline(int enable);
 TS_API int ts_dp_exchange_timeline_read(char* buf, int buf_bytes);
 TS_API int ts_dp_exchange_peer(int N, int K, int degree, int world, int rank, int n_pieces,

@@ -394,13 +394,17 @@ int emu_peer_exchange(int world, int N, int Ns, int K, int deg, int W, int H, co
     // persistent grid: fewer CTAs than 256-row blocks, so that every CTA iterates and reuses both of its buffers
     const int pblocks = (N + ts::kPushRows - 1) / ts::kPushRows;
     const int pgrid = pblocks > 3 ? (pblocks + 2) / 3 : 1;
+    // odd ranks push geometry and colour rows in two passes (what = 1, then 2: the split exchange), even ranks in one
     for (int r = 0; r < world; ++r) {
-        int rc = ts_emu::launch(dim3(pgrid), ts::kPushThreads, [&]() {
-            ts::dp_push_kernel(N, Ns, Npad, world, r, radii_all + (size_t)r * N, mask_all + (size_t)r * N,
-                               (const float4*)(recs_all + (size_t)r * N * 12), (const float4*)(packed_all + (size_t)r * N * 12),
-                               cams_all + (size_t)r * 32, pgeo, prgb, pcams, (float2*)(v_xys_all + (size_t)r * N * 2));
-        });
-        if (rc) return rc;
+        for (int pass = 0; pass < ((r & 1) ? 2 : 1); ++pass) {
+            const int what = (r & 1) ? pass + 1 : 3;
+            int rc = ts_emu::launch(dim3(pgrid), ts::kPushThreads, [&]() {
+                ts::dp_push_kernel(N, Ns, Npad, world, r, radii_all + (size_t)r * N, mask_all + (size_t)r * N,
+                                   (const float4*)(recs_all + (size_t)r * N * 12), (const float4*)(packed_all + (size_t)r * N * 12),
+                                   cams_all + (size_t)r * 32, pgeo, prgb, pcams, (float2*)(v_xys_all + (size_t)r * N * 2), what);
+            });
+            if (rc) return rc;
+        }
     }
     const int flags = TS_PROJ_LOG_SCALES | TS_PROJ_RAW_QUATS;
     for (int r = 0; r < world; ++r) {

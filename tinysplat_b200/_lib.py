@@ -54,7 +54,8 @@ _SIGNATURES = {
     "ts_sh_bwd_views_rgb": ([_i, _i, _i, _i, _p, _p, _p, C.c_int64, _f, _p, _p, _p], C.c_int),
     "ts_project_bwd_views_peer": ([_i, _i, _p, _p, _f, _p, _p, _i, _i, _i, _p, C.c_int64, _p, _f, _i, _i,
                                    _p, _p, _p, _p, _p], C.c_int),
-    "ts_dp_push": ([_i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p], C.c_int),
+    "ts_dp_push": ([_i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _p], C.c_int),
+    "ts_dp_exchange_split": ([_i], C.c_int),
     "ts_peer_barrier": ([_i, _i, _p, _i, C.c_uint32, _p, C.c_double, _i, _p], C.c_int),
     "ts_peer_barrier_slots": ([], C.c_int),
     "ts_dp_exchange_timeline": ([_i], C.c_int),

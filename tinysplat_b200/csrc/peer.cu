@@ -19,6 +19,7 @@
 // 128-bit stores to peer-mapped addresses), ts_peer_barrier (system-scope release/acquire flags in
 // peer memory).  Peer buffers are plain cudaMalloc allocations shared through CUDA IPC handles.
 #include <cstdio>
+#include <cstdlib>
 #include "ts_common.cuh"
 #include "ts_peer.cuh"
 
@@ -38,11 +39,15 @@ __global__ void __launch_bounds__(kPushThreads)
 dp_push_kernel(int N, int Ns, int Npad, int world, int rank, const int32_t* __restrict__ radii,
                const uint8_t* __restrict__ clamp_mask, const float4* __restrict__ recs,
                const float4* __restrict__ grads, const float* __restrict__ cam_row, PeerPtrs geo,
-               PeerPtrs rgb, PeerPtrs cams, float2* __restrict__ v_xys) {
+               PeerPtrs rgb, PeerPtrs cams, float2* __restrict__ v_xys, int what) {
+    // what: bit 0 = geometry rows (+ this view's d loss / d xy and its camera), bit 1 = colour rows.  The
+    // exchange pushes the geometry first and signals it separately: the owners' projection-backward then
+    // runs under the (three times larger) colour transfer (ts_dp_exchange_peer).
+    const bool do_geo = (what & 1) != 0, do_rgb = (what & 2) != 0;
     __shared__ __align__(128) float4 s_geo[2][kPushRows * 2];     // the block's geometry rows, 2 x 8 KB
     __shared__ __align__(128) float s_rgb[2][kPushRows * 3];      // the block's colour rows, 2 x 3 KB
     const int tid = threadIdx.x;
-    if (blockIdx.x == 0) {                          // this view's camera -> every rank's cams[rank]
+    if (blockIdx.x == 0 && do_geo) {                // this view's camera -> every rank's cams[rank]
         for (int idx = tid; idx < kCamRowFloats * world; idx += kPushThreads) {
             const int r = idx / kCamRowFloats, k = idx - r * kCamRowFloats;
             (reinterpret_cast<float*>(cams.p[r]) + (size_t)rank * kCamRowFloats)[k] = __ldg(cam_row + k);
@@ -81,7 +86,7 @@ dp_push_kernel(int N, int Ns, int Npad, int world, int rank, const int32_t* __re
                         if (!(m & 4u)) g2.z = 0.f;
                     }
                 }
-                if (v_xys) {                                // this view's d loss / d xy (densification statistic)
+                if (v_xys && do_geo) {                      // this view's d loss / d xy (densification statistic)
                     float2 v = make_float2(0.f, 0.f);
                     if (live) {
                         const float4 q1 = __ldg(recs + 3 * (size_t)i + 1);   // {.5 log2e a, log2e b, .5 log2e c, opacity}
@@ -106,9 +111,11 @@ dp_push_kernel(int N, int Ns, int Npad, int world, int rank, const int32_t* __re
             fence_proxy_async();        // generic-proxy smem writes -> visible to the copy engine
             __syncthreads();
             if (tid == 0) {
-                float4* gdst = reinterpret_cast<float4*>(geo.p[owner0]) + ((size_t)rank * Ns + (item0 - owner0 * Ns)) * 2;
-                bulk_s2g(gdst, s_geo[buf], kPushRows * 32);
-                for (int d = 0; d < world; ++d) {       // start at the next rank: spreads the links
+                if (do_geo) {
+                    float4* gdst = reinterpret_cast<float4*>(geo.p[owner0]) + ((size_t)rank * Ns + (item0 - owner0 * Ns)) * 2;
+                    bulk_s2g(gdst, s_geo[buf], kPushRows * 32);
+                }
+                for (int d = 0; d < world && do_rgb; ++d) {     // start at the next rank: spreads the links
                     const int r = (rank + 1 + d) % world;
                     bulk_s2g(reinterpret_cast<float*>(rgb.p[r]) + rgb_off, s_rgb[buf], kPushRows * 12);
                 }
@@ -116,14 +123,14 @@ dp_push_kernel(int N, int Ns, int Npad, int world, int rank, const int32_t* __re
             if (tid == 0) bulk_commit();                // one group per iteration (empty groups complete at once)
         } else {
             __syncthreads();
-            for (int t = tid; t < nvalid; t += kPushThreads) {
+            for (int t = tid; t < nvalid && do_geo; t += kPushThreads) {
                 const int i = item0 + t;
                 const int owner = i / Ns, il = i - owner * Ns;
                 float4* dst = reinterpret_cast<float4*>(geo.p[owner]) + ((size_t)rank * Ns + il) * 2;
                 dst[0] = s_geo[buf][2 * t];
                 dst[1] = s_geo[buf][2 * t + 1];
             }
-            const int nfl = nvalid * 3;
+            const int nfl = do_rgb ? nvalid * 3 : 0;
             const int nv4 = nfl >> 2;
             for (int idx = tid; idx < nv4 * world; idx += kPushThreads) {
                 const int d = idx / nv4, k = idx - d * nv4;
@@ -142,6 +149,19 @@ dp_push_kernel(int N, int Ns, int Npad, int world, int rank, const int32_t* __re
     }
     // performed, not just read: the flag signal that follows the kernel publishes them
     if (tid == 0) bulk_wait0();
+}
+
+static int g_exchange_split = -1;
+static bool exchange_split() {
+    if (g_exchange_split < 0) {
+#ifndef TS_HOST_EMU
+        const char* e = getenv("TINYSPLAT_B200_PEER_SPLIT");
+        g_exchange_split = (e && e[0] == '0') ? 0 : 1;
+#else
+        g_exchange_split = 1;
+#endif
+    }
+    return g_exchange_split == 1;
 }
 
 // Flags live one per 128-byte line: flags[slot][source rank][32 words].
@@ -230,7 +250,8 @@ int ts_peer_ipc_close(void* dev_ptr) {
 int ts_dp_push(int N, int shard_rows, int padded_rows, int world, int rank, const int32_t* radii,
                const uint8_t* clamp_mask, const float* recs, const float* grads, const float* cam_row,
                void* const* geo_ptrs_host, void* const* rgb_ptrs_host, void* const* cam_ptrs_host,
-               float* v_xys, ts_stream_t stream) {
+               float* v_xys, int what, ts_stream_t stream) {
+    if (what < 1 || what > 3) return TS_ERR_INVALID;
     if (N < 0 || world < 1 || world > ts::kMaxPeers || rank < 0 || rank >= world || shard_rows <= 0 ||
         (shard_rows % 4) != 0 || padded_rows < N || (padded_rows % 4) != 0 ||
         (int64_t)shard_rows * world < N)
@@ -252,7 +273,7 @@ int ts_dp_push(int N, int shard_rows, int padded_rows, int world, int rank, cons
     const int grid = max(1, min(nblocks, sms * ts::kPushCtasPerSm));               // block 0 always ships the camera
     ts::dp_push_kernel<<<grid, ts::kPushThreads, 0, (cudaStream_t)stream>>>(
         N, shard_rows, padded_rows, world, rank, radii, clamp_mask, (const float4*)recs, (const float4*)grads,
-        cam_row, geo, rgb, cams, (float2*)v_xys);
+        cam_row, geo, rgb, cams, (float2*)v_xys, what);
     TS_CHECK_LAUNCH("ts_dp_push");
     return TS_OK;
 }
@@ -275,6 +296,14 @@ int ts_peer_barrier(int world, int rank, void* const* flag_ptrs_host, int slot, 
 }
 
 int ts_peer_barrier_slots(void) { return ts::kBarrierSlots; }
+
+// -1: TINYSPLAT_B200_PEER_SPLIT environment variable / default (1); 0: one push per piece; 1: geometry and
+// colour rows pushed and signalled separately (see ts_dp_exchange_peer)
+int ts_dp_exchange_split(int mode) {
+    if (mode < -1 || mode > 1) return TS_ERR_INVALID;
+    ts::g_exchange_split = mode;
+    return TS_OK;
+}
 
 // ---- the whole data-parallel backward tail as ONE call --------------------------------------------
 // A three-stream pipeline over row pieces (see the header).  Everything here is host-side launch
@@ -347,8 +376,9 @@ int ts_dp_exchange_peer(int N, int K, int degree, int world, int rank, int n_pie
                         const int64_t* seg_offsets_host, int img_height, int img_width, int proj_flags,
                         float out_scale, uint32_t epoch, double timeout_s, float* v_xys, ts_stream_t main_stream,
                         ts_stream_t side_stream, ts_stream_t side2_stream) {
+    const bool split = ts::exchange_split();
     if (N < 0 || world < 1 || world > ts::kMaxPeers || rank < 0 || rank >= world || n_pieces < 0 ||
-        n_pieces >= ts::kBarrierSlots || !peer_bases_host || !seg_offsets_host || !cam_row || (n_pieces > 0 && !piece_plan_host))
+        (split ? 2 : 1) * n_pieces >= ts::kBarrierSlots || !peer_bases_host || !seg_offsets_host || !cam_row || (n_pieces > 0 && !piece_plan_host))
         return TS_ERR_INVALID;
     enum { SEG_FLAGS, SEG_ERR, SEG_CAMS, SEG_GEO, SEG_RGB, SEG_REST, SEG_DC, SEG_MEANS, SEG_SCALES, SEG_QUATS, SEG_LOGIT };
     cudaStream_t sm = (cudaStream_t)main_stream, s1 = (cudaStream_t)side_stream, s2 = (cudaStream_t)side2_stream;
@@ -377,7 +407,7 @@ int ts_dp_exchange_peer(int N, int K, int degree, int world, int rank, int n_pie
         table(t_geo, SEG_GEO, 0);
         table(t_rgb, SEG_RGB, 0);
         rc = ts_dp_push(0, 4, padded_rows > 0 ? padded_rows : 4 * world, world, rank, nullptr, nullptr, nullptr, nullptr,
-                        cam_row, t_geo, t_rgb, t_cams, nullptr, main_stream);
+                        cam_row, t_geo, t_rgb, t_cams, nullptr, 3, main_stream);
         if (rc != TS_OK) return rc;
     }
     for (int c = 0; c < n_pieces; ++c) {
@@ -387,42 +417,65 @@ int ts_dp_exchange_peer(int N, int K, int degree, int world, int rank, int n_pie
         const int64_t geo_off = (int64_t)world * g0 * 32;
         table(t_geo, SEG_GEO, geo_off);
         table(t_rgb, SEG_RGB, 12 * r0);
-        // main: push the piece, signal; never waits for a peer
-        rc = ts_dp_push((int)n, (int)ns_c, padded_rows, world, rank, radii + r0, clamp_mask ? clamp_mask + r0 : nullptr,
-                        recs + 12 * r0, grads + 12 * r0, cam_row, t_geo, t_rgb, t_cams, v_xys ? v_xys + 2 * r0 : nullptr,
-                        main_stream);
-        if (rc != TS_OK) return rc;
-        tl_mark(sm, "pushed", c);
-        rc = ts_peer_barrier(world, rank, t_flags, c, epoch, err, timeout_s, 1, main_stream);
-        if (rc != TS_OK) return rc;
-        // side: every rank's rows of this piece have landed here -> SH gradient of the piece (local)
-        rc = ts_peer_barrier(world, rank, t_flags, c, epoch, err, timeout_s, 2, side_stream);
-        if (rc != TS_OK) return rc;
-        cudaEvent_t landed = pool_event(dev);
-        TS_CHECK_CUDA(cudaEventRecord(landed, s1), "ts_dp_exchange_peer/event");
-        tl_mark(s1, "landed", c);
-        rc = ts_sh_bwd_views_rgb(world, (int)n, degree, K, means3d + 3 * r0, cams_local,
-                                 (const float*)seg(rank, SEG_RGB, 12 * r0), (int64_t)padded_rows * 3, out_scale,
-                                 (float*)seg(rank, SEG_DC, 12 * r0), (float*)seg(rank, SEG_REST, 4 * (int64_t)R * r0),
-                                 side_stream);
-        if (rc != TS_OK) return rc;
-        tl_mark(s1, "sh_done", c);
-        // side 2: projection-backward over all views for MY shard of the piece, stored into every rank
-        const int64_t s0 = r0 + (int64_t)rank * ns_c;
-        int64_t ns = (int64_t)(rank + 1) * ns_c < n ? ns_c : n - (int64_t)rank * ns_c;
-        if (ns > 0) {
-            if (s2 != s1) TS_CHECK_CUDA(cudaStreamWaitEvent(s2, landed, 0), "ts_dp_exchange_peer/wait");
+        const int64_t s0 = r0 + (int64_t)rank * ns_c;      // my shard of the piece (global rows)
+        const int64_t ns = (int64_t)(rank + 1) * ns_c < n ? ns_c : n - (int64_t)rank * ns_c;
+        auto push = [&](int what) {
+            return ts_dp_push((int)n, (int)ns_c, padded_rows, world, rank, radii + r0, clamp_mask ? clamp_mask + r0 : nullptr,
+                              recs + 12 * r0, grads + 12 * r0, cam_row, t_geo, t_rgb, t_cams,
+                              v_xys ? v_xys + 2 * r0 : nullptr, what, main_stream);
+        };
+        auto shard_projection = [&]() -> int {             // over all views for MY shard, stored into every rank
+            if (ns <= 0) return TS_OK;
             table(t_m, SEG_MEANS, 12 * s0);
             table(t_s, SEG_SCALES, 12 * s0);
             table(t_q, SEG_QUATS, 16 * s0);
             table(t_l, SEG_LOGIT, 4 * s0);
-            rc = ts_project_bwd_views_peer(world, (int)ns, means3d + 3 * s0, scales + 3 * s0, 1.0f, quats + 4 * s0,
-                                           cams_local, img_height, img_width, proj_flags,
-                                           (const float*)seg(rank, SEG_GEO, geo_off), ns_c * 8,
-                                           opacity_logits ? opacity_logits + s0 : nullptr, out_scale, world,
-                                           (rank + 1) % world, t_m, t_s, t_q, t_l, side2_stream);
-            if (rc != TS_OK) return rc;
-            tl_mark(s2, "proj_done", c);
+            int r = ts_project_bwd_views_peer(world, (int)ns, means3d + 3 * s0, scales + 3 * s0, 1.0f, quats + 4 * s0,
+                                              cams_local, img_height, img_width, proj_flags,
+                                              (const float*)seg(rank, SEG_GEO, geo_off), ns_c * 8,
+                                              opacity_logits ? opacity_logits + s0 : nullptr, out_scale, world,
+                                              (rank + 1) % world, t_m, t_s, t_q, t_l, side2_stream);
+            if (r == TS_OK) tl_mark(s2, "proj_done", c);
+            return r;
+        };
+        auto sh_gradient = [&]() -> int {                   // of the piece's Gaussians, from all views' colours (local)
+            int r = ts_sh_bwd_views_rgb(world, (int)n, degree, K, means3d + 3 * r0, cams_local,
+                                        (const float*)seg(rank, SEG_RGB, 12 * r0), (int64_t)padded_rows * 3, out_scale,
+                                        (float*)seg(rank, SEG_DC, 12 * r0), (float*)seg(rank, SEG_REST, 4 * (int64_t)R * r0),
+                                        side_stream);
+            if (r == TS_OK) tl_mark(s1, "sh_done", c);
+            return r;
+        };
+        if (split) {
+            // main: geometry rows (28 of the 112 remote MB per rank at 8 GPUs) first, signalled on their own:
+            // the owners' projection-backward (issue-bound) then runs under the colour transfer
+            const int slot_geo = 2 * c, slot_rgb = 2 * c + 1;
+            if ((rc = push(1)) != TS_OK) return rc;
+            tl_mark(sm, "geo_pushed", c);
+            if ((rc = ts_peer_barrier(world, rank, t_flags, slot_geo, epoch, err, timeout_s, 1, main_stream)) != TS_OK) return rc;
+            if ((rc = push(2)) != TS_OK) return rc;
+            tl_mark(sm, "rgb_pushed", c);
+            if ((rc = ts_peer_barrier(world, rank, t_flags, slot_rgb, epoch, err, timeout_s, 1, main_stream)) != TS_OK) return rc;
+            if ((rc = ts_peer_barrier(world, rank, t_flags, slot_geo, epoch, err, timeout_s, 2, side2_stream)) != TS_OK) return rc;
+            tl_mark(s2, "geo_landed", c);
+            if ((rc = shard_projection()) != TS_OK) return rc;
+            if ((rc = ts_peer_barrier(world, rank, t_flags, slot_rgb, epoch, err, timeout_s, 2, side_stream)) != TS_OK) return rc;
+            tl_mark(s1, "rgb_landed", c);
+            if ((rc = sh_gradient()) != TS_OK) return rc;
+        } else {
+            // main: push the piece, signal; never waits for a peer
+            if ((rc = push(3)) != TS_OK) return rc;
+            tl_mark(sm, "pushed", c);
+            if ((rc = ts_peer_barrier(world, rank, t_flags, c, epoch, err, timeout_s, 1, main_stream)) != TS_OK) return rc;
+            // side: every rank's rows of this piece have landed here -> SH gradient of the piece (local)
+            if ((rc = ts_peer_barrier(world, rank, t_flags, c, epoch, err, timeout_s, 2, side_stream)) != TS_OK) return rc;
+            cudaEvent_t landed = pool_event(dev);
+            TS_CHECK_CUDA(cudaEventRecord(landed, s1), "ts_dp_exchange_peer/event");
+            tl_mark(s1, "landed", c);
+            if ((rc = sh_gradient()) != TS_OK) return rc;
+            // side 2: projection-backward over all views for MY shard of the piece
+            if (ns > 0 && s2 != s1) TS_CHECK_CUDA(cudaStreamWaitEvent(s2, landed, 0), "ts_dp_exchange_peer/wait");
+            if ((rc = shard_projection()) != TS_OK) return rc;
         }
     }
     // every shard's gradients have landed in my segment: final barrier on the side stream, then main joins

@@ -149,7 +149,8 @@ class _RenderFused(Function):
         # blend-backward accumulates into a zeroed [N,12] buffer (48 MB at 1M): zero it NOW on the side
         # stream, idle while the blend kernel runs, instead of at the head of backward's critical path
         ctx.prezeroed = None
-        if PREZERO_GRADS and dp is None and side is not main and any(ctx.needs_input_grad[:6]):
+        if PREZERO_GRADS and (dp is None or getattr(dp, "peer", False)) and side is not main and \
+                any(ctx.needs_input_grad[:6]):
             with torch.cuda.stream(side):
                 buf = torch.zeros(N, lib.ts_grad_floats(), **f32)
                 ev = torch.cuda.Event()

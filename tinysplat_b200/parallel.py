@@ -208,7 +208,7 @@ class PeerLayout:
     so that the six parameter gradients handed to autograd are views of this buffer."""
 
     SHARD_ALIGN = 256          # rows; keeps every shard slice of every tensor 16-byte aligned
-    MAX_CHUNKS = 8             # the rows are pushed in up to this many chunks (one barrier slot each)
+    MAX_CHUNKS = 7             # the rows are pushed in up to this many pieces (two barrier slots each + a final one)
 
     def __init__(self, world: int, cap_rows: int, K: int, flag_bytes: int):
         self.world, self.cap_rows, self.K = world, cap_rows, K
