@@ -148,18 +148,18 @@ class ClockSampler:
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the `ncu --set full` capture of this
 # same command summarised in profiles/r1_ncu_full_all_kernels.txt and, for the blend kernels of the
-# current default (packed grouped backward, list-walking forward, longest-list-first tile order),
-# profiles/r2g_ncu_blend_fwd_bwd.txt (default workload, fused pipeline)
+# final build of round 2, profiles/r2x_ncu_full_all_kernels.txt (default workload, fused pipeline)
 NCU_TRAFFIC_SOURCE = ("constant from one `ncu --set full` capture of this command (profiles/), per launch; "
                       "not re-measured in this run")
 # sm__inst_issued.avg.pct_of_peak_sustained_active of the same capture: the blend kernels' real limiter
-NCU_ISSUE_PCT = {"ts_blend_bwd": 77.7, "ts_blend_fwd": 87.8}
+NCU_ISSUE_PCT = {"ts_blend_bwd": 77.6, "ts_blend_fwd": 87.6}
 NCU_TRAFFIC = {
     "synthetic_1M_1080p": {
-        "ts_blend_bwd": (184.47 + 22.49) * 1e6, "ts_blend_fwd": (62.70 + 19.58) * 1e6,
-        "ts_sh_fwd": (228.81 + 25.18) * 1e6, "ts_sh_bwd": (61.03 + 134.51) * 1e6,
-        "ts_project_fwd": (61.73 + 24.12) * 1e6, "ts_project_bwd": (95.97 + 23.53) * 1e6,
-        "ts_bin_emit": (56.04 + 1.25) * 1e6, "ts_bin_sort": (16.43 + 0.0) * 1e6,
+        "ts_blend_bwd": (187.99 + 24.18) * 1e6, "ts_blend_fwd": (62.85 + 22.86) * 1e6,
+        "ts_sh_fwd": (228.72 + 24.87) * 1e6, "ts_sh_bwd": (61.03 + 134.51) * 1e6,
+        "ts_project_fwd": (62.80 + 23.48) * 1e6, "ts_project_bwd": (95.97 + 23.53) * 1e6,
+        "ts_project_sh_bwd": (97.04 + 186.62) * 1e6,
+        "ts_bin_emit": (56.31 + 1.16) * 1e6, "ts_bin_sort": (16.08 + 0.0) * 1e6,
     }
 }
 
@@ -173,6 +173,8 @@ def algorithmic_bytes(name: str, N: int, M: int, P: int, CH: int, K: int, nb: in
         "ts_project_bwd": 108 * N,                     # 68 in, 40 out
         "ts_sh_fwd": (24 + 12 * nb) * N,
         "ts_sh_bwd": (24 + 12 * K) * N,
+        # K6 + K7 in one kernel: 97 in (means, scales, quats, radii, packed row, logit, mask) + 52 + 12 K out
+        "ts_project_sh_bwd": (97 + 52 + 12 * K) * N,
         "ts_bin_count": (76 + 4 * CH) * N + 4 * M,     # pack 48 B record + count atomics
         "ts_bin_scan": 8 * (P // 256),
         "ts_bin_emit": 24 * N + 12 * M,
@@ -710,10 +712,10 @@ def run_ours(args):
                 "traffic_source": NCU_TRAFFIC_SOURCE if traffic else None,
                 "note": "blend kernels are fp32-issue/atomic bound, not HBM bound (DESIGN.md); "
                         "streaming kernels listed in `kernels`",
-                # what does bound it (one `ncu --set full` capture of this command, profiles/r2g_ncu_blend_fwd_bwd.txt)
+                # what does bound it (one `ncu --set full` capture of this command, profiles/r2x_ncu_full_all_kernels.txt)
                 "issue_slots_busy_pct_ncu": NCU_ISSUE_PCT.get(top) if args.pipeline == "fused" else None}
     # the best streaming (genuinely HBM-bound) kernel, for a roofline fraction that means something
-    stream_names = [k for k in ("ts_sh_bwd", "ts_sh_fwd", "ts_project_bwd", "ts_project_fwd") if k in kern]
+    stream_names = [k for k in ("ts_sh_bwd", "ts_sh_fwd", "ts_project_sh_bwd", "ts_project_bwd", "ts_project_fwd") if k in kern]
     best_stream = max(stream_names, key=lambda k: kern[k]["gbs"] or 0) if stream_names else None
     roof_stream = None
     if best_stream:
