@@ -3,7 +3,7 @@ count  [behind gsplat.rasterize_gaussians, REF tinysplat/splatting/rasterize.py:
 
 The number of (tile, Gaussian) pairs M is only known on the device after the scan, and the key / id
 buffers have to be sized on the host.  Round 1 read M back and stalled the host in the middle of every
-forward pass.  Now the buffers are sized from what earlier calls needed (+25 %), emit / sort / blend
+forward pass.  Now the buffers are sized from what earlier calls needed (+50 %), emit / sort / blend
 are launched immediately with that capacity — the kernels never write or read past it — and the three
 integers (M, longest list, oversized tiles) are read AFTER the blend kernel has been queued: by then
 the copy has long finished, so the host does not drain the GPU, and the GPU always has a few hundred
@@ -27,7 +27,8 @@ stats = {"speculative": 0, "exact_first": 0, "redone": 0}      # counters (tests
 
 # A/B switch (bench only): TINYSPLAT_B200_TILE_ORDER=0 launches the blend kernels in raster order
 USE_TILE_ORDER = os.environ.get("TINYSPLAT_B200_TILE_ORDER", "1") != "0"
-HEADROOM = 1.25
+HEADROOM = 1.5          # key / id buffers: memory only (12 B per pair), a too-small guess costs a repeated pass
+LIST_HEADROOM = 1.25    # longest-list bound: decides which sort size classes are launched, so kept tight
 SLACK = 4096
 
 
@@ -67,7 +68,7 @@ class PendingBins:
         cap_used, bound_used = self.capacity
         st = _state.setdefault(self._key, [0, 0, 0])
         st[0] = max(st[0], int(M * HEADROOM) + SLACK)
-        st[1] = max(st[1], int(max_count * HEADROOM) + 1)
+        st[1] = max(st[1], int(max_count * LIST_HEADROOM) + 1)
         st[2] = n_big
         if M <= cap_used and max_count <= bound_used and n_big == 0:
             return False
@@ -149,7 +150,7 @@ def emit_and_sort(N: int, T: int, tx: int, ty: int, cull_mode: int, depths: Tens
         bins.capacity, bins.cap_arg = (M, max_count), 0
         launch(bins, M, max_count, n_big, True)
         prev = st or [0, 0, 0]
-        _state[key] = [max(prev[0], int(M * HEADROOM) + SLACK), max(prev[1], int(max_count * HEADROOM) + 1), n_big]
+        _state[key] = [max(prev[0], int(M * HEADROOM) + SLACK), max(prev[1], int(max_count * LIST_HEADROOM) + 1), n_big]
         if order_done is not None:
             main.wait_event(order_done)
         return bins
