@@ -305,9 +305,10 @@ class PeerGradExchange:
         # (measured on 2 and 8 B200s: 1, 2 and 4 pieces are within 1 % of each other — profiles/README.md)
         self.n_chunks = int(n_chunks if n_chunks is not None else os.environ.get("TINYSPLAT_B200_PEER_CHUNKS", "1"))
         # geometry rows pushed and signalled before the colour rows (the shard projection-backward runs under
-        # the colour transfer): 8 GPUs 1.3332 vs 1.3357 ms, 2 GPUs 1.145 vs 1.130 ms -> on from 4 ranks up
+        # the colour transfer): 8 GPUs 1.3332 vs 1.3357 ms, 2 GPUs 1.145 vs 1.130 ms (4 GPUs: not measured)
+        # -> on at 8 ranks only
         if "TINYSPLAT_B200_PEER_SPLIT" not in os.environ:
-            _lib.load().ts_dp_exchange_split(1 if self.world >= 4 else 0)
+            _lib.load().ts_dp_exchange_split(1 if self.world >= 8 else 0)
         self.layout: Optional[PeerLayout] = None
         self.device = None
         self._base = None            # my allocation
