@@ -6,7 +6,9 @@ backward kernels; on a B200 the step is then bound by CPU launch overhead, not b
 Here every one of those activations is folded into the sm_100a kernels (flags of the C ABI),
 SH colour is written straight into the packed raster record, RGB and depth share one
 4-channel blend pass, and blend-backward's packed gradients are consumed directly by
-projection-backward and SH-backward.  Forward = 7-8 launches, backward = 3 + one memset.
+projection-backward and SH-backward (one kernel, ts_project_sh_bwd).  Forward = 8 launches (projection +
+pack + count, SH on a side stream, scan, tile order on a side stream, emit, sort, blend; + the zero fill
+of the gradient buffer on the side stream), backward = 2.
 
 The single device->host read (3 ints: intersection count, max list length, oversize tiles) no
 longer stalls the step: emit / sort / blend are launched with buffers sized from earlier steps and
